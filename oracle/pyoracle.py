@@ -1,0 +1,224 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle*.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg,
+never by the hexed_b200 package. Works on `hexed_b200.mesh.FlatMesh` objects in place.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EULER, NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS = range(5)
+
+
+class ho_basis(C.Structure):
+    _fields_ = [("row_size", C.c_int), ("node", C.c_double*8), ("weight", C.c_double*8),
+                ("diff_mat", C.c_double*64), ("boundary", C.c_double*16), ("orthogonal", C.c_double*64),
+                ("filter", C.c_double*64), ("prolong", C.c_double*128), ("restrict_", C.c_double*128),
+                ("min_eig_convection", C.c_double), ("min_eig_diffusion", C.c_double), ("quadratic_safety", C.c_double)]
+
+
+class ho_transport(C.Structure):
+    _fields_ = [("const_val", C.c_double), ("ref_val", C.c_double), ("ref_temp", C.c_double),
+                ("sqrt_ref_temp", C.c_double), ("temp_offset", C.c_double), ("is_viscous", C.c_int)]
+
+
+class ho_options(C.Structure):
+    _fields_ = [("dt", C.c_double), ("i_stage", C.c_int), ("compute_residual", C.c_int), ("use_filter", C.c_int)]
+
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class ho_mesh(C.Structure):
+    _fields_ = [("n_dim", C.c_int), ("row_size", C.c_int), ("n_car", C.c_int), ("n_def", C.c_int), ("n_slot", C.c_int),
+                ("elem_data", dp), ("nom_size", dp), ("vertex_tss", dp), ("uncert", dp), ("ref_normals", dp), ("det", dp),
+                ("n_face_slot", C.c_int), ("face_state", dp), ("face_ldg", dp), ("face_wide", dp),
+                ("n_normal_slot", C.c_int), ("normals", dp),
+                ("n_car_con", C.c_int), ("car_con", ip), ("n_def_con", C.c_int), ("def_con", ip),
+                ("n_ref", C.c_int), ("ref_face", ip)]
+
+
+CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
+
+
+def inviscid():
+    """Transport_model::inviscid() (reference include/Transport_model.hpp:40)"""
+    return ho_transport(0., 0., 1., 1., 1., 0)
+
+
+def constant(value):
+    return ho_transport(value, 0., 1., 1., 1., 1)
+
+
+def sutherland(ref_val, ref_temp, temp_offset):
+    return ho_transport(0., ref_val, ref_temp, float(np.sqrt(ref_temp)), temp_offset, 1)
+
+
+def build(target="liboracle.so", jobs=8):
+    subprocess.run(["make", "-C", HERE, "-j%d" % jobs, target], check=True, stdout=subprocess.DEVNULL)
+
+
+def _fill(dst, src):
+    flat = np.ascontiguousarray(src, dtype=np.float64).ravel()
+    for i, v in enumerate(flat):
+        dst[i] = v
+
+
+def pack_basis(b):
+    rs = b.row_size
+    o = ho_basis()
+    o.row_size = rs
+    _fill(o.node, b.node); _fill(o.weight, b.weight)
+
+    def pad(m):
+        p = np.zeros(m.shape[:-2] + (8, 8)); p[..., :m.shape[-2], :m.shape[-1]] = m
+        return p
+    _fill(o.diff_mat, pad(b.diff_mat)); _fill(o.orthogonal, pad(b.orthogonal)); _fill(o.filter, pad(b.filter))
+    _fill(o.prolong, pad(b.prolong)); _fill(o.restrict_, pad(b.restrict))
+    bd = np.zeros((2, 8)); bd[:, :rs] = b.boundary
+    _fill(o.boundary, bd)
+    o.min_eig_convection = b.min_eig_convection; o.min_eig_diffusion = b.min_eig_diffusion
+    o.quadratic_safety = b.quadratic_safety
+    return o
+
+
+def _ptr(a, typ):
+    if a is None:
+        return C.cast(None, typ)
+    assert a.flags["C_CONTIGUOUS"], "oracle needs contiguous arrays"
+    return a.ctypes.data_as(typ)
+
+
+class Oracle:
+    def __init__(self, lib="liboracle.so", autobuild=True):
+        path = os.path.join(HERE, lib)
+        if not os.path.exists(path) and autobuild:
+            build(lib)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.ho_compute_euler.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options]
+        L.ho_compute_advection.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, C.c_double]
+        L.ho_compute_navier_stokes.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, CALLBACK, C.c_void_p, ho_transport, ho_transport]
+        L.ho_compute_smooth_av.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, CALLBACK, C.c_void_p, C.c_double, C.c_double]
+        L.ho_compute_fix_therm_admis.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, CALLBACK, C.c_void_p]
+        L.ho_max_dt.argtypes = [C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh), C.c_double, C.c_double, C.c_int, ho_transport, ho_transport, C.c_double, dp]
+        L.ho_compute_write_face.argtypes = [C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh)]
+        L.ho_compute_prolong.argtypes = [C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh), C.c_int, C.c_int]
+        L.ho_compute_restrict.argtypes = [C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh), C.c_int, C.c_int]
+        L.ho_face_permutation.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int, dp]
+        L.ho_stabilizing_art_visc.argtypes = [C.POINTER(ho_basis), C.POINTER(ho_mesh), C.c_double]
+        L.ho_neighbor.argtypes = [C.c_int, C.c_int, C.POINTER(ho_mesh), C.c_int, ho_transport, ho_transport, C.c_double, C.c_double]
+        L.ho_local.argtypes = [C.c_int, C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, ho_transport, ho_transport, C.c_double, C.c_double]
+        L.ho_neighbor_reconcile.argtypes = [C.c_int, C.c_int, C.POINTER(ho_mesh)]
+        L.ho_reconcile_ldg_flux.argtypes = [C.c_int, C.c_int, C.POINTER(ho_basis), C.POINTER(ho_mesh), ho_options, ho_transport, ho_transport, C.c_double, C.c_double]
+        L.ho_derivative.argtypes = [C.POINTER(ho_basis), C.c_int, dp, dp, dp]
+        L.ho_bc_freestream.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, dp]
+        L.ho_bc_copy.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip]
+        L.ho_bc_nonpenetration.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip, ip]
+
+    @staticmethod
+    def _check(rc):
+        if rc == 1:
+            raise RuntimeError("demand for invalid kernel")
+        if rc:
+            raise RuntimeError("oracle error %d" % rc)
+
+    def num_threads(self):
+        return self.lib.ho_num_threads()
+
+    @staticmethod
+    def pack_mesh(m):
+        """m: FlatMesh with numpy arrays. The returned struct borrows the arrays (keep `m` alive)."""
+        o = ho_mesh()
+        o.n_dim, o.row_size, o.n_car, o.n_def, o.n_slot = m.n_dim, m.row_size, m.n_car, m.n_def, m.n_slot
+        o.elem_data = _ptr(m.elem_data, dp); o.nom_size = _ptr(m.nom_size, dp); o.vertex_tss = _ptr(m.vertex_tss, dp)
+        o.uncert = _ptr(m.uncert, dp); o.ref_normals = _ptr(m.ref_normals, dp); o.det = _ptr(m.det, dp)
+        o.n_face_slot = m.n_face_slot
+        o.face_state = _ptr(m.face_state, dp); o.face_ldg = _ptr(m.face_ldg, dp); o.face_wide = _ptr(m.face_wide, dp)
+        o.n_normal_slot = m.n_normal_slot; o.normals = _ptr(m.normals, dp)
+        o.n_car_con = m.car_con.shape[0]; o.car_con = _ptr(m.car_con, ip)
+        o.n_def_con = m.def_con.shape[0]; o.def_con = _ptr(m.def_con, ip)
+        o.n_ref = m.ref_face.shape[0]; o.ref_face = _ptr(m.ref_face, ip)
+        return o
+
+    @staticmethod
+    def opts(dt=1., i_stage=0, compute_residual=False, use_filter=False):
+        return ho_options(dt, int(i_stage), int(compute_residual), int(use_filter))
+
+    # ---- mirrors of the reference's kernels.hpp entry points ----
+    def compute_euler(self, basis, m, **kw):
+        self._check(self.lib.ho_compute_euler(pack_basis(basis), self.pack_mesh(m), self.opts(**kw)))
+
+    def compute_advection(self, basis, m, advect_length, **kw):
+        self._check(self.lib.ho_compute_advection(pack_basis(basis), self.pack_mesh(m), self.opts(**kw), advect_length))
+
+    def _cb(self, flux_bc):
+        return CALLBACK((lambda _: flux_bc()) if flux_bc else (lambda _: None))
+
+    def compute_navier_stokes(self, basis, m, flux_bc, visc, therm_cond, **kw):
+        self._check(self.lib.ho_compute_navier_stokes(pack_basis(basis), self.pack_mesh(m), self.opts(**kw), self._cb(flux_bc), None, visc, therm_cond))
+
+    def compute_smooth_av(self, basis, m, flux_bc, diff_time, cheby_step, **kw):
+        self._check(self.lib.ho_compute_smooth_av(pack_basis(basis), self.pack_mesh(m), self.opts(**kw), self._cb(flux_bc), None, diff_time, cheby_step))
+
+    def compute_fix_therm_admis(self, basis, m, flux_bc, **kw):
+        self._check(self.lib.ho_compute_fix_therm_admis(pack_basis(basis), self.pack_mesh(m), self.opts(**kw), self._cb(flux_bc), None))
+
+    def max_dt(self, pde, basis, m, safety_conv, safety_diff, local_time, visc=None, therm_cond=None, advect_length=1.):
+        out = C.c_double(0.)
+        self._check(self.lib.ho_max_dt(pde, pack_basis(basis), self.pack_mesh(m), safety_conv, safety_diff, int(local_time),
+                                      visc or inviscid(), therm_cond or inviscid(), advect_length, C.byref(out)))
+        return out.value
+
+    def compute_write_face(self, basis, m, pde=EULER):
+        self._check(self.lib.ho_compute_write_face(pde, pack_basis(basis), self.pack_mesh(m)))
+
+    def compute_prolong(self, basis, m, scale=False, offset=False, pde=EULER):
+        self._check(self.lib.ho_compute_prolong(pde, pack_basis(basis), self.pack_mesh(m), int(scale), int(offset)))
+
+    def compute_restrict(self, basis, m, scale=True, offset=False, pde=EULER):
+        self._check(self.lib.ho_compute_restrict(pde, pack_basis(basis), self.pack_mesh(m), int(scale), int(offset)))
+
+    def face_permutation(self, n_dim, row_size, n_var, direction, data, restore=False):
+        d = (C.c_int*4)(*direction.as_list())
+        self._check(self.lib.ho_face_permutation(n_dim, row_size, n_var, d, int(restore), _ptr(data, dp)))
+
+    def stabilizing_art_visc(self, basis, m, char_speed):
+        self._check(self.lib.ho_stabilizing_art_visc(pack_basis(basis), self.pack_mesh(m), char_speed))
+
+    def neighbor(self, pde, deformed, m, i_stage=0, visc=None, therm_cond=None, p0=1., p1=1.):
+        self._check(self.lib.ho_neighbor(pde, int(deformed), self.pack_mesh(m), i_stage, visc or inviscid(), therm_cond or inviscid(), p0, p1))
+
+    def local(self, pde, deformed, basis, m, visc=None, therm_cond=None, p0=1., p1=1., **kw):
+        self._check(self.lib.ho_local(pde, int(deformed), pack_basis(basis), self.pack_mesh(m), self.opts(**kw), visc or inviscid(), therm_cond or inviscid(), p0, p1))
+
+    def neighbor_reconcile(self, pde, deformed, m):
+        self._check(self.lib.ho_neighbor_reconcile(pde, int(deformed), self.pack_mesh(m)))
+
+    def reconcile_ldg_flux(self, pde, deformed, basis, m, visc=None, therm_cond=None, p0=1., p1=1., **kw):
+        self._check(self.lib.ho_reconcile_ldg_flux(pde, int(deformed), pack_basis(basis), self.pack_mesh(m), self.opts(**kw), visc or inviscid(), therm_cond or inviscid(), p0, p1))
+
+    def derivative(self, basis, qpoint_vals, boundary_vals):
+        q = np.ascontiguousarray(qpoint_vals, dtype=np.float64)
+        bv = np.ascontiguousarray(boundary_vals, dtype=np.float64)
+        out = np.zeros_like(q)
+        self._check(self.lib.ho_derivative(pack_basis(basis), q.shape[0], _ptr(q, dp), _ptr(bv, dp), _ptr(out, dp)))
+        return out
+
+    def apply_state_bcs(self, m):
+        """ghost-state fill for the device-capable boundary conditions (reference src/Solver.cpp:56-67)"""
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION
+        pm = self.pack_mesh(m)
+        for bc in m.bcs:
+            n = bc["ghost_slot"].size
+            if bc["kind"] == BC_FREESTREAM:
+                fs = np.ascontiguousarray(bc["params"], dtype=np.float64)
+                self.lib.ho_bc_freestream(pm, n, _ptr(bc["ghost_slot"], ip), _ptr(fs, dp))
+            elif bc["kind"] == BC_COPY:
+                self.lib.ho_bc_copy(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip))
+            elif bc["kind"] == BC_NONPENETRATION:
+                self.lib.ho_bc_nonpenetration(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip), _ptr(bc["normal_slot"], ip))
