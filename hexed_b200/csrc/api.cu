@@ -1,0 +1,483 @@
+/* api.cu -- C ABI (include/hexed_b200.h): context life cycle, device mirror of the flattened mesh, transfers and the
+ * stage drivers that sequence the kernels exactly like the reference's macros
+ * (src/kernels_convective.cpp:8-16, src/kernels_max_dt.cpp:8-12). */
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace hb {
+
+static std::string g_create_error;
+
+int fail(hexed_b200_ctx* c, int code, const std::string& msg)
+{
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int check(hexed_b200_ctx* c, cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return 0;
+  return fail(c, HEXED_B200_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class T>
+static int dev_alloc(hexed_b200_ctx* c, T** p, size_t n, bool zero = true)
+{
+  *p = nullptr;
+  if (!n) n = 1;
+  HB_CUDA(c, cudaMalloc(p, sizeof(T)*n));
+  if (zero) HB_CUDA(c, cudaMemsetAsync(*p, 0, sizeof(T)*n, c->stream));
+  return 0;
+}
+
+template <class T> static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static void free_mesh(hexed_b200_ctx* c)
+{
+  dev_free(c->state); dev_free(c->tss); dev_free(c->cache); dev_free(c->av); dev_free(c->forcing); dev_free(c->adv);
+  dev_free(c->nom); dev_free(c->vtss); dev_free(c->uncert); dev_free(c->refn); dev_free(c->det);
+  dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
+  dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face);
+  for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
+  c->lists.clear();
+  for (auto& b : c->bcs) { dev_free(b.inside); dev_free(b.ghost); dev_free(b.normal); dev_free(b.params); }
+  c->bcs.clear();
+  c->have_mesh = false;
+}
+
+/* match_faces index table for one direction: matched[p] = original[table[p]]; transpose, then flip
+ * (reference include/Spatial.hpp:85-129, include/Kernel_connection.hpp:22-36) */
+static void build_perm(int nd, int rs, int d0, int d1, int s0, int s1, int* table)
+{
+  const int nfq = ipow(rs, nd - 1);
+  const bool flip_n0 = (s0 == 0), flip_n1 = (s1 == 1);
+  const bool flip_tang = (d0 != d1) && (flip_n0 == flip_n1);
+  const bool transpose = (d0 == 0 && d1 == 2) || (d0 == 2 && d1 == 0);
+  for (int p = 0; p < nfq; ++p) table[p] = p;
+  if (nd == 3) {
+    std::vector<int> cur(table, table + nfq), next(nfq);
+    if (transpose) {
+      for (int a = 0; a < rs; ++a) for (int b = 0; b < rs; ++b) next[a*rs + b] = cur[b*rs + a];
+      cur = next;
+    }
+    if (flip_tang) {
+      // Eigen colwise().reverse() on the column-major map == reversal of the fastest face index
+      const bool fast = (d0 > 3 - d0 - d1) != transpose;
+      for (int a = 0; a < rs; ++a) for (int b = 0; b < rs; ++b) next[a*rs + b] = fast ? cur[a*rs + (rs - 1 - b)] : cur[(rs - 1 - a)*rs + b];
+      cur = next;
+    }
+    for (int p = 0; p < nfq; ++p) table[p] = cur[p];
+  } else if (nd == 2) {
+    if (flip_tang) for (int p = 0; p < nfq; ++p) table[p] = nfq - 1 - p;
+  }
+}
+
+static int slot_array(hexed_b200_ctx* c, int slot, double** base, size_t* elem_stride, bool alloc)
+{
+  // maps a reference element slot to (device array base of that slot for element 0, stride in doubles)
+  const int nv = c->nv, nq = c->nq, rs = c->rs;
+  const size_t ne = c->n_elem;
+  auto lazy = [&](double** arr, size_t per_elem) -> int {
+    if (!*arr) { if (!alloc) { *base = nullptr; return 0; } int rc = dev_alloc(c, arr, ne*per_elem); if (rc) return rc; }
+    return 0;
+  };
+  int rc = 0;
+  if (slot < nv) { *base = c->state + (size_t)slot*nq; *elem_stride = (size_t)nv*nq; }
+  else if (slot == nv) { *base = c->tss; *elem_stride = nq; }
+  else if (slot < nv + 3) { rc = lazy(&c->av, 2*(size_t)nq); *base = c->av ? c->av + (size_t)(slot - nv - 1)*nq : nullptr; *elem_stride = 2*(size_t)nq; }
+  else if (slot < nv + 7) { rc = lazy(&c->forcing, 4*(size_t)nq); *base = c->forcing ? c->forcing + (size_t)(slot - nv - 3)*nq : nullptr; *elem_stride = 4*(size_t)nq; }
+  else if (slot < nv + 7 + rs) { rc = lazy(&c->adv, (size_t)rs*nq); *base = c->adv ? c->adv + (size_t)(slot - nv - 7)*nq : nullptr; *elem_stride = (size_t)rs*nq; }
+  else {
+    const int k = slot - (nv + 7 + rs);
+    if (k >= nv) { *base = nullptr; *elem_stride = 0; return 0; } // cache slots beyond nv are only used by pde::Advection (not mirrored yet)
+    *base = c->cache + (size_t)k*nq; *elem_stride = (size_t)nv*nq;
+  }
+  return rc;
+}
+
+} // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hexed_b200_device_count(int* count)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  *count = (e == cudaSuccess) ? n : 0;
+  return 0;
+}
+
+const char* hexed_b200_last_error(const hexed_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size, const double* basis, int n_basis)
+{
+  *out = nullptr;
+  if (n_dim < 1 || n_dim > 3 || row_size < 2 || row_size > MAX_RS) return fail(nullptr, HEXED_B200_INVALID_KERNEL, "demand for invalid kernel");
+  const int rs = row_size;
+  const int expect = 2*rs + 3*rs*rs + 2*rs + 4*rs*rs + 3;
+  if (n_basis != expect) return fail(nullptr, HEXED_B200_BAD_ARGUMENT, "basis table has the wrong length");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device || device < 0)
+    return fail(nullptr, HEXED_B200_NO_DEVICE, "no CUDA device available: hexed_b200 has no CPU fallback");
+  hexed_b200_ctx* c = new hexed_b200_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(nullptr, HEXED_B200_NO_DEVICE, "cudaSetDevice failed"); }
+  c->nd = n_dim; c->rs = rs; c->nq = ipow(rs, n_dim); c->nfq = c->nq/rs; c->nv = n_dim + 2; c->n_vert = ipow(2, n_dim);
+  const double* p = basis;
+  double diff[MAX_RS][MAX_RS] = {}, bnd[2][MAX_RS] = {};
+  std::memset(&c->ops, 0, sizeof(c->ops)); std::memset(&c->filt, 0, sizeof(c->filt)); std::memset(&c->transfer, 0, sizeof(c->transfer));
+  for (int i = 0; i < rs; ++i) c->ops.node[i] = *p++;
+  for (int i = 0; i < rs; ++i) c->weight[i] = *p++;
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) diff[i][j] = *p++;
+  for (int s = 0; s < 2; ++s) for (int j = 0; j < rs; ++j) bnd[s][j] = *p++;
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->orthogonal[i][j] = *p++;
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->filt.filter[i][j] = *p++;
+  for (int h = 0; h < 2; ++h) for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->transfer.prolong[h][i][j] = *p++;
+  for (int h = 0; h < 2; ++h) for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->transfer.restrict_[h][i][j] = *p++;
+  c->min_eig_conv = *p++; c->min_eig_diff = *p++; c->quad_safety = *p++;
+  for (int i = 0; i < rs; ++i) {
+    // lift = diag(1/w) boundary^T diag(-1, +1)   (reference include/Derivative.hpp:20-29)
+    const double inv_w = 1./c->weight[i];
+    c->ops.lift[i][0] = inv_w*bnd[0][i]*-1.;
+    c->ops.lift[i][1] = inv_w*bnd[1][i]*1.;
+    for (int j = 0; j < rs; ++j) {
+      c->ops.diff[i][j] = diff[i][j];
+      c->ops.bnd[0][j] = bnd[0][j]; c->ops.bnd[1][j] = bnd[1][j];
+    }
+  }
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j)
+    c->ops.dfull[i][j] = diff[i][j] - (c->ops.lift[i][0]*bnd[0][j] + c->ops.lift[i][1]*bnd[1][j]);
+  static const char* names[ST_COUNT] = {"neighbor", "neighbor", "local", "local", "compute time step", "compute time step",
+                                        "prolong/restrict", "boundary conditions", "write face"};
+  static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2};
+  for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].name = names[i]; c->stats[i].deformed = trees[i]; }
+  int rc = check(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
+  if (!rc) rc = check(c, cudaEventCreate(&c->ev1), "cudaEventCreate");
+  if (!rc) rc = dev_alloc(c, &c->d_scalar, 8);
+  if (!rc) rc = check(c, cudaMallocHost(&c->h_scalar, sizeof(double)*8), "cudaMallocHost");
+  // permutation tables for all 36 direction codes
+  c->h_perm.assign((size_t)36*c->nfq, 0);
+  for (int d0 = 0; d0 < 3; ++d0) for (int d1 = 0; d1 < 3; ++d1) for (int s0 = 0; s0 < 2; ++s0) for (int s1 = 0; s1 < 2; ++s1) {
+    int* t = c->h_perm.data() + (size_t)dir_code(d0, d1, s0, s1)*c->nfq;
+    if (d0 < n_dim && d1 < n_dim) build_perm(n_dim, rs, d0, d1, s0, s1, t);
+    else for (int q = 0; q < c->nfq; ++q) t[q] = q;
+  }
+  if (!rc) rc = dev_alloc(c, &c->perm, c->h_perm.size(), false);
+  if (!rc) rc = check(c, cudaMemcpyAsync(c->perm, c->h_perm.data(), sizeof(int)*c->h_perm.size(), cudaMemcpyHostToDevice, c->stream), "upload perm");
+  if (!rc) rc = dev_alloc(c, &c->d_face_scratch, 2*(size_t)(c->nd + c->rs)*c->nfq);
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "create sync");
+  if (rc) { g_create_error = c->err; hexed_b200_destroy(c); return rc; }
+  *out = c;
+  return 0;
+}
+
+int hexed_b200_destroy(hexed_b200_ctx* c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_mesh(c);
+  dev_free(c->perm); dev_free(c->block_min); dev_free(c->d_scalar); dev_free(c->d_face_scratch);
+  if (c->h_scalar) cudaFreeHost(c->h_scalar);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int hexed_b200_synchronize(hexed_b200_ctx* c) { HB_CUDA(c, cudaStreamSynchronize(c->stream)); return 0; }
+int hexed_b200_cuda_stream(hexed_b200_ctx* c, void** stream) { *stream = (void*)c->stream; return 0; }
+
+int hexed_b200_mesh_create(hexed_b200_ctx* c, const hexed_b200_mesh_desc* d)
+{
+  HB_CUDA(c, cudaSetDevice(c->device));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_mesh(c);
+  if (d->n_car < 0 || d->n_def < 0 || d->n_car_con < 0 || d->n_def_con < 0 || d->n_ref < 0) return fail(c, HEXED_B200_BAD_ARGUMENT, "negative count");
+  const size_t ne = (size_t)d->n_car + d->n_def;
+  const int nf = 2*c->nd;
+  if ((size_t)d->n_face_slot < nf*ne) return fail(c, HEXED_B200_BAD_ARGUMENT, "n_face_slot smaller than 2*n_dim*n_elem");
+  if ((size_t)d->n_normal_slot < (size_t)nf*d->n_def) return fail(c, HEXED_B200_BAD_ARGUMENT, "n_normal_slot smaller than 2*n_dim*n_def");
+  c->n_car = d->n_car; c->n_def = d->n_def; c->n_elem = (int)ne;
+  c->n_face_slot = d->n_face_slot; c->n_normal_slot = d->n_normal_slot;
+  c->n_car_con = d->n_car_con; c->n_def_con = d->n_def_con; c->n_ref = d->n_ref;
+  const size_t nq = c->nq, nfq = c->nfq, nv = c->nv;
+  int rc = 0;
+  if (!rc) rc = dev_alloc(c, &c->state, ne*nv*nq);
+  if (!rc) rc = dev_alloc(c, &c->tss, ne*nq);
+  if (!rc) rc = dev_alloc(c, &c->cache, ne*nv*nq);
+  if (!rc) rc = dev_alloc(c, &c->nom, ne);
+  if (!rc) rc = dev_alloc(c, &c->vtss, ne*c->n_vert);
+  if (!rc) rc = dev_alloc(c, &c->uncert, ne);
+  if (!rc) rc = dev_alloc(c, &c->refn, (size_t)d->n_def*c->nd*c->nd*nq);
+  if (!rc) rc = dev_alloc(c, &c->det, (size_t)d->n_def*nq);
+  if (!rc) rc = dev_alloc(c, &c->face_state, (size_t)d->n_face_slot*nv*nfq);
+  if (!rc) rc = dev_alloc(c, &c->normals, (size_t)d->n_normal_slot*c->nd*nfq);
+  if (rc) { free_mesh(c); return rc; }
+  // validate + repack the integer tables
+  std::vector<int> car((size_t)d->n_car_con*4), def((size_t)d->n_def_con*4), ref((size_t)d->n_ref*8);
+  auto slot_ok = [&](int s) { return s >= 0 && s < d->n_face_slot; };
+  for (int i = 0; i < d->n_car_con; ++i) {
+    const int* t = d->car_con + (size_t)i*3;
+    if (!slot_ok(t[0]) || !slot_ok(t[1]) || t[2] < 0 || t[2] >= c->nd) { free_mesh(c); return fail(c, HEXED_B200_BAD_ARGUMENT, "bad cartesian connection table entry"); }
+    car[(size_t)i*4] = t[0]; car[(size_t)i*4 + 1] = t[1]; car[(size_t)i*4 + 2] = t[2]; car[(size_t)i*4 + 3] = 0;
+  }
+  for (int i = 0; i < d->n_def_con; ++i) {
+    const int* t = d->def_con + (size_t)i*7;
+    const bool ok = slot_ok(t[0]) && slot_ok(t[1]) && t[2] >= 0 && t[2] < c->nd && t[3] >= 0 && t[3] < c->nd
+                    && (t[4] == 0 || t[4] == 1) && (t[5] == 0 || t[5] == 1) && t[6] >= 0 && t[6] < d->n_normal_slot;
+    if (!ok) { free_mesh(c); return fail(c, HEXED_B200_BAD_ARGUMENT, "bad deformed connection table entry"); }
+    def[(size_t)i*4] = t[0]; def[(size_t)i*4 + 1] = t[1]; def[(size_t)i*4 + 2] = dir_code(t[2], t[3], t[4], t[5]); def[(size_t)i*4 + 3] = t[6];
+  }
+  for (int i = 0; i < d->n_ref; ++i) {
+    const int* t = d->ref_face + (size_t)i*7;
+    int nfine = ipow(2, c->nd - 1);
+    for (int k = 0; k < c->nd - 1; ++k) nfine /= 1 + (t[5 + k] != 0);
+    bool ok = slot_ok(t[0]);
+    for (int k = 0; k < nfine; ++k) ok = ok && slot_ok(t[1 + k]);
+    if (!ok) { free_mesh(c); return fail(c, HEXED_B200_BAD_ARGUMENT, "bad refined face table entry"); }
+    for (int k = 0; k < 5; ++k) ref[(size_t)i*8 + k] = t[k];
+    ref[(size_t)i*8 + 5] = t[5] != 0; ref[(size_t)i*8 + 6] = t[6] != 0; ref[(size_t)i*8 + 7] = 0;
+  }
+  if (!rc) rc = dev_alloc(c, &c->car_con, car.size(), false);
+  if (!rc) rc = dev_alloc(c, &c->def_con, def.size(), false);
+  if (!rc) rc = dev_alloc(c, &c->ref_face, ref.size(), false);
+  if (!rc && !car.empty()) rc = check(c, cudaMemcpyAsync(c->car_con, car.data(), sizeof(int)*car.size(), cudaMemcpyHostToDevice, c->stream), "upload car_con");
+  if (!rc && !def.empty()) rc = check(c, cudaMemcpyAsync(c->def_con, def.data(), sizeof(int)*def.size(), cudaMemcpyHostToDevice, c->stream), "upload def_con");
+  if (!rc && !ref.empty()) rc = check(c, cudaMemcpyAsync(c->ref_face, ref.data(), sizeof(int)*ref.size(), cudaMemcpyHostToDevice, c->stream), "upload ref_face");
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "mesh_create sync");
+  if (rc) { free_mesh(c); return rc; }
+  c->have_mesh = true;
+  return 0;
+}
+
+static int array_info(hexed_b200_ctx* c, int which, double*** arr, size_t* item, size_t* count, bool alloc)
+{
+  const size_t nq = c->nq, nfq = c->nfq;
+  switch (which) {
+    case HEXED_B200_NOMINAL_SIZE: *arr = &c->nom; *item = 1; *count = c->n_elem; break;
+    case HEXED_B200_VERTEX_TSS: *arr = &c->vtss; *item = c->n_vert; *count = c->n_elem; break;
+    case HEXED_B200_REF_NORMALS: *arr = &c->refn; *item = (size_t)c->nd*c->nd*nq; *count = c->n_def; break;
+    case HEXED_B200_JAC_DET: *arr = &c->det; *item = nq; *count = c->n_def; break;
+    case HEXED_B200_FACE_STATE: *arr = &c->face_state; *item = c->nv*nfq; *count = c->n_face_slot; break;
+    case HEXED_B200_FACE_LDG: *arr = &c->face_ldg; *item = c->nv*nfq; *count = c->n_face_slot; break;
+    case HEXED_B200_FACE_WIDE: *arr = &c->face_wide; *item = (size_t)(c->nd + c->rs)*nfq; *count = c->n_face_slot; break;
+    case HEXED_B200_NORMALS: *arr = &c->normals; *item = c->nd*nfq; *count = c->n_normal_slot; break;
+    case HEXED_B200_UNCERT: *arr = &c->uncert; *item = 1; *count = c->n_elem; break;
+    default: return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown array id");
+  }
+  if (!**arr && alloc) { int rc = dev_alloc(c, *arr, (*item)*(*count)); if (rc) return rc; }
+  return 0;
+}
+
+int hexed_b200_upload(hexed_b200_ctx* c, int which, const double* src, size_t first, size_t n)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  double** arr; size_t item, count;
+  int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
+  if (first + n > count) return fail(c, HEXED_B200_BAD_ARGUMENT, "upload range out of bounds");
+  if (!n) return 0;
+  HB_CUDA(c, cudaMemcpyAsync(*arr + first*item, src, sizeof(double)*n*item, cudaMemcpyDefault, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hexed_b200_download(hexed_b200_ctx* c, int which, double* dst, size_t first, size_t n)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  double** arr; size_t item, count;
+  int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
+  if (first + n > count) return fail(c, HEXED_B200_BAD_ARGUMENT, "download range out of bounds");
+  if (!n) return 0;
+  HB_CUDA(c, cudaMemcpyAsync(dst, *arr + first*item, sizeof(double)*n*item, cudaMemcpyDefault, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int move_slots(hexed_b200_ctx* c, double* host, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem, bool up)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const int total_slots = c->nv + 7 + c->rs + (c->nv > c->rs ? c->nv : c->rs);
+  if (first_slot < 0 || n_slots < 0 || first_slot + n_slots > total_slots) return fail(c, HEXED_B200_BAD_ARGUMENT, "slot range out of bounds");
+  if (first_elem < 0 || n_elem < 0 || first_elem + n_elem > c->n_elem) return fail(c, HEXED_B200_BAD_ARGUMENT, "element range out of bounds");
+  if (!n_elem) return 0;
+  for (int s = 0; s < n_slots; ++s) {
+    double* base; size_t dstride;
+    int rc = slot_array(c, first_slot + s, &base, &dstride, up); if (rc) return rc;
+    double* h = host + (size_t)s*c->nq;
+    if (!base) { // array never allocated (or slot not mirrored): reads as zero, writes are dropped
+      if (!up) HB_CUDA(c, cudaMemset2DAsync(h, sizeof(double)*elem_stride, 0, sizeof(double)*c->nq, n_elem, c->stream));
+      continue;
+    }
+    double* dptr = base + (size_t)first_elem*dstride;
+    if (up) HB_CUDA(c, cudaMemcpy2DAsync(dptr, sizeof(double)*dstride, h, sizeof(double)*elem_stride, sizeof(double)*c->nq, n_elem, cudaMemcpyDefault, c->stream));
+    else HB_CUDA(c, cudaMemcpy2DAsync(h, sizeof(double)*elem_stride, dptr, sizeof(double)*dstride, sizeof(double)*c->nq, n_elem, cudaMemcpyDefault, c->stream));
+  }
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hexed_b200_upload_elem_slots(hexed_b200_ctx* c, const double* src, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem)
+{ return move_slots(c, const_cast<double*>(src), elem_stride, first_slot, n_slots, first_elem, n_elem, true); }
+
+int hexed_b200_download_elem_slots(hexed_b200_ctx* c, double* dst, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem)
+{ return move_slots(c, dst, elem_stride, first_slot, n_slots, first_elem, n_elem, false); }
+
+int hexed_b200_face_list_create(hexed_b200_ctx* c, const int* slots, int n, int* list_id)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= c->n_face_slot) return fail(c, HEXED_B200_BAD_ARGUMENT, "face slot out of range");
+  FaceList l; l.n = n;
+  int rc = dev_alloc(c, &l.d_slots, n, false); if (rc) return rc;
+  l.buf_doubles = (size_t)n*(c->nd + c->rs)*c->nfq;
+  rc = dev_alloc(c, &l.d_buf, l.buf_doubles, false); if (rc) return rc;
+  if (n) HB_CUDA(c, cudaMemcpyAsync(l.d_slots, slots, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->lists.push_back(l);
+  *list_id = (int)c->lists.size() - 1;
+  return 0;
+}
+
+static int list_face_array(hexed_b200_ctx* c, int kind, double** arr, int* width)
+{
+  double** a; size_t item, count;
+  const int which = kind == 0 ? HEXED_B200_FACE_STATE : kind == 1 ? HEXED_B200_FACE_LDG : kind == 2 ? HEXED_B200_FACE_WIDE : -1;
+  int rc = array_info(c, which, &a, &item, &count, true); if (rc) return rc;
+  *arr = *a; *width = (int)item;
+  return 0;
+}
+
+int hexed_b200_face_list_download(hexed_b200_ctx* c, int list_id, int kind, double* dst)
+{
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  double* arr; int width;
+  int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  rc = launch_gather_faces(c, arr, width, l.d_slots, l.n, l.d_buf); if (rc) return rc;
+  if (l.n) HB_CUDA(c, cudaMemcpyAsync(dst, l.d_buf, sizeof(double)*l.n*width, cudaMemcpyDefault, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hexed_b200_face_list_upload(hexed_b200_ctx* c, int list_id, int kind, const double* src)
+{
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  double* arr; int width;
+  int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  if (l.n) HB_CUDA(c, cudaMemcpyAsync(l.d_buf, src, sizeof(double)*l.n*width, cudaMemcpyDefault, c->stream));
+  return launch_scatter_faces(c, arr, width, l.d_slots, l.n, l.d_buf);
+}
+
+int hexed_b200_face_permutation_table(hexed_b200_ctx* c, const int dir[4], int* out)
+{
+  if (dir[0] < 0 || dir[0] >= c->nd || dir[1] < 0 || dir[1] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad direction");
+  const int* t = c->h_perm.data() + (size_t)dir_code(dir[0], dir[1], dir[2] != 0, dir[3] != 0)*c->nfq;
+  for (int q = 0; q < c->nfq; ++q) out[q] = t[q];
+  return 0;
+}
+
+int hexed_b200_face_permutation(hexed_b200_ctx* c, const int dir[4], int restore, double* data)
+{
+  if (dir[0] < 0 || dir[0] >= c->nd || dir[1] < 0 || dir[1] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad direction");
+  const size_t n = (size_t)c->nv*c->nfq;
+  HB_CUDA(c, cudaMemcpyAsync(c->d_face_scratch, data, sizeof(double)*n, cudaMemcpyDefault, c->stream));
+  int rc = launch_permute_face(c, c->d_face_scratch, c->nv, dir_code(dir[0], dir[1], dir[2] != 0, dir[3] != 0), restore); if (rc) return rc;
+  HB_CUDA(c, cudaMemcpyAsync(data, c->d_face_scratch, sizeof(double)*n, cudaMemcpyDefault, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+/* ---- stage drivers ---- */
+
+int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
+{
+  // reference src/kernels_convective.cpp:8-16: Neighbor(car) Neighbor(def) Restrict Local(car) Local(def) Prolong
+  int rc;
+  if ((rc = launch_neighbor_euler(c, 0))) return rc;
+  if ((rc = launch_neighbor_euler(c, 1))) return rc;
+  if ((rc = launch_restrict(c, 0, c->nv, 1))) return rc;
+  if ((rc = launch_local_euler(c, 0, o))) return rc;
+  if ((rc = launch_local_euler(c, 1, o))) return rc;
+  if ((rc = launch_prolong(c, 0, c->nv, 0))) return rc;
+  return 0;
+}
+
+int hexed_b200_max_dt_euler(hexed_b200_ctx* c, hexed_b200_options, double safety_conv, double, int local_time, double* dt)
+{ return launch_max_dt_euler(c, safety_conv, local_time, dt); }
+
+int hexed_b200_compute_write_face(hexed_b200_ctx* c) { return launch_write_face(c); }
+
+int hexed_b200_compute_prolong(hexed_b200_ctx* c, int scale, int offset)
+{
+  if (offset && !c->face_ldg) { int rc = dev_alloc(c, &c->face_ldg, (size_t)c->n_face_slot*c->nv*c->nfq); if (rc) return rc; }
+  return launch_prolong(c, offset ? 1 : 0, c->nv, scale);
+}
+
+int hexed_b200_compute_restrict(hexed_b200_ctx* c, int scale, int offset)
+{
+  if (offset && !c->face_ldg) { int rc = dev_alloc(c, &c->face_ldg, (size_t)c->n_face_slot*c->nv*c->nfq); if (rc) return rc; }
+  return launch_restrict(c, offset ? 1 : 0, c->nv, scale);
+}
+
+int hexed_b200_neighbor_euler(hexed_b200_ctx* c, int deformed) { return launch_neighbor_euler(c, deformed); }
+int hexed_b200_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o) { return launch_local_euler(c, deformed, o); }
+
+int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, const int* ghost, const int* normal,
+                         const double* params, int n_params, int* bc_id)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (kind < 0 || kind > HEXED_B200_BC_NONPENETRATION) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary condition kind");
+  if (kind == HEXED_B200_BC_FREESTREAM && n_params != c->nv) return fail(c, HEXED_B200_BAD_ARGUMENT, "freestream needs n_dim + 2 parameters");
+  for (int i = 0; i < n; ++i) {
+    if (ghost[i] < 0 || ghost[i] >= c->n_face_slot || inside[i] < 0 || inside[i] >= c->n_face_slot) return fail(c, HEXED_B200_BAD_ARGUMENT, "face slot out of range");
+    if (kind == HEXED_B200_BC_NONPENETRATION && (normal[i] < 0 || normal[i] >= c->n_normal_slot)) return fail(c, HEXED_B200_BAD_ARGUMENT, "normal slot out of range");
+  }
+  Bc b; b.kind = kind; b.n = n; b.n_params = n_params;
+  int rc = 0;
+  if (!rc) rc = dev_alloc(c, &b.inside, n, false);
+  if (!rc) rc = dev_alloc(c, &b.ghost, n, false);
+  if (!rc) rc = dev_alloc(c, &b.normal, n, true);
+  if (!rc) rc = dev_alloc(c, &b.params, n_params, false);
+  if (rc) return rc;
+  if (n) {
+    HB_CUDA(c, cudaMemcpyAsync(b.inside, inside, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(c, cudaMemcpyAsync(b.ghost, ghost, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));
+    if (normal) HB_CUDA(c, cudaMemcpyAsync(b.normal, normal, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (n_params) HB_CUDA(c, cudaMemcpyAsync(b.params, params, sizeof(double)*n_params, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->bcs.push_back(b);
+  *bc_id = (int)c->bcs.size() - 1;
+  return 0;
+}
+
+int hexed_b200_apply_state_bcs(hexed_b200_ctx* c) { return launch_bcs(c); }
+
+int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled != 0; return 0; }
+
+int hexed_b200_kernel_stats(hexed_b200_ctx* c, hexed_b200_kernel_stat* out, int capacity, int* n_out)
+{
+  int n = 0;
+  for (int i = 0; i < ST_COUNT && n < capacity; ++i, ++n) {
+    out[n].name = c->stats[i].name; out[n].deformed = c->stats[i].deformed; out[n].work_units = c->stats[i].work_units;
+    out[n].launches = c->stats[i].launches; out[n].device_seconds = c->stats[i].seconds;
+  }
+  *n_out = n;
+  return 0;
+}
+
+int hexed_b200_reset_stats(hexed_b200_ctx* c)
+{
+  for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].work_units = 0; c->stats[i].launches = 0; c->stats[i].seconds = 0; }
+  return 0;
+}
+
+long long hexed_b200_launch_count(const hexed_b200_ctx* c) { return c->launches; }
+
+} // extern "C"

@@ -1,0 +1,137 @@
+/* common.cuh -- context, device-side constants and dispatch helpers shared by all translation units. */
+#ifndef HB_COMMON_CUH_
+#define HB_COMMON_CUH_
+
+#include "hb_rt.cuh"
+#include "../../include/hexed_b200.h"
+#include <cfloat>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace hb {
+
+constexpr int MAX_RS = 8;
+
+__host__ __device__ constexpr int ipow(int b, int e) { int r = 1; for (int i = 0; i < e; ++i) r *= b; return r; }
+
+/* 1-D operators of the basis, passed by value to kernels (kernel parameters live in the constant bank).
+ * `dfull = diff_mat - lift*boundary` folds the interior part of the DG derivative
+ *   D(q, b) = diff_mat q + lift (b - boundary q)        (reference include/Derivative.hpp:51-55)
+ * into one matrix so that D(q, b) = dfull q + lift b. */
+struct Ops
+{
+  double diff[MAX_RS][MAX_RS];
+  double dfull[MAX_RS][MAX_RS];
+  double bnd[2][MAX_RS];
+  double lift[MAX_RS][2];
+  double node[MAX_RS];
+};
+
+struct FilterOp { double filter[MAX_RS][MAX_RS]; };
+struct TransferOps { double prolong[2][MAX_RS][MAX_RS]; double restrict_[2][MAX_RS][MAX_RS]; };
+
+struct Stat
+{
+  const char* name; int deformed; long long work_units = 0; long long launches = 0; double seconds = 0;
+};
+enum { ST_NEIGHBOR_CAR, ST_NEIGHBOR_DEF, ST_LOCAL_CAR, ST_LOCAL_DEF, ST_MAX_DT_CAR, ST_MAX_DT_DEF, ST_PR, ST_BC, ST_WRITE_FACE, ST_COUNT };
+
+struct FaceList { int n = 0; int* d_slots = nullptr; double* d_buf = nullptr; size_t buf_doubles = 0; };
+struct Bc { int kind; int n; int *inside = nullptr, *ghost = nullptr, *normal = nullptr; double* params = nullptr; int n_params = 0; };
+
+} // namespace hb
+
+struct hexed_b200_ctx
+{
+  int device = 0;
+  int nd = 0, rs = 0, nq = 0, nfq = 0, nv = 0, n_vert = 0;
+  hb::Ops ops;
+  hb::FilterOp filt;
+  hb::TransferOps transfer;
+  double weight[hb::MAX_RS];
+  double orthogonal[hb::MAX_RS][hb::MAX_RS];
+  double min_eig_conv = 0, min_eig_diff = 0, quad_safety = 0;
+  cudaStream_t stream = nullptr;
+  // mesh
+  bool have_mesh = false;
+  int n_car = 0, n_def = 0, n_elem = 0, n_face_slot = 0, n_normal_slot = 0, n_car_con = 0, n_def_con = 0, n_ref = 0;
+  double *state = nullptr, *tss = nullptr, *cache = nullptr, *av = nullptr, *forcing = nullptr, *adv = nullptr;
+  double *nom = nullptr, *vtss = nullptr, *uncert = nullptr, *refn = nullptr, *det = nullptr;
+  double *face_state = nullptr, *face_ldg = nullptr, *face_wide = nullptr, *normals = nullptr;
+  int *car_con = nullptr;  // [n][4]: slot0, slot1, i_dim, 0
+  int *def_con = nullptr;  // [n][4]: slot0, slot1, dir code, normal slot
+  int *ref_face = nullptr; // [n][8]: coarse, fine0..3, stretch0, stretch1, 0
+  int *perm = nullptr;     // [36][nfq] face permutation tables, indexed by dir code
+  std::vector<int> h_perm;
+  // scratch
+  double* block_min = nullptr; size_t block_min_cap = 0;
+  double* d_scalar = nullptr; double* h_scalar = nullptr;
+  double* d_face_scratch = nullptr;
+  std::vector<hb::FaceList> lists;
+  std::vector<hb::Bc> bcs;
+  // stats
+  hb::Stat stats[hb::ST_COUNT];
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace hb {
+
+/* direction code used to index the permutation tables: i_dim0 + 3*i_dim1 + 9*sign0 + 18*sign1 */
+__host__ __device__ inline int dir_code(int d0, int d1, int s0, int s1) { return d0 + 3*d1 + 9*s0 + 18*s1; }
+
+int fail(hexed_b200_ctx* c, int code, const std::string& msg);
+int check(hexed_b200_ctx* c, cudaError_t e, const char* what);
+#define HB_CUDA(c, call) do { int hb_rc_ = hb::check(c, (call), #call); if (hb_rc_) return hb_rc_; } while (0)
+
+struct StatScope
+{
+  hexed_b200_ctx* c; int id;
+  StatScope(hexed_b200_ctx* ctx, int stat_id, long long work) : c{ctx}, id{stat_id}
+  {
+    c->stats[id].work_units += work;
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~StatScope()
+  {
+    if (c->timing) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->stats[id].seconds += ms*1e-3;
+    }
+  }
+};
+inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->stats[stat_id].launches; }
+
+/* launchers implemented in the kernel translation units; return a HEXED_B200_* code */
+int launch_neighbor_euler(hexed_b200_ctx* c, int deformed);
+int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o);
+int launch_write_face(hexed_b200_ctx* c);
+int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
+int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale);
+int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale);
+int launch_bcs(hexed_b200_ctx* c);
+int launch_gather_faces(hexed_b200_ctx* c, const double* src, int width, const int* d_slots, int n, double* dst);
+int launch_scatter_faces(hexed_b200_ctx* c, double* dst, int width, const int* d_slots, int n, const double* src);
+int launch_permute_face(hexed_b200_ctx* c, double* d_data, int n_var, int code, int restore);
+
+/* run-time (n_dim, row_size) -> compile-time dispatch; the analogue of the reference's kernel_factory
+ * (include/kernel_factory.hpp:64-119). F is a generic lambda taking two integral_constants. */
+template <int V> struct IC { static constexpr int value = V; };
+template <class F>
+int dispatch(hexed_b200_ctx* c, F&& f)
+{
+  #define HB_CASE(ND, RS) if (c->nd == ND && c->rs == RS) return f(IC<ND>{}, IC<RS>{});
+  #define HB_ROW(ND) HB_CASE(ND, 2) HB_CASE(ND, 3) HB_CASE(ND, 4) HB_CASE(ND, 5) HB_CASE(ND, 6) HB_CASE(ND, 7) HB_CASE(ND, 8)
+  HB_ROW(1) HB_ROW(2) HB_ROW(3)
+  #undef HB_ROW
+  #undef HB_CASE
+  return fail(c, HEXED_B200_INVALID_KERNEL, "demand for invalid kernel");
+}
+
+} // namespace hb
+#endif

@@ -1,0 +1,60 @@
+/* euler.cuh -- pointwise Euler physics shared by the kernels.
+ * Follows pde::Navier_stokes<false>::Pde::Computation (reference include/pde.hpp:94-122,160-166):
+ * state order [momentum_0..nd-1, mass, total energy], heat ratio 1.4. Divisions by the mass are done with one
+ * IEEE reciprocal per point and multiplications (<= 1 ulp from the reference's divisions; covered by the 1e-11 bar). */
+#ifndef HB_EULER_CUH_
+#define HB_EULER_CUH_
+#include "common.cuh"
+
+namespace hb {
+
+constexpr double heat_rat = 1.4;
+
+template <int ND>
+struct EulerPoint
+{
+  double s[ND + 2];
+  double inv_mass, pressure;
+  __device__ __forceinline__ void scalars()
+  {
+    inv_mass = 1./s[ND];
+    double ke = 0;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) ke += s[i]*s[i];
+    ke *= .5*inv_mass;
+    pressure = (heat_rat - 1.)*(s[ND + 1] - ke);
+  }
+  /* flux through the (area-weighted) direction n */
+  __device__ __forceinline__ void flux(const double (&n)[ND], double (&f)[ND + 2]) const
+  {
+    double mass_flux = 0;
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) mass_flux += s[j]*n[j];
+    const double vol_flux = mass_flux*inv_mass;
+    f[ND] = mass_flux;
+    f[ND + 1] = (s[ND + 1] + pressure)*vol_flux;
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) f[j] = s[j]*vol_flux + pressure*n[j];
+  }
+  /* flux along reference direction d of a Cartesian element (unit normal e_d) */
+  __device__ __forceinline__ void flux_axis(int d, double (&f)[ND + 2]) const
+  {
+    const double mass_flux = s[d];
+    const double vol_flux = mass_flux*inv_mass;
+    f[ND] = mass_flux;
+    f[ND + 1] = (s[ND + 1] + pressure)*vol_flux;
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) f[j] = s[j]*vol_flux + (j == d ? pressure : 0.);
+  }
+  __device__ __forceinline__ double char_speed() const
+  {
+    const double sound = sqrt(heat_rat*(heat_rat - 1)*s[ND + 1]*inv_mass);
+    double sq = 0;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) sq += s[i]*s[i];
+    return sound + sqrt(sq)*inv_mass;
+  }
+};
+
+} // namespace hb
+#endif

@@ -1,0 +1,311 @@
+/* misc_kernels.cu -- CFL time step, hanging-node transfer, boundary ghost fill, face gather/scatter. */
+#include "euler.cuh"
+
+namespace hb {
+
+/* ---------------- Max_dt: reference include/Spatial.hpp:784-828, include/math.hpp:207-218 ----------------
+ * One thread per quadrature point: n-linear interpolation of the vertex spacing, characteristic speed, local
+ * time-step scale written to tss (or 1.) and, for global time stepping, a warp-shuffle + shared-memory block minimum
+ * followed by a one-block final reduction. The Cartesian and deformed instantiations of the reference are the same
+ * arithmetic, so one launch covers every element. */
+struct MaxDtArgs
+{
+  const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; double* block_min;
+};
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(256)
+max_dt_euler_kernel(MaxDtArgs a, Ops ops)
+{
+  constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND);
+  __shared__ double warp_min[8];
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int e = (int)(gid/nq), q = (int)(gid % nq);
+  double val = DBL_MAX;
+  if (e < a.n_elem) {
+    double vals[n_vert];
+    #pragma unroll
+    for (int i = 0; i < n_vert; ++i) vals[i] = a.vtss[(size_t)e*n_vert + i];
+    int stride = n_vert;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+      stride /= 2;
+      #pragma unroll
+      for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
+    }
+    const double spacing = vals[0];
+    EulerPoint<ND> p;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
+    p.inv_mass = 1./p.s[ND];
+    const double scale = p.char_speed()/a.max_cfl_c/spacing;
+    if (a.is_local) a.tss[(size_t)e*nq + q] = 1./scale;
+    else { a.tss[(size_t)e*nq + q] = 1.; val = fmin(val, 1./scale); }
+  }
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = warp_min[0];
+    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
+    a.block_min[blockIdx.x] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_min_kernel(const double* in, int n, double* out)
+{
+  __shared__ double warp_min[8];
+  double val = DBL_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) val = fmin(val, in[i]);
+  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = warp_min[0];
+    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
+    *out = m;
+  }
+}
+
+int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  StatScope s_car(c, ST_MAX_DT_CAR, c->n_car);
+  c->stats[ST_MAX_DT_DEF].work_units += c->n_def;
+  if (!c->n_elem) { *dt = local_time ? 1. : DBL_MAX; return 0; }
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    const long long total = (long long)c->n_elem*ipow(RS, ND);
+    const int grid = (int)((total + 255)/256);
+    if ((size_t)grid > c->block_min_cap) {
+      if (c->block_min) cudaFree(c->block_min);
+      HB_CUDA(c, cudaMalloc(&c->block_min, sizeof(double)*grid));
+      c->block_min_cap = grid;
+    }
+    MaxDtArgs a;
+    a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
+    a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9) * safety (Spatial.hpp:777)
+    a.is_local = local_time; a.block_min = c->block_min;
+    { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
+    count_launch(c, ST_MAX_DT_CAR);
+    HB_CUDA(c, cudaGetLastError());
+    if (local_time) { *dt = 1.; return 0; }
+    HB_LAUNCH(reduce_min_kernel, 1, 256, 0, c->stream, c->block_min, grid, c->d_scalar);
+    count_launch(c, ST_MAX_DT_CAR);
+    HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *dt = *c->h_scalar;
+    return 0;
+  });
+}
+
+/* ---------------- hanging-node transfer: reference include/Spatial.hpp:153-206 (prolong), :230-285 (restrict) ----------------
+ * One CTA per refined face; the fine faces are processed one after another in shared memory with the same
+ * dimension-by-dimension in-place sweeps (and the same accumulation order into the coarse face) as the reference.
+ * Restrict mutates the fine (mortar) data exactly like the reference does. */
+template <int ND, int RS>
+__device__ void transfer_sweeps(double* buf, int n_var, const double (*mat)[MAX_RS][MAX_RS], const int* str, int i_face, double mult, bool divide)
+{
+  constexpr int nfq = ipow(RS, ND - 1);
+  for (int d = 0; d < ND - 1; ++d) {
+    if (str[d]) {
+      for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) buf[i] = divide ? buf[i]/mult : buf[i]*mult;
+    } else {
+      const int pw = ND - 2 - d;
+      const int face_stride = str[ND - 2 >= 0 ? ND - 2 : 0] ? 1 : ipow(2, pw);
+      const int qstride = ipow(RS, pw);
+      const int i_half = (i_face/face_stride) % 2;
+      const int lines_per_var = nfq/RS;
+      for (int line = threadIdx.x; line < n_var*lines_per_var; line += blockDim.x) {
+        const int v = line/lines_per_var, l = line % lines_per_var;
+        const int o = l/qstride, in = l % qstride;
+        double* p = buf + v*nfq + o*RS*qstride + in;
+        double row[RS], res[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) row[k] = p[k*qstride];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double s = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) s += mat[i_half][i][k]*row[k];
+          res[i] = s;
+        }
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) p[k*qstride] = res[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(128)
+prolong_kernel(double* faces, int width, int n_var, const int* ref_face, TransferOps ops, int scl)
+{
+  constexpr int nfq = ipow(RS, ND - 1);
+  HB_DYN_SMEM(double, buf);
+  const int* rf = ref_face + (size_t)blockIdx.x*8;
+  const int str[2] = {rf[5], rf[6]};
+  int nf = ipow(2, ND - 1);
+  for (int d = 0; d < ND - 1; ++d) nf /= 1 + str[d];
+  const double* coarse = faces + (size_t)rf[0]*width;
+  for (int f = 0; f < nf; ++f) {
+    for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) buf[i] = coarse[i];
+    __syncthreads();
+    transfer_sweeps<ND, RS>(buf, n_var, ops.prolong, str, f, 1. + scl, false);
+    double* fine = faces + (size_t)rf[1 + f]*width;
+    for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) fine[i] = buf[i];
+    __syncthreads();
+  }
+}
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(128)
+restrict_kernel(double* faces, int width, int n_var, const int* ref_face, TransferOps ops, int scl)
+{
+  constexpr int nfq = ipow(RS, ND - 1);
+  HB_DYN_SMEM(double, buf);
+  double* acc = buf + n_var*nfq;
+  const int* rf = ref_face + (size_t)blockIdx.x*8;
+  const int str[2] = {rf[5], rf[6]};
+  int nf = ipow(2, ND - 1);
+  for (int d = 0; d < ND - 1; ++d) nf /= 1 + str[d];
+  for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) acc[i] = 0.;
+  for (int f = 0; f < nf; ++f) {
+    double* fine = faces + (size_t)rf[1 + f]*width;
+    for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) buf[i] = fine[i];
+    __syncthreads();
+    transfer_sweeps<ND, RS>(buf, n_var, ops.restrict_, str, f, 1. + scl, true);
+    for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) { fine[i] = buf[i]; acc[i] += buf[i]; }
+    __syncthreads();
+  }
+  double* coarse = faces + (size_t)rf[0]*width;
+  for (int i = threadIdx.x; i < n_var*nfq; i += blockDim.x) coarse[i] = acc[i];
+}
+
+static double* face_array(hexed_b200_ctx* c, int kind) { return kind == 0 ? c->face_state : kind == 1 ? c->face_ldg : c->face_wide; }
+static int face_width(hexed_b200_ctx* c, int kind) { return (kind == 2 ? c->nd + c->rs : c->nv)*c->nfq; }
+
+template <bool PROLONG>
+static int launch_transfer(hexed_b200_ctx* c, int kind, int n_var, int scale)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  StatScope scope(c, ST_PR, c->n_ref);
+  if (!c->n_ref) return 0;
+  double* faces = face_array(c, kind);
+  if (!faces) return fail(c, HEXED_B200_BAD_ARGUMENT, "face storage of the requested kind has not been allocated");
+  const int width = face_width(c, kind);
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    const size_t smem = sizeof(double)*n_var*ipow(RS, ND - 1)*(PROLONG ? 1 : 2);
+    if (PROLONG) { auto k = prolong_kernel<ND, RS>; HB_LAUNCH(k, c->n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale); }
+    else { auto k = restrict_kernel<ND, RS>; HB_LAUNCH(k, c->n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale); }
+    count_launch(c, ST_PR);
+    HB_CUDA(c, cudaGetLastError());
+    return 0;
+  });
+}
+int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<true>(c, kind, n_var, scale); }
+int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<false>(c, kind, n_var, scale); }
+
+/* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */
+__global__ void __launch_bounds__(256)
+bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params,
+          double* faces, double* faces_ldg, const double* normals, int nd, int nfq)
+{
+  const int nv = nd + 2, w = nv*nfq;
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = (int)(gid/nfq), q = (int)(gid % nfq);
+  if (i >= n) return;
+  double* gh = faces + (size_t)ghost[i]*w + q;
+  if (kind == HEXED_B200_BC_FREESTREAM) { // Freestream::apply_state :66-76
+    for (int v = 0; v < nv; ++v) gh[v*nfq] = params[v];
+    return;
+  }
+  const double* in = faces + (size_t)inside[i]*w + q;
+  if (kind == HEXED_B200_BC_COPY) { // copy_state :12-23 copies both halves of the face storage
+    for (int v = 0; v < nv; ++v) gh[v*nfq] = in[v*nfq];
+    if (faces_ldg) for (int v = 0; v < nv; ++v) faces_ldg[(size_t)ghost[i]*w + q + v*nfq] = faces_ldg[(size_t)inside[i]*w + q + v*nfq];
+    return;
+  }
+  // Nonpenetration::apply_state -> reflect_momentum / reflect_normal :301-327
+  const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  double dot = 0., nsq = 0.;
+  for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; dot += in[d*nfq]*nn; nsq += nn*nn; }
+  for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq] - 2*dot*nr[d*nfq]/nsq;
+  gh[nd*nfq] = in[nd*nfq];
+  gh[(nd + 1)*nfq] = in[(nd + 1)*nfq];
+}
+
+int launch_bcs(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  long long total_faces = 0;
+  for (auto& b : c->bcs) total_faces += b.n;
+  StatScope scope(c, ST_BC, total_faces);
+  for (auto& b : c->bcs) {
+    if (!b.n) continue;
+    const long long total = (long long)b.n*c->nfq;
+    HB_LAUNCH(bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal, b.params,
+              c->face_state, c->face_ldg, c->normals, c->nd, c->nfq);
+    count_launch(c, ST_BC);
+    HB_CUDA(c, cudaGetLastError());
+  }
+  return 0;
+}
+
+/* ---------------- packed gather / scatter of face slots (boundary faces crossing PCIe) ---------------- */
+__global__ void __launch_bounds__(256) gather_kernel(const double* src, int width, const int* slots, int n, double* dst)
+{
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const long long i = gid/width; const int k = (int)(gid % width);
+  if (i < n) dst[i*width + k] = src[(size_t)slots[i]*width + k];
+}
+__global__ void __launch_bounds__(256) scatter_kernel(double* dst, int width, const int* slots, int n, const double* src)
+{
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const long long i = gid/width; const int k = (int)(gid % width);
+  if (i < n) dst[(size_t)slots[i]*width + k] = src[i*width + k];
+}
+int launch_gather_faces(hexed_b200_ctx* c, const double* src, int width, const int* d_slots, int n, double* dst)
+{
+  const long long total = (long long)n*width;
+  if (!total) return 0;
+  HB_LAUNCH(gather_kernel, (int)((total + 255)/256), 256, 0, c->stream, src, width, d_slots, n, dst);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+int launch_scatter_faces(hexed_b200_ctx* c, double* dst, int width, const int* d_slots, int n, const double* src)
+{
+  const long long total = (long long)n*width;
+  if (!total) return 0;
+  HB_LAUNCH(scatter_kernel, (int)((total + 255)/256), 256, 0, c->stream, dst, width, d_slots, n, src);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+/* ---------------- Face_permutation on one face (reference include/Spatial.hpp:73-131) ---------------- */
+__global__ void permute_face_kernel(double* data, double* tmp, int n_var, int nfq, const int* table, int restore)
+{
+  const int total = n_var*nfq;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) tmp[i] = data[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int v = i/nfq, p = i % nfq;
+    if (restore) data[v*nfq + table[p]] = tmp[i];   // inverse permutation
+    else data[i] = tmp[v*nfq + table[p]];           // matched[p] = original[table[p]]
+  }
+}
+int launch_permute_face(hexed_b200_ctx* c, double* d_data, int n_var, int code, int restore)
+{
+  HB_LAUNCH(permute_face_kernel, 1, 128, 0, c->stream, d_data, d_data + n_var*c->nfq, n_var, c->nfq, c->perm + code*c->nfq, restore);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+} // namespace hb

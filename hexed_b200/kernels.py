@@ -1,0 +1,285 @@
+"""ctypes binding of libhexed_b200.so plus a small host mirror of the reference's `kernels.hpp` entry points.
+
+`Device` owns one `hexed_b200_ctx` (one GPU, one (n_dim, row_size)); `Device.load_mesh(FlatMesh)` creates the device
+mirror of a flattened mesh and the methods `compute_euler`, `max_dt_euler`, `compute_write_face`, `compute_prolong`,
+`compute_restrict`, `face_permutation` carry the same names, argument meaning and error behaviour as the reference's
+free functions (include/kernels.hpp:22-42): invalid (n_dim, row_size) raises RuntimeError("demand for invalid kernel")
+like include/kernel_factory.hpp:114-116.
+
+There is no CPU path here. If the shared library is missing, or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, n_slot
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhexed_b200.so")
+
+(NOMINAL_SIZE, VERTEX_TSS, REF_NORMALS, JAC_DET, FACE_STATE, FACE_LDG, FACE_WIDE, NORMALS, UNCERT) = range(9)
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("n_car", C.c_int), ("n_def", C.c_int), ("n_face_slot", C.c_int), ("n_normal_slot", C.c_int),
+                ("n_car_con", C.c_int), ("n_def_con", C.c_int), ("n_ref", C.c_int),
+                ("car_con", ip), ("def_con", ip), ("ref_face", ip)]
+
+
+class Options(C.Structure):
+    _fields_ = [("dt", C.c_double), ("i_stage", C.c_int), ("compute_residual", C.c_int), ("use_filter", C.c_int)]
+
+
+class Transport(C.Structure):
+    _fields_ = [("const_val", C.c_double), ("ref_val", C.c_double), ("ref_temp", C.c_double),
+                ("sqrt_ref_temp", C.c_double), ("temp_offset", C.c_double), ("is_viscous", C.c_int)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("deformed", C.c_int), ("work_units", C.c_longlong), ("launches", C.c_longlong),
+                ("device_seconds", C.c_double)]
+
+
+# every symbol include/hexed_b200.h declares, with its argument types (restype is int unless noted)
+SIGNATURES = {
+    "hexed_b200_device_count": [ip],
+    "hexed_b200_create": [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp, C.c_int],
+    "hexed_b200_destroy": [C.c_void_p],
+    "hexed_b200_last_error": [C.c_void_p],
+    "hexed_b200_synchronize": [C.c_void_p],
+    "hexed_b200_cuda_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "hexed_b200_mesh_create": [C.c_void_p, C.POINTER(MeshDesc)],
+    "hexed_b200_upload": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t],
+    "hexed_b200_download": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t],
+    "hexed_b200_upload_elem_slots": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int],
+    "hexed_b200_download_elem_slots": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int],
+    "hexed_b200_face_list_create": [C.c_void_p, ip, C.c_int, ip],
+    "hexed_b200_face_list_download": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "hexed_b200_face_list_upload": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "hexed_b200_face_permutation_table": [C.c_void_p, ip, ip],
+    "hexed_b200_compute_euler": [C.c_void_p, Options],
+    "hexed_b200_max_dt_euler": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
+    "hexed_b200_compute_write_face": [C.c_void_p],
+    "hexed_b200_compute_prolong": [C.c_void_p, C.c_int, C.c_int],
+    "hexed_b200_compute_restrict": [C.c_void_p, C.c_int, C.c_int],
+    "hexed_b200_face_permutation": [C.c_void_p, ip, C.c_int, dp],
+    "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
+    "hexed_b200_local_euler": [C.c_void_p, C.c_int, Options],
+    "hexed_b200_bc_create": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, dp, C.c_int, ip],
+    "hexed_b200_apply_state_bcs": [C.c_void_p],
+    "hexed_b200_set_timing": [C.c_void_p, C.c_int],
+    "hexed_b200_kernel_stats": [C.c_void_p, C.POINTER(KernelStat), C.c_int, ip],
+    "hexed_b200_reset_stats": [C.c_void_p],
+    "hexed_b200_launch_count": [C.c_void_p],
+}
+_RESTYPES = {"hexed_b200_last_error": C.c_char_p, "hexed_b200_launch_count": C.c_longlong}
+
+
+def load_library(path=None):
+    """load the C-ABI library and attach prototypes; raises (loudly) if it has not been built"""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(hexed_b200 has no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    return lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _addr(a):
+    """address of a numpy array or torch tensor (host or device)"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64
+        return a.ctypes.data
+    assert a.is_contiguous() and str(a.dtype) == "torch.float64"
+    return a.data_ptr()
+
+
+class Device:
+    def __init__(self, n_dim, row_size, basis, device=0, lib_path=None):
+        self.lib = load_library(lib_path)
+        self.n_dim, self.row_size, self.basis = n_dim, row_size, basis
+        self.ctx = C.c_void_p()
+        packed = np.ascontiguousarray(basis.packed()) if basis is not None else np.zeros(1)
+        rc = self.lib.hexed_b200_create(C.byref(self.ctx), device, n_dim, row_size, packed.ctypes.data_as(dp), packed.size)
+        if rc:
+            msg = self.lib.hexed_b200_last_error(None).decode()
+            self.ctx = None
+            raise RuntimeError(msg)
+        self.mesh = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.hexed_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(self.lib.hexed_b200_last_error(self.ctx).decode())
+
+    # ---- mesh epoch ----
+    def load_mesh(self, m, upload_elem_data=True):
+        """create the device mirror of FlatMesh `m` and upload everything the kernels read"""
+        assert m.n_dim == self.n_dim and m.row_size == self.row_size
+        car, dfc, ref = _i32(m.car_con), _i32(m.def_con), _i32(m.ref_face)
+        d = MeshDesc(m.n_car, m.n_def, m.n_face_slot, m.n_normal_slot, car.shape[0], dfc.shape[0], ref.shape[0],
+                     car.ctypes.data_as(ip), dfc.ctypes.data_as(ip), ref.ctypes.data_as(ip))
+        self._check(self.lib.hexed_b200_mesh_create(self.ctx, C.byref(d)))
+        self.mesh = m
+        self.upload(NOMINAL_SIZE, m.nom_size)
+        self.upload(VERTEX_TSS, m.vertex_tss)
+        if m.n_def:
+            self.upload(REF_NORMALS, m.ref_normals)
+            self.upload(JAC_DET, m.det)
+        if m.n_normal_slot:
+            self.upload(NORMALS, m.normals)
+        if upload_elem_data and m.elem_data is not None:
+            self.upload_elements(m.elem_data)
+        self.upload(FACE_STATE, m.face_state)
+        if m.face_ldg is not None:
+            self.upload(FACE_LDG, m.face_ldg)
+        self.bc_ids = []
+        for bc in m.bcs:
+            self.bc_ids.append(self.add_bc(bc))
+        return self
+
+    def add_bc(self, bc):
+        kind = bc["kind"]
+        if kind not in (BC_FREESTREAM, BC_COPY, BC_NONPENETRATION):
+            return None  # host-applied boundary condition
+        ins, gh, nr = _i32(bc["inside_slot"]), _i32(bc["ghost_slot"]), _i32(bc["normal_slot"])
+        params = np.ascontiguousarray(bc["params"], dtype=np.float64) if bc.get("params") is not None else np.zeros(0)
+        out = C.c_int(-1)
+        self._check(self.lib.hexed_b200_bc_create(self.ctx, kind, ins.size, ins.ctypes.data_as(ip), gh.ctypes.data_as(ip),
+                                                  nr.ctypes.data_as(ip), params.ctypes.data_as(dp), params.size, C.byref(out)))
+        return out.value
+
+    def upload(self, which, arr, first=0):
+        n = arr.shape[0]
+        self._check(self.lib.hexed_b200_upload(self.ctx, which, _addr(arr), first, n))
+
+    def download(self, which, arr, first=0):
+        self._check(self.lib.hexed_b200_download(self.ctx, which, _addr(arr), first, arr.shape[0]))
+        return arr
+
+    def upload_elements(self, elem_data, first_slot=0, n_slots=None, first_elem=0):
+        """elem_data: (n, n_slots_in_array, nq) in the reference's slot order, starting at `first_slot`"""
+        n, ns, nq = elem_data.shape
+        n_slots = ns if n_slots is None else n_slots
+        self._check(self.lib.hexed_b200_upload_elem_slots(self.ctx, _addr(elem_data), ns*nq, first_slot, n_slots, first_elem, n))
+
+    def download_elements(self, elem_data, first_slot=0, n_slots=None, first_elem=0):
+        n, ns, nq = elem_data.shape
+        n_slots = ns if n_slots is None else n_slots
+        self._check(self.lib.hexed_b200_download_elem_slots(self.ctx, _addr(elem_data), ns*nq, first_slot, n_slots, first_elem, n))
+        return elem_data
+
+    def sync_to_host(self, m=None):
+        """conservative sync-out: bring back everything the kernels may have written"""
+        m = m or self.mesh
+        self.download_elements(m.elem_data)
+        self.download(FACE_STATE, m.face_state)
+        if m.face_ldg is not None:
+            self.download(FACE_LDG, m.face_ldg)
+        self.download(UNCERT, m.uncert)
+        return m
+
+    def face_list(self, slots):
+        s = _i32(slots)
+        out = C.c_int(-1)
+        self._check(self.lib.hexed_b200_face_list_create(self.ctx, s.ctypes.data_as(ip), s.size, C.byref(out)))
+        return out.value
+
+    def face_list_download(self, list_id, dst, kind=0):
+        self._check(self.lib.hexed_b200_face_list_download(self.ctx, list_id, kind, _addr(dst)))
+        return dst
+
+    def face_list_upload(self, list_id, src, kind=0):
+        self._check(self.lib.hexed_b200_face_list_upload(self.ctx, list_id, kind, _addr(src)))
+
+    def synchronize(self):
+        self._check(self.lib.hexed_b200_synchronize(self.ctx))
+
+    def cuda_stream(self):
+        s = C.c_void_p()
+        self._check(self.lib.hexed_b200_cuda_stream(self.ctx, C.byref(s)))
+        return s.value or 0
+
+    # ---- mirrors of kernels.hpp ----
+    @staticmethod
+    def _opts(dt=1., i_stage=0, compute_residual=False, use_filter=False):
+        return Options(dt, int(i_stage), int(compute_residual), int(use_filter))
+
+    def compute_euler(self, **kw):
+        self._check(self.lib.hexed_b200_compute_euler(self.ctx, self._opts(**kw)))
+
+    def max_dt_euler(self, convective_safety, diffusive_safety, local_time, **kw):
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_max_dt_euler(self.ctx, self._opts(**kw), convective_safety, diffusive_safety, int(local_time), C.byref(out)))
+        return out.value
+
+    def compute_write_face(self):
+        self._check(self.lib.hexed_b200_compute_write_face(self.ctx))
+
+    def compute_prolong(self, scale=False, offset=False):
+        self._check(self.lib.hexed_b200_compute_prolong(self.ctx, int(scale), int(offset)))
+
+    def compute_restrict(self, scale=True, offset=False):
+        self._check(self.lib.hexed_b200_compute_restrict(self.ctx, int(scale), int(offset)))
+
+    def face_permutation(self, direction, data, restore=False):
+        d = (C.c_int*4)(*direction.as_list())
+        assert data.size == (self.n_dim + 2)*self.row_size**(self.n_dim - 1)
+        self._check(self.lib.hexed_b200_face_permutation(self.ctx, d, int(restore), data.ctypes.data_as(dp)))
+        return data
+
+    def face_permutation_table(self, direction):
+        d = (C.c_int*4)(*direction.as_list())
+        out = np.zeros(self.row_size**(self.n_dim - 1), np.int32)
+        self._check(self.lib.hexed_b200_face_permutation_table(self.ctx, d, out.ctypes.data_as(ip)))
+        return out
+
+    def neighbor_euler(self, deformed):
+        self._check(self.lib.hexed_b200_neighbor_euler(self.ctx, int(deformed)))
+
+    def local_euler(self, deformed, **kw):
+        self._check(self.lib.hexed_b200_local_euler(self.ctx, int(deformed), self._opts(**kw)))
+
+    def apply_state_bcs(self):
+        self._check(self.lib.hexed_b200_apply_state_bcs(self.ctx))
+
+    # ---- profiling side-contract ----
+    def set_timing(self, enabled):
+        self._check(self.lib.hexed_b200_set_timing(self.ctx, int(enabled)))
+
+    def kernel_stats(self):
+        buf = (KernelStat*16)()
+        n = C.c_int(0)
+        self._check(self.lib.hexed_b200_kernel_stats(self.ctx, buf, 16, C.byref(n)))
+        return [dict(name=buf[i].name.decode(), deformed=buf[i].deformed, work_units=buf[i].work_units,
+                     launches=buf[i].launches, device_seconds=buf[i].device_seconds) for i in range(n.value)]
+
+    def reset_stats(self):
+        self._check(self.lib.hexed_b200_reset_stats(self.ctx))
+
+    def launch_count(self):
+        return self.lib.hexed_b200_launch_count(self.ctx)

@@ -1,0 +1,169 @@
+/* hexed_b200.h -- C ABI of the B200-native implementation of Hexed's per-stage DG residual update.
+ *
+ * This is the drop-in boundary for the hot path behind `hexed::Solver::update`: the functions below are what a
+ * replacement of the reference's four kernel-driver files (src/kernels_convective.cpp, src/kernels_diffusive.cpp,
+ * src/kernels_max_dt.cpp, src/stabilizing_art_visc.cpp) binds to. Each compute entry point cites the reference
+ * declaration it replaces (paths relative to the Hexed source tree). The C++ adapter that implements the genuine
+ * `hexed::compute_euler(Kernel_mesh, Kernel_options)` signatures on top of this ABI is hexed_b200/host/ (see
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or a HEXED_B200_* error code, and
+ *     `hexed_b200_last_error` gives the message. The C++ adapter turns code 1 into
+ *     std::runtime_error("demand for invalid kernel") exactly like include/kernel_factory.hpp:114-116.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with HEXED_B200_NO_DEVICE.
+ *   - data pointers passed to upload/download calls may be host (pageable or pinned) or device memory.
+ *   - all floating point data is IEEE double; all index tables are 32-bit int.
+ *
+ * Flattened mesh (one "mesh epoch"; the reference's pointer graph include/connection.hpp:111-123 turned into slots)
+ *   nq = row_size^n_dim, nfq = row_size^(n_dim-1), nv = n_dim + 2
+ *   elements [0, n_car) Cartesian, [n_car, n_car + n_def) deformed (order of Kernel_mesh::car_elems / def_elems)
+ *   element "slots" of nq doubles, reference order (src/Element.cpp:114-142,187-189, src/Storage_params.cpp:32-35):
+ *       state nv | time-step scale 1 | bulk AV 1 | laplacian AV 1 | AV forcing 4 | advection row_size | residual cache max(nv,row_size)
+ *   face slot of element e face f (= 2*i_dim + sign): e*2*n_dim + f; connection-owned faces (boundary ghosts, hanging-node
+ *       mortar faces) use slots >= 2*n_dim*n_elem.  A face slot holds [nv][nfq] doubles per "kind":
+ *       kind 0 = `face(i, false)` / `state(side, false)`, kind 1 = the LDG half `(…, true)`,
+ *       kind 2 = the (n_dim+row_size)-variable view used by pde::Advection.
+ *   normal slot of deformed element d (= e - n_car) face f: d*2*n_dim + f, [n_dim][nfq] doubles
+ *       (`Kernel_element::kernel_face_normal`, unit normal when the reference returns nullptr, include/Spatial.hpp:366);
+ *       connection-owned normals (`Kernel_connection::normal()`) that alias no element face use later slots.
+ *   car_con[n][3] = {slot side 0, slot side 1, i_dim}
+ *   def_con[n][7] = {slot side 0, slot side 1, i_dim0, i_dim1, face_sign0, face_sign1, normal slot}
+ *       (`Connection_direction`, include/Kernel_connection.hpp:7-37; boundary connections are included, as in
+ *        src/Accessible_mesh.cpp:136-147)
+ *   ref_face[n][7] = {coarse slot, fine slot 0..3 (-1 = unused), stretch0, stretch1}   (include/Refined_face.hpp:9-15)
+ *
+ * Basis tables (argument `basis` of hexed_b200_create): packed doubles, rs = row_size, matrices row-major M[i][j]
+ *   node[rs] weight[rs] diff_mat[rs][rs] boundary[2][rs] orthogonal[rs][rs] filter[rs][rs] prolong[2][rs][rs]
+ *   restrict[2][rs][rs] min_eig_convection min_eig_diffusion quadratic_safety      (include/Basis.hpp:16-66)
+ */
+#ifndef HEXED_B200_H_
+#define HEXED_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hexed_b200_ctx hexed_b200_ctx;
+
+enum {
+  HEXED_B200_OK = 0,
+  HEXED_B200_INVALID_KERNEL = 1, /* n_dim not in 1..3 or row_size not in 2..8: "demand for invalid kernel" */
+  HEXED_B200_NO_DEVICE = 2,
+  HEXED_B200_CUDA_ERROR = 3,
+  HEXED_B200_BAD_ARGUMENT = 4,
+  HEXED_B200_NO_MESH = 5,
+  HEXED_B200_NOT_IMPLEMENTED = 6
+};
+
+/* element arrays addressable by hexed_b200_upload / hexed_b200_download (item = one element unless noted) */
+enum {
+  HEXED_B200_NOMINAL_SIZE = 0, /* [n_elem]                 Kernel_element::nominal_size() */
+  HEXED_B200_VERTEX_TSS = 1,   /* [n_elem][2^n_dim]        Kernel_element::vertex_time_step_scale(i) */
+  HEXED_B200_REF_NORMALS = 2,  /* [n_def][n_dim*n_dim][nq] Kernel_element::reference_level_normals() */
+  HEXED_B200_JAC_DET = 3,      /* [n_def][nq]              Kernel_element::jacobian_determinant() */
+  HEXED_B200_FACE_STATE = 4,   /* [n_face_slot][nv*nfq]    item = face slot */
+  HEXED_B200_FACE_LDG = 5,     /* [n_face_slot][nv*nfq]    item = face slot */
+  HEXED_B200_FACE_WIDE = 6,    /* [n_face_slot][(n_dim+row_size)*nfq] item = face slot */
+  HEXED_B200_NORMALS = 7,      /* [n_normal_slot][n_dim*nfq] item = normal slot */
+  HEXED_B200_UNCERT = 8        /* [n_elem]                 Kernel_element::uncert() */
+};
+
+enum { HEXED_B200_BC_FREESTREAM = 0, HEXED_B200_BC_COPY = 1, HEXED_B200_BC_NONPENETRATION = 2 };
+
+typedef struct {
+  int n_car, n_def;
+  int n_face_slot, n_normal_slot;
+  int n_car_con, n_def_con, n_ref;
+  const int* car_con;
+  const int* def_con;
+  const int* ref_face;
+} hexed_b200_mesh_desc;
+
+/* mirrors hexed::Kernel_options minus the stopwatches (include/kernels.hpp:11-20) */
+typedef struct {
+  double dt;
+  int i_stage;
+  int compute_residual;
+  int use_filter;
+} hexed_b200_options;
+
+/* the five doubles + flag of hexed::Transport_model (include/Transport_model.hpp:16-31) */
+typedef struct {
+  double const_val, ref_val, ref_temp, sqrt_ref_temp, temp_offset;
+  int is_viscous;
+} hexed_b200_transport;
+
+typedef void (*hexed_b200_callback)(void* user);
+
+/* per-kernel work-unit counters and device time, keeps the reference's Stopwatch_tree side-contract alive
+ * (include/kernel_factory.hpp:32-45); names match the reference's children: "neighbor", "local",
+ * "reconcile LDG flux", "compute time step", "prolong/restrict", "boundary conditions" */
+typedef struct {
+  const char* name;
+  int deformed;           /* 0 = cartesian tree, 1 = deformed tree, 2 = prolong/restrict / other */
+  long long work_units;
+  long long launches;
+  double device_seconds;  /* only accumulated while timing is enabled */
+} hexed_b200_kernel_stat;
+
+/* ---- life cycle ---- */
+int hexed_b200_device_count(int* count);
+int hexed_b200_create(hexed_b200_ctx** ctx, int device, int n_dim, int row_size, const double* basis, int n_basis);
+int hexed_b200_destroy(hexed_b200_ctx* ctx);
+const char* hexed_b200_last_error(const hexed_b200_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+int hexed_b200_synchronize(hexed_b200_ctx* ctx);
+int hexed_b200_cuda_stream(hexed_b200_ctx* ctx, void** stream); /* the cudaStream_t all kernels of this context run on */
+
+/* ---- mesh epoch: (re)builds the device mirror; previous mesh storage is released ---- */
+int hexed_b200_mesh_create(hexed_b200_ctx* ctx, const hexed_b200_mesh_desc* desc);
+int hexed_b200_upload(hexed_b200_ctx* ctx, int which, const double* src, size_t first_item, size_t n_items);
+int hexed_b200_download(hexed_b200_ctx* ctx, int which, double* dst, size_t first_item, size_t n_items);
+/* element slots in the reference's per-element layout; `elem_stride` = doubles between consecutive elements in the host array */
+int hexed_b200_upload_elem_slots(hexed_b200_ctx* ctx, const double* src, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem);
+int hexed_b200_download_elem_slots(hexed_b200_ctx* ctx, double* dst, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem);
+/* registered lists of face slots (e.g. all boundary faces) moved as one packed block [n][width(kind)] */
+int hexed_b200_face_list_create(hexed_b200_ctx* ctx, const int* slots, int n, int* list_id);
+int hexed_b200_face_list_download(hexed_b200_ctx* ctx, int list_id, int kind, double* dst);
+int hexed_b200_face_list_upload(hexed_b200_ctx* ctx, int list_id, int kind, const double* src);
+/* integer table the kernels use for `Face_permutation::match_faces` (include/Spatial.hpp:85-129): out[nfq] */
+int hexed_b200_face_permutation_table(hexed_b200_ctx* ctx, const int dir[4], int* out);
+
+/* ---- stage drivers ---- */
+/* void compute_euler(Kernel_mesh, Kernel_options)                                  include/kernels.hpp:22, src/kernels_convective.cpp:18 */
+int hexed_b200_compute_euler(hexed_b200_ctx* ctx, hexed_b200_options opts);
+/* double max_dt_euler(Kernel_mesh, Kernel_options, double, double, bool)           include/kernels.hpp:29, src/kernels_max_dt.cpp:14 */
+int hexed_b200_max_dt_euler(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time, double* dt);
+/* void compute_write_face(Kernel_mesh)                                             include/kernels.hpp:40, src/kernels_convective.cpp:43-46 */
+int hexed_b200_compute_write_face(hexed_b200_ctx* ctx);
+/* void compute_prolong(Kernel_mesh, bool scale, bool offset)                       include/kernels.hpp:36, src/kernels_convective.cpp:23-26 */
+int hexed_b200_compute_prolong(hexed_b200_ctx* ctx, int scale, int offset);
+/* void compute_restrict(Kernel_mesh, bool scale, bool offset)                      include/kernels.hpp:37, src/kernels_convective.cpp:28-31 */
+int hexed_b200_compute_restrict(hexed_b200_ctx* ctx, int scale, int offset);
+/* std::unique_ptr<Face_permutation_dynamic> face_permutation(int, int, Connection_direction, double*)
+ *                                                                                  include/kernels.hpp:39, src/kernels_convective.cpp:38-41
+ * applies match_faces (restore = 0) or restore (restore = 1) to nv variables of one face held in `data` */
+int hexed_b200_face_permutation(hexed_b200_ctx* ctx, const int dir[4], int restore, double* data);
+
+/* ---- individual kernels of the Euler sequence (for unit-level parity; deformed: 0 = Cartesian set, 1 = deformed set) ---- */
+int hexed_b200_neighbor_euler(hexed_b200_ctx* ctx, int deformed);   /* Spatial<..>::Neighbor   include/Spatial.hpp:613-704 */
+int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options opts); /* Spatial<..>::Local include/Spatial.hpp:326-509 */
+
+/* ---- device-resident ghost-state boundary conditions (Solver::apply_state_bcs, src/Solver.cpp:56-67) ---- */
+/* Freestream src/Boundary_condition.cpp:66-76 (params = nv doubles), Copy :450-453, Nonpenetration :301-327 */
+int hexed_b200_bc_create(hexed_b200_ctx* ctx, int kind, int n, const int* inside_slot, const int* ghost_slot,
+                         const int* normal_slot, const double* params, int n_params, int* bc_id);
+int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
+
+/* ---- profiling side-contract ---- */
+int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
+int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);
+int hexed_b200_reset_stats(hexed_b200_ctx* ctx);
+long long hexed_b200_launch_count(const hexed_b200_ctx* ctx); /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
