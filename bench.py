@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py -- DOF-stage-updates/s of the per-stage DG residual update (BASELINE.json metric).
+
+One "step" = one `Solver::update` iteration of the reference (src/Solver.cpp:846-868) on a synthetic 3-D box of
+row-size-6 hexes: max_dt (CFL reduction) followed by two stages, each = ghost-state boundary fill + compute_euler
+(neighbor flux, hanging-node restrict, local residual/update/face extrapolation, prolong). value = elements * 1080 DOF *
+2 stages * steps / device time. See DESIGN.md "Measurement" for the byte counts behind the roofline object.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n BOX] [--mesh deformed|cartesian]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DOF-stage-updates/sec"
+# fixed roofline denominators: doubles per element-stage, 3-D row size 6 Euler
+ALG_DOUBLES = {"deformed": {"stage": 11556, "local": 8424, "neighbor": 2484, "max_dt_half": 648},
+               "cartesian": {"stage": 8424, "local": 5616, "neighbor": 2160, "max_dt_half": 648}}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="box edge in elements per GPU (100 -> 1M elements)")
+    ap.add_argument("--mesh", default="deformed", choices=["deformed", "cartesian"])
+    ap.add_argument("--cpu-n", type=int, default=32, help="box edge of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650., "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_native_oracle():
+    """rebuild the oracle for this host's CPU (-march=native, row size 6 only); falls back to the portable build"""
+    try:
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        return "liboracle_native.so"
+    except Exception:
+        return "liboracle_fast.so"
+
+
+def cpu_reference_rate(args, steps, warmup):
+    """the CPU port of the reference kernels (oracle) on a bounded sample of the same workload, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hexed_b200 as hb
+    from hexed_b200 import mesh as M
+    from pyoracle import Oracle, EULER
+    from util import density_wave, freestream_state
+    lib = build_native_oracle()
+    o = Oracle(lib)
+    basis = hb.gauss_legendre(6)
+    n = args.cpu_n
+    m = M.box_mesh(3, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    o.compute_write_face(basis, m)
+
+    def step():
+        dt = o.max_dt(EULER, basis, m, 0.7, 0.7, False)
+        for stage in (0, 1):
+            o.apply_state_bcs(m)
+            o.compute_euler(basis, m, dt=dt, i_stage=stage)
+    for _ in range(warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    el = time.perf_counter() - t
+    rate = m.n_elem*1080*2*steps/el
+    return rate, el/steps, o.num_threads(), "%d^3 = %d %s elements, %d steps (max_dt + 2 stages), %s, OpenMP" % (n, m.n_elem, args.mesh, steps, lib)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, sec, cores, sample = cpu_reference_rate(args, args.steps, args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "DOF-stage/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": sec*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "synthetic 3D %s hex box, row_size 6, Euler; bounded CPU sample" % args.mesh, "sample": sample},
+           "cpu_baseline": {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": rate, "unit": "DOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import hexed_b200 as hb
+    from hexed_b200 import mesh as M
+    from hexed_b200.kernels import Device
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import freestream_state
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: hexed_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nd, rs, n = 3, 6, args.n
+    deformed = args.mesh == "deformed"
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd)
+    cuda = torch.device("cuda", local_rank)
+
+    # ---- synthetic mesh (geometry computed on the GPU, never leaves it) and initial state ----
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=fs, device=cuda,
+                   geometry_chunk=32768, keep_geometry_on_device=deformed, lean=True)
+    ne, nq, nv = m.n_elem, m.nq, m.nv
+    dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
+    # density wave initial condition, written from pinned host memory (the solver's state lives in host arrays in the reference)
+    pos = torch.as_tensor(m.qpoint_pos, device=cuda) if not torch.is_tensor(m.qpoint_pos) else m.qpoint_pos
+    phase = sum(torch.sin(2*np.pi*pos[:, d] + 0.3*d) for d in range(nd))/nd
+    rho = 1.2*(1 + 0.1*phase)
+    vel = [0.3*340.*(0.6 + 0.2*d) for d in range(nd)]
+    p = 101325.*(1 + 0.05*torch.cos(2*np.pi*pos[:, 0]))
+    st = torch.empty((ne, nv + 1, nq), dtype=torch.float64, device=cuda)
+    ke = 0
+    for d in range(nd):
+        st[:, d] = rho*vel[d]; ke = ke + 0.5*rho*vel[d]**2
+    st[:, nd] = rho; st[:, nd + 1] = p/0.4 + ke; st[:, nd + 2] = 1.
+    dev.upload_elements(st, 0, nv + 1)
+    del st, pos, phase, rho, p, ke
+    m.qpoint_pos = None; m.ref_normals = None; m.det = None; m.normals = None
+    torch.cuda.empty_cache()
+    dev.compute_write_face()
+    stream = torch.cuda.ExternalStream(dev.cuda_stream(), device=cuda)
+
+    def global_dt(dt):
+        if dist is None:
+            return dt
+        t = torch.tensor([dt], dtype=torch.float64, device=cuda)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def step():
+        dt = global_dt(dev.max_dt_euler(0.7, 0.7, False))
+        for stage in (0, 1):
+            dev.apply_state_bcs()
+            dev.compute_euler(dt=dt, i_stage=stage)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        dev.synchronize(); torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=cuda)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms*1e-3
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = dev.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sec = timed(step, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = dev.launch_count() - launches0
+    dof_stage = ne*nv*nq*2*args.steps*world
+    value = dof_stage/sec
+
+    # ---- per-kernel device time (separate pass with per-launch CUDA events on the kernels' stream) ----
+    dev.reset_stats(); dev.set_timing(True)
+    n_prof = max(2, min(args.steps, 4))
+    for _ in range(n_prof):
+        step()
+    dev.set_timing(False)
+    stats = dev.kernel_stats()
+    alg = ALG_DOUBLES[args.mesh]
+    peak, peak_src = peaks()
+    local_stat = [s for s in stats if s["name"] == "local" and s["deformed"] == int(deformed)][0]
+    local_sec = local_stat["device_seconds"]/max(local_stat["launches"], 1)
+    local_gbs = ne*alg["local"]*8/local_sec/1e9
+    shares = {("%s/%s" % (("car", "def", "shared")[s["deformed"]], s["name"])): s["device_seconds"]/n_prof for s in stats if s["launches"]}
+    stage_gbs = value/world*(alg["stage"]*8/1080.)/1e9
+
+    # ---- end to end through the public API with host buffers: boundary faces cross PCIe every stage ----
+    e2e = None
+    if not args.no_e2e:
+        bc = m.bcs[0]
+        inside_list, ghost_list = dev.face_list(bc["inside_slot"]), dev.face_list(bc["ghost_slot"])
+        nb, w = bc["inside_slot"].size, nv*m.nfq
+        h_in = torch.empty((nb, w), dtype=torch.float64, pin_memory=True)
+        h_gh = torch.empty((nb, w), dtype=torch.float64, pin_memory=True)
+        fs_t = torch.as_tensor(fs).repeat_interleave(m.nfq)
+
+        def step_e2e():
+            dt = global_dt(dev.max_dt_euler(0.7, 0.7, False))       # D2H: the time step
+            for stage in (0, 1):
+                dev.face_list_download(inside_list, h_in)             # D2H: inside boundary faces for the host Flow_bc
+                h_gh[:] = fs_t                                        # host boundary condition (Freestream::apply_state)
+                dev.face_list_upload(ghost_list, h_gh)                # H2D: ghost faces
+                dev.compute_euler(dt=dt, i_stage=stage)
+        for _ in range(2):
+            step_e2e()
+        sec_e2e = timed(step_e2e, args.steps)
+        e2e = {"value": dof_stage/sec_e2e, "unit": "DOF-stage/s", "h2d_bytes_per_step": 2*nb*w*8, "d2h_bytes_per_step": 2*nb*w*8 + 8,
+               "mode": "resident state; per stage the boundary faces go D2H, the host applies the ghost-state BC, ghost faces go H2D (pinned); dt D2H per step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, cs, cores, sample = cpu_reference_rate(args, args.cpu_steps, 1)
+            cpu = {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample}
+        except Exception as ex:  # the baseline is informative; never let it take the GPU number down
+            cpu = {"value": None, "unit": "DOF-stage/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "DOF-stage/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec/args.steps*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 3D %s hex box %d^3 = %d elements per GPU, row_size 6, Euler, freestream ghosts; "
+                                   "step = max_dt + 2 x (ghost BC fill + compute_euler)" % (args.mesh, n, ne),
+                       "elements_per_gpu": ne, "dof_per_element": nv*nq, "stages_per_step": 2,
+                       "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (ne*50e3/1e9),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent boxes (replicas) + NCCL allreduce(min) of dt; halo exchange not implemented yet" % world},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "local_euler_kernel<3,6,%s>" % ("true" if deformed else "false"),
+                         "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
+                         "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/1080.},
+                         "kernel_seconds_per_step": shares},
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    dev.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

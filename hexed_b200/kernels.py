@@ -154,7 +154,8 @@ class Device:
             self.upload(NORMALS, m.normals)
         if upload_elem_data and m.elem_data is not None:
             self.upload_elements(m.elem_data)
-        self.upload(FACE_STATE, m.face_state)
+        if m.face_state is not None:
+            self.upload(FACE_STATE, m.face_state)
         if m.face_ldg is not None:
             self.upload(FACE_LDG, m.face_ldg)
         self.bc_ids = []

@@ -44,7 +44,7 @@ class FlatMesh:
     """slot-indexed arrays + integer tables; see module docstring"""
 
     def __init__(self, n_dim, row_size, n_car, n_def, n_ghost=0, n_extra_normal=0, alloc_elem_data=True,
-                 with_ldg=False, with_wide=False):
+                 with_ldg=False, with_wide=False, alloc_faces=True):
         self.n_dim, self.row_size = n_dim, row_size
         self.n_car, self.n_def = n_car, n_def
         self.nq = row_size**n_dim
@@ -62,7 +62,7 @@ class FlatMesh:
         self.uncert = np.zeros(ne)
         self.ref_normals = np.zeros((n_def, n_dim*n_dim, self.nq))
         self.det = np.ones((n_def, self.nq))
-        self.face_state = np.zeros((self.n_face_slot, self.nv*self.nfq))
+        self.face_state = np.zeros((self.n_face_slot, self.nv*self.nfq)) if alloc_faces else None
         self.face_ldg = np.zeros((self.n_face_slot, self.nv*self.nfq)) if with_ldg else None
         self.face_wide = np.zeros((self.n_face_slot, (n_dim + row_size)*self.nfq)) if with_wide else None
         self.normals = np.zeros((self.n_normal_slot, n_dim, self.nfq))
@@ -206,13 +206,14 @@ def default_warp(x, amplitude):
 
 
 def box_mesh(n_dim, row_size, n, basis, deformed=False, warp_amplitude=0.1, bc_kind=BC_FREESTREAM, bc_params=None,
-             device=None, geometry_chunk=32768, with_ldg=False, keep_geometry_on_device=False):
+             device=None, geometry_chunk=32768, with_ldg=False, keep_geometry_on_device=False, lean=False):
     """`n^n_dim` elements on the unit box, all Cartesian or all deformed, with a boundary connection on every outer face.
 
     Interior connections run along each dimension between neighbours (direction {d, d}, {1, 0});
     boundary connections are deformed-type connections {d, d}, {sign, !sign} against a ghost face, as in the
     reference (src/Accessible_mesh.cpp:136-147, include/connection.hpp:346-366).
     If `keep_geometry_on_device`, the large metric arrays are returned as torch tensors on `device`.
+    `lean` skips the host allocation of element data and face storage (benchmark-sized meshes live on the device only).
     """
     nd, rs = n_dim, row_size
     E = n**nd
@@ -228,7 +229,8 @@ def box_mesh(n_dim, row_size, n, basis, deformed=False, warp_amplitude=0.1, bc_k
     b_elem, b_dim, b_sign = np.concatenate(b_elem), np.concatenate(b_dim), np.concatenate(b_sign)
     n_bc = b_elem.size
     n_car, n_def = (0, E) if deformed else (E, 0)
-    mesh = FlatMesh(nd, rs, n_car, n_def, n_ghost=n_bc, n_extra_normal=0 if deformed else n_bc, with_ldg=with_ldg)
+    mesh = FlatMesh(nd, rs, n_car, n_def, n_ghost=n_bc, n_extra_normal=0 if deformed else n_bc, with_ldg=with_ldg,
+                    alloc_elem_data=not lean, alloc_faces=not lean)
     mesh.nom_size[:] = h
     mesh.box_n = n
     mesh.elem_index = idx

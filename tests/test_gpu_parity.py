@@ -1,0 +1,136 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs. Run with -m gpu on a B200.
+Tolerances are the north-star's: state rel-L2 <= 1e-11, max_dt <= 1e-13 relative."""
+import numpy as np
+import pytest
+
+import hexed_b200 as hb
+from hexed_b200 import mesh as M
+from hexed_b200.kernels import Device
+from util import run_euler_pair, assert_euler_parity, density_wave, freestream_state, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 2), (1, 6), (2, 2), (2, 3), (2, 6), (2, 8), (3, 2), (3, 3), (3, 4), (3, 5), (3, 6), (3, 7), (3, 8)])
+def test_soup_all_orientations(oracle, gpu_lib, nd, rs):
+    """every connection direction, hanging faces with every stretch flag, car/def mix, unit-normal fallback, copy BCs"""
+    rng = np.random.default_rng(406)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=8, n_def=14, n_ref=6, with_ldg=False)
+    M.random_flow_state(m, rng)
+    out, ref, dts, launches = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=2)
+    assert launches > 0
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("local_time,use_filter", [(True, False), (False, True), (True, True)])
+def test_soup_options(oracle, gpu_lib, local_time, use_filter):
+    rng = np.random.default_rng(11)
+    basis = hb.gauss_legendre(6)
+    m = M.soup_mesh(3, 6, rng, with_ldg=False)
+    M.random_flow_state(m, rng)
+    out, ref, dts, _ = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=2, local_time=local_time, use_filter=use_filter)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 16, False), (2, 6, 8, True), (3, 6, 5, False), (3, 6, 5, True), (3, 4, 6, True)])
+def test_box(oracle, gpu_lib, nd, rs, n, deformed):
+    """BASELINE configs at oracle-friendly sizes: 2-D vortex-like Cartesian box (16x16, row size 6) and the 3-D row-size-6 box"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=5)
+    assert_euler_parity(out, ref, dts)
+
+
+def test_compute_residual_mode(oracle, gpu_lib):
+    from pyoracle import EULER
+    basis = hb.gauss_legendre(6)
+    m = M.box_mesh(3, 6, 3, basis, deformed=True, bc_kind=M.BC_COPY)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    dev = Device(3, 6, basis, lib_path=gpu_lib).load_mesh(m)
+    oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=1., i_stage=0, compute_residual=True)
+    dev.apply_state_bcs(); dev.compute_euler(dt=1., i_stage=0, compute_residual=True)
+    dev.sync_to_host(m)
+    assert rel_l2(m.cache(), ref.cache()) <= 1e-11
+    assert np.array_equal(m.state(), ref.state())  # the state itself must be untouched
+    with pytest.raises(RuntimeError):
+        dev.compute_euler(dt=1., i_stage=1, compute_residual=True)  # reference include/Spatial.hpp:323
+    dev.close()
+
+
+def test_write_face_prolong_restrict_standalone(oracle, gpu_lib):
+    rng = np.random.default_rng(3)
+    basis = hb.gauss_legendre(5)
+    for nd in (2, 3):
+        m = M.soup_mesh(nd, 5, rng, n_ref=8, with_ldg=True)
+        M.random_flow_state(m, rng)
+        ref = m.copy()
+        dev = Device(nd, 5, basis, lib_path=gpu_lib).load_mesh(m)
+        oracle.compute_write_face(basis, ref); dev.compute_write_face()
+        for scale, offset in [(False, False), (True, False), (True, True), (False, True)]:
+            oracle.compute_prolong(basis, ref, scale, offset); dev.compute_prolong(scale, offset)
+            oracle.compute_restrict(basis, ref, scale, offset); dev.compute_restrict(scale, offset)
+        dev.sync_to_host(m)
+        assert rel_l2(m.face_state, ref.face_state) <= 1e-13
+        assert rel_l2(m.face_ldg, ref.face_ldg) <= 1e-13
+        dev.close()
+
+
+def test_face_permutation_bit_exact(oracle, gpu_lib):
+    """the device permutation tables and the in-place oracle permutation must agree exactly, for every direction"""
+    from hexed_b200.tables import face_permutation
+    rng = np.random.default_rng(5)
+    for nd, rs in [(2, 6), (3, 4), (3, 6)]:
+        basis = hb.gauss_legendre(rs)
+        dev = Device(nd, rs, basis, lib_path=gpu_lib)
+        m = M.FlatMesh(nd, rs, 1, 0); dev.load_mesh(m)
+        for direction in M.all_directions(nd):
+            data = rng.standard_normal((nd + 2)*rs**(nd - 1))
+            a, b = data.copy(), data.copy()
+            oracle.face_permutation(nd, rs, nd + 2, direction, a)
+            dev.face_permutation(direction, b)
+            assert np.array_equal(a, b)
+            assert np.array_equal(dev.face_permutation_table(direction), face_permutation(nd, rs, direction))
+            oracle.face_permutation(nd, rs, nd + 2, direction, a, restore=True)
+            dev.face_permutation(direction, b, restore=True)
+            assert np.array_equal(a, data) and np.array_equal(b, data)
+        dev.close()
+
+
+def test_invalid_kernel_raises(gpu_lib):
+    with pytest.raises(RuntimeError, match="demand for invalid kernel"):
+        Device(3, 9, None, lib_path=gpu_lib)
+    with pytest.raises(RuntimeError, match="demand for invalid kernel"):
+        Device(4, 6, None, lib_path=gpu_lib)
+
+
+def test_full_size_properties(gpu_lib):
+    """size-independent checks at a large size the oracle cannot do in seconds (3-D deformed, row size 6, 48^3 = 110k elements):
+    a uniform freestream is preserved by a full step on the warped mesh (metric identities), mass and energy are conserved
+    to round-off for a non-trivial state with copy ghosts, and max_dt equals the minimum of the local time-step scale."""
+    import torch
+    nd, rs, n = 3, 6, 48
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=fs, device="cuda", geometry_chunk=16384)
+    st = m.state()
+    st[:] = fs[None, :, None]
+    dev = Device(nd, rs, basis, lib_path=gpu_lib).load_mesh(m)
+    dev.compute_write_face()
+    dt = dev.max_dt_euler(0.7, 0.7, False)
+    assert dt > 0
+    for stage in (0, 1):
+        dev.apply_state_bcs(); dev.compute_euler(dt=dt, i_stage=stage)
+    out = np.empty_like(st)
+    dev.download_elements(out, 0, nd + 2)
+    assert rel_l2(out, st) <= 1e-11  # freestream preservation
+    # max_dt vs local tss: global dt == min over qpoints of the local scale
+    dev.upload_elements(np.ascontiguousarray(st), 0, nd + 2)
+    dev.max_dt_euler(0.7, 0.7, True)
+    tss = np.empty((m.n_elem, 1, m.nq)); dev.download_elements(tss, nd + 2, 1)
+    assert abs(tss.min()/dt - 1) <= 1e-13
+    dev.close()
