@@ -101,11 +101,11 @@ def build_native_oracle():
 
 def cpu_reference_rate(args, steps, warmup):
     """the CPU port of the reference kernels (oracle) on a bounded sample of the same workload, all host threads"""
-    sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hexed_b200 as hb
     from hexed_b200 import mesh as M
     from pyoracle import Oracle, EULER
-    from util import density_wave, freestream_state
+    from hexed_b200.cases import density_wave, freestream_state
     lib = build_native_oracle()
     o = Oracle(lib)
     basis = hb.gauss_legendre(6)
@@ -152,8 +152,7 @@ def main():
     import hexed_b200 as hb
     from hexed_b200 import mesh as M
     from hexed_b200.kernels import Device
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from util import freestream_state
+    from hexed_b200.cases import freestream_state
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():

@@ -5,5 +5,5 @@ This package is the thin host side used by the tests and the benchmark: basis ta
 ctypes binding that mirrors the reference's `kernels.hpp` entry points. There is no CPU fallback: if the
 library is missing or no GPU is present, compute calls raise.
 """
-from . import basis, tables, mesh  # noqa: F401
+from . import basis, tables, mesh, cases  # noqa: F401
 from .basis import gauss_legendre, gauss_lobatto  # noqa: F401

@@ -299,6 +299,13 @@ int hexed_b200_download(hexed_b200_ctx* c, int which, double* dst, size_t first,
   return 0;
 }
 
+static bool is_device_ptr(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 static int move_slots(hexed_b200_ctx* c, double* host, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem, bool up)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
@@ -311,7 +318,10 @@ static int move_slots(hexed_b200_ctx* c, double* host, size_t elem_stride, int f
     int rc = slot_array(c, first_slot + s, &base, &dstride, up); if (rc) return rc;
     double* h = host + (size_t)s*c->nq;
     if (!base) { // array never allocated (or slot not mirrored): reads as zero, writes are dropped
-      if (!up) HB_CUDA(c, cudaMemset2DAsync(h, sizeof(double)*elem_stride, 0, sizeof(double)*c->nq, n_elem, c->stream));
+      if (!up) {
+        if (is_device_ptr(h)) HB_CUDA(c, cudaMemset2DAsync(h, sizeof(double)*elem_stride, 0, sizeof(double)*c->nq, n_elem, c->stream));
+        else for (int e = 0; e < n_elem; ++e) std::memset(h + (size_t)e*elem_stride, 0, sizeof(double)*c->nq);
+      }
       continue;
     }
     double* dptr = base + (size_t)first_elem*dstride;

@@ -139,6 +139,9 @@ inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
 template <class F> cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeUnregistered; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { *a = cudaPointerAttributes(); return cudaSuccess; }
 
 #define HB_LAUNCH(kern, grid, block, smem, stream, ...) hb_emu::launch(dim3(grid), dim3(block), [&] { kern(__VA_ARGS__); })
 #define HB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(hb_emu::g_dyn_smem)

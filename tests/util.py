@@ -5,6 +5,7 @@ import hexed_b200 as hb
 from hexed_b200 import mesh as M
 from hexed_b200.kernels import Device
 from pyoracle import EULER
+from hexed_b200.cases import density_wave, freestream_state  # noqa: F401
 
 STATE_TOL = 1e-11   # north-star: state after N stages within relative L2 <= 1e-11 of the reference CPU kernels
 MAX_DT_TOL = 1e-13  # north-star: max_dt within 1e-13 relative
@@ -43,27 +44,3 @@ def assert_euler_parity(out, ref, dts):
     assert rel_l2(out.cache(), ref.cache()) <= 1e-10  # cancellation-prone residual difference, looser by design
     assert rel_l2(out.face_state, ref.face_state) <= STATE_TOL
     assert rel_l2(out.tss(), ref.tss()) <= MAX_DT_TOL
-
-
-def density_wave(mesh, basis, mach=0.3, amplitude=0.1):
-    """smooth admissible initial condition on the box meshes: travelling density wave (cf. reference test/test_Solver.cpp:103-124)"""
-    nd = mesh.n_dim
-    x = np.asarray(mesh.qpoint_pos)
-    phase = sum(np.sin(2*np.pi*x[:, d] + 0.3*d) for d in range(nd))/nd
-    rho = 1.2*(1 + amplitude*phase)
-    vel = [mach*340.*(0.6 + 0.2*d) for d in range(nd)]
-    p = 101325.*(1 + 0.05*np.cos(2*np.pi*x[:, 0]))
-    st = mesh.state()
-    ke = 0
-    for d in range(nd):
-        st[:, d] = rho*vel[d]
-        ke = ke + 0.5*rho*vel[d]**2
-    st[:, nd] = rho
-    st[:, nd + 1] = p/0.4 + ke
-    return mesh
-
-
-def freestream_state(nd, mach=0.3):
-    rho, p = 1.2, 101325.
-    vel = [mach*340.*(0.6 + 0.2*d) for d in range(nd)]
-    return np.array([rho*v for v in vel] + [rho, p/0.4 + 0.5*rho*sum(v*v for v in vel)])
