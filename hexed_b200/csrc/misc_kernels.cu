@@ -10,7 +10,7 @@ namespace hb {
  * arithmetic, so one launch covers every element. */
 struct MaxDtArgs
 {
-  const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; double* block_min;
+  const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; unsigned long long* global_min;
 };
 
 template <int ND, int RS>
@@ -39,10 +39,12 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
     #pragma unroll
     for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
     p.inv_mass = 1./p.s[ND];
-    const double scale = p.char_speed()/a.max_cfl_c/spacing;
-    if (a.is_local) a.tss[(size_t)e*nq + q] = 1./scale;
-    else { a.tss[(size_t)e*nq + q] = 1.; val = fmin(val, 1./scale); }
+    // 1/scale with scale = char_speed/max_cfl/spacing (Spatial.hpp:808-822), rearranged to a single division
+    const double local_dt = a.max_cfl_c*spacing/p.char_speed();
+    if (a.is_local) a.tss[(size_t)e*nq + q] = local_dt;
+    else { a.tss[(size_t)e*nq + q] = 1.; val = local_dt; }
   }
+  if (a.is_local) return;
   #pragma unroll
   for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
   if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
@@ -50,22 +52,8 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
   if (threadIdx.x == 0) {
     double m = warp_min[0];
     for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
-    a.block_min[blockIdx.x] = m;
-  }
-}
-
-__global__ void __launch_bounds__(256) reduce_min_kernel(const double* in, int n, double* out)
-{
-  __shared__ double warp_min[8];
-  double val = DBL_MAX;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) val = fmin(val, in[i]);
-  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
-  if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = warp_min[0];
-    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
-    *out = m;
+    // time steps are positive, so the IEEE bit patterns order like unsigned integers
+    atomicMin(a.global_min, (unsigned long long)__double_as_longlong(m));
   }
 }
 
@@ -79,21 +67,15 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)c->n_elem*ipow(RS, ND);
     const int grid = (int)((total + 255)/256);
-    if ((size_t)grid > c->block_min_cap) {
-      if (c->block_min) cudaFree(c->block_min);
-      HB_CUDA(c, cudaMalloc(&c->block_min, sizeof(double)*grid));
-      c->block_min_cap = grid;
-    }
     MaxDtArgs a;
     a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
     a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9) * safety (Spatial.hpp:777)
-    a.is_local = local_time; a.block_min = c->block_min;
+    a.is_local = local_time; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
+    if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream)); // 0x7f7f... = 1.4e306
     { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
     if (local_time) { *dt = 1.; return 0; }
-    HB_LAUNCH(reduce_min_kernel, 1, 256, 0, c->stream, c->block_min, grid, c->d_scalar);
-    count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(c, cudaStreamSynchronize(c->stream));
     *dt = *c->h_scalar;
