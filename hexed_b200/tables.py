@@ -156,3 +156,24 @@ def row_qpoint(n_dim, row_size, i_dim, i_fq, i_node):
     stride = row_size**(n_dim - 1 - i_dim)
     i_outer, i_inner = divmod(i_fq, stride)
     return i_outer*stride*row_size + i_inner + i_node*stride
+
+
+def hanging_vertex_match(n_dim, vertex_vals, i_dim, is_positive, stretch=(False, False)):
+    """`Hanging_vertex_matcher::match` on plain arrays (reference src/Hanging_vertex_matcher.cpp:13-41).
+
+    vertex_vals: (n_fine_elem, 2^n_dim) array of per-vertex values of the fine elements, modified in place: the values on
+    face (i_dim, is_positive) are replaced by the multilinear interpolant of the coarse-face corner values."""
+    vals = np.asarray(vertex_vals)
+    n_vert = 2**(n_dim - 1)
+    inds = hanging_vertex_face_inds(n_dim, i_dim, is_positive)
+    corner = np.array([vals[stretched_ind(n_dim, i, stretch), inds[i]] for i in range(n_vert)], dtype=np.float64)
+    interp = np.array([[1., 0.], [.5, .5], [0., 1.]])
+    cube = corner.reshape((2,)*(n_dim - 1))
+    for axis in range(n_dim - 1):
+        cube = np.moveaxis(np.tensordot(interp, cube, axes=([1], [axis])), 0, axis)
+    flat = cube.reshape(-1)
+    table = hanging_vertex_interp_inds(n_dim, vals.shape[0], stretch)
+    for i_elem in range(vals.shape[0]):
+        for i_vert in range(n_vert):
+            vals[i_elem, inds[i_vert]] = flat[table[i_elem][i_vert]]
+    return vals
