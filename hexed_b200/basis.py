@@ -42,6 +42,7 @@ class Basis:
     min_eig_convection: float
     min_eig_diffusion: float
     quadratic_safety: float
+    legendre_node: np.ndarray = None  # nodes of Gauss_legendre(row_size): pde::Advection uses them whatever the basis (include/pde.hpp:281)
 
     def max_cfl(self):
         """reference src/Basis.cpp:6-9"""
@@ -58,6 +59,7 @@ class Basis:
             self.node, self.weight, self.diff_mat.ravel(), self.boundary.ravel(), self.orthogonal.ravel(),
             self.filter.ravel(), self.prolong.ravel(), self.restrict.ravel(),
             [self.min_eig_convection, self.min_eig_diffusion, self.quadratic_safety],
+            self.legendre_node if self.legendre_node is not None else self.node,
         ]).astype(np.float64)
 
 
@@ -74,6 +76,7 @@ def _make(name, row_size):
         restrict=_arr(t["restrict"]) if "restrict" in t else zero,
         min_eig_convection=float(t["min_eig_convection"]), min_eig_diffusion=float(t["min_eig_diffusion"]),
         quadratic_safety=float(_tables()["quadratic_safety"][name]),
+        legendre_node=_arr(_tables()["Gauss_legendre"][str(rs)]["node"]),
     )
 
 

@@ -90,8 +90,8 @@ static int slot_array(hexed_b200_ctx* c, int slot, double** base, size_t* elem_s
   else if (slot < nv + 7 + rs) { rc = lazy(&c->adv, (size_t)rs*nq); *base = c->adv ? c->adv + (size_t)(slot - nv - 7)*nq : nullptr; *elem_stride = (size_t)rs*nq; }
   else {
     const int k = slot - (nv + 7 + rs);
-    if (k >= nv) { *base = nullptr; *elem_stride = 0; return 0; } // cache slots beyond nv are only used by pde::Advection (not mirrored yet)
-    *base = c->cache + (size_t)k*nq; *elem_stride = (size_t)nv*nq;
+    const int cs = nv > rs ? nv : rs; // residual cache: max(n_var, row_size) slots (reference src/Storage_params.cpp:32-35)
+    *base = c->cache + (size_t)k*nq; *elem_stride = (size_t)cs*nq;
   }
   return rc;
 }
@@ -117,7 +117,7 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   *out = nullptr;
   if (n_dim < 1 || n_dim > 3 || row_size < 2 || row_size > MAX_RS) return fail(nullptr, HEXED_B200_INVALID_KERNEL, "demand for invalid kernel");
   const int rs = row_size;
-  const int expect = 2*rs + 3*rs*rs + 2*rs + 4*rs*rs + 3;
+  const int expect = 2*rs + 3*rs*rs + 2*rs + 4*rs*rs + 3 + rs;
   if (n_basis != expect) return fail(nullptr, HEXED_B200_BAD_ARGUMENT, "basis table has the wrong length");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= device || device < 0)
@@ -138,6 +138,7 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   for (int h = 0; h < 2; ++h) for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->transfer.prolong[h][i][j] = *p++;
   for (int h = 0; h < 2; ++h) for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) c->transfer.restrict_[h][i][j] = *p++;
   c->min_eig_conv = *p++; c->min_eig_diff = *p++; c->quad_safety = *p++;
+  for (int i = 0; i < rs; ++i) c->gl_node[i] = *p++;
   for (int i = 0; i < rs; ++i) {
     // lift = diag(1/w) boundary^T diag(-1, +1)   (reference include/Derivative.hpp:20-29)
     const double inv_w = 1./c->weight[i];
@@ -151,8 +152,8 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j)
     c->ops.dfull[i][j] = diff[i][j] - (c->ops.lift[i][0]*bnd[0][j] + c->ops.lift[i][1]*bnd[1][j]);
   static const char* names[ST_COUNT] = {"neighbor", "neighbor", "local", "local", "compute time step", "compute time step",
-                                        "prolong/restrict", "boundary conditions", "write face"};
-  static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2};
+                                        "prolong/restrict", "boundary conditions", "write face", "reconcile LDG flux", "reconcile LDG flux"};
+  static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2, 0, 1};
   for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].name = names[i]; c->stats[i].deformed = trees[i]; }
   int rc = check(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
@@ -181,7 +182,7 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_mesh(c);
-  dev_free(c->perm); dev_free(c->block_min); dev_free(c->d_scalar); dev_free(c->d_face_scratch);
+  dev_free(c->perm); dev_free(c->d_scalar); dev_free(c->d_face_scratch);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -210,7 +211,7 @@ int hexed_b200_mesh_create(hexed_b200_ctx* c, const hexed_b200_mesh_desc* d)
   int rc = 0;
   if (!rc) rc = dev_alloc(c, &c->state, ne*nv*nq);
   if (!rc) rc = dev_alloc(c, &c->tss, ne*nq);
-  if (!rc) rc = dev_alloc(c, &c->cache, ne*nv*nq);
+  if (!rc) rc = dev_alloc(c, &c->cache, ne*(nv > (size_t)c->rs ? nv : (size_t)c->rs)*nq);
   if (!rc) rc = dev_alloc(c, &c->nom, ne);
   if (!rc) rc = dev_alloc(c, &c->vtss, ne*c->n_vert);
   if (!rc) rc = dev_alloc(c, &c->uncert, ne);
@@ -420,6 +421,153 @@ int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
 
 int hexed_b200_max_dt_euler(hexed_b200_ctx* c, hexed_b200_options, double safety_conv, double, int local_time, double* dt)
 { return launch_max_dt_euler(c, safety_conv, local_time, dt); }
+
+/* ---- generic PDEs ---- */
+static const GenericOps* generic_ops(int pde)
+{
+  switch (pde) {
+    case 1: return &generic_ops_pde1;
+    case 2: return &generic_ops_pde2;
+    case 3: return &generic_ops_pde3;
+    case 4: return &generic_ops_pde4;
+  }
+  return nullptr;
+}
+
+static PdeParams make_params(hexed_b200_ctx* c, int pde, hexed_b200_transport visc, hexed_b200_transport cond, double p0, double p1)
+{
+  PdeParams pp;
+  std::memset(&pp, 0, sizeof(pp));
+  pp.visc = visc; pp.cond = cond; pp.p0 = p0; pp.p1 = p1;
+  // pde::Advection uses the nodes of Gauss_legendre(row_size) mapped to [-1, 1] whatever the solution basis is (include/pde.hpp:281)
+  for (int i = 0; i < c->rs; ++i) pp.adv_nodes[i] = 2*c->gl_node[i] - 1;
+  (void)pde;
+  return pp;
+}
+
+static const hexed_b200_transport no_transport = {0., 0., 1., 1., 1., 0}; // Transport_model::inviscid (include/Transport_model.hpp:40)
+
+static int n_extrap_of(hexed_b200_ctx* c, int pde) { return pde == 2 ? c->nd + c->rs : pde == 3 ? 3 : c->nv; }
+
+/* reference src/kernels_convective.cpp:8-16 */
+static int convection_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, const PdeParams& pp)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const GenericOps* g = generic_ops(pde);
+  const int kind = pde == 2 ? 2 : 0, ne = n_extrap_of(c, pde);
+  int rc;
+  if ((rc = g->neighbor(c, 0, pp, false))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false))) return rc;
+  if ((rc = launch_restrict(c, kind, ne, 1))) return rc;
+  if ((rc = g->local(c, 0, o, pp, false))) return rc;
+  if ((rc = g->local(c, 1, o, pp, false))) return rc;
+  if ((rc = launch_prolong(c, kind, ne, 0))) return rc;
+  return 0;
+}
+
+/* reference src/kernels_diffusive.cpp:8-26 */
+static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, const PdeParams& pp, hexed_b200_callback flux_bc, void* user)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const GenericOps* g = generic_ops(pde);
+  const int ne = n_extrap_of(c, pde);
+  int rc;
+  if ((rc = g->neighbor(c, 0, pp, false))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false))) return rc;
+  if ((rc = launch_restrict(c, 0, ne, 1))) return rc;
+  if ((rc = launch_restrict(c, 1, ne, 0))) return rc;
+  if ((rc = g->local(c, 0, o, pp, false))) return rc;
+  if ((rc = g->local(c, 1, o, pp, false))) return rc;
+  if (!o.i_stage) {
+    if ((rc = launch_prolong(c, 1, ne, 1))) return rc;
+    if (flux_bc) flux_bc(user); // host callback = Solver::apply_flux_bcs; it may enqueue device work on this context's stream
+    if ((rc = g->neighbor(c, 0, pp, true))) return rc;
+    if ((rc = g->neighbor(c, 1, pp, true))) return rc;
+    if ((rc = launch_restrict(c, 1, ne, 1))) return rc;
+    if ((rc = g->local(c, 0, o, pp, true))) return rc;
+    if ((rc = g->local(c, 1, o, pp, true))) return rc;
+  }
+  if ((rc = launch_prolong(c, 0, ne, 0))) return rc;
+  return 0;
+}
+
+int hexed_b200_compute_advection(hexed_b200_ctx* c, hexed_b200_options o, double advect_length)
+{ return convection_stage(c, 2, o, make_params(c, 2, no_transport, no_transport, advect_length, 0.)); }
+
+int hexed_b200_compute_navier_stokes(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
+                                     hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{ return diffusion_stage(c, 1, o, make_params(c, 1, visc, therm_cond, 0., 0.), flux_bc, user); }
+
+int hexed_b200_compute_smooth_av(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user, double diff_time, double chebyshev_step)
+{ return diffusion_stage(c, 3, o, make_params(c, 3, no_transport, no_transport, diff_time, chebyshev_step), flux_bc, user); }
+
+int hexed_b200_compute_fix_therm_admis(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user)
+{ return diffusion_stage(c, 4, o, make_params(c, 4, no_transport, no_transport, 0., 0.), flux_bc, user); }
+
+int hexed_b200_max_dt_navier_stokes(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time,
+                                    hexed_b200_transport visc, hexed_b200_transport therm_cond, double* dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(1)->max_dt(c, make_params(c, 1, visc, therm_cond, 0., 0.), sc, sd, local_time, dt);
+}
+
+int hexed_b200_max_dt_advection(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double advect_length, double* dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(2)->max_dt(c, make_params(c, 2, no_transport, no_transport, advect_length, 0.), sc, sd, local_time, dt);
+}
+
+int hexed_b200_max_dt_smooth_av(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double* dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(3)->max_dt(c, make_params(c, 3, no_transport, no_transport, 1., 1.), sc, sd, local_time, dt); // src/kernels_max_dt.cpp:20
+}
+
+int hexed_b200_max_dt_fix_therm_admis(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double* dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(4)->max_dt(c, make_params(c, 4, no_transport, no_transport, 0., 0.), sc, sd, local_time, dt);
+}
+
+int hexed_b200_compute_write_face_advection(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(2)->write_face(c, make_params(c, 2, no_transport, no_transport, 1., 0.)); // src/kernels_convective.cpp:48-51
+}
+
+int hexed_b200_compute_write_face_smooth_av(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  return generic_ops(3)->write_face(c, make_params(c, 3, no_transport, no_transport, 1., 1.)); // src/kernels_convective.cpp:53-56
+}
+
+int hexed_b200_compute_prolong_advection(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->face_wide) { int rc = dev_alloc(c, &c->face_wide, (size_t)c->n_face_slot*(c->nd + c->rs)*c->nfq); if (rc) return rc; }
+  return launch_prolong(c, 2, c->nd + c->rs, 0); // src/kernels_convective.cpp:33-36
+}
+
+int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* c, double char_speed) { return launch_stab_art_visc(c, char_speed); }
+
+int hexed_b200_apply_flux_bcs(hexed_b200_ctx* c) { return launch_flux_bcs(c); }
+
+/* individual kernels of a generic PDE, for unit-level parity: which = 0 Neighbor, 1 Local, 2 Neighbor_reconcile, 3 Reconcile_ldg_flux */
+int hexed_b200_pde_kernel(hexed_b200_ctx* c, int pde, int which, int deformed, hexed_b200_options o,
+                          hexed_b200_transport visc, hexed_b200_transport therm_cond, double p0, double p1)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const GenericOps* g = generic_ops(pde);
+  if (!g) return fail(c, HEXED_B200_BAD_ARGUMENT, "pde must be 1 (Navier-Stokes), 2 (advection), 3 (smooth AV) or 4 (fix therm admis)");
+  const PdeParams pp = make_params(c, pde, visc, therm_cond, p0, p1);
+  switch (which) {
+    case 0: return g->neighbor(c, deformed, pp, false);
+    case 1: return g->local(c, deformed, o, pp, false);
+    case 2: return g->neighbor(c, deformed, pp, true);
+    case 3: return g->local(c, deformed, o, pp, true);
+  }
+  return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown kernel id");
+}
 
 int hexed_b200_compute_write_face(hexed_b200_ctx* c) { return launch_write_face(c); }
 

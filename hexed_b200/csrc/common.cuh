@@ -35,7 +35,16 @@ struct Stat
 {
   const char* name; int deformed; long long work_units = 0; long long launches = 0; double seconds = 0;
 };
-enum { ST_NEIGHBOR_CAR, ST_NEIGHBOR_DEF, ST_LOCAL_CAR, ST_LOCAL_DEF, ST_MAX_DT_CAR, ST_MAX_DT_DEF, ST_PR, ST_BC, ST_WRITE_FACE, ST_COUNT };
+enum { ST_NEIGHBOR_CAR, ST_NEIGHBOR_DEF, ST_LOCAL_CAR, ST_LOCAL_DEF, ST_MAX_DT_CAR, ST_MAX_DT_DEF, ST_PR, ST_BC, ST_WRITE_FACE,
+       ST_RECONCILE_CAR, ST_RECONCILE_DEF, ST_COUNT };
+
+/* scalar parameters of every PDE, passed by value to the generic kernels (pde.cuh) */
+struct PdeParams
+{
+  hexed_b200_transport visc, cond; // Navier-Stokes
+  double p0, p1;                   // advection: advect_length | smooth_av: diff_time, chebyshev_step
+  double adv_nodes[MAX_RS];        // advection: Gauss-Legendre nodes mapped to [-1, 1] (reference include/pde.hpp:281)
+};
 
 struct FaceList { int n = 0; int* d_slots = nullptr; double* d_buf = nullptr; size_t buf_doubles = 0; };
 struct Bc { int kind; int n; int *inside = nullptr, *ghost = nullptr, *normal = nullptr; double* params = nullptr; int n_params = 0; };
@@ -50,6 +59,7 @@ struct hexed_b200_ctx
   hb::FilterOp filt;
   hb::TransferOps transfer;
   double weight[hb::MAX_RS];
+  double gl_node[hb::MAX_RS]; // nodes of Gauss_legendre(row_size), used by pde::Advection whatever the solution basis
   double orthogonal[hb::MAX_RS][hb::MAX_RS];
   double min_eig_conv = 0, min_eig_diff = 0, quad_safety = 0;
   cudaStream_t stream = nullptr;
@@ -65,7 +75,6 @@ struct hexed_b200_ctx
   int *perm = nullptr;     // [36][nfq] face permutation tables, indexed by dir code
   std::vector<int> h_perm;
   // scratch
-  double* block_min = nullptr; size_t block_min_cap = 0;
   double* d_scalar = nullptr; double* h_scalar = nullptr;
   double* d_face_scratch = nullptr;
   std::vector<hb::FaceList> lists;
@@ -118,6 +127,18 @@ int launch_bcs(hexed_b200_ctx* c);
 int launch_gather_faces(hexed_b200_ctx* c, const double* src, int width, const int* d_slots, int n, double* dst);
 int launch_scatter_faces(hexed_b200_ctx* c, double* dst, int width, const int* d_slots, int n, const double* src);
 int launch_permute_face(hexed_b200_ctx* c, double* d_data, int n_var, int code, int restore);
+
+/* per-PDE launchers of the generic kernels (generic_part.cu, one translation unit per PDE) */
+struct GenericOps
+{
+  int (*neighbor)(hexed_b200_ctx*, int deformed, const PdeParams&, bool reconcile);
+  int (*local)(hexed_b200_ctx*, int deformed, hexed_b200_options, const PdeParams&, bool reconcile);
+  int (*write_face)(hexed_b200_ctx*, const PdeParams&);
+  int (*max_dt)(hexed_b200_ctx*, const PdeParams&, double safety_conv, double safety_diff, int local_time, double* dt);
+};
+extern const GenericOps generic_ops_pde1, generic_ops_pde2, generic_ops_pde3, generic_ops_pde4;
+int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
+int launch_flux_bcs(hexed_b200_ctx* c);
 
 /* run-time (n_dim, row_size) -> compile-time dispatch; the analogue of the reference's kernel_factory
  * (include/kernel_factory.hpp:64-119). F is a generic lambda taking two integral_constants. */

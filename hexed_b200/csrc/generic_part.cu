@@ -1,0 +1,739 @@
+/* generic_part.cu -- PDE-generic kernels (one translation unit per PDE: compile with -DHB_PDE=<1..4>).
+ *
+ * Covers the reference kernels for pde::Navier_stokes<true>, pde::Advection, pde::Smooth_art_visc and pde::Fix_therm_admis:
+ *   Spatial<Pde, is_deformed>::Neighbor            include/Spatial.hpp:613-704   (LLF flux and/or LDG average state)
+ *   Spatial<Pde, is_deformed>::Local               include/Spatial.hpp:326-509   (gradient, convective/diffusive flux, source, update)
+ *   Spatial<Pde, is_deformed>::Neighbor_reconcile  include/Spatial.hpp:716-759
+ *   Spatial<Pde, is_deformed>::Reconcile_ldg_flux  include/Spatial.hpp:543-594
+ *   Spatial<Pde, is_deformed>::Max_dt              include/Spatial.hpp:784-828
+ *   Spatial<Pde, false>::Write_face                include/Spatial.hpp:41-70
+ * The inviscid Euler path has its own kernels (local_euler.cu, neighbor_euler.cu); these share their structure:
+ * one thread per quadrature point, line contractions through shared memory, connection tables for the faces.
+ */
+#include "pde.cuh"
+
+#ifndef HB_PDE
+#error "compile with -DHB_PDE=<1..4>"
+#endif
+
+namespace hb {
+namespace {
+
+struct GArgs
+{
+  ElemData ed;
+  const double* nom; const double* refn; const double* det; const double* normals; const double* vtss;
+  double* faces; double* faces_ldg; int face_width;
+  const int* con; const int* perm; int n_con;
+  int elem_begin, elem_end, n_car;
+  double update; int stage, compute_residual, use_filter;
+  double max_cfl_c, max_cfl_d; int is_local; unsigned long long* global_min;
+  PdeParams pp;
+};
+
+template <int ND, int RS> struct Line
+{
+  int stride, node, base, fq;
+  __device__ Line(int d, int q)
+  {
+    stride = 1;
+    for (int i = 0; i < ND - 1 - d; ++i) stride *= RS;
+    node = (q/stride) % RS;
+    base = q - node*stride;
+    fq = (q/(stride*RS))*stride + q % stride;
+  }
+};
+
+/* ---------------- Neighbor ---------------- */
+template <int ND, int RS, class P, bool DEF>
+__global__ void __launch_bounds__(128)
+g_neighbor_kernel(GArgs a)
+{
+  constexpr int nfq = ipow(RS, ND - 1), ne = P::n_extrap, nu = P::n_update, wl = (ND + 2)*nfq;
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int con = (int)(gid/nfq), q0 = (int)(gid % nfq);
+  if (con >= a.n_con) return;
+  const int* tab = a.con + (size_t)con*4;
+  const int slot0 = tab[0], slot1 = tab[1];
+  int q1 = q0;
+  double n[ND];
+  double sign0 = 1., sign1 = 1.;
+  if constexpr (DEF) {
+    const int code = tab[2];
+    q1 = a.perm[code*nfq + q0];
+    sign0 = ((code/9) % 2) ? 1. : -1.;   // flip_normal(0) = (face_sign[0] == 0)   include/Kernel_connection.hpp:19
+    sign1 = ((code/18) % 2) ? -1. : 1.;  // flip_normal(1) = (face_sign[1] == 1)
+    const double* nr = a.normals + (size_t)tab[3]*ND*nfq;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) n[d] = sign0*nr[d*nfq + q0];
+  } else {
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) n[d] = (d == tab[2]) ? 1. : 0.;
+  }
+  double* f0 = a.faces + (size_t)slot0*a.face_width + q0;
+  double* f1 = a.faces + (size_t)slot1*a.face_width + q1;
+  double x0[ne], x1[ne];
+  #pragma unroll
+  for (int v = 0; v < ne; ++v) { x0[v] = f0[v*nfq]; x1[v] = f1[v*nfq]; }
+  if constexpr (P::has_diffusion) {
+    double* l0 = a.faces_ldg + (size_t)slot0*wl + q0;
+    double* l1 = a.faces_ldg + (size_t)slot1*wl + q1;
+    #pragma unroll
+    for (int v = 0; v < ne; ++v) { const double avg = .5*(x0[v] + x1[v]); l0[v*nfq] = avg; l1[v*nfq] = avg; }
+  }
+  if constexpr (P::has_convection) {
+    typename P::template Comp<1> c0, c1;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) { c0.normal[d][0] = n[d]; c1.normal[d][0] = n[d]; }
+    c0.from_extrap(x0); c1.from_extrap(x1);
+    c0.compute_flux_conv(a.pp); c0.compute_char_speed();
+    c1.compute_flux_conv(a.pp); c1.compute_char_speed();
+    double nsq = 0;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) nsq += n[d]*n[d];
+    const double speed = fmax(c0.char_speed, c1.char_speed)*sqrt(nsq);
+    #pragma unroll
+    for (int v = 0; v < nu; ++v) {
+      const double flux = .5*(c0.flux_conv[v][0] + c1.flux_conv[v][0] + speed*(c0.update_state[v] - c1.update_state[v]));
+      f0[v*nfq] = sign0*flux;
+      f1[v*nfq] = sign1*flux;
+    }
+  }
+}
+
+/* ---------------- Neighbor_reconcile ---------------- */
+template <int ND, int RS, class P, bool DEF>
+__global__ void __launch_bounds__(128)
+g_neighbor_reconcile_kernel(GArgs a)
+{
+  constexpr int nfq = ipow(RS, ND - 1), nu = P::n_update, wl = (ND + 2)*nfq;
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int con = (int)(gid/nfq), q0 = (int)(gid % nfq);
+  if (con >= a.n_con) return;
+  const int* tab = a.con + (size_t)con*4;
+  int q1 = q0;
+  double sign0 = 1., sign1 = 1.;
+  if constexpr (DEF) {
+    const int code = tab[2];
+    q1 = a.perm[code*nfq + q0];
+    sign0 = ((code/9) % 2) ? 1. : -1.;
+    sign1 = ((code/18) % 2) ? -1. : 1.;
+  }
+  double* l0 = a.faces_ldg + (size_t)tab[0]*wl + q0;
+  double* l1 = a.faces_ldg + (size_t)tab[1]*wl + q1;
+  #pragma unroll
+  for (int v = 0; v < nu; ++v) {
+    const double g0 = l0[v*nfq], g1 = l1[v*nfq];
+    double avg = 0;
+    avg += .5*sign0*g0;
+    avg += .5*sign1*g1;
+    l0[v*nfq] = sign0*avg - g0;
+    l1[v*nfq] = sign1*avg - g1;
+  }
+}
+
+/* ---------------- Local ---------------- */
+template <int ND, int RS, class P>
+struct GCfg
+{
+  static constexpr int nq = ipow(RS, ND), nfq = nq/RS, ne = P::n_extrap, nu = P::n_update;
+  static constexpr int epb = nq >= 128 ? 1 : (128 + nq - 1)/nq;
+  static constexpr int threads = epb*nq;
+  static constexpr int nbuf = (ND > 2 ? ND : 2)*(nu > ne ? nu : ne)*nq;  // flux of one kind / filter scratch / face-extrapolation scratch
+  static constexpr int nx = P::has_diffusion ? ne*nq : 0;                   // variables whose gradient is taken
+  static constexpr int nface = P::has_convection ? 2*ND*nu*nfq : 0;         // numerical convective flux on the element's faces
+  static constexpr int nvface = P::has_diffusion ? 2*ND*ne*nfq : 0;         // LDG face state
+  static constexpr int nops = 3*RS*RS + 2*RS;                               // dfull, diff, filter, lift
+  static constexpr int per_elem = nbuf + nx + nface + nvface;
+  static constexpr int smem_doubles = nops + epb*per_elem;
+};
+
+template <int ND, int RS, class P>
+__device__ __forceinline__ void load_ops(double* s_ops, const Ops& ops, const FilterOp& filt, int t, int nt)
+{
+  for (int i = t; i < RS*RS; i += nt) {
+    s_ops[i] = ops.dfull[i/RS][i % RS];
+    s_ops[RS*RS + i] = ops.diff[i/RS][i % RS];
+    s_ops[2*RS*RS + i] = filt.filter[i/RS][i % RS];
+  }
+  for (int i = t; i < 2*RS; i += nt) s_ops[3*RS*RS + i] = ops.lift[i/2][i % 2];
+}
+
+/* extrapolate [n_var][nq] values held in shared memory to the 2*ND faces of element e: dst[(e*2ND + f)*width + v*nfq + fq] */
+template <int ND, int RS>
+__device__ __forceinline__ void extrapolate_faces(const double* sval, int n_var, double* dst_elem, int width, const Ops& ops, int q)
+{
+  constexpr int nq = ipow(RS, ND), nfq = nq/RS;
+  for (int item = q; item < ND*n_var*nfq; item += nq) {
+    const int d = item/(n_var*nfq), v = (item/nfq) % n_var, fq = item % nfq;
+    int stride = 1;
+    for (int i = 0; i < ND - 1 - d; ++i) stride *= RS;
+    const int base = (fq/stride)*stride*RS + fq % stride;
+    double e0 = 0, e1 = 0;
+    #pragma unroll
+    for (int k = 0; k < RS; ++k) {
+      const double x = sval[v*nq + base + k*stride];
+      e0 += ops.bnd[0][k]*x;
+      e1 += ops.bnd[1][k]*x;
+    }
+    dst_elem[(size_t)(2*d)*width + v*nfq + fq] = e0;
+    dst_elem[(size_t)(2*d + 1)*width + v*nfq + fq] = e1;
+  }
+}
+
+template <int ND, int RS, class P, bool DEF>
+__global__ void __launch_bounds__(GCfg<ND, RS, P>::threads)
+g_local_kernel(GArgs a, Ops ops, FilterOp filt)
+{
+  using C = GCfg<ND, RS, P>;
+  constexpr int nq = C::nq, nfq = C::nfq, ne = C::ne, nu = C::nu, nv = ND + 2, wl = nv*nfq;
+  constexpr int cache_slot0 = nv + 7 + RS;
+  HB_DYN_SMEM(double, smem);
+  const int t = threadIdx.x;
+  const int le = t/nq, q = t % nq;
+  const int e = a.elem_begin + blockIdx.x*C::epb + le;
+  const bool active = e < a.elem_end;
+  double* s_dfull = smem; double* s_diff = smem + RS*RS; double* s_filt = smem + 2*RS*RS; double* s_lift = smem + 3*RS*RS;
+  double* sbuf = smem + C::nops + le*C::per_elem;
+  double* sx = sbuf + C::nbuf;
+  double* sface = sx + C::nx;
+  double* svface = sface + C::nface;
+  load_ops<ND, RS, P>(smem, ops, filt, t, C::threads);
+
+  typename P::template Comp<ND> comp;
+  double det = 1., tss = 0., nom = 1.;
+  if (active) {
+    if constexpr (P::has_convection) {
+      const double* base = a.faces + (size_t)e*2*ND*a.face_width;
+      for (int i = q; i < 2*ND*nu*nfq; i += nq) sface[i] = base[(size_t)(i/(nu*nfq))*a.face_width + i % (nu*nfq)];
+    }
+    if constexpr (P::has_diffusion) {
+      const double* base = a.faces_ldg + (size_t)e*2*ND*wl;
+      for (int i = q; i < 2*ND*ne*nfq; i += nq) svface[i] = base[(size_t)(i/(ne*nfq))*wl + i % (ne*nfq)];
+    }
+    #pragma unroll
+    for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>(e, P::state_slot(i))[q];
+    tss = a.ed.tss[(size_t)e*nq + q];
+    nom = a.nom[e];
+    if constexpr (DEF) {
+      det = a.det[(size_t)(e - a.n_car)*nq + q];
+      const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.normal[j][d] = rn[(d*ND + j)*nq + q];
+    }
+    if constexpr (P::has_diffusion) {
+      #pragma unroll
+      for (int v = 0; v < ne; ++v) sx[v*nq + q] = a.ed.template slot<ND, RS>(e, P::extrap_slot(v))[q];
+    }
+  }
+  __syncthreads();
+
+  // gradient of the extrapolated variables (times the jacobian determinant for deformed elements): Spatial.hpp:371-402
+  if constexpr (P::has_diffusion) {
+    if (active) {
+      #pragma unroll
+      for (int v = 0; v < ne; ++v)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = 0.;
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const Line<ND, RS> ln(d, q);
+        double m[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) m[k] = s_dfull[ln.node*RS + k];
+        const double l0 = s_lift[ln.node*2], l1 = s_lift[ln.node*2 + 1];
+        if constexpr (DEF) {
+          const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+          const double* fn = a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq;
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) {
+            double nk[RS];
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + ln.base + k*ln.stride];
+            const double fn0 = fn[((2*d)*ND + j)*nfq + ln.fq], fn1 = fn[((2*d + 1)*ND + j)*nfq + ln.fq];
+            #pragma unroll
+            for (int v = 0; v < ne; ++v) {
+              double acc = 0;
+              #pragma unroll
+              for (int k = 0; k < RS; ++k) acc += m[k]*(nk[k]*sx[v*nq + ln.base + k*ln.stride]);
+              acc += l0*(fn0*svface[((2*d)*ne + v)*nfq + ln.fq]);
+              acc += l1*(fn1*svface[((2*d + 1)*ne + v)*nfq + ln.fq]);
+              comp.gradient[v][j] += acc/nom;
+            }
+          }
+        } else {
+          #pragma unroll
+          for (int v = 0; v < ne; ++v) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += m[k]*sx[v*nq + ln.base + k*ln.stride];
+            acc += l0*svface[((2*d)*ne + v)*nfq + ln.fq];
+            acc += l1*svface[((2*d + 1)*ne + v)*nfq + ln.fq];
+            comp.gradient[v][d] = acc/nom;
+          }
+        }
+      }
+      if constexpr (DEF) {
+        #pragma unroll
+        for (int v = 0; v < ne; ++v)
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) comp.gradient[v][j] /= det;
+      }
+    }
+  }
+
+  // convective flux and its derivative: Spatial.hpp:405-419,445-456
+  double r0[nu], r1[nu];
+  #pragma unroll
+  for (int v = 0; v < nu; ++v) { r0[v] = 0.; r1[v] = 0.; }
+  if constexpr (P::has_convection) {
+    if (active) {
+      comp.compute_flux_conv(a.pp);
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) sbuf[(d*nu + v)*nq + q] = comp.flux_conv[v][d];
+    }
+    __syncthreads();
+    if (active) {
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const Line<ND, RS> ln(d, q);
+        double m[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) m[k] = s_dfull[ln.node*RS + k];
+        const double l0 = s_lift[ln.node*2], l1 = s_lift[ln.node*2 + 1];
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) {
+          const double* row = sbuf + (d*nu + v)*nq + ln.base;
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += m[k]*row[k*ln.stride];
+          acc += l0*sface[((2*d)*nu + v)*nfq + ln.fq];
+          acc += l1*sface[((2*d + 1)*nu + v)*nfq + ln.fq];
+          r0[v] -= acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // source: Spatial.hpp:436-441
+  if constexpr (P::has_source) {
+    if (active && !a.stage) {
+      comp.compute_source(a.pp);
+      double mult = nom;
+      if constexpr (DEF) mult *= det;
+      #pragma unroll
+      for (int v = 0; v < nu; ++v) r1[v] = mult*comp.source[v];
+    }
+  }
+  // diffusive flux, its interior derivative and its extrapolation to the LDG faces: Spatial.hpp:420-435,458-468
+  if constexpr (P::has_diffusion) {
+    if (active) {
+      comp.compute_flux_diff(a.pp);
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) sbuf[(d*nu + v)*nq + q] = comp.flux_diff[v][d];
+    }
+    __syncthreads();
+    if (active) {
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const Line<ND, RS> ln(d, q);
+        double m[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) m[k] = s_diff[ln.node*RS + k];
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) {
+          const double* row = sbuf + (d*nu + v)*nq + ln.base;
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += m[k]*row[k*ln.stride];
+          r1[v] -= acc;
+        }
+      }
+      double* dst = a.faces_ldg + (size_t)e*2*ND*wl;
+      for (int item = q; item < ND*nu*nfq; item += nq) {
+        const int d = item/(nu*nfq), v = (item/nfq) % nu, fq = item % nfq;
+        int stride = 1;
+        for (int i = 0; i < ND - 1 - d; ++i) stride *= RS;
+        const int base = (fq/stride)*stride*RS + fq % stride;
+        double e0 = 0, e1 = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) {
+          const double x = sbuf[(d*nu + v)*nq + base + k*stride];
+          e0 += ops.bnd[0][k]*x;
+          e1 += ops.bnd[1][k]*x;
+        }
+        dst[(size_t)(2*d)*wl + v*nfq + fq] = e0;
+        dst[(size_t)(2*d + 1)*wl + v*nfq + fq] = e1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // modal filter of both parts of the time rate: Spatial.hpp:473-481
+  if (a.use_filter) {
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (active) {
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) { sbuf[v*nq + q] = r0[v]; sbuf[(nu + v)*nq + q] = r1[v]; }
+      }
+      __syncthreads();
+      if (active) {
+        const Line<ND, RS> ln(d, q);
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) {
+          double acc0 = 0, acc1 = 0;
+          for (int k = 0; k < RS; ++k) {
+            const double f = s_filt[ln.node*RS + k];
+            acc0 += f*sbuf[v*nq + ln.base + k*ln.stride];
+            acc1 += f*sbuf[(nu + v)*nq + ln.base + k*ln.stride];
+          }
+          r0[v] = acc0; r1[v] = acc1;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // update: Spatial.hpp:484-503
+  if (active) {
+    double mult = a.update*tss/nom;
+    if constexpr (DEF) mult /= det;
+    double upd[nu]; double* tgt[nu];
+    #pragma unroll
+    for (int v = 0; v < nu; ++v) {
+      double* cache = a.ed.template slot<ND, RS>(e, cache_slot0 + v) + q;
+      double u = r0[v];
+      if (a.stage) u -= *cache;
+      else {
+        if constexpr (P::has_convection) *cache = u;
+        if constexpr (P::has_diffusion || P::has_source) u += r1[v];
+      }
+      u *= mult;
+      upd[v] = 0.;
+      if (a.compute_residual) *cache = u;
+      else upd[v] = u;
+      tgt[v] = a.ed.template slot<ND, RS>(e, P::update_slot(v)) + q;
+    }
+    P::write_update(a.pp, upd, tgt, tss, !P::has_diffusion && !a.stage);
+  }
+  // face extrapolation of the updated state (inviscid PDEs only): Spatial.hpp:507
+  if constexpr (!P::has_diffusion) {
+    if (active) {
+      #pragma unroll
+      for (int v = 0; v < ne; ++v) sbuf[v*nq + q] = a.ed.template slot<ND, RS>(e, P::extrap_slot(v))[q];
+    }
+    __syncthreads();
+    if (active) extrapolate_faces<ND, RS>(sbuf, ne, a.faces + (size_t)e*2*ND*a.face_width, a.face_width, ops, q);
+  }
+}
+
+/* ---------------- Reconcile_ldg_flux ---------------- */
+template <int ND, int RS, class P, bool DEF>
+__global__ void __launch_bounds__(GCfg<ND, RS, P>::threads)
+g_reconcile_kernel(GArgs a, Ops ops, FilterOp filt)
+{
+  using C = GCfg<ND, RS, P>;
+  constexpr int nq = C::nq, nfq = C::nfq, ne = C::ne, nu = C::nu, nv = ND + 2, wl = nv*nfq;
+  constexpr int cache_slot0 = nv + 7 + RS;
+  HB_DYN_SMEM(double, smem);
+  const int t = threadIdx.x;
+  const int le = t/nq, q = t % nq;
+  const int e = a.elem_begin + blockIdx.x*C::epb + le;
+  const bool active = e < a.elem_end;
+  double* s_filt = smem + 2*RS*RS; double* s_lift = smem + 3*RS*RS;
+  double* sbuf = smem + C::nops + le*C::per_elem;
+  double* svface = sbuf + C::nbuf + C::nx + C::nface;
+  load_ops<ND, RS, P>(smem, ops, filt, t, C::threads);
+  if (active) {
+    const double* base = a.faces_ldg + (size_t)e*2*ND*wl;
+    for (int i = q; i < 2*ND*nu*nfq; i += nq) svface[i] = base[(size_t)(i/(nu*nfq))*wl + i % (nu*nfq)];
+  }
+  __syncthreads();
+  double r[nu];
+  #pragma unroll
+  for (int v = 0; v < nu; ++v) r[v] = 0.;
+  if (active) {
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const Line<ND, RS> ln(d, q);
+      const double l0 = s_lift[ln.node*2], l1 = s_lift[ln.node*2 + 1];
+      #pragma unroll
+      for (int v = 0; v < nu; ++v) {
+        double acc = 0;
+        acc += l0*svface[((2*d)*nu + v)*nfq + ln.fq];
+        acc += l1*svface[((2*d + 1)*nu + v)*nfq + ln.fq];
+        r[v] -= acc;
+      }
+    }
+  }
+  if (a.use_filter) {
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (active) {
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) sbuf[v*nq + q] = r[v];
+      }
+      __syncthreads();
+      if (active) {
+        const Line<ND, RS> ln(d, q);
+        #pragma unroll
+        for (int v = 0; v < nu; ++v) {
+          double acc = 0;
+          for (int k = 0; k < RS; ++k) acc += s_filt[ln.node*RS + k]*sbuf[v*nq + ln.base + k*ln.stride];
+          r[v] = acc;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (active) {
+    const double tss = a.ed.tss[(size_t)e*nq + q];
+    double mult = a.update*tss/a.nom[e];
+    if constexpr (DEF) mult /= a.det[(size_t)(e - a.n_car)*nq + q];
+    double upd[nu]; double* tgt[nu];
+    #pragma unroll
+    for (int v = 0; v < nu; ++v) {
+      upd[v] = r[v]*mult;
+      // the reference hands `write_update` the residual cache as base pointer when only the residual is wanted (Spatial.hpp:579,587)
+      tgt[v] = a.ed.template slot<ND, RS>(e, a.compute_residual ? cache_slot0 + P::update_slot(v) : P::update_slot(v)) + q;
+    }
+    P::write_update(a.pp, upd, tgt, tss, true);
+    #pragma unroll
+    for (int v = 0; v < ne; ++v) sbuf[v*nq + q] = a.ed.template slot<ND, RS>(e, P::extrap_slot(v))[q];
+  }
+  __syncthreads();
+  if (active) extrapolate_faces<ND, RS>(sbuf, ne, a.faces + (size_t)e*2*ND*a.face_width, a.face_width, ops, q);
+}
+
+/* ---------------- Write_face ---------------- */
+template <int ND, int RS, class P>
+__global__ void __launch_bounds__(GCfg<ND, RS, P>::threads)
+g_write_face_kernel(GArgs a, Ops ops)
+{
+  using C = GCfg<ND, RS, P>;
+  constexpr int nq = C::nq, ne = C::ne;
+  HB_DYN_SMEM(double, smem);
+  const int t = threadIdx.x;
+  const int le = t/nq, q = t % nq;
+  const int e = a.elem_begin + blockIdx.x*C::epb + le;
+  const bool active = e < a.elem_end;
+  double* sbuf = smem + le*ne*nq;
+  if (active) {
+    #pragma unroll
+    for (int v = 0; v < ne; ++v) sbuf[v*nq + q] = a.ed.template slot<ND, RS>(e, P::extrap_slot(v))[q];
+  }
+  __syncthreads();
+  if (active) extrapolate_faces<ND, RS>(sbuf, ne, a.faces + (size_t)e*2*ND*a.face_width, a.face_width, ops, q);
+}
+
+/* ---------------- Max_dt ---------------- */
+template <int ND, int RS, class P>
+__global__ void __launch_bounds__(256)
+g_max_dt_kernel(GArgs a, Ops ops)
+{
+  constexpr int nq = ipow(RS, ND), n_vert = ipow(2, ND);
+  __shared__ double warp_min[8];
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int e = (int)(gid/nq), q = (int)(gid % nq);
+  double val = DBL_MAX;
+  if (e < a.elem_end) {
+    double vals[n_vert];
+    #pragma unroll
+    for (int i = 0; i < n_vert; ++i) vals[i] = a.vtss[(size_t)e*n_vert + i];
+    int stride = n_vert;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+      stride /= 2;
+      #pragma unroll
+      for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
+    }
+    const double spacing = vals[0];
+    typename P::template Comp<ND> comp;
+    #pragma unroll
+    for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>(e, P::state_slot(i))[q];
+    double scale = 0;
+    if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed/a.max_cfl_c/spacing; }
+    if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity/a.max_cfl_d/spacing/spacing; }
+    if (a.is_local) a.ed.tss[(size_t)e*nq + q] = 1./scale;
+    else { a.ed.tss[(size_t)e*nq + q] = 1.; val = 1./scale; }
+  }
+  if (a.is_local) return;
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = warp_min[0];
+    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
+    atomicMin(a.global_min, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+/* ---------------- host side ---------------- */
+template <int ND, int RS> using Pde = typename PdeSelect<HB_PDE, ND, RS>::type;
+
+int fill_args(hexed_b200_ctx* c, GArgs& a, const PdeParams& pp)
+{
+  const int kind = (HB_PDE == PDE_ADVECTION) ? 2 : 0;
+  const size_t nq = c->nq, ne = c->n_elem;
+  auto need = [&](double** arr, size_t per_elem) -> int {
+    if (*arr) return 0;
+    HB_CUDA(c, cudaMalloc(arr, sizeof(double)*(ne ? ne : 1)*per_elem));
+    HB_CUDA(c, cudaMemsetAsync(*arr, 0, sizeof(double)*(ne ? ne : 1)*per_elem, c->stream));
+    return 0;
+  };
+  int rc = 0;
+  if (HB_PDE == PDE_NAVIER_STOKES) rc = need(&c->av, 2*nq);
+  if (!rc && HB_PDE == PDE_SMOOTH_AV) rc = need(&c->forcing, 4*nq);
+  if (!rc && HB_PDE == PDE_ADVECTION) rc = need(&c->adv, (size_t)c->rs*nq);
+  if (rc) return rc;
+  const size_t nslot = c->n_face_slot ? c->n_face_slot : 1;
+  if (HB_PDE != PDE_ADVECTION && !c->face_ldg) {
+    HB_CUDA(c, cudaMalloc(&c->face_ldg, sizeof(double)*nslot*c->nv*c->nfq));
+    HB_CUDA(c, cudaMemsetAsync(c->face_ldg, 0, sizeof(double)*nslot*c->nv*c->nfq, c->stream));
+  }
+  if (HB_PDE == PDE_ADVECTION && !c->face_wide) {
+    HB_CUDA(c, cudaMalloc(&c->face_wide, sizeof(double)*nslot*(c->nd + c->rs)*c->nfq));
+    HB_CUDA(c, cudaMemsetAsync(c->face_wide, 0, sizeof(double)*nslot*(c->nd + c->rs)*c->nfq, c->stream));
+  }
+  a.ed.state = c->state; a.ed.tss = c->tss; a.ed.av = c->av; a.ed.forcing = c->forcing; a.ed.adv = c->adv; a.ed.cache = c->cache;
+  a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.normals = c->normals; a.vtss = c->vtss;
+  a.faces = kind == 2 ? c->face_wide : c->face_state; a.faces_ldg = c->face_ldg;
+  a.face_width = (kind == 2 ? c->nd + c->rs : c->nv)*c->nfq;
+  a.con = nullptr; a.perm = c->perm; a.n_con = 0;
+  a.elem_begin = 0; a.elem_end = c->n_elem; a.n_car = c->n_car;
+  a.update = 0; a.stage = 0; a.compute_residual = 0; a.use_filter = 0;
+  a.max_cfl_c = 1; a.max_cfl_d = 1; a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
+  a.pp = pp;
+  return 0;
+}
+
+template <class K> int set_smem(hexed_b200_ctx* c, K k, size_t smem)
+{
+  if (smem > 48*1024) HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+int g_neighbor(hexed_b200_ctx* c, int deformed, const PdeParams& pp, bool reconcile)
+{
+  const int n_con = deformed ? c->n_def_con : c->n_car_con;
+  StatScope scope(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR, n_con);
+  if (!n_con) return 0;
+  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
+  a.con = deformed ? c->def_con : c->car_con; a.n_con = n_con;
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    using P = Pde<ND, RS>;
+    const long long total = (long long)n_con*ipow(RS, ND - 1);
+    const int grid = (int)((total + 127)/128);
+    if (reconcile) {
+      if constexpr (P::has_diffusion) {
+        if (deformed) { auto k = g_neighbor_reconcile_kernel<ND, RS, P, true>; HB_LAUNCH(k, grid, 128, 0, c->stream, a); }
+        else { auto k = g_neighbor_reconcile_kernel<ND, RS, P, false>; HB_LAUNCH(k, grid, 128, 0, c->stream, a); }
+      } else return fail(c, HEXED_B200_BAD_ARGUMENT, "Neighbor_reconcile needs a diffusive PDE");
+    } else {
+      if (deformed) { auto k = g_neighbor_kernel<ND, RS, P, true>; HB_LAUNCH(k, grid, 128, 0, c->stream, a); }
+      else { auto k = g_neighbor_kernel<ND, RS, P, false>; HB_LAUNCH(k, grid, 128, 0, c->stream, a); }
+    }
+    count_launch(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR);
+    HB_CUDA(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdeParams& pp, bool reconcile)
+{
+  const int begin = deformed ? c->n_car : 0, end = deformed ? c->n_elem : c->n_car;
+  StatScope scope(c, reconcile ? (deformed ? ST_RECONCILE_DEF : ST_RECONCILE_CAR) : (deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR), end - begin);
+  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
+  a.elem_begin = begin; a.elem_end = end;
+  a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual; a.use_filter = o.use_filter;
+  a.update = (a.stage && !reconcile) ? o.dt*(.5/c->quad_safety) : o.dt; // Spatial.hpp:317 (Local) / :534 (Reconcile_ldg_flux)
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    using P = Pde<ND, RS>;
+    using C = GCfg<ND, RS, P>;
+    // argument checks of the reference constructors (Spatial.hpp:322-323,539-540)
+    if (P::has_diffusion && a.stage) return fail(c, HEXED_B200_BAD_ARGUMENT, "two-stage stabilization is not applicable to diffusion equations");
+    if (a.stage && a.compute_residual) return fail(c, HEXED_B200_BAD_ARGUMENT, "residual calculation is a single-stage operation");
+    if (end == begin) return 0;
+    const int grid = (end - begin + C::epb - 1)/C::epb;
+    const size_t smem = sizeof(double)*C::smem_doubles;
+    if (reconcile) {
+      if constexpr (P::has_diffusion) {
+        if (a.compute_residual && HB_PDE == PDE_SMOOTH_AV)
+          return fail(c, HEXED_B200_NOT_IMPLEMENTED, "residual-only LDG reconciliation is undefined for Smooth_art_visc (the reference indexes past the residual cache)");
+        if (deformed) { auto k = g_reconcile_kernel<ND, RS, P, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
+        else { auto k = g_reconcile_kernel<ND, RS, P, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
+      } else return fail(c, HEXED_B200_BAD_ARGUMENT, "Reconcile_ldg_flux needs a diffusive PDE");
+    } else {
+      if (deformed) { auto k = g_local_kernel<ND, RS, P, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
+      else { auto k = g_local_kernel<ND, RS, P, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
+    }
+    count_launch(c, reconcile ? (deformed ? ST_RECONCILE_DEF : ST_RECONCILE_CAR) : (deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR));
+    HB_CUDA(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+int g_write_face(hexed_b200_ctx* c, const PdeParams& pp)
+{
+  StatScope scope(c, ST_WRITE_FACE, c->n_elem);
+  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
+  if (!c->n_elem) return 0;
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    using P = Pde<ND, RS>;
+    using C = GCfg<ND, RS, P>;
+    const int grid = (c->n_elem + C::epb - 1)/C::epb;
+    const size_t smem = sizeof(double)*C::epb*C::ne*C::nq;
+    auto k = g_write_face_kernel<ND, RS, P>;
+    int r = set_smem(c, k, smem); if (r) return r;
+    HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops);
+    count_launch(c, ST_WRITE_FACE);
+    HB_CUDA(c, cudaGetLastError());
+    return 0;
+  });
+}
+
+int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double safety_diff, int local_time, double* dt)
+{
+  StatScope s_car(c, ST_MAX_DT_CAR, c->n_car);
+  c->stats[ST_MAX_DT_DEF].work_units += c->n_def;
+  if (!c->n_elem) { *dt = local_time ? 1. : DBL_MAX; return 0; }
+  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
+  a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9), Spatial.hpp:777
+  a.max_cfl_d = -2/c->min_eig_diff*safety_diff;                   // Spatial.hpp:778
+  a.is_local = local_time;
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    using P = Pde<ND, RS>;
+    const long long total = (long long)c->n_elem*ipow(RS, ND);
+    const int grid = (int)((total + 255)/256);
+    if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream));
+    { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
+    count_launch(c, ST_MAX_DT_CAR);
+    HB_CUDA(c, cudaGetLastError());
+    if (local_time) { *dt = 1.; return 0; }
+    HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *dt = *c->h_scalar;
+    return 0;
+  });
+}
+
+} // namespace
+
+#define HB_CAT2(a, b) a##b
+#define HB_CAT(a, b) HB_CAT2(a, b)
+const GenericOps HB_CAT(generic_ops_pde, HB_PDE) = {g_neighbor, g_local, g_write_face, g_max_dt};
+
+} // namespace hb

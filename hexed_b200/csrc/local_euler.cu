@@ -21,6 +21,7 @@ template <int ND, int RS>
 struct LocalCfg
 {
   static constexpr int nq = ipow(RS, ND), nfq = nq/RS, nv = ND + 2;
+  static constexpr int cs = nv > RS ? nv : RS; // slots per element in the residual cache array (src/Storage_params.cpp:32-35)
   static constexpr int epb = nq >= 128 ? 1 : (128 + nq - 1)/nq;
   static constexpr int threads = epb*nq;
   static constexpr int flux_doubles = ND*nv*nq;
@@ -148,7 +149,7 @@ local_euler_kernel(LocalArgs a, Ops ops, FilterOp filt)
   if (active) {
     double mult = a.update*a.tss[(size_t)e*nq + q]/a.nom[e];
     if constexpr (DEF) mult /= det;
-    double* cache = a.cache + (size_t)e*nv*nq + q;
+    double* cache = a.cache + (size_t)e*C::cs*nq + q;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double u = r[v];

@@ -238,6 +238,114 @@ int launch_bcs(hexed_b200_ctx* c)
   return 0;
 }
 
+/* flux boundary conditions: Solver::apply_flux_bcs (reference src/Solver.cpp:69-81) */
+__global__ void __launch_bounds__(256)
+flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal,
+               double* faces, double* faces_ldg, const double* normals, int nd, int nfq)
+{
+  const int nv = nd + 2, w = nv*nfq;
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = (int)(gid/nfq), q = (int)(gid % nfq);
+  if (i >= n) return;
+  double* gh = faces_ldg + (size_t)ghost[i]*w + q;
+  const double* in = faces_ldg + (size_t)inside[i]*w + q;
+  if (kind == HEXED_B200_BC_FREESTREAM || kind == HEXED_B200_BC_COPY) { // copy_state: both halves (src/Boundary_condition.cpp:12-23)
+    for (int v = 0; v < nv; ++v) gh[v*nfq] = in[v*nfq];
+    for (int v = 0; v < nv; ++v) faces[(size_t)ghost[i]*w + q + v*nfq] = faces[(size_t)inside[i]*w + q + v*nfq];
+    return;
+  }
+  // Nonpenetration::apply_flux (src/Boundary_condition.cpp:329-341): negate, then un-invert the normal momentum flux
+  for (int v = 0; v < nv; ++v) gh[v*nfq] = -in[v*nfq];
+  const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  double dot = 0., nsq = 0.;
+  for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; dot += gh[d*nfq]*nn; nsq += nn*nn; }
+  for (int d = 0; d < nd; ++d) gh[d*nfq] -= 2*dot*nr[d*nfq]/nsq;
+}
+
+int launch_flux_bcs(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->face_ldg) return fail(c, HEXED_B200_BAD_ARGUMENT, "flux boundary conditions need the LDG face storage (run a viscous kernel first)");
+  long long total_faces = 0;
+  for (auto& b : c->bcs) total_faces += b.n;
+  StatScope scope(c, ST_BC, total_faces);
+  for (auto& b : c->bcs) {
+    if (!b.n) continue;
+    const long long total = (long long)b.n*c->nfq;
+    HB_LAUNCH(flux_bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal,
+              c->face_state, c->face_ldg, c->normals, c->nd, c->nfq);
+    count_launch(c, ST_BC);
+    HB_CUDA(c, cudaGetLastError());
+  }
+  return 0;
+}
+
+/* ---------------- smoothness indicator: reference src/stabilizing_art_visc.cpp:8-66 ----------------
+ * One CTA per element. Pointwise and per-line terms are computed in parallel into shared memory; the two sums are then
+ * accumulated by one thread in the reference's loop order, so the result does not depend on the launch geometry. */
+struct StabArgs { const double* state; const double* nom; double* uncert; int n_elem; double char_speed; double proj[MAX_RS]; double weight[MAX_RS]; };
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(ipow(RS, ND) < 32 ? 32 : ipow(RS, ND))
+stab_art_visc_kernel(StabArgs a)
+{
+  constexpr int nq = ipow(RS, ND), nfq = nq/RS, nv = ND + 2;
+  __shared__ double ind[nq], t1[nq], t2[ND*nfq];
+  const int e = blockIdx.x, q = threadIdx.x;
+  if (q < nq) {
+    const double x = 1./a.state[((size_t)e*nv + ND)*nq + q];
+    double w = 1;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) w *= a.weight[(q/ipow(RS, ND - 1 - d)) % RS];
+    ind[q] = x;
+    t1[q] = x*x*w;
+  }
+  __syncthreads();
+  for (int item = q; item < ND*nfq; item += blockDim.x) {
+    const int d = item/nfq, fq = item % nfq;
+    const int stride = ipow(RS, ND - 1 - d);
+    const int base = (fq/stride)*stride*RS + fq % stride;
+    double dot = 0;
+    #pragma unroll
+    for (int k = 0; k < RS; ++k) dot += ind[base + k*stride]*a.proj[k];
+    double fw = 1;
+    #pragma unroll
+    for (int dd = 0; dd < ND - 1; ++dd) fw *= a.weight[(fq/ipow(RS, ND - 2 - dd)) % RS];
+    t2[item] = dot*dot*fw;
+  }
+  __syncthreads();
+  if (q == 0) {
+    double norm_sq = 0, nonsmooth = 0;
+    for (int i = 0; i < nq; ++i) norm_sq += t1[i];
+    for (int i = 0; i < ND*nfq; ++i) nonsmooth += t2[i];
+    nonsmooth /= norm_sq*ND;
+    const double ramp_center = -4.25*log((double)(RS - 1))/log(10.), half_width = 0.5;
+    double indicator = log(nonsmooth)/log(10.);
+    if (indicator <= ramp_center - half_width) indicator = 0;
+    else if (indicator < ramp_center + half_width) indicator = .5*(1 + sin(3.14159265358979323846*(indicator - ramp_center)/2/half_width));
+    else indicator = 1;
+    a.uncert[e] = (RS - 1)*a.char_speed*a.nom[e]*indicator;
+  }
+}
+
+int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->n_elem) return 0;
+  StabArgs a;
+  a.state = c->state; a.nom = c->nom; a.uncert = c->uncert; a.n_elem = c->n_elem; a.char_speed = char_speed;
+  for (int i = 0; i < MAX_RS; ++i) { a.weight[i] = i < c->rs ? c->weight[i] : 0.; a.proj[i] = i < c->rs ? c->orthogonal[c->rs - 1][i]*c->weight[i] : 0.; }
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    constexpr int threads = ipow(RS, ND) < 32 ? 32 : ipow(RS, ND);
+    auto k = stab_art_visc_kernel<ND, RS>;
+    HB_LAUNCH(k, c->n_elem, threads, 0, c->stream, a);
+    ++c->launches;
+    HB_CUDA(c, cudaGetLastError());
+    return 0;
+  });
+}
+
 /* ---------------- packed gather / scatter of face slots (boundary faces crossing PCIe) ---------------- */
 __global__ void __launch_bounds__(256) gather_kernel(const double* src, int width, const int* slots, int n, double* dst)
 {

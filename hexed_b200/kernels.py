@@ -67,6 +67,20 @@ SIGNATURES = {
     "hexed_b200_compute_prolong": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_compute_restrict": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_face_permutation": [C.c_void_p, ip, C.c_int, dp],
+    "hexed_b200_compute_advection": [C.c_void_p, Options, C.c_double],
+    "hexed_b200_compute_navier_stokes": [C.c_void_p, Options, C.c_void_p, C.c_void_p, Transport, Transport],
+    "hexed_b200_compute_smooth_av": [C.c_void_p, Options, C.c_void_p, C.c_void_p, C.c_double, C.c_double],
+    "hexed_b200_compute_fix_therm_admis": [C.c_void_p, Options, C.c_void_p, C.c_void_p],
+    "hexed_b200_max_dt_navier_stokes": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, Transport, Transport, dp],
+    "hexed_b200_max_dt_advection": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, C.c_double, dp],
+    "hexed_b200_max_dt_smooth_av": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
+    "hexed_b200_max_dt_fix_therm_admis": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
+    "hexed_b200_compute_prolong_advection": [C.c_void_p],
+    "hexed_b200_compute_write_face_advection": [C.c_void_p],
+    "hexed_b200_compute_write_face_smooth_av": [C.c_void_p],
+    "hexed_b200_stabilizing_art_visc": [C.c_void_p, C.c_double],
+    "hexed_b200_pde_kernel": [C.c_void_p, C.c_int, C.c_int, C.c_int, Options, Transport, Transport, C.c_double, C.c_double],
+    "hexed_b200_apply_flux_bcs": [C.c_void_p],
     "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
     "hexed_b200_local_euler": [C.c_void_p, C.c_int, Options],
     "hexed_b200_bc_create": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, dp, C.c_int, ip],
@@ -77,6 +91,26 @@ SIGNATURES = {
     "hexed_b200_launch_count": [C.c_void_p],
 }
 _RESTYPES = {"hexed_b200_last_error": C.c_char_p, "hexed_b200_launch_count": C.c_longlong}
+
+
+CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
+NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS = 1, 2, 3, 4
+K_NEIGHBOR, K_LOCAL, K_NEIGHBOR_RECONCILE, K_RECONCILE_LDG = 0, 1, 2, 3
+
+
+def inviscid():
+    """Transport_model::inviscid() (reference include/Transport_model.hpp:40)"""
+    return Transport(0., 0., 1., 1., 1., 0)
+
+
+def constant_transport(value):
+    """Transport_model::constant (reference include/Transport_model.hpp:42)"""
+    return Transport(value, 0., 1., 1., 1., 1)
+
+
+def sutherland(ref_val, ref_temp, temp_offset):
+    """Transport_model::sutherland (reference include/Transport_model.hpp:44-47)"""
+    return Transport(0., ref_val, ref_temp, float(np.sqrt(ref_temp)), temp_offset, 1)
 
 
 def load_library(path=None):
@@ -158,6 +192,8 @@ class Device:
             self.upload(FACE_STATE, m.face_state)
         if m.face_ldg is not None:
             self.upload(FACE_LDG, m.face_ldg)
+        if m.face_wide is not None:
+            self.upload(FACE_WIDE, m.face_wide)
         self.bc_ids = []
         for bc in m.bcs:
             self.bc_ids.append(self.add_bc(bc))
@@ -201,6 +237,8 @@ class Device:
         self.download(FACE_STATE, m.face_state)
         if m.face_ldg is not None:
             self.download(FACE_LDG, m.face_ldg)
+        if m.face_wide is not None:
+            self.download(FACE_WIDE, m.face_wide)
         self.download(UNCERT, m.uncert)
         return m
 
@@ -258,6 +296,64 @@ class Device:
         out = np.zeros(self.row_size**(self.n_dim - 1), np.int32)
         self._check(self.lib.hexed_b200_face_permutation_table(self.ctx, d, out.ctypes.data_as(ip)))
         return out
+
+    def _cb(self, flux_bc):
+        if flux_bc is None:
+            return None
+        cb = CALLBACK(lambda _: flux_bc())
+        self._keep = cb
+        return C.cast(cb, C.c_void_p)
+
+    def compute_advection(self, advect_length, **kw):
+        self._check(self.lib.hexed_b200_compute_advection(self.ctx, self._opts(**kw), advect_length))
+
+    def compute_navier_stokes(self, flux_bc, visc, therm_cond, **kw):
+        self._check(self.lib.hexed_b200_compute_navier_stokes(self.ctx, self._opts(**kw), self._cb(flux_bc), None, visc, therm_cond))
+
+    def compute_smooth_av(self, flux_bc, diff_time, chebyshev_step, **kw):
+        self._check(self.lib.hexed_b200_compute_smooth_av(self.ctx, self._opts(**kw), self._cb(flux_bc), None, diff_time, chebyshev_step))
+
+    def compute_fix_therm_admis(self, flux_bc, **kw):
+        self._check(self.lib.hexed_b200_compute_fix_therm_admis(self.ctx, self._opts(**kw), self._cb(flux_bc), None))
+
+    def max_dt_navier_stokes(self, convective_safety, diffusive_safety, local_time, visc, therm_cond, **kw):
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_max_dt_navier_stokes(self.ctx, self._opts(**kw), convective_safety, diffusive_safety, int(local_time), visc, therm_cond, C.byref(out)))
+        return out.value
+
+    def max_dt_advection(self, convective_safety, diffusive_safety, local_time, advect_length, **kw):
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_max_dt_advection(self.ctx, self._opts(**kw), convective_safety, diffusive_safety, int(local_time), advect_length, C.byref(out)))
+        return out.value
+
+    def max_dt_smooth_av(self, convective_safety, diffusive_safety, local_time, **kw):
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_max_dt_smooth_av(self.ctx, self._opts(**kw), convective_safety, diffusive_safety, int(local_time), C.byref(out)))
+        return out.value
+
+    def max_dt_fix_therm_admis(self, convective_safety, diffusive_safety, local_time, **kw):
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_max_dt_fix_therm_admis(self.ctx, self._opts(**kw), convective_safety, diffusive_safety, int(local_time), C.byref(out)))
+        return out.value
+
+    def compute_prolong_advection(self):
+        self._check(self.lib.hexed_b200_compute_prolong_advection(self.ctx))
+
+    def compute_write_face_advection(self):
+        self._check(self.lib.hexed_b200_compute_write_face_advection(self.ctx))
+
+    def compute_write_face_smooth_av(self):
+        self._check(self.lib.hexed_b200_compute_write_face_smooth_av(self.ctx))
+
+    def stabilizing_art_visc(self, char_speed):
+        self._check(self.lib.hexed_b200_stabilizing_art_visc(self.ctx, char_speed))
+
+    def pde_kernel(self, pde, which, deformed, visc=None, therm_cond=None, p0=1., p1=1., **kw):
+        self._check(self.lib.hexed_b200_pde_kernel(self.ctx, pde, which, int(deformed), self._opts(**kw), visc or inviscid(),
+                                                   therm_cond or inviscid(), p0, p1))
+
+    def apply_flux_bcs(self):
+        self._check(self.lib.hexed_b200_apply_flux_bcs(self.ctx))
 
     def neighbor_euler(self, deformed):
         self._check(self.lib.hexed_b200_neighbor_euler(self.ctx, int(deformed)))

@@ -36,6 +36,7 @@
  * Basis tables (argument `basis` of hexed_b200_create): packed doubles, rs = row_size, matrices row-major M[i][j]
  *   node[rs] weight[rs] diff_mat[rs][rs] boundary[2][rs] orthogonal[rs][rs] filter[rs][rs] prolong[2][rs][rs]
  *   restrict[2][rs][rs] min_eig_convection min_eig_diffusion quadratic_safety      (include/Basis.hpp:16-66)
+ *   legendre_node[rs]   nodes of Gauss_legendre(row_size), which pde::Advection uses whatever the basis (include/pde.hpp:281)
  */
 #ifndef HEXED_B200_H_
 #define HEXED_B200_H_
@@ -147,6 +148,40 @@ int hexed_b200_compute_restrict(hexed_b200_ctx* ctx, int scale, int offset);
  * applies match_faces (restore = 0) or restore (restore = 1) to nv variables of one face held in `data` */
 int hexed_b200_face_permutation(hexed_b200_ctx* ctx, const int dir[4], int restore, double* data);
 
+/* void compute_advection(Kernel_mesh, Kernel_options, double advect_length)        include/kernels.hpp:23, src/kernels_convective.cpp:19 */
+int hexed_b200_compute_advection(hexed_b200_ctx* ctx, hexed_b200_options opts, double advect_length);
+/* void compute_navier_stokes(Kernel_mesh, Kernel_options, std::function<void()> flux_bc, Transport_model visc, Transport_model therm_cond)
+ *                                                                                  include/kernels.hpp:24-25, src/kernels_diffusive.cpp:28-29
+ * `flux_bc(user)` is called on the calling thread between Prolong and Neighbor_reconcile of stage 0 (src/kernels_diffusive.cpp:18);
+ * it may be NULL, and it may call hexed_b200_apply_flux_bcs / face_list transfers on this context. */
+int hexed_b200_compute_navier_stokes(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_callback flux_bc, void* user,
+                                     hexed_b200_transport visc, hexed_b200_transport therm_cond);
+/* void compute_smooth_av(Kernel_mesh, Kernel_options, std::function<void()> flux_bc, double diff_time, double chebyshev_step)
+ *                                                                                  include/kernels.hpp:26, src/kernels_diffusive.cpp:30-31 */
+int hexed_b200_compute_smooth_av(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_callback flux_bc, void* user, double diff_time, double chebyshev_step);
+/* void compute_fix_therm_admis(Kernel_mesh, Kernel_options, std::function<void()> flux_bc)   include/kernels.hpp:27, src/kernels_diffusive.cpp:32 */
+int hexed_b200_compute_fix_therm_admis(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_callback flux_bc, void* user);
+/* double max_dt_navier_stokes / _advection / _smooth_av / _fix_therm_admis(...)    include/kernels.hpp:30-34, src/kernels_max_dt.cpp:15-21 */
+int hexed_b200_max_dt_navier_stokes(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time,
+                                    hexed_b200_transport visc, hexed_b200_transport therm_cond, double* dt);
+int hexed_b200_max_dt_advection(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time, double advect_length, double* dt);
+int hexed_b200_max_dt_smooth_av(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time, double* dt);
+int hexed_b200_max_dt_fix_therm_admis(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time, double* dt);
+/* void compute_prolong_advection(Kernel_mesh)                                      include/kernels.hpp:38, src/kernels_convective.cpp:33-36 */
+int hexed_b200_compute_prolong_advection(hexed_b200_ctx* ctx);
+/* void compute_write_face_advection / _smooth_av(Kernel_mesh)                      include/kernels.hpp:41-42, src/kernels_convective.cpp:48-56 */
+int hexed_b200_compute_write_face_advection(hexed_b200_ctx* ctx);
+int hexed_b200_compute_write_face_smooth_av(hexed_b200_ctx* ctx);
+/* void stabilizing_art_visc(Kernel_mesh, double char_speed)                        include/stabilizing_art_visc.hpp:13, src/stabilizing_art_visc.cpp:8-66
+ * result in the HEXED_B200_UNCERT array */
+int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* ctx, double char_speed);
+
+/* individual kernels of the other PDEs, for unit-level parity. pde: 1 Navier-Stokes, 2 advection, 3 smooth AV, 4 fix therm admis;
+ * which: 0 Neighbor, 1 Local, 2 Neighbor_reconcile, 3 Reconcile_ldg_flux (include/Spatial.hpp:613-704,326-509,716-759,543-594);
+ * p0, p1: advect_length | diff_time, chebyshev_step */
+int hexed_b200_pde_kernel(hexed_b200_ctx* ctx, int pde, int which, int deformed, hexed_b200_options opts,
+                          hexed_b200_transport visc, hexed_b200_transport therm_cond, double p0, double p1);
+
 /* ---- individual kernels of the Euler sequence (for unit-level parity; deformed: 0 = Cartesian set, 1 = deformed set) ---- */
 int hexed_b200_neighbor_euler(hexed_b200_ctx* ctx, int deformed);   /* Spatial<..>::Neighbor   include/Spatial.hpp:613-704 */
 int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options opts); /* Spatial<..>::Local include/Spatial.hpp:326-509 */
@@ -156,6 +191,9 @@ int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options
 int hexed_b200_bc_create(hexed_b200_ctx* ctx, int kind, int n, const int* inside_slot, const int* ghost_slot,
                          const int* normal_slot, const double* params, int n_params, int* bc_id);
 int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
+/* Solver::apply_flux_bcs (src/Solver.cpp:69-81) for the same boundary conditions: Freestream/Copy::apply_flux = copy_state
+ * (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341). The flux cache copy of :75-76 is host-side. */
+int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 
 /* ---- profiling side-contract ---- */
 int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);

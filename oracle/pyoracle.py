@@ -222,3 +222,21 @@ class Oracle:
                 self.lib.ho_bc_copy(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip))
             elif bc["kind"] == BC_NONPENETRATION:
                 self.lib.ho_bc_nonpenetration(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip), _ptr(bc["normal_slot"], ip))
+
+    def apply_flux_bcs(self, m):
+        """flux boundary conditions of the same kinds (reference src/Solver.cpp:69-81): Freestream/Copy::apply_flux = copy_state
+        (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341); numpy, small meshes only"""
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION
+        nd, nfq = m.n_dim, m.nfq
+        for bc in m.bcs:
+            ins, gh = bc["inside_slot"], bc["ghost_slot"]
+            if bc["kind"] in (BC_FREESTREAM, BC_COPY):
+                m.face_ldg[gh] = m.face_ldg[ins]
+                m.face_state[gh] = m.face_state[ins]
+            elif bc["kind"] == BC_NONPENETRATION:
+                g = -m.face_ldg[ins].reshape(-1, nd + 2, nfq)
+                n = m.normals[bc["normal_slot"]]
+                dot = (g[:, :nd]*n).sum(1)
+                nsq = (n*n).sum(1)
+                g[:, :nd] -= 2*dot[:, None, :]*n/nsq[:, None, :]
+                m.face_ldg[gh] = g.reshape(len(gh), -1)

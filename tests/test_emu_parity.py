@@ -6,7 +6,8 @@ import pytest
 
 import hexed_b200 as hb
 from hexed_b200 import mesh as M
-from util import run_euler_pair, assert_euler_parity, density_wave, freestream_state
+from util import (run_euler_pair, assert_euler_parity, density_wave, freestream_state, run_pde_pair, assert_pde_parity,
+                  prepare_pde_state, NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS)
 
 
 @pytest.mark.parametrize("nd,rs", [(1, 3), (2, 2), (2, 5), (3, 2), (3, 3)])
@@ -36,3 +37,31 @@ def test_box_2d(oracle, emu_lib, deformed):
     oracle.compute_write_face(basis, m)
     out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=1)
     assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("pde", [NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS])
+@pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
+def test_soup_other_pdes(oracle, emu_lib, pde, nd, rs):
+    rng = np.random.default_rng(100*pde + 10*nd + rs)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, with_ldg=True, with_wide=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, pde)
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, pde, n_steps=1, use_filter=(rs == 3))
+    assert_pde_parity(out, ref, dts)
+
+
+def test_stab_art_visc(oracle, emu_lib):
+    from hexed_b200.kernels import Device
+    rng = np.random.default_rng(8)
+    basis = hb.gauss_legendre(4)
+    m = M.soup_mesh(2, 4, rng, with_ldg=False)
+    M.random_flow_state(m, rng)
+    m.state()[:, 2] *= 1 + 0.3*rng.random(m.state()[:, 2].shape)  # rough density so the indicator lands on the ramp for some elements
+    ref = m.copy()
+    dev = Device(2, 4, basis, lib_path=emu_lib).load_mesh(m)
+    oracle.stabilizing_art_visc(basis, ref, 340.)
+    dev.stabilizing_art_visc(340.)
+    dev.sync_to_host(m)
+    assert np.abs(m.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
+    dev.close()

@@ -6,7 +6,8 @@ import pytest
 import hexed_b200 as hb
 from hexed_b200 import mesh as M
 from hexed_b200.kernels import Device
-from util import run_euler_pair, assert_euler_parity, density_wave, freestream_state, rel_l2
+from util import (run_euler_pair, assert_euler_parity, density_wave, freestream_state, rel_l2, run_pde_pair, assert_pde_parity,
+                  prepare_pde_state, NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS)
 
 pytestmark = pytest.mark.gpu
 
@@ -134,3 +135,57 @@ def test_full_size_properties(gpu_lib):
     tss = np.empty((m.n_elem, 1, m.nq)); dev.download_elements(tss, nd + 2, 1)
     assert abs(tss.min()/dt - 1) <= 1e-13
     dev.close()
+
+
+@pytest.mark.parametrize("pde", [NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS])
+@pytest.mark.parametrize("nd,rs", [(1, 4), (2, 2), (2, 6), (3, 3), (3, 6), (3, 8)])
+def test_soup_other_pdes(oracle, gpu_lib, pde, nd, rs):
+    """compute_navier_stokes / compute_advection / compute_smooth_av / compute_fix_therm_admis and their max_dt_* on the
+    structurally complete soup mesh (every orientation, hanging faces, car/def mix); 2 steps, with and without the modal filter"""
+    rng = np.random.default_rng(100*pde + 10*nd + rs)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, with_ldg=True, with_wide=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, pde)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, pde, n_steps=2, use_filter=(rs % 2 == 0), safety=0.1)
+    assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("pde", [NAVIER_STOKES, FIX_THERM_ADMIS])
+def test_other_pdes_residual_mode_and_local_time(oracle, gpu_lib, pde):
+    rng = np.random.default_rng(77)
+    basis = hb.gauss_legendre(6)
+    m = M.soup_mesh(3, 6, rng, with_ldg=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, pde)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, pde, n_steps=1, compute_residual=True, safety=0.1)
+    assert_pde_parity(out, ref, dts)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, pde, n_steps=1, local_time=True, safety=0.05)
+    assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,n,deformed", [(2, 8, True), (2, 8, False), (3, 4, True)])
+def test_box_navier_stokes(oracle, gpu_lib, nd, n, deformed):
+    """BASELINE config samples/cylinder in miniature: row size 6 viscous flow with Sutherland viscosity on a box, 3 steps"""
+    basis = hb.gauss_legendre(6)
+    m = M.box_mesh(nd, 6, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd), with_ldg=True)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=3, safety=0.5)
+    assert_pde_parity(out, ref, dts)
+
+
+def test_stabilizing_art_visc(oracle, gpu_lib):
+    rng = np.random.default_rng(8)
+    for nd, rs in [(2, 6), (3, 6), (3, 4)]:
+        basis = hb.gauss_legendre(rs)
+        m = M.soup_mesh(nd, rs, rng, with_ldg=False)
+        M.random_flow_state(m, rng)
+        m.state()[:, nd] *= 1 + 0.3*rng.random(m.state()[:, nd].shape)
+        ref = m.copy()
+        dev = Device(nd, rs, basis, lib_path=gpu_lib).load_mesh(m)
+        oracle.stabilizing_art_visc(basis, ref, 340.)
+        dev.stabilizing_art_visc(340.)
+        dev.sync_to_host(m)
+        assert np.abs(m.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
+        dev.close()

@@ -44,3 +44,92 @@ def assert_euler_parity(out, ref, dts):
     assert rel_l2(out.cache(), ref.cache()) <= 1e-10  # cancellation-prone residual difference, looser by design
     assert rel_l2(out.face_state, ref.face_state) <= STATE_TOL
     assert rel_l2(out.tss(), ref.tss()) <= MAX_DT_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the other PDEs (reference include/pde.hpp): Navier-Stokes, advection, smooth artificial viscosity, fix therm admis
+# ---------------------------------------------------------------------------------------------------------------
+from pyoracle import NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS  # noqa: E402
+import pyoracle  # noqa: E402
+from hexed_b200 import kernels as K  # noqa: E402
+
+
+def prepare_pde_state(mesh, rng, pde):
+    """random but benign data in the element slots the PDE touches (slot numbers: reference include/pde.hpp:17-21)"""
+    nd, rs = mesh.n_dim, mesh.row_size
+    d = mesh.elem_data
+    ne, nq = mesh.n_elem, mesh.nq
+    if pde == NAVIER_STOKES:
+        d[:, M.BULK_AV_SLOT(nd)] = 1e-4*rng.random((ne, nq))
+        d[:, M.LAPLACIAN_AV_SLOT(nd)] = 1e-4*rng.random((ne, nq))
+    elif pde == ADVECTION:
+        d[:, :nd] = rng.standard_normal((ne, nd, nq))                 # advection velocity lives in the momentum slots
+        d[:, M.ADVECTION_SLOT(nd):M.ADVECTION_SLOT(nd) + rs] = 1. + 0.1*rng.standard_normal((ne, rs, nq))
+        mesh.face_wide[:] = rng.standard_normal(mesh.face_wide.shape)
+    elif pde == SMOOTH_AV:
+        d[:, M.FORCING_SLOT(nd):M.FORCING_SLOT(nd) + 4] = rng.standard_normal((ne, 4, nq))
+
+
+def run_pde_pair(oracle, lib_path, mesh, basis, pde, n_steps=1, local_time=False, use_filter=False, safety=0.3, compute_residual=False):
+    """one `max_dt_*` + stage sequence per step on both implementations, mirroring how Solver drives each PDE"""
+    ref = mesh.copy()
+    dev = Device(mesh.n_dim, mesh.row_size, basis, lib_path=lib_path).load_mesh(mesh)
+    visc_o, cond_o = pyoracle.sutherland(1.7e-5, 273., 110.), pyoracle.constant(2.5e-2)
+    visc_d, cond_d = K.sutherland(1.7e-5, 273., 110.), K.constant_transport(2.5e-2)
+    dts = []
+    for _ in range(n_steps):
+        if pde == NAVIER_STOKES:
+            dt_o = oracle.max_dt(pde, basis, ref, safety, safety, local_time, visc_o, cond_o)
+            dt_d = dev.max_dt_navier_stokes(safety, safety, local_time, visc_d, cond_d)
+            oracle.apply_state_bcs(ref); dev.apply_state_bcs()
+            oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0,
+                                         use_filter=use_filter, compute_residual=compute_residual)
+            dev.compute_navier_stokes(dev.apply_flux_bcs, visc_d, cond_d, dt=dt_o, i_stage=0, use_filter=use_filter, compute_residual=compute_residual)
+            if not compute_residual:
+                oracle.apply_state_bcs(ref); dev.apply_state_bcs()
+                oracle.compute_euler(basis, ref, dt=dt_o, i_stage=1, use_filter=use_filter)
+                dev.compute_euler(dt=dt_o, i_stage=1, use_filter=use_filter)
+        elif pde == ADVECTION:
+            dt_o = oracle.max_dt(pde, basis, ref, safety, safety, local_time, advect_length=0.7)
+            dt_d = dev.max_dt_advection(safety, safety, local_time, 0.7)
+            for stage in (0, 1):
+                oracle.compute_advection(basis, ref, 0.7, dt=dt_o, i_stage=stage, use_filter=use_filter)
+                dev.compute_advection(0.7, dt=dt_o, i_stage=stage, use_filter=use_filter)
+        elif pde == SMOOTH_AV:
+            dt_o = oracle.max_dt(pde, basis, ref, safety, safety, local_time)
+            dt_d = dev.max_dt_smooth_av(safety, safety, local_time)
+            oracle.compute_smooth_av(basis, ref, None, 0.4, 1.3, dt=dt_o, i_stage=0, use_filter=use_filter)
+            dev.compute_smooth_av(None, 0.4, 1.3, dt=dt_o, i_stage=0, use_filter=use_filter)
+        else:
+            dt_o = oracle.max_dt(pde, basis, ref, safety, safety, local_time)
+            dt_d = dev.max_dt_fix_therm_admis(safety, safety, local_time)
+            oracle.compute_fix_therm_admis(basis, ref, None, dt=dt_o, i_stage=0, use_filter=use_filter, compute_residual=compute_residual)
+            dev.compute_fix_therm_admis(None, dt=dt_o, i_stage=0, use_filter=use_filter, compute_residual=compute_residual)
+        dts.append((dt_d, dt_o))
+    out = mesh.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    return out, ref, dts
+
+
+def assert_pde_parity(out, ref, dts, tol=STATE_TOL):
+    for dt_d, dt_o in dts:
+        assert abs(dt_d - dt_o) <= MAX_DT_TOL*abs(dt_o), (dt_d, dt_o)
+    nd, rs = out.n_dim, out.row_size
+    c = M.cache_slot(nd, rs)
+    # one comparison per slot group so that a small-magnitude group cannot hide behind the flow state
+    groups = {"state": (0, nd + 2), "av": (nd + 3, nd + 5), "forcing": (nd + 5, nd + 9), "advection": (nd + 9, nd + 9 + rs)}
+    for name, (lo, hi) in groups.items():
+        a, b = out.elem_data[:, lo:hi], ref.elem_data[:, lo:hi]
+        assert np.isfinite(b).all(), name
+        if np.linalg.norm(b) == 0:
+            assert np.array_equal(a, b), name
+        else:
+            assert rel_l2(a, b) <= tol, name
+    a, b = out.elem_data[:, c:], ref.elem_data[:, c:]
+    assert (np.array_equal(a, b) if np.linalg.norm(b) == 0 else rel_l2(a, b) <= 10*tol), "residual cache"  # cancellation-prone difference
+    assert rel_l2(out.tss(), ref.tss()) <= MAX_DT_TOL
+    for name in ("face_state", "face_ldg", "face_wide"):
+        a, b = getattr(out, name), getattr(ref, name)
+        if a is not None:
+            assert rel_l2(a, b) <= tol, name
