@@ -619,6 +619,12 @@ int hexed_b200_apply_state_bcs(hexed_b200_ctx* c) { return launch_bcs(c); }
 
 int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled != 0; return 0; }
 
+int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
+{
+  if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; return 0; }
+  return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown option");
+}
+
 int hexed_b200_kernel_stats(hexed_b200_ctx* c, hexed_b200_kernel_stat* out, int capacity, int* n_out)
 {
   int n = 0;

@@ -82,6 +82,7 @@ struct hexed_b200_ctx
   // stats
   hb::Stat stats[hb::ST_COUNT];
   bool timing = false;
+  bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   std::string err;
@@ -119,6 +120,7 @@ inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->s
 /* launchers implemented in the kernel translation units; return a HEXED_B200_* code */
 int launch_neighbor_euler(hexed_b200_ctx* c, int deformed);
 int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o);
+int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end);
 int launch_write_face(hexed_b200_ctx* c);
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
 int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale);

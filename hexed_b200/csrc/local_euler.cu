@@ -234,6 +234,11 @@ int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o)
   const int begin = deformed ? c->n_car : 0, end = deformed ? c->n_elem : c->n_car;
   StatScope scope(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR, end - begin);
   if (end == begin) return 0;
+  {
+    const int rc = launch_local_euler_pipe(c, deformed, o, begin, end);
+    if (rc == 0) count_launch(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR);
+    if (rc >= 0) return rc;
+  }
   LocalArgs a;
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;

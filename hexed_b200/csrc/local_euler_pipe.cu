@@ -1,0 +1,251 @@
+/* local_euler_pipe.cu -- persistent, TMA-pipelined version of the Euler `Local` kernel for 3-D elements.
+ *
+ * Same arithmetic as local_euler.cu (reference include/Spatial.hpp:326-509 + the trailing write_face :41-57,507) but organised
+ * around the two things the first profile showed to bound that kernel (profiles/r01a_ncu_full.md: 76 % L1/shared-memory
+ * pipe, long-scoreboard stalls on the global loads, 53 % occupancy):
+ *
+ *  1. HBM latency. A persistent CTA (grid = SMs x resident CTAs) walks elements blockIdx.x, +gridDim.x, ... . Every input of an
+ *     element is one contiguous run in the element-major layout (state nv*nq, the 2*ND numerical-flux faces, ND*ND normals,
+ *     determinant, time-step scale, residual cache), so one elected thread fetches them with 1-D bulk TMA copies
+ *     (cp.async.bulk -> UBLKCP) that complete on mbarriers. The (state, faces, normals) set is double buffered: the copies for
+ *     element i+2 are in flight while element i is computed; the late inputs (cache, tss, det) are single buffered and
+ *     fetched one phase ahead. No thread ever stalls on a global load.
+ *  2. Shared-memory traffic. Work is split into LINE tasks (one thread owns the row_size points of one line of one dimension)
+ *     instead of one thread per point: a line task reads each flux value once and produces row_size derivative values from
+ *     registers, with the 1-D operator entries as constant-bank operands. 2.6x fewer shared-memory bytes per element than the
+ *     point-per-thread kernel.
+ *
+ * Phases per element: A (line tasks: pointwise flux on the line, derivative + lifted face flux -> R_d[v][q]),
+ * B (point tasks: r = R_0 + R_1 + R_2, two-stage update, new state -> HBM and in place in shared memory),
+ * C (line tasks: extrapolate the new state to both faces of the line -> HBM).
+ */
+#include "euler.cuh"
+
+namespace hb {
+
+template <int RS, bool DEF>
+struct PipeCfg
+{
+  static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5;
+  static constexpr int n_line = ND*nfq;
+  static constexpr int threads = ((n_line + 31)/32)*32;
+  static constexpr int cs = nv > RS ? nv : RS;
+  // double-buffered stage: state | numerical flux faces | reference level normals
+  static constexpr int st_state = 0, st_face = nv*nq, st_nrml = st_face + 2*ND*nv*nfq;
+  static constexpr int stage_doubles = st_nrml + (DEF ? ND*ND*nq : 0);
+  // single-buffered late inputs: residual cache | tss | det
+  static constexpr int lt_cache = 0, lt_tss = nv*nq, lt_det = lt_tss + nq;
+  static constexpr int late_doubles = lt_det + (DEF ? nq : 0);
+  static constexpr int r_doubles = ND*nv*nq;
+  static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t);
+};
+
+struct PipeArgs
+{
+  double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
+  int elem_begin, elem_end, n_car;
+  double update; int stage; int compute_residual;
+};
+
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe_issue_stage(const PipeArgs& a, int e, double* buf, mbar_t* bar)
+{
+  using C = PipeCfg<RS, DEF>;
+  constexpr unsigned b_state = sizeof(double)*C::nv*C::nq, b_face = sizeof(double)*2*C::ND*C::nv*C::nfq, b_nrml = sizeof(double)*C::ND*C::ND*C::nq;
+  mbar_arrive_expect_tx(bar, b_state + b_face + (DEF ? b_nrml : 0u));
+  bulk_g2s(buf + C::st_state, a.state + (size_t)e*C::nv*C::nq, b_state, bar);
+  bulk_g2s(buf + C::st_face, a.faces + (size_t)e*2*C::ND*C::nv*C::nfq, b_face, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::st_nrml, a.refn + (size_t)(e - a.n_car)*C::ND*C::ND*C::nq, b_nrml, bar);
+}
+
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe_issue_late(const PipeArgs& a, int e, double* buf, mbar_t* bar)
+{
+  using C = PipeCfg<RS, DEF>;
+  constexpr unsigned b_cache = sizeof(double)*C::nv*C::nq, b_pt = sizeof(double)*C::nq;
+  mbar_arrive_expect_tx(bar, (a.stage ? b_cache : 0u) + b_pt + (DEF ? b_pt : 0u));
+  if (a.stage) bulk_g2s(buf + C::lt_cache, a.cache + (size_t)e*C::cs*C::nq, b_cache, bar);
+  bulk_g2s(buf + C::lt_tss, a.tss + (size_t)e*C::nq, b_pt, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e - a.n_car)*C::nq, b_pt, bar);
+}
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(PipeCfg<RS, DEF>::threads)
+local_euler_pipe_kernel(PipeArgs a, Ops ops)
+{
+  using C = PipeCfg<RS, DEF>;
+  constexpr int ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv;
+  HB_DYN_SMEM(double, smem);
+  double* late = smem + 2*C::stage_doubles;
+  double* R = late + C::late_doubles;
+  mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
+  const int t = threadIdx.x;
+  const int stride_e = gridDim.x;
+  int e = a.elem_begin + blockIdx.x;
+  if (e >= a.elem_end) return;
+
+  if (t == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (t == 0) {
+    pipe_issue_stage<RS, DEF>(a, e, smem, &bars[0]);
+    if (e + stride_e < a.elem_end) pipe_issue_stage<RS, DEF>(a, e + stride_e, smem + C::stage_doubles, &bars[1]);
+    pipe_issue_late<RS, DEF>(a, e, late, &bars[2]);
+  }
+
+  // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
+  const bool has_line = t < C::n_line;
+  const int d = t/nfq, l = t % nfq;
+  const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+  const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
+
+  for (int it = 0; e < a.elem_end; ++it, e += stride_e) {
+    const int s = it & 1;
+    const unsigned par = (it >> 1) & 1;
+    double* const stage_buf = smem + s*C::stage_doubles;
+    double* S = stage_buf + C::st_state;
+    const double* F = stage_buf + C::st_face;
+    const double* N = stage_buf + C::st_nrml;
+    mbar_wait(&bars[s], par);
+
+    /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
+    if (has_line) {
+      double f[nv][RS];
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) {
+        EulerPoint<ND> p;
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) p.s[v] = S[v*nq + q0 + k*stride];
+        p.scalars();
+        double fl[nv];
+        if constexpr (DEF) {
+          double n[ND];
+          // normal[j] of reference direction d at this point: refn[d][j][q] (reference Spatial.hpp:411)
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) n[j] = N[(d*ND + j)*nq + q0 + k*stride];
+          p.flux(n, fl);
+        } else {
+          // unit normal e_d; selects instead of a dynamically indexed register array
+          const double mass_flux = d == 0 ? p.s[0] : d == 1 ? p.s[1] : p.s[2];
+          const double vol_flux = mass_flux*p.inv_mass;
+          fl[ND] = mass_flux;
+          fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+        }
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
+      }
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          R[(d*nv + v)*nq + q0 + i*stride] = -acc;
+        }
+      }
+    }
+    __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
+
+    /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
+    mbar_wait(&bars[2], it & 1);
+    {
+      const double nom = a.nom[e];
+      for (int q = t; q < nq; q += C::threads) {
+        double mult = a.update*late[C::lt_tss + q]/nom;
+        if constexpr (DEF) mult /= late[C::lt_det + q];
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          double u = R[(0*nv + v)*nq + q];
+          u += R[(1*nv + v)*nq + q];
+          u += R[(2*nv + v)*nq + q];
+          double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+          if (a.stage) u -= late[C::lt_cache + v*nq + q];
+          else if (!a.compute_residual) *cache = u;
+          u *= mult;
+          if (a.compute_residual) *cache = u;
+          else {
+            const double x = S[v*nq + q] + u;
+            S[v*nq + q] = x;
+            a.state[((size_t)e*nv + v)*nq + q] = x;
+          }
+        }
+      }
+    }
+    __syncthreads(); // new state complete in S; late buffer free
+    if (t == 0 && e + stride_e < a.elem_end) {
+      fence_proxy_async();
+      pipe_issue_late<RS, DEF>(a, e + stride_e, late, &bars[2]);
+    }
+
+    /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
+    if (has_line) {
+      double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double e0 = 0, e1 = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) {
+          const double x = S[v*nq + q0 + k*stride];
+          e0 += ops.bnd[0][k]*x;
+          e1 += ops.bnd[1][k]*x;
+        }
+        fout[((2*d)*nv + v)*nfq + l] = e0;
+        fout[((2*d + 1)*nv + v)*nfq + l] = e1;
+      }
+    }
+    __syncthreads(); // stage buffer s free
+    if (t == 0 && e + 2*stride_e < a.elem_end) {
+      fence_proxy_async();
+      pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
+    }
+  }
+}
+
+template <int RS, bool DEF>
+static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
+{
+  using C = PipeCfg<RS, DEF>;
+  auto k = local_euler_pipe_kernel<RS, DEF>;
+  static int blocks_per_sm = 0; // per instantiation
+  if (!blocks_per_sm) {
+    HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
+    int n = 0;
+    HB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::threads, C::smem_bytes));
+    if (n < 1) return fail(c, HEXED_B200_CUDA_ERROR, "pipelined local kernel does not fit on this device");
+    blocks_per_sm = n;
+  }
+  int sms = 0;
+  HB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const int n_elem = a.elem_end - a.elem_begin;
+  int grid = sms*blocks_per_sm;
+  if (grid > n_elem) grid = n_elem;
+  HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops);
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+/* returns -1 if this (n_dim, row_size, options) combination is not covered and the caller should use the general kernel */
+int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end)
+{
+  if (c->nd != 3 || (c->rs != 4 && c->rs != 6) || o.use_filter || !c->use_pipe) return -1;
+  PipeArgs a;
+  a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
+  a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
+  a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
+  a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
+  int rc;
+  if (c->rs == 6) rc = deformed ? launch_pipe<6, true>(c, a) : launch_pipe<6, false>(c, a);
+  else rc = deformed ? launch_pipe<4, true>(c, a) : launch_pipe<4, false>(c, a);
+  return rc;
+}
+
+} // namespace hb

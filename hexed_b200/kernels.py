@@ -86,6 +86,7 @@ SIGNATURES = {
     "hexed_b200_bc_create": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, dp, C.c_int, ip],
     "hexed_b200_apply_state_bcs": [C.c_void_p],
     "hexed_b200_set_timing": [C.c_void_p, C.c_int],
+    "hexed_b200_set_option": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_kernel_stats": [C.c_void_p, C.POINTER(KernelStat), C.c_int, ip],
     "hexed_b200_reset_stats": [C.c_void_p],
     "hexed_b200_launch_count": [C.c_void_p],
@@ -367,6 +368,9 @@ class Device:
     # ---- profiling side-contract ----
     def set_timing(self, enabled):
         self._check(self.lib.hexed_b200_set_timing(self.ctx, int(enabled)))
+
+    def set_option(self, option, value):
+        self._check(self.lib.hexed_b200_set_option(self.ctx, option, int(value)))
 
     def kernel_stats(self):
         buf = (KernelStat*16)()

@@ -197,6 +197,10 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 
 /* ---- profiling side-contract ---- */
 int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
+/* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined
+ * Local kernel where it applies (3-D, row size 4 or 6, no modal filter); default 1 */
+enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0 };
+int hexed_b200_set_option(hexed_b200_ctx* ctx, int option, int value);
 int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);
 int hexed_b200_reset_stats(hexed_b200_ctx* ctx);
 long long hexed_b200_launch_count(const hexed_b200_ctx* ctx); /* kernels launched by this context so far */

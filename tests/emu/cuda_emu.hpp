@@ -143,6 +143,26 @@ enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cu
 struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeUnregistered; };
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { *a = cudaPointerAttributes(); return cudaSuccess; }
 
+struct cudaFuncAttributes { int numRegs = 0; };
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return cudaSuccess; } // one "SM": persistent kernels iterate
+enum { cudaDevAttrMultiProcessorCount = 16 };
+template <class F> cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
+
+/* emulated mbarrier + bulk copy: the copy is done synchronously by the issuing thread; waiters spin on the phase counter */
+namespace hb {
+struct mbar_t { std::atomic<long long> pending{0}; std::atomic<unsigned> phase{0}; };
+inline void mbar_init(mbar_t* bar, unsigned) { bar->pending = 0; bar->phase = 0; }
+inline void mbar_init_fence() {}
+inline void mbar_arrive_expect_tx(mbar_t* bar, unsigned bytes) { bar->pending += (long long)bytes; }
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* bar)
+{
+  std::memcpy(dst, src, bytes);
+  if ((bar->pending -= (long long)bytes) == 0) bar->phase++;
+}
+inline void mbar_wait(mbar_t* bar, unsigned parity) { while ((bar->phase.load() & 1u) == parity) std::this_thread::yield(); }
+inline void fence_proxy_async() {}
+}
+
 #define HB_LAUNCH(kern, grid, block, smem, stream, ...) hb_emu::launch(dim3(grid), dim3(block), [&] { kern(__VA_ARGS__); })
 #define HB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(hb_emu::g_dyn_smem)
 

@@ -65,3 +65,15 @@ def test_stab_art_visc(oracle, emu_lib):
     dev.sync_to_host(m)
     assert np.abs(m.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
     dev.close()
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+def test_box_3d_pipelined_local(oracle, emu_lib, deformed):
+    """3-D row size 4 takes the persistent TMA-pipelined Local kernel (local_euler_pipe.cu); the emulated device has one SM with
+    two resident CTAs, so every CTA walks several elements and both stage buffers and all barrier phases are exercised"""
+    basis = hb.gauss_legendre(4)
+    m = M.box_mesh(3, 4, 2, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2)
+    assert_euler_parity(out, ref, dts)
