@@ -169,8 +169,11 @@ def main():
     cuda = torch.device("cuda", local_rank)
 
     # ---- synthetic mesh (geometry computed on the GPU, never leaves it) and initial state ----
+    # one block of the global box per rank, blocks laid out in Z-order (space-filling-curve split of the structured box)
+    blocks = M.proc_grid(world, nd)
     m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=fs, device=cuda,
-                   geometry_chunk=32768, keep_geometry_on_device=deformed, lean=True)
+                   geometry_chunk=32768, keep_geometry_on_device=deformed, lean=True,
+                   blocks=blocks, block=M.block_coords(rank, blocks))
     ne, nq, nv = m.n_elem, m.nq, m.nv
     dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
     # density wave initial condition, written from pinned host memory (the solver's state lives in host arrays in the reference)
@@ -191,6 +194,9 @@ def main():
     dev.compute_write_face()
     stream = torch.cuda.ExternalStream(dev.cuda_stream(), device=cuda)
 
+    from hexed_b200.halo import DeviceHalo
+    halo = DeviceHalo(dev, m) if world > 1 else None
+
     def global_dt(dt):
         if dist is None:
             return dt
@@ -198,11 +204,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
+    def stage_kernels(dt, stage):
+        if halo is None:
+            dev.compute_euler(dt=dt, i_stage=stage)
+        else:
+            halo.start()                 # gather cut faces, NCCL send/recv over NVLink ...
+            dev.compute_euler_begin()    # ... overlapped with the flux on interior connections
+            halo.finish()
+            dev.compute_euler_finish(dt=dt, i_stage=stage)
+
     def step():
         dt = global_dt(dev.max_dt_euler(0.7, 0.7, False))
         for stage in (0, 1):
             dev.apply_state_bcs()
-            dev.compute_euler(dt=dt, i_stage=stage)
+            stage_kernels(dt, stage)
 
     def barrier():
         if dist is not None:
@@ -265,7 +280,7 @@ def main():
                 dev.face_list_download(inside_list, h_in)             # D2H: inside boundary faces for the host Flow_bc
                 h_gh[:] = fs_t                                        # host boundary condition (Freestream::apply_state)
                 dev.face_list_upload(ghost_list, h_gh)                # H2D: ghost faces
-                dev.compute_euler(dt=dt, i_stage=stage)
+                stage_kernels(dt, stage)
         for _ in range(2):
             step_e2e()
         sec_e2e = timed(step_e2e, args.steps)
@@ -289,10 +304,12 @@ def main():
                                    "step = max_dt + 2 x (ghost BC fill + compute_euler)" % (args.mesh, n, ne),
                        "elements_per_gpu": ne, "dof_per_element": nv*nq, "stages_per_step": 2,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (ne*50e3/1e9),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent boxes (replicas) + NCCL allreduce(min) of dt; halo exchange not implemented yet" % world},
+                       "parallelism": "1 GPU" if world == 1 else
+                       "%s blocks of one global box (Z-order split), cut faces exchanged by NCCL send/recv (%d B per rank and stage) overlapped with interior flux work, dt by NCCL allreduce(min)"
+                       % ("x".join(map(str, blocks)), halo.bytes_per_exchange)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "local_euler_kernel<3,6,%s>" % ("true" if deformed else "false"),
+            "roofline": {"bound": "hbm", "kernel": "local_euler_pipe_kernel<6,%s>" % ("true" if deformed else "false"),
                          "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
                          "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/1080.},

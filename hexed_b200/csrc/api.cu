@@ -38,7 +38,8 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->state); dev_free(c->tss); dev_free(c->cache); dev_free(c->av); dev_free(c->forcing); dev_free(c->adv);
   dev_free(c->nom); dev_free(c->vtss); dev_free(c->uncert); dev_free(c->refn); dev_free(c->det);
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
-  dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face);
+  dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
+  c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
   for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
   c->lists.clear();
   for (auto& b : c->bcs) { dev_free(b.inside); dev_free(b.ghost); dev_free(b.normal); dev_free(b.params); }
@@ -412,6 +413,64 @@ int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
   int rc;
   if ((rc = launch_neighbor_euler(c, 0))) return rc;
   if ((rc = launch_neighbor_euler(c, 1))) return rc;
+  if ((rc = launch_restrict(c, 0, c->nv, 1))) return rc;
+  if ((rc = launch_local_euler(c, 0, o))) return rc;
+  if ((rc = launch_local_euler(c, 1, o))) return rc;
+  if ((rc = launch_prolong(c, 0, c->nv, 0))) return rc;
+  return 0;
+}
+
+/* ---- domain decomposition ---- */
+int hexed_b200_set_partition(hexed_b200_ctx* c, int n_cut_car, int n_cut_def, int n_pre_prolong, const int* pre_prolong_ref)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (n_cut_car < 0 || n_cut_car > c->n_car_con || n_cut_def < 0 || n_cut_def > c->n_def_con || n_pre_prolong < 0)
+    return fail(c, HEXED_B200_BAD_ARGUMENT, "cut connection counts out of range");
+  for (int i = 0; i < n_pre_prolong; ++i) if (pre_prolong_ref[i] < 0 || pre_prolong_ref[i] >= c->n_ref) return fail(c, HEXED_B200_BAD_ARGUMENT, "refined face index out of range");
+  dev_free(c->pre_prolong);
+  int rc = dev_alloc(c, &c->pre_prolong, n_pre_prolong, false); if (rc) return rc;
+  if (n_pre_prolong) HB_CUDA(c, cudaMemcpyAsync(c->pre_prolong, pre_prolong_ref, sizeof(int)*n_pre_prolong, cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_cut_car = n_cut_car; c->n_cut_def = n_cut_def; c->n_pre_prolong = n_pre_prolong;
+  return 0;
+}
+
+int hexed_b200_face_list_gather(hexed_b200_ctx* c, int list_id, int kind, double* device_dst)
+{
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  double* arr; int width;
+  int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  return launch_gather_faces(c, arr, width, l.d_slots, l.n, device_dst);
+}
+
+int hexed_b200_face_list_scatter(hexed_b200_ctx* c, int list_id, int kind, const double* device_src)
+{
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  double* arr; int width;
+  int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  return launch_scatter_faces(c, arr, width, l.d_slots, l.n, device_src);
+}
+
+/* compute_euler in two halves so that the halo exchange overlaps the interior flux work:
+ *   begin : Neighbor on the connections that touch no halo face
+ *   finish: Prolong of hanging faces whose coarse face arrived through a halo, Neighbor on the cut connections, then the rest
+ *           of the reference sequence (src/kernels_convective.cpp:8-16) */
+int hexed_b200_compute_euler_begin(hexed_b200_ctx* c)
+{
+  int rc;
+  if ((rc = launch_neighbor_euler(c, 0, 0, c->n_car_con - c->n_cut_car))) return rc;
+  if ((rc = launch_neighbor_euler(c, 1, 0, c->n_def_con - c->n_cut_def))) return rc;
+  return 0;
+}
+
+int hexed_b200_compute_euler_finish(hexed_b200_ctx* c, hexed_b200_options o)
+{
+  int rc;
+  if (c->n_pre_prolong && (rc = launch_prolong(c, 0, c->nv, 0, c->pre_prolong, c->n_pre_prolong))) return rc;
+  if ((rc = launch_neighbor_euler(c, 0, c->n_car_con - c->n_cut_car, c->n_cut_car))) return rc;
+  if ((rc = launch_neighbor_euler(c, 1, c->n_def_con - c->n_cut_def, c->n_cut_def))) return rc;
   if ((rc = launch_restrict(c, 0, c->nv, 1))) return rc;
   if ((rc = launch_local_euler(c, 0, o))) return rc;
   if ((rc = launch_local_euler(c, 1, o))) return rc;

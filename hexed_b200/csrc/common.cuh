@@ -73,6 +73,9 @@ struct hexed_b200_ctx
   int *def_con = nullptr;  // [n][4]: slot0, slot1, dir code, normal slot
   int *ref_face = nullptr; // [n][8]: coarse, fine0..3, stretch0, stretch1, 0
   int *perm = nullptr;     // [36][nfq] face permutation tables, indexed by dir code
+  // domain decomposition (hexed_b200_set_partition): cut connections sit at the end of the tables
+  int n_cut_car = 0, n_cut_def = 0, n_pre_prolong = 0;
+  int *pre_prolong = nullptr; // indices into ref_face whose coarse face is a halo slot
   std::vector<int> h_perm;
   // scratch
   double* d_scalar = nullptr; double* h_scalar = nullptr;
@@ -118,12 +121,12 @@ struct StatScope
 inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->stats[stat_id].launches; }
 
 /* launchers implemented in the kernel translation units; return a HEXED_B200_* code */
-int launch_neighbor_euler(hexed_b200_ctx* c, int deformed);
+int launch_neighbor_euler(hexed_b200_ctx* c, int deformed, int first = 0, int count = -1);
 int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o);
 int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end);
 int launch_write_face(hexed_b200_ctx* c);
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
-int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale);
+int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index = nullptr, int n_index = 0);
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale);
 int launch_bcs(hexed_b200_ctx* c);
 int launch_gather_faces(hexed_b200_ctx* c, const double* src, int width, const int* d_slots, int n, double* dst);

@@ -124,11 +124,11 @@ __device__ void transfer_sweeps(double* buf, int n_var, const double (*mat)[MAX_
 
 template <int ND, int RS>
 __global__ void __launch_bounds__(128)
-prolong_kernel(double* faces, int width, int n_var, const int* ref_face, TransferOps ops, int scl)
+prolong_kernel(double* faces, int width, int n_var, const int* ref_face, TransferOps ops, int scl, const int* ref_index)
 {
   constexpr int nfq = ipow(RS, ND - 1);
   HB_DYN_SMEM(double, buf);
-  const int* rf = ref_face + (size_t)blockIdx.x*8;
+  const int* rf = ref_face + (size_t)(ref_index ? ref_index[blockIdx.x] : (int)blockIdx.x)*8;
   const int str[2] = {rf[5], rf[6]};
   int nf = ipow(2, ND - 1);
   for (int d = 0; d < ND - 1; ++d) nf /= 1 + str[d];
@@ -171,25 +171,26 @@ static double* face_array(hexed_b200_ctx* c, int kind) { return kind == 0 ? c->f
 static int face_width(hexed_b200_ctx* c, int kind) { return (kind == 2 ? c->nd + c->rs : c->nv)*c->nfq; }
 
 template <bool PROLONG>
-static int launch_transfer(hexed_b200_ctx* c, int kind, int n_var, int scale)
+static int launch_transfer(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index = nullptr, int n_index = 0)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
-  StatScope scope(c, ST_PR, c->n_ref);
-  if (!c->n_ref) return 0;
+  const int n_ref = ref_index ? n_index : c->n_ref;
+  StatScope scope(c, ST_PR, n_ref);
+  if (!n_ref) return 0;
   double* faces = face_array(c, kind);
   if (!faces) return fail(c, HEXED_B200_BAD_ARGUMENT, "face storage of the requested kind has not been allocated");
   const int width = face_width(c, kind);
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const size_t smem = sizeof(double)*n_var*ipow(RS, ND - 1)*(PROLONG ? 1 : 2);
-    if (PROLONG) { auto k = prolong_kernel<ND, RS>; HB_LAUNCH(k, c->n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale); }
-    else { auto k = restrict_kernel<ND, RS>; HB_LAUNCH(k, c->n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale); }
+    if (PROLONG) { auto k = prolong_kernel<ND, RS>; HB_LAUNCH(k, n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale, ref_index); }
+    else { auto k = restrict_kernel<ND, RS>; HB_LAUNCH(k, n_ref, 128, smem, c->stream, faces, width, n_var, c->ref_face, c->transfer, scale); }
     count_launch(c, ST_PR);
     HB_CUDA(c, cudaGetLastError());
     return 0;
   });
 }
-int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<true>(c, kind, n_var, scale); }
+int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index, int n_index) { return launch_transfer<true>(c, kind, n_var, scale, ref_index, n_index); }
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<false>(c, kind, n_var, scale); }
 
 /* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */

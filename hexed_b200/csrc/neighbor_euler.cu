@@ -63,14 +63,17 @@ neighbor_euler_kernel(NeighborArgs a)
   }
 }
 
-int launch_neighbor_euler(hexed_b200_ctx* c, int deformed)
+int launch_neighbor_euler(hexed_b200_ctx* c, int deformed, int first, int count)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
-  const int n_con = deformed ? c->n_def_con : c->n_car_con;
+  const int n_all = deformed ? c->n_def_con : c->n_car_con;
+  if (count < 0) count = n_all - first;
+  if (first < 0 || first + count > n_all) return fail(c, HEXED_B200_BAD_ARGUMENT, "connection range out of bounds");
+  const int n_con = count;
   StatScope scope(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR, n_con);
   if (!n_con) return 0;
   NeighborArgs a;
-  a.faces = c->face_state; a.normals = c->normals; a.con = deformed ? c->def_con : c->car_con; a.perm = c->perm; a.n_con = n_con;
+  a.faces = c->face_state; a.normals = c->normals; a.con = (deformed ? c->def_con : c->car_con) + (size_t)first*4; a.perm = c->perm; a.n_con = n_con;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)n_con*ipow(RS, ND - 1);

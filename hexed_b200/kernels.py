@@ -61,6 +61,11 @@ SIGNATURES = {
     "hexed_b200_face_list_download": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_list_upload": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_permutation_table": [C.c_void_p, ip, ip],
+    "hexed_b200_set_partition": [C.c_void_p, C.c_int, C.c_int, C.c_int, ip],
+    "hexed_b200_face_list_gather": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "hexed_b200_face_list_scatter": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "hexed_b200_compute_euler_begin": [C.c_void_p],
+    "hexed_b200_compute_euler_finish": [C.c_void_p, Options],
     "hexed_b200_compute_euler": [C.c_void_p, Options],
     "hexed_b200_max_dt_euler": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
     "hexed_b200_compute_write_face": [C.c_void_p],
@@ -198,6 +203,11 @@ class Device:
         self.bc_ids = []
         for bc in m.bcs:
             self.bc_ids.append(self.add_bc(bc))
+        if getattr(m, "halo", None) is not None:
+            pp = _i32(m.pre_prolong)
+            self._check(self.lib.hexed_b200_set_partition(self.ctx, m.n_cut_car, m.n_cut_def, pp.size, pp.ctypes.data_as(ip)))
+            self.send_lists = {peer: self.face_list(s) for peer, s in m.halo.send.items()}
+            self.recv_lists = {peer: self.face_list(s) for peer, s in m.halo.recv.items()}
         return self
 
     def add_bc(self, bc):
@@ -255,6 +265,19 @@ class Device:
 
     def face_list_upload(self, list_id, src, kind=0):
         self._check(self.lib.hexed_b200_face_list_upload(self.ctx, list_id, kind, _addr(src)))
+
+    def face_list_gather(self, list_id, device_dst, kind=0):
+        """asynchronous on the context's stream; `device_dst` must be device memory"""
+        self._check(self.lib.hexed_b200_face_list_gather(self.ctx, list_id, kind, _addr(device_dst)))
+
+    def face_list_scatter(self, list_id, device_src, kind=0):
+        self._check(self.lib.hexed_b200_face_list_scatter(self.ctx, list_id, kind, _addr(device_src)))
+
+    def compute_euler_begin(self):
+        self._check(self.lib.hexed_b200_compute_euler_begin(self.ctx))
+
+    def compute_euler_finish(self, **kw):
+        self._check(self.lib.hexed_b200_compute_euler_finish(self.ctx, self._opts(**kw)))
 
     def synchronize(self):
         self._check(self.lib.hexed_b200_synchronize(self.ctx))

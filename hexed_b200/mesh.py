@@ -205,35 +205,103 @@ def default_warp(x, amplitude):
     return x + amplitude*s[..., None]
 
 
+def proc_grid(world, n_dim=3):
+    """blocks per dimension for `world` ranks, filled in Z-order (x halves first): 1 -> (1,1,1), 2 -> (2,1,1), 4 -> (2,2,1), 8 -> (2,2,2)"""
+    grid = [1]*n_dim
+    d = 0
+    w = world
+    while w > 1:
+        if w % 2:
+            raise ValueError("world size must be a power of two")
+        grid[d % n_dim] *= 2
+        w //= 2
+        d += 1
+    return tuple(grid)
+
+
+def block_rank(coords, grid):
+    """rank of the block at integer block coordinates: Z-order (Morton) over the block grid, consistent with partition.morton_keys"""
+    nd = len(grid)
+    bits = max(int(g - 1).bit_length() for g in grid)
+    key = 0
+    for b in range(bits):
+        for d in range(nd):
+            key |= ((coords[d] >> b) & 1) << (b*nd + (nd - 1 - d))
+    # compact the key to 0..world-1 (grid sides are powers of two, possibly unequal)
+    order = sorted(_all_block_keys(grid))
+    return order.index(key)
+
+
+def _all_block_keys(grid):
+    nd = len(grid)
+    bits = max(int(g - 1).bit_length() for g in grid)
+    keys = []
+    for c in np.ndindex(*grid):
+        key = 0
+        for b in range(bits):
+            for d in range(nd):
+                key |= ((c[d] >> b) & 1) << (b*nd + (nd - 1 - d))
+        keys.append(key)
+    return keys
+
+
+def block_coords(rank, grid):
+    for c in np.ndindex(*grid):
+        if block_rank(c, grid) == rank:
+            return tuple(int(x) for x in c)
+    raise ValueError("rank outside the block grid")
+
+
 def box_mesh(n_dim, row_size, n, basis, deformed=False, warp_amplitude=0.1, bc_kind=BC_FREESTREAM, bc_params=None,
-             device=None, geometry_chunk=32768, with_ldg=False, keep_geometry_on_device=False, lean=False):
-    """`n^n_dim` elements on the unit box, all Cartesian or all deformed, with a boundary connection on every outer face.
+             device=None, geometry_chunk=32768, with_ldg=False, keep_geometry_on_device=False, lean=False,
+             blocks=None, block=None):
+    """`n^n_dim` elements, all Cartesian or all deformed, with a boundary connection on every outer face.
 
     Interior connections run along each dimension between neighbours (direction {d, d}, {1, 0});
     boundary connections are deformed-type connections {d, d}, {sign, !sign} against a ghost face, as in the
     reference (src/Accessible_mesh.cpp:136-147, include/connection.hpp:346-366).
     If `keep_geometry_on_device`, the large metric arrays are returned as torch tensors on `device`.
     `lean` skips the host allocation of element data and face storage (benchmark-sized meshes live on the device only).
+
+    Domain decomposition: with `blocks` = blocks per dimension and `block` = this rank's block coordinates the function builds
+    ONE block of a global box of `blocks[d]*n` elements per dimension (unit spacing 1/(blocks[0]*n)): faces shared with a
+    neighbouring block become cut connections against halo face slots, exactly as `partition.partition_mesh` would produce them
+    from the undivided mesh (same table layout: interior, boundary, cut), and `mesh.halo` lists what to exchange with whom.
+    Metric terms are evaluated on the block plus one layer of neighbours so that shared normals and vertex spacings are the
+    same numbers on both sides of a cut.
     """
+    from .partition import Halo
     nd, rs = n_dim, row_size
+    blocks = tuple(blocks) if blocks is not None else (1,)*nd
+    block = tuple(block) if block is not None else (0,)*nd
+    gdim = [blocks[d]*n for d in range(nd)]
+    origin = np.array([block[d]*n for d in range(nd)])
     E = n**nd
-    h = 1./n
+    h = 1./gdim[0]
     idx = np.stack(np.meshgrid(*[np.arange(n)]*nd, indexing="ij"), -1).reshape(E, nd)  # row-major, last fastest
     strides = np.array([n**(nd - 1 - d) for d in range(nd)])
-    # boundary faces
+    # outer faces of the block: physical boundary (ghost + boundary condition) or cut (halo + peer)
     b_elem, b_dim, b_sign = [], [], []
+    c_elem, c_dim, c_sign, c_peer = [], [], [], []
     for d in range(nd):
         for sign in range(2):
             sel = np.nonzero(idx[:, d] == (n - 1 if sign else 0))[0]
-            b_elem.append(sel); b_dim.append(np.full(sel.size, d)); b_sign.append(np.full(sel.size, sign))
-    b_elem, b_dim, b_sign = np.concatenate(b_elem), np.concatenate(b_dim), np.concatenate(b_sign)
-    n_bc = b_elem.size
+            nb = list(block); nb[d] += 1 if sign else -1
+            if 0 <= nb[d] < blocks[d]:
+                c_elem.append(sel); c_dim.append(np.full(sel.size, d)); c_sign.append(np.full(sel.size, sign))
+                c_peer.append(np.full(sel.size, block_rank(nb, blocks)))
+            else:
+                b_elem.append(sel); b_dim.append(np.full(sel.size, d)); b_sign.append(np.full(sel.size, sign))
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0, np.int64)  # noqa: E731
+    b_elem, b_dim, b_sign = cat(b_elem), cat(b_dim), cat(b_sign)
+    c_elem, c_dim, c_sign, c_peer = cat(c_elem), cat(c_dim), cat(c_sign), cat(c_peer)
+    n_bc, n_cut = b_elem.size, c_elem.size
     n_car, n_def = (0, E) if deformed else (E, 0)
-    mesh = FlatMesh(nd, rs, n_car, n_def, n_ghost=n_bc, n_extra_normal=0 if deformed else n_bc, with_ldg=with_ldg,
+    mesh = FlatMesh(nd, rs, n_car, n_def, n_ghost=n_bc + n_cut, n_extra_normal=0 if deformed else n_bc, with_ldg=with_ldg,
                     alloc_elem_data=not lean, alloc_faces=not lean)
     mesh.nom_size[:] = h
     mesh.box_n = n
-    mesh.elem_index = idx
+    mesh.elem_index = idx + origin
     nfq = mesh.nfq
     # interior connections
     cons = []
@@ -259,51 +327,91 @@ def box_mesh(n_dim, row_size, n, basis, deformed=False, warp_amplitude=0.1, bc_k
     bc = np.zeros((n_bc, 7), np.int32)
     bc[:, 0] = inside; bc[:, 1] = ghost
     bc[:, 2] = b_dim; bc[:, 3] = b_dim; bc[:, 4] = b_sign; bc[:, 5] = 1 - b_sign
+    # cut connections: the element on the low side of the shared face is side 0, as in the undivided mesh
+    halo_slot = 2*nd*E + n_bc + np.arange(n_cut)
+    own = c_elem*2*nd + 2*c_dim + c_sign
     if deformed:
+        cut = np.zeros((n_cut, 7), np.int32)
+        cut[:, 0] = np.where(c_sign == 1, own, halo_slot); cut[:, 1] = np.where(c_sign == 1, halo_slot, own)
+        cut[:, 2] = c_dim; cut[:, 3] = c_dim; cut[:, 4] = 1; cut[:, 5] = 0
+        cut[:, 6] = own  # the shared (averaged) normal is stored on both elements' faces
         bc[:, 6] = inside  # element face normal slot == face slot numbering for an all-deformed mesh
-        mesh.def_con = np.concatenate([interior, bc]).astype(np.int32)
+        mesh.def_con = np.concatenate([interior, bc, cut]).astype(np.int32)
+        mesh.n_cut_car, mesh.n_cut_def = 0, n_cut
         con_index = interior.shape[0] + np.arange(n_bc)
     else:
+        cut = np.zeros((n_cut, 3), np.int32)
+        cut[:, 0] = np.where(c_sign == 1, own, halo_slot); cut[:, 1] = np.where(c_sign == 1, halo_slot, own)
+        cut[:, 2] = c_dim
         bc[:, 6] = np.arange(n_bc)  # connection-owned unit normals
         mesh.normals[np.arange(n_bc), b_dim, :] = 1.
-        mesh.car_con = interior.astype(np.int32)
+        mesh.car_con = np.concatenate([interior, cut]).astype(np.int32)
         mesh.def_con = bc
+        mesh.n_cut_car, mesh.n_cut_def = n_cut, 0
         con_index = np.arange(n_bc)
+    mesh.pre_prolong = np.zeros(0, np.int32)
     mesh.bcs.append(dict(kind=bc_kind, inside_slot=inside.astype(np.int32), ghost_slot=ghost.astype(np.int32),
                          normal_slot=bc[:, 6].copy(), con_index=con_index.astype(np.int32), params=bc_params))
+    if any(b > 1 for b in blocks):
+        mesh.halo = Halo()
+        for peer in np.unique(c_peer):
+            sel = c_peer == peer  # both sides enumerate the shared plane in row-major order of the tangential indices
+            mesh.halo.send[int(peer)] = own[sel].astype(np.int32)
+            mesh.halo.recv[int(peer)] = halo_slot[sel].astype(np.int32)
     # geometry
     if deformed:
         dev = torch.device(device) if device is not None else torch.device("cpu")
-        vgrid = torch.stack(torch.meshgrid(*[torch.arange(n + 1, dtype=torch.float64, device=dev)*h]*nd, indexing="ij"), -1)
+        # extended index range: the block plus one layer of neighbours, clipped to the global box
+        lo_ext = [max(int(origin[d]) - 1, 0) for d in range(nd)]
+        hi_ext = [min(int(origin[d]) + n + 1, gdim[d]) for d in range(nd)]
+        ext = [hi_ext[d] - lo_ext[d] for d in range(nd)]
+        Ee = int(np.prod(ext))
+        eidx = np.stack(np.meshgrid(*[np.arange(lo_ext[d], hi_ext[d]) for d in range(nd)], indexing="ij"), -1).reshape(Ee, nd)
+        estr = np.array([int(np.prod(ext[d + 1:])) for d in range(nd)])
+        # vertices of the extended range (global vertex coordinates -> positions through the analytic warp)
+        vgrid = torch.stack(torch.meshgrid(*[torch.arange(lo_ext[d], hi_ext[d] + 1, dtype=torch.float64, device=dev)*h for d in range(nd)], indexing="ij"), -1)
         vgrid = default_warp(vgrid, warp_amplitude*h)
         vflat = vgrid.reshape(-1, nd)
-        vstr = torch.tensor([(n + 1)**(nd - 1 - d) for d in range(nd)], device=dev)
+        vstr = torch.tensor([int(np.prod([ext[k] + 1 for k in range(d + 1, nd)])) for d in range(nd)], device=dev)
         corner = torch.stack(torch.meshgrid(*[torch.arange(2, device=dev)]*nd, indexing="ij"), -1).reshape(-1, nd)
-        idx_t = torch.as_tensor(idx, device=dev)
-        vid = ((idx_t[:, None, :] + corner[None, :, :])*vstr).sum(-1)  # (E, 2^nd) vertex ids
+        eloc_t = torch.as_tensor(eidx - np.array(lo_ext), device=dev)
+        vid = ((eloc_t[:, None, :] + corner[None, :, :])*vstr).sum(-1)  # (Ee, 2^nd) vertex ids within the extended range
+        # which extended elements are the block's own, in the block's row-major order
+        own_ext = ((idx + origin - np.array(lo_ext))*estr).sum(-1)
+        is_own = np.zeros(Ee, bool); is_own[own_ext] = True
         out_dev = dev if keep_geometry_on_device else torch.device("cpu")
         refn = torch.empty((E, nd*nd, mesh.nq), dtype=torch.float64, device=out_dev)
         det = torch.empty((E, mesh.nq), dtype=torch.float64, device=out_dev)
-        fn = torch.empty((E, 2*nd, nd, nfq), dtype=torch.float64, device=out_dev)
-        vtss = torch.empty((E, 2**nd), dtype=torch.float64, device=dev)
         pos = torch.empty((E, nd, mesh.nq), dtype=torch.float64, device=out_dev)
-        nom = torch.full((E,), h, dtype=torch.float64, device=dev)
-        for s in range(0, E, geometry_chunk):
-            sl = slice(s, min(E, s + geometry_chunk))
+        fn_ext = torch.empty((Ee, 2*nd, nd, nfq), dtype=torch.float64, device=out_dev)  # face normals of the extended range
+        vtss = torch.empty((Ee, 2**nd), dtype=torch.float64, device=dev)
+        nom = torch.full((Ee,), h, dtype=torch.float64, device=dev)
+        local_of_ext = np.full(Ee, -1); local_of_ext[own_ext] = np.arange(E)
+        for s in range(0, Ee, geometry_chunk):
+            sl = slice(s, min(Ee, s + geometry_chunk))
             g = element_metrics(vflat[vid[sl]], nom[sl], basis)
-            refn[sl] = g["ref_normals"].to(out_dev); det[sl] = g["det"].to(out_dev)
-            fn[sl] = g["face_normals"].to(out_dev); vtss[sl] = g["vertex_tss"]; pos[sl] = g["pos"].to(out_dev)
+            fn_ext[sl] = g["face_normals"].to(out_dev); vtss[sl] = g["vertex_tss"]
+            lo_ids = local_of_ext[sl]
+            keep = np.nonzero(lo_ids >= 0)[0]
+            if keep.size:
+                kt = torch.as_tensor(keep, device=dev)
+                dst = torch.as_tensor(lo_ids[keep], device=out_dev)
+                refn[dst] = g["ref_normals"][kt].to(out_dev); det[dst] = g["det"][kt].to(out_dev); pos[dst] = g["pos"][kt].to(out_dev)
         # shared face normal = sign-aware average of both sides (src/Solver.cpp:327-352); here both signs are +1
         for d in range(nd):
-            lo = torch.as_tensor(np.nonzero(idx[:, d] < n - 1)[0], device=out_dev)
-            hi = lo + int(strides[d])
-            avg = 0.5*fn[lo, 2*d + 1] + 0.5*fn[hi, 2*d]
-            fn[lo, 2*d + 1] = avg
-            fn[hi, 2*d] = avg
+            lo = np.nonzero(eidx[:, d] < hi_ext[d] - 1)[0]
+            hi = lo + int(estr[d])
+            sel = is_own[lo] | is_own[hi]
+            lo_t = torch.as_tensor(lo[sel], device=out_dev); hi_t = torch.as_tensor(hi[sel], device=out_dev)
+            avg = 0.5*fn_ext[lo_t, 2*d + 1] + 0.5*fn_ext[hi_t, 2*d]
+            fn_ext[lo_t, 2*d + 1] = avg
+            fn_ext[hi_t, 2*d] = avg
+        fn = fn_ext[torch.as_tensor(own_ext, device=out_dev)]
+        del fn_ext
         # vertex time step scale: minimum over the elements sharing each vertex (src/Solver.cpp:380, src/Vertex.cpp vector_min)
-        vmin = torch.full(((n + 1)**nd,), float("inf"), dtype=torch.float64, device=dev)
+        vmin = torch.full((int(np.prod([e + 1 for e in ext])),), float("inf"), dtype=torch.float64, device=dev)
         vmin.scatter_reduce_(0, vid.reshape(-1), vtss.reshape(-1), reduce="amin")
-        vtss = vmin[vid]
+        vtss = vmin[vid[torch.as_tensor(own_ext, device=dev)]]
         mesh.vertex_tss = vtss.cpu().numpy()
         if keep_geometry_on_device:
             mesh.ref_normals, mesh.det, mesh.qpoint_pos = refn, det, pos
@@ -313,7 +421,7 @@ def box_mesh(n_dim, row_size, n, basis, deformed=False, warp_amplitude=0.1, bc_k
             mesh.normals = fn.reshape(E*2*nd, nd, nfq).numpy().copy()
     else:
         mesh.vertex_tss[:] = h/nd  # reference src/Element.cpp:17
-        mesh.qpoint_pos = qpoint_positions_cartesian(idx, mesh.nom_size, basis, nd)
+        mesh.qpoint_pos = qpoint_positions_cartesian(idx + origin, mesh.nom_size, basis, nd)
     return mesh
 
 

@@ -195,6 +195,19 @@ int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
  * (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341). The flux cache copy of :75-76 is host-side. */
 int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 
+/* ---- domain decomposition (new in this implementation: the reference is single-process) ----
+ * A rank's mesh is self-contained: faces of remote elements are HALO face slots (ordinary slots >= 2*n_dim*n_elem). The host
+ * registers the slots it sends / receives as face lists and moves them with face_list_gather / face_list_scatter (device
+ * buffers, asynchronous on the context's stream; the transport - NCCL send/recv - is the caller's). Cut connections must be
+ * the last `n_cut_car` / `n_cut_def` rows of the connection tables; `pre_prolong_ref` lists the refined faces whose coarse face
+ * is a halo slot (it is prolonged onto the local mortar faces after the exchange). */
+int hexed_b200_set_partition(hexed_b200_ctx* ctx, int n_cut_car, int n_cut_def, int n_pre_prolong, const int* pre_prolong_ref);
+int hexed_b200_face_list_gather(hexed_b200_ctx* ctx, int list_id, int kind, double* device_dst);
+int hexed_b200_face_list_scatter(hexed_b200_ctx* ctx, int list_id, int kind, const double* device_src);
+/* compute_euler split around the exchange: begin = Neighbor on interior connections; finish = everything else */
+int hexed_b200_compute_euler_begin(hexed_b200_ctx* ctx);
+int hexed_b200_compute_euler_finish(hexed_b200_ctx* ctx, hexed_b200_options opts);
+
 /* ---- profiling side-contract ---- */
 int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
 /* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined
