@@ -394,6 +394,14 @@ int hexed_b200_face_permutation_table(hexed_b200_ctx* c, const int dir[4], int* 
   return 0;
 }
 
+int hexed_b200_face_permutation_indices(int n_dim, int row_size, const int dir[4], int* out)
+{
+  if (n_dim < 1 || n_dim > 3 || row_size < 2 || row_size > MAX_RS) return HEXED_B200_INVALID_KERNEL;
+  if (dir[0] < 0 || dir[0] >= n_dim || dir[1] < 0 || dir[1] >= n_dim) return HEXED_B200_BAD_ARGUMENT;
+  build_perm(n_dim, row_size, dir[0], dir[1], dir[2] != 0, dir[3] != 0, out);
+  return 0;
+}
+
 int hexed_b200_face_permutation(hexed_b200_ctx* c, const int dir[4], int restore, double* data)
 {
   if (dir[0] < 0 || dir[0] >= c->nd || dir[1] < 0 || dir[1] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad direction");

@@ -1,0 +1,706 @@
+/* adapter.cpp -- hexed::compute_euler(Kernel_mesh, Kernel_options) & co. implemented on the B200 C ABI (include/hexed_b200.h).
+ *
+ * Replaces, in a Hexed build, src/kernels_convective.cpp, src/kernels_diffusive.cpp, src/kernels_max_dt.cpp and
+ * src/stabilizing_art_visc.cpp (and nothing else). Per mesh epoch it walks the Sequence<> views once, turns the pointer graph
+ * (faces owned by connections and aliased by elements, include/connection.hpp:111-123) into the slot tables the device uses, and
+ * from then on only moves data (policy: adapter.hpp) and drives the C ABI. No arithmetic of the hot path happens here: if the
+ * library finds no CUDA device every entry point throws.
+ */
+#include "adapter.hpp"
+#include "../../include/hexed_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <memory>
+#include <unordered_map>
+
+#ifdef HEXED_B200_WITH_HEXED_HEADERS
+#include <Gauss_legendre.hpp>
+#endif
+
+namespace hexed_b200
+{
+
+namespace
+{
+
+using hexed::Kernel_mesh;
+using hexed::Kernel_options;
+
+int ipow(int b, int e) {int r = 1; for (int i = 0; i < e; ++i) r *= b; return r;}
+
+// Basis keeps two of the numbers the kernels need protected (include/Basis.hpp:19-22); a derived class may re-export them
+struct Basis_access : public hexed::Basis
+{
+  using hexed::Basis::min_eig_convection;
+  using hexed::Basis::quadratic_safety;
+};
+
+void legendre_nodes(int row_size, double* out)
+{
+  #ifdef HEXED_B200_WITH_HEXED_HEADERS
+  hexed::Gauss_legendre gl(row_size); // pde::Advection always uses the Legendre nodes (include/pde.hpp:281)
+  for (int i = 0; i < row_size; ++i) out[i] = gl.node(i);
+  #else
+  static const double table [7][8] {
+    #include "legendre_nodes.inc"
+  };
+  for (int i = 0; i < row_size; ++i) out[i] = table[row_size - 2][i];
+  #endif
+}
+
+//! the packed basis table of hexed_b200_create (layout: include/hexed_b200.h "Basis tables")
+std::vector<double> pack_basis(const hexed::Basis& b)
+{
+  const int rs = b.row_size;
+  std::vector<double> p;
+  for (int i = 0; i < rs; ++i) p.push_back(b.node(i));
+  auto w = b.node_weights();
+  for (int i = 0; i < rs; ++i) p.push_back(w(i));
+  auto d = b.diff_mat();
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) p.push_back(d(i, j));
+  auto bd = b.boundary();
+  for (int s = 0; s < 2; ++s) for (int j = 0; j < rs; ++j) p.push_back(bd(s, j));
+  for (int deg = 0; deg < rs; ++deg) {
+    auto o = b.orthogonal(deg);
+    for (int i = 0; i < rs; ++i) p.push_back(o(i));
+  }
+  auto f = b.filter();
+  for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) p.push_back(f(i, j));
+  for (int transfer = 0; transfer < 2; ++transfer) {
+    for (int h = 0; h < 2; ++h) {
+      bool have = true;
+      decltype(b.prolong(0)) m;
+      try {m = transfer ? b.restrict(h) : b.prolong(h);}
+      catch (...) {have = false;} // Gauss_lobatto does not implement them (include/Gauss_lobatto.hpp)
+      for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j) p.push_back(have ? m(i, j) : 0.);
+    }
+  }
+  p.push_back((b.*(&Basis_access::min_eig_convection))());
+  p.push_back(b.min_eig_diffusion());
+  p.push_back((b.*(&Basis_access::quadratic_safety))());
+  std::vector<double> gl(rs);
+  legendre_nodes(rs, gl.data());
+  p.insert(p.end(), gl.begin(), gl.end());
+  return p;
+}
+
+/* Transport_model hides its five coefficients (include/Transport_model.hpp:16-27). They are read here by object layout:
+ * five doubles in declaration order followed by the `is_viscous` flag. LAYOUT-DEPENDENT -- the static_assert and the
+ * coefficient() cross-check below catch a changed class. */
+hexed_b200_transport transport(const hexed::Transport_model& t)
+{
+  static_assert(sizeof(hexed::Transport_model) == 6*sizeof(double), "Transport_model layout changed: update hexed_b200::transport");
+  double v [5];
+  std::memcpy(v, &t, sizeof(v));
+  hexed_b200_transport out {v[0], v[1], v[2], v[3], v[4], t.is_viscous ? 1 : 0};
+  const double probe = 17.25; // sqrt(temperature) of the cross-check
+  double r = probe/out.sqrt_ref_temp;
+  double expect = out.const_val + out.ref_val*r*r*r*(out.ref_temp + out.temp_offset)/(probe*probe + out.temp_offset);
+  double got = t.coefficient(probe);
+  if (std::abs(expect - got) > 1e-12*std::max(std::abs(got), 1e-300)) throw std::runtime_error("hexed_b200: Transport_model layout is not the expected one");
+  return out;
+}
+
+struct Mirror
+{
+  hexed_b200_ctx* ctx = nullptr;
+  int n_dim = 0, row_size = 0;
+  Flat_tables tab;
+  bool have_mesh = false;
+  std::vector<const void*> fingerprint;
+  int boundary_list = -1; // face list id of the boundary connections' faces
+  std::vector<int> boundary_slots;
+  std::vector<double> staging;
+  ~Mirror() {if (ctx) hexed_b200_destroy(ctx);}
+};
+
+Sync_mode g_mode = sync_every_call;
+int g_device = 0;
+std::map<std::pair<int, int>, std::unique_ptr<Mirror>> g_mirrors;
+
+void check(Mirror* m, int rc)
+{
+  if (!rc) return;
+  if (rc == HEXED_B200_INVALID_KERNEL) throw std::runtime_error("demand for invalid kernel"); // include/kernel_factory.hpp:114-116
+  throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_last_error(m ? m->ctx : nullptr));
+}
+
+std::vector<const void*> make_fingerprint(Kernel_mesh& km)
+{
+  std::vector<const void*> f;
+  auto num = [&](int n) {f.push_back(reinterpret_cast<const void*>(size_t(n)));};
+  num(km.n_dim); num(km.row_size);
+  f.push_back(&km.basis);
+  auto elems = [&](hexed::Sequence<hexed::Kernel_element&>& s) {
+    int n = s.size(); num(n);
+    for (int i : {0, n/2, n - 1}) if (n) {auto& e = s[i]; f.push_back(e.state()); f.push_back(e.face(0, false));}
+  };
+  auto cons = [&](hexed::Sequence<hexed::Kernel_connection&>& s) {
+    int n = s.size(); num(n);
+    for (int i : {0, n/2, n - 1}) if (n) {auto& c = s[i]; f.push_back(c.state(0, false)); f.push_back(c.state(1, false));}
+  };
+  elems(km.car_elems); elems(km.def_elems); cons(km.car_cons); cons(km.def_cons);
+  int nr = km.ref_faces.size(); num(nr);
+  for (int i : {0, nr/2, nr - 1}) if (nr) f.push_back(km.ref_faces[i].coarse);
+  return f;
+}
+
+} // namespace
+
+Flat_tables flatten(Kernel_mesh km)
+{
+  Flat_tables t;
+  const int nd = km.n_dim, nf = 2*nd;
+  t.n_dim = nd; t.row_size = km.row_size;
+  t.n_car = km.car_elems.size(); t.n_def = km.def_elems.size();
+  const int ne = t.n_car + t.n_def;
+  if (km.elems.size() != ne) throw std::runtime_error("hexed_b200: Kernel_mesh::elems is not car_elems + def_elems");
+  t.elem.resize(ne);
+  t.face_ptr.assign(size_t(nf)*ne, nullptr);
+  t.normal_ptr.assign(size_t(nf)*t.n_def, nullptr);
+  std::unordered_map<const double*, int> face_slot, normal_slot;
+  face_slot.reserve(size_t(nf)*ne*2);
+  for (int e = 0; e < ne; ++e) {
+    hexed::Kernel_element& el = e < t.n_car ? km.car_elems[e] : km.def_elems[e - t.n_car];
+    if (el.deformed() != (e >= t.n_car)) throw std::runtime_error("hexed_b200: element in the wrong Kernel_mesh view");
+    t.elem[e] = &el;
+    for (int f = 0; f < nf; ++f) {
+      double* p = el.face(f, false);
+      if (!p) continue;
+      t.face_ptr[size_t(e)*nf + f] = p;
+      face_slot[p] = e*nf + f;
+      if (e >= t.n_car) {
+        double* n = el.kernel_face_normal(f);
+        int s = (e - t.n_car)*nf + f;
+        t.normal_ptr[s] = n;
+        if (n) normal_slot[n] = s;
+      }
+    }
+  }
+  auto face_of = [&](double* p) -> int { // faces that no element aliases (ghosts, mortar faces) get the slots after the elements'
+    auto it = face_slot.find(p);
+    if (it != face_slot.end()) return it->second;
+    int s = int(t.face_ptr.size());
+    t.face_ptr.push_back(p); face_slot[p] = s;
+    return s;
+  };
+  int n_cc = km.car_cons.size();
+  t.car_con.resize(size_t(n_cc)*3);
+  for (int i = 0; i < n_cc; ++i) {
+    auto& c = km.car_cons[i];
+    auto dir = c.get_direction();
+    t.car_con[size_t(i)*3] = face_of(c.state(0, false));
+    t.car_con[size_t(i)*3 + 1] = face_of(c.state(1, false));
+    t.car_con[size_t(i)*3 + 2] = dir.i_dim[0];
+  }
+  int n_dc = km.def_cons.size();
+  t.def_con.resize(size_t(n_dc)*7);
+  std::vector<int> fresh_side1; // connections whose side 1 is not an element face: boundary or coarse-side mortar
+  for (int i = 0; i < n_dc; ++i) {
+    auto& c = km.def_cons[i];
+    auto dir = c.get_direction();
+    int* row = t.def_con.data() + size_t(i)*7;
+    row[0] = face_of(c.state(0, false));
+    int before = int(t.face_ptr.size());
+    row[1] = face_of(c.state(1, false));
+    if (row[1] >= before && row[0] < nf*ne) fresh_side1.push_back(i);
+    row[2] = dir.i_dim[0]; row[3] = dir.i_dim[1]; row[4] = dir.face_sign[0]; row[5] = dir.face_sign[1];
+    double* n = c.normal();
+    if (!n) throw std::runtime_error("hexed_b200: deformed connection without a normal");
+    auto it = normal_slot.find(n);
+    if (it != normal_slot.end()) row[6] = it->second;
+    else {
+      row[6] = int(t.normal_ptr.size());
+      t.normal_ptr.push_back(n); normal_slot[n] = row[6];
+    }
+  }
+  int n_rf = km.ref_faces.size();
+  t.ref_face.assign(size_t(n_rf)*7, -1);
+  for (int i = 0; i < n_rf; ++i) {
+    auto& r = km.ref_faces[i];
+    int* row = t.ref_face.data() + size_t(i)*7;
+    row[0] = face_of(r.coarse);
+    int n_fine = ipow(2, nd - 1);
+    for (int k = 0; k < nd - 1; ++k) if (r.stretch[k]) n_fine /= 2;
+    for (int k = 0; k < n_fine; ++k) row[1 + k] = face_of(r.fine[k]);
+    row[5] = r.stretch[0]; row[6] = nd > 2 ? int(r.stretch[1]) : 0;
+  }
+  // a connection whose side 1 belongs to no element is a boundary connection unless that face is a mortar face of a refined face
+  std::vector<char> is_mortar(t.face_ptr.size(), 0);
+  for (int i = 0; i < n_rf; ++i) for (int k = 1; k < 5; ++k) if (t.ref_face[size_t(i)*7 + k] >= 0) is_mortar[t.ref_face[size_t(i)*7 + k]] = 1;
+  for (int i : fresh_side1) if (!is_mortar[t.def_con[size_t(i)*7 + 1]]) t.boundary_con.push_back(i);
+  t.n_face_slot = int(t.face_ptr.size());
+  t.n_normal_slot = int(t.normal_ptr.size());
+  return t;
+}
+
+namespace
+{
+
+// ---- data movement between the host objects and the device mirror ----
+
+struct Slot_range {int first, n;};
+
+std::vector<Slot_range> slot_ranges(const Mirror& m, unsigned groups)
+{
+  const int nv = m.n_dim + 2, rs = m.row_size;
+  std::vector<Slot_range> r; // element slots in reference order (src/Element.cpp:114-142,187-189)
+  if (groups & state) r.push_back({0, nv});
+  if (groups & tss) r.push_back({nv, 1});
+  if (groups & art_visc) r.push_back({nv + 1, 6});
+  if (groups & advection) r.push_back({nv + 7, rs});
+  if (groups & res_cache) r.push_back({nv + 7 + rs, std::max(nv, rs)});
+  std::vector<Slot_range> merged; // adjacent groups travel together
+  for (auto s : r) {
+    if (!merged.empty() && merged.back().first + merged.back().n == s.first) merged.back().n += s.n;
+    else merged.push_back(s);
+  }
+  return merged;
+}
+
+void move_elements(Mirror& m, unsigned groups, bool up)
+{
+  const int nq = ipow(m.row_size, m.n_dim);
+  const int ne = int(m.tab.elem.size());
+  const int chunk = 8192;
+  for (auto range : slot_ranges(m, groups)) {
+    const size_t per_elem = size_t(range.n)*nq;
+    m.staging.resize(per_elem*std::min(chunk, std::max(ne, 1)));
+    for (int first = 0; first < ne; first += chunk) {
+      const int n = std::min(chunk, ne - first);
+      if (up) {
+        #pragma omp parallel for
+        for (int i = 0; i < n; ++i) std::memcpy(m.staging.data() + per_elem*i, m.tab.elem[first + i]->state() + size_t(range.first)*nq, per_elem*sizeof(double));
+        check(&m, hexed_b200_upload_elem_slots(m.ctx, m.staging.data(), per_elem, range.first, range.n, first, n));
+      } else {
+        check(&m, hexed_b200_download_elem_slots(m.ctx, m.staging.data(), per_elem, range.first, range.n, first, n));
+        #pragma omp parallel for
+        for (int i = 0; i < n; ++i) std::memcpy(m.tab.elem[first + i]->state() + size_t(range.first)*nq, m.staging.data() + per_elem*i, per_elem*sizeof(double));
+      }
+    }
+  }
+}
+
+//! one face array (`which` = HEXED_B200_FACE_STATE / _LDG / _WIDE) for all slots; `offset` doubles into each host face
+void move_face_array(Mirror& m, int which, size_t width, size_t offset, bool up)
+{
+  const int ns = m.tab.n_face_slot;
+  const int chunk = 1 << 16;
+  m.staging.resize(width*std::min(chunk, std::max(ns, 1)));
+  for (int first = 0; first < ns; first += chunk) {
+    const int n = std::min(chunk, ns - first);
+    if (up) {
+      #pragma omp parallel for
+      for (int i = 0; i < n; ++i) {
+        double* p = m.tab.face_ptr[first + i];
+        if (p) std::memcpy(m.staging.data() + width*i, p + offset, width*sizeof(double));
+        else std::memset(m.staging.data() + width*i, 0, width*sizeof(double));
+      }
+      check(&m, hexed_b200_upload(m.ctx, which, m.staging.data(), first, n));
+    } else {
+      check(&m, hexed_b200_download(m.ctx, which, m.staging.data(), first, n));
+      #pragma omp parallel for
+      for (int i = 0; i < n; ++i) {
+        double* p = m.tab.face_ptr[first + i];
+        if (p) std::memcpy(p + offset, m.staging.data() + width*i, width*sizeof(double));
+      }
+    }
+  }
+}
+
+void move_faces(Mirror& m, unsigned groups, bool up)
+{
+  const int nfq = ipow(m.row_size, m.n_dim - 1), nv = m.n_dim + 2;
+  if (groups & faces) { // `face(i, is_ldg)` = storage + is_ldg*n_var*nfq (src/Element.cpp:189, include/connection.hpp:66)
+    move_face_array(m, HEXED_B200_FACE_STATE, size_t(nv)*nfq, 0, up);
+    move_face_array(m, HEXED_B200_FACE_LDG, size_t(nv)*nfq, size_t(nv)*nfq, up);
+  }
+  if (groups & faces_wide) move_face_array(m, HEXED_B200_FACE_WIDE, size_t(m.n_dim + m.row_size)*nfq, 0, up);
+}
+
+void upload_geometry(Mirror& m)
+{
+  const int nd = m.n_dim, nq = ipow(m.row_size, nd), nfq = nq/m.row_size, nf = 2*nd, n_vert = ipow(2, nd);
+  const int ne = int(m.tab.elem.size()), n_def = m.tab.n_def, n_car = m.tab.n_car;
+  std::vector<double> buf(ne);
+  for (int e = 0; e < ne; ++e) buf[e] = m.tab.elem[e]->nominal_size();
+  check(&m, hexed_b200_upload(m.ctx, HEXED_B200_NOMINAL_SIZE, buf.data(), 0, ne));
+  buf.resize(size_t(ne)*n_vert);
+  for (int e = 0; e < ne; ++e) for (int v = 0; v < n_vert; ++v) buf[size_t(e)*n_vert + v] = m.tab.elem[e]->vertex_time_step_scale(v);
+  check(&m, hexed_b200_upload(m.ctx, HEXED_B200_VERTEX_TSS, buf.data(), 0, ne));
+  const int chunk = 8192;
+  for (int first = 0; first < n_def; first += chunk) {
+    const int n = std::min(chunk, n_def - first);
+    buf.resize(size_t(n)*nd*nd*nq);
+    #pragma omp parallel for
+    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nd*nd*nq, m.tab.elem[n_car + first + i]->reference_level_normals(), sizeof(double)*nd*nd*nq);
+    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_REF_NORMALS, buf.data(), first, n));
+    #pragma omp parallel for
+    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nq, m.tab.elem[n_car + first + i]->jacobian_determinant(), sizeof(double)*nq);
+    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_JAC_DET, buf.data(), first, n));
+  }
+  const int nn = m.tab.n_normal_slot;
+  buf.assign(size_t(nn)*nd*nfq, 0.);
+  for (int s = 0; s < nn; ++s) {
+    double* dst = buf.data() + size_t(s)*nd*nfq;
+    if (m.tab.normal_ptr[s]) std::memcpy(dst, m.tab.normal_ptr[s], sizeof(double)*nd*nfq);
+    else { // deformed element face in a Cartesian connection: unit normal of the face's dimension (include/Spatial.hpp:331-339,366)
+      const int i_dim = (s % nf)/2;
+      for (int q = 0; q < nfq; ++q) dst[size_t(i_dim)*nfq + q] = 1.;
+    }
+  }
+  if (nn) check(&m, hexed_b200_upload(m.ctx, HEXED_B200_NORMALS, buf.data(), 0, nn));
+}
+
+void download_uncert(Mirror& m)
+{
+  const int ne = int(m.tab.elem.size());
+  std::vector<double> buf(ne);
+  check(&m, hexed_b200_download(m.ctx, HEXED_B200_UNCERT, buf.data(), 0, ne));
+  for (int e = 0; e < ne; ++e) m.tab.elem[e]->uncert() = buf[e];
+}
+
+void move(Mirror& m, unsigned groups, bool up)
+{
+  move_elements(m, groups, up);
+  move_faces(m, groups, up);
+  if (up && (groups & geometry)) upload_geometry(m);
+  if (!up && (groups & uncert)) download_uncert(m);
+}
+
+void move_boundary(Mirror& m, bool up)
+{
+  if (m.boundary_slots.empty()) return;
+  const int nfq = ipow(m.row_size, m.n_dim - 1), nv = m.n_dim + 2;
+  const size_t width = size_t(nv)*nfq, n = m.boundary_slots.size();
+  m.staging.resize(width*n);
+  for (int kind = 0; kind < 2; ++kind) { // 0: state half, 1: LDG half
+    if (up) {
+      #pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) std::memcpy(m.staging.data() + width*i, m.tab.face_ptr[m.boundary_slots[i]] + kind*width, width*sizeof(double));
+      check(&m, hexed_b200_face_list_upload(m.ctx, m.boundary_list, kind, m.staging.data()));
+    } else {
+      check(&m, hexed_b200_face_list_download(m.ctx, m.boundary_list, kind, m.staging.data()));
+      #pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) std::memcpy(m.tab.face_ptr[m.boundary_slots[i]] + kind*width, m.staging.data() + width*i, width*sizeof(double));
+    }
+  }
+}
+
+//! finds (or builds) the device mirror of `km`; a new mesh epoch uploads geometry and, in resident mode, all data
+Mirror& mirror(Kernel_mesh& km)
+{
+  auto key = std::make_pair(km.n_dim, km.row_size);
+  auto& slot = g_mirrors[key];
+  if (!slot) {
+    std::unique_ptr<Mirror> m(new Mirror);
+    m->n_dim = km.n_dim; m->row_size = km.row_size;
+    std::vector<double> packed;
+    if (km.n_dim >= 1 && km.n_dim <= 3 && km.row_size >= 2 && km.row_size <= 8) packed = pack_basis(km.basis);
+    else packed.assign(1, 0.); // the library answers "demand for invalid kernel" before it looks at the table
+    check(nullptr, hexed_b200_create(&m->ctx, g_device, km.n_dim, km.row_size, packed.data(), int(packed.size())));
+    slot = std::move(m);
+  }
+  Mirror& m = *slot;
+  auto fp = make_fingerprint(km);
+  if (m.have_mesh && fp == m.fingerprint) return m;
+  m.tab = flatten(km);
+  hexed_b200_mesh_desc d {};
+  d.n_car = m.tab.n_car; d.n_def = m.tab.n_def; d.n_face_slot = m.tab.n_face_slot; d.n_normal_slot = m.tab.n_normal_slot;
+  d.n_car_con = int(m.tab.car_con.size()/3); d.n_def_con = int(m.tab.def_con.size()/7); d.n_ref = int(m.tab.ref_face.size()/7);
+  d.car_con = m.tab.car_con.data(); d.def_con = m.tab.def_con.data(); d.ref_face = m.tab.ref_face.data();
+  check(&m, hexed_b200_mesh_create(m.ctx, &d));
+  m.boundary_slots.clear();
+  for (int i : m.tab.boundary_con) {m.boundary_slots.push_back(m.tab.def_con[size_t(i)*7]); m.boundary_slots.push_back(m.tab.def_con[size_t(i)*7 + 1]);}
+  m.boundary_list = -1;
+  if (!m.boundary_slots.empty()) check(&m, hexed_b200_face_list_create(m.ctx, m.boundary_slots.data(), int(m.boundary_slots.size()), &m.boundary_list));
+  m.fingerprint = fp;
+  m.have_mesh = true;
+  upload_geometry(m);
+  if (g_mode == resident) move(m, all_elem | faces | faces_wide, true);
+  return m;
+}
+
+hexed_b200_options options(const Kernel_options& o) {return {o.dt, o.i_stage, o.compute_residual, o.use_filter};}
+
+//! RAII for one entry point: sync-in on construction, sync-out in finish() (not in the destructor: downloads can throw)
+struct Call
+{
+  Mirror& m;
+  unsigned out;
+  Call(Kernel_mesh& km, unsigned in, unsigned out_groups) : m{mirror(km)}, out{out_groups}
+  {
+    if (g_mode == sync_every_call) {
+      // kernels write their outputs only partly (e.g. write_face leaves ghost and mortar faces alone), so everything that will be
+      // downloaded must first hold the host's values
+      in |= out & ~unsigned(uncert);
+      if (in & tss) upload_geometry_light();
+      move(m, in, true);
+    }
+  }
+  void upload_geometry_light()
+  { // vertex_time_step_scale is rewritten by Solver::set_local_tss between calls; it is tiny, so it always travels with tss
+    const int n_vert = ipow(2, m.n_dim), ne = int(m.tab.elem.size());
+    std::vector<double> buf(size_t(ne)*n_vert);
+    for (int e = 0; e < ne; ++e) for (int v = 0; v < n_vert; ++v) buf[size_t(e)*n_vert + v] = m.tab.elem[e]->vertex_time_step_scale(v);
+    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_VERTEX_TSS, buf.data(), 0, ne));
+  }
+  void finish() {if (g_mode == sync_every_call) move(m, out, false);}
+};
+
+// the Stopwatch_tree side-contract (include/kernel_factory.hpp:32-45): every kernel call adds sequence.size() work units to its
+// child. Device work of one stage is a single asynchronous C call, so its host time is charged to the category stopwatches
+// as a whole; per-kernel device time is available from hexed_b200_kernel_stats.
+struct Watch
+{
+  std::vector<std::unique_ptr<hexed::Stopwatch::Operator>> running;
+  void start(hexed::Stopwatch_tree& t) {if (!t.stopwatch.running()) running.emplace_back(new hexed::Stopwatch::Operator(t.stopwatch));}
+};
+
+void count(hexed::Stopwatch_tree& category, const char* name, int units) {category.children.at(name).work_units_completed += units;}
+
+void count_convective(Kernel_mesh& km, Kernel_options& o)
+{
+  count(o.sw_car, "neighbor", km.car_cons.size()); count(o.sw_def, "neighbor", km.def_cons.size());
+  o.sw_pr.work_units_completed += km.ref_faces.size();
+  count(o.sw_car, "local", km.car_elems.size()); count(o.sw_def, "local", km.def_elems.size());
+  o.sw_pr.work_units_completed += km.ref_faces.size();
+}
+
+void count_diffusive(Kernel_mesh& km, Kernel_options& o)
+{ // src/kernels_diffusive.cpp:8-26
+  count(o.sw_car, "neighbor", km.car_cons.size()); count(o.sw_def, "neighbor", km.def_cons.size());
+  o.sw_pr.work_units_completed += 2*km.ref_faces.size();
+  count(o.sw_car, "local", km.car_elems.size()); count(o.sw_def, "local", km.def_elems.size());
+  if (!o.i_stage) {
+    o.sw_pr.work_units_completed += km.ref_faces.size();
+    count(o.sw_car, "neighbor", km.car_cons.size()); count(o.sw_def, "neighbor", km.def_cons.size());
+    o.sw_pr.work_units_completed += km.ref_faces.size();
+    count(o.sw_car, "reconcile LDG flux", km.car_elems.size()); count(o.sw_def, "reconcile LDG flux", km.def_elems.size());
+  }
+  o.sw_pr.work_units_completed += km.ref_faces.size();
+}
+
+struct Flux_bc_thunk
+{
+  Mirror* m;
+  std::function<void()>* fun;
+  static void call(void* user)
+  {
+    auto* self = static_cast<Flux_bc_thunk*>(user);
+    if (!*self->fun) return;
+    // the host callback reads and writes boundary faces (Solver::apply_flux_bcs, src/Solver.cpp:69-81)
+    if (g_mode == sync_every_call) move_faces(*self->m, faces, false); else move_boundary(*self->m, false);
+    (*self->fun)();
+    if (g_mode == sync_every_call) move_faces(*self->m, faces, true); else move_boundary(*self->m, true);
+  }
+};
+
+template <typename F>
+double max_dt_call(Kernel_mesh& km, Kernel_options& o, unsigned in, F launch)
+{
+  Call call(km, in | tss, tss);
+  Watch w; w.start(o.sw_car); w.start(o.sw_def);
+  double dt = 0.;
+  check(&call.m, launch(call.m.ctx, &dt));
+  count(o.sw_car, "compute time step", km.car_elems.size()); count(o.sw_def, "compute time step", km.def_elems.size());
+  call.finish();
+  return dt;
+}
+
+class Face_permutation_host : public hexed::Face_permutation_dynamic
+{
+  std::vector<int> table; // matched[p] = original[table[p]]
+  int n_var;
+  double* data;
+  std::vector<double> tmp;
+  public:
+  Face_permutation_host(int n_dim, int row_size, hexed::Connection_direction dir, double* d) : n_var{n_dim + 2}, data{d}
+  {
+    table.resize(ipow(row_size, n_dim - 1));
+    int dr [4] {dir.i_dim[0], dir.i_dim[1], dir.face_sign[0], dir.face_sign[1]};
+    int rc = hexed_b200_face_permutation_indices(n_dim, row_size, dr, table.data());
+    if (rc == HEXED_B200_INVALID_KERNEL) throw std::runtime_error("demand for invalid kernel");
+    if (rc) throw std::runtime_error("hexed_b200: bad connection direction");
+    tmp.resize(table.size());
+  }
+  void match_faces() override
+  {
+    const size_t n = table.size();
+    for (int v = 0; v < n_var; ++v) {
+      for (size_t p = 0; p < n; ++p) tmp[p] = data[v*n + table[p]];
+      std::memcpy(data + v*n, tmp.data(), n*sizeof(double));
+    }
+  }
+  void restore() override
+  {
+    const size_t n = table.size();
+    for (int v = 0; v < n_var; ++v) {
+      for (size_t p = 0; p < n; ++p) tmp[table[p]] = data[v*n + p];
+      std::memcpy(data + v*n, tmp.data(), n*sizeof(double));
+    }
+  }
+};
+
+} // namespace
+
+void set_sync_mode(Sync_mode mode) {g_mode = mode;}
+Sync_mode sync_mode() {return g_mode;}
+void set_device(int d) {g_device = d;}
+void invalidate() {for (auto& kv : g_mirrors) if (kv.second) kv.second->have_mesh = false;}
+void release() {g_mirrors.clear();}
+void to_host(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(geometry), false);}
+void to_device(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(uncert), true);}
+void boundary_faces_to_host(Kernel_mesh km) {move_boundary(mirror(km), false);}
+void ghost_faces_to_device(Kernel_mesh km) {move_boundary(mirror(km), true);}
+void synchronize(Kernel_mesh km) {Mirror& m = mirror(km); check(&m, hexed_b200_synchronize(m.ctx));}
+
+} // namespace hexed_b200
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the reference's entry points (include/kernels.hpp:22-42, include/stabilizing_art_visc.hpp:13)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace hexed
+{
+
+using namespace hexed_b200;
+
+void compute_euler(Kernel_mesh mesh, Kernel_options opts)
+{ // src/kernels_convective.cpp:18
+  Call call(mesh, state | tss | res_cache | faces, state | res_cache | faces);
+  Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
+  check(&call.m, hexed_b200_compute_euler(call.m.ctx, options(opts)));
+  count_convective(mesh, opts);
+  call.finish();
+}
+
+void compute_advection(Kernel_mesh mesh, Kernel_options opts, double advect_length)
+{ // src/kernels_convective.cpp:19
+  Call call(mesh, state | tss | advection | res_cache | faces_wide, advection | res_cache | faces_wide);
+  Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
+  check(&call.m, hexed_b200_compute_advection(call.m.ctx, options(opts), advect_length));
+  count_convective(mesh, opts);
+  call.finish();
+}
+
+void compute_navier_stokes(Kernel_mesh mesh, Kernel_options opts, std::function<void()> flux_bc, Transport_model visc, Transport_model therm_cond)
+{ // src/kernels_diffusive.cpp:28-29
+  Call call(mesh, state | tss | art_visc | res_cache | faces, state | res_cache | faces);
+  Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
+  Flux_bc_thunk thunk {&call.m, &flux_bc};
+  check(&call.m, hexed_b200_compute_navier_stokes(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
+  count_diffusive(mesh, opts);
+  call.finish();
+}
+
+void compute_smooth_av(Kernel_mesh mesh, Kernel_options opts, std::function<void()> flux_bc, double diff_time, double chebyshev_step)
+{ // src/kernels_diffusive.cpp:30-31
+  Call call(mesh, state | tss | art_visc | res_cache | faces, art_visc | res_cache | faces);
+  Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
+  Flux_bc_thunk thunk {&call.m, &flux_bc};
+  check(&call.m, hexed_b200_compute_smooth_av(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk, diff_time, chebyshev_step));
+  count_diffusive(mesh, opts);
+  call.finish();
+}
+
+void compute_fix_therm_admis(Kernel_mesh mesh, Kernel_options opts, std::function<void()> flux_bc)
+{ // src/kernels_diffusive.cpp:32
+  Call call(mesh, state | tss | art_visc | res_cache | faces, state | res_cache | faces);
+  Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
+  Flux_bc_thunk thunk {&call.m, &flux_bc};
+  check(&call.m, hexed_b200_compute_fix_therm_admis(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk));
+  count_diffusive(mesh, opts);
+  call.finish();
+}
+
+double max_dt_euler(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
+{ // src/kernels_max_dt.cpp:14
+  return max_dt_call(mesh, opts, state, [&](hexed_b200_ctx* c, double* dt) {
+    return hexed_b200_max_dt_euler(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+}
+
+double max_dt_navier_stokes(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time,
+                            Transport_model visc, Transport_model therm_cond)
+{ // src/kernels_max_dt.cpp:15-17
+  auto v = transport(visc), k = transport(therm_cond);
+  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
+    return hexed_b200_max_dt_navier_stokes(c, options(opts), convective_safety, diffusive_safety, local_time, v, k, dt);});
+}
+
+double max_dt_advection(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time, double advect_length)
+{ // src/kernels_max_dt.cpp:18-19
+  return max_dt_call(mesh, opts, state | advection, [&](hexed_b200_ctx* c, double* dt) {
+    return hexed_b200_max_dt_advection(c, options(opts), convective_safety, diffusive_safety, local_time, advect_length, dt);});
+}
+
+double max_dt_smooth_av(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
+{ // src/kernels_max_dt.cpp:20
+  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
+    return hexed_b200_max_dt_smooth_av(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+}
+
+double max_dt_fix_therm_admis(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
+{ // src/kernels_max_dt.cpp:21
+  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
+    return hexed_b200_max_dt_fix_therm_admis(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+}
+
+void compute_prolong(Kernel_mesh mesh, bool scale, bool offset)
+{ // src/kernels_convective.cpp:23-26
+  Call call(mesh, faces, faces);
+  check(&call.m, hexed_b200_compute_prolong(call.m.ctx, scale, offset));
+  call.finish();
+}
+
+void compute_restrict(Kernel_mesh mesh, bool scale, bool offset)
+{ // src/kernels_convective.cpp:28-31
+  Call call(mesh, faces, faces);
+  check(&call.m, hexed_b200_compute_restrict(call.m.ctx, scale, offset));
+  call.finish();
+}
+
+void compute_prolong_advection(Kernel_mesh mesh)
+{ // src/kernels_convective.cpp:33-36
+  Call call(mesh, faces_wide, faces_wide);
+  check(&call.m, hexed_b200_compute_prolong_advection(call.m.ctx));
+  call.finish();
+}
+
+std::unique_ptr<Face_permutation_dynamic> face_permutation(int n_dim, int row_size, Connection_direction dir, double* data)
+{ // src/kernels_convective.cpp:38-41. `data` is one host face ([n_var][nfq]); the integer table comes from the library.
+  return std::unique_ptr<Face_permutation_dynamic>(new Face_permutation_host(n_dim, row_size, dir, data));
+}
+
+void compute_write_face(Kernel_mesh mesh)
+{ // src/kernels_convective.cpp:43-46
+  Call call(mesh, state, faces);
+  check(&call.m, hexed_b200_compute_write_face(call.m.ctx));
+  call.finish();
+}
+
+void compute_write_face_advection(Kernel_mesh mesh)
+{ // src/kernels_convective.cpp:48-51
+  Call call(mesh, state | advection, faces_wide);
+  check(&call.m, hexed_b200_compute_write_face_advection(call.m.ctx));
+  call.finish();
+}
+
+void compute_write_face_smooth_av(Kernel_mesh mesh)
+{ // src/kernels_convective.cpp:53-56
+  Call call(mesh, state | art_visc, faces);
+  check(&call.m, hexed_b200_compute_write_face_smooth_av(call.m.ctx));
+  call.finish();
+}
+
+void stabilizing_art_visc(Kernel_mesh mesh, double char_speed)
+{ // src/stabilizing_art_visc.cpp:8-66
+  Call call(mesh, state, uncert);
+  check(&call.m, hexed_b200_stabilizing_art_visc(call.m.ctx, char_speed));
+  call.finish();
+}
+
+}

@@ -1,0 +1,77 @@
+/* adapter.hpp -- what the B200 replacement of Hexed's kernel drivers offers BEYOND include/kernels.hpp.
+ *
+ * adapter.cpp defines the reference's own free functions (hexed::compute_euler(Kernel_mesh, Kernel_options), ...; same
+ * signatures as include/kernels.hpp:22-42 and include/stabilizing_art_visc.hpp:13), so swapping it for
+ * src/kernels_convective.cpp, src/kernels_diffusive.cpp, src/kernels_max_dt.cpp and src/stabilizing_art_visc.cpp is the whole
+ * integration. The reference API has no begin/end-of-epoch call and its callers read and write element and
+ * face storage between kernel calls, so coherence is a policy the caller picks here:
+ *
+ *   sync_every_call (default)  every entry point uploads what it reads from the host objects and downloads what it wrote:
+ *                              always correct, no Solver change, PCIe-bound.
+ *   resident                   the device copy is authoritative between calls; entry points move nothing except their return
+ *                              value. The caller moves data explicitly with to_host / to_device (whole groups) or
+ *                              boundary_faces_to_host / ghost_faces_to_device (the per-stage traffic of host-applied
+ *                              boundary conditions, src/Solver.cpp:56-81).
+ */
+#ifndef HEXED_B200_ADAPTER_HPP_
+#define HEXED_B200_ADAPTER_HPP_
+
+#include <vector>
+#ifdef HEXED_B200_WITH_HEXED_HEADERS
+#include <kernels.hpp>
+#include <stabilizing_art_visc.hpp>
+#else
+#include "hexed_standin.hpp"
+#endif
+
+namespace hexed_b200
+{
+
+enum Sync_mode {sync_every_call = 0, resident = 1};
+
+//! groups of host data (bit mask) for to_host / to_device
+enum Data_group : unsigned {
+  state = 1,       //!< element slots [0, n_var)
+  tss = 2,         //!< time_step_scale()
+  art_visc = 4,    //!< bulk + laplacian AV coefficient and the 4 AV forcing slots
+  advection = 8,   //!< the row_size advection-state slots
+  res_cache = 16,  //!< residual_cache()
+  faces = 32,      //!< face(i, false) and face(i, true) of every face slot (elements, ghosts, mortar faces)
+  faces_wide = 64, //!< the same storage viewed as (n_dim + row_size) variables (pde::Advection)
+  geometry = 128,  //!< normals, Jacobian determinant, face normals, nominal size, vertex time step scale (to_device only)
+  uncert = 256,    //!< Kernel_element::uncert() (to_host only)
+  all_elem = state | tss | art_visc | advection | res_cache,
+  everything = all_elem | faces | uncert
+};
+
+void set_sync_mode(Sync_mode);
+Sync_mode sync_mode();
+void set_device(int cuda_device); //!< device used for contexts created from now on (default 0)
+//! forget the flattened mesh: the next entry point re-walks the Sequence views (call after mesh adaptation or `calc_jacobian`).
+//! Changes of the sequence sizes or of the first/middle/last storage pointers are detected without this.
+void invalidate();
+void release(); //!< destroy every device context (also done at exit)
+
+void to_host(hexed::Kernel_mesh, unsigned groups = everything);
+void to_device(hexed::Kernel_mesh, unsigned groups = everything | geometry);
+void boundary_faces_to_host(hexed::Kernel_mesh);  //!< both sides of every boundary connection, state + LDG halves
+void ghost_faces_to_device(hexed::Kernel_mesh);   //!< the same faces back
+void synchronize(hexed::Kernel_mesh);
+
+/*! \brief the pointer graph of a Kernel_mesh turned into slot tables (layout: include/hexed_b200.h). Device-free. */
+struct Flat_tables
+{
+  int n_dim = 0, row_size = 0;
+  int n_car = 0, n_def = 0, n_face_slot = 0, n_normal_slot = 0;
+  std::vector<int> car_con;  //!< [n][3]
+  std::vector<int> def_con;  //!< [n][7]
+  std::vector<int> ref_face; //!< [n][7]
+  std::vector<hexed::Kernel_element*> elem; //!< car_elems then def_elems
+  std::vector<double*> face_ptr;   //!< [n_face_slot] host address of `face(i, false)` / `state(side, false)`; nullptr = unconnected
+  std::vector<double*> normal_ptr; //!< [n_normal_slot] host address; nullptr = unit normal of the face's dimension
+  std::vector<int> boundary_con;   //!< indices into def_con of the boundary connections (side 1 = ghost face of no element)
+};
+Flat_tables flatten(hexed::Kernel_mesh);
+
+}
+#endif

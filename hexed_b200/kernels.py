@@ -61,6 +61,7 @@ SIGNATURES = {
     "hexed_b200_face_list_download": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_list_upload": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_permutation_table": [C.c_void_p, ip, ip],
+    "hexed_b200_face_permutation_indices": [C.c_int, C.c_int, ip, ip],
     "hexed_b200_set_partition": [C.c_void_p, C.c_int, C.c_int, C.c_int, ip],
     "hexed_b200_face_list_gather": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_list_scatter": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],

@@ -131,6 +131,9 @@ int hexed_b200_face_list_download(hexed_b200_ctx* ctx, int list_id, int kind, do
 int hexed_b200_face_list_upload(hexed_b200_ctx* ctx, int list_id, int kind, const double* src);
 /* integer table the kernels use for `Face_permutation::match_faces` (include/Spatial.hpp:85-129): out[nfq] */
 int hexed_b200_face_permutation_table(hexed_b200_ctx* ctx, const int dir[4], int* out);
+/* the same table without a context or a device (pure integer host logic, used by the C++ adapter's `face_permutation`):
+ * dir = {i_dim0, i_dim1, face_sign0, face_sign1}; out[row_size^(n_dim-1)]; matched[p] = original[out[p]] */
+int hexed_b200_face_permutation_indices(int n_dim, int row_size, const int dir[4], int* out);
 
 /* ---- stage drivers ---- */
 /* void compute_euler(Kernel_mesh, Kernel_options)                                  include/kernels.hpp:22, src/kernels_convective.cpp:18 */

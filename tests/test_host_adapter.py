@@ -1,0 +1,289 @@
+"""The C++ adapter (hexed_b200/host/adapter.cpp): `hexed::compute_euler(Kernel_mesh, Kernel_options)` & co. with the reference's
+signatures (include/kernels.hpp:22-42), driven on a reference-shaped pointer-graph mesh (hexed_b200/host/harness.cpp).
+
+CPU part (no marker): the device-free flattening reproduces the integer tables the mesh was built from bit for bit, the
+library exports every symbol, and the whole adapter -> C ABI -> kernel-source chain agrees with the oracle when the C ABI is the
+host-thread emulation build of the same .cu files. GPU part (-m gpu): the same calls through libhexed_b200.so on the B200.
+The boundary conditions are applied ON THE HOST between calls (oracle code on the fetched FlatMesh), the way Solver does."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import hexed_b200 as hb
+from hexed_b200 import mesh as M
+from hexed_b200.tables import Connection_direction
+import host_harness as H
+from pyoracle import EULER, NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS
+import pyoracle
+from util import rel_l2, assert_euler_parity, assert_pde_parity, prepare_pde_state, density_wave, freestream_state
+
+
+@pytest.fixture(scope="module")
+def host_emu(emu_lib):
+    return H.build(emu=True)
+
+
+@pytest.fixture(scope="module")
+def host_gpu(gpu_lib):
+    return H.build(emu=False)
+
+
+def soup(nd, rs, seed, **kw):
+    rng = np.random.default_rng(seed)
+    m = M.soup_mesh(nd, rs, rng, **kw)
+    M.random_flow_state(m, rng)
+    return m, rng
+
+
+# ------------------------------------------------------------------------------------------------ flattening (integer-exact)
+@pytest.mark.parametrize("nd,rs", [(1, 2), (2, 3), (2, 6), (3, 2), (3, 6)])
+def test_flatten_reproduces_tables(host_emu, nd, rs):
+    """pointer graph -> slot tables must give back exactly the tables the pointer graph was made from: connection order,
+    face slots of both sides, direction codes, normal slots, refined-face fine ordering and stretch flags, boundary detection"""
+    m, _ = soup(nd, rs, 5 + nd, n_car=8, n_def=14, n_ref=6)
+    for seed in (1, 2):  # two different heap layouts
+        h = H.HostHarness(host_emu, m, hb.gauss_legendre(rs), seed=seed)
+        counts, car, dfc, ref, bnd = h.flatten()
+        assert counts[0] == m.n_car and counts[1] == m.n_def
+        assert counts[2] == m.n_face_slot and counts[3] == m.n_normal_slot
+        assert np.array_equal(car, m.car_con)
+        assert np.array_equal(dfc, m.def_con)
+        assert np.array_equal(ref, m.ref_face)
+        assert np.array_equal(bnd, m.bcs[0]["con_index"])
+        assert counts[5] == int((H.normal_present(m) == 0).sum())  # faces that fall back to the unit normal
+        h.close()
+
+
+def test_flatten_box_with_cartesian_boundaries(host_emu):
+    """a Cartesian box: boundary connections of Cartesian elements sit in def_cons (src/Accessible_mesh.cpp:136-147)"""
+    basis = hb.gauss_legendre(3)
+    m = M.box_mesh(2, 3, 3, basis, deformed=False, bc_kind=M.BC_COPY)
+    h = H.HostHarness(host_emu, m, basis)
+    counts, car, dfc, ref, bnd = h.flatten()
+    assert np.array_equal(car, m.car_con) and np.array_equal(dfc, m.def_con)
+    assert sorted(bnd.tolist()) == sorted(np.concatenate([bc["con_index"] for bc in m.bcs]).tolist())
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------------ drivers shared by emu and GPU
+def host_bcs(oracle, h, work, resident, flux=False):
+    """what Solver::apply_state_bcs / apply_flux_bcs do: read the inside faces of the host objects, write the ghost faces"""
+    if resident:
+        h.boundary_faces_to_host()
+    h.fetch(work)
+    (oracle.apply_flux_bcs if flux else oracle.apply_state_bcs)(work)
+    h.put(work)
+    if resident:
+        h.ghost_faces_to_device()
+
+
+def run_euler(oracle, lib, m, basis, resident, n_steps=2, local_time=False, use_filter=False, safety=0.7):
+    ref, work = m.copy(), m.copy()
+    h = H.HostHarness(lib, m, basis, seed=3)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    dts = []
+    for _ in range(n_steps):
+        dt_o = oracle.max_dt(EULER, basis, ref, safety, safety, local_time)
+        dt_d = h.call("max_dt_euler", safety, safety, local_time)
+        dts.append((dt_d, dt_o))
+        for stage in (0, 1):
+            oracle.apply_state_bcs(ref)
+            oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage, use_filter=use_filter)
+            host_bcs(oracle, h, work, resident)
+            h.call("compute_euler", dt=dt_o, i_stage=stage, use_filter=use_filter)
+    if resident:
+        h.to_host(H.ALL_ELEM | H.FACES | H.UNCERT)
+    h.fetch(work)
+    units = h.work_units()
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    return work, ref, dts, units
+
+
+def check_work_units(m, units, n_steps, diffusive_stage0=0):
+    n_cc, n_dc, n_ref = m.car_con.shape[0], m.def_con.shape[0], m.ref_face.shape[0]
+    stages = 2*n_steps
+    assert units[0] == n_cc*stages and units[4] == n_dc*stages          # "neighbor"
+    assert units[1] == m.n_car*stages and units[5] == m.n_def*stages    # "local"
+    assert units[3] == m.n_car*n_steps and units[7] == m.n_def*n_steps  # "compute time step"
+    assert units[8] == 2*n_ref*stages                                   # restrict + prolong through sw_pr
+    assert units[9] > 0
+
+
+def run_pde(oracle, lib, m, basis, pde, resident):
+    ref, work = m.copy(), m.copy()
+    wide = pde == ADVECTION
+    h = H.HostHarness(lib, m, basis, seed=4)
+    if wide:
+        h.put(m, wide=True)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    visc_o, cond_o = pyoracle.sutherland(1.7e-5, 273., 110.), pyoracle.constant(2.5e-2)
+    visc_h, cond_h = H.sutherland(1.7e-5, 273., 110.), H.constant(2.5e-2)
+    s = 0.3
+    if pde == NAVIER_STOKES:
+        dt_o = oracle.max_dt(pde, basis, ref, s, s, False, visc_o, cond_o)
+        dt_d = h.call("max_dt_navier_stokes", s, s, False, *visc_h, *cond_h)
+        oracle.apply_state_bcs(ref)
+        oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0)
+        host_bcs(oracle, h, work, resident)
+
+        def flux_bc():  # the adapter has already brought the faces the callback touches back to the host objects
+            h.fetch(work); oracle.apply_flux_bcs(work); h.put(work)
+        h.set_flux_bc(flux_bc)
+        h.call("compute_navier_stokes", *visc_h, *cond_h, dt=dt_o, i_stage=0)
+        oracle.apply_state_bcs(ref)
+        oracle.compute_euler(basis, ref, dt=dt_o, i_stage=1)
+        host_bcs(oracle, h, work, resident)
+        h.call("compute_euler", dt=dt_o, i_stage=1)
+    elif pde == ADVECTION:
+        dt_o = oracle.max_dt(pde, basis, ref, s, s, False, advect_length=0.7)
+        dt_d = h.call("max_dt_advection", s, s, False, 0.7)
+        for stage in (0, 1):
+            oracle.compute_advection(basis, ref, 0.7, dt=dt_o, i_stage=stage)
+            h.call("compute_advection", 0.7, dt=dt_o, i_stage=stage)
+    elif pde == SMOOTH_AV:
+        dt_o = oracle.max_dt(pde, basis, ref, s, s, False)
+        dt_d = h.call("max_dt_smooth_av", s, s, False)
+        oracle.compute_smooth_av(basis, ref, None, 0.4, 1.3, dt=dt_o, i_stage=0)
+        h.call("compute_smooth_av", 0.4, 1.3, dt=dt_o, i_stage=0)
+    else:
+        dt_o = oracle.max_dt(pde, basis, ref, s, s, False)
+        dt_d = h.call("max_dt_fix_therm_admis", s, s, False)
+        oracle.compute_fix_therm_admis(basis, ref, None, dt=dt_o, i_stage=0)
+        h.call("compute_fix_therm_admis", dt=dt_o, i_stage=0)
+    if resident:
+        h.to_host(H.ALL_ELEM | (H.FACES_WIDE if wide else H.FACES))
+    h.fetch(work, wide=wide)
+    if wide:  # the narrow views of the same host storage are not what this PDE wrote
+        work.face_state, work.face_ldg, ref.face_state, ref.face_ldg = None, None, None, None
+    else:
+        work.face_wide, ref.face_wide = None, None
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    return work, ref, [(dt_d, dt_o)]
+
+
+# ------------------------------------------------------------------------------------------------ CPU: adapter on the emulation build
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("nd,rs", [(2, 3), (3, 2)])
+def test_adapter_euler_emu(oracle, host_emu, nd, rs, resident):
+    m, _ = soup(nd, rs, 21, with_ldg=True)
+    out, ref, dts, units = run_euler(oracle, host_emu, m, hb.gauss_legendre(rs), resident, n_steps=2)
+    assert_euler_parity(out, ref, dts)
+    check_work_units(m, units, 2)
+
+
+def test_adapter_euler_options_emu(oracle, host_emu):
+    m, _ = soup(2, 4, 22, with_ldg=True)
+    out, ref, dts, _ = run_euler(oracle, host_emu, m, hb.gauss_legendre(4), False, n_steps=1, local_time=True, use_filter=True, safety=0.05)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("pde", [NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS])
+def test_adapter_other_pdes_emu(oracle, host_emu, pde, resident):
+    m, rng = soup(2, 3, 30 + pde, with_ldg=True, with_wide=True)
+    prepare_pde_state(m, rng, pde)
+    out, ref, dts = run_pde(oracle, host_emu, m, hb.gauss_legendre(3), pde, resident)
+    assert_pde_parity(out, ref, dts)
+
+
+def test_adapter_standalone_entry_points_emu(oracle, host_emu):
+    """write_face, prolong, restrict, stabilizing_art_visc through the reference signatures"""
+    basis = hb.gauss_legendre(4)
+    m, rng = soup(2, 4, 41, with_ldg=True)
+    m.state()[:, 2] *= 1 + 0.3*rng.random(m.state()[:, 2].shape)
+    ref, work = m.copy(), m.copy()
+    h = H.HostHarness(host_emu, m, basis)
+    h.invalidate()
+    oracle.compute_write_face(basis, ref); h.call("compute_write_face")
+    oracle.compute_prolong(basis, ref); h.call("compute_prolong", 0, 0)
+    oracle.compute_restrict(basis, ref); h.call("compute_restrict", 1, 0)
+    oracle.stabilizing_art_visc(basis, ref, 340.); h.call("stabilizing_art_visc", 340.)
+    h.fetch(work)
+    assert rel_l2(work.face_state, ref.face_state) <= 1e-13
+    assert np.abs(work.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
+    h.close()
+
+
+def test_adapter_mesh_epoch_detection_emu(oracle, host_emu):
+    """a different mesh behind the same (n_dim, row_size) must be re-flattened without an explicit invalidate"""
+    basis = hb.gauss_legendre(3)
+    for seed, n_def in ((51, 10), (52, 7)):
+        m, _ = soup(2, 3, seed, n_def=n_def, with_ldg=True)
+        ref, work = m.copy(), m.copy()
+        h = H.HostHarness(host_emu, m, basis, seed=seed)
+        oracle.compute_euler(basis, ref, dt=1e-4, i_stage=0)
+        h.call("compute_euler", dt=1e-4, i_stage=0)
+        h.fetch(work)
+        assert rel_l2(work.state(), ref.state()) <= 1e-11
+        h.lib.hbh_destroy.argtypes = [ctypes.c_void_p]
+        # deliberately no h.close() (which invalidates): the next mesh must be detected through its fingerprint
+        h.h = None
+
+
+def test_adapter_errors(host_emu):
+    """bad (n_dim, row_size) -> std::runtime_error("demand for invalid kernel") like include/kernel_factory.hpp:114-116"""
+    m, _ = soup(2, 3, 61)
+    h = H.HostHarness(host_emu, m, hb.gauss_legendre(3))
+    with pytest.raises(RuntimeError, match="demand for invalid kernel"):
+        h.face_permutation(4, 3, [0, 0, 1, 0], np.zeros(64))
+    with pytest.raises(RuntimeError, match="demand for invalid kernel"):
+        h.face_permutation(2, 9, [0, 0, 1, 0], np.zeros(64))
+    h.close()
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_adapter_face_permutation(oracle, host_emu, nd):
+    """hexed::face_permutation(n_dim, row_size, dir, data)->match_faces()/restore() against the oracle for every direction"""
+    rs = 5
+    m, rng = soup(nd, 2, 62)
+    h = H.HostHarness(host_emu, m, hb.gauss_legendre(2))
+    for d0 in range(nd):
+        for d1 in range(nd):
+            for s0 in range(2):
+                for s1 in range(2):
+                    data = rng.standard_normal((nd + 2)*rs**(nd - 1))
+                    a, b = data.copy(), data.copy()
+                    oracle.face_permutation(nd, rs, nd + 2, Connection_direction([d0, d1], [s0, s1]), a)
+                    h.face_permutation(nd, rs, [d0, d1, s0, s1], b)
+                    assert np.array_equal(a, b)
+                    h.face_permutation(nd, rs, [d0, d1, s0, s1], b, restore=True)
+                    assert np.array_equal(b, data)
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------------ GPU: adapter on the product library
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 4), (3, 6)])
+def test_adapter_euler_gpu(oracle, host_gpu, nd, rs, resident):
+    m, _ = soup(nd, rs, 71, n_car=8, n_def=14, n_ref=6, with_ldg=True)
+    out, ref, dts, units = run_euler(oracle, host_gpu, m, hb.gauss_legendre(rs), resident, n_steps=2)
+    assert_euler_parity(out, ref, dts)
+    check_work_units(m, units, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_box_gpu(oracle, host_gpu, resident):
+    """the headline mesh class at an oracle-friendly size: 3-D deformed box, row size 6, host-applied freestream ghosts"""
+    basis = hb.gauss_legendre(6)
+    m = M.box_mesh(3, 6, 5, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler(oracle, host_gpu, m, basis, resident, n_steps=3)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("pde", [NAVIER_STOKES, ADVECTION, SMOOTH_AV, FIX_THERM_ADMIS])
+def test_adapter_other_pdes_gpu(oracle, host_gpu, pde, resident):
+    m, rng = soup(3, 4, 80 + pde, with_ldg=True, with_wide=True)
+    prepare_pde_state(m, rng, pde)
+    out, ref, dts = run_pde(oracle, host_gpu, m, hb.gauss_legendre(4), pde, resident)
+    assert_pde_parity(out, ref, dts)
