@@ -31,6 +31,12 @@ struct GArgs
   PdeParams pp;
 };
 
+template <class K> int set_smem(hexed_b200_ctx* c, K k, size_t smem)
+{
+  if (smem > 48*1024) HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
 template <int ND, int RS> struct Line
 {
   int stride, node, base, fq;
@@ -434,6 +440,227 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
   }
 }
 
+#if HB_PDE == 1 /* PDE_NAVIER_STOKES */
+/* ---------------- Navier-Stokes Local, 3-D, line-task formulation ----------------
+ * Same arithmetic as g_local_kernel<3, RS, PdeNs<3, RS, true>, DEF> without the modal filter (reference include/Spatial.hpp:326-509
+ * for pde::Navier_stokes<true>), reorganised because the first profile of the point-per-thread kernel (profiles/r01c_ncu_full_ns.md)
+ * showed it instruction- and occupancy-bound: 220 registers -> one 216-thread CTA per SM, 4 000 instructions per point, 9 % of the
+ * HBM roofline. Here one thread owns a LINE of row_size points wherever a 1-D operator is applied (the products along the line are
+ * formed once and reused for row_size outputs, operator entries are constant-bank operands) and a POINT only for the physics:
+ *   P1  gradient of the state: one sub-phase per reference direction d; task = (line of d, physical component j) accumulates
+ *       D_d(n_dj * u) + lifted LDG face terms into G[v][j]                          (Spatial.hpp:371-402)
+ *   P2  pointwise: convective and diffusive flux in reference directions; F <- flux_conv, G <- flux_diff   (:405-435)
+ *   P3  line (d, l): F <- -(D_d flux_conv + lifted numerical flux) in place; diffusive flux extrapolated to faces 2d, 2d+1 -> LDG
+ *       face storage; G <- -diff_mat_d flux_diff in place                           (:445-468)
+ *   P4  pointwise: sum over d, residual cache, update                                (:484-503)
+ * Shared memory: state + G + F = 7 n_var nq doubles (60 KB at row size 6) -> 3 CTAs of 128 threads per SM; everything that is
+ * used once (face data, normals, determinant, AV coefficients) is read straight from global memory by the thread that needs it. */
+template <int RS, bool DEF>
+struct NsCfg
+{
+  static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5, n_line = ND*nfq;
+  static constexpr int threads = ((n_line + 31)/32)*32;
+  static constexpr int s_state = 0, s_grad = nv*nq, s_flux = s_grad + ND*nv*nq, smem_doubles = s_flux + ND*nv*nq;
+};
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(NsCfg<RS, DEF>::threads, 3)
+ns_local_line_kernel(GArgs a, Ops ops)
+{
+  using C = NsCfg<RS, DEF>;
+  using P = PdeNs<3, RS, true>;
+  constexpr int ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads;
+  constexpr int cs = nv > RS ? nv : RS;
+  HB_DYN_SMEM(double, smem);
+  double* S = smem + C::s_state;
+  double* G = smem + C::s_grad;
+  double* F = smem + C::s_flux;
+  const int t = threadIdx.x;
+  const int e = a.elem_begin + blockIdx.x;
+  if (e >= a.elem_end) return;
+  const double nom = a.nom[e];
+  {
+    const double* src = a.ed.state + (size_t)e*nv*nq;
+    for (int i = t; i < nv*nq; i += T) S[i] = src[i];
+  }
+  const double* fldg = a.faces_ldg + (size_t)e*2*ND*wl;
+  __syncthreads();
+
+  /* ---- P1: gradient ---- */
+  if constexpr (DEF) {
+    const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+    const double* fn = a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq;
+    const int l = t % nfq, j = t/nfq; // task of every sub-phase: line l of the current direction, physical component j
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (t < ND*nfq) {
+        const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+        const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
+        double nk[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride];
+        const double fn0 = fn[((2*d)*ND + j)*nfq + l], fn1 = fn[((2*d + 1)*ND + j)*nfq + l];
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          double p[RS];
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) p[k] = nk[k]*S[v*nq + q0 + k*stride];
+          const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            double* g = G + (v*ND + j)*nq + q0 + i*stride;
+            if (d == 0) *g = acc/nom; else *g += acc/nom;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    if (t < C::n_line) {
+      const int d = t/nfq, l = t % nfq;
+      const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+      const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double p[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
+        const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          G[(v*ND + d)*nq + q0 + i*stride] = acc/nom;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  /* ---- P2: pointwise fluxes ---- */
+  for (int q = t; q < nq; q += T) {
+    typename P::template Comp<ND> comp;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) comp.state[v] = S[v*nq + q];
+    comp.state[nv] = a.ed.av[((size_t)e*2)*nq + q];
+    comp.state[nv + 1] = a.ed.av[((size_t)e*2 + 1)*nq + q];
+    if constexpr (DEF) {
+      const double det = a.det[(size_t)(e - a.n_car)*nq + q];
+      const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.normal[j][d] = rn[(d*ND + j)*nq + q];
+      #pragma unroll
+      for (int v = 0; v < nv; ++v)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q]/det;
+    } else {
+      #pragma unroll
+      for (int v = 0; v < nv; ++v)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q];
+    }
+    comp.compute_flux_conv(a.pp);
+    comp.compute_flux_diff(a.pp);
+    #pragma unroll
+    for (int d = 0; d < ND; ++d)
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        F[(d*nv + v)*nq + q] = comp.flux_conv[v][d];
+        G[(d*nv + v)*nq + q] = comp.flux_diff[v][d]; // all of this point's gradient entries are in registers by now
+      }
+  }
+  __syncthreads();
+
+  /* ---- P3: line derivatives in place, diffusive flux to the LDG faces ---- */
+  if (t < C::n_line) {
+    const int d = t/nfq, l = t % nfq;
+    const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+    const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
+    const double* fc = a.faces + (size_t)e*2*ND*a.face_width;
+    double* fl = a.faces_ldg + (size_t)e*2*ND*wl;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      double* row = F + (d*nv + v)*nq + q0;
+      double f[RS];
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
+      const double b0 = fc[(size_t)(2*d)*a.face_width + v*nfq + l], b1 = fc[(size_t)(2*d + 1)*a.face_width + v*nfq + l];
+      #pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        double acc = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
+        acc += ops.lift[i][0]*b0;
+        acc += ops.lift[i][1]*b1;
+        row[i*stride] = -acc;
+      }
+      double* drow = G + (d*nv + v)*nq + q0;
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
+      double e0 = 0, e1 = 0;
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) { e0 += ops.bnd[0][k]*f[k]; e1 += ops.bnd[1][k]*f[k]; }
+      fl[(size_t)(2*d)*wl + v*nfq + l] = e0;
+      fl[(size_t)(2*d + 1)*wl + v*nfq + l] = e1;
+      #pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        double acc = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
+        drow[i*stride] = -acc;
+      }
+    }
+  }
+  __syncthreads();
+
+  /* ---- P4: combine and update ---- */
+  for (int q = t; q < nq; q += T) {
+    double mult = a.update*a.ed.tss[(size_t)e*nq + q]/nom;
+    if constexpr (DEF) mult /= a.det[(size_t)(e - a.n_car)*nq + q];
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      double r0 = 0., r1 = 0.;
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) { r0 += F[(d*nv + v)*nq + q]; r1 += G[(d*nv + v)*nq + q]; }
+      double* cache = a.ed.cache + ((size_t)e*cs + v)*nq + q;
+      double u = r0;
+      *cache = u;
+      u += r1;
+      u *= mult;
+      if (a.compute_residual) *cache = u;
+      else a.ed.state[((size_t)e*nv + v)*nq + q] = S[v*nq + q] + u;
+    }
+  }
+}
+
+/* returns -1 when the combination is not covered and the caller should use g_local_kernel */
+template <int ND, int RS>
+int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
+{
+  if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
+    if (a.use_filter || !c->use_pipe) return -1;
+    using C = NsCfg<RS, true>;
+    const size_t smem = sizeof(double)*C::smem_doubles;
+    const int grid = a.elem_end - a.elem_begin;
+    if (deformed) { auto k = ns_local_line_kernel<RS, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops); }
+    else { auto k = ns_local_line_kernel<RS, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops); }
+    return 0;
+  } else {
+    return -1;
+  }
+}
+#endif
+
 /* ---------------- Reconcile_ldg_flux ---------------- */
 template <int ND, int RS, class P, bool DEF>
 __global__ void __launch_bounds__(GCfg<ND, RS, P>::threads)
@@ -616,12 +843,6 @@ int fill_args(hexed_b200_ctx* c, GArgs& a, const PdeParams& pp)
   return 0;
 }
 
-template <class K> int set_smem(hexed_b200_ctx* c, K k, size_t smem)
-{
-  if (smem > 48*1024) HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return 0;
-}
-
 int g_neighbor(hexed_b200_ctx* c, int deformed, const PdeParams& pp, bool reconcile)
 {
   const int n_con = deformed ? c->n_def_con : c->n_car_con;
@@ -675,6 +896,13 @@ int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdePara
         else { auto k = g_reconcile_kernel<ND, RS, P, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
       } else return fail(c, HEXED_B200_BAD_ARGUMENT, "Reconcile_ldg_flux needs a diffusive PDE");
     } else {
+#if HB_PDE == 1 /* PDE_NAVIER_STOKES */
+      {
+        const int r = launch_ns_local_line<ND, RS>(c, a, deformed);
+        if (r > 0) return r;
+        if (r == 0) { count_launch(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR); HB_CUDA(c, cudaGetLastError()); return 0; }
+      }
+#endif
       if (deformed) { auto k = g_local_kernel<ND, RS, P, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
       else { auto k = g_local_kernel<ND, RS, P, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
     }

@@ -274,6 +274,12 @@ class Device:
     def face_list_scatter(self, list_id, device_src, kind=0):
         self._check(self.lib.hexed_b200_face_list_scatter(self.ctx, list_id, kind, _addr(device_src)))
 
+    def set_partition(self, n_cut_car, n_cut_def, pre_prolong=()):
+        """the last n_cut_* rows of the connection tables wait for faces that arrive from outside (halo exchange, or ghost faces a
+        host boundary condition writes): compute_euler_begin skips them, compute_euler_finish does them first"""
+        pp = _i32(pre_prolong)
+        self._check(self.lib.hexed_b200_set_partition(self.ctx, int(n_cut_car), int(n_cut_def), pp.size, pp.ctypes.data_as(ip)))
+
     def compute_euler_begin(self):
         self._check(self.lib.hexed_b200_compute_euler_begin(self.ctx))
 

@@ -77,3 +77,22 @@ def test_box_3d_pipelined_local(oracle, emu_lib, deformed):
     oracle.compute_write_face(basis, m)
     out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2)
     assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("kind", ["soup", "box_car", "box_def"])
+def test_navier_stokes_3d_line_kernel(oracle, emu_lib, kind):
+    """3-D row size 4 Navier-Stokes takes the line-task Local kernel (ns_local_line_kernel in generic_part.cu)"""
+    rng = np.random.default_rng(77)
+    basis = hb.gauss_legendre(4)
+    if kind == "soup":
+        m = M.soup_mesh(3, 4, rng, n_car=3, n_def=5, n_ref=2, with_ldg=True)
+        M.random_flow_state(m, rng)
+    else:
+        m = M.box_mesh(3, 4, 2, basis, deformed=kind == "box_def", bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+        density_wave(m, basis)
+        oracle.compute_write_face(basis, m)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2)
+    assert_pde_parity(out, ref, dts)
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
+    assert_pde_parity(out, ref, dts)

@@ -164,7 +164,7 @@ def test_other_pdes_residual_mode_and_local_time(oracle, gpu_lib, pde):
     assert_pde_parity(out, ref, dts)
 
 
-@pytest.mark.parametrize("nd,n,deformed", [(2, 8, True), (2, 8, False), (3, 4, True)])
+@pytest.mark.parametrize("nd,n,deformed", [(2, 8, True), (2, 8, False), (3, 4, True), (3, 4, False)])
 def test_box_navier_stokes(oracle, gpu_lib, nd, n, deformed):
     """BASELINE config samples/cylinder in miniature: row size 6 viscous flow with Sutherland viscosity on a box, 3 steps"""
     basis = hb.gauss_legendre(6)
@@ -172,6 +172,19 @@ def test_box_navier_stokes(oracle, gpu_lib, nd, n, deformed):
     density_wave(m, basis)
     oracle.compute_write_face(basis, m)
     out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=3, safety=0.5)
+    assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("rs", [4, 6])
+def test_navier_stokes_3d_line_kernel(oracle, gpu_lib, rs):
+    """3-D row size 4 / 6 without the modal filter takes ns_local_line_kernel; the generic point-per-thread kernel (option off)
+    must give the same answer to round-off"""
+    rng = np.random.default_rng(91)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(3, rs, rng, n_car=8, n_def=14, n_ref=6, with_ldg=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1)
     assert_pde_parity(out, ref, dts)
 
 
