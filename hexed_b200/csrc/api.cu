@@ -39,6 +39,7 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->nom); dev_free(c->vtss); dev_free(c->uncert); dev_free(c->refn); dev_free(c->det);
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
   dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
+  dev_free(c->cfl_ratio); invalidate_cfl_cache(c); c->tss_is_one = false;
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
   for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
   c->lists.clear();
@@ -284,6 +285,7 @@ int hexed_b200_upload(hexed_b200_ctx* c, int which, const double* src, size_t fi
   int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
   if (first + n > count) return fail(c, HEXED_B200_BAD_ARGUMENT, "upload range out of bounds");
   if (!n) return 0;
+  if (which == HEXED_B200_VERTEX_TSS) invalidate_cfl_cache(c);
   HB_CUDA(c, cudaMemcpyAsync(*arr + first*item, src, sizeof(double)*n*item, cudaMemcpyDefault, c->stream));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -315,6 +317,10 @@ static int move_slots(hexed_b200_ctx* c, double* host, size_t elem_stride, int f
   if (first_slot < 0 || n_slots < 0 || first_slot + n_slots > total_slots) return fail(c, HEXED_B200_BAD_ARGUMENT, "slot range out of bounds");
   if (first_elem < 0 || n_elem < 0 || first_elem + n_elem > c->n_elem) return fail(c, HEXED_B200_BAD_ARGUMENT, "element range out of bounds");
   if (!n_elem) return 0;
+  if (up) { // the caller may be rewriting the flow state or the time-step scale
+    if (first_slot < c->nv) invalidate_cfl_cache(c);
+    if (first_slot <= c->nv && first_slot + n_slots > c->nv) c->tss_is_one = false;
+  }
   for (int s = 0; s < n_slots; ++s) {
     double* base; size_t dstride;
     int rc = slot_array(c, first_slot + s, &base, &dstride, up); if (rc) return rc;
@@ -689,6 +695,7 @@ int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled 
 int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
 {
   if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; return 0; }
+  if (option == HEXED_B200_OPT_CFL_CACHE) { c->use_cfl_cache = value != 0; invalidate_cfl_cache(c); return 0; }
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown option");
 }
 

@@ -86,6 +86,13 @@ struct hexed_b200_ctx
   hb::Stat stats[hb::ST_COUNT];
   bool timing = false;
   bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
+  // CFL cache: min over the element's points of spacing/char_speed of the state the stage-1 Local kernel has just written;
+  // cfl_valid[0|1] = every Cartesian | deformed element's entry belongs to the current state. Anything else that writes the state
+  // or the vertex spacing clears the flags (invalidate_cfl_cache), and max_dt_euler then runs its full kernel.
+  bool use_cfl_cache = true;
+  double* cfl_ratio = nullptr;
+  bool cfl_valid[2] = {false, false};
+  bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   std::string err;
@@ -118,6 +125,7 @@ struct StatScope
     }
   }
 };
+inline void invalidate_cfl_cache(hexed_b200_ctx* c) { c->cfl_valid[0] = c->cfl_valid[1] = false; }
 inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->stats[stat_id].launches; }
 
 /* launchers implemented in the kernel translation units; return a HEXED_B200_* code */

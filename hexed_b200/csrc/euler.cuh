@@ -56,5 +56,25 @@ struct EulerPoint
   }
 };
 
+/* n-linear interpolation of the vertex time-step scale to quadrature point q (reference include/math.hpp:207-218 as used by
+ * Spatial::Max_dt, include/Spatial.hpp:800-806); `vt` = the element's 2^ND vertex values */
+template <int ND, int RS>
+__device__ __forceinline__ double interp_vertex_spacing(const double* vt, const Ops& ops, int q)
+{
+  constexpr int n_vert = ipow(2, ND);
+  double vals[n_vert];
+  #pragma unroll
+  for (int i = 0; i < n_vert; ++i) vals[i] = vt[i];
+  int stride = n_vert;
+  #pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+    stride /= 2;
+    #pragma unroll
+    for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
+  }
+  return vals[0];
+}
+
 } // namespace hb
 #endif

@@ -875,6 +875,7 @@ int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdePara
   const int begin = deformed ? c->n_car : 0, end = deformed ? c->n_elem : c->n_car;
   StatScope scope(c, reconcile ? (deformed ? ST_RECONCILE_DEF : ST_RECONCILE_CAR) : (deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR), end - begin);
   GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
+  invalidate_cfl_cache(c); // these kernels may rewrite the flow state
   a.elem_begin = begin; a.elem_end = end;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual; a.use_filter = o.use_filter;
   a.update = (a.stage && !reconcile) ? o.dt*(.5/c->quad_safety) : o.dt; // Spatial.hpp:317 (Local) / :534 (Reconcile_ldg_flux)
@@ -950,6 +951,7 @@ int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double 
     { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
+    c->tss_is_one = !local_time;
     if (local_time) { *dt = 1.; return 0; }
     HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -239,6 +239,7 @@ int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o)
     if (rc == 0) count_launch(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR);
     if (rc >= 0) return rc;
   }
+  c->cfl_valid[deformed ? 1 : 0] = false; // the general kernel rewrites the state without leaving CFL ratios behind
   LocalArgs a;
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;

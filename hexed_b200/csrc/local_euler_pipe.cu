@@ -38,7 +38,7 @@ struct PipeCfg
   static constexpr int late_doubles = lt_det + (DEF ? nq : 0);
   static constexpr int r_doubles = ND*nv*nq;
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
-  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t);
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + per-warp CFL minima
 };
 
 struct PipeArgs
@@ -46,6 +46,7 @@ struct PipeArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
+  const double* vtss; double* cfl_ratio; // cfl_ratio != nullptr: leave min_q spacing/char_speed of the NEW state behind (see common.cuh)
 };
 
 template <int RS, bool DEF>
@@ -80,6 +81,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   double* late = smem + 2*C::stage_doubles;
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
+  double* warp_cfl = reinterpret_cast<double*>(bars + 4);
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -159,9 +161,11 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_wait(&bars[2], it & 1);
     {
       const double nom = a.nom[e];
+      double cfl = DBL_MAX;
       for (int q = t; q < nq; q += C::threads) {
         double mult = a.update*late[C::lt_tss + q]/nom;
         if constexpr (DEF) mult /= late[C::lt_det + q];
+        EulerPoint<ND> pt;
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
           double u = R[(0*nv + v)*nq + q];
@@ -176,11 +180,26 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
             const double x = S[v*nq + q] + u;
             S[v*nq + q] = x;
             a.state[((size_t)e*nv + v)*nq + q] = x;
+            pt.s[v] = x;
           }
         }
+        if (a.cfl_ratio) { // the CFL reduction of the next max_dt_euler, taken while the new state is in registers (Spatial.hpp:808-822)
+          pt.inv_mass = 1./pt.s[ND];
+          cfl = fmin(cfl, interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*8, ops, q)/pt.char_speed());
+        }
+      }
+      if (a.cfl_ratio) {
+        #pragma unroll
+        for (int off = 16; off > 0; off /= 2) cfl = fmin(cfl, __shfl_xor_sync(0xffffffffu, cfl, off));
+        if (t % 32 == 0) warp_cfl[t/32] = cfl;
       }
     }
     __syncthreads(); // new state complete in S; late buffer free
+    if (t == 0 && a.cfl_ratio) {
+      double m = warp_cfl[0];
+      for (int i = 1; i < C::threads/32; ++i) m = fmin(m, warp_cfl[i]);
+      a.cfl_ratio[e] = m;
+    }
     if (t == 0 && e + stride_e < a.elem_end) {
       fence_proxy_async();
       pipe_issue_late<RS, DEF>(a, e + stride_e, late, &bars[2]);
@@ -242,9 +261,17 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
+  a.vtss = c->vtss; a.cfl_ratio = nullptr;
+  c->cfl_valid[deformed ? 1 : 0] = false; // this launch rewrites the state of the set
+  const bool leave_cfl = c->use_cfl_cache && a.stage && !a.compute_residual;
+  if (leave_cfl) {
+    if (!c->cfl_ratio) HB_CUDA(c, cudaMalloc(&c->cfl_ratio, sizeof(double)*c->n_elem));
+    a.cfl_ratio = c->cfl_ratio;
+  }
   int rc;
   if (c->rs == 6) rc = deformed ? launch_pipe<6, true>(c, a) : launch_pipe<6, false>(c, a);
   else rc = deformed ? launch_pipe<4, true>(c, a) : launch_pipe<4, false>(c, a);
+  if (rc == 0 && leave_cfl) c->cfl_valid[deformed ? 1 : 0] = true;
   return rc;
 }
 

@@ -23,18 +23,7 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
   const int e = (int)(gid/nq), q = (int)(gid % nq);
   double val = DBL_MAX;
   if (e < a.n_elem) {
-    double vals[n_vert];
-    #pragma unroll
-    for (int i = 0; i < n_vert; ++i) vals[i] = a.vtss[(size_t)e*n_vert + i];
-    int stride = n_vert;
-    #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
-      stride /= 2;
-      #pragma unroll
-      for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
-    }
-    const double spacing = vals[0];
+    const double spacing = interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*n_vert, ops, q);
     EulerPoint<ND> p;
     #pragma unroll
     for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
@@ -57,12 +46,60 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
   }
 }
 
+/* Global time step from the per-element CFL ratios min_q spacing/char_speed that the stage-1 Local kernel leaves behind
+ * (local_euler_pipe.cu): the reduction the reference does in Max_dt, without re-reading the state. */
+__global__ void __launch_bounds__(256)
+cfl_reduce_kernel(const double* ratio, int n, unsigned long long* global_min)
+{
+  __shared__ double warp_min[8];
+  double val = DBL_MAX;
+  for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) val = fmin(val, ratio[i]);
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = warp_min[0];
+    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
+    atomicMin(global_min, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_kernel(double* dst, long long n, double value)
+{
+  for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) dst[i] = value;
+}
+
+static int max_dt_from_cfl_cache(hexed_b200_ctx* c, double max_cfl_c, double* dt)
+{
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  if (!c->tss_is_one) { // the reference's Max_dt writes time_step_scale = 1 for global time stepping (Spatial.hpp:823-825)
+    HB_LAUNCH(fill_kernel, sms*8, 256, 0, c->stream, c->tss, (long long)c->n_elem*c->nq, 1.);
+    count_launch(c, ST_MAX_DT_CAR);
+  }
+  HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream));
+  int grid = (c->n_elem + 255)/256;
+  if (grid > sms*8) grid = sms*8;
+  HB_LAUNCH(cfl_reduce_kernel, grid, 256, 0, c->stream, c->cfl_ratio, c->n_elem, reinterpret_cast<unsigned long long*>(c->d_scalar));
+  count_launch(c, ST_MAX_DT_CAR);
+  HB_CUDA(c, cudaGetLastError());
+  HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *dt = max_cfl_c*(*c->h_scalar); // max_cfl*spacing/char_speed with the division done when the state was written
+  c->tss_is_one = true;
+  return 0;
+}
+
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   StatScope s_car(c, ST_MAX_DT_CAR, c->n_car);
   c->stats[ST_MAX_DT_DEF].work_units += c->n_def;
   if (!c->n_elem) { *dt = local_time ? 1. : DBL_MAX; return 0; }
+  if (!local_time && c->use_cfl_cache && c->cfl_ratio && (c->n_car == 0 || c->cfl_valid[0]) && (c->n_def == 0 || c->cfl_valid[1]))
+    return max_dt_from_cfl_cache(c, (-2*c->quad_safety/c->min_eig_conv)*safety_conv, dt);
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)c->n_elem*ipow(RS, ND);
@@ -75,6 +112,7 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
+    c->tss_is_one = !local_time;
     if (local_time) { *dt = 1.; return 0; }
     HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(c, cudaStreamSynchronize(c->stream));

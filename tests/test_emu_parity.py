@@ -96,3 +96,8 @@ def test_navier_stokes_3d_line_kernel(oracle, emu_lib, kind):
     assert_pde_parity(out, ref, dts)
     out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
     assert_pde_parity(out, ref, dts)
+
+
+def test_cfl_cache_follows_the_state(oracle, emu_lib):
+    from util import check_cfl_cache
+    check_cfl_cache(oracle, emu_lib, 4, 2)

@@ -188,6 +188,12 @@ def test_navier_stokes_3d_line_kernel(oracle, gpu_lib, rs):
     assert_pde_parity(out, ref, dts)
 
 
+@pytest.mark.parametrize("rs,n", [(4, 5), (6, 4)])
+def test_cfl_cache_follows_the_state(oracle, gpu_lib, rs, n):
+    from util import check_cfl_cache
+    check_cfl_cache(oracle, gpu_lib, rs, n)
+
+
 def test_stabilizing_art_visc(oracle, gpu_lib):
     rng = np.random.default_rng(8)
     for nd, rs in [(2, 6), (3, 6), (3, 4)]:

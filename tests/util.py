@@ -133,3 +133,41 @@ def assert_pde_parity(out, ref, dts, tol=STATE_TOL):
         a, b = getattr(out, name), getattr(ref, name)
         if a is not None:
             assert rel_l2(a, b) <= tol, name
+
+
+def check_cfl_cache(oracle, lib, rs, n):
+    """the stage-1 Local kernel leaves per-element CFL ratios behind for the next max_dt_euler (HEXED_B200_OPT_CFL_CACHE); any
+    other write to the state must invalidate them, and the cached and the full reduction must agree to round-off"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(3, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    dev = Device(3, rs, basis, lib_path=lib).load_mesh(m)
+    dt = dev.max_dt_euler(0.7, 0.7, False)
+    for stage in (0, 1):
+        oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt, i_stage=stage)
+        dev.apply_state_bcs(); dev.compute_euler(dt=dt, i_stage=stage)
+    n0 = dev.launch_count()
+    dt_cached = dev.max_dt_euler(0.7, 0.7, False)           # reduction of the cached ratios
+    assert dev.launch_count() - n0 == 1
+    dt_o = oracle.max_dt(EULER, basis, ref, 0.7, 0.7, False)
+    assert abs(dt_cached/dt_o - 1) <= 1e-13
+    dev.set_option(1, 0)                                     # HEXED_B200_OPT_CFL_CACHE off: the full kernel
+    assert abs(dev.max_dt_euler(0.7, 0.7, False)/dt_o - 1) <= 1e-13
+    dev.set_option(1, 1)
+    # a host write to the state: the cache must not be used
+    st = ref.state().copy(); st[:, 3 + 1] *= 4.                # four times the energy -> twice the sound speed
+    ref.state()[:] = st
+    dev.upload_elements(np.ascontiguousarray(st), 0, 5)
+    dt_new = dev.max_dt_euler(0.7, 0.7, False)
+    dt_o = oracle.max_dt(EULER, basis, ref, 0.7, 0.7, False)
+    assert abs(dt_new/dt_o - 1) <= 1e-13 and dt_new < 0.8*dt_cached
+    # local time stepping never uses it and leaves tss != 1; the next global call must restore tss = 1
+    dev.max_dt_euler(0.7, 0.7, True)
+    for stage in (0, 1):
+        dev.apply_state_bcs(); dev.compute_euler(dt=1e-9, i_stage=stage)
+    dev.max_dt_euler(0.7, 0.7, False)
+    out = m.copy(); dev.sync_to_host(out)
+    assert np.array_equal(out.tss(), np.ones_like(out.tss()))
+    dev.close()
