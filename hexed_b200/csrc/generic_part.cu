@@ -152,6 +152,10 @@ struct GCfg
   static constexpr int nops = 3*RS*RS + 2*RS;                               // dfull, diff, filter, lift
   static constexpr int per_elem = nbuf + nx + nface + nvface;
   static constexpr int smem_doubles = nops + epb*per_elem;
+  // Reconcile_ldg_flux needs only one scratch field set and the LDG faces: a smaller footprint keeps more CTAs resident
+  static constexpr int rec_buf = (nu > ne ? nu : ne)*nq;
+  static constexpr int rec_per_elem = rec_buf + nvface;
+  static constexpr int rec_smem_doubles = nops + epb*rec_per_elem;
 };
 
 template <int ND, int RS, class P>
@@ -207,7 +211,7 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
   load_ops<ND, RS, P>(smem, ops, filt, t, C::threads);
 
   typename P::template Comp<ND> comp;
-  double det = 1., tss = 0., nom = 1.;
+  double det = 1., tss = 0., nom = 1., inv_nom = 1.;
   if (active) {
     if constexpr (P::has_convection) {
       const double* base = a.faces + (size_t)e*2*ND*a.face_width;
@@ -221,6 +225,7 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
     for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>(e, P::state_slot(i))[q];
     tss = a.ed.tss[(size_t)e*nq + q];
     nom = a.nom[e];
+    inv_nom = 1./nom; // one reciprocal instead of a division per gradient term (<= 1 ulp each; FP64 division is ~30 instructions)
     if constexpr (DEF) {
       det = a.det[(size_t)(e - a.n_car)*nq + q];
       const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
@@ -266,7 +271,7 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
               for (int k = 0; k < RS; ++k) acc += m[k]*(nk[k]*sx[v*nq + ln.base + k*ln.stride]);
               acc += l0*(fn0*svface[((2*d)*ne + v)*nfq + ln.fq]);
               acc += l1*(fn1*svface[((2*d + 1)*ne + v)*nfq + ln.fq]);
-              comp.gradient[v][j] += acc/nom;
+              comp.gradient[v][j] += acc*inv_nom;
             }
           }
         } else {
@@ -277,15 +282,16 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
             for (int k = 0; k < RS; ++k) acc += m[k]*sx[v*nq + ln.base + k*ln.stride];
             acc += l0*svface[((2*d)*ne + v)*nfq + ln.fq];
             acc += l1*svface[((2*d + 1)*ne + v)*nfq + ln.fq];
-            comp.gradient[v][d] = acc/nom;
+            comp.gradient[v][d] = acc*inv_nom;
           }
         }
       }
       if constexpr (DEF) {
+        const double inv_det = 1./det;
         #pragma unroll
         for (int v = 0; v < ne; ++v)
           #pragma unroll
-          for (int j = 0; j < ND; ++j) comp.gradient[v][j] /= det;
+          for (int j = 0; j < ND; ++j) comp.gradient[v][j] *= inv_det;
       }
     }
   }
@@ -479,6 +485,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
   const int e = a.elem_begin + blockIdx.x;
   if (e >= a.elem_end) return;
   const double nom = a.nom[e];
+  const double inv_nom = 1./nom; // reciprocals instead of divisions, see g_local_kernel
   {
     const double* src = a.ed.state + (size_t)e*nv*nq;
     for (int i = t; i < nv*nq; i += T) S[i] = src[i];
@@ -514,7 +521,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
             acc += ops.lift[i][0]*b0;
             acc += ops.lift[i][1]*b1;
             double* g = G + (v*ND + j)*nq + q0 + i*stride;
-            if (d == 0) *g = acc/nom; else *g += acc/nom;
+            if (d == 0) *g = acc*inv_nom; else *g += acc*inv_nom;
           }
         }
       }
@@ -538,7 +545,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
           for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
           acc += ops.lift[i][0]*b0;
           acc += ops.lift[i][1]*b1;
-          G[(v*ND + d)*nq + q0 + i*stride] = acc/nom;
+          G[(v*ND + d)*nq + q0 + i*stride] = acc*inv_nom;
         }
       }
     }
@@ -553,7 +560,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
     comp.state[nv] = a.ed.av[((size_t)e*2)*nq + q];
     comp.state[nv + 1] = a.ed.av[((size_t)e*2 + 1)*nq + q];
     if constexpr (DEF) {
-      const double det = a.det[(size_t)(e - a.n_car)*nq + q];
+      const double inv_det = 1./a.det[(size_t)(e - a.n_car)*nq + q];
       const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
       #pragma unroll
       for (int d = 0; d < ND; ++d)
@@ -562,7 +569,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
       #pragma unroll
       for (int v = 0; v < nv; ++v)
         #pragma unroll
-        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q]/det;
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q]*inv_det;
     } else {
       #pragma unroll
       for (int v = 0; v < nv; ++v)
@@ -675,8 +682,8 @@ g_reconcile_kernel(GArgs a, Ops ops, FilterOp filt)
   const int e = a.elem_begin + blockIdx.x*C::epb + le;
   const bool active = e < a.elem_end;
   double* s_filt = smem + 2*RS*RS; double* s_lift = smem + 3*RS*RS;
-  double* sbuf = smem + C::nops + le*C::per_elem;
-  double* svface = sbuf + C::nbuf + C::nx + C::nface;
+  double* sbuf = smem + C::nops + le*C::rec_per_elem;
+  double* svface = sbuf + C::rec_buf;
   load_ops<ND, RS, P>(smem, ops, filt, t, C::threads);
   if (active) {
     const double* base = a.faces_ldg + (size_t)e*2*ND*wl;
@@ -888,7 +895,7 @@ int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdePara
     if (a.stage && a.compute_residual) return fail(c, HEXED_B200_BAD_ARGUMENT, "residual calculation is a single-stage operation");
     if (end == begin) return 0;
     const int grid = (end - begin + C::epb - 1)/C::epb;
-    const size_t smem = sizeof(double)*C::smem_doubles;
+    const size_t smem = sizeof(double)*(reconcile ? C::rec_smem_doubles : C::smem_doubles);
     if (reconcile) {
       if constexpr (P::has_diffusion) {
         if (a.compute_residual && HB_PDE == PDE_SMOOTH_AV)

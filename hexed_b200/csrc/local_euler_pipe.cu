@@ -81,7 +81,10 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   double* late = smem + 2*C::stage_doubles;
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
-  double* warp_cfl = reinterpret_cast<double*>(bars + 4);
+  float* warp_cfl = reinterpret_cast<float*>(bars + 4);                       // per-warp minima of the single-precision CFL screen
+  unsigned long long* cfl_exact = reinterpret_cast<unsigned long long*>(bars + 6); // bit pattern of the element's exact minimum
+  constexpr int n_round = (nq + C::threads - 1)/C::threads;
+  float cfl_approx[n_round];
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -161,48 +164,93 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_wait(&bars[2], it & 1);
     {
       const double nom = a.nom[e];
-      double cfl = DBL_MAX;
-      for (int q = t; q < nq; q += C::threads) {
-        double mult = a.update*late[C::lt_tss + q]/nom;
-        if constexpr (DEF) mult /= late[C::lt_det + q];
-        EulerPoint<ND> pt;
+      float vt[8];
+      if (a.cfl_ratio) {
         #pragma unroll
-        for (int v = 0; v < nv; ++v) {
-          double u = R[(0*nv + v)*nq + q];
-          u += R[(1*nv + v)*nq + q];
-          u += R[(2*nv + v)*nq + q];
-          double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
-          if (a.stage) u -= late[C::lt_cache + v*nq + q];
-          else if (!a.compute_residual) *cache = u;
-          u *= mult;
-          if (a.compute_residual) *cache = u;
-          else {
-            const double x = S[v*nq + q] + u;
-            S[v*nq + q] = x;
-            a.state[((size_t)e*nv + v)*nq + q] = x;
-            pt.s[v] = x;
+        for (int i = 0; i < 8; ++i) vt[i] = (float)a.vtss[(size_t)e*8 + i];
+      }
+      float cfl_min = 3.0e38f;
+      #pragma unroll
+      for (int it_q = 0; it_q < n_round; ++it_q) {
+        const int q = t + it_q*C::threads;
+        cfl_approx[it_q] = 3.0e38f;
+        if (q < nq) {
+          double mult = a.update*late[C::lt_tss + q]/nom;
+          if constexpr (DEF) mult /= late[C::lt_det + q];
+          double x[nv];
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) {
+            double u = R[(0*nv + v)*nq + q];
+            u += R[(1*nv + v)*nq + q];
+            u += R[(2*nv + v)*nq + q];
+            double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+            if (a.stage) u -= late[C::lt_cache + v*nq + q];
+            else if (!a.compute_residual) *cache = u;
+            u *= mult;
+            x[v] = 0.;
+            if (a.compute_residual) *cache = u;
+            else {
+              x[v] = S[v*nq + q] + u;
+              S[v*nq + q] = x[v];
+              a.state[((size_t)e*nv + v)*nq + q] = x[v];
+            }
           }
-        }
-        if (a.cfl_ratio) { // the CFL reduction of the next max_dt_euler, taken while the new state is in registers (Spatial.hpp:808-822)
-          pt.inv_mass = 1./pt.s[ND];
-          cfl = fmin(cfl, interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*8, ops, q)/pt.char_speed());
+          if (a.cfl_ratio) {
+            /* CFL screening in single precision (a few MUFU-assisted instructions instead of two FP64 square roots and two
+             * divisions per point): spacing/char_speed of the new state to ~1e-6 relative; the exact FP64 value is evaluated
+             * below only for the points within 1e-5 of the element's minimum. Anything that is not a positive finite float
+             * makes every point of the element a candidate. */
+            const float rho = (float)x[ND], en = (float)x[ND + 1];
+            const float mx = (float)x[0], my = (float)x[1], mz = (float)x[2];
+            const float inv = 1.f/rho;
+            const float cs = sqrtf(0.56f*en*inv) + sqrtf(mx*mx + my*my + mz*mz)*inv;
+            float sv[8];
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) sv[i] = vt[i];
+            int str = 8;
+            #pragma unroll
+            for (int d = 0; d < ND; ++d) {
+              const float coord = (float)ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+              str /= 2;
+              #pragma unroll
+              for (int i = 0; i < 4; ++i) if (i < str) sv[i] += coord*(sv[i + str] - sv[i]);
+            }
+            float r = sv[0]/cs;
+            if (!(r > 0.f && r < 3.0e38f)) r = -1.f;
+            cfl_approx[it_q] = r;
+            cfl_min = fminf(cfl_min, r);
+          }
         }
       }
       if (a.cfl_ratio) {
         #pragma unroll
-        for (int off = 16; off > 0; off /= 2) cfl = fmin(cfl, __shfl_xor_sync(0xffffffffu, cfl, off));
-        if (t % 32 == 0) warp_cfl[t/32] = cfl;
+        for (int off = 16; off > 0; off /= 2) cfl_min = fminf(cfl_min, __shfl_xor_sync(0xffffffffu, cfl_min, off));
+        if (t % 32 == 0) warp_cfl[t/32] = cfl_min;
+        if (t == 0) *cfl_exact = 0x7ff0000000000000ull; // +infinity
       }
     }
     __syncthreads(); // new state complete in S; late buffer free
-    if (t == 0 && a.cfl_ratio) {
-      double m = warp_cfl[0];
-      for (int i = 1; i < C::threads/32; ++i) m = fmin(m, warp_cfl[i]);
-      a.cfl_ratio[e] = m;
-    }
     if (t == 0 && e + stride_e < a.elem_end) {
       fence_proxy_async();
       pipe_issue_late<RS, DEF>(a, e + stride_e, late, &bars[2]);
+    }
+    if (a.cfl_ratio) { // exact CFL ratio of the candidate points (reference Spatial.hpp:808-822 arithmetic, as in max_dt_euler_kernel)
+      float bmin = warp_cfl[0];
+      #pragma unroll
+      for (int i = 1; i < C::threads/32; ++i) bmin = fminf(bmin, warp_cfl[i]);
+      const float thr = bmin < 0.f ? 3.4e38f : bmin*1.00001f;
+      #pragma unroll
+      for (int it_q = 0; it_q < n_round; ++it_q) {
+        const int q = t + it_q*C::threads;
+        if (q < nq && cfl_approx[it_q] <= thr) {
+          EulerPoint<ND> pt;
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) pt.s[v] = S[v*nq + q];
+          pt.inv_mass = 1./pt.s[ND];
+          const double ratio = interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*8, ops, q)/pt.char_speed();
+          atomicMin(cfl_exact, (unsigned long long)__double_as_longlong(ratio));
+        }
+      }
     }
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
@@ -222,6 +270,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
       }
     }
     __syncthreads(); // stage buffer s free
+    if (t == 0 && a.cfl_ratio) a.cfl_ratio[e] = __longlong_as_double((long long)*cfl_exact);
     if (t == 0 && e + 2*stride_e < a.elem_end) {
       fence_proxy_async();
       pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);

@@ -18,7 +18,7 @@ struct NeighborArgs
 };
 
 template <int ND, int RS, bool DEF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 neighbor_euler_kernel(NeighborArgs a)
 {
   constexpr int nfq = ipow(RS, ND - 1), nv = ND + 2, w = nv*nfq;

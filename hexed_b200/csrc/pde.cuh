@@ -63,7 +63,7 @@ struct PdeNs
   {
     double state[n_state], update_state[n_update], normal[ND][NDF], flux_conv[n_update][NDF];
     double gradient[n_extrap][ND], flux_diff[n_update][ND], source[n_update];
-    double mass, kin_ener, pressure, bulk_av, laplacian_av, dyn_visc_coef, energy_cond, char_speed, diffusivity;
+    double mass, inv_mass, kin_ener, pressure, bulk_av, laplacian_av, dyn_visc_coef, energy_cond, char_speed, diffusivity;
     __device__ Comp()
     {
       #pragma unroll
@@ -79,11 +79,14 @@ struct PdeNs
     }
     __device__ void scalars_conv()
     {
+      // FP64 division costs ~30 instructions on the device: one IEEE reciprocal of the mass per point, then multiplications
+      // (<= 1 ulp per use from the reference's divisions, include/pde.hpp:94-158; covered by the 1e-11 / 1e-13 bars)
       mass = state[ND];
+      inv_mass = 1./mass;
       kin_ener = 0;
       #pragma unroll
       for (int i = 0; i < ND; ++i) kin_ener += state[i]*state[i];
-      kin_ener *= .5/mass;
+      kin_ener *= .5*inv_mass;
       pressure = (heat_rat_ns - 1.)*(state[ND + 1] - kin_ener);
     }
     __device__ void compute_flux_conv(const PdeParams&)
@@ -95,7 +98,7 @@ struct PdeNs
         #pragma unroll
         for (int j = 0; j < ND; ++j) mass_flux += state[j]*normal[j][d];
         flux_conv[ND][d] = mass_flux;
-        const double vol_flux = mass_flux/mass;
+        const double vol_flux = mass_flux*inv_mass;
         flux_conv[ND + 1][d] = (state[ND + 1] + pressure)*vol_flux;
         #pragma unroll
         for (int j = 0; j < ND; ++j) flux_conv[j][d] = state[j]*vol_flux + pressure*normal[j][d];
@@ -105,10 +108,11 @@ struct PdeNs
     {
       bulk_av = fabs(state[ND + 2]);
       laplacian_av = fabs(state[ND + 3]);
-      const double sqrt_temp = sqrt(fmax((state[ND + 1] - kin_ener)/mass, 0.)*(heat_rat_ns - 1)/specific_gas_air);
+      constexpr double gm1_over_r = (heat_rat_ns - 1)/specific_gas_air;
+      const double sqrt_temp = sqrt(fmax((state[ND + 1] - kin_ener)*inv_mass, 0.)*gm1_over_r);
       dyn_visc_coef = transport_coef(p.visc, sqrt_temp);
       const double therm_cond_coef = transport_coef(p.cond, sqrt_temp);
-      energy_cond = therm_cond_coef*(heat_rat_ns - 1)/specific_gas_air;
+      energy_cond = therm_cond_coef*gm1_over_r;
     }
     __device__ void compute_flux_diff(const PdeParams& p)
     {
@@ -116,11 +120,11 @@ struct PdeNs
         scalars_diff(p);
         double veloc[ND], vgrad[ND][ND], stress[ND][ND], fd[n_update][ND];
         #pragma unroll
-        for (int i = 0; i < ND; ++i) veloc[i] = state[i]/mass;
+        for (int i = 0; i < ND; ++i) veloc[i] = state[i]*inv_mass;
         #pragma unroll
         for (int i = 0; i < ND; ++i)
           #pragma unroll
-          for (int j = 0; j < ND; ++j) vgrad[i][j] = (gradient[i][j] - veloc[i]*gradient[ND][j])/mass;
+          for (int j = 0; j < ND; ++j) vgrad[i][j] = (gradient[i][j] - veloc[i]*gradient[ND][j])*inv_mass;
         double trace = 0;
         #pragma unroll
         for (int i = 0; i < ND; ++i) trace += vgrad[i][i];
@@ -142,7 +146,7 @@ struct PdeNs
           double conv = 0, work = 0;
           #pragma unroll
           for (int i = 0; i < ND; ++i) { conv += veloc[i]*vgrad[i][j]; work += veloc[i]*stress[i][j]; }
-          const double int_ener_grad = -state[ND + 1]/mass/mass*gradient[ND][j] + gradient[ND + 1][j]/mass - conv;
+          const double int_ener_grad = -state[ND + 1]*inv_mass*inv_mass*gradient[ND][j] + gradient[ND + 1][j]*inv_mass - conv;
           fd[ND + 1][j] -= work + energy_cond*int_ener_grad;
         }
         #pragma unroll
@@ -169,7 +173,7 @@ struct PdeNs
     {
       scalars_conv();
       scalars_diff(p);
-      diffusivity = fabs(laplacian_av) + fmax(fabs(bulk_av) + dyn_visc_coef/mass, energy_cond/mass);
+      diffusivity = fabs(laplacian_av) + fmax(fabs(bulk_av) + dyn_visc_coef*inv_mass, energy_cond*inv_mass);
     }
   };
 };
