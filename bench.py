@@ -25,6 +25,31 @@ ALG_DOUBLES = {"deformed": {"stage": 11556, "local": 8424, "neighbor": 2484, "ma
                "cartesian": {"stage": 8424, "local": 5616, "neighbor": 2160, "max_dt_half": 648}}
 
 
+def alg_doubles(nd, rs, deformed):
+    """the same accounting for any (n_dim, row_size): compulsory HBM traffic of one Euler stage per element, following the
+    reference data flow: Local R state + tss + face flux + residual cache (R or W) + W state + W faces
+    (+ normals, determinant, face normals when deformed); Neighbor R + W of n_dim connections per element (+ normals);
+    half a Max_dt (R state + W tss)"""
+    nq, nfq, nv = rs**nd, rs**(nd - 1), nd + 2
+    faces = 2*nd*nv*nfq
+    local = nv*nq + nq + faces + nv*nq + nv*nq + faces
+    neighbor = 2*faces
+    if deformed:
+        local += nd*nd*nq + nq + 2*nd*nd*nfq
+        neighbor += nd*nd*nfq
+    half_dt = (nv*nq + nq)//2
+    return {"stage": local + neighbor + half_dt, "local": local, "neighbor": neighbor, "max_dt_half": half_dt}
+
+
+def workload_name(args, viscous=False):
+    nd = args.dim
+    n = 1000 if (nd == 2 and args.n == 100) else args.n
+    return ("synthetic %dD %s %s box %d^%d = %d elements per GPU, row_size 6, %s, freestream ghosts; step = %s"
+            % (nd, args.mesh, "hex" if nd == 3 else "quad", n, nd, n**nd, "Navier-Stokes (Sutherland air)" if viscous else "Euler",
+               "max_dt + ghost fill + compute_navier_stokes (stage 0, LDG) + ghost fill + compute_euler (stage 1)" if viscous
+               else "max_dt + 2 x (ghost BC fill + compute_euler)"))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -33,6 +58,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=100, help="box edge in elements per GPU (100 -> 1M elements)")
     ap.add_argument("--mesh", default="deformed", choices=["deformed", "cartesian"])
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3 = the headline; 2 = the shape of the 2-D BASELINE configs (vortex / naca0012 / cylinder)")
     ap.add_argument("--pde", default="euler", choices=["euler", "navier_stokes"],
                     help="euler = the headline; navier_stokes = Solver::update with use_ldg (stage 0 viscous/LDG, stage 1 inviscid), 1 GPU only")
     ap.add_argument("--cpu-n", type=int, default=32, help="box edge of the bounded CPU sample")
@@ -40,6 +66,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def ncu_traffic(kernel, n_elem):
+    """DRAM bytes per launch of `kernel` as measured by ncu (profiles/ncu_traffic.json), or None"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        entry = json.load(open(p)).get(kernel)
+        return {"bytes": entry["bytes_per_element"]*n_elem, "source": entry["source"]} if entry else None
+    except Exception:
+        return None
 
 
 def peaks():
@@ -111,8 +147,9 @@ def cpu_reference_rate(args, steps, warmup):
     lib = build_native_oracle()
     o = Oracle(lib)
     basis = hb.gauss_legendre(6)
-    n = args.cpu_n
-    m = M.box_mesh(3, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    nd = args.dim
+    n = args.cpu_n if nd == 3 else int(round(args.cpu_n**1.5))
+    m = M.box_mesh(nd, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
     density_wave(m, basis)
     o.compute_write_face(basis, m)
 
@@ -127,8 +164,8 @@ def cpu_reference_rate(args, steps, warmup):
     for _ in range(steps):
         step()
     el = time.perf_counter() - t
-    rate = m.n_elem*1080*2*steps/el
-    return rate, el/steps, o.num_threads(), "%d^3 = %d %s elements, %d steps (max_dt + 2 stages), %s, OpenMP" % (n, m.n_elem, args.mesh, steps, lib)
+    rate = m.n_elem*m.nv*m.nq*2*steps/el
+    return rate, el/steps, o.num_threads(), "%d^%d = %d %s elements, %d steps (max_dt + 2 stages), %s, OpenMP" % (n, nd, m.n_elem, args.mesh, steps, lib)
 
 
 def run_reference(args):
@@ -139,7 +176,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "DOF-stage/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "synthetic 3D %s hex box, row_size 6, Euler; bounded CPU sample" % args.mesh, "sample": sample},
+           "config": {"workload": workload_name(args), "sample": "CPU arm timed on a bounded sample of that workload: " + sample},
            "cpu_baseline": {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": rate, "unit": "DOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -164,7 +201,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    nd, rs, n = 3, 6, args.n
+    nd, rs, n = args.dim, 6, args.n
+    if nd == 2 and args.n == 100:
+        n = 1000  # 10^6 quads
     deformed = args.mesh == "deformed"
     basis = hb.gauss_legendre(rs)
     fs = freestream_state(nd)
@@ -271,13 +310,18 @@ def main():
         step()
     dev.set_timing(False)
     stats = dev.kernel_stats()
-    alg = ALG_DOUBLES[args.mesh]
+    alg = alg_doubles(nd, rs, deformed)
+    assert nd != 3 or alg == ALG_DOUBLES[args.mesh]
     peak, peak_src = peaks()
     local_stat = max((s for s in stats if s["name"] == "local" and s["deformed"] == int(deformed)), key=lambda s: s["launches"])
     local_sec = local_stat["device_seconds"]/max(local_stat["launches"], 1)
     local_gbs = ne*alg["local"]*8/local_sec/1e9
     shares = {("%s/%s" % (("car", "def", "shared")[s["deformed"]], s["name"])): s["device_seconds"]/n_prof for s in stats if s["launches"]}
-    stage_gbs = value/world*(alg["stage"]*8/1080.)/1e9
+    local_name = ("local_euler_pipe_kernel<6,%s>" if nd == 3 else "local_euler_kernel<2,6,%s>") % ("true" if deformed else "false")
+    if viscous:
+        local_name += " + ns_local_line_kernel (both count as 'local'; see kernel_seconds_per_step)"
+    traffic = ncu_traffic(local_name, ne) if not viscous else None
+    stage_gbs = value/world*(alg["stage"]*8/float(nv*nq))/1e9
 
     # ---- end to end through the public API with HOST buffers: the boundary condition is applied by the host (as the reference's
     # Solver::apply_state_bcs does, src/Solver.cpp:56-67), so every stage the inside boundary faces go D2H and the ghost faces
@@ -340,19 +384,19 @@ def main():
             "metric": METRIC, "value": value, "unit": "DOF-stage/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec/args.steps*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 3D %s hex box %d^3 = %d elements per GPU, row_size 6, Euler, freestream ghosts; "
-                                   "step = max_dt + 2 x (ghost BC fill + compute_euler)" % (args.mesh, n, ne),
+            "config": {"workload": workload_name(args, viscous),
                        "elements_per_gpu": ne, "dof_per_element": nv*nq, "stages_per_step": 2,
-                       "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (ne*50e3/1e9),
+                       "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (ne*(50e3 if nd == 3 else 6.2e3)/1e9),
                        "parallelism": "1 GPU" if world == 1 else
                        "%s blocks of one global box (Z-order split), cut faces exchanged by NCCL send/recv (%d B per rank and stage) overlapped with interior flux work, dt by NCCL allreduce(min)"
                        % ("x".join(map(str, blocks)), halo.bytes_per_exchange)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "local_euler_pipe_kernel<6,%s>" % ("true" if deformed else "false"),
-                         "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": local_name,
+                         "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak,
+                         "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
-                         "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/1080.},
+                         "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/float(nv*nq)},
                          "kernel_seconds_per_step": shares},
             "e2e": e2e, "cpu_baseline": cpu,
         }

@@ -39,7 +39,7 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->nom); dev_free(c->vtss); dev_free(c->uncert); dev_free(c->refn); dev_free(c->det);
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
   dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
-  dev_free(c->cfl_ratio); invalidate_cfl_cache(c); c->tss_is_one = false;
+  dev_free(c->cfl_approx); invalidate_cfl_cache(c); c->tss_is_one = false;
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
   for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
   c->lists.clear();

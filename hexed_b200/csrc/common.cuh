@@ -86,11 +86,12 @@ struct hexed_b200_ctx
   hb::Stat stats[hb::ST_COUNT];
   bool timing = false;
   bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
-  // CFL cache: min over the element's points of spacing/char_speed of the state the stage-1 Local kernel has just written;
-  // cfl_valid[0|1] = every Cartesian | deformed element's entry belongs to the current state. Anything else that writes the state
-  // or the vertex spacing clears the flags (invalidate_cfl_cache), and max_dt_euler then runs its full kernel.
+  // CFL screen: single-precision min over the element's points of spacing/char_speed of the state the stage-1 Local kernel has
+  // just written (0 = not representable, always re-evaluate); cfl_valid[0|1] = every Cartesian | deformed element's entry belongs
+  // to the current state. Anything else that writes the state or the vertex spacing clears the flags (invalidate_cfl_cache), and
+  // max_dt_euler then runs its full kernel. With valid entries it re-evaluates in FP64 only the elements within 1e-5 of the minimum.
   bool use_cfl_cache = true;
-  double* cfl_ratio = nullptr;
+  float* cfl_approx = nullptr;
   bool cfl_valid[2] = {false, false};
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

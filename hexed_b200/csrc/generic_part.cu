@@ -459,18 +459,24 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
  *   P3  line (d, l): F <- -(D_d flux_conv + lifted numerical flux) in place; diffusive flux extrapolated to faces 2d, 2d+1 -> LDG
  *       face storage; G <- -diff_mat_d flux_diff in place                           (:445-468)
  *   P4  pointwise: sum over d, residual cache, update                                (:484-503)
- * Shared memory: state + G + F = 7 n_var nq doubles (60 KB at row size 6) -> 3 CTAs of 128 threads per SM; everything that is
- * used once (face data, normals, determinant, AV coefficients) is read straight from global memory by the thread that needs it. */
+ * Every input of the element (state, LDG faces, flux faces, normals, face normals, determinant, tss, AV coefficients) is one
+ * contiguous run, fetched by 1-D bulk TMA copies onto one mbarrier at the top (the second profile, profiles/r01e_ncu_full_ns.md,
+ * showed the version with per-thread global loads stalled on them: long-scoreboard 6.5 cycles per issue at 18 % occupancy);
+ * with G and F that is 105 KB at row size 6 -> 2 CTAs of 128 threads per SM, one loading while the other computes. */
 template <int RS, bool DEF>
 struct NsCfg
 {
   static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5, n_line = ND*nfq;
   static constexpr int threads = ((n_line + 31)/32)*32;
-  static constexpr int s_state = 0, s_grad = nv*nq, s_flux = s_grad + ND*nv*nq, smem_doubles = s_flux + ND*nv*nq;
+  // inputs, each one contiguous run of the element-major layout, fetched by 1-D bulk TMA copies onto one mbarrier
+  static constexpr int s_state = 0, s_ldg = s_state + nv*nq, s_fc = s_ldg + 2*ND*nv*nfq, s_tss = s_fc + 2*ND*nv*nfq, s_av = s_tss + nq;
+  static constexpr int s_nrml = s_av + 2*nq, s_fn = s_nrml + (DEF ? ND*ND*nq : 0), s_det = s_fn + (DEF ? 2*ND*ND*nfq : 0);
+  static constexpr int s_grad = s_det + (DEF ? nq : 0), s_flux = s_grad + ND*nv*nq, smem_doubles = s_flux + ND*nv*nq;
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 2*sizeof(mbar_t);
 };
 
 template <int RS, bool DEF>
-__global__ void __launch_bounds__(NsCfg<RS, DEF>::threads, 3)
+__global__ void __launch_bounds__(NsCfg<RS, DEF>::threads, 2)
 ns_local_line_kernel(GArgs a, Ops ops)
 {
   using C = NsCfg<RS, DEF>;
@@ -479,24 +485,41 @@ ns_local_line_kernel(GArgs a, Ops ops)
   constexpr int cs = nv > RS ? nv : RS;
   HB_DYN_SMEM(double, smem);
   double* S = smem + C::s_state;
+  const double* fldg = smem + C::s_ldg;
+  const double* fc = smem + C::s_fc;
+  const double* s_tss = smem + C::s_tss;
+  const double* s_av = smem + C::s_av;
+  const double* rn = smem + C::s_nrml;
+  const double* fn = smem + C::s_fn;
+  const double* s_det = smem + C::s_det;
   double* G = smem + C::s_grad;
   double* F = smem + C::s_flux;
+  mbar_t* bar = reinterpret_cast<mbar_t*>(smem + C::smem_doubles);
   const int t = threadIdx.x;
   const int e = a.elem_begin + blockIdx.x;
   if (e >= a.elem_end) return;
+  if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncthreads();
+  if (t == 0) {
+    constexpr unsigned b_field = sizeof(double)*nq, b_face = sizeof(double)*2*ND*nv*nfq;
+    mbar_arrive_expect_tx(bar, nv*b_field + 2*b_face + 3*b_field + (DEF ? (ND*ND + 1)*b_field + sizeof(double)*2*ND*ND*nfq : 0u));
+    bulk_g2s(S, a.ed.state + (size_t)e*nv*nq, nv*b_field, bar);
+    bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
+    bulk_g2s(smem + C::s_fc, a.faces + (size_t)e*2*ND*wl, b_face, bar);
+    bulk_g2s(smem + C::s_tss, a.ed.tss + (size_t)e*nq, b_field, bar);
+    bulk_g2s(smem + C::s_av, a.ed.av + (size_t)e*2*nq, 2*b_field, bar);
+    if constexpr (DEF) {
+      bulk_g2s(smem + C::s_nrml, a.refn + (size_t)(e - a.n_car)*ND*ND*nq, ND*ND*b_field, bar);
+      bulk_g2s(smem + C::s_fn, a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq, sizeof(double)*2*ND*ND*nfq, bar);
+      bulk_g2s(smem + C::s_det, a.det + (size_t)(e - a.n_car)*nq, b_field, bar);
+    }
+  }
   const double nom = a.nom[e];
   const double inv_nom = 1./nom; // reciprocals instead of divisions, see g_local_kernel
-  {
-    const double* src = a.ed.state + (size_t)e*nv*nq;
-    for (int i = t; i < nv*nq; i += T) S[i] = src[i];
-  }
-  const double* fldg = a.faces_ldg + (size_t)e*2*ND*wl;
-  __syncthreads();
+  mbar_wait(bar, 0);
 
   /* ---- P1: gradient ---- */
   if constexpr (DEF) {
-    const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
-    const double* fn = a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq;
     const int l = t % nfq, j = t/nfq; // task of every sub-phase: line l of the current direction, physical component j
     #pragma unroll
     for (int d = 0; d < ND; ++d) {
@@ -557,11 +580,10 @@ ns_local_line_kernel(GArgs a, Ops ops)
     typename P::template Comp<ND> comp;
     #pragma unroll
     for (int v = 0; v < nv; ++v) comp.state[v] = S[v*nq + q];
-    comp.state[nv] = a.ed.av[((size_t)e*2)*nq + q];
-    comp.state[nv + 1] = a.ed.av[((size_t)e*2 + 1)*nq + q];
+    comp.state[nv] = s_av[q];
+    comp.state[nv + 1] = s_av[nq + q];
     if constexpr (DEF) {
-      const double inv_det = 1./a.det[(size_t)(e - a.n_car)*nq + q];
-      const double* rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+      const double inv_det = 1./s_det[q];
       #pragma unroll
       for (int d = 0; d < ND; ++d)
         #pragma unroll
@@ -593,7 +615,6 @@ ns_local_line_kernel(GArgs a, Ops ops)
     const int d = t/nfq, l = t % nfq;
     const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
     const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
-    const double* fc = a.faces + (size_t)e*2*ND*a.face_width;
     double* fl = a.faces_ldg + (size_t)e*2*ND*wl;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
@@ -601,7 +622,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
       double f[RS];
       #pragma unroll
       for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
-      const double b0 = fc[(size_t)(2*d)*a.face_width + v*nfq + l], b1 = fc[(size_t)(2*d + 1)*a.face_width + v*nfq + l];
+      const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
       #pragma unroll
       for (int i = 0; i < RS; ++i) {
         double acc = 0;
@@ -632,8 +653,8 @@ ns_local_line_kernel(GArgs a, Ops ops)
 
   /* ---- P4: combine and update ---- */
   for (int q = t; q < nq; q += T) {
-    double mult = a.update*a.ed.tss[(size_t)e*nq + q]/nom;
-    if constexpr (DEF) mult /= a.det[(size_t)(e - a.n_car)*nq + q];
+    double mult = a.update*s_tss[q]/nom;
+    if constexpr (DEF) mult /= s_det[q];
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double r0 = 0., r1 = 0.;
@@ -656,11 +677,9 @@ int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
 {
   if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
     if (a.use_filter || !c->use_pipe) return -1;
-    using C = NsCfg<RS, true>;
-    const size_t smem = sizeof(double)*C::smem_doubles;
     const int grid = a.elem_end - a.elem_begin;
-    if (deformed) { auto k = ns_local_line_kernel<RS, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops); }
-    else { auto k = ns_local_line_kernel<RS, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops); }
+    if (deformed) { using C = NsCfg<RS, true>; auto k = ns_local_line_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    else { using C = NsCfg<RS, false>; auto k = ns_local_line_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
     return 0;
   } else {
     return -1;

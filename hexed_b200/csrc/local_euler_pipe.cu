@@ -35,7 +35,8 @@ struct PipeCfg
   static constexpr int stage_doubles = st_nrml + (DEF ? ND*ND*nq : 0);
   // single-buffered late inputs: residual cache | tss | det
   static constexpr int lt_cache = 0, lt_tss = nv*nq, lt_det = lt_tss + nq;
-  static constexpr int late_doubles = lt_det + (DEF ? nq : 0);
+  static constexpr int lt_vtss = lt_det + (DEF ? nq : 0);
+  static constexpr int late_doubles = lt_vtss + 8; // + the 2^3 vertex time-step scales (used by the CFL screen)
   static constexpr int r_doubles = ND*nv*nq;
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
   static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + per-warp CFL minima
@@ -46,7 +47,7 @@ struct PipeArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
-  const double* vtss; double* cfl_ratio; // cfl_ratio != nullptr: leave min_q spacing/char_speed of the NEW state behind (see common.cuh)
+  const double* vtss; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
 
 template <int RS, bool DEF>
@@ -60,18 +61,19 @@ __device__ __forceinline__ void pipe_issue_stage(const PipeArgs& a, int e, doubl
   if constexpr (DEF) bulk_g2s(buf + C::st_nrml, a.refn + (size_t)(e - a.n_car)*C::ND*C::ND*C::nq, b_nrml, bar);
 }
 
-template <int RS, bool DEF>
+template <int RS, bool DEF, bool CFL>
 __device__ __forceinline__ void pipe_issue_late(const PipeArgs& a, int e, double* buf, mbar_t* bar)
 {
   using C = PipeCfg<RS, DEF>;
   constexpr unsigned b_cache = sizeof(double)*C::nv*C::nq, b_pt = sizeof(double)*C::nq;
-  mbar_arrive_expect_tx(bar, (a.stage ? b_cache : 0u) + b_pt + (DEF ? b_pt : 0u));
+  mbar_arrive_expect_tx(bar, (a.stage ? b_cache : 0u) + b_pt + (DEF ? b_pt : 0u) + (CFL ? 64u : 0u));
+  if constexpr (CFL) bulk_g2s(buf + C::lt_vtss, a.vtss + (size_t)e*8, 64u, bar);
   if (a.stage) bulk_g2s(buf + C::lt_cache, a.cache + (size_t)e*C::cs*C::nq, b_cache, bar);
   bulk_g2s(buf + C::lt_tss, a.tss + (size_t)e*C::nq, b_pt, bar);
   if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e - a.n_car)*C::nq, b_pt, bar);
 }
 
-template <int RS, bool DEF>
+template <int RS, bool DEF, bool CFL>
 __global__ void __launch_bounds__(PipeCfg<RS, DEF>::threads)
 local_euler_pipe_kernel(PipeArgs a, Ops ops)
 {
@@ -81,10 +83,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   double* late = smem + 2*C::stage_doubles;
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
-  float* warp_cfl = reinterpret_cast<float*>(bars + 4);                       // per-warp minima of the single-precision CFL screen
-  unsigned long long* cfl_exact = reinterpret_cast<unsigned long long*>(bars + 6); // bit pattern of the element's exact minimum
-  constexpr int n_round = (nq + C::threads - 1)/C::threads;
-  float cfl_approx[n_round];
+  [[maybe_unused]] float* warp_cfl = reinterpret_cast<float*>(bars + 4); // per-warp minima of the single-precision CFL screen
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -98,7 +97,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   if (t == 0) {
     pipe_issue_stage<RS, DEF>(a, e, smem, &bars[0]);
     if (e + stride_e < a.elem_end) pipe_issue_stage<RS, DEF>(a, e + stride_e, smem + C::stage_doubles, &bars[1]);
-    pipe_issue_late<RS, DEF>(a, e, late, &bars[2]);
+    pipe_issue_late<RS, DEF, CFL>(a, e, late, &bars[2]);
   }
 
   // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
@@ -164,93 +163,71 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_wait(&bars[2], it & 1);
     {
       const double nom = a.nom[e];
-      float vt[8];
-      if (a.cfl_ratio) {
+      [[maybe_unused]] float cfl_min = 3.0e38f;
+      for (int q = t; q < nq; q += C::threads) {
+        double mult = a.update*late[C::lt_tss + q]/nom;
+        if constexpr (DEF) mult /= late[C::lt_det + q];
+        [[maybe_unused]] double x[nv];
         #pragma unroll
-        for (int i = 0; i < 8; ++i) vt[i] = (float)a.vtss[(size_t)e*8 + i];
-      }
-      float cfl_min = 3.0e38f;
-      #pragma unroll
-      for (int it_q = 0; it_q < n_round; ++it_q) {
-        const int q = t + it_q*C::threads;
-        cfl_approx[it_q] = 3.0e38f;
-        if (q < nq) {
-          double mult = a.update*late[C::lt_tss + q]/nom;
-          if constexpr (DEF) mult /= late[C::lt_det + q];
-          double x[nv];
-          #pragma unroll
-          for (int v = 0; v < nv; ++v) {
-            double u = R[(0*nv + v)*nq + q];
-            u += R[(1*nv + v)*nq + q];
-            u += R[(2*nv + v)*nq + q];
-            double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
-            if (a.stage) u -= late[C::lt_cache + v*nq + q];
-            else if (!a.compute_residual) *cache = u;
-            u *= mult;
-            x[v] = 0.;
-            if (a.compute_residual) *cache = u;
-            else {
-              x[v] = S[v*nq + q] + u;
-              S[v*nq + q] = x[v];
-              a.state[((size_t)e*nv + v)*nq + q] = x[v];
-            }
-          }
-          if (a.cfl_ratio) {
-            /* CFL screening in single precision (a few MUFU-assisted instructions instead of two FP64 square roots and two
-             * divisions per point): spacing/char_speed of the new state to ~1e-6 relative; the exact FP64 value is evaluated
-             * below only for the points within 1e-5 of the element's minimum. Anything that is not a positive finite float
-             * makes every point of the element a candidate. */
-            const float rho = (float)x[ND], en = (float)x[ND + 1];
-            const float mx = (float)x[0], my = (float)x[1], mz = (float)x[2];
-            const float inv = 1.f/rho;
-            const float cs = sqrtf(0.56f*en*inv) + sqrtf(mx*mx + my*my + mz*mz)*inv;
-            float sv[8];
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) sv[i] = vt[i];
-            int str = 8;
-            #pragma unroll
-            for (int d = 0; d < ND; ++d) {
-              const float coord = (float)ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
-              str /= 2;
-              #pragma unroll
-              for (int i = 0; i < 4; ++i) if (i < str) sv[i] += coord*(sv[i + str] - sv[i]);
-            }
-            float r = sv[0]/cs;
-            if (!(r > 0.f && r < 3.0e38f)) r = -1.f;
-            cfl_approx[it_q] = r;
-            cfl_min = fminf(cfl_min, r);
+        for (int v = 0; v < nv; ++v) {
+          double u = R[(0*nv + v)*nq + q];
+          u += R[(1*nv + v)*nq + q];
+          u += R[(2*nv + v)*nq + q];
+          double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+          if (a.stage) u -= late[C::lt_cache + v*nq + q];
+          else if (!a.compute_residual) *cache = u;
+          u *= mult;
+          if (a.compute_residual) *cache = u;
+          else {
+            const double xv = S[v*nq + q] + u;
+            S[v*nq + q] = xv;
+            a.state[((size_t)e*nv + v)*nq + q] = xv;
+            if constexpr (CFL) x[v] = xv;
           }
         }
+        if constexpr (CFL) {
+          /* CFL screen in single precision while the new state is in registers: spacing/char_speed (reference Spatial.hpp:808-822)
+           * to ~1e-6 relative with MUFU-assisted float instructions. The next max_dt_euler reduces these and re-evaluates in
+           * FP64 only the elements within 1e-5 of the global minimum (misc_kernels.cu), so the time step itself is exact. A value
+           * that is not a positive finite float is stored as 0 = "always re-evaluate this element". */
+          const float rho = (float)x[ND], en = (float)x[ND + 1];
+          const float mx = (float)x[0], my = (float)x[1], mz = (float)x[2];
+          const float inv = 1.f/rho;
+          const float cs = sqrtf(0.56f*en*inv) + sqrtf(mx*mx + my*my + mz*mz)*inv;
+          float sv[8];
+          #pragma unroll
+          for (int i = 0; i < 8; ++i) sv[i] = (float)late[C::lt_vtss + i];
+          int str = 8;
+          #pragma unroll
+          for (int d = 0; d < ND; ++d) {
+            const float coord = (float)ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+            str /= 2;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < str) sv[i] += coord*(sv[i + str] - sv[i]);
+          }
+          float r = sv[0]/cs;
+          if (!(r > 0.f && r < 3.0e38f)) r = 0.f;
+          cfl_min = fminf(cfl_min, r);
+        }
       }
-      if (a.cfl_ratio) {
+      if constexpr (CFL) {
         #pragma unroll
         for (int off = 16; off > 0; off /= 2) cfl_min = fminf(cfl_min, __shfl_xor_sync(0xffffffffu, cfl_min, off));
         if (t % 32 == 0) warp_cfl[t/32] = cfl_min;
-        if (t == 0) *cfl_exact = 0x7ff0000000000000ull; // +infinity
       }
     }
     __syncthreads(); // new state complete in S; late buffer free
+    if constexpr (CFL) {
+      if (t == 0) {
+        float m = warp_cfl[0];
+        #pragma unroll
+        for (int i = 1; i < C::threads/32; ++i) m = fminf(m, warp_cfl[i]);
+        a.cfl_approx[e] = m;
+      }
+    }
     if (t == 0 && e + stride_e < a.elem_end) {
       fence_proxy_async();
-      pipe_issue_late<RS, DEF>(a, e + stride_e, late, &bars[2]);
-    }
-    if (a.cfl_ratio) { // exact CFL ratio of the candidate points (reference Spatial.hpp:808-822 arithmetic, as in max_dt_euler_kernel)
-      float bmin = warp_cfl[0];
-      #pragma unroll
-      for (int i = 1; i < C::threads/32; ++i) bmin = fminf(bmin, warp_cfl[i]);
-      const float thr = bmin < 0.f ? 3.4e38f : bmin*1.00001f;
-      #pragma unroll
-      for (int it_q = 0; it_q < n_round; ++it_q) {
-        const int q = t + it_q*C::threads;
-        if (q < nq && cfl_approx[it_q] <= thr) {
-          EulerPoint<ND> pt;
-          #pragma unroll
-          for (int v = 0; v < nv; ++v) pt.s[v] = S[v*nq + q];
-          pt.inv_mass = 1./pt.s[ND];
-          const double ratio = interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*8, ops, q)/pt.char_speed();
-          atomicMin(cfl_exact, (unsigned long long)__double_as_longlong(ratio));
-        }
-      }
+      pipe_issue_late<RS, DEF, CFL>(a, e + stride_e, late, &bars[2]);
     }
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
@@ -270,7 +247,6 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
       }
     }
     __syncthreads(); // stage buffer s free
-    if (t == 0 && a.cfl_ratio) a.cfl_ratio[e] = __longlong_as_double((long long)*cfl_exact);
     if (t == 0 && e + 2*stride_e < a.elem_end) {
       fence_proxy_async();
       pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
@@ -278,11 +254,11 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   }
 }
 
-template <int RS, bool DEF>
+template <int RS, bool DEF, bool CFL>
 static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
 {
   using C = PipeCfg<RS, DEF>;
-  auto k = local_euler_pipe_kernel<RS, DEF>;
+  auto k = local_euler_pipe_kernel<RS, DEF, CFL>;
   static int blocks_per_sm = 0; // per instantiation
   if (!blocks_per_sm) {
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
@@ -310,16 +286,20 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
-  a.vtss = c->vtss; a.cfl_ratio = nullptr;
+  a.vtss = c->vtss; a.cfl_approx = nullptr;
   c->cfl_valid[deformed ? 1 : 0] = false; // this launch rewrites the state of the set
   const bool leave_cfl = c->use_cfl_cache && a.stage && !a.compute_residual;
   if (leave_cfl) {
-    if (!c->cfl_ratio) HB_CUDA(c, cudaMalloc(&c->cfl_ratio, sizeof(double)*c->n_elem));
-    a.cfl_ratio = c->cfl_ratio;
+    if (!c->cfl_approx) HB_CUDA(c, cudaMalloc(&c->cfl_approx, sizeof(float)*c->n_elem));
+    a.cfl_approx = c->cfl_approx;
   }
   int rc;
-  if (c->rs == 6) rc = deformed ? launch_pipe<6, true>(c, a) : launch_pipe<6, false>(c, a);
-  else rc = deformed ? launch_pipe<4, true>(c, a) : launch_pipe<4, false>(c, a);
+  if (leave_cfl) {
+    if (c->rs == 6) rc = deformed ? launch_pipe<6, true, true>(c, a) : launch_pipe<6, false, true>(c, a);
+    else rc = deformed ? launch_pipe<4, true, true>(c, a) : launch_pipe<4, false, true>(c, a);
+  }
+  else if (c->rs == 6) rc = deformed ? launch_pipe<6, true, false>(c, a) : launch_pipe<6, false, false>(c, a);
+  else rc = deformed ? launch_pipe<4, true, false>(c, a) : launch_pipe<4, false, false>(c, a);
   if (rc == 0 && leave_cfl) c->cfl_valid[deformed ? 1 : 0] = true;
   return rc;
 }

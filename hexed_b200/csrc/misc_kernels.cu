@@ -46,23 +46,55 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
   }
 }
 
-/* Global time step from the per-element CFL ratios min_q spacing/char_speed that the stage-1 Local kernel leaves behind
- * (local_euler_pipe.cu): the reduction the reference does in Max_dt, without re-reading the state. */
+/* Global time step from the single-precision CFL screen that the stage-1 Local kernel leaves behind (local_euler_pipe.cu):
+ *   1. cfl_screen_min_kernel: minimum of the positive screen values (bit pattern of a positive float orders like an int);
+ *   2. cfl_exact_kernel: one warp per element; an element whose screen value is 0 (not representable) or within 1e-5 of that
+ *      minimum (the screen is good to ~1e-6) is re-evaluated from its state with the exact FP64 arithmetic of max_dt_euler_kernel.
+ * Typically a handful of elements are touched instead of the whole state; a uniform flow degenerates to the full pass. */
 __global__ void __launch_bounds__(256)
-cfl_reduce_kernel(const double* ratio, int n, unsigned long long* global_min)
+cfl_screen_min_kernel(const float* approx, int n, int* global_min_bits)
 {
-  __shared__ double warp_min[8];
-  double val = DBL_MAX;
-  for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) val = fmin(val, ratio[i]);
+  __shared__ float warp_min[8];
+  float val = 3.0e38f;
+  for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) {
+    const float a = approx[i];
+    if (a > 0.f) val = fminf(val, a);
+  }
   #pragma unroll
-  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  for (int off = 16; off > 0; off /= 2) val = fminf(val, __shfl_xor_sync(0xffffffffu, val, off));
   if (threadIdx.x % 32 == 0) warp_min[threadIdx.x/32] = val;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double m = warp_min[0];
-    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
-    atomicMin(global_min, (unsigned long long)__double_as_longlong(m));
+    float m = warp_min[0];
+    for (int i = 1; i < (int)blockDim.x/32; ++i) m = fminf(m, warp_min[i]);
+    atomicMin(global_min_bits, __float_as_int(m));
   }
+}
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(256)
+cfl_exact_kernel(MaxDtArgs a, Ops ops, const float* approx, const int* screen_min_bits)
+{
+  constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND);
+  const float thr = __int_as_float(*screen_min_bits)*1.00001f;
+  const int lane = threadIdx.x % 32;
+  const long long warp0 = ((long long)blockIdx.x*blockDim.x + threadIdx.x)/32, n_warp = (long long)gridDim.x*blockDim.x/32;
+  double val = DBL_MAX;
+  for (long long e = warp0; e < a.n_elem; e += n_warp) {
+    const float ap = approx[e];
+    if (ap > thr) continue;
+    for (int q = lane; q < nq; q += 32) {
+      const double spacing = interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*n_vert, ops, q);
+      EulerPoint<ND> p;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
+      p.inv_mass = 1./p.s[ND];
+      val = fmin(val, a.max_cfl_c*spacing/p.char_speed());
+    }
+  }
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, off));
+  if (lane == 0 && val < DBL_MAX) atomicMin(a.global_min, (unsigned long long)__double_as_longlong(val));
 }
 
 __global__ void __launch_bounds__(256)
@@ -71,7 +103,7 @@ fill_kernel(double* dst, long long n, double value)
   for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) dst[i] = value;
 }
 
-static int max_dt_from_cfl_cache(hexed_b200_ctx* c, double max_cfl_c, double* dt)
+static int max_dt_from_cfl_screen(hexed_b200_ctx* c, double max_cfl_c, double* dt)
 {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -79,15 +111,29 @@ static int max_dt_from_cfl_cache(hexed_b200_ctx* c, double max_cfl_c, double* dt
     HB_LAUNCH(fill_kernel, sms*8, 256, 0, c->stream, c->tss, (long long)c->n_elem*c->nq, 1.);
     count_launch(c, ST_MAX_DT_CAR);
   }
-  HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream));
+  HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, 2*sizeof(double), c->stream)); // slot 0: exact minimum (1.4e306), slot 1: screen minimum (3.4e38f)
+  int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
   int grid = (c->n_elem + 255)/256;
   if (grid > sms*8) grid = sms*8;
-  HB_LAUNCH(cfl_reduce_kernel, grid, 256, 0, c->stream, c->cfl_ratio, c->n_elem, reinterpret_cast<unsigned long long*>(c->d_scalar));
+  HB_LAUNCH(cfl_screen_min_kernel, grid, 256, 0, c->stream, c->cfl_approx, c->n_elem, screen_bits);
+  count_launch(c, ST_MAX_DT_CAR);
+  int rc = dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    MaxDtArgs a;
+    a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem; a.max_cfl_c = max_cfl_c; a.is_local = 0;
+    a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
+    long long blocks = ((long long)c->n_elem*32 + 255)/256;
+    if (blocks > sms*16) blocks = sms*16;
+    auto k = cfl_exact_kernel<ND, RS>;
+    HB_LAUNCH(k, (int)blocks, 256, 0, c->stream, a, c->ops, (const float*)c->cfl_approx, (const int*)screen_bits);
+    return 0;
+  });
+  if (rc) return rc;
   count_launch(c, ST_MAX_DT_CAR);
   HB_CUDA(c, cudaGetLastError());
   HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
-  *dt = max_cfl_c*(*c->h_scalar); // max_cfl*spacing/char_speed with the division done when the state was written
+  *dt = *c->h_scalar;
   c->tss_is_one = true;
   return 0;
 }
@@ -98,8 +144,8 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
   StatScope s_car(c, ST_MAX_DT_CAR, c->n_car);
   c->stats[ST_MAX_DT_DEF].work_units += c->n_def;
   if (!c->n_elem) { *dt = local_time ? 1. : DBL_MAX; return 0; }
-  if (!local_time && c->use_cfl_cache && c->cfl_ratio && (c->n_car == 0 || c->cfl_valid[0]) && (c->n_def == 0 || c->cfl_valid[1]))
-    return max_dt_from_cfl_cache(c, (-2*c->quad_safety/c->min_eig_conv)*safety_conv, dt);
+  if (!local_time && c->use_cfl_cache && c->cfl_approx && (c->n_car == 0 || c->cfl_valid[0]) && (c->n_def == 0 || c->cfl_valid[1]))
+    return max_dt_from_cfl_screen(c, (-2*c->quad_safety/c->min_eig_conv)*safety_conv, dt);
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)c->n_elem*ipow(RS, ND);

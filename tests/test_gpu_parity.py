@@ -129,6 +129,13 @@ def test_full_size_properties(gpu_lib):
     out = np.empty_like(st)
     dev.download_elements(out, 0, nd + 2)
     assert rel_l2(out, st) <= 1e-11  # freestream preservation
+    # the CFL screen left by the stage-1 Local kernel: in a uniform flow every element ties, so every element is re-evaluated;
+    # the result must be the very number the full max_dt kernel computes
+    n0 = dev.launch_count()
+    dt_screen = dev.max_dt_euler(0.7, 0.7, False)
+    assert dev.launch_count() - n0 == 2
+    dev.set_option(1, 0); dt_full = dev.max_dt_euler(0.7, 0.7, False); dev.set_option(1, 1)
+    assert dt_screen == dt_full
     # max_dt vs local tss: global dt == min over qpoints of the local scale
     dev.upload_elements(np.ascontiguousarray(st), 0, nd + 2)
     dev.max_dt_euler(0.7, 0.7, True)
