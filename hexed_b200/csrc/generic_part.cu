@@ -52,7 +52,7 @@ template <int ND, int RS> struct Line
 
 /* ---------------- Neighbor ---------------- */
 template <int ND, int RS, class P, bool DEF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 g_neighbor_kernel(GArgs a)
 {
   constexpr int nfq = ipow(RS, ND - 1), ne = P::n_extrap, nu = P::n_update, wl = (ND + 2)*nfq;
@@ -526,10 +526,10 @@ ns_local_line_kernel(GArgs a, Ops ops)
       if (t < ND*nfq) {
         const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
         const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
-        double nk[RS];
+        double nk[RS]; // the 1/nominal-size factor of the gradient (Spatial.hpp:398) is folded into the normals once per line
         #pragma unroll
-        for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride];
-        const double fn0 = fn[((2*d)*ND + j)*nfq + l], fn1 = fn[((2*d + 1)*ND + j)*nfq + l];
+        for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride]*inv_nom;
+        const double fn0 = fn[((2*d)*ND + j)*nfq + l]*inv_nom, fn1 = fn[((2*d + 1)*ND + j)*nfq + l]*inv_nom;
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
           double p[RS];
@@ -544,7 +544,7 @@ ns_local_line_kernel(GArgs a, Ops ops)
             acc += ops.lift[i][0]*b0;
             acc += ops.lift[i][1]*b1;
             double* g = G + (v*ND + j)*nq + q0 + i*stride;
-            if (d == 0) *g = acc*inv_nom; else *g += acc*inv_nom;
+            if (d == 0) *g = acc; else *g += acc;
           }
         }
       }
@@ -653,8 +653,9 @@ ns_local_line_kernel(GArgs a, Ops ops)
 
   /* ---- P4: combine and update ---- */
   for (int q = t; q < nq; q += T) {
-    double mult = a.update*s_tss[q]/nom;
-    if constexpr (DEF) mult /= s_det[q];
+    double mult; // update*tss/nom/det with one division (<= 1 ulp)
+    if constexpr (DEF) mult = a.update*s_tss[q]/(nom*s_det[q]);
+    else mult = a.update*s_tss[q]/nom;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double r0 = 0., r1 = 0.;

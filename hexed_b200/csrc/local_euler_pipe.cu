@@ -39,7 +39,7 @@ struct PipeCfg
   static constexpr int late_doubles = lt_vtss + 8; // + the 2^3 vertex time-step scales (used by the CFL screen)
   static constexpr int r_doubles = ND*nv*nq;
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
-  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + per-warp CFL minima
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + CFL screen scratch (4 per-warp minima, 8 vertex spacings, floats)
 };
 
 struct PipeArgs
@@ -47,7 +47,7 @@ struct PipeArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
-  const double* vtss; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
+  const double* vtss; float nodef[MAX_RS]; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
 
 template <int RS, bool DEF>
@@ -84,6 +84,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
   [[maybe_unused]] float* warp_cfl = reinterpret_cast<float*>(bars + 4); // per-warp minima of the single-precision CFL screen
+  [[maybe_unused]] float* vt_f = warp_cfl + 4;                           // the element's 8 vertex spacings in single precision
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -115,6 +116,9 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     const double* N = stage_buf + C::st_nrml;
     mbar_wait(&bars[s], par);
 
+    if constexpr (CFL) { // published to everyone by the barrier between phases A and B
+      if (t < 8) { mbar_wait(&bars[2], it & 1); vt_f[t] = (float)late[C::lt_vtss + t]; }
+    }
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if (has_line) {
       double f[nv][RS];
@@ -165,8 +169,10 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
       const double nom = a.nom[e];
       [[maybe_unused]] float cfl_min = 3.0e38f;
       for (int q = t; q < nq; q += C::threads) {
-        double mult = a.update*late[C::lt_tss + q]/nom;
-        if constexpr (DEF) mult /= late[C::lt_det + q];
+        // update*tss/nom/det (reference Spatial.hpp:484-487) with one division instead of two (<= 1 ulp)
+        double mult;
+        if constexpr (DEF) mult = a.update*late[C::lt_tss + q]/(nom*late[C::lt_det + q]);
+        else mult = a.update*late[C::lt_tss + q]/nom;
         [[maybe_unused]] double x[nv];
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
@@ -191,21 +197,22 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
            * FP64 only the elements within 1e-5 of the global minimum (misc_kernels.cu), so the time step itself is exact. A value
            * that is not a positive finite float is stored as 0 = "always re-evaluate this element". */
           const float rho = (float)x[ND], en = (float)x[ND + 1];
-          const float mx = (float)x[0], my = (float)x[1], mz = (float)x[2];
-          const float inv = 1.f/rho;
-          const float cs = sqrtf(0.56f*en*inv) + sqrtf(mx*mx + my*my + mz*mz)*inv;
+          const float m2 = (float)(x[0]*x[0] + x[1]*x[1] + x[2]*x[2]);
+          const float inv = __fdividef(1.f, rho);
+          const float a2 = 0.56f*en*inv;
+          const float cs = a2*rsqrtf(a2) + m2*rsqrtf(m2 + 1e-30f)*inv; // sqrt(x) = x*rsqrt(x): one MUFU each
           float sv[8];
           #pragma unroll
-          for (int i = 0; i < 8; ++i) sv[i] = (float)late[C::lt_vtss + i];
+          for (int i = 0; i < 8; ++i) sv[i] = vt_f[i];
           int str = 8;
           #pragma unroll
           for (int d = 0; d < ND; ++d) {
-            const float coord = (float)ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+            const float coord = a.nodef[(q/ipow(RS, ND - 1 - d)) % RS];
             str /= 2;
             #pragma unroll
             for (int i = 0; i < 4; ++i) if (i < str) sv[i] += coord*(sv[i + str] - sv[i]);
           }
-          float r = sv[0]/cs;
+          float r = __fdividef(sv[0], cs);
           if (!(r > 0.f && r < 3.0e38f)) r = 0.f;
           cfl_min = fminf(cfl_min, r);
         }
@@ -287,6 +294,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   a.vtss = c->vtss; a.cfl_approx = nullptr;
+  for (int i = 0; i < MAX_RS; ++i) a.nodef[i] = (float)c->ops.node[i];
   c->cfl_valid[deformed ? 1 : 0] = false; // this launch rewrites the state of the set
   const bool leave_cfl = c->use_cfl_cache && a.stage && !a.compute_residual;
   if (leave_cfl) {
