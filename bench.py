@@ -237,6 +237,7 @@ def main():
 
     from hexed_b200.halo import DeviceHalo
     halo = DeviceHalo(dev, m) if world > 1 else None
+    halo_ldg = DeviceHalo(dev, m, kind=1) if (world > 1 and args.pde == "navier_stokes") else None
 
     def global_dt(dt):
         if dist is None:
@@ -255,18 +256,24 @@ def main():
             dev.compute_euler_finish(dt=dt, i_stage=stage)
 
     viscous = args.pde == "navier_stokes"
-    if viscous and world > 1:
-        raise RuntimeError("--pde navier_stokes is a single-GPU bench line (the viscous halo exchange is not wired into bench.py)")
     from hexed_b200.kernels import sutherland
     visc, cond = sutherland(1.716e-5, 273., 111.), sutherland(0.0241, 273., 194.)  # air (reference samples/Case.hil:83-90)
 
     def step():
         if viscous:  # Solver::update with use_ldg(): src/Solver.cpp:857-865
-            dt = dev.max_dt_navier_stokes(0.7, 0.7, False, visc, cond)
+            dt = global_dt(dev.max_dt_navier_stokes(0.7, 0.7, False, visc, cond))
             dev.apply_state_bcs()
-            dev.compute_navier_stokes(dev.apply_flux_bcs, visc, cond, dt=dt, i_stage=0)
+            if halo is None:
+                dev.compute_navier_stokes(dev.apply_flux_bcs, visc, cond, dt=dt, i_stage=0)
+            else:  # two exchanges: state faces before Neighbor, viscous-flux (LDG) faces before Neighbor_reconcile
+                halo.start()
+                dev.compute_navier_stokes_begin(visc, cond, dt=dt, i_stage=0)
+                halo.finish()
+                dev.compute_navier_stokes_middle(lambda: (dev.apply_flux_bcs(), halo_ldg.start()), visc, cond, dt=dt, i_stage=0)
+                halo_ldg.finish()
+                dev.compute_navier_stokes_finish(visc, cond, dt=dt, i_stage=0)
             dev.apply_state_bcs()
-            dev.compute_euler(dt=dt, i_stage=1)
+            stage_kernels(dt, 1)
             return
         dt = global_dt(dev.max_dt_euler(0.7, 0.7, False))
         for stage in (0, 1):

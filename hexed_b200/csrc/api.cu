@@ -529,8 +529,8 @@ static int convection_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, co
   const GenericOps* g = generic_ops(pde);
   const int kind = pde == 2 ? 2 : 0, ne = n_extrap_of(c, pde);
   int rc;
-  if ((rc = g->neighbor(c, 0, pp, false))) return rc;
-  if ((rc = g->neighbor(c, 1, pp, false))) return rc;
+  if ((rc = g->neighbor(c, 0, pp, false, 0, -1))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false, 0, -1))) return rc;
   if ((rc = launch_restrict(c, kind, ne, 1))) return rc;
   if ((rc = g->local(c, 0, o, pp, false))) return rc;
   if ((rc = g->local(c, 1, o, pp, false))) return rc;
@@ -545,8 +545,8 @@ static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, con
   const GenericOps* g = generic_ops(pde);
   const int ne = n_extrap_of(c, pde);
   int rc;
-  if ((rc = g->neighbor(c, 0, pp, false))) return rc;
-  if ((rc = g->neighbor(c, 1, pp, false))) return rc;
+  if ((rc = g->neighbor(c, 0, pp, false, 0, -1))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false, 0, -1))) return rc;
   if ((rc = launch_restrict(c, 0, ne, 1))) return rc;
   if ((rc = launch_restrict(c, 1, ne, 0))) return rc;
   if ((rc = g->local(c, 0, o, pp, false))) return rc;
@@ -554,8 +554,64 @@ static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, con
   if (!o.i_stage) {
     if ((rc = launch_prolong(c, 1, ne, 1))) return rc;
     if (flux_bc) flux_bc(user); // host callback = Solver::apply_flux_bcs; it may enqueue device work on this context's stream
-    if ((rc = g->neighbor(c, 0, pp, true))) return rc;
-    if ((rc = g->neighbor(c, 1, pp, true))) return rc;
+    if ((rc = g->neighbor(c, 0, pp, true, 0, -1))) return rc;
+    if ((rc = g->neighbor(c, 1, pp, true, 0, -1))) return rc;
+    if ((rc = launch_restrict(c, 1, ne, 1))) return rc;
+    if ((rc = g->local(c, 0, o, pp, true))) return rc;
+    if ((rc = g->local(c, 1, o, pp, true))) return rc;
+  }
+  if ((rc = launch_prolong(c, 0, ne, 0))) return rc;
+  return 0;
+}
+
+/* compute_navier_stokes in three parts around the two halo exchanges of a partitioned mesh (see include/hexed_b200.h) */
+int hexed_b200_compute_navier_stokes_begin(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
+  const GenericOps* g = generic_ops(1);
+  int rc;
+  if ((rc = g->neighbor(c, 0, pp, false, 0, c->n_car_con - c->n_cut_car))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false, 0, c->n_def_con - c->n_cut_def))) return rc;
+  return 0;
+}
+
+int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
+                                            hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
+  const GenericOps* g = generic_ops(1);
+  const int ne = c->nv;
+  int rc;
+  if (c->n_pre_prolong && (rc = launch_prolong(c, 0, ne, 0, c->pre_prolong, c->n_pre_prolong))) return rc;
+  if ((rc = g->neighbor(c, 0, pp, false, c->n_car_con - c->n_cut_car, c->n_cut_car))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, false, c->n_def_con - c->n_cut_def, c->n_cut_def))) return rc;
+  if ((rc = launch_restrict(c, 0, ne, 1))) return rc;
+  if ((rc = launch_restrict(c, 1, ne, 0))) return rc;
+  if ((rc = g->local(c, 0, o, pp, false))) return rc;
+  if ((rc = g->local(c, 1, o, pp, false))) return rc;
+  if (!o.i_stage) {
+    if ((rc = launch_prolong(c, 1, ne, 1))) return rc;
+    if (flux_bc) flux_bc(user);
+    // the viscous-flux faces of the cut connections travel now; the interior connections are reconciled meanwhile
+    if ((rc = g->neighbor(c, 0, pp, true, 0, c->n_car_con - c->n_cut_car))) return rc;
+    if ((rc = g->neighbor(c, 1, pp, true, 0, c->n_def_con - c->n_cut_def))) return rc;
+  }
+  return 0;
+}
+
+int hexed_b200_compute_navier_stokes_finish(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
+  const GenericOps* g = generic_ops(1);
+  const int ne = c->nv;
+  int rc;
+  if (!o.i_stage) {
+    if (c->n_pre_prolong && (rc = launch_prolong(c, 1, ne, 1, c->pre_prolong, c->n_pre_prolong))) return rc;
+    if ((rc = g->neighbor(c, 0, pp, true, c->n_car_con - c->n_cut_car, c->n_cut_car))) return rc;
+    if ((rc = g->neighbor(c, 1, pp, true, c->n_def_con - c->n_cut_def, c->n_cut_def))) return rc;
     if ((rc = launch_restrict(c, 1, ne, 1))) return rc;
     if ((rc = g->local(c, 0, o, pp, true))) return rc;
     if ((rc = g->local(c, 1, o, pp, true))) return rc;
@@ -634,9 +690,9 @@ int hexed_b200_pde_kernel(hexed_b200_ctx* c, int pde, int which, int deformed, h
   if (!g) return fail(c, HEXED_B200_BAD_ARGUMENT, "pde must be 1 (Navier-Stokes), 2 (advection), 3 (smooth AV) or 4 (fix therm admis)");
   const PdeParams pp = make_params(c, pde, visc, therm_cond, p0, p1);
   switch (which) {
-    case 0: return g->neighbor(c, deformed, pp, false);
+    case 0: return g->neighbor(c, deformed, pp, false, 0, -1);
     case 1: return g->local(c, deformed, o, pp, false);
-    case 2: return g->neighbor(c, deformed, pp, true);
+    case 2: return g->neighbor(c, deformed, pp, true, 0, -1);
     case 3: return g->local(c, deformed, o, pp, true);
   }
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown kernel id");

@@ -145,7 +145,7 @@ int launch_permute_face(hexed_b200_ctx* c, double* d_data, int n_var, int code, 
 /* per-PDE launchers of the generic kernels (generic_part.cu, one translation unit per PDE) */
 struct GenericOps
 {
-  int (*neighbor)(hexed_b200_ctx*, int deformed, const PdeParams&, bool reconcile);
+  int (*neighbor)(hexed_b200_ctx*, int deformed, const PdeParams&, bool reconcile, int first, int count); // count < 0: to the end
   int (*local)(hexed_b200_ctx*, int deformed, hexed_b200_options, const PdeParams&, bool reconcile);
   int (*write_face)(hexed_b200_ctx*, const PdeParams&);
   int (*max_dt)(hexed_b200_ctx*, const PdeParams&, double safety_conv, double safety_diff, int local_time, double* dt);

@@ -870,13 +870,16 @@ int fill_args(hexed_b200_ctx* c, GArgs& a, const PdeParams& pp)
   return 0;
 }
 
-int g_neighbor(hexed_b200_ctx* c, int deformed, const PdeParams& pp, bool reconcile)
+int g_neighbor(hexed_b200_ctx* c, int deformed, const PdeParams& pp, bool reconcile, int first, int count)
 {
-  const int n_con = deformed ? c->n_def_con : c->n_car_con;
+  const int n_all = deformed ? c->n_def_con : c->n_car_con;
+  if (count < 0) count = n_all - first;
+  if (first < 0 || first + count > n_all) return fail(c, HEXED_B200_BAD_ARGUMENT, "connection range out of bounds");
+  const int n_con = count;
   StatScope scope(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR, n_con);
+  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc; // also allocates the LDG face storage on first use
   if (!n_con) return 0;
-  GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
-  a.con = deformed ? c->def_con : c->car_con; a.n_con = n_con;
+  a.con = (deformed ? c->def_con : c->car_con) + (size_t)first*4; a.n_con = n_con;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     using P = Pde<ND, RS>;

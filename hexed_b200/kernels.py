@@ -67,6 +67,9 @@ SIGNATURES = {
     "hexed_b200_face_list_scatter": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_compute_euler_begin": [C.c_void_p],
     "hexed_b200_compute_euler_finish": [C.c_void_p, Options],
+    "hexed_b200_compute_navier_stokes_begin": [C.c_void_p, Options, Transport, Transport],
+    "hexed_b200_compute_navier_stokes_middle": [C.c_void_p, Options, C.c_void_p, C.c_void_p, Transport, Transport],
+    "hexed_b200_compute_navier_stokes_finish": [C.c_void_p, Options, Transport, Transport],
     "hexed_b200_compute_euler": [C.c_void_p, Options],
     "hexed_b200_max_dt_euler": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
     "hexed_b200_compute_write_face": [C.c_void_p],
@@ -285,6 +288,15 @@ class Device:
 
     def compute_euler_finish(self, **kw):
         self._check(self.lib.hexed_b200_compute_euler_finish(self.ctx, self._opts(**kw)))
+
+    def compute_navier_stokes_begin(self, visc, therm_cond, **kw):
+        self._check(self.lib.hexed_b200_compute_navier_stokes_begin(self.ctx, self._opts(**kw), visc, therm_cond))
+
+    def compute_navier_stokes_middle(self, flux_bc, visc, therm_cond, **kw):
+        self._check(self.lib.hexed_b200_compute_navier_stokes_middle(self.ctx, self._opts(**kw), self._cb(flux_bc), None, visc, therm_cond))
+
+    def compute_navier_stokes_finish(self, visc, therm_cond, **kw):
+        self._check(self.lib.hexed_b200_compute_navier_stokes_finish(self.ctx, self._opts(**kw), visc, therm_cond))
 
     def synchronize(self):
         self._check(self.lib.hexed_b200_synchronize(self.ctx))

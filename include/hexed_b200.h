@@ -211,6 +211,19 @@ int hexed_b200_face_list_scatter(hexed_b200_ctx* ctx, int list_id, int kind, con
 int hexed_b200_compute_euler_begin(hexed_b200_ctx* ctx);
 int hexed_b200_compute_euler_finish(hexed_b200_ctx* ctx, hexed_b200_options opts);
 
+/* compute_navier_stokes split around its TWO exchanges (the viscous stage also couples ranks through the LDG faces):
+ *   begin : Neighbor (numerical flux + LDG average state) on the connections that touch no halo face
+ *           -- meanwhile the caller exchanges the state faces (kind 0) of the cut connections --
+ *   middle: pre-prolong, Neighbor on the cut connections, Restrict x2, Local, and for stage 0 Prolong of the viscous flux, flux_bc,
+ *           Neighbor_reconcile on the interior connections
+ *           -- meanwhile the caller exchanges the LDG faces (kind 1) of the cut connections --
+ *   finish: (stage 0) pre-prolong of the LDG halves, Neighbor_reconcile on the cut connections, Restrict, Reconcile_ldg_flux; Prolong
+ * Same kernel order as src/kernels_diffusive.cpp:8-26 on every connection / element. */
+int hexed_b200_compute_navier_stokes_begin(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_transport visc, hexed_b200_transport therm_cond);
+int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_callback flux_bc, void* user,
+                                            hexed_b200_transport visc, hexed_b200_transport therm_cond);
+int hexed_b200_compute_navier_stokes_finish(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_transport visc, hexed_b200_transport therm_cond);
+
 /* ---- profiling side-contract ---- */
 int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
 /* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined

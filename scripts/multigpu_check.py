@@ -30,7 +30,7 @@ def main():
     blocks = M.proc_grid(world, nd)
 
     def build(r):
-        m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=fs, blocks=blocks, block=M.block_coords(r, blocks))
+        m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=fs, blocks=blocks, block=M.block_coords(r, blocks), with_ldg=True)
         density_wave(m, basis)
         return m
     m = build(rank)
@@ -46,13 +46,28 @@ def main():
             dev.apply_state_bcs()
             halo.start(); dev.compute_euler_begin(); halo.finish()
             dev.compute_euler_finish(dt=dt, i_stage=stage)
+    # ---- one viscous step on top: compute_navier_stokes split around its two exchanges, then the inviscid second stage ----
+    from hexed_b200.kernels import sutherland, constant_transport
+    visc, cond = sutherland(1.7e-5, 273., 110.), constant_transport(2.5e-2)
+    halo_ldg = DeviceHalo(dev, m, kind=1)
+    dt_ns = allreduce_min(dev.max_dt_navier_stokes(0.3, 0.3, False, visc, cond), device=cuda)
+    dev.apply_state_bcs()
+    halo.start(); dev.compute_navier_stokes_begin(visc, cond, dt=dt_ns, i_stage=0); halo.finish()
+    dev.compute_navier_stokes_middle(lambda: (dev.apply_flux_bcs(), halo_ldg.start()), visc, cond, dt=dt_ns, i_stage=0)
+    halo_ldg.finish()
+    dev.compute_navier_stokes_finish(visc, cond, dt=dt_ns, i_stage=0)
+    dev.apply_state_bcs()
+    halo.start(); dev.compute_euler_begin(); halo.finish()
+    dev.compute_euler_finish(dt=dt_ns, i_stage=1)
     dev.sync_to_host(m)
     mine = torch.from_numpy(m.state().copy()).to(cuda)
     gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, gathered, dst=0)
     if rank == 0:
         from pyoracle import Oracle
-        from test_partition import oracle_step_parts, in_process_exchange
+        from test_partition import (oracle_step_parts, in_process_exchange, ldg_exchange, oracle_ns_first_half, oracle_ns_second_half,
+                                    oracle_pre_prolong, VISC_O, COND_O)
+        from pyoracle import NAVIER_STOKES
         oracle = Oracle()
         parts = [build(r) for r in range(world)]
         for p in parts:
@@ -62,13 +77,31 @@ def main():
         for s in range(steps):
             dt_o = oracle_step_parts(oracle, basis, parts, ex, safety=0.7)
             dt_errs.append(abs(dts[s]/dt_o - 1))
+        ex1 = ldg_exchange(parts)
+        dt_o = min(oracle.max_dt(NAVIER_STOKES, basis, p, 0.3, 0.3, False, VISC_O, COND_O) for p in parts)
+        dt_errs.append(abs(dt_ns/dt_o - 1))
+        for p in parts:
+            oracle.apply_state_bcs(p)
+        ex()
+        for p in parts:
+            oracle_ns_first_half(oracle, basis, p, dt_o)
+        ex1()
+        for p in parts:
+            oracle_ns_second_half(oracle, basis, p, dt_o)
+        for p in parts:
+            oracle.apply_state_bcs(p)
+        ex()
+        for p in parts:
+            oracle_pre_prolong(oracle, basis, p)
+            oracle.compute_euler(basis, p, dt=dt_o, i_stage=1)
         for r in range(world):
             ref = parts[r].state()
             got = gathered[r].cpu().numpy()
             errs.append(float(np.linalg.norm(got - ref)/np.linalg.norm(ref)))
         ok = max(errs) <= 1e-11 and max(dt_errs) <= 1e-13
         print(json.dumps({"multigpu_check": "ok" if ok else "FAIL", "world": world, "blocks": blocks, "state_rel_l2_per_rank": errs,
-                          "max_dt_rel_err": max(dt_errs), "halo_bytes_per_exchange": halo.bytes_per_exchange}))
+                          "max_dt_rel_err": max(dt_errs), "halo_bytes_per_exchange": halo.bytes_per_exchange,
+                          "steps": "%d Euler steps + 1 viscous step (Navier-Stokes stage 0 with both exchanges, Euler stage 1)" % steps}))
     dev.close()
     dist.barrier()
     dist.destroy_process_group()

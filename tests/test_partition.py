@@ -249,3 +249,164 @@ def test_box_blocks_match_undivided(oracle, deformed, blocks):
         # conservation across the cuts: both ranks computed the same flux, so the faces of a cut hold identical numbers
         for r, m in enumerate(parts):
             assert np.isfinite(m.elem_data).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# viscous stage: two exchanges (state faces before Neighbor, LDG viscous-flux faces before Neighbor_reconcile)
+# ---------------------------------------------------------------------------------------------------------------
+from pyoracle import NAVIER_STOKES  # noqa: E402
+import pyoracle  # noqa: E402
+
+VISC_O, COND_O = pyoracle.sutherland(1.7e-5, 273., 110.), pyoracle.constant(2.5e-2)
+
+
+def _sub_refs(m):
+    view = copy.copy(m)
+    view.ref_face = np.ascontiguousarray(m.ref_face[m.pre_prolong])
+    return view
+
+
+def oracle_ns_first_half(oracle, basis, m, dt):
+    """src/kernels_diffusive.cpp:10-18 kernel by kernel (what compute_navier_stokes_begin + _middle do on the device)"""
+    NS = NAVIER_STOKES
+    if len(getattr(m, "pre_prolong", ())):
+        oracle.compute_prolong(basis, _sub_refs(m), pde=NS)
+    for deformed in (0, 1):
+        oracle.neighbor(NS, deformed, m, 0, VISC_O, COND_O)
+    oracle.compute_restrict(basis, m, True, False, pde=NS)
+    oracle.compute_restrict(basis, m, False, True, pde=NS)
+    for deformed in (0, 1):
+        oracle.local(NS, deformed, basis, m, VISC_O, COND_O, dt=dt, i_stage=0)
+    oracle.compute_prolong(basis, m, True, True, pde=NS)
+    oracle.apply_flux_bcs(m)
+
+
+def oracle_ns_second_half(oracle, basis, m, dt):
+    """src/kernels_diffusive.cpp:19-25"""
+    NS = NAVIER_STOKES
+    if len(getattr(m, "pre_prolong", ())):
+        oracle.compute_prolong(basis, _sub_refs(m), True, True, pde=NS)
+    for deformed in (0, 1):
+        oracle.neighbor_reconcile(NS, deformed, m)
+    oracle.compute_restrict(basis, m, True, True, pde=NS)
+    for deformed in (0, 1):
+        oracle.reconcile_ldg_flux(NS, deformed, basis, m, VISC_O, COND_O, dt=dt, i_stage=0)
+    oracle.compute_prolong(basis, m, pde=NS)
+
+
+def make_ns_case(kind, rng, oracle):
+    from util import prepare_pde_state
+    if kind == "soup2d":
+        basis = hb.gauss_legendre(3)
+        m = M.soup_mesh(2, 3, rng, n_car=8, n_def=14, n_ref=6, with_ldg=True)
+        M.random_flow_state(m, rng)
+        oracle.compute_prolong(basis, m)
+    else:
+        basis = hb.gauss_legendre(3)
+        m = M.box_mesh(3, 3, 4, basis, deformed=True, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+        density_wave(m, basis)
+        oracle.compute_write_face(basis, m)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    return basis, m
+
+
+def ns_reference_step(oracle, basis, m, safety=0.3):
+    ref = m.copy()
+    dt = oracle.max_dt(NAVIER_STOKES, basis, ref, safety, safety, False, VISC_O, COND_O)
+    oracle.apply_state_bcs(ref)
+    oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), VISC_O, COND_O, dt=dt, i_stage=0)
+    oracle.apply_state_bcs(ref)
+    oracle.compute_euler(basis, ref, dt=dt, i_stage=1)
+    return ref, dt
+
+
+def ldg_exchange(parts):
+    def get(p, slots):
+        return parts[p].face_ldg[slots].copy()
+
+    def put(q, slots, data):
+        parts[q].face_ldg[slots] = data
+    return lambda: exchange_in_process(parts, get, put)
+
+
+@pytest.mark.parametrize("kind,n_parts", [("soup2d", 1), ("soup2d", 3), ("box_def", 2), ("box_def", 4)])
+def test_partitioned_viscous_oracle_matches_undivided(oracle, kind, n_parts):
+    """the kernel-by-kernel viscous stage with its two exchanges reproduces compute_navier_stokes on the undivided mesh bit for bit
+    (n_parts = 1: the decomposition itself; > 1: arbitrary ownership, split hanging faces included)"""
+    rng = np.random.default_rng(17)
+    basis, m = make_ns_case(kind, rng, oracle)
+    ref, dt = ns_reference_step(oracle, basis, m)
+    part = rng.integers(0, n_parts, m.n_elem) if kind.startswith("soup") else P.split_by_curve(P.morton_keys(m.elem_index), n_parts)
+    parts = P.partition_mesh(m, part, n_parts)
+    ex0, ex1 = in_process_exchange(parts), ldg_exchange(parts)
+    assert min(oracle.max_dt(NAVIER_STOKES, basis, p, 0.3, 0.3, False, VISC_O, COND_O) for p in parts) == dt
+    for p in parts:
+        oracle.apply_state_bcs(p)
+    ex0()
+    for p in parts:
+        oracle_ns_first_half(oracle, basis, p, dt)
+    ex1()
+    for p in parts:
+        oracle_ns_second_half(oracle, basis, p, dt)
+    for p in parts:
+        oracle.apply_state_bcs(p)
+    ex0()
+    for p in parts:
+        oracle_pre_prolong(oracle, basis, p)
+        oracle.compute_euler(basis, p, dt=dt, i_stage=1)
+    out = m.copy()
+    P.gather_elements(parts, out)
+    assert np.array_equal(out.elem_data, ref.elem_data)
+
+
+@pytest.mark.parametrize("kind,n_parts", [("soup2d", 3), ("box_def", 2)])
+def test_partitioned_viscous_device_split(oracle, emu_lib, kind, n_parts):
+    """compute_navier_stokes_begin / middle / finish of the CUDA sources with both exchanges, several parts in one process"""
+    from hexed_b200.kernels import Device, sutherland, constant_transport
+    from util import rel_l2
+    rng = np.random.default_rng(17)
+    basis, m = make_ns_case(kind, rng, oracle)
+    ref, dt = ns_reference_step(oracle, basis, m)
+    part = rng.integers(0, n_parts, m.n_elem) if kind.startswith("soup") else P.split_by_curve(P.morton_keys(m.elem_index), n_parts)
+    parts = P.partition_mesh(m, part, n_parts)
+    devs = [Device(m.n_dim, m.row_size, basis, lib_path=emu_lib).load_mesh(p) for p in parts]
+    visc, cond = sutherland(1.7e-5, 273., 110.), constant_transport(2.5e-2)
+    w = m.nv*m.nfq
+
+    def exchange(face_kind):
+        def get(p, slots):
+            buf = np.empty((len(slots), w))
+            devs[p].face_list_gather(devs[p].send_lists[[q for q, s in parts[p].halo.send.items() if s is slots][0]], buf, face_kind)
+            devs[p].synchronize()
+            return buf
+
+        def put(q, slots, data):
+            peer = [p for p, s in parts[q].halo.recv.items() if s is slots][0]
+            devs[q].face_list_scatter(devs[q].recv_lists[peer], np.ascontiguousarray(data), face_kind)
+            devs[q].synchronize()
+        exchange_in_process(parts, get, put)
+    dt_d = min(d.max_dt_navier_stokes(0.3, 0.3, False, visc, cond) for d in devs)
+    assert abs(dt_d/dt - 1) <= 1e-13
+    for d in devs:
+        d.apply_state_bcs()
+        d.compute_navier_stokes_begin(visc, cond, dt=dt, i_stage=0)
+    exchange(0)
+    for d in devs:
+        d.compute_navier_stokes_middle(d.apply_flux_bcs, visc, cond, dt=dt, i_stage=0)
+    exchange(1)
+    for d in devs:
+        d.compute_navier_stokes_finish(visc, cond, dt=dt, i_stage=0)
+    for d in devs:
+        d.apply_state_bcs()
+        d.compute_euler_begin()
+    exchange(0)
+    for d in devs:
+        d.compute_euler_finish(dt=dt, i_stage=1)
+    for d, p in zip(devs, parts):
+        d.sync_to_host(p)
+        d.close()
+    out = m.copy()
+    P.gather_elements(parts, out)
+    assert rel_l2(out.state(), ref.state()) <= 1e-11
+    nf = 2*m.n_dim
+    assert rel_l2(out.face_state[:nf*m.n_elem], ref.face_state[:nf*m.n_elem]) <= 1e-11
