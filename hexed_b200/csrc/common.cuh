@@ -90,7 +90,7 @@ struct hexed_b200_ctx
   // just written (0 = not representable, always re-evaluate); cfl_valid[0|1] = every Cartesian | deformed element's entry belongs
   // to the current state. Anything else that writes the state or the vertex spacing clears the flags (invalidate_cfl_cache), and
   // max_dt_euler then runs its full kernel. With valid entries it re-evaluates in FP64 only the elements within 1e-5 of the minimum.
-  bool use_cfl_cache = true;
+  bool use_cfl_cache = false; // measured break-even on B200 (profiles/r01g_ncu_full_euler.md): off unless asked for
   float* cfl_approx = nullptr;
   bool cfl_valid[2] = {false, false};
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)

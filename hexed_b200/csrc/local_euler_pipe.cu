@@ -84,7 +84,6 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
   [[maybe_unused]] float* warp_cfl = reinterpret_cast<float*>(bars + 4); // per-warp minima of the single-precision CFL screen
-  [[maybe_unused]] float* vt_f = warp_cfl + 4;                           // the element's 8 vertex spacings in single precision
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -116,9 +115,6 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     const double* N = stage_buf + C::st_nrml;
     mbar_wait(&bars[s], par);
 
-    if constexpr (CFL) { // published to everyone by the barrier between phases A and B
-      if (t < 8) { mbar_wait(&bars[2], it & 1); vt_f[t] = (float)late[C::lt_vtss + t]; }
-    }
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if (has_line) {
       double f[nv][RS];
@@ -168,6 +164,11 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     {
       const double nom = a.nom[e];
       [[maybe_unused]] float cfl_min = 3.0e38f;
+      [[maybe_unused]] float vt_f[8];
+      if constexpr (CFL) {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) vt_f[i] = (float)late[C::lt_vtss + i];
+      }
       for (int q = t; q < nq; q += C::threads) {
         // update*tss/nom/det (reference Spatial.hpp:484-487) with one division instead of two (<= 1 ulp)
         double mult;

@@ -229,7 +229,8 @@ int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
 /* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined
  * Local kernel where it applies (3-D, row size 4 or 6, no modal filter); default 1
  * HEXED_B200_OPT_CFL_CACHE = the stage-1 Local kernel leaves min(spacing/char_speed) per element behind and the next global-time-step
- * max_dt_euler reduces those instead of re-reading the state (any other write to the state invalidates them); default 1 */
+ * max_dt_euler re-evaluates only the near-minimum elements instead of re-reading the whole state (any other write to the state
+ * invalidates the screen); default 0 -- on B200 the extra work in the Local kernel costs what the saved pass over the state gains */
 enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1 };
 int hexed_b200_set_option(hexed_b200_ctx* ctx, int option, int value);
 int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);

@@ -121,6 +121,7 @@ def test_full_size_properties(gpu_lib):
     st = m.state()
     st[:] = fs[None, :, None]
     dev = Device(nd, rs, basis, lib_path=gpu_lib).load_mesh(m)
+    dev.set_option(1, 1)  # HEXED_B200_OPT_CFL_CACHE on for the screen check below
     dev.compute_write_face()
     dt = dev.max_dt_euler(0.7, 0.7, False)
     assert dt > 0

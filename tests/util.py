@@ -144,6 +144,7 @@ def check_cfl_cache(oracle, lib, rs, n):
     oracle.compute_write_face(basis, m)
     ref = m.copy()
     dev = Device(3, rs, basis, lib_path=lib).load_mesh(m)
+    dev.set_option(1, 1)                                     # HEXED_B200_OPT_CFL_CACHE (off by default)
     dt = dev.max_dt_euler(0.7, 0.7, False)
     for stage in (0, 1):
         oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt, i_stage=stage)
