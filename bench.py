@@ -140,6 +140,8 @@ def build_native_oracle():
 def cpu_reference_rate(args, steps, warmup):
     """the CPU port of the reference kernels (oracle) on a bounded sample of the same workload, all host threads"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core (libgomp reads this at load time)
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     import hexed_b200 as hb
     from hexed_b200 import mesh as M
     from pyoracle import Oracle, EULER

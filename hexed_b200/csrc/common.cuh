@@ -47,7 +47,8 @@ struct PdeParams
 };
 
 struct FaceList { int n = 0; int* d_slots = nullptr; double* d_buf = nullptr; size_t buf_doubles = 0; };
-struct Bc { int kind; int n; int *inside = nullptr, *ghost = nullptr, *normal = nullptr; double* params = nullptr; int n_params = 0; };
+struct Bc { int kind; int n; int *inside = nullptr, *ghost = nullptr, *normal = nullptr; double* params = nullptr; int n_params = 0;
+            double* cache = nullptr; /* No_slip: Boundary_face::state_cache(), [n][nv*nfq] */ };
 
 } // namespace hb
 

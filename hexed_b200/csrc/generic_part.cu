@@ -27,7 +27,7 @@ struct GArgs
   const int* con; const int* perm; int n_con;
   int elem_begin, elem_end, n_car;
   double update; int stage, compute_residual, use_filter;
-  double max_cfl_c, max_cfl_d; int is_local; unsigned long long* global_min;
+  double max_cfl_c, max_cfl_d, inv_max_cfl_c, inv_max_cfl_d; int is_local; unsigned long long* global_min;
   PdeParams pp;
 };
 
@@ -706,6 +706,12 @@ g_reconcile_kernel(GArgs a, Ops ops, FilterOp filt)
   double* svface = sbuf + C::rec_buf;
   load_ops<ND, RS, P>(smem, ops, filt, t, C::threads);
   if (active) {
+    // the per-point inputs of the update are needed only after the face terms: start fetching them now (the first profile of this
+    // kernel showed 20 cycles of long-scoreboard stall per issue on exactly these loads, profiles/r01g_ncu_full_ns.md)
+    prefetch_l1(a.ed.tss + (size_t)e*nq + q);
+    if constexpr (DEF) prefetch_l1(a.det + (size_t)(e - a.n_car)*nq + q);
+    #pragma unroll
+    for (int v = 0; v < nu; ++v) prefetch_l1(a.ed.template slot<ND, RS>(e, a.compute_residual ? cache_slot0 + P::update_slot(v) : P::update_slot(v)) + q);
     const double* base = a.faces_ldg + (size_t)e*2*ND*wl;
     for (int i = q; i < 2*ND*nu*nfq; i += nq) svface[i] = base[(size_t)(i/(nu*nfq))*wl + i % (nu*nfq)];
   }
@@ -813,9 +819,12 @@ g_max_dt_kernel(GArgs a, Ops ops)
     typename P::template Comp<ND> comp;
     #pragma unroll
     for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>(e, P::state_slot(i))[q];
+    // Spatial.hpp:808-822 with the five divisions by max_cfl / spacing replaced by one reciprocal of the spacing and the
+    // host-side reciprocals of the CFL numbers (<= 1 ulp per use; FP64 division is ~30 instructions and this kernel was issue-bound)
+    const double inv_spacing = 1./spacing;
     double scale = 0;
-    if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed/a.max_cfl_c/spacing; }
-    if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity/a.max_cfl_d/spacing/spacing; }
+    if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed*a.inv_max_cfl_c*inv_spacing; }
+    if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity*a.inv_max_cfl_d*inv_spacing*inv_spacing; }
     if (a.is_local) a.ed.tss[(size_t)e*nq + q] = 1./scale;
     else { a.ed.tss[(size_t)e*nq + q] = 1.; val = 1./scale; }
   }
@@ -865,7 +874,7 @@ int fill_args(hexed_b200_ctx* c, GArgs& a, const PdeParams& pp)
   a.con = nullptr; a.perm = c->perm; a.n_con = 0;
   a.elem_begin = 0; a.elem_end = c->n_elem; a.n_car = c->n_car;
   a.update = 0; a.stage = 0; a.compute_residual = 0; a.use_filter = 0;
-  a.max_cfl_c = 1; a.max_cfl_d = 1; a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
+  a.max_cfl_c = 1; a.max_cfl_d = 1; a.inv_max_cfl_c = 1; a.inv_max_cfl_d = 1; a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
   a.pp = pp;
   return 0;
 }
@@ -971,6 +980,7 @@ int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double 
   GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
   a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9), Spatial.hpp:777
   a.max_cfl_d = -2/c->min_eig_diff*safety_diff;                   // Spatial.hpp:778
+    a.inv_max_cfl_c = 1./a.max_cfl_c; a.inv_max_cfl_d = 1./a.max_cfl_d;
   a.is_local = local_time;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;

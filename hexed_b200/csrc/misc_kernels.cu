@@ -278,8 +278,9 @@ int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int*
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<false>(c, kind, n_var, scale); }
 
 /* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */
+constexpr double specific_gas_air_c = 287.05287; // include/constants.hpp:44
 __global__ void __launch_bounds__(256)
-bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params,
+bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params, double* cache,
           double* faces, double* faces_ldg, const double* normals, int nd, int nfq)
 {
   const int nv = nd + 2, w = nv*nfq;
@@ -292,13 +293,37 @@ bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* norma
     return;
   }
   const double* in = faces + (size_t)inside[i]*w + q;
-  if (kind == HEXED_B200_BC_COPY) { // copy_state :12-23 copies both halves of the face storage
+  if (kind == HEXED_B200_BC_COPY || kind == HEXED_B200_BC_OUTFLOW) { // copy_state :12-23 copies both halves of the face storage (Outflow::apply_state :465-468)
     for (int v = 0; v < nv; ++v) gh[v*nfq] = in[v*nfq];
     if (faces_ldg) for (int v = 0; v < nv; ++v) faces_ldg[(size_t)ghost[i]*w + q + v*nfq] = faces_ldg[(size_t)inside[i]*w + q + v*nfq];
     return;
   }
-  // Nonpenetration::apply_state -> reflect_momentum / reflect_normal :301-327
+  if (kind == HEXED_B200_BC_NO_SLIP) { // No_slip::apply_state :367-385
+    const double mass = in[nd*nfq], ener = in[(nd + 1)*nfq];
+    for (int d = 0; d < nd; ++d) gh[d*nfq] = -in[d*nfq];
+    gh[nd*nfq] = mass;
+    // Thermal_bc::ghost_energy: Prescribed_energy -> energy_per_mass*mass, otherwise the inside energy (include/Boundary_condition.hpp:154-186)
+    const double ge = ((int)params[0] == 1) ? params[1]*mass : ener;
+    gh[(nd + 1)*nfq] = ge*ge/ener; // math::pow(x, 2)/state(last)
+    double* sc = cache + (size_t)i*w + q; // state cache = average of ghost and inside state, used by the thermal flux condition
+    for (int v = 0; v < nv; ++v) sc[v*nfq] = (gh[v*nfq] + in[v*nfq])/2;
+    return;
+  }
   const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  if (kind == HEXED_B200_BC_PRESSURE_OUTFLOW) { // Pressure_outflow::apply_state :184-211
+    const int sign = 2*((inside[i] % (2*nd)) % 2) - 1;
+    const double mass = in[nd*nfq];
+    double dot = 0., nsq = 0., msq = 0.;
+    for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq], m = in[d*nfq]; dot += m*nn; nsq += nn*nn; msq += m*m; }
+    const double nrml_veloc = dot/mass/sqrt(nsq);
+    const double kin_ener = .5*msq/mass;
+    const double pres = fmax(.4*(in[(nd + 1)*nfq] - kin_ener), 0.);
+    const double sound_speed = sqrt(1.4*pres/mass);
+    for (int v = 0; v < nv; ++v) gh[v*nfq] = in[v*nfq];
+    if (nrml_veloc*sign < sound_speed) gh[(nd + 1)*nfq] = params[0]/.4 + kin_ener; // subsonic: impose the specified pressure
+    return;
+  }
+  // Nonpenetration::apply_state -> reflect_momentum / reflect_normal :301-327
   double dot = 0., nsq = 0.;
   for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; dot += in[d*nfq]*nn; nsq += nn*nn; }
   for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq] - 2*dot*nr[d*nfq]/nsq;
@@ -315,7 +340,7 @@ int launch_bcs(hexed_b200_ctx* c)
   for (auto& b : c->bcs) {
     if (!b.n) continue;
     const long long total = (long long)b.n*c->nfq;
-    HB_LAUNCH(bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal, b.params,
+    HB_LAUNCH(bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal, b.params, b.cache,
               c->face_state, c->face_ldg, c->normals, c->nd, c->nfq);
     count_launch(c, ST_BC);
     HB_CUDA(c, cudaGetLastError());
@@ -325,7 +350,7 @@ int launch_bcs(hexed_b200_ctx* c)
 
 /* flux boundary conditions: Solver::apply_flux_bcs (reference src/Solver.cpp:69-81) */
 __global__ void __launch_bounds__(256)
-flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal,
+flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params, const double* cache,
                double* faces, double* faces_ldg, const double* normals, int nd, int nfq)
 {
   const int nv = nd + 2, w = nv*nfq;
@@ -339,9 +364,35 @@ flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* 
     for (int v = 0; v < nv; ++v) faces[(size_t)ghost[i]*w + q + v*nfq] = faces[(size_t)inside[i]*w + q + v*nfq];
     return;
   }
+  if (kind == HEXED_B200_BC_OUTFLOW || kind == HEXED_B200_BC_PRESSURE_OUTFLOW) { // negative of the inside flux :213-221,470-477
+    for (int v = 0; v < nv; ++v) gh[v*nfq] = -in[v*nfq];
+    return;
+  }
+  const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  if (kind == HEXED_B200_BC_NO_SLIP) { // No_slip::apply_flux :387-418
+    for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq];
+    gh[nd*nfq] = -in[nd*nfq];
+    double nsq = 0.;
+    for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; nsq += nn*nn; }
+    const double nrm = sqrt(nsq);
+    const int flux_sign = 2*((inside[i] % (2*nd)) % 2) - 1;
+    const double in_e = in[(nd + 1)*nfq];
+    const int thermal = (int)params[0];
+    double ghf; // Thermal_bc::ghost_heat_flux(state cache, inside heat flux per area)
+    if (thermal == 0) ghf = params[1];
+    else if (thermal == 1) ghf = in_e*flux_sign/nrm;
+    else { // Thermal_equilibrium::ghost_heat_flux :359-365
+      const double* sc = cache + (size_t)i*w + q;
+      const double temp = sc[(nd + 1)*nfq]*.4/sc[nd*nfq]/specific_gas_air_c;
+      const double radiative = params[1]*params[5]*(temp*temp*temp*temp);
+      const double conductive = params[2]*(temp - params[3]);
+      ghf = radiative + conductive;
+    }
+    gh[(nd + 1)*nfq] = params[4]*(nrm*flux_sign*ghf - in_e) + in_e;
+    return;
+  }
   // Nonpenetration::apply_flux (src/Boundary_condition.cpp:329-341): negate, then un-invert the normal momentum flux
   for (int v = 0; v < nv; ++v) gh[v*nfq] = -in[v*nfq];
-  const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
   double dot = 0., nsq = 0.;
   for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; dot += gh[d*nfq]*nn; nsq += nn*nn; }
   for (int d = 0; d < nd; ++d) gh[d*nfq] -= 2*dot*nr[d*nfq]/nsq;
@@ -357,7 +408,7 @@ int launch_flux_bcs(hexed_b200_ctx* c)
   for (auto& b : c->bcs) {
     if (!b.n) continue;
     const long long total = (long long)b.n*c->nfq;
-    HB_LAUNCH(flux_bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal,
+    HB_LAUNCH(flux_bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, b.kind, b.n, b.inside, b.ghost, b.normal, b.params, b.cache,
               c->face_state, c->face_ldg, c->normals, c->nd, c->nfq);
     count_launch(c, ST_BC);
     HB_CUDA(c, cudaGetLastError());

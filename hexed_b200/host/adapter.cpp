@@ -115,6 +115,7 @@ struct Mirror
   int boundary_list = -1; // face list id of the boundary connections' faces
   std::vector<int> boundary_slots;
   std::vector<double> staging;
+  bool device_bcs_ran = false; // set by apply_state_bcs / apply_flux_bcs; lets the flux_bc thunk see what its callback did
   ~Mirror() {if (ctx) hexed_b200_destroy(ctx);}
 };
 
@@ -494,9 +495,13 @@ struct Flux_bc_thunk
     auto* self = static_cast<Flux_bc_thunk*>(user);
     if (!*self->fun) return;
     // the host callback reads and writes boundary faces (Solver::apply_flux_bcs, src/Solver.cpp:69-81)
+    // (resident mode: a callback that applies its conditions on the device through hexed_b200::apply_flux_bcs owns the boundary faces
+    // itself -- uploading the host copy afterwards would overwrite what the device just computed)
     if (g_mode == sync_every_call) move_faces(*self->m, faces, false); else move_boundary(*self->m, false);
+    self->m->device_bcs_ran = false;
     (*self->fun)();
-    if (g_mode == sync_every_call) move_faces(*self->m, faces, true); else move_boundary(*self->m, true);
+    if (g_mode == sync_every_call) move_faces(*self->m, faces, true);
+    else if (!self->m->device_bcs_ran) move_boundary(*self->m, true);
   }
 };
 
@@ -558,6 +563,39 @@ void to_device(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsi
 void boundary_faces_to_host(Kernel_mesh km) {move_boundary(mirror(km), false);}
 void ghost_faces_to_device(Kernel_mesh km) {move_boundary(mirror(km), true);}
 void synchronize(Kernel_mesh km) {Mirror& m = mirror(km); check(&m, hexed_b200_synchronize(m.ctx));}
+
+int add_device_bc(Kernel_mesh km, int kind, const std::vector<double*>& inside_faces, const std::vector<double>& params)
+{
+  Mirror& m = mirror(km);
+  std::unordered_map<const double*, int> con_of_inside; // inside face of a boundary connection -> its row in def_con
+  for (int i : m.tab.boundary_con) con_of_inside[m.tab.face_ptr[m.tab.def_con[size_t(i)*7]]] = i;
+  std::vector<int> inside, ghost, normal;
+  for (double* p : inside_faces) {
+    auto it = con_of_inside.find(p);
+    if (it == con_of_inside.end()) throw std::runtime_error("hexed_b200: add_device_bc: not the inside face of a boundary connection");
+    const int* row = m.tab.def_con.data() + size_t(it->second)*7;
+    inside.push_back(row[0]); ghost.push_back(row[1]); normal.push_back(row[6]);
+  }
+  int id = -1;
+  check(&m, hexed_b200_bc_create(m.ctx, kind, int(inside.size()), inside.data(), ghost.data(), normal.data(), params.data(), int(params.size()), &id));
+  return id;
+}
+
+void apply_state_bcs(Kernel_mesh km)
+{
+  Call call(km, faces, faces);
+  check(&call.m, hexed_b200_apply_state_bcs(call.m.ctx));
+  call.m.device_bcs_ran = true;
+  call.finish();
+}
+
+void apply_flux_bcs(Kernel_mesh km)
+{
+  Call call(km, faces, faces);
+  check(&call.m, hexed_b200_apply_flux_bcs(call.m.ctx));
+  call.m.device_bcs_ran = true;
+  call.finish();
+}
 
 } // namespace hexed_b200
 

@@ -303,6 +303,33 @@ int hbh_control(void* handle, int what, unsigned arg)
   }
 }
 
+/* registers a device boundary condition for the boundary connections whose def_con rows are listed, then the two apply calls */
+int hbh_add_device_bc(void* handle, int kind, const int* def_con_index, int n, const double* params, int n_params)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    std::vector<double*> inside;
+    for (int i = 0; i < n; ++i) inside.push_back(h->def_cons[def_con_index[i]]->state(0, false));
+    hexed_b200::add_device_bc(h->mesh(), kind, inside, std::vector<double>(params, params + n_params));
+    return 0;
+  } catch (const std::exception& ex) {
+    h->error = ex.what();
+    return 1;
+  }
+}
+
+int hbh_apply_bcs(void* handle, int flux)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    if (flux) hexed_b200::apply_flux_bcs(h->mesh()); else hexed_b200::apply_state_bcs(h->mesh());
+    return 0;
+  } catch (const std::exception& ex) {
+    h->error = ex.what();
+    return 1;
+  }
+}
+
 /* the adapter's flattening (device-free), translated back to the harness's slot numbering through the host pointers so the test
  * can compare it entry by entry with the tables the mesh was built from. counts[6] = n_car, n_def, n_face_slot, n_normal_slot,
  * n_boundary, n_null_normal */

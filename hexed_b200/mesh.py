@@ -19,7 +19,27 @@ from .tables import Connection_direction
 
 N_FORCING = 4  # reference include/Storage_params.hpp:21
 
-BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_HOST = 0, 1, 2, 3
+BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP = 0, 1, 2, 3, 4, 5  # include/hexed_b200.h
+BC_HOST = 99  # applied by the host (anything the device does not implement)
+THERMAL_HEAT_FLUX, THERMAL_ENERGY, THERMAL_EQUILIBRIUM = 0, 1, 2  # Prescribed_heat_flux / Prescribed_energy / Thermal_equilibrium
+
+
+def _mpow(x, n):
+    """math::pow (reference include/math.hpp:29-36): repeated multiplication starting from 1"""
+    r = 1.
+    for _ in range(n):
+        r = r*x
+    return r
+
+
+# reference include/constants.hpp:52 with the same operation order
+STEFAN_BOLTZMANN = 2*_mpow(np.pi, 5)*_mpow(1.380649e-23, 4)/(15*_mpow(299792458., 2)*_mpow(6.62607015e-34, 3))
+
+
+def no_slip_params(thermal_kind=THERMAL_HEAT_FLUX, a=0., b=0., c=0., coercion=2.):
+    """parameter block of the device No_slip boundary condition: [thermal kind, a, b, c, coercion, stefan_boltzmann] with
+    a = heat flux | energy per mass | emissivity, b = heat transfer coefficient, c = temperature (reference include/Boundary_condition.hpp:140-200)"""
+    return np.array([thermal_kind, a, b, c, coercion, STEFAN_BOLTZMANN], dtype=np.float64)
 
 
 def n_slot(n_dim, row_size):

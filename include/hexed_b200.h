@@ -72,7 +72,8 @@ enum {
   HEXED_B200_UNCERT = 8        /* [n_elem]                 Kernel_element::uncert() */
 };
 
-enum { HEXED_B200_BC_FREESTREAM = 0, HEXED_B200_BC_COPY = 1, HEXED_B200_BC_NONPENETRATION = 2 };
+enum { HEXED_B200_BC_FREESTREAM = 0, HEXED_B200_BC_COPY = 1, HEXED_B200_BC_NONPENETRATION = 2,
+       HEXED_B200_BC_OUTFLOW = 3, HEXED_B200_BC_PRESSURE_OUTFLOW = 4, HEXED_B200_BC_NO_SLIP = 5 };
 
 typedef struct {
   int n_car, n_def;
@@ -190,7 +191,10 @@ int hexed_b200_neighbor_euler(hexed_b200_ctx* ctx, int deformed);   /* Spatial<.
 int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options opts); /* Spatial<..>::Local include/Spatial.hpp:326-509 */
 
 /* ---- device-resident ghost-state boundary conditions (Solver::apply_state_bcs, src/Solver.cpp:56-67) ---- */
-/* Freestream src/Boundary_condition.cpp:66-76 (params = nv doubles), Copy :450-453, Nonpenetration :301-327 */
+/* Freestream src/Boundary_condition.cpp:66-76 (params = nv doubles), Copy :450-453, Nonpenetration :301-327, Outflow :465-477,
+ * Pressure_outflow :184-223 (params = {specified pressure}), No_slip :367-418 (params = {thermal kind, a, b, c, heat flux coercion,
+ * stefan_boltzmann}: kind 0 Prescribed_heat_flux(a), 1 Prescribed_energy(a), 2 Thermal_equilibrium(emissivity a, heat transfer
+ * coefficient b, temperature c), include/Boundary_condition.hpp:140-200; its state cache lives on the device) */
 int hexed_b200_bc_create(hexed_b200_ctx* ctx, int kind, int n, const int* inside_slot, const int* ghost_slot,
                          const int* normal_slot, const double* params, int n_params, int* bc_id);
 int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);

@@ -210,11 +210,17 @@ class Oracle:
         return out
 
     def apply_state_bcs(self, m):
-        """ghost-state fill for the device-capable boundary conditions (reference src/Solver.cpp:56-67)"""
-        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION
+        """ghost-state fill for the device-capable boundary conditions (reference src/Solver.cpp:56-67). Freestream, Copy and
+        Nonpenetration run in the C oracle; Outflow, Pressure_outflow and No_slip are numpy restatements of
+        src/Boundary_condition.cpp:184-211,367-385,465-468 (operation order kept; small meshes only)."""
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP
         pm = self.pack_mesh(m)
+        nd, nfq, nv = m.n_dim, m.nfq, m.n_dim + 2
         for bc in m.bcs:
             n = bc["ghost_slot"].size
+            ins, gh = bc["inside_slot"], bc["ghost_slot"]
+            if n == 0:
+                continue
             if bc["kind"] == BC_FREESTREAM:
                 fs = np.ascontiguousarray(bc["params"], dtype=np.float64)
                 self.lib.ho_bc_freestream(pm, n, _ptr(bc["ghost_slot"], ip), _ptr(fs, dp))
@@ -222,14 +228,45 @@ class Oracle:
                 self.lib.ho_bc_copy(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip))
             elif bc["kind"] == BC_NONPENETRATION:
                 self.lib.ho_bc_nonpenetration(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip), _ptr(bc["normal_slot"], ip))
+            elif bc["kind"] == BC_OUTFLOW:  # copy_state: both halves
+                m.face_state[gh] = m.face_state[ins]
+                if m.face_ldg is not None:
+                    m.face_ldg[gh] = m.face_ldg[ins]
+            elif bc["kind"] == BC_PRESSURE_OUTFLOW:
+                f = m.face_state[ins].reshape(n, nv, nfq)
+                nr = m.normals[bc["normal_slot"]]
+                sign = 2*((ins % (2*nd)) % 2) - 1
+                dot = np.zeros((n, nfq)); nsq = np.zeros((n, nfq)); msq = np.zeros((n, nfq))
+                for d in range(nd):
+                    dot = dot + f[:, d]*nr[:, d]; nsq = nsq + nr[:, d]*nr[:, d]; msq = msq + f[:, d]*f[:, d]
+                mass = f[:, nd]
+                nrml_veloc = dot/mass/np.sqrt(nsq)
+                kin = .5*msq/mass
+                pres = np.maximum(.4*(f[:, nd + 1] - kin), 0.)
+                sound = np.sqrt(1.4*pres/mass)
+                g = f.copy()
+                g[:, nd + 1] = np.where(nrml_veloc*sign[:, None] < sound, bc["params"][0]/.4 + kin, f[:, nd + 1])
+                m.face_state[gh] = g.reshape(n, -1)
+            elif bc["kind"] == BC_NO_SLIP:
+                f = m.face_state[ins].reshape(n, nv, nfq)
+                g = f.copy()
+                g[:, :nd] = -f[:, :nd]
+                ge = bc["params"][1]*f[:, nd] if int(bc["params"][0]) == 1 else f[:, nd + 1]
+                g[:, nd + 1] = ge*ge/f[:, nd + 1]
+                m.face_state[gh] = g.reshape(n, -1)
+                bc["cache"] = ((g + f)/2).reshape(n, -1)
 
     def apply_flux_bcs(self, m):
         """flux boundary conditions of the same kinds (reference src/Solver.cpp:69-81): Freestream/Copy::apply_flux = copy_state
-        (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341); numpy, small meshes only"""
-        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION
+        (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341), Outflow / Pressure_outflow
+        (:213-221,470-477), No_slip (:387-418) with its three Thermal_bc kinds (include/Boundary_condition.hpp:140-186);
+        numpy, small meshes only"""
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP
         nd, nfq = m.n_dim, m.nfq
         for bc in m.bcs:
             ins, gh = bc["inside_slot"], bc["ghost_slot"]
+            if ins.size == 0:
+                continue
             if bc["kind"] in (BC_FREESTREAM, BC_COPY):
                 m.face_ldg[gh] = m.face_ldg[ins]
                 m.face_state[gh] = m.face_state[ins]
@@ -239,4 +276,29 @@ class Oracle:
                 dot = (g[:, :nd]*n).sum(1)
                 nsq = (n*n).sum(1)
                 g[:, :nd] -= 2*dot[:, None, :]*n/nsq[:, None, :]
+                m.face_ldg[gh] = g.reshape(len(gh), -1)
+            elif bc["kind"] in (BC_OUTFLOW, BC_PRESSURE_OUTFLOW):
+                m.face_ldg[gh] = -m.face_ldg[ins]
+            elif bc["kind"] == BC_NO_SLIP:
+                p = bc["params"]
+                f = m.face_ldg[ins].reshape(-1, nd + 2, nfq)
+                g = f.copy()
+                g[:, nd] = -f[:, nd]
+                nr = m.normals[bc["normal_slot"]]
+                nsq = np.zeros((len(ins), nfq))
+                for d in range(nd):
+                    nsq = nsq + nr[:, d]*nr[:, d]
+                nrm = np.sqrt(nsq)
+                flux_sign = (2*((ins % (2*nd)) % 2) - 1)[:, None]
+                in_e = f[:, nd + 1]
+                kind = int(p[0])
+                if kind == 0:
+                    ghf = p[1]
+                elif kind == 1:
+                    ghf = in_e*flux_sign/nrm
+                else:
+                    sc = bc["cache"].reshape(-1, nd + 2, nfq)
+                    temp = sc[:, nd + 1]*.4/sc[:, nd]/287.05287
+                    ghf = p[1]*p[5]*(temp*temp*temp*temp) + p[2]*(temp - p[3])
+                g[:, nd + 1] = p[4]*(nrm*flux_sign*ghf - in_e) + in_e
                 m.face_ldg[gh] = g.reshape(len(gh), -1)

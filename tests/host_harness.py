@@ -81,6 +81,8 @@ class HostHarness:
         L.hbh_control.argtypes = [C.c_void_p, C.c_int, C.c_uint]
         L.hbh_flatten.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.hbh_work_units.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.hbh_add_device_bc.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, dp, C.c_int]
+        L.hbh_apply_bcs.argtypes = [C.c_void_p, C.c_int]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
         m = mesh
         self.m = m
@@ -135,6 +137,17 @@ class HostHarness:
     def ghost_faces_to_device(self): self.control(4)
     def invalidate(self): self.control(5)
     def release(self): self.control(6)
+
+    def add_device_bcs(self, mesh):
+        """register every boundary condition of `mesh` on the device through hexed_b200::add_device_bc"""
+        for bc in mesh.bcs:
+            idx = np.ascontiguousarray(bc["con_index"], dtype=np.int32)
+            params = np.ascontiguousarray(bc["params"], dtype=np.float64) if bc.get("params") is not None else np.zeros(1)
+            n_params = params.size if bc.get("params") is not None else 0
+            self._check(self.lib.hbh_add_device_bc(self.h, bc["kind"], _i(idx), idx.size, _d(params), n_params))
+
+    def apply_state_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 0))
+    def apply_flux_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 1))
 
     def flatten(self):
         m = self.m

@@ -101,3 +101,20 @@ def test_navier_stokes_3d_line_kernel(oracle, emu_lib, kind):
 def test_cfl_cache_follows_the_state(oracle, emu_lib):
     from util import check_cfl_cache
     check_cfl_cache(oracle, emu_lib, 4, 2)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 3), (3, 2)])
+def test_every_device_boundary_condition(oracle, emu_lib, nd, rs):
+    """Freestream, Copy, Nonpenetration, Outflow, Pressure_outflow and No_slip (isothermal / heat flux / thermal equilibrium) as ghost-state
+    and flux conditions of a viscous step (src/Boundary_condition.cpp), each on its own subset of the boundary faces"""
+    from util import mixed_bcs
+    rng = np.random.default_rng(5)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=10, n_def=24, n_ref=2, with_ldg=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    n_bc_faces = m.bcs[0]["ghost_slot"].size
+    mixed_bcs(m, rng)
+    assert n_bc_faces >= 8, n_bc_faces
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2)
+    assert_pde_parity(out, ref, dts)

@@ -216,3 +216,19 @@ def test_stabilizing_art_visc(oracle, gpu_lib):
         dev.sync_to_host(m)
         assert np.abs(m.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
         dev.close()
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 4)])
+def test_every_device_boundary_condition(oracle, gpu_lib, nd, rs):
+    """Freestream, Copy, Nonpenetration, Outflow, Pressure_outflow, No_slip (three thermal kinds) on the device,
+    as ghost-state and flux conditions of viscous steps"""
+    from util import mixed_bcs
+    rng = np.random.default_rng(5)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=10, n_def=24, n_ref=4, with_ldg=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    assert m.bcs[0]["ghost_slot"].size >= 8
+    mixed_bcs(m, rng)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1)
+    assert_pde_parity(out, ref, dts)

@@ -191,6 +191,43 @@ def test_adapter_other_pdes_emu(oracle, host_emu, pde, resident):
     assert_pde_parity(out, ref, dts)
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_device_bcs_emu(oracle, host_emu, resident):
+    """hexed_b200::add_device_bc / apply_state_bcs / apply_flux_bcs: a viscous step with every device-side boundary condition and no
+    host boundary loop at all"""
+    from util import mixed_bcs
+    m, rng = soup(2, 3, 45, n_car=10, n_def=24, n_ref=2, with_ldg=True)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    assert m.bcs[0]["ghost_slot"].size >= 8
+    mixed_bcs(m, rng)
+    basis = hb.gauss_legendre(3)
+    ref, work = m.copy(), m.copy()
+    h = H.HostHarness(host_emu, m, basis, seed=9)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    visc_o, cond_o = pyoracle.sutherland(1.7e-5, 273., 110.), pyoracle.constant(2.5e-2)
+    visc_h, cond_h = H.sutherland(1.7e-5, 273., 110.), H.constant(2.5e-2)
+    dt = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, False, visc_o, cond_o)
+    dt_d = h.call("max_dt_navier_stokes", 0.3, 0.3, False, *visc_h, *cond_h)  # first call of the epoch: the mirror exists from here on
+    h.add_device_bcs(m)
+    oracle.apply_state_bcs(ref)
+    oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt, i_stage=0)
+    oracle.apply_state_bcs(ref)
+    oracle.compute_euler(basis, ref, dt=dt, i_stage=1)
+    h.apply_state_bcs()
+    h.set_flux_bc(h.apply_flux_bcs)
+    h.call("compute_navier_stokes", *visc_h, *cond_h, dt=dt, i_stage=0)
+    h.apply_state_bcs()
+    h.call("compute_euler", dt=dt, i_stage=1)
+    if resident:
+        h.to_host(H.ALL_ELEM | H.FACES)
+    h.fetch(work)
+    work.face_wide, ref.face_wide = None, None
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    assert_pde_parity(work, ref, [(dt_d, dt)])
+
+
 def test_adapter_standalone_entry_points_emu(oracle, host_emu):
     """write_face, prolong, restrict, stabilizing_art_visc through the reference signatures"""
     basis = hb.gauss_legendre(4)

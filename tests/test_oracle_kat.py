@@ -297,3 +297,65 @@ def test_freestream_and_conservation(oracle):
         oracle.apply_state_bcs(m)
         oracle.compute_euler(b, m, dt=1e-5, i_stage=stage)
     assert np.abs(m.state() - before).max() <= 1e-11*np.abs(before).max()
+
+
+# ---------------------------------------------------------------- test_Boundary_condition.cpp
+def _one_face_mesh(nd, rs, face_sign, normal):
+    """one deformed element with a boundary connection on face (dimension 0, `face_sign`), like Typed_bound_connection(element, 0, sign, 0)"""
+    m = M.FlatMesh(nd, rs, 0, 1, n_ghost=1, with_ldg=True)
+    inside, ghost = np.array([face_sign], np.int32), np.array([2*nd], np.int32)
+    m.normals[face_sign] = np.asarray(normal)[:, None]
+    m.def_con = np.array([[face_sign, 2*nd, 0, 0, face_sign, 1 - face_sign, face_sign]], np.int32)
+    return m, inside, ghost
+
+
+def test_bc_nonpenetration(oracle):
+    """test/test_Boundary_condition.cpp:150-192"""
+    rs = 8
+    m, ins, gh = _one_face_mesh(2, rs, 1, [-4., 3.])
+    state = np.array([1., 1., 1.2, 1e5/0.4 + 0.5*1.2*2.])
+    m.face_state[ins] = np.repeat(state, rs)
+    m.face_ldg[ins] = np.repeat(state, rs)
+    m.bcs = [dict(kind=M.BC_NONPENETRATION, inside_slot=ins, ghost_slot=gh, normal_slot=ins.copy(), con_index=np.array([0], np.int32), params=None)]
+    oracle.apply_state_bcs(m)
+    g = m.face_state[gh].reshape(4, rs)
+    assert np.allclose(3*g[0] + 4*g[1], 7.) and np.allclose(-4*g[0] + 3*g[1], 1.)
+    oracle.apply_flux_bcs(m)
+    g = m.face_ldg[gh].reshape(4, rs)
+    assert np.allclose(3*g[0] + 4*g[1], -7.) and np.allclose(-4*g[0] + 3*g[1], -1.)
+    assert np.allclose(g[2], -state[2]) and np.allclose(g[3], -state[3])
+
+
+@pytest.mark.parametrize("section", ["isothermal", "specified flux", "specified emissivity"])
+def test_bc_no_slip(oracle, section):
+    """test/test_Boundary_condition.cpp:194-276"""
+    rs = 8
+    m, ins, gh = _one_face_mesh(2, rs, 0, [.7/np.sqrt(2.)]*2)
+    state = np.array([1., 1., 1.2, 1e5/0.4 + 0.5*1.2*2.])
+    flux = np.array([10., -20., 1.3, 10.])
+    if section == "specified emissivity":
+        state[3] = 1e5/.4
+    m.face_state[ins] = np.repeat(state, rs)
+    m.face_ldg[ins] = np.repeat(flux, rs)
+    params = {"isothermal": M.no_slip_params(M.THERMAL_ENERGY, 1e6), "specified flux": M.no_slip_params(M.THERMAL_HEAT_FLUX, 3.),
+              "specified emissivity": M.no_slip_params(M.THERMAL_EQUILIBRIUM, .8, 0., 0.)}[section]
+    m.bcs = [dict(kind=M.BC_NO_SLIP, inside_slot=ins, ghost_slot=gh, normal_slot=ins.copy(), con_index=np.array([0], np.int32), params=params)]
+    oracle.apply_state_bcs(m)
+    g = m.face_state[gh].reshape(4, rs)
+    if section != "specified emissivity":
+        assert np.allclose(g[0], -1.) and np.allclose(g[1], -1.) and np.allclose(g[2], 1.2)
+    if section == "isothermal":
+        assert np.allclose(np.sqrt(g[3]*state[3]), 1e6*1.2)
+    elif section == "specified flux":
+        assert np.allclose(g[3], state[3])
+    oracle.apply_flux_bcs(m)
+    g = m.face_ldg[gh].reshape(4, rs)
+    if section == "isothermal":
+        assert np.allclose(g, np.array([10., -20., -1.3, 10.])[:, None])
+    elif section == "specified flux":
+        assert np.allclose(g[:3], np.array([10., -20., -1.3])[:, None])
+        assert np.allclose((g[3] + flux[3])/2, -3.*.7)
+    else:
+        temp = 1e5/1.2/287.05287
+        assert np.isclose(M.STEFAN_BOLTZMANN, 5.670374419e-8, rtol=1e-9)
+        assert np.allclose((g[3] + flux[3])/2, -.8*M.STEFAN_BOLTZMANN*temp**4*.7)

@@ -172,3 +172,20 @@ def check_cfl_cache(oracle, lib, rs, n):
     out = m.copy(); dev.sync_to_host(out)
     assert np.array_equal(out.tss(), np.ones_like(out.tss()))
     dev.close()
+
+
+def mixed_bcs(mesh, rng):
+    """replace the soup mesh's single boundary condition by one of every device-side kind over disjoint subsets of its faces"""
+    src = mesh.bcs[0]
+    n = src["ghost_slot"].size
+    nd = mesh.n_dim
+    kinds = [(M.BC_COPY, None), (M.BC_NONPENETRATION, None), (M.BC_FREESTREAM, freestream_state(nd)), (M.BC_OUTFLOW, None),
+             (M.BC_PRESSURE_OUTFLOW, np.array([0.9e5])), (M.BC_NO_SLIP, M.no_slip_params(M.THERMAL_ENERGY, 2.1e5)),
+             (M.BC_NO_SLIP, M.no_slip_params(M.THERMAL_HEAT_FLUX, 30.)), (M.BC_NO_SLIP, M.no_slip_params(M.THERMAL_EQUILIBRIUM, .8, 12., 280.))]
+    owner = np.arange(n) % len(kinds)
+    bcs = []
+    for k, (kind, params) in enumerate(kinds):
+        sel = np.nonzero(owner == k)[0]
+        bcs.append(dict(kind=kind, params=params, **{key: np.ascontiguousarray(src[key][sel]) for key in ("inside_slot", "ghost_slot", "normal_slot", "con_index")}))
+    mesh.bcs = bcs
+    return mesh
