@@ -193,14 +193,24 @@ def test_adapter_other_pdes_emu(oracle, host_emu, pde, resident):
 
 @pytest.mark.parametrize("resident", [False, True])
 def test_adapter_device_bcs_emu(oracle, host_emu, resident):
+    check_adapter_device_bcs(oracle, host_emu, resident, 2, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_device_bcs_gpu(oracle, host_gpu, resident):
+    check_adapter_device_bcs(oracle, host_gpu, resident, 3, 4)
+
+
+def check_adapter_device_bcs(oracle, host_emu, resident, nd, rs):
     """hexed_b200::add_device_bc / apply_state_bcs / apply_flux_bcs: a viscous step with every device-side boundary condition and no
     host boundary loop at all"""
     from util import mixed_bcs
-    m, rng = soup(2, 3, 45, n_car=10, n_def=24, n_ref=2, with_ldg=True)
+    m, rng = soup(nd, rs, 45, n_car=10, n_def=24, n_ref=2, with_ldg=True)
     prepare_pde_state(m, rng, NAVIER_STOKES)
     assert m.bcs[0]["ghost_slot"].size >= 8
     mixed_bcs(m, rng)
-    basis = hb.gauss_legendre(3)
+    basis = hb.gauss_legendre(rs)
     ref, work = m.copy(), m.copy()
     h = H.HostHarness(host_emu, m, basis, seed=9)
     h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
