@@ -584,3 +584,103 @@ def random_flow_state(mesh, rng, mach=0.3):
     f[:, nd + 1] = p/0.4 + 0.5*rho*(vel**2).sum(1)
     if mesh.face_ldg is not None:
         mesh.face_ldg[:] = rng.standard_normal(mesh.face_ldg.shape)
+
+
+# --------------------------------------------------------------------------------------
+# locally refined Cartesian box: real 2:1 hanging-node faces (the topology class of the adaptive BASELINE configs)
+# --------------------------------------------------------------------------------------
+
+def refined_box_mesh(n_dim, row_size, n, basis, refine, bc_kind=BC_NONPENETRATION, bc_params=None, with_ldg=False):
+    """`n^n_dim` Cartesian cells of size 1/n on the unit box; the cells with `refine[cell index tuple]` true are replaced by their
+    2^n_dim children. Faces between a cell and the children of a refined neighbour are hanging-node faces built the way the
+    reference's `Refined_connection<Element>` builds them (include/connection.hpp:195-262): the coarse element's face is the coarse
+    face of a `Refined_face`, each child meets its own mortar face through a Cartesian connection (mortar on the coarse element's
+    side: side 0 when the coarse element is below the face, side 1 -- "reversed" -- when it is above), children listed in row-major
+    order of the face's tangential dimensions. Boundary faces get ghost faces and deformed-type boundary connections as in
+    `box_mesh`. Adds `mesh.cell_volume` (per element) for conservation checks."""
+    nd, rs = n_dim, row_size
+    refine = np.asarray(refine, bool)
+    assert refine.shape == (n,)*nd
+    h = 1./n
+    elems = []      # (size level: 0 coarse / 1 fine, integer origin in units of its own size)
+    index_of = {}   # (level, tuple origin) -> element id
+    for cell in np.ndindex(*(n,)*nd):
+        if refine[cell]:
+            for child in np.ndindex(*(2,)*nd):
+                o = tuple(2*c + k for c, k in zip(cell, child))
+                index_of[(1, o)] = len(elems); elems.append((1, o))
+        else:
+            index_of[(0, cell)] = len(elems); elems.append((0, cell))
+    E = len(elems)
+    nf = 2*nd
+    car, refs, bc_rows = [], [], []
+    extra = 0  # mortar + ghost slots after the element faces
+
+    def slot(e, d, sign):
+        return e*nf + 2*d + sign
+
+    def tangential_children(d):
+        dims = [k for k in range(nd) if k != d]
+        return dims, list(np.ndindex(*(2,)*(nd - 1)))
+
+    for e, (lvl, o) in enumerate(elems):
+        size_cells = n*(2 if lvl else 1)  # number of cells of this level per dimension
+        for d in range(nd):
+            # neighbour across the positive face
+            if o[d] + 1 < size_cells:
+                nb = list(o); nb[d] += 1; nb = tuple(nb)
+                if (lvl, nb) in index_of:  # same level
+                    car.append([slot(e, d, 1), slot(index_of[(lvl, nb)], d, 0), d])
+                elif lvl == 0:  # coarse below, children of the refined neighbour above: not reversed, mortar faces are side 0
+                    dims, kids = tangential_children(d)
+                    fine = []
+                    for kid in kids:
+                        fo = [0]*nd
+                        fo[d] = 2*nb[d]
+                        for t, k in zip(dims, kid):
+                            fo[t] = 2*nb[t] + k
+                        fe = index_of[(1, tuple(fo))]
+                        mortar = E*nf + extra; extra += 1
+                        car.append([mortar, slot(fe, d, 0), d])
+                        fine.append(mortar)
+                    refs.append([slot(e, d, 1)] + fine + [-1]*(4 - len(fine)) + [0, 0])
+                else:  # fine below, coarse above: reversed, mortar faces are side 1; handled once per coarse face below
+                    pass
+            else:
+                bc_rows.append((e, d, 1))
+            if o[d] == 0:
+                bc_rows.append((e, d, 0))
+            elif lvl == 0:
+                # neighbour across the negative face of a coarse element: if it is refined, this coarse face is a reversed hanging face
+                nb = list(o); nb[d] -= 1; nb = tuple(nb)
+                if (0, nb) not in index_of:
+                    dims, kids = tangential_children(d)
+                    fine = []
+                    for kid in kids:
+                        fo = [0]*nd
+                        fo[d] = 2*nb[d] + 1
+                        for t, k in zip(dims, kid):
+                            fo[t] = 2*nb[t] + k
+                        fe = index_of[(1, tuple(fo))]
+                        mortar = E*nf + extra; extra += 1
+                        car.append([slot(fe, d, 1), mortar, d])
+                        fine.append(mortar)
+                    refs.append([slot(e, d, 0)] + fine + [-1]*(4 - len(fine)) + [0, 0])
+    n_bc = len(bc_rows)
+    mesh = FlatMesh(nd, rs, E, 0, n_ghost=extra + n_bc, n_extra_normal=n_bc, with_ldg=with_ldg)
+    size = np.array([h/2 if lvl else h for lvl, _ in elems])
+    mesh.nom_size[:] = size
+    mesh.vertex_tss[:] = (size/nd)[:, None]  # reference src/Element.cpp:17
+    mesh.cell_volume = size**nd
+    origin = np.array([o for _, o in elems])
+    mesh.qpoint_pos = qpoint_positions_cartesian(origin, size, basis, nd)
+    mesh.car_con = np.array(car, np.int32).reshape(-1, 3)
+    mesh.ref_face = np.array(refs, np.int32).reshape(-1, 7)
+    bc = np.zeros((n_bc, 7), np.int32)
+    for i, (e, d, sign) in enumerate(bc_rows):
+        bc[i] = [slot(e, d, sign), E*nf + extra + i, d, d, sign, 1 - sign, i]
+        mesh.normals[i, d, :] = 1.
+    mesh.def_con = bc
+    mesh.bcs.append(dict(kind=bc_kind, inside_slot=bc[:, 0].copy(), ghost_slot=bc[:, 1].copy(), normal_slot=bc[:, 6].copy(),
+                         con_index=np.arange(n_bc, dtype=np.int32), params=bc_params))
+    return mesh
