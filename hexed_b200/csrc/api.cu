@@ -719,12 +719,14 @@ int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, 
                          const double* params, int n_params, int* bc_id)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
-  if (kind < 0 || kind > HEXED_B200_BC_NO_SLIP) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary condition kind");
-  if (kind == HEXED_B200_BC_FREESTREAM && n_params != c->nv) return fail(c, HEXED_B200_BAD_ARGUMENT, "freestream needs n_dim + 2 parameters");
+  if (kind < 0 || kind > HEXED_B200_BC_RIEMANN_INVARIANTS) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary condition kind");
+  if ((kind == HEXED_B200_BC_FREESTREAM || kind == HEXED_B200_BC_RIEMANN_INVARIANTS) && n_params != c->nv)
+    return fail(c, HEXED_B200_BAD_ARGUMENT, "freestream needs n_dim + 2 parameters");
   if (kind == HEXED_B200_BC_PRESSURE_OUTFLOW && n_params != 1) return fail(c, HEXED_B200_BAD_ARGUMENT, "pressure outflow needs 1 parameter");
   if (kind == HEXED_B200_BC_NO_SLIP && n_params != 6) return fail(c, HEXED_B200_BAD_ARGUMENT, "no-slip needs 6 parameters");
-  const bool needs_normal = kind == HEXED_B200_BC_NONPENETRATION || kind == HEXED_B200_BC_PRESSURE_OUTFLOW || kind == HEXED_B200_BC_NO_SLIP;
-  const bool needs_sign = kind == HEXED_B200_BC_PRESSURE_OUTFLOW || kind == HEXED_B200_BC_NO_SLIP; // inside_face_sign is read off the slot number
+  const bool needs_normal = kind == HEXED_B200_BC_NONPENETRATION || kind == HEXED_B200_BC_PRESSURE_OUTFLOW || kind == HEXED_B200_BC_NO_SLIP
+                            || kind == HEXED_B200_BC_RIEMANN_INVARIANTS;
+  const bool needs_sign = kind == HEXED_B200_BC_PRESSURE_OUTFLOW || kind == HEXED_B200_BC_NO_SLIP || kind == HEXED_B200_BC_RIEMANN_INVARIANTS; // inside_face_sign is read off the slot number
   for (int i = 0; i < n; ++i) {
     if (ghost[i] < 0 || ghost[i] >= c->n_face_slot || inside[i] < 0 || inside[i] >= c->n_face_slot) return fail(c, HEXED_B200_BAD_ARGUMENT, "face slot out of range");
     if (needs_normal && (normal[i] < 0 || normal[i] >= c->n_normal_slot)) return fail(c, HEXED_B200_BAD_ARGUMENT, "normal slot out of range");
@@ -736,7 +738,7 @@ int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, 
   if (!rc) rc = dev_alloc(c, &b.ghost, n, false);
   if (!rc) rc = dev_alloc(c, &b.normal, n, true);
   if (!rc) rc = dev_alloc(c, &b.params, n_params, false);
-  if (!rc && kind == HEXED_B200_BC_NO_SLIP) rc = dev_alloc(c, &b.cache, (size_t)n*c->nv*c->nfq, true);
+  if (!rc && (kind == HEXED_B200_BC_NO_SLIP || kind == HEXED_B200_BC_RIEMANN_INVARIANTS)) rc = dev_alloc(c, &b.cache, (size_t)n*c->nv*c->nfq, true);
   if (rc) return rc;
   if (n) {
     HB_CUDA(c, cudaMemcpyAsync(b.inside, inside, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream));

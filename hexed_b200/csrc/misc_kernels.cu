@@ -1,5 +1,6 @@
 /* misc_kernels.cu -- CFL time step, hanging-node transfer, boundary ghost fill, face gather/scatter. */
 #include "euler.cuh"
+#include "characteristics.cuh"
 
 namespace hb {
 
@@ -279,6 +280,44 @@ int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale) { return 
 
 /* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */
 constexpr double specific_gas_air_c = 287.05287; // include/constants.hpp:44
+
+/* Riemann_invariants for one face point (src/Boundary_condition.cpp:97-182): `in`/`gh`/`sc`/`nr` point at this point's first
+ * variable (stride nfq). sign = velocity sign of incoming characteristics = 1 - 2*inside_face_sign. */
+template <int ND>
+__device__ void riemann_state_point(const double* in, double* gh, double* sc, const double* nr, const double* fs, int sign, int nfq)
+{
+  constexpr int NV = ND + 2;
+  double inside[NV], outside[NV], n[ND], st[NV];
+  #pragma unroll
+  for (int v = 0; v < NV; ++v) { inside[v] = in[v*nfq]; outside[v] = fs[v]; }
+  #pragma unroll
+  for (int d = 0; d < ND; ++d) n[d] = nr[d*nfq];
+  apply_char<ND>(inside, n, sign, inside, outside, st); // incoming characteristics from the freestream, outgoing left alone
+  // limit the ghost state to keep it thermodynamically admissible (:125-128)
+  st[ND] = fmax(st[ND], inside[ND]/2);
+  double gsq = 0., isq = 0.;
+  #pragma unroll
+  for (int d = 0; d < ND; ++d) { gsq += st[d]*st[d]; isq += inside[d]*inside[d]; }
+  const double kin_ener = .5*gsq/st[ND];
+  const double inside_kin_ener = .5*isq/inside[ND];
+  st[ND + 1] = fmax(kin_ener + fmax(st[ND + 1] - kin_ener, (inside[ND + 1] - inside_kin_ener)/2), 0.);
+  #pragma unroll
+  for (int v = 0; v < NV; ++v) { gh[v*nfq] = st[v]; sc[v*nfq] = inside[v]; } // state cache primed with the inside state (:134-138)
+}
+
+template <int ND>
+__device__ void riemann_flux_point(const double* in, double* gh, const double* sc, const double* nr, int sign, int nfq)
+{
+  constexpr int NV = ND + 2;
+  double flux[NV], zero[NV], cache[NV], n[ND], st[NV];
+  #pragma unroll
+  for (int v = 0; v < NV; ++v) { flux[v] = in[v*nfq]; cache[v] = sc[v*nfq]; zero[v] = 0.; }
+  #pragma unroll
+  for (int d = 0; d < ND; ++d) n[d] = nr[d*nfq];
+  apply_char<ND>(cache, n, sign, zero, flux, st); // outgoing characteristic flux zero, incoming left alone (:165-173)
+  #pragma unroll
+  for (int v = 0; v < NV; ++v) gh[v*nfq] = st[v];
+}
 __global__ void __launch_bounds__(256)
 bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params, double* cache,
           double* faces, double* faces_ldg, const double* normals, int nd, int nfq)
@@ -310,6 +349,14 @@ bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* norma
     return;
   }
   const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  if (kind == HEXED_B200_BC_RIEMANN_INVARIANTS) { // Riemann_invariants::apply_state :97-139
+    const int sign = 1 - 2*((inside[i] % (2*nd)) % 2);
+    double* sc = cache + (size_t)i*w + q;
+    if (nd == 3) riemann_state_point<3>(in, gh, sc, nr, params, sign, nfq);
+    else if (nd == 2) riemann_state_point<2>(in, gh, sc, nr, params, sign, nfq);
+    else riemann_state_point<1>(in, gh, sc, nr, params, sign, nfq);
+    return;
+  }
   if (kind == HEXED_B200_BC_PRESSURE_OUTFLOW) { // Pressure_outflow::apply_state :184-211
     const int sign = 2*((inside[i] % (2*nd)) % 2) - 1;
     const double mass = in[nd*nfq];
@@ -369,6 +416,14 @@ flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* 
     return;
   }
   const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+  if (kind == HEXED_B200_BC_RIEMANN_INVARIANTS) { // Riemann_invariants::apply_flux :141-182
+    const int sign = 1 - 2*((inside[i] % (2*nd)) % 2);
+    const double* sc = cache + (size_t)i*w + q;
+    if (nd == 3) riemann_flux_point<3>(in, gh, sc, nr, sign, nfq);
+    else if (nd == 2) riemann_flux_point<2>(in, gh, sc, nr, sign, nfq);
+    else riemann_flux_point<1>(in, gh, sc, nr, sign, nfq);
+    return;
+  }
   if (kind == HEXED_B200_BC_NO_SLIP) { // No_slip::apply_flux :387-418
     for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq];
     gh[nd*nfq] = -in[nd*nfq];

@@ -60,7 +60,7 @@ void synchronize(hexed::Kernel_mesh);
 
 /*! \brief device-resident boundary conditions: removes the per-stage PCIe round trip of the boundary faces.
  * \details `kind` / `params` as in `hexed_b200_bc_create` (include/hexed_b200.h: Freestream, Copy, Nonpenetration, Outflow,
- * Pressure_outflow, No_slip); `inside_faces[i]` = `Boundary_connection::inside_face(false)` of the i-th face the condition applies to
+ * Pressure_outflow, No_slip, Riemann_invariants); `inside_faces[i]` = `Boundary_connection::inside_face(false)` of the i-th face the condition applies to
  * (= `Kernel_connection::state(0, false)` of its boundary connection). Registrations belong to the current mesh epoch.
  * `apply_state_bcs` / `apply_flux_bcs` then stand in for the loops of `Solver::apply_state_bcs` / `apply_flux_bcs`
  * (src/Solver.cpp:56-81) for the registered faces. */

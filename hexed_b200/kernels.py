@@ -13,7 +13,8 @@ import os
 
 import numpy as np
 
-from .mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, n_slot
+from .mesh import (BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, BC_RIEMANN_INVARIANTS,
+                   n_slot)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhexed_b200.so")
@@ -216,7 +217,7 @@ class Device:
 
     def add_bc(self, bc):
         kind = bc["kind"]
-        if kind not in (BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP):
+        if kind not in (BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, BC_RIEMANN_INVARIANTS):
             return None  # host-applied boundary condition
         ins, gh, nr = _i32(bc["inside_slot"]), _i32(bc["ghost_slot"]), _i32(bc["normal_slot"])
         params = np.ascontiguousarray(bc["params"], dtype=np.float64) if bc.get("params") is not None else np.zeros(0)

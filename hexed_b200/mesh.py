@@ -19,7 +19,7 @@ from .tables import Connection_direction
 
 N_FORCING = 4  # reference include/Storage_params.hpp:21
 
-BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP = 0, 1, 2, 3, 4, 5  # include/hexed_b200.h
+BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, BC_RIEMANN_INVARIANTS = 0, 1, 2, 3, 4, 5, 6  # include/hexed_b200.h
 BC_HOST = 99  # applied by the host (anything the device does not implement)
 THERMAL_HEAT_FLUX, THERMAL_ENERGY, THERMAL_EQUILIBRIUM = 0, 1, 2  # Prescribed_heat_flux / Prescribed_energy / Thermal_equilibrium
 

@@ -73,7 +73,8 @@ enum {
 };
 
 enum { HEXED_B200_BC_FREESTREAM = 0, HEXED_B200_BC_COPY = 1, HEXED_B200_BC_NONPENETRATION = 2,
-       HEXED_B200_BC_OUTFLOW = 3, HEXED_B200_BC_PRESSURE_OUTFLOW = 4, HEXED_B200_BC_NO_SLIP = 5 };
+       HEXED_B200_BC_OUTFLOW = 3, HEXED_B200_BC_PRESSURE_OUTFLOW = 4, HEXED_B200_BC_NO_SLIP = 5,
+       HEXED_B200_BC_RIEMANN_INVARIANTS = 6 };
 
 typedef struct {
   int n_car, n_def;
@@ -194,7 +195,9 @@ int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options
 /* Freestream src/Boundary_condition.cpp:66-76 (params = nv doubles), Copy :450-453, Nonpenetration :301-327, Outflow :465-477,
  * Pressure_outflow :184-223 (params = {specified pressure}), No_slip :367-418 (params = {thermal kind, a, b, c, heat flux coercion,
  * stefan_boltzmann}: kind 0 Prescribed_heat_flux(a), 1 Prescribed_energy(a), 2 Thermal_equilibrium(emissivity a, heat transfer
- * coefficient b, temperature c), include/Boundary_condition.hpp:140-200; its state cache lives on the device) */
+ * coefficient b, temperature c), include/Boundary_condition.hpp:140-200; its state cache lives on the device),
+ * Riemann_invariants :97-182 (params = nv doubles of freestream state; characteristic decomposition include/pde.hpp:181-256 with the
+ * 3x3 column-pivoted Householder QR done per face point in registers; state cache on the device) */
 int hexed_b200_bc_create(hexed_b200_ctx* ctx, int kind, int n, const int* inside_slot, const int* ghost_slot,
                          const int* normal_slot, const double* params, int n_params, int* bc_id);
 int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);

@@ -112,6 +112,10 @@ int ho_derivative(const ho_basis*, int n_var, const double* qpoint_vals, const d
 int ho_bc_freestream(ho_mesh*, int n_bc, const int* ghost_slot, const double* freestream);
 int ho_bc_copy(ho_mesh*, int n_bc, const int* inside_slot, const int* ghost_slot);
 int ho_bc_nonpenetration(ho_mesh*, int n_bc, const int* inside_slot, const int* ghost_slot, const int* normal_slot);
+/* Riemann_invariants (src/Boundary_condition.cpp:97-182) and the Characteristics decomposition it uses (include/pde.hpp:181-256) */
+int ho_characteristics(int n_dim, const double* state, const double* direction, const double* state1, double* eigvals, double* decomp);
+int ho_bc_riemann_state(ho_mesh*, int n_bc, const int* inside_slot, const int* ghost_slot, const int* normal_slot, const double* freestream, double* cache);
+int ho_bc_riemann_flux(ho_mesh*, int n_bc, const int* inside_slot, const int* ghost_slot, const int* normal_slot, const double* cache);
 int ho_num_threads(void);
 
 #ifdef __cplusplus

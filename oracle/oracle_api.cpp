@@ -3,6 +3,7 @@
  * ones are routed to the ho_part_<nd>_<pde> translation units. */
 #include "oracle_impl.hpp"
 #include "oracle_call.h"
+#include "characteristics.hpp"
 #include <type_traits>
 
 namespace {
@@ -190,6 +191,71 @@ int ho_bc_nonpenetration(ho_mesh* m, int n_bc, const int* inside_slot, const int
       double dot = 0., nsq = 0.;
       for (int d = 0; d < nd; ++d) { dot += gh[d*nfq + q]*n[d*nfq + q]; nsq += n[d*nfq + q]*n[d*nfq + q]; }
       for (int d = 0; d < nd; ++d) gh[d*nfq + q] -= 2*dot*n[d*nfq + q]/nsq;
+    }
+  }
+  return 0;
+}
+
+/* Characteristics (reference include/pde.hpp:181-256): eigvals[3], decomp[(nd+2)][3] of `state1` about `state` along `direction` */
+int ho_characteristics(int nd, const double* state, const double* direction, const double* state1, double* eigvals, double* decomp)
+{
+  auto run = [&](auto ndc) {
+    constexpr int ND = decltype(ndc)::value;
+    Characteristics<ND> ch(state, direction);
+    double d[ND + 2][3];
+    ch.decomp(state1, d);
+    for (int j = 0; j < 3; ++j) eigvals[j] = ch.vals[j];
+    for (int v = 0; v < ND + 2; ++v) for (int j = 0; j < 3; ++j) decomp[v*3 + j] = d[v][j];
+  };
+  if (nd == 1) run(std::integral_constant<int, 1>{});
+  else if (nd == 2) run(std::integral_constant<int, 2>{});
+  else if (nd == 3) run(std::integral_constant<int, 3>{});
+  else return 1;
+  return 0;
+}
+
+/* Riemann_invariants::apply_state (reference src/Boundary_condition.cpp:97-139); `cache` [n_bc][nv*nfq] receives the inside state */
+int ho_bc_riemann_state(ho_mesh* m, int n_bc, const int* inside_slot, const int* ghost_slot, const int* normal_slot, const double* fs, double* cache)
+{
+  const int nd = m->n_dim, nfq = ipow(m->row_size, nd - 1), nv = nd + 2, w = nv*nfq;
+  if (nd < 1 || nd > 3) return 1;
+  for (int i = 0; i < n_bc; ++i) {
+    double* gh = m->face_state + (size_t)ghost_slot[i]*w;
+    const double* in = m->face_state + (size_t)inside_slot[i]*w;
+    const double* n = m->normals + (size_t)normal_slot[i]*nd*nfq;
+    const int sign = 1 - 2*((inside_slot[i] % (2*nd)) % 2);
+    for (int q = 0; q < nfq; ++q) {
+      double inside[5], nrml[3], ghost[5];
+      for (int v = 0; v < nv; ++v) inside[v] = in[v*nfq + q];
+      for (int d = 0; d < nd; ++d) nrml[d] = n[d*nfq + q];
+      if (nd == 1) riemann_state_point<1>(inside, nrml, sign, fs, ghost);
+      else if (nd == 2) riemann_state_point<2>(inside, nrml, sign, fs, ghost);
+      else riemann_state_point<3>(inside, nrml, sign, fs, ghost);
+      for (int v = 0; v < nv; ++v) gh[v*nfq + q] = ghost[v];
+    }
+    for (int k = 0; k < w; ++k) cache[(size_t)i*w + k] = in[k];
+  }
+  return 0;
+}
+
+/* Riemann_invariants::apply_flux (reference src/Boundary_condition.cpp:141-182) on the LDG halves of the faces */
+int ho_bc_riemann_flux(ho_mesh* m, int n_bc, const int* inside_slot, const int* ghost_slot, const int* normal_slot, const double* cache)
+{
+  const int nd = m->n_dim, nfq = ipow(m->row_size, nd - 1), nv = nd + 2, w = nv*nfq;
+  if (nd < 1 || nd > 3 || !m->face_ldg) return 1;
+  for (int i = 0; i < n_bc; ++i) {
+    double* gh = m->face_ldg + (size_t)ghost_slot[i]*w;
+    const double* in = m->face_ldg + (size_t)inside_slot[i]*w;
+    const double* n = m->normals + (size_t)normal_slot[i]*nd*nfq;
+    const int sign = 1 - 2*((inside_slot[i] % (2*nd)) % 2);
+    for (int q = 0; q < nfq; ++q) {
+      double flux[5], sc[5], nrml[3], ghost[5];
+      for (int v = 0; v < nv; ++v) { flux[v] = in[v*nfq + q]; sc[v] = cache[(size_t)i*w + v*nfq + q]; }
+      for (int d = 0; d < nd; ++d) nrml[d] = n[d*nfq + q];
+      if (nd == 1) riemann_flux_point<1>(sc, nrml, sign, flux, ghost);
+      else if (nd == 2) riemann_flux_point<2>(sc, nrml, sign, flux, ghost);
+      else riemann_flux_point<3>(sc, nrml, sign, flux, ghost);
+      for (int v = 0; v < nv; ++v) gh[v*nfq + q] = ghost[v];
     }
   }
   return 0;

@@ -119,6 +119,9 @@ class Oracle:
         L.ho_bc_freestream.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, dp]
         L.ho_bc_copy.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip]
         L.ho_bc_nonpenetration.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip, ip]
+        L.ho_characteristics.argtypes = [C.c_int, dp, dp, dp, dp, dp]
+        L.ho_bc_riemann_state.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip, ip, dp, dp]
+        L.ho_bc_riemann_flux.argtypes = [C.POINTER(ho_mesh), C.c_int, ip, ip, ip, dp]
 
     @staticmethod
     def _check(rc):
@@ -209,11 +212,21 @@ class Oracle:
         self._check(self.lib.ho_derivative(pack_basis(basis), q.shape[0], _ptr(q, dp), _ptr(bv, dp), _ptr(out, dp)))
         return out
 
+    def characteristics(self, state, direction, state1):
+        """(eigvals[3], decomp[nv][3]) of reference include/pde.hpp:181-256 Characteristics(state, direction).decomp(state1)"""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        direction = np.ascontiguousarray(direction, dtype=np.float64)
+        state1 = np.ascontiguousarray(state1, dtype=np.float64)
+        nd = direction.size
+        vals = np.zeros(3); dec = np.zeros((nd + 2, 3))
+        self._check(self.lib.ho_characteristics(nd, _ptr(state, dp), _ptr(direction, dp), _ptr(state1, dp), _ptr(vals, dp), _ptr(dec, dp)))
+        return vals, dec
+
     def apply_state_bcs(self, m):
         """ghost-state fill for the device-capable boundary conditions (reference src/Solver.cpp:56-67). Freestream, Copy and
         Nonpenetration run in the C oracle; Outflow, Pressure_outflow and No_slip are numpy restatements of
         src/Boundary_condition.cpp:184-211,367-385,465-468 (operation order kept; small meshes only)."""
-        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, BC_RIEMANN_INVARIANTS
         pm = self.pack_mesh(m)
         nd, nfq, nv = m.n_dim, m.nfq, m.n_dim + 2
         for bc in m.bcs:
@@ -228,6 +241,11 @@ class Oracle:
                 self.lib.ho_bc_copy(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip))
             elif bc["kind"] == BC_NONPENETRATION:
                 self.lib.ho_bc_nonpenetration(pm, n, _ptr(bc["inside_slot"], ip), _ptr(bc["ghost_slot"], ip), _ptr(bc["normal_slot"], ip))
+            elif bc["kind"] == BC_RIEMANN_INVARIANTS:  # C oracle, oracle/characteristics.hpp
+                fs = np.ascontiguousarray(bc["params"], dtype=np.float64)
+                bc["cache"] = np.zeros((n, nv*nfq))
+                self._check(self.lib.ho_bc_riemann_state(pm, n, _ptr(ins, ip), _ptr(gh, ip), _ptr(bc["normal_slot"], ip), _ptr(fs, dp),
+                                                         _ptr(bc["cache"], dp)))
             elif bc["kind"] == BC_OUTFLOW:  # copy_state: both halves
                 m.face_state[gh] = m.face_state[ins]
                 if m.face_ldg is not None:
@@ -261,7 +279,7 @@ class Oracle:
         (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341), Outflow / Pressure_outflow
         (:213-221,470-477), No_slip (:387-418) with its three Thermal_bc kinds (include/Boundary_condition.hpp:140-186);
         numpy, small meshes only"""
-        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP
+        from hexed_b200.mesh import BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRESSURE_OUTFLOW, BC_NO_SLIP, BC_RIEMANN_INVARIANTS
         nd, nfq = m.n_dim, m.nfq
         for bc in m.bcs:
             ins, gh = bc["inside_slot"], bc["ghost_slot"]
@@ -277,6 +295,9 @@ class Oracle:
                 nsq = (n*n).sum(1)
                 g[:, :nd] -= 2*dot[:, None, :]*n/nsq[:, None, :]
                 m.face_ldg[gh] = g.reshape(len(gh), -1)
+            elif bc["kind"] == BC_RIEMANN_INVARIANTS:
+                self._check(self.lib.ho_bc_riemann_flux(self.pack_mesh(m), ins.size, _ptr(ins, ip), _ptr(gh, ip), _ptr(bc["normal_slot"], ip),
+                                                        _ptr(bc["cache"], dp)))
             elif bc["kind"] in (BC_OUTFLOW, BC_PRESSURE_OUTFLOW):
                 m.face_ldg[gh] = -m.face_ldg[ins]
             elif bc["kind"] == BC_NO_SLIP:

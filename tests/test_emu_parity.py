@@ -118,3 +118,9 @@ def test_every_device_boundary_condition(oracle, emu_lib, nd, rs):
     assert n_bc_faces >= 8, n_bc_faces
     out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2)
     assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
+def test_riemann_invariants_bc(oracle, emu_lib, nd, rs):
+    from util import check_riemann_bc
+    check_riemann_bc(oracle, emu_lib, nd, rs)

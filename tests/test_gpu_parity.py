@@ -232,3 +232,12 @@ def test_every_device_boundary_condition(oracle, gpu_lib, nd, rs):
     mixed_bcs(m, rng)
     out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1)
     assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nd,rs", [(1, 6), (2, 6), (3, 6), (3, 3)])
+def test_riemann_invariants_bc(oracle, gpu_lib, nd, rs):
+    """Riemann_invariants (the `characteristic` condition of every sample case) state + flux against the oracle's restatement of
+    Characteristics / ColPivHouseholderQR, over sub/supersonic in/outflow and singular (zero-pressure) points"""
+    from util import check_riemann_bc
+    check_riemann_bc(oracle, gpu_lib, nd, rs)

@@ -359,3 +359,77 @@ def test_bc_no_slip(oracle, section):
         temp = 1e5/1.2/287.05287
         assert np.isclose(M.STEFAN_BOLTZMANN, 5.670374419e-8, rtol=1e-9)
         assert np.allclose((g[3] + flux[3])/2, -.8*M.STEFAN_BOLTZMANN*temp**4*.7)
+
+
+# ---------------------------------------------------------------- test_Characteristics.cpp / Riemann_invariants
+def _euler_flux(state, normal):
+    nd = normal.size
+    veloc = state[:nd]/state[nd]
+    pres = .4*(state[nd + 1] - .5*state[:nd] @ veloc)
+    vn = veloc @ normal
+    return np.concatenate([state[:nd]*vn + pres*normal, [state[nd]*vn, (state[nd + 1] + pres)*vn]])
+
+
+def test_characteristics(oracle):
+    """test/test_Characteristics.cpp:4-42: the decomposition sums to the input state and its columns are eigenvectors of the
+    linearised flux with the reported eigenvalues"""
+    mass, veloc, pres = 1.225, np.array([10., 4., 12.]), 101325.
+    state = np.concatenate([mass*veloc, [mass, pres/.4 + .5*mass*veloc @ veloc]])
+    normal = np.array([1., 1., 1.])
+    state1 = np.array([1., 2., 3., 1.3, 2e5])
+    vals, dec = oracle.characteristics(state, normal, state1)
+    assert np.linalg.norm((dec.sum(1) - state1)/state1) < 1e-10  # reference: Catch::Approx(0).scale(1.), i.e. 1.2e-5
+    sound = np.sqrt(1.4*pres/mass)
+    vn = veloc @ normal/np.sqrt(3.)
+    assert np.allclose(vals, [vn - sound, vn + sound, vn], rtol=1e-14)
+    diff = 1e-6
+    for i in range(3):
+        perturb = (_euler_flux(state + diff*dec[:, i], normal) - _euler_flux(state, normal))/np.sqrt(3.)
+        assert np.linalg.norm(perturb/(diff*vals[i]*dec[:, i]) - 1.) < 1e-4  # Catch::Approx(0.).scale(1.): 1.2e-4
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+def test_characteristics_dims(oracle, nd):
+    """same two properties in every dimensionality, random states (against numpy's eigen-decomposition of the flux Jacobian)"""
+    rng = np.random.default_rng(7 + nd)
+    for _ in range(20):
+        veloc = rng.normal(0., 200., nd)
+        mass, pres = rng.uniform(.5, 2.), rng.uniform(5e4, 2e5)
+        state = np.concatenate([mass*veloc, [mass, pres/.4 + .5*mass*veloc @ veloc]])
+        normal = rng.normal(0., 1., nd)
+        state1 = state*(1. + .3*rng.uniform(-1., 1., nd + 2))
+        vals, dec = oracle.characteristics(state, normal, state1)
+        assert np.allclose(dec.sum(1), state1, rtol=1e-11, atol=1e-9*np.abs(state1).max())
+        unit = normal/np.linalg.norm(normal)
+        h = 1e-6
+        jac = np.stack([(_euler_flux(state + h*np.abs(state[k])*e, unit) - _euler_flux(state - h*np.abs(state[k])*e, unit))/(2*h*np.abs(state[k]))
+                        for k, e in enumerate(np.eye(nd + 2))], axis=1)
+        for i in range(3):
+            scale = np.linalg.norm(dec[:, i])*np.abs(vals).max() + 1e-300
+            assert np.linalg.norm(jac @ dec[:, i] - vals[i]*dec[:, i])/scale < 1e-6
+
+
+def test_bc_riemann_invariants(oracle):
+    """test/test_Boundary_condition.cpp:75-117 "supersonic inflow": first point supersonic outflow (ghost = inside), the rest
+    supersonic inflow (ghost = freestream); the flux is left alone where the state was set and zero elsewhere"""
+    rs = 8
+    nfq = rs*rs
+    m = M.FlatMesh(3, rs, 1, 0, n_ghost=1, n_extra_normal=1, with_ldg=True)
+    ins, gh = np.array([2], np.int32), np.array([6], np.int32)  # face (dimension 1, negative side)
+    fs = np.array([10., 30., -20., 1.3, 4e5])
+    inside_state = np.array([1/1.2, -600/1.2, 1/1.2, 1.2, 101325/.4 + .5*1.2*360002])
+    f = np.repeat(inside_state, nfq).reshape(5, nfq)
+    f[1, 1:] *= -1
+    m.face_state[ins] = f.reshape(1, -1)
+    m.normals[0] = np.repeat(np.array([0., 1., 0.]), nfq).reshape(3, nfq)
+    m.bcs = [dict(kind=M.BC_RIEMANN_INVARIANTS, inside_slot=ins, ghost_slot=gh, normal_slot=np.array([0], np.int32),
+                  con_index=np.array([0], np.int32), params=fs)]
+    oracle.apply_state_bcs(m)
+    g = m.face_state[gh].reshape(5, nfq)
+    assert np.allclose(g[:, 0], inside_state, rtol=1e-10)
+    assert np.allclose(g[:, 1:], fs[:, None], rtol=1e-10)
+    assert np.array_equal(m.bcs[0]["cache"], m.face_state[ins])
+    m.face_ldg[ins] = 1.
+    oracle.apply_flux_bcs(m)
+    g = m.face_ldg[gh].reshape(5, nfq)
+    assert np.allclose(g[:, 0], 0., atol=1e-10) and np.allclose(g[:, 1:], 1., atol=1e-10)
