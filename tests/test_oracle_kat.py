@@ -14,7 +14,8 @@ import hexed_b200 as hb
 from hexed_b200 import mesh as M
 from hexed_b200.basis import Basis
 from hexed_b200.tables import Connection_direction, vertex_inds
-from pyoracle import EULER
+import pyoracle
+from pyoracle import EULER, NAVIER_STOKES
 
 APPROX = 1.2e-5  # Catch::Approx default epsilon (100 * float epsilon)
 
@@ -433,3 +434,39 @@ def test_bc_riemann_invariants(oracle):
     oracle.apply_flux_bcs(m)
     g = m.face_ldg[gh].reshape(5, nfq)
     assert np.allclose(g[:, 0], 0., atol=1e-10) and np.allclose(g[:, 1:], 1., atol=1e-10)
+
+
+# ---------------------------------------------------------------- test_Solver.cpp "Solver viscosity"
+@pytest.mark.parametrize("nd,rs,deformed", [(2, 8, False), (2, 8, True), (3, 6, True), (1, 8, False), (3, 8, False)])
+def test_viscous_momentum_decay(oracle, nd, rs, deformed):
+    """test/test_Solver.cpp:588-615 (`test_visc`, run by "Solver viscosity" :676-708): constant density and pressure with the
+    divergence-free sinusoidal velocity of `Sinusoid_veloc0` (:57-75) and constant viscosity 3; the momentum residual of one
+    `compute_navier_stokes` in residual mode must be -n_dim*3*momentum/1.2 (pure viscous decay) to the reference's own margin
+    (1.2e-3 for row size > 6, 1.2 otherwise). This is the reference's only pin on the LDG path: Neighbor's LDG average, the gradient
+    and compute_flux_diff in Local, Neighbor_reconcile and Reconcile_ldg_flux all have to be right for it to hold."""
+    if nd == 1 and deformed:
+        pytest.skip("no deformed 1-D elements")
+    b = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 3, b, deformed=deformed, bc_kind=M.BC_COPY, with_ldg=True, warp_amplitude=0.05)
+    x = np.asarray(m.qpoint_pos)  # [n_elem, nd, nq]
+    cos_part = np.cos(x.sum(1))
+    st = m.state()
+    for d in range(nd):
+        st[:, d] = 1.2*cos_part
+    st[:, 0] *= 1 - nd
+    st[:, nd] = 1.2
+    st[:, nd + 1] = 1e5/.4 + .5*1.2*(nd - 1 + (1 - nd)**2)*cos_part**2
+    oracle.compute_write_face(b, m)
+    visc, cond = pyoracle.constant(3.), pyoracle.inviscid()
+    oracle.max_dt(NAVIER_STOKES, b, m, 1e-4, 1e-4, False, visc, cond)  # global time step: tss = 1
+    before = m.state().copy()
+    oracle.apply_state_bcs(m)
+    oracle.compute_navier_stokes(b, m, lambda: oracle.apply_flux_bcs(m), visc, cond, dt=1., i_stage=0, compute_residual=True)
+    assert np.array_equal(m.state(), before)  # residual mode leaves the state alone
+    c = M.cache_slot(nd, rs)
+    resid = m.elem_data[:, c:c + nd + 2]
+    margin = 1.2*(1e-3 if rs > 6 else 1.)
+    assert np.abs(resid[:, :nd] - (-nd*3.*before[:, :nd]/1.2)).max() <= margin
+    if nd > 1:
+        assert np.abs(resid[:, :nd]).max() > 3.  # the decay rate is not trivially inside the margin
+    assert np.abs(resid[:, nd]).max() <= margin  # rate of change of mass is 0
