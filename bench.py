@@ -326,7 +326,7 @@ def main():
     local_sec = local_stat["device_seconds"]/max(local_stat["launches"], 1)
     local_gbs = ne*alg["local"]*8/local_sec/1e9
     shares = {("%s/%s" % (("car", "def", "shared")[s["deformed"]], s["name"])): s["device_seconds"]/n_prof for s in stats if s["launches"]}
-    local_name = ("local_euler_pipe_kernel<6,%s>" if nd == 3 else "local_euler_kernel<2,6,%s>") % ("true" if deformed else "false")
+    local_name = ("local_euler_pipe_kernel<6,%s>" if nd == 3 else "local_euler_pipe2d_kernel<6,%s>") % ("true" if deformed else "false")
     if viscous:
         local_name += " + ns_local_line_kernel (both count as 'local'; see kernel_seconds_per_step)"
     traffic = ncu_traffic(local_name, ne) if not viscous else None

@@ -134,6 +134,7 @@ inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->s
 int launch_neighbor_euler(hexed_b200_ctx* c, int deformed, int first = 0, int count = -1);
 int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o);
 int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end);
+int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end);
 int launch_write_face(hexed_b200_ctx* c);
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
 int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index = nullptr, int n_index = 0);

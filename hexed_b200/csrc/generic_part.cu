@@ -672,6 +672,110 @@ ns_local_line_kernel(GArgs a, Ops ops)
   }
 }
 
+/* ---------------- Navier-Stokes Reconcile_ldg_flux, 3-D, bulk-copy staging ----------------
+ * Same arithmetic as g_reconcile_kernel<3, RS, PdeNs<3, RS, true>, DEF> without the modal filter and outside residual mode
+ * (reference include/Spatial.hpp:543-594). The kernel is a pure stream (38 KB in+out per element at row size 6 against ~60 flops
+ * per point); the generic version reached 2.85 TB/s because each CTA walks load -> barrier -> load -> store -> barrier -> store with
+ * per-thread global loads (profiles/r01g_ncu_full_ns.md: long-scoreboard 19.7 cycles per issue). Here the element's state, LDG
+ * faces, time-step scale and determinant arrive as four 1-D bulk TMA copies on one mbarrier and ~9 one-shot CTAs per SM keep
+ * enough bytes in flight; the new state is written from registers, the faces from the updated shared-memory copy. */
+template <int RS, bool DEF>
+struct NsRecCfg
+{
+  static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5;
+  static constexpr int threads = ((nq + 31)/32)*32 > 256 ? 256 : ((nq + 31)/32)*32;
+  static constexpr int s_state = 0, s_ldg = s_state + nv*nq, s_tss = s_ldg + 2*ND*nv*nfq, s_det = s_tss + nq;
+  static constexpr int smem_doubles = s_det + (DEF ? nq : 0);
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 2*sizeof(mbar_t);
+};
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(NsRecCfg<RS, DEF>::threads)
+ns_reconcile_bulk_kernel(GArgs a, Ops ops)
+{
+  using C = NsRecCfg<RS, DEF>;
+  constexpr int ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads;
+  HB_DYN_SMEM(double, smem);
+  double* S = smem + C::s_state;
+  const double* fldg = smem + C::s_ldg;
+  const double* s_tss = smem + C::s_tss;
+  const double* s_det = smem + C::s_det;
+  mbar_t* bar = reinterpret_cast<mbar_t*>(smem + C::smem_doubles);
+  const int t = threadIdx.x;
+  const int e = a.elem_begin + blockIdx.x;
+  if (e >= a.elem_end) return;
+  if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncthreads();
+  if (t == 0) {
+    constexpr unsigned b_field = sizeof(double)*nq, b_face = sizeof(double)*2*ND*nv*nfq;
+    mbar_arrive_expect_tx(bar, nv*b_field + b_face + b_field + (DEF ? b_field : 0u));
+    bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
+    bulk_g2s(S, a.ed.state + (size_t)e*nv*nq, nv*b_field, bar);
+    bulk_g2s(smem + C::s_tss, a.ed.tss + (size_t)e*nq, b_field, bar);
+    if constexpr (DEF) bulk_g2s(smem + C::s_det, a.det + (size_t)(e - a.n_car)*nq, b_field, bar);
+  }
+  const double nom = a.nom[e];
+  mbar_wait(bar, 0);
+  for (int q = t; q < nq; q += T) {
+    double r[nv];
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) r[v] = 0.;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+      const int node = (q/stride) % RS;
+      const int fq = (q/(stride*RS))*stride + q % stride;
+      const double l0 = ops.lift[node][0], l1 = ops.lift[node][1];
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double acc = 0;
+        acc += l0*fldg[((2*d)*nv + v)*nfq + fq];
+        acc += l1*fldg[((2*d + 1)*nv + v)*nfq + fq];
+        r[v] -= acc;
+      }
+    }
+    double mult = a.update*s_tss[q]/nom;
+    if constexpr (DEF) mult /= s_det[q];
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      const double u = S[v*nq + q] + r[v]*mult;
+      S[v*nq + q] = u;
+      a.ed.state[((size_t)e*nv + v)*nq + q] = u;
+    }
+  }
+  __syncthreads();
+  double* dst = a.faces + (size_t)e*2*ND*wl;
+  for (int item = t; item < ND*nv*nfq; item += T) {
+    const int d = item/(nv*nfq), v = (item/nfq) % nv, fq = item % nfq;
+    const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+    const int base = (fq/stride)*stride*RS + fq % stride;
+    double e0 = 0, e1 = 0;
+    #pragma unroll
+    for (int k = 0; k < RS; ++k) {
+      const double x = S[v*nq + base + k*stride];
+      e0 += ops.bnd[0][k]*x;
+      e1 += ops.bnd[1][k]*x;
+    }
+    dst[(size_t)(2*d)*wl + v*nfq + fq] = e0;
+    dst[(size_t)(2*d + 1)*wl + v*nfq + fq] = e1;
+  }
+}
+
+/* returns -1 when the combination is not covered and the caller should use g_reconcile_kernel */
+template <int ND, int RS>
+int launch_ns_reconcile_bulk(hexed_b200_ctx* c, const GArgs& a, int deformed)
+{
+  if constexpr (ND == 3 && (RS == 2 || RS == 4 || RS == 6)) { // bulk copies need 16-byte multiples: nq*8 with even row size
+    if (a.use_filter || a.compute_residual || !c->use_pipe) return -1;
+    const int grid = a.elem_end - a.elem_begin;
+    if (deformed) { using C = NsRecCfg<RS, true>; auto k = ns_reconcile_bulk_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    else { using C = NsRecCfg<RS, false>; auto k = ns_reconcile_bulk_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    return 0;
+  } else {
+    return -1;
+  }
+}
+
 /* returns -1 when the combination is not covered and the caller should use g_local_kernel */
 template <int ND, int RS>
 int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
@@ -932,6 +1036,13 @@ int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdePara
       if constexpr (P::has_diffusion) {
         if (a.compute_residual && HB_PDE == PDE_SMOOTH_AV)
           return fail(c, HEXED_B200_NOT_IMPLEMENTED, "residual-only LDG reconciliation is undefined for Smooth_art_visc (the reference indexes past the residual cache)");
+#if HB_PDE == 1 /* PDE_NAVIER_STOKES */
+        {
+          const int r = launch_ns_reconcile_bulk<ND, RS>(c, a, deformed);
+          if (r > 0) return r;
+          if (r == 0) { count_launch(c, deformed ? ST_RECONCILE_DEF : ST_RECONCILE_CAR); HB_CUDA(c, cudaGetLastError()); return 0; }
+        }
+#endif
         if (deformed) { auto k = g_reconcile_kernel<ND, RS, P, true>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
         else { auto k = g_reconcile_kernel<ND, RS, P, false>; int r = set_smem(c, k, smem); if (r) return r; HB_LAUNCH(k, grid, C::threads, smem, c->stream, a, c->ops, c->filt); }
       } else return fail(c, HEXED_B200_BAD_ARGUMENT, "Reconcile_ldg_flux needs a diffusive PDE");

@@ -235,7 +235,8 @@ int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o)
   StatScope scope(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR, end - begin);
   if (end == begin) return 0;
   {
-    const int rc = launch_local_euler_pipe(c, deformed, o, begin, end);
+    int rc = launch_local_euler_pipe(c, deformed, o, begin, end);
+    if (rc == -1) rc = launch_local_euler_pipe2d(c, deformed, o, begin, end);
     if (rc == 0) count_launch(c, deformed ? ST_LOCAL_DEF : ST_LOCAL_CAR);
     if (rc >= 0) return rc;
   }

@@ -1,0 +1,253 @@
+/* local_euler_pipe2d.cu -- persistent, TMA-pipelined Euler `Local` kernel for 2-D elements (the vortex / naca0012 / cylinder
+ * configurations of BASELINE.json are 2-D, row size 6).
+ *
+ * Same arithmetic as local_euler.cu (reference include/Spatial.hpp:326-509 + the trailing write_face :41-57,507) and the same
+ * organisation as the 3-D kernel of local_euler_pipe.cu, with one difference forced by the element size: a 2-D element is only
+ * row_size^2 points (36 at row size 6, 1.1 KB of state), so the unit of work of a persistent CTA is a BATCH of B consecutive
+ * elements. Because the layout is element-major, the state / numerical-flux faces / reference normals / time-step scale /
+ * determinant of a batch are each ONE contiguous run: a batch is fetched with a handful of 1-D bulk TMA copies
+ * (cp.async.bulk -> UBLKCP) onto mbarriers, double buffered two batches ahead (late inputs one phase ahead), exactly like one
+ * 3-D element. The point-per-thread kernel it replaces reached 47 % (Cartesian) / 62 % (deformed) of the measured HBM bandwidth
+ * (profiles/r01g_bench_lines.jsonl): 144-thread CTAs with per-thread global loads between barriers.
+ *
+ * Phases per batch: A (line tasks (element, dimension, line): pointwise flux on the line, derivative + lifted face flux -> R_d),
+ * B (point tasks: r = R_0 + R_1, two-stage update, new state -> HBM and in place in shared memory),
+ * C (line tasks: extrapolate the new state to both ends of the line -> HBM).
+ */
+#include "euler.cuh"
+
+namespace hb {
+
+template <int RS, bool DEF>
+struct Pipe2Cfg
+{
+  static constexpr int ND = 2, nq = RS*RS, nfq = RS, nv = 4;
+  static constexpr int lines_per_elem = ND*nfq;
+  static constexpr int B = 128/lines_per_elem;            // elements per batch: 10 at row size 6
+  static constexpr int n_line = B*lines_per_elem;
+  static constexpr int threads = ((n_line + 31)/32)*32;
+  static constexpr int cs = nv > RS ? nv : RS;            // slots per element of the residual cache array
+  // per-element doubles of each staged array
+  static constexpr int e_state = nv*nq, e_face = 2*ND*nv*nfq, e_nrml = DEF ? ND*ND*nq : 0;
+  static constexpr int st_state = 0, st_face = B*e_state, st_nrml = st_face + B*e_face;
+  static constexpr int stage_doubles = st_nrml + B*e_nrml;
+  static constexpr int lt_cache = 0, lt_tss = B*e_state, lt_det = lt_tss + B*nq;
+  static constexpr int late_doubles = lt_det + (DEF ? B*nq : 0);
+  static constexpr int r_doubles = B*ND*nv*nq;
+  static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t);
+};
+
+struct Pipe2Args
+{
+  double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
+  int elem_begin, elem_end, n_car;
+  double update; int stage; int compute_residual;
+};
+
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe2_issue_stage(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+{
+  using C = Pipe2Cfg<RS, DEF>;
+  const unsigned b_state = sizeof(double)*C::e_state*n, b_face = sizeof(double)*C::e_face*n, b_nrml = sizeof(double)*C::e_nrml*n;
+  mbar_arrive_expect_tx(bar, b_state + b_face + b_nrml);
+  bulk_g2s(buf + C::st_state, a.state + (size_t)e0*C::e_state, b_state, bar);
+  bulk_g2s(buf + C::st_face, a.faces + (size_t)e0*C::e_face, b_face, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::st_nrml, a.refn + (size_t)(e0 - a.n_car)*C::e_nrml, b_nrml, bar);
+}
+
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe2_issue_late(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+{
+  using C = Pipe2Cfg<RS, DEF>;
+  const unsigned b_cache = sizeof(double)*C::e_state, b_pt = sizeof(double)*C::nq*n;
+  mbar_arrive_expect_tx(bar, (a.stage ? b_cache*n : 0u) + b_pt + (DEF ? b_pt : 0u));
+  // the residual cache array keeps max(nv, row_size) slots per element, of which Euler uses the first nv: one copy per element
+  if (a.stage) for (int i = 0; i < n; ++i) bulk_g2s(buf + C::lt_cache + i*C::e_state, a.cache + (size_t)(e0 + i)*C::cs*C::nq, b_cache, bar);
+  bulk_g2s(buf + C::lt_tss, a.tss + (size_t)e0*C::nq, b_pt, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e0 - a.n_car)*C::nq, b_pt, bar);
+}
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(Pipe2Cfg<RS, DEF>::threads)
+local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
+{
+  using C = Pipe2Cfg<RS, DEF>;
+  constexpr int ND = 2, nq = C::nq, nfq = C::nfq, nv = C::nv, B = C::B;
+  HB_DYN_SMEM(double, smem);
+  double* late = smem + 2*C::stage_doubles;
+  double* R = late + C::late_doubles;
+  mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
+  const int t = threadIdx.x;
+  const int stride_e = gridDim.x*B;
+  int e0 = a.elem_begin + blockIdx.x*B;
+  if (e0 >= a.elem_end) return;
+  auto count = [&](int first) { const int n = a.elem_end - first; return n < B ? n : B; };
+
+  if (t == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (t == 0) {
+    pipe2_issue_stage<RS, DEF>(a, e0, count(e0), smem, &bars[0]);
+    if (e0 + stride_e < a.elem_end) pipe2_issue_stage<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), smem + C::stage_doubles, &bars[1]);
+    pipe2_issue_late<RS, DEF>(a, e0, count(e0), late, &bars[2]);
+  }
+
+  // line task of this thread: element le of the batch, dimension d, line l; points q0 + k*stride
+  const int le = t/C::lines_per_elem, d = (t % C::lines_per_elem)/nfq, l = t % nfq;
+  const int stride = d == 0 ? RS : 1;
+  const int q0 = d == 0 ? l : l*RS;
+
+  for (int it = 0; e0 < a.elem_end; ++it, e0 += stride_e) {
+    const int s = it & 1;
+    const unsigned par = (it >> 1) & 1;
+    const int n = count(e0);
+    const bool has_line = t < C::n_line && le < n;
+    double* const stage_buf = smem + s*C::stage_doubles;
+    double* S = stage_buf + C::st_state;
+    const double* F = stage_buf + C::st_face;
+    const double* N = stage_buf + C::st_nrml;
+    mbar_wait(&bars[s], par);
+
+    /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
+    if (has_line) {
+      const double* Se = S + le*C::e_state;
+      double f[nv][RS];
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) {
+        EulerPoint<ND> p;
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) p.s[v] = Se[v*nq + q0 + k*stride];
+        p.scalars();
+        double fl[nv];
+        if constexpr (DEF) {
+          double nr[ND];
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) nr[j] = N[le*C::e_nrml + (d*ND + j)*nq + q0 + k*stride];
+          p.flux(nr, fl);
+        } else {
+          const double mass_flux = d == 0 ? p.s[0] : p.s[1];
+          const double vol_flux = mass_flux*p.inv_mass;
+          fl[ND] = mass_flux;
+          fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+        }
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
+      }
+      const double* Fe = F + le*C::e_face;
+      double* Re = R + le*ND*nv*nq;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        const double b0 = Fe[((2*d)*nv + v)*nfq + l], b1 = Fe[((2*d + 1)*nv + v)*nfq + l];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          Re[(d*nv + v)*nq + q0 + i*stride] = -acc;
+        }
+      }
+    }
+    __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
+
+    /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
+    mbar_wait(&bars[2], it & 1);
+    for (int pt = t; pt < n*nq; pt += C::threads) {
+      const int pe = pt/nq, q = pt % nq;
+      const int e = e0 + pe;
+      double mult; // update*tss/nom/det with one division (<= 1 ulp)
+      if constexpr (DEF) mult = a.update*late[C::lt_tss + pt]/(a.nom[e]*late[C::lt_det + pt]);
+      else mult = a.update*late[C::lt_tss + pt]/a.nom[e];
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double u = R[pe*ND*nv*nq + (0*nv + v)*nq + q];
+        u += R[pe*ND*nv*nq + (1*nv + v)*nq + q];
+        double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+        if (a.stage) u -= late[C::lt_cache + pe*C::e_state + v*nq + q];
+        else if (!a.compute_residual) *cache = u;
+        u *= mult;
+        if (a.compute_residual) *cache = u;
+        else {
+          const double xv = S[pe*C::e_state + v*nq + q] + u;
+          S[pe*C::e_state + v*nq + q] = xv;
+          a.state[(size_t)e*C::e_state + v*nq + q] = xv;
+        }
+      }
+    }
+    __syncthreads(); // new state complete in S; late buffer free
+    if (t == 0 && e0 + stride_e < a.elem_end) {
+      fence_proxy_async();
+      pipe2_issue_late<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), late, &bars[2]);
+    }
+
+    /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
+    if (has_line) {
+      const double* Se = S + le*C::e_state;
+      double* fout = a.faces + (size_t)(e0 + le)*C::e_face;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double x0 = 0, x1 = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) {
+          const double x = Se[v*nq + q0 + k*stride];
+          x0 += ops.bnd[0][k]*x;
+          x1 += ops.bnd[1][k]*x;
+        }
+        fout[((2*d)*nv + v)*nfq + l] = x0;
+        fout[((2*d + 1)*nv + v)*nfq + l] = x1;
+      }
+    }
+    __syncthreads(); // stage buffer s free
+    if (t == 0 && e0 + 2*stride_e < a.elem_end) {
+      fence_proxy_async();
+      pipe2_issue_stage<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), stage_buf, &bars[s]);
+    }
+  }
+}
+
+template <int RS, bool DEF>
+static int launch_pipe2(hexed_b200_ctx* c, const Pipe2Args& a)
+{
+  using C = Pipe2Cfg<RS, DEF>;
+  auto k = local_euler_pipe2d_kernel<RS, DEF>;
+  static int blocks_per_sm = 0; // per instantiation
+  if (!blocks_per_sm) {
+    HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
+    int n = 0;
+    HB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::threads, C::smem_bytes));
+    if (n < 1) return fail(c, HEXED_B200_CUDA_ERROR, "pipelined 2-D local kernel does not fit on this device");
+    blocks_per_sm = n;
+  }
+  int sms = 0;
+  HB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const int n_batch = (a.elem_end - a.elem_begin + C::B - 1)/C::B;
+  int grid = sms*blocks_per_sm;
+  if (grid > n_batch) grid = n_batch;
+  HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops);
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+/* returns -1 if this (n_dim, row_size, options) combination is not covered and the caller should use the general kernel.
+ * Bulk copies need 16-byte multiples: row_size^2*8 bytes per field -> even row sizes. */
+int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end)
+{
+  if (c->nd != 2 || (c->rs != 4 && c->rs != 6 && c->rs != 8) || o.use_filter || !c->use_pipe) return -1;
+  Pipe2Args a;
+  a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
+  a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
+  a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
+  a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
+  c->cfl_valid[deformed ? 1 : 0] = false;
+  if (c->rs == 6) return deformed ? launch_pipe2<6, true>(c, a) : launch_pipe2<6, false>(c, a);
+  if (c->rs == 4) return deformed ? launch_pipe2<4, true>(c, a) : launch_pipe2<4, false>(c, a);
+  return deformed ? launch_pipe2<8, true>(c, a) : launch_pipe2<8, false>(c, a);
+}
+
+} // namespace hb

@@ -124,3 +124,16 @@ def test_every_device_boundary_condition(oracle, emu_lib, nd, rs):
 def test_riemann_invariants_bc(oracle, emu_lib, nd, rs):
     from util import check_riemann_bc
     check_riemann_bc(oracle, emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("rs,n", [(6, 11), (4, 9), (8, 5)])
+@pytest.mark.parametrize("deformed", [False, True])
+def test_box_2d_pipelined_local(oracle, emu_lib, deformed, rs, n):
+    """local_euler_pipe2d.cu: batches of elements per persistent CTA; sizes chosen so that a CTA iterates several times (both
+    stage buffers reused) and the last batch is partial"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(2, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(2))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2)
+    assert_euler_parity(out, ref, dts)

@@ -34,7 +34,8 @@ def test_soup_options(oracle, gpu_lib, local_time, use_filter):
     assert_euler_parity(out, ref, dts)
 
 
-@pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 16, False), (2, 6, 8, True), (3, 6, 5, False), (3, 6, 5, True), (3, 4, 6, True)])
+@pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 16, False), (2, 6, 8, True), (3, 6, 5, False), (3, 6, 5, True), (3, 4, 6, True),
+                                              (2, 6, 101, False), (2, 6, 101, True), (2, 4, 150, True), (2, 8, 70, False)])
 def test_box(oracle, gpu_lib, nd, rs, n, deformed):
     """BASELINE configs at oracle-friendly sizes: 2-D vortex-like Cartesian box (16x16, row size 6) and the 3-D row-size-6 box"""
     basis = hb.gauss_legendre(rs)
