@@ -40,6 +40,7 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
   dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
   dev_free(c->cfl_approx); invalidate_cfl_cache(c); c->tss_is_one = false;
+  dev_free(c->record);
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
   for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
   c->lists.clear();
@@ -154,8 +155,8 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j)
     c->ops.dfull[i][j] = diff[i][j] - (c->ops.lift[i][0]*bnd[0][j] + c->ops.lift[i][1]*bnd[1][j]);
   static const char* names[ST_COUNT] = {"neighbor", "neighbor", "local", "local", "compute time step", "compute time step",
-                                        "prolong/restrict", "boundary conditions", "write face", "reconcile LDG flux", "reconcile LDG flux"};
-  static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2, 0, 1};
+                                        "prolong/restrict", "boundary conditions", "write face", "reconcile LDG flux", "reconcile LDG flux", "check admis."};
+  static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2, 0, 1, 2};
   for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].name = names[i]; c->stats[i].deformed = trees[i]; }
   int rc = check(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
@@ -186,6 +187,8 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   free_mesh(c);
   dev_free(c->perm); dev_free(c->d_scalar); dev_free(c->d_face_scratch);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->d_flags) cudaFree(c->d_flags);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -680,6 +683,22 @@ int hexed_b200_compute_prolong_advection(hexed_b200_ctx* c)
 int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* c, double char_speed) { return launch_stab_art_visc(c, char_speed); }
 
 int hexed_b200_apply_flux_bcs(hexed_b200_ctx* c) { return launch_flux_bcs(c); }
+
+int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
+{
+  if (!admissible) return fail(c, HEXED_B200_BAD_ARGUMENT, "null result pointer");
+  return launch_is_admissible(c, admissible);
+}
+
+int hexed_b200_download_record(hexed_b200_ctx* c, int* dst, int first_elem, int n_elem)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (first_elem < 0 || n_elem < 0 || first_elem + n_elem > c->n_elem) return fail(c, HEXED_B200_BAD_ARGUMENT, "element range out of bounds");
+  if (!c->record) return fail(c, HEXED_B200_BAD_ARGUMENT, "no record yet: call hexed_b200_is_admissible first");
+  HB_CUDA(c, cudaMemcpyAsync(dst, c->record + first_elem, sizeof(int)*n_elem, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
 
 /* individual kernels of a generic PDE, for unit-level parity: which = 0 Neighbor, 1 Local, 2 Neighbor_reconcile, 3 Reconcile_ldg_flux */
 int hexed_b200_pde_kernel(hexed_b200_ctx* c, int pde, int which, int deformed, hexed_b200_options o,

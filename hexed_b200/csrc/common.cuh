@@ -36,7 +36,7 @@ struct Stat
   const char* name; int deformed; long long work_units = 0; long long launches = 0; double seconds = 0;
 };
 enum { ST_NEIGHBOR_CAR, ST_NEIGHBOR_DEF, ST_LOCAL_CAR, ST_LOCAL_DEF, ST_MAX_DT_CAR, ST_MAX_DT_DEF, ST_PR, ST_BC, ST_WRITE_FACE,
-       ST_RECONCILE_CAR, ST_RECONCILE_DEF, ST_COUNT };
+       ST_RECONCILE_CAR, ST_RECONCILE_DEF, ST_ADMIS, ST_COUNT };
 
 /* scalar parameters of every PDE, passed by value to the generic kernels (pde.cuh) */
 struct PdeParams
@@ -95,6 +95,8 @@ struct hexed_b200_ctx
   float* cfl_approx = nullptr;
   bool cfl_valid[2] = {false, false};
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
+  int* record = nullptr;  // Element::record as left by is_admissible: 1 = thermodynamically inadmissible element
+  int* d_flags = nullptr; int* h_flags = nullptr; // {inadmissible, non-finite} found by the last is_admissible
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   std::string err;
@@ -155,6 +157,7 @@ struct GenericOps
 extern const GenericOps generic_ops_pde1, generic_ops_pde2, generic_ops_pde3, generic_ops_pde4;
 int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
+int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
 
 /* run-time (n_dim, row_size) -> compile-time dispatch; the analogue of the reference's kernel_factory
  * (include/kernel_factory.hpp:64-119). F is a generic lambda taking two integral_constants. */

@@ -278,6 +278,66 @@ static int launch_transfer(hexed_b200_ctx* c, int kind, int n_var, int scale, co
 int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index, int n_index) { return launch_transfer<true>(c, kind, n_var, scale, ref_index, n_index); }
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale) { return launch_transfer<false>(c, kind, n_var, scale); }
 
+/* ---------------- thermodynamic admissibility: Solver::is_admissible (reference src/Solver.cpp:921-958, src/thermo.cpp:6-18) ----------
+ * Runs after EVERY stage of Solver::update when fix_admis is on, over the whole state and every face: left on the host it would pull
+ * the full state across PCIe each stage. One warp per element scans the element's state and its 2*n_dim faces (mass > 0 and energy > 0
+ * at every point; every variable finite, the reference's HEXED_ASSERT), writes Element::record (1 = inadmissible) and ORs two global
+ * flags; the warps after the last element scan the fine mortar faces of the refined faces (:946-954), which set the flag but no record. */
+__global__ void __launch_bounds__(256)
+admissible_kernel(const double* state, const double* faces, const int* ref_face, int n_elem, int n_ref, int nd, int nq, int nfq, int* record, int* flags)
+{
+  const int warp = (int)(((long long)blockIdx.x*blockDim.x + threadIdx.x)/32), lane = threadIdx.x % 32;
+  const bool in_range = warp < n_elem + n_ref; // no early return: the warp votes below want every lane
+  const int nv = nd + 2;
+  bool inadmissible = false, nonfinite = false;
+  auto scan = [&](const double* data, int n_point) {
+    for (int i = lane; i < nv*n_point; i += 32) {
+      const double x = data[i];
+      if (!isfinite(x)) nonfinite = true;
+      if (i >= nd*n_point && !(x > 0.)) inadmissible = true;
+    }
+  };
+  if (!in_range) {}
+  else if (warp < n_elem) {
+    scan(state + (size_t)warp*nv*nq, nq);
+    for (int f = 0; f < 2*nd; ++f) scan(faces + ((size_t)warp*2*nd + f)*nv*nfq, nfq);
+  }
+  else {
+    const int* rf = ref_face + (size_t)(warp - n_elem)*8;
+    int n_fine = 1 << (nd - 1);
+    for (int i = 0; i < nd - 1; ++i) n_fine /= 1 + rf[5 + i];
+    for (int i = 0; i < n_fine; ++i) scan(faces + (size_t)rf[1 + i]*nv*nfq, nfq);
+  }
+  inadmissible = __any_sync(0xffffffffu, inadmissible);
+  nonfinite = __any_sync(0xffffffffu, nonfinite);
+  if (lane == 0 && in_range) {
+    if (warp < n_elem) record[warp] = inadmissible ? 1 : 0;
+    if (inadmissible) atomicOr(&flags[0], 1);
+    if (nonfinite) atomicOr(&flags[1], 1);
+  }
+}
+
+int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->record) { HB_CUDA(c, cudaMalloc(&c->record, sizeof(int)*(c->n_elem ? c->n_elem : 1))); }
+  if (!c->d_flags) { HB_CUDA(c, cudaMalloc(&c->d_flags, 2*sizeof(int))); HB_CUDA(c, cudaMallocHost(&c->h_flags, 2*sizeof(int))); }
+  StatScope scope(c, ST_ADMIS, c->n_elem);
+  HB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2*sizeof(int), c->stream));
+  const long long warps = (long long)c->n_elem + c->n_ref;
+  if (warps) {
+    HB_LAUNCH(admissible_kernel, (int)((warps*32 + 255)/256), 256, 0, c->stream, c->state, c->face_state, c->ref_face, c->n_elem, c->n_ref,
+              c->nd, c->nq, c->nfq, c->record, c->d_flags);
+    count_launch(c, ST_ADMIS);
+    HB_CUDA(c, cudaGetLastError());
+  }
+  HB_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 2*sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_flags[1]) return fail(c, HEXED_B200_NOT_FINITE, "state is not finite");
+  *admissible = c->h_flags[0] ? 0 : 1;
+  return 0;
+}
+
 /* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */
 constexpr double specific_gas_air_c = 287.05287; // include/constants.hpp:44
 

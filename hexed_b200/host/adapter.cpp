@@ -127,6 +127,7 @@ void check(Mirror* m, int rc)
 {
   if (!rc) return;
   if (rc == HEXED_B200_INVALID_KERNEL) throw std::runtime_error("demand for invalid kernel"); // include/kernel_factory.hpp:114-116
+  if (rc == HEXED_B200_NOT_FINITE) throw std::runtime_error("state is not finite"); // HEXED_ASSERT of src/thermo.cpp:14
   throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_last_error(m ? m->ctx : nullptr));
 }
 
@@ -587,6 +588,19 @@ void apply_state_bcs(Kernel_mesh km)
   check(&call.m, hexed_b200_apply_state_bcs(call.m.ctx));
   call.m.device_bcs_ran = true;
   call.finish();
+}
+
+bool is_admissible(Kernel_mesh km, std::vector<int>* record)
+{ // Solver::is_admissible, src/Solver.cpp:921-958
+  Call call(km, state | faces, 0);
+  int ok = 0;
+  check(&call.m, hexed_b200_is_admissible(call.m.ctx, &ok));
+  if (record) {
+    record->resize(call.m.tab.elem.size());
+    check(&call.m, hexed_b200_download_record(call.m.ctx, record->data(), 0, int(record->size())));
+  }
+  call.finish();
+  return ok != 0;
 }
 
 void apply_flux_bcs(Kernel_mesh km)

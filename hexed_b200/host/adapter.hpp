@@ -68,6 +68,12 @@ int add_device_bc(hexed::Kernel_mesh, int kind, const std::vector<double*>& insi
 void apply_state_bcs(hexed::Kernel_mesh);
 void apply_flux_bcs(hexed::Kernel_mesh);
 
+/*! \brief `Solver::is_admissible` (src/Solver.cpp:921-958) on the device: the check Solver::update makes after every
+ * stage. Returns what the reference returns; `record`, if given, receives `Element::record` of every element in `Kernel_mesh::elems` order
+ * (1 = inadmissible), which `fix_admissibility` spreads to the vertices. Throws `std::runtime_error("state is not finite")` like the
+ * reference's HEXED_ASSERT. One 8-byte read-back instead of a pass over the whole state on the host. */
+bool is_admissible(hexed::Kernel_mesh, std::vector<int>* record = nullptr);
+
 /*! \brief the pointer graph of a Kernel_mesh turned into slot tables (layout: include/hexed_b200.h). Device-free. */
 struct Flat_tables
 {

@@ -330,6 +330,21 @@ int hbh_apply_bcs(void* handle, int flux)
   }
 }
 
+/* hexed_b200::is_admissible: *ok = result, record[n_elem] in Kernel_mesh::elems order */
+int hbh_is_admissible(void* handle, int* ok, int* record)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    std::vector<int> rec;
+    *ok = hexed_b200::is_admissible(h->mesh(), &rec) ? 1 : 0;
+    for (size_t i = 0; i < rec.size(); ++i) record[i] = rec[i];
+    return 0;
+  } catch (const std::exception& ex) {
+    h->error = ex.what();
+    return 1;
+  }
+}
+
 /* the adapter's flattening (device-free), translated back to the harness's slot numbering through the host pointers so the test
  * can compare it entry by entry with the tables the mesh was built from. counts[6] = n_car, n_def, n_face_slot, n_normal_slot,
  * n_boundary, n_null_normal */

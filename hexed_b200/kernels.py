@@ -91,6 +91,8 @@ SIGNATURES = {
     "hexed_b200_stabilizing_art_visc": [C.c_void_p, C.c_double],
     "hexed_b200_pde_kernel": [C.c_void_p, C.c_int, C.c_int, C.c_int, Options, Transport, Transport, C.c_double, C.c_double],
     "hexed_b200_apply_flux_bcs": [C.c_void_p],
+    "hexed_b200_is_admissible": [C.c_void_p, ip],
+    "hexed_b200_download_record": [C.c_void_p, ip, C.c_int, C.c_int],
     "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
     "hexed_b200_local_euler": [C.c_void_p, C.c_int, Options],
     "hexed_b200_bc_create": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, dp, C.c_int, ip],
@@ -398,6 +400,20 @@ class Device:
 
     def apply_flux_bcs(self):
         self._check(self.lib.hexed_b200_apply_flux_bcs(self.ctx))
+
+    def is_admissible(self):
+        """Solver::is_admissible (reference src/Solver.cpp:921-958); raises RuntimeError("state is not finite") like the reference's
+        HEXED_ASSERT (src/thermo.cpp:14)"""
+        out = C.c_int(-1)
+        self._check(self.lib.hexed_b200_is_admissible(self.ctx, C.byref(out)))
+        return bool(out.value)
+
+    def record(self):
+        """Element::record of every element as left by the last is_admissible (1 = inadmissible)"""
+        n = self.mesh.n_elem
+        out = np.zeros(n, np.int32)
+        self._check(self.lib.hexed_b200_download_record(self.ctx, out.ctypes.data_as(ip), 0, n))
+        return out
 
     def neighbor_euler(self, deformed):
         self._check(self.lib.hexed_b200_neighbor_euler(self.ctx, int(deformed)))

@@ -56,7 +56,8 @@ enum {
   HEXED_B200_CUDA_ERROR = 3,
   HEXED_B200_BAD_ARGUMENT = 4,
   HEXED_B200_NO_MESH = 5,
-  HEXED_B200_NOT_IMPLEMENTED = 6
+  HEXED_B200_NOT_IMPLEMENTED = 6,
+  HEXED_B200_NOT_FINITE = 7      /* a state value is NaN/Inf: the reference's HEXED_ASSERT("state is not finite"), src/thermo.cpp:14 */
 };
 
 /* element arrays addressable by hexed_b200_upload / hexed_b200_download (item = one element unless noted) */
@@ -204,6 +205,14 @@ int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
 /* Solver::apply_flux_bcs (src/Solver.cpp:69-81) for the same boundary conditions: Freestream/Copy::apply_flux = copy_state
  * (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341). The flux cache copy of :75-76 is host-side. */
 int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
+
+/* ---- thermodynamic admissibility: Solver::is_admissible (src/Solver.cpp:921-958, src/thermo.cpp:6-18), which
+ * Solver::update runs after EVERY stage through fix_admissibility (:864-868). *admissible = 1 iff mass > 0 and energy > 0 at every
+ * point of every element's state, of its 2*n_dim faces and of the fine mortar faces of every refined face; the per-element result
+ * (Element::record, 1 = inadmissible) stays on the device for hexed_b200_download_record. One 8-byte read-back per call.
+ * Returns HEXED_B200_NOT_FINITE where the reference throws "state is not finite". ---- */
+int hexed_b200_is_admissible(hexed_b200_ctx* ctx, int* admissible);
+int hexed_b200_download_record(hexed_b200_ctx* ctx, int* dst, int first_elem, int n_elem);
 
 /* ---- domain decomposition (new in this implementation: the reference is single-process) ----
  * A rank's mesh is self-contained: faces of remote elements are HALO face slots (ordinary slots >= 2*n_dim*n_elem). The host

@@ -222,6 +222,25 @@ class Oracle:
         self._check(self.lib.ho_characteristics(nd, _ptr(state, dp), _ptr(direction, dp), _ptr(state1, dp), _ptr(vals, dp), _ptr(dec, dp)))
         return vals, dec
 
+    def is_admissible(self, m):
+        """Solver::is_admissible (reference src/Solver.cpp:921-958) with thermo::admissible (src/thermo.cpp:6-18): returns
+        (admissible, record[n_elem]); raises RuntimeError("state is not finite") where the reference's HEXED_ASSERT fires. numpy."""
+        nd, nq, nfq, nv = m.n_dim, m.nq, m.nfq, m.n_dim + 2
+        st = m.state()
+        faces = m.face_state[:2*nd*m.n_elem].reshape(m.n_elem, 2*nd, nv, nfq)
+        fine = []
+        for row in np.asarray(m.ref_face).reshape(-1, 7):
+            n_fine = 2**(nd - 1)
+            for i in range(nd - 1):
+                n_fine //= 1 + int(row[5 + i])
+            fine += [int(s) for s in row[1:1 + n_fine]]
+        fine_faces = m.face_state[fine].reshape(len(fine), nv, nfq)
+        if not (np.isfinite(st).all() and np.isfinite(faces).all() and np.isfinite(fine_faces).all()):
+            raise RuntimeError("state is not finite")
+        ok_elem = (st[:, nd:] > 0.).all(axis=(1, 2)) & (faces[:, :, nd:] > 0.).all(axis=(1, 2, 3))
+        ok_fine = bool((fine_faces[:, nd:] > 0.).all())
+        return bool(ok_elem.all() and ok_fine), (~ok_elem).astype(np.int32)
+
     def apply_state_bcs(self, m):
         """ghost-state fill for the device-capable boundary conditions (reference src/Solver.cpp:56-67). Freestream, Copy and
         Nonpenetration run in the C oracle; Outflow, Pressure_outflow and No_slip are numpy restatements of

@@ -90,6 +90,31 @@ template <class T> T __shfl_xor_sync(unsigned, T v, int mask) { return hb_emu_ex
 template <class T> T __shfl_down_sync(unsigned, T v, int delta) { return hb_emu_exchange(v, (int)(hb_emu_tid() % 32) + delta); }
 template <class T> T __shfl_sync(unsigned, T v, int lane) { return hb_emu_exchange(v, lane); }
 
+inline int __any_sync(unsigned, int pred)
+{
+  const unsigned tid = hb_emu_tid();
+  const unsigned nt = blockDim.x*blockDim.y*blockDim.z;
+  const double mine = pred ? 1. : 0.;
+  std::memcpy(&hb_emu::g_shfl[tid], &mine, sizeof(double));
+  __syncthreads();
+  int any = 0;
+  for (unsigned i = (tid/32)*32; i < (tid/32)*32 + 32 && i < nt; ++i) { double v; std::memcpy(&v, &hb_emu::g_shfl[i], sizeof(double)); any |= v != 0.; }
+  __syncthreads();
+  return any;
+}
+inline int __syncthreads_or(int pred)
+{
+  const unsigned tid = hb_emu_tid();
+  const unsigned nt = blockDim.x*blockDim.y*blockDim.z;
+  const double mine = pred ? 1. : 0.;
+  std::memcpy(&hb_emu::g_shfl[tid], &mine, sizeof(double));
+  __syncthreads();
+  int any = 0;
+  for (unsigned i = 0; i < nt; ++i) { double v; std::memcpy(&v, &hb_emu::g_shfl[i], sizeof(double)); any |= v != 0.; }
+  __syncthreads();
+  return any;
+}
+template <class T> T atomicOr(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; *p = o | v; return o; }
 template <class T> T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; *p = o + v; return o; }
 template <class T> T atomicMin(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; if (v < o) *p = v; return o; }
 template <class T> T atomicMax(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; if (v > o) *p = v; return o; }
@@ -105,7 +130,7 @@ inline int __float_as_int(float f) { int r; std::memcpy(&r, &f, 4); return r; }
 inline float __int_as_float(int i) { float r; std::memcpy(&r, &i, 4); return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __drcp_rn(double a) { return 1./a; }
-using std::fabs; using std::fmax; using std::fmin; using std::sqrt;
+using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::isfinite;
 
 /* ---- host API subset ---- */
 typedef int cudaError_t;

@@ -83,6 +83,7 @@ class HostHarness:
         L.hbh_work_units.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.hbh_add_device_bc.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, dp, C.c_int]
         L.hbh_apply_bcs.argtypes = [C.c_void_p, C.c_int]
+        L.hbh_is_admissible.argtypes = [C.c_void_p, ip, ip]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
         m = mesh
         self.m = m
@@ -145,6 +146,11 @@ class HostHarness:
             params = np.ascontiguousarray(bc["params"], dtype=np.float64) if bc.get("params") is not None else np.zeros(1)
             n_params = params.size if bc.get("params") is not None else 0
             self._check(self.lib.hbh_add_device_bc(self.h, bc["kind"], _i(idx), idx.size, _d(params), n_params))
+
+    def is_admissible(self):
+        ok = np.zeros(1, np.int32); rec = np.zeros(max(self.m.n_elem, 1), np.int32)
+        self._check(self.lib.hbh_is_admissible(self.h, _i(ok), _i(rec)))
+        return bool(ok[0]), rec[:self.m.n_elem]
 
     def apply_state_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 0))
     def apply_flux_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 1))

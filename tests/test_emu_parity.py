@@ -137,3 +137,10 @@ def test_box_2d_pipelined_local(oracle, emu_lib, deformed, rs, n):
     oracle.compute_write_face(basis, m)
     out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2)
     assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
+def test_is_admissible(oracle, emu_lib, nd, rs):
+    """SURVEY section 8 f-2: Solver::is_admissible / Element::record on the device"""
+    from util import check_admissibility
+    check_admissibility(oracle, emu_lib, nd, rs)

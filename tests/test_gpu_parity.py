@@ -242,3 +242,10 @@ def test_riemann_invariants_bc(oracle, gpu_lib, nd, rs):
     Characteristics / ColPivHouseholderQR, over sub/supersonic in/outflow and singular (zero-pressure) points"""
     from util import check_riemann_bc
     check_riemann_bc(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 6), (2, 6), (3, 6), (3, 4)])
+def test_is_admissible(oracle, gpu_lib, nd, rs):
+    """SURVEY section 8 f-2: Solver::is_admissible / Element::record on the device"""
+    from util import check_admissibility
+    check_admissibility(oracle, gpu_lib, nd, rs)

@@ -202,6 +202,36 @@ def test_adapter_device_bcs_gpu(oracle, host_gpu, resident):
     check_adapter_device_bcs(oracle, host_gpu, resident, 3, 4)
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_is_admissible_emu(oracle, host_emu, resident):
+    """hexed_b200::is_admissible through the pointer-graph adapter: same answer and Element::record as the oracle's restatement of
+    Solver::is_admissible, and the reference's exception text for a non-finite state"""
+    nd, rs = 2, 3
+    m, rng = soup(nd, rs, 12, n_car=7, n_def=9, n_ref=2)
+    basis = hb.gauss_legendre(rs)
+    oracle.compute_write_face(basis, m)
+    oracle.compute_prolong(basis, m)
+    m.state()[4, nd, 2] = -1.
+    m.face_state[2*nd*9 + 3].reshape(nd + 2, -1)[nd + 1, 1] = 0.
+    want, want_rec = oracle.is_admissible(m)
+    assert not want and want_rec.sum() == 2
+    h = H.HostHarness(host_emu, m, basis, seed=4)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    if resident:
+        h.to_device(H.ALL_ELEM | H.FACES)
+    got, rec = h.is_admissible()
+    assert got == want and np.array_equal(rec, want_rec)
+    m.state()[4, nd, 2] = np.nan
+    h.put(m)
+    if resident:
+        h.to_device(H.ALL_ELEM | H.FACES)
+    with pytest.raises(RuntimeError, match="state is not finite"):
+        h.is_admissible()
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+
+
 def check_adapter_device_bcs(oracle, host_emu, resident, nd, rs):
     """hexed_b200::add_device_bc / apply_state_bcs / apply_flux_bcs: a viscous step with every device-side boundary condition and no
     host boundary loop at all"""
