@@ -159,6 +159,45 @@ int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
 
+/* Thread -> line-task map. In the dense [i][j][k] field layout that the bulk copies deliver, lines of dimension 0 (stride RS^2) are
+ * conflict-free for consecutive lanes, but with 8-byte accesses consecutive lines of dimension 1 (stride RS) and 2 (stride 1) hit every
+ * shared-memory bank twice (profiles/r01g_ncu_full_euler.md: 217 M of 537 M shared wavefronts were bank conflicts, L1/shared pipe 73 %
+ * busy). At row size 6 the map therefore
+ *   - gives dimension-2 lines 16-byte accesses (two points per LDS.128/STS.128): 8 consecutive lines then cover 8 distinct 16-byte
+ *     bank groups ((2i + 3j) mod 8 advances by 3 per line), conflict-free;
+ *   - places dimension-1 lines half-warp by half-warp as rows i = (0,2), (1,3), (4,5) with 6 active lanes of every 8: rows 0/2 and 1/3
+ *     sit 8 banks apart (conflict-free), only the (4,5) pair still shares two banks.
+ * 120 of 128 threads carry a line. Other row sizes keep the plain map. */
+template <int RS> struct LineMap
+{
+  static constexpr bool vec2 = false; // 16-byte accesses along dimension 2
+  __device__ static __forceinline__ bool get(int t, int& d, int& l)
+  {
+    d = t/(RS*RS); l = t % (RS*RS);
+    return t < 3*RS*RS;
+  }
+};
+template <> struct LineMap<6>
+{
+  static constexpr bool vec2 = true;
+  __device__ static __forceinline__ bool get(int t, int& d, int& l)
+  {
+    if (t < 36) { d = 0; l = t; return true; }
+    if (t < 72) { d = 2; l = t - 36; return true; }
+    if (t < 80) { d = 0; l = 0; return false; }
+    d = 1;
+    const int u = t - 80, h = u/16, w = u % 16, slot = w/8, k = w % 8;
+    const int i = h < 2 ? h + 2*slot : 4 + slot;
+    l = i*6 + (k < 6 ? k : 0);
+    return k < 6;
+  }
+};
+
+__device__ __forceinline__ void ld2(const double* p, double& a, double& b)
+{ const double2 v = *reinterpret_cast<const double2*>(p); a = v.x; b = v.y; }
+__device__ __forceinline__ void st2(double* p, double a, double b)
+{ double2 v; v.x = a; v.y = b; *reinterpret_cast<double2*>(p) = v; }
+
 /* run-time (n_dim, row_size) -> compile-time dispatch; the analogue of the reference's kernel_factory
  * (include/kernel_factory.hpp:64-119). F is a generic lambda taking two integral_constants. */
 template <int V> struct IC { static constexpr int value = V; };

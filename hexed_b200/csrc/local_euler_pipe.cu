@@ -29,6 +29,7 @@ struct PipeCfg
   static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5;
   static constexpr int n_line = ND*nfq;
   static constexpr int threads = ((n_line + 31)/32)*32;
+  static_assert(RS % 2 == 0, "the line tasks process points in pairs");
   static constexpr int cs = nv > RS ? nv : RS;
   // double-buffered stage: state | numerical flux faces | reference level normals
   static constexpr int st_state = 0, st_face = nv*nq, st_nrml = st_face + 2*ND*nv*nfq;
@@ -101,8 +102,9 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
   }
 
   // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
-  const bool has_line = t < C::n_line;
-  const int d = t/nfq, l = t % nfq;
+  int d, l;
+  const bool has_line = LineMap<RS>::get(t, d, l);
+  const bool vec = LineMap<RS>::vec2 && d == 2; // this thread's line is contiguous: 16-byte accesses
   const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
   const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
 
@@ -117,35 +119,57 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if (has_line) {
-      double f[nv][RS];
-      #pragma unroll
-      for (int k = 0; k < RS; ++k) {
-        EulerPoint<ND> p;
+      double f[nv][RS]; // the state on the line, replaced point by point by the flux through reference direction d
+      if (vec) {
         #pragma unroll
-        for (int v = 0; v < nv; ++v) p.s[v] = S[v*nq + q0 + k*stride];
-        p.scalars();
-        double fl[nv];
+        for (int v = 0; v < nv; ++v)
+          #pragma unroll
+          for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, f[v][k], f[v][k + 1]);
+      } else {
+        #pragma unroll
+        for (int v = 0; v < nv; ++v)
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) f[v][k] = S[v*nq + q0 + k*stride];
+      }
+      #pragma unroll
+      for (int k2 = 0; k2 < RS; k2 += 2) {
+        [[maybe_unused]] double n[2][ND];
         if constexpr (DEF) {
-          double n[ND];
-          // normal[j] of reference direction d at this point: refn[d][j][q] (reference Spatial.hpp:411)
-          #pragma unroll
-          for (int j = 0; j < ND; ++j) n[j] = N[(d*ND + j)*nq + q0 + k*stride];
-          p.flux(n, fl);
-        } else {
-          // unit normal e_d; selects instead of a dynamically indexed register array
-          const double mass_flux = d == 0 ? p.s[0] : d == 1 ? p.s[1] : p.s[2];
-          const double vol_flux = mass_flux*p.inv_mass;
-          fl[ND] = mass_flux;
-          fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
-          #pragma unroll
-          for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+          // normal[j] of reference direction d at these points: refn[d][j][q] (reference Spatial.hpp:411)
+          if (vec) {
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) ld2(N + (d*ND + j)*nq + q0 + k2, n[0][j], n[1][j]);
+          } else {
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) { n[0][j] = N[(d*ND + j)*nq + q0 + k2*stride]; n[1][j] = N[(d*ND + j)*nq + q0 + (k2 + 1)*stride]; }
+          }
         }
         #pragma unroll
-        for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = k2 + kk;
+          EulerPoint<ND> p;
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) p.s[v] = f[v][k];
+          p.scalars();
+          double fl[nv];
+          if constexpr (DEF) p.flux(n[kk], fl);
+          else {
+            // unit normal e_d; selects instead of a dynamically indexed register array
+            const double mass_flux = d == 0 ? p.s[0] : d == 1 ? p.s[1] : p.s[2];
+            const double vol_flux = mass_flux*p.inv_mass;
+            fl[ND] = mass_flux;
+            fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+          }
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
+        }
       }
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
         #pragma unroll
         for (int i = 0; i < RS; ++i) {
           double acc = 0;
@@ -153,7 +177,15 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
           for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
           acc += ops.lift[i][0]*b0;
           acc += ops.lift[i][1]*b1;
-          R[(d*nv + v)*nq + q0 + i*stride] = -acc;
+          r[i] = -acc;
+        }
+        double* row = R + (d*nv + v)*nq + q0;
+        if (vec) {
+          #pragma unroll
+          for (int i = 0; i + 1 < RS; i += 2) st2(row + i, r[i], r[i + 1]);
+        } else {
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
         }
       }
     }
@@ -243,12 +275,19 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
       double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
+        double x[RS];
+        if (vec) {
+          #pragma unroll
+          for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, x[k], x[k + 1]);
+        } else {
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) x[k] = S[v*nq + q0 + k*stride];
+        }
         double e0 = 0, e1 = 0;
         #pragma unroll
         for (int k = 0; k < RS; ++k) {
-          const double x = S[v*nq + q0 + k*stride];
-          e0 += ops.bnd[0][k]*x;
-          e1 += ops.bnd[1][k]*x;
+          e0 += ops.bnd[0][k]*x[k];
+          e1 += ops.bnd[1][k]*x[k];
         }
         fout[((2*d)*nv + v)*nfq + l] = e0;
         fout[((2*d + 1)*nv + v)*nfq + l] = e1;

@@ -67,28 +67,31 @@ def test_stab_art_visc(oracle, emu_lib):
     dev.close()
 
 
+@pytest.mark.parametrize("rs", [4, 6])
 @pytest.mark.parametrize("deformed", [False, True])
-def test_box_3d_pipelined_local(oracle, emu_lib, deformed):
-    """3-D row size 4 takes the persistent TMA-pipelined Local kernel (local_euler_pipe.cu); the emulated device has one SM with
-    two resident CTAs, so every CTA walks several elements and both stage buffers and all barrier phases are exercised"""
-    basis = hb.gauss_legendre(4)
-    m = M.box_mesh(3, 4, 2, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+def test_box_3d_pipelined_local(oracle, emu_lib, deformed, rs):
+    """3-D row size 4 / 6 takes the persistent TMA-pipelined Local kernel (local_euler_pipe.cu); the emulated device has one SM with
+    two resident CTAs, so every CTA walks several elements and both stage buffers and all barrier phases are exercised. Row size 6
+    uses the bank-conflict-avoiding line map (LineMap<6>: sparse dimension-1 lanes, 16-byte dimension-2 accesses)"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(3, rs, 2, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
     density_wave(m, basis)
     oracle.compute_write_face(basis, m)
     out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2)
     assert_euler_parity(out, ref, dts)
 
 
+@pytest.mark.parametrize("rs", [4, 6])
 @pytest.mark.parametrize("kind", ["soup", "box_car", "box_def"])
-def test_navier_stokes_3d_line_kernel(oracle, emu_lib, kind):
-    """3-D row size 4 Navier-Stokes takes the line-task Local kernel (ns_local_line_kernel in generic_part.cu)"""
+def test_navier_stokes_3d_line_kernel(oracle, emu_lib, kind, rs):
+    """3-D row size 4 / 6 Navier-Stokes takes the line-task Local kernel (ns_local_line_kernel in generic_part.cu)"""
     rng = np.random.default_rng(77)
-    basis = hb.gauss_legendre(4)
+    basis = hb.gauss_legendre(rs)
     if kind == "soup":
-        m = M.soup_mesh(3, 4, rng, n_car=3, n_def=5, n_ref=2, with_ldg=True)
+        m = M.soup_mesh(3, rs, rng, n_car=3, n_def=5, n_ref=2, with_ldg=True)
         M.random_flow_state(m, rng)
     else:
-        m = M.box_mesh(3, 4, 2, basis, deformed=kind == "box_def", bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+        m = M.box_mesh(3, rs, 2, basis, deformed=kind == "box_def", bc_kind=M.BC_NONPENETRATION, with_ldg=True)
         density_wave(m, basis)
         oracle.compute_write_face(basis, m)
     prepare_pde_state(m, rng, NAVIER_STOKES)
