@@ -330,6 +330,14 @@ def main():
     if viscous:
         local_name += " + ns_local_line_kernel (both count as 'local'; see kernel_seconds_per_step)"
     traffic = ncu_traffic(local_name, ne) if not viscous else None
+    # Solver::is_admissible (reference src/Solver.cpp:921-958) runs after every stage of Solver::update when fix_admis is on; it is not
+    # part of the metric (the reference accounts it under "check admis."), so it is timed separately and reported beside the step
+    dev.reset_stats(); dev.set_timing(True)
+    admissible = [dev.is_admissible() for _ in range(3)]
+    dev.set_timing(False)
+    admis_stat = [s for s in dev.kernel_stats() if s["name"] == "check admis."]
+    aux = {"is_admissible_ms_per_call": admis_stat[0]["device_seconds"]/3*1e3 if admis_stat else None, "admissible": all(admissible),
+           "is_admissible_bytes": ne*(nv*nq + 2*nd*nv*m.nfq)*8}
     stage_gbs = value/world*(alg["stage"]*8/float(nv*nq))/1e9
 
     # ---- end to end through the public API with HOST buffers: the boundary condition is applied by the host (as the reference's
@@ -407,7 +415,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
                          "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/float(nv*nq)},
                          "kernel_seconds_per_step": shares},
-            "e2e": e2e, "cpu_baseline": cpu,
+            "e2e": e2e, "cpu_baseline": cpu, "aux": aux,
         }
         print(json.dumps(out))
     dev.close()

@@ -684,6 +684,27 @@ int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* c, double char_speed) { retu
 
 int hexed_b200_apply_flux_bcs(hexed_b200_ctx* c) { return launch_flux_bcs(c); }
 
+int hexed_b200_set_jacobian(hexed_b200_ctx* c, const double* vertex_pos, const double* node_adj)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (c->n_def && !vertex_pos) return fail(c, HEXED_B200_BAD_ARGUMENT, "vertex positions of the deformed elements are required");
+  double *d_vert = nullptr, *d_adj = nullptr;
+  const size_t n_vert_d = (size_t)c->n_def*c->n_vert*c->nd, n_adj = (size_t)c->n_def*2*c->nd*c->nfq;
+  int rc = 0;
+  if (c->n_def) {
+    rc = dev_alloc(c, &d_vert, n_vert_d, false);
+    if (!rc) rc = check(c, cudaMemcpyAsync(d_vert, vertex_pos, sizeof(double)*n_vert_d, cudaMemcpyHostToDevice, c->stream), "upload vertex positions");
+    if (!rc && node_adj) {
+      rc = dev_alloc(c, &d_adj, n_adj, false);
+      if (!rc) rc = check(c, cudaMemcpyAsync(d_adj, node_adj, sizeof(double)*n_adj, cudaMemcpyHostToDevice, c->stream), "upload node adjustments");
+    }
+  }
+  if (!rc) rc = launch_set_jacobian(c, d_vert, d_adj);
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "set_jacobian");
+  dev_free(d_vert); dev_free(d_adj);
+  return rc;
+}
+
 int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
 {
   if (!admissible) return fail(c, HEXED_B200_BAD_ARGUMENT, "null result pointer");

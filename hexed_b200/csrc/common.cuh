@@ -158,6 +158,7 @@ extern const GenericOps generic_ops_pde1, generic_ops_pde2, generic_ops_pde3, ge
 int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
+int launch_set_jacobian(hexed_b200_ctx* c, const double* d_vert, const double* d_node_adj);
 
 /* Thread -> line-task map. In the dense [i][j][k] field layout that the bulk copies deliver, lines of dimension 0 (stride RS^2) are
  * conflict-free for consecutive lanes, but with 8-byte accesses consecutive lines of dimension 1 (stride RS) and 2 (stride 1) hit every
@@ -167,8 +168,13 @@ int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
  *     bank groups ((2i + 3j) mod 8 advances by 3 per line), conflict-free;
  *   - places dimension-1 lines half-warp by half-warp as rows i = (0,2), (1,3), (4,5) with 6 active lanes of every 8: rows 0/2 and 1/3
  *     sit 8 banks apart (conflict-free), only the (4,5) pair still shares two banks.
- * 120 of 128 threads carry a line. Other row sizes keep the plain map. */
-template <int RS> struct LineMap
+ * 120 of 128 threads carry a line. Other row sizes keep the plain map.
+ * Measured (profiles/r01i_ncu_full_euler.md against r01g): shared wavefronts -19 %, conflicts 217 M -> 67 M, L1/shared pipe 73 % -> 50 %
+ * busy, and yet the deformed Euler kernel got 3 % SLOWER (104 -> 168 registers, +11 % instructions, fixed-latency "wait" stalls 1.4 ->
+ * 2.4 per issue): with 8 warps per SM the kernel is latency-bound, not LSU-bound. The Cartesian kernel, which has no normals to stage
+ * and half the arithmetic per line, gained 7 %. The map is therefore used by the Cartesian instantiation only (SPARSE = !DEF), and the
+ * Navier-Stokes line kernel (8.2 -> 8.5 ms with it) keeps the plain map. */
+template <int RS, bool SPARSE = true> struct LineMap
 {
   static constexpr bool vec2 = false; // 16-byte accesses along dimension 2
   __device__ static __forceinline__ bool get(int t, int& d, int& l)
@@ -177,7 +183,7 @@ template <int RS> struct LineMap
     return t < 3*RS*RS;
   }
 };
-template <> struct LineMap<6>
+template <> struct LineMap<6, true>
 {
   static constexpr bool vec2 = true;
   __device__ static __forceinline__ bool get(int t, int& d, int& l)

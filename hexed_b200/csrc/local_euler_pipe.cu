@@ -103,8 +103,9 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
 
   // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
   int d, l;
-  const bool has_line = LineMap<RS>::get(t, d, l);
-  const bool vec = LineMap<RS>::vec2 && d == 2; // this thread's line is contiguous: 16-byte accesses
+  using Map = LineMap<RS, !DEF>; // measured: pays off for the Cartesian kernel only (see common.cuh)
+  const bool has_line = Map::get(t, d, l);
+  const bool vec = Map::vec2 && d == 2; // this thread's line is contiguous: 16-byte accesses
   const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
   const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
 
@@ -118,42 +119,95 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_wait(&bars[s], par);
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
-    if (has_line) {
-      double f[nv][RS]; // the state on the line, replaced point by point by the flux through reference direction d
-      if (vec) {
-        #pragma unroll
-        for (int v = 0; v < nv; ++v)
+    if constexpr (Map::vec2) {
+      if (has_line) {
+        double f[nv][RS]; // the state on the line, replaced point by point by the flux through reference direction d
+        if (vec) {
           #pragma unroll
-          for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, f[v][k], f[v][k + 1]);
-      } else {
-        #pragma unroll
-        for (int v = 0; v < nv; ++v)
+          for (int v = 0; v < nv; ++v)
+            #pragma unroll
+            for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, f[v][k], f[v][k + 1]);
+        } else {
           #pragma unroll
-          for (int k = 0; k < RS; ++k) f[v][k] = S[v*nq + q0 + k*stride];
-      }
-      #pragma unroll
-      for (int k2 = 0; k2 < RS; k2 += 2) {
-        [[maybe_unused]] double n[2][ND];
-        if constexpr (DEF) {
-          // normal[j] of reference direction d at these points: refn[d][j][q] (reference Spatial.hpp:411)
-          if (vec) {
+          for (int v = 0; v < nv; ++v)
             #pragma unroll
-            for (int j = 0; j < ND; ++j) ld2(N + (d*ND + j)*nq + q0 + k2, n[0][j], n[1][j]);
-          } else {
+            for (int k = 0; k < RS; ++k) f[v][k] = S[v*nq + q0 + k*stride];
+        }
+        #pragma unroll
+        for (int k2 = 0; k2 < RS; k2 += 2) {
+          [[maybe_unused]] double n[2][ND];
+          if constexpr (DEF) {
+            // normal[j] of reference direction d at these points: refn[d][j][q] (reference Spatial.hpp:411)
+            if (vec) {
+              #pragma unroll
+              for (int j = 0; j < ND; ++j) ld2(N + (d*ND + j)*nq + q0 + k2, n[0][j], n[1][j]);
+            } else {
+              #pragma unroll
+              for (int j = 0; j < ND; ++j) { n[0][j] = N[(d*ND + j)*nq + q0 + k2*stride]; n[1][j] = N[(d*ND + j)*nq + q0 + (k2 + 1)*stride]; }
+            }
+          }
+          #pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = k2 + kk;
+            EulerPoint<ND> p;
             #pragma unroll
-            for (int j = 0; j < ND; ++j) { n[0][j] = N[(d*ND + j)*nq + q0 + k2*stride]; n[1][j] = N[(d*ND + j)*nq + q0 + (k2 + 1)*stride]; }
+            for (int v = 0; v < nv; ++v) p.s[v] = f[v][k];
+            p.scalars();
+            double fl[nv];
+            if constexpr (DEF) p.flux(n[kk], fl);
+            else {
+              // unit normal e_d; selects instead of a dynamically indexed register array
+              const double mass_flux = d == 0 ? p.s[0] : d == 1 ? p.s[1] : p.s[2];
+              const double vol_flux = mass_flux*p.inv_mass;
+              fl[ND] = mass_flux;
+              fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
+              #pragma unroll
+              for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+            }
+            #pragma unroll
+            for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
           }
         }
         #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const int k = k2 + kk;
+        for (int v = 0; v < nv; ++v) {
+          const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
+          double r[RS];
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            r[i] = -acc;
+          }
+          double* row = R + (d*nv + v)*nq + q0;
+          if (vec) {
+            #pragma unroll
+            for (int i = 0; i + 1 < RS; i += 2) st2(row + i, r[i], r[i + 1]);
+          } else {
+            #pragma unroll
+            for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
+          }
+        }
+      }
+    } else {
+      if (has_line) {
+        double f[nv][RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) {
           EulerPoint<ND> p;
           #pragma unroll
-          for (int v = 0; v < nv; ++v) p.s[v] = f[v][k];
+          for (int v = 0; v < nv; ++v) p.s[v] = S[v*nq + q0 + k*stride];
           p.scalars();
           double fl[nv];
-          if constexpr (DEF) p.flux(n[kk], fl);
-          else {
+          if constexpr (DEF) {
+            double n[ND];
+            // normal[j] of reference direction d at this point: refn[d][j][q] (reference Spatial.hpp:411)
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) n[j] = N[(d*ND + j)*nq + q0 + k*stride];
+            p.flux(n, fl);
+          } else {
             // unit normal e_d; selects instead of a dynamically indexed register array
             const double mass_flux = d == 0 ? p.s[0] : d == 1 ? p.s[1] : p.s[2];
             const double vol_flux = mass_flux*p.inv_mass;
@@ -165,27 +219,18 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
           #pragma unroll
           for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
         }
-      }
-      #pragma unroll
-      for (int v = 0; v < nv; ++v) {
-        const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
-        double r[RS];
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
+        for (int v = 0; v < nv; ++v) {
+          const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
           #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          r[i] = -acc;
-        }
-        double* row = R + (d*nv + v)*nq + q0;
-        if (vec) {
-          #pragma unroll
-          for (int i = 0; i + 1 < RS; i += 2) st2(row + i, r[i], r[i + 1]);
-        } else {
-          #pragma unroll
-          for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
+          for (int i = 0; i < RS; ++i) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            R[(d*nv + v)*nq + q0 + i*stride] = -acc;
+          }
         }
       }
     }
@@ -271,26 +316,44 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     }
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
-    if (has_line) {
-      double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
-      #pragma unroll
-      for (int v = 0; v < nv; ++v) {
-        double x[RS];
-        if (vec) {
-          #pragma unroll
-          for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, x[k], x[k + 1]);
-        } else {
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) x[k] = S[v*nq + q0 + k*stride];
-        }
-        double e0 = 0, e1 = 0;
+    if constexpr (Map::vec2) {
+      if (has_line) {
+        double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
         #pragma unroll
-        for (int k = 0; k < RS; ++k) {
-          e0 += ops.bnd[0][k]*x[k];
-          e1 += ops.bnd[1][k]*x[k];
+        for (int v = 0; v < nv; ++v) {
+          double x[RS];
+          if (vec) {
+            #pragma unroll
+            for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, x[k], x[k + 1]);
+          } else {
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) x[k] = S[v*nq + q0 + k*stride];
+          }
+          double e0 = 0, e1 = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) {
+            e0 += ops.bnd[0][k]*x[k];
+            e1 += ops.bnd[1][k]*x[k];
+          }
+          fout[((2*d)*nv + v)*nfq + l] = e0;
+          fout[((2*d + 1)*nv + v)*nfq + l] = e1;
         }
-        fout[((2*d)*nv + v)*nfq + l] = e0;
-        fout[((2*d + 1)*nv + v)*nfq + l] = e1;
+      }
+    } else {
+      if (has_line) {
+        double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          double e0 = 0, e1 = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) {
+            const double x = S[v*nq + q0 + k*stride];
+            e0 += ops.bnd[0][k]*x;
+            e1 += ops.bnd[1][k]*x;
+          }
+          fout[((2*d)*nv + v)*nfq + l] = e0;
+          fout[((2*d + 1)*nv + v)*nfq + l] = e1;
+        }
       }
     }
     __syncthreads(); // stage buffer s free

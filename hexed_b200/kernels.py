@@ -91,6 +91,7 @@ SIGNATURES = {
     "hexed_b200_stabilizing_art_visc": [C.c_void_p, C.c_double],
     "hexed_b200_pde_kernel": [C.c_void_p, C.c_int, C.c_int, C.c_int, Options, Transport, Transport, C.c_double, C.c_double],
     "hexed_b200_apply_flux_bcs": [C.c_void_p],
+    "hexed_b200_set_jacobian": [C.c_void_p, dp, dp],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
     "hexed_b200_download_record": [C.c_void_p, ip, C.c_int, C.c_int],
     "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
@@ -400,6 +401,13 @@ class Device:
 
     def apply_flux_bcs(self):
         self._check(self.lib.hexed_b200_apply_flux_bcs(self.ctx))
+
+    def set_jacobian(self, vertex_pos, node_adj=None):
+        """element loop of Solver::calc_jacobian (reference src/Solver.cpp:281-286, src/Deformed_element.cpp:60-136): vertex_pos
+        (n_def, 2^nd, nd), node_adj (n_def, 2*nd, nfq) or None"""
+        v = np.ascontiguousarray(vertex_pos, dtype=np.float64)
+        a = None if node_adj is None else np.ascontiguousarray(node_adj, dtype=np.float64)
+        self._check(self.lib.hexed_b200_set_jacobian(self.ctx, v.ctypes.data_as(dp), None if a is None else a.ctypes.data_as(dp)))
 
     def is_admissible(self):
         """Solver::is_admissible (reference src/Solver.cpp:921-958); raises RuntimeError("state is not finite") like the reference's

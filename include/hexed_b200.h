@@ -214,6 +214,15 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 int hexed_b200_is_admissible(hexed_b200_ctx* ctx, int* admissible);
 int hexed_b200_download_record(hexed_b200_ctx* ctx, int* dst, int first_elem, int n_elem);
 
+/* ---- metric terms on the device: the element loop of Solver::calc_jacobian (src/Solver.cpp:281-286), i.e.
+ * Deformed_element::set_jacobian (src/Deformed_element.cpp:60-136, positions by :15-58 including the face-warping node adjustments)
+ * for every deformed element and Element::set_jacobian (src/Element.cpp:99-112) for every Cartesian one. Host inputs:
+ * vertex_pos [n_def][2^n_dim][n_dim] (vertex index row-major, dimension 0 slowest; Vertex::pos), node_adj [n_def][2*n_dim][nfq]
+ * (Deformed_element::node_adjustments(), may be NULL = all zero); nominal sizes must have been uploaded. Writes reference-level normals,
+ * determinant, vertex time-step scale of the deformed elements and, like the reference, each element's face normals into the first
+ * n_dim*nfq doubles of its face storage (HEXED_B200_FACE_STATE), where the shared-normal pass of calc_jacobian (:287-357, host) reads them. ---- */
+int hexed_b200_set_jacobian(hexed_b200_ctx* ctx, const double* vertex_pos, const double* node_adj);
+
 /* ---- domain decomposition (new in this implementation: the reference is single-process) ----
  * A rank's mesh is self-contained: faces of remote elements are HALO face slots (ordinary slots >= 2*n_dim*n_elem). The host
  * registers the slots it sends / receives as face lists and moves them with face_list_gather / face_list_scatter (device

@@ -342,3 +342,101 @@ class Oracle:
                     ghf = p[1]*p[5]*(temp*temp*temp*temp) + p[2]*(temp - p[3])
                 g[:, nd + 1] = p[4]*(nrm*flux_sign*ghf - in_e) + in_e
                 m.face_ldg[gh] = g.reshape(len(gh), -1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# metric terms: numpy restatement of Deformed_element::position / set_jacobian, one element at a time with
+# plain loops (small cases only). TEST INFRASTRUCTURE like everything else in this directory.
+# ---------------------------------------------------------------------------------------------------------------------
+def _dimension_matvec(mat, vec, i_dim):
+    """math::dimension_matvec (reference src/math.cpp:58-81): vec viewed as [cols^i_dim][cols][rest], contract the middle index"""
+    mat = np.atleast_2d(mat)
+    rows, cols = mat.shape
+    n_rows = cols**(i_dim + 1)
+    n_cols = vec.size//n_rows
+    v = vec.reshape(n_rows//cols, cols, n_cols)
+    return np.einsum("rc,ocn->orn", mat, v).reshape(-1)
+
+
+def element_position(vert, node_adj, basis, q):
+    """Deformed_element::position (reference src/Deformed_element.cpp:15-58): vert (2^nd, nd), node_adj (2*nd*nfq,)"""
+    n_vert, nd = vert.shape
+    rs = basis.row_size
+    nq = rs**nd
+    nfq = nq//rs
+    pos = np.zeros(nd)
+    for i_dim in range(nd):
+        vert_pos = vert[:, i_dim].copy()
+        adjustments = [vert_pos.copy() for _ in range(nd)]
+        for j_dim in range(nd - 1, -1, -1):
+            stride = rs**(nd - j_dim - 1)
+            node = basis.node[(q//stride) % rs]
+            interp = np.array([[1. - node, node]])
+            vert_pos = _dimension_matvec(interp, vert_pos, j_dim)
+            fq, face_stride = 0, nq//rs//rs if nd > 1 else 0
+            for k_dim in range(nd):
+                if k_dim != j_dim:
+                    fq += ((q//rs**(nd - k_dim - 1)) % rs)*face_stride
+                    face_stride //= rs
+            for k_dim in range(nd):
+                i_adjust = 2*j_dim*nfq + fq
+                adjust = np.array([[node_adj[i_adjust], node_adj[i_adjust + nfq]]])
+                difference = np.array([[-1., 1.], [-1., 1.]])
+                contract = (adjust*interp) @ difference if j_dim == k_dim else interp
+                adjustments[k_dim] = _dimension_matvec(contract, adjustments[k_dim], j_dim)
+        pos[i_dim] = vert_pos[0]
+        for j_dim in range(nd):
+            pos[i_dim] += adjustments[j_dim][0]
+    return pos
+
+
+def set_jacobian(vert, node_adj, nom, basis):
+    """Deformed_element::set_jacobian (reference src/Deformed_element.cpp:60-136) for one element.
+    returns dict: jac (nd, nd, nq) [i][j] = d pos_i/d ref_j/nom, ref_normals (nd*nd, nq), det (nq,), face_normals (2*nd, nd, nfq),
+    vertex_tss (2^nd,). Determinants by numpy (LU with partial pivoting, like Eigen's dynamic-size determinant())."""
+    n_vert, nd = vert.shape
+    rs = basis.row_size
+    nq = rs**nd
+    nfq = nq//rs
+    diff, bnd = np.asarray(basis.diff_mat), np.asarray(basis.boundary)
+    pos = np.array([element_position(vert, node_adj, basis, q) for q in range(nq)])  # (nq, nd)
+    jac = np.zeros((nd, nd, nq))
+    for i in range(nd):
+        for j in range(nd):
+            jac[i, j] = _dimension_matvec(diff, pos[:, i].copy(), j)/nom
+    refn = np.zeros((nd*nd, nq))
+    det = np.zeros(nq)
+    for q in range(nq):
+        J = jac[:, :, q]
+        det[q] = np.linalg.det(J)
+        for i in range(nd):
+            for j in range(nd):
+                c = J.copy()
+                c[:, i] = 0.
+                c[j, i] = 1.
+                refn[i*nd + j, q] = np.linalg.det(c)
+    fn = np.zeros((2*nd, nd, nfq))
+    for i in range(nd):
+        for sign in range(2):
+            fj = np.array([[_dimension_matvec(bnd[sign:sign + 1], jac[a, b].copy(), i) for b in range(nd)] for a in range(nd)])  # (nd, nd, nfq)
+            for fq in range(nfq):
+                for j in range(nd):
+                    c = fj[:, :, fq].copy()
+                    c[:, i] = 0.
+                    c[j, i] = 1.
+                    fn[2*i + sign, j, fq] = np.linalg.det(c)
+
+    def to_vertices(field):
+        v = field.copy()
+        for d in range(nd - 1, -1, -1):  # hypercube_matvec(boundary, .): contract every dimension with the 2 x rs boundary matrix
+            v = _dimension_matvec(bnd, v, d)   # (last dimension first, so the leading dimensions still have row_size entries)
+        return v
+    vn = np.array([to_vertices(refn[k]) for k in range(nd*nd)])  # (nd*nd, n_vert)
+    vd = to_vertices(det)
+    vtss = np.zeros(n_vert)
+    for iv in range(n_vert):
+        norm_sum = 0.
+        for i in range(nd):
+            norm_sum += np.sqrt(sum(vn[i*nd + j, iv]**2 for j in range(nd)))
+        vtss[iv] = nom*vd[iv]/norm_sum
+    return dict(jac=jac, ref_normals=refn, det=det, face_normals=fn, vertex_tss=vtss, pos=pos)

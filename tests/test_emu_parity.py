@@ -147,3 +147,10 @@ def test_is_admissible(oracle, emu_lib, nd, rs):
     """SURVEY section 8 f-2: Solver::is_admissible / Element::record on the device"""
     from util import check_admissibility
     check_admissibility(oracle, emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 3), (3, 2), (3, 3)])
+def test_set_jacobian(emu_lib, nd, rs):
+    """metric terms of deformed elements computed on the device from vertex positions and node adjustments"""
+    from util import check_set_jacobian
+    check_set_jacobian(emu_lib, nd, rs)

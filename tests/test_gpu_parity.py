@@ -249,3 +249,10 @@ def test_is_admissible(oracle, gpu_lib, nd, rs):
     """SURVEY section 8 f-2: Solver::is_admissible / Element::record on the device"""
     from util import check_admissibility
     check_admissibility(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 4), (3, 8)])
+def test_set_jacobian(gpu_lib, nd, rs):
+    """metric terms of deformed elements computed on the device from vertex positions and node adjustments"""
+    from util import check_set_jacobian
+    check_set_jacobian(gpu_lib, nd, rs)

@@ -470,3 +470,59 @@ def test_viscous_momentum_decay(oracle, nd, rs, deformed):
     if nd > 1:
         assert np.abs(resid[:, :nd]).max() > 3.  # the decay rate is not trivially inside the margin
     assert np.abs(resid[:, nd]).max() <= margin  # rate of change of mass is 0
+
+
+# ---------------------------------------------------------------- test_Deformed_element.cpp with node adjustments (f-4 oracle)
+def _unit_vertices(nd, size=1., origin=None):
+    v = np.array([[(i >> (nd - 1 - d)) & 1 for d in range(nd)] for i in range(2**nd)], dtype=float)
+    return (v + (0. if origin is None else np.asarray(origin, dtype=float)))*size
+
+
+def test_position_with_node_adjustments():
+    """test/test_Deformed_element.cpp:65-83"""
+    b = _equidistant(3)
+    adj = np.zeros(4*3); adj[1] = 0.1
+    x = [pyoracle.element_position(_unit_vertices(2), adj, b, q)[0] for q in (0, 6, 4)]
+    assert approx(x[1], 1.) and approx(x[2], .55) and abs(x[0]) <= 1e-15
+    adj = np.zeros(6*9); adj[4] = 0.01
+    p = pyoracle.element_position(_unit_vertices(3, .2), adj, b, 13)
+    assert approx(p[0], .101) and approx(p[1], .1) and approx(p[2], .1)
+    leg = hb.gauss_legendre(3)
+    adj = np.zeros(4*3); adj[1] = 0.1; adj[3] = -0.2
+    assert approx(pyoracle.element_position(_unit_vertices(2, .2), adj, leg, 3)[0], .08)
+    assert approx(pyoracle.element_position(_unit_vertices(2, .2), adj, leg, 4)[0], .11)
+
+
+def test_set_jacobian_oracle():
+    """test/test_Deformed_element.cpp:85-139 against the loop-by-loop restatement (node adjustments included), and agreement of that
+    restatement with the vectorised one used to build the synthetic meshes"""
+    b = _equidistant(3)
+    vert = _unit_vertices(2, .2); vert[3] = [.8*.2, .8*.2]
+    g = pyoracle.set_jacobian(vert, np.zeros(12), .2, b)
+    J = g["jac"]
+    assert np.allclose(J[:, :, 0], np.eye(2), atol=1e-12)
+    assert np.allclose(J[:, :, 6], [[1., -.2], [0., .8]], atol=1e-12)
+    assert np.allclose(J[:, :, 8], [[.8, -.2], [-.2, .8]], atol=1e-12)
+    assert approx(g["det"][6], .8)
+    fn = g["face_normals"]
+    assert approx(fn[0, 0, 0], 1.) and abs(fn[0, 1, 0]) <= 1e-12
+    assert approx(fn[3, 0, 2], .2) and approx(fn[3, 1, 2], .8)
+    assert g["vertex_tss"][0] == .2/2
+    assert approx(g["vertex_tss"][3], .2/2*(.8*.8 - .2*.2)/np.sqrt(.8*.8 + .2*.2))
+    adj = np.zeros(12); adj[6 + 1] = 0.1
+    g1 = pyoracle.set_jacobian(_unit_vertices(2, .2, origin=[1, 1]), adj, .2, b)
+    assert np.allclose(g1["jac"][:, :, 5], [[1., 0.], [0., .9]], atol=1e-12)
+    vert3 = _unit_vertices(3, .2); vert3[7] = .8*.2
+    g2 = pyoracle.set_jacobian(vert3, np.zeros(54), .2, b)
+    assert g2["jac"][0, 0, 0] == 1.
+    assert np.allclose(g2["jac"][0, :, 26], [.8, -.2, -.2]) and np.allclose(g2["jac"][2, 1:, 26], [-.2, .8])
+    # the vectorised restatement (hexed_b200.mesh.element_metrics, zero adjustments) gives the same numbers
+    rng = np.random.default_rng(3)
+    leg = hb.gauss_legendre(4)
+    for nd in (2, 3):
+        v = _unit_vertices(nd, .3) + rng.uniform(-.03, .03, (2**nd, nd))
+        a = pyoracle.set_jacobian(v, np.zeros(2*nd*4**(nd - 1)), .3, leg)
+        t = M.element_metrics(v[None], np.array([.3]), leg)
+        for key in ("ref_normals", "det", "vertex_tss"):
+            assert np.allclose(t[key].numpy()[0], a[key], rtol=1e-12, atol=1e-14), key
+        assert np.allclose(t["face_normals"].numpy()[0], a["face_normals"], rtol=1e-12, atol=1e-14)
