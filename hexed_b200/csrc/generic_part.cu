@@ -33,7 +33,11 @@ struct GArgs
 
 template <class K> int set_smem(hexed_b200_ctx* c, K k, size_t smem)
 {
-  if (smem > 48*1024) HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48*1024) {
+    HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // several such CTAs per SM only fit with the largest shared-memory carve-out
+    HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
   return 0;
 }
 
@@ -468,15 +472,26 @@ struct NsCfg
 {
   static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5, n_line = ND*nfq;
   static constexpr int threads = ((n_line + 31)/32)*32;
-  // inputs, each one contiguous run of the element-major layout, fetched by 1-D bulk TMA copies onto one mbarrier
-  static constexpr int s_state = 0, s_ldg = s_state + nv*nq, s_fc = s_ldg + 2*ND*nv*nfq, s_tss = s_fc + 2*ND*nv*nfq, s_av = s_tss + nq;
-  static constexpr int s_nrml = s_av + 2*nq, s_fn = s_nrml + (DEF ? ND*ND*nq : 0), s_det = s_fn + (DEF ? 2*ND*ND*nfq : 0);
-  static constexpr int s_grad = s_det + (DEF ? nq : 0), s_flux = s_grad + ND*nv*nq, smem_doubles = s_flux + ND*nv*nq;
+  // Shared-memory plan, sized so that THREE CTAs are resident per SM at row size 6 (72.6 KB each; the first version staged every input
+  // and kept G and F apart: 105 KB, two CTAs, 12 % occupancy, profiles/r01h_ncu_full_ns.md):
+  //   state | flux faces | region A = [LDG faces | reference normals | face normals] | G
+  // fetched by 1-D bulk TMA copies onto one mbarrier. F (the convective flux, then its derivative) ALIASES region A: the LDG faces and
+  // face normals are dead after P1 (a barrier separates P1 from P2), and F's fields 5..13 coincide field for field with the nine
+  // reference normals, which the thread that writes F[.][q] has itself just read at the same q and nobody else reads at that q.
+  // The per-point scalars (tss, determinant, AV coefficients; used once or twice per point) are read straight from HBM after a
+  // prefetch issued at the top of the kernel.
+  static constexpr int s_state = 0, s_fc = s_state + nv*nq, s_ldg = s_fc + 2*ND*nv*nfq;
+  static constexpr int s_nrml = s_ldg + 2*ND*nv*nfq, s_fn = s_nrml + (DEF ? ND*ND*nq : 0);
+  static constexpr int a_end = s_fn + (DEF ? 2*ND*ND*nfq : 0);
+  static constexpr int s_flux = s_nrml - nv*nq; // aliases region A so that F field 5 lands on the first reference normal (= s_ldg at row size 6)
+  static_assert(s_flux >= s_ldg, "the LDG faces must be at least as large as nv fields (row size <= 6)");
+  static constexpr int s_grad = (a_end > s_flux + ND*nv*nq) ? a_end : s_flux + ND*nv*nq;
+  static constexpr int smem_doubles = s_grad + ND*nv*nq;
   static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 2*sizeof(mbar_t);
 };
 
 template <int RS, bool DEF>
-__global__ void __launch_bounds__(NsCfg<RS, DEF>::threads, 2)
+__global__ void __launch_bounds__(NsCfg<RS, DEF>::threads, 3)
 ns_local_line_kernel(GArgs a, Ops ops)
 {
   using C = NsCfg<RS, DEF>;
@@ -487,11 +502,8 @@ ns_local_line_kernel(GArgs a, Ops ops)
   double* S = smem + C::s_state;
   const double* fldg = smem + C::s_ldg;
   const double* fc = smem + C::s_fc;
-  const double* s_tss = smem + C::s_tss;
-  const double* s_av = smem + C::s_av;
   const double* rn = smem + C::s_nrml;
   const double* fn = smem + C::s_fn;
-  const double* s_det = smem + C::s_det;
   double* G = smem + C::s_grad;
   double* F = smem + C::s_flux;
   mbar_t* bar = reinterpret_cast<mbar_t*>(smem + C::smem_doubles);
@@ -502,16 +514,24 @@ ns_local_line_kernel(GArgs a, Ops ops)
   __syncthreads();
   if (t == 0) {
     constexpr unsigned b_field = sizeof(double)*nq, b_face = sizeof(double)*2*ND*nv*nfq;
-    mbar_arrive_expect_tx(bar, nv*b_field + 2*b_face + 3*b_field + (DEF ? (ND*ND + 1)*b_field + sizeof(double)*2*ND*ND*nfq : 0u));
+    mbar_arrive_expect_tx(bar, nv*b_field + 2*b_face + (DEF ? ND*ND*b_field + sizeof(double)*2*ND*ND*nfq : 0u));
     bulk_g2s(S, a.ed.state + (size_t)e*nv*nq, nv*b_field, bar);
     bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
     bulk_g2s(smem + C::s_fc, a.faces + (size_t)e*2*ND*wl, b_face, bar);
-    bulk_g2s(smem + C::s_tss, a.ed.tss + (size_t)e*nq, b_field, bar);
-    bulk_g2s(smem + C::s_av, a.ed.av + (size_t)e*2*nq, 2*b_field, bar);
     if constexpr (DEF) {
       bulk_g2s(smem + C::s_nrml, a.refn + (size_t)(e - a.n_car)*ND*ND*nq, ND*ND*b_field, bar);
       bulk_g2s(smem + C::s_fn, a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq, sizeof(double)*2*ND*ND*nfq, bar);
-      bulk_g2s(smem + C::s_det, a.det + (size_t)(e - a.n_car)*nq, b_field, bar);
+    }
+  }
+  // per-point scalars: prefetch their cache lines now, read them in P2 / P4
+  const double* g_tss = a.ed.tss + (size_t)e*nq;
+  const double* g_av = a.ed.av + (size_t)e*2*nq;
+  [[maybe_unused]] const double* g_det = DEF ? a.det + (size_t)(e - a.n_car)*nq : nullptr;
+  {
+    constexpr int lines = (nq*8 + 127)/128; // 128-byte lines per field
+    for (int i = t; i < (DEF ? 4 : 3)*lines; i += T) {
+      const int fld = i/lines, off = (i % lines)*16;
+      prefetch_l1(fld == 0 ? g_tss + off : fld == 1 ? g_av + off : fld == 2 ? g_av + nq + off : g_det + off);
     }
   }
   const double nom = a.nom[e];
@@ -580,10 +600,10 @@ ns_local_line_kernel(GArgs a, Ops ops)
     typename P::template Comp<ND> comp;
     #pragma unroll
     for (int v = 0; v < nv; ++v) comp.state[v] = S[v*nq + q];
-    comp.state[nv] = s_av[q];
-    comp.state[nv + 1] = s_av[nq + q];
+    comp.state[nv] = g_av[q];
+    comp.state[nv + 1] = g_av[nq + q];
     if constexpr (DEF) {
-      const double inv_det = 1./s_det[q];
+      const double inv_det = 1./g_det[q];
       #pragma unroll
       for (int d = 0; d < ND; ++d)
         #pragma unroll
@@ -654,8 +674,8 @@ ns_local_line_kernel(GArgs a, Ops ops)
   /* ---- P4: combine and update ---- */
   for (int q = t; q < nq; q += T) {
     double mult; // update*tss/nom/det with one division (<= 1 ulp)
-    if constexpr (DEF) mult = a.update*s_tss[q]/(nom*s_det[q]);
-    else mult = a.update*s_tss[q]/nom;
+    if constexpr (DEF) mult = a.update*g_tss[q]/(nom*g_det[q]);
+    else mult = a.update*g_tss[q]/nom;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double r0 = 0., r1 = 0.;

@@ -138,7 +138,8 @@ typedef void* cudaStream_t;
 typedef struct hb_emu_event { int dummy; }* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaHostAllocDefault = 0,
+       cudaFuncAttributePreferredSharedMemoryCarveout = 9, cudaSharedmemCarveoutMaxShared = 100 };
 struct cudaDeviceProp { int multiProcessorCount = 148; char name[64] = "host-emulation"; int major = 10, minor = 0; };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated cuda error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
