@@ -705,6 +705,42 @@ int hexed_b200_set_jacobian(hexed_b200_ctx* c, const double* vertex_pos, const d
   return rc;
 }
 
+int hexed_b200_av_scale_velocity(hexed_b200_ctx* c, int restore) { return launch_av_scale_velocity(c, restore); }
+
+int hexed_b200_av_project_forcing(hexed_b200_ctx* c, const double* node_weights, const double* orthogonal)
+{
+  if (!node_weights || !orthogonal) return fail(c, HEXED_B200_BAD_ARGUMENT, "null operator");
+  return launch_av_project_forcing(c, node_weights, orthogonal);
+}
+
+int hexed_b200_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, const double* node_weights, double* residual)
+{
+  if (!node_weights || !residual) return fail(c, HEXED_B200_BAD_ARGUMENT, "null argument");
+  double sq = 0;
+  int rc = launch_av_finish(c, mult, us_max, n_real, node_weights, &sq);
+  if (!rc) *residual = sqrt(sq);
+  return rc;
+}
+
+int hexed_b200_interp_vertices(hexed_b200_ctx* c, int target, const double* vertex_values, const double* interp)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!vertex_values || !interp) return fail(c, HEXED_B200_BAD_ARGUMENT, "null argument");
+  double *d_vert = nullptr, *d_interp = nullptr;
+  const size_t nv = (size_t)c->n_elem*c->n_vert;
+  int rc = dev_alloc(c, &d_vert, nv, false);
+  if (!rc) rc = dev_alloc(c, &d_interp, (size_t)2*c->rs, false);
+  if (!rc && nv) rc = check(c, cudaMemcpyAsync(d_vert, vertex_values, sizeof(double)*nv, cudaMemcpyHostToDevice, c->stream), "upload vertex values");
+  if (!rc) rc = check(c, cudaMemcpyAsync(d_interp, interp, sizeof(double)*2*c->rs, cudaMemcpyHostToDevice, c->stream), "upload interpolation matrix");
+  if (!rc) rc = launch_interp_vertices(c, target, d_vert, d_interp);
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "interp_vertices");
+  dev_free(d_vert); dev_free(d_interp);
+  return rc;
+}
+
+int hexed_b200_av_swap(hexed_b200_ctx* c) { return launch_av_swap(c); }
+int hexed_b200_apply_aux_bcs(hexed_b200_ctx* c, int mode) { return launch_aux_bcs(c, mode); }
+
 int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
 {
   if (!admissible) return fail(c, HEXED_B200_BAD_ARGUMENT, "null result pointer");

@@ -159,6 +159,12 @@ int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
 int launch_set_jacobian(hexed_b200_ctx* c, const double* d_vert, const double* d_node_adj);
+int launch_av_scale_velocity(hexed_b200_ctx* c, int restore);
+int launch_av_project_forcing(hexed_b200_ctx* c, const double* weights, const double* orth);
+int launch_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, const double* node_weights, double* resid_sq);
+int launch_interp_vertices(hexed_b200_ctx* c, int target, const double* d_vert, const double* d_interp);
+int launch_av_swap(hexed_b200_ctx* c);
+int launch_aux_bcs(hexed_b200_ctx* c, int mode);
 
 /* Thread -> line-task map. In the dense [i][j][k] field layout that the bulk copies deliver, lines of dimension 0 (stride RS^2) are
  * conflict-free for consecutive lanes, but with 8-byte accesses consecutive lines of dimension 1 (stride RS) and 2 (stride 1) hit every

@@ -455,6 +455,75 @@ int launch_bcs(hexed_b200_ctx* c)
   return 0;
 }
 
+/* boundary loops of the artificial-viscosity and admissibility pipelines. mode:
+ *   HEXED_B200_BC_MODE_ADVECTION  Flow_bc::apply_advection on the wide (n_dim + row_size variable) faces, Solver.cpp:505-510:
+ *       default (src/Boundary_condition.cpp:24-41) velocity = inside, advected scalars = 2 - inside; Nonpenetration (:346-369) reflected
+ *       velocity, scalars copied; No_slip (:429-448) negated velocity, scalars copied; Copy (:460-463) = copy_state, which copies the
+ *       first 2*(n_dim + 2)*nfq doubles of the face storage
+ *   HEXED_B200_BC_MODE_COPY_STATE  Flow_bc::apply_diffusion (:43-52) for every kind (Solver::apply_avc_diff_bcs, Solver.cpp:83-91) and
+ *       the ghost copy inside fix_admissibility (Solver.cpp:1063-1068)
+ *   HEXED_B200_BC_MODE_NEGATE_FLUX  Flow_bc::flux_diffusion (:54-60) for every kind (Solver::apply_avc_diff_flux_bcs, Solver.cpp:93-101)
+ *       and Solver::apply_fta_flux_bcs (Solver.cpp:103-115) */
+__global__ void __launch_bounds__(256)
+aux_bc_kernel(int mode, int kind, int n, const int* inside, const int* ghost, const int* normal,
+              double* faces, double* faces_ldg, double* faces_wide, const double* normals, int nd, int rs, int nfq)
+{
+  const int nv = nd + 2, w = nv*nfq, ww = (nd + rs)*nfq;
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = (int)(gid/nfq), q = (int)(gid % nfq);
+  if (i >= n) return;
+  if (mode == HEXED_B200_BC_MODE_COPY_STATE) {
+    for (int v = 0; v < nv; ++v) faces[(size_t)ghost[i]*w + v*nfq + q] = faces[(size_t)inside[i]*w + v*nfq + q];
+    return;
+  }
+  if (mode == HEXED_B200_BC_MODE_NEGATE_FLUX) {
+    for (int v = 0; v < nv; ++v) faces_ldg[(size_t)ghost[i]*w + v*nfq + q] = -faces_ldg[(size_t)inside[i]*w + v*nfq + q];
+    return;
+  }
+  const double* in = faces_wide + (size_t)inside[i]*ww + q;
+  double* gh = faces_wide + (size_t)ghost[i]*ww + q;
+  if (kind == HEXED_B200_BC_COPY) {
+    const int n_copy = 2*nv < nd + rs ? 2*nv : nd + rs; // copy_state stops after 2*(n_dim + 2)*nfq doubles
+    for (int v = 0; v < n_copy; ++v) gh[v*nfq] = in[v*nfq];
+    return;
+  }
+  if (kind == HEXED_B200_BC_NONPENETRATION) {
+    const double* nr = normals + (size_t)normal[i]*nd*nfq + q;
+    double dot = 0., nsq = 0.;
+    for (int d = 0; d < nd; ++d) { const double nn = nr[d*nfq]; dot += in[d*nfq]*nn; nsq += nn*nn; }
+    for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq] - 2*dot*nr[d*nfq]/nsq;
+    for (int a = 0; a < rs; ++a) gh[(nd + a)*nfq] = in[(nd + a)*nfq];
+    return;
+  }
+  if (kind == HEXED_B200_BC_NO_SLIP) {
+    for (int d = 0; d < nd; ++d) gh[d*nfq] = -in[d*nfq];
+    for (int a = 0; a < rs; ++a) gh[(nd + a)*nfq] = in[(nd + a)*nfq];
+    return;
+  }
+  for (int d = 0; d < nd; ++d) gh[d*nfq] = in[d*nfq];
+  for (int a = 0; a < rs; ++a) gh[(nd + a)*nfq] = 2. - in[(nd + a)*nfq];
+}
+
+int launch_aux_bcs(hexed_b200_ctx* c, int mode)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (mode < HEXED_B200_BC_MODE_ADVECTION || mode > HEXED_B200_BC_MODE_NEGATE_FLUX) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary mode");
+  if (mode == HEXED_B200_BC_MODE_ADVECTION && !c->face_wide) return fail(c, HEXED_B200_BAD_ARGUMENT, "advection faces have not been allocated");
+  if (mode == HEXED_B200_BC_MODE_NEGATE_FLUX && !c->face_ldg) return fail(c, HEXED_B200_BAD_ARGUMENT, "LDG faces have not been allocated");
+  long long total_faces = 0;
+  for (auto& b : c->bcs) total_faces += b.n;
+  StatScope scope(c, ST_BC, total_faces);
+  for (auto& b : c->bcs) {
+    if (!b.n) continue;
+    const long long total = (long long)b.n*c->nfq;
+    HB_LAUNCH(aux_bc_kernel, (int)((total + 255)/256), 256, 0, c->stream, mode, b.kind, b.n, b.inside, b.ghost, b.normal,
+              c->face_state, c->face_ldg, c->face_wide, c->normals, c->nd, c->rs, c->nfq);
+    count_launch(c, ST_BC);
+    HB_CUDA(c, cudaGetLastError());
+  }
+  return 0;
+}
+
 /* flux boundary conditions: Solver::apply_flux_bcs (reference src/Solver.cpp:69-81) */
 __global__ void __launch_bounds__(256)
 flux_bc_kernel(int kind, int n, const int* inside, const int* ghost, const int* normal, const double* params, const double* cache,

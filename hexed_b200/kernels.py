@@ -92,6 +92,12 @@ SIGNATURES = {
     "hexed_b200_pde_kernel": [C.c_void_p, C.c_int, C.c_int, C.c_int, Options, Transport, Transport, C.c_double, C.c_double],
     "hexed_b200_apply_flux_bcs": [C.c_void_p],
     "hexed_b200_set_jacobian": [C.c_void_p, dp, dp],
+    "hexed_b200_av_scale_velocity": [C.c_void_p, C.c_int],
+    "hexed_b200_av_project_forcing": [C.c_void_p, dp, dp],
+    "hexed_b200_av_finish": [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp],
+    "hexed_b200_interp_vertices": [C.c_void_p, C.c_int, dp, dp],
+    "hexed_b200_av_swap": [C.c_void_p],
+    "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
     "hexed_b200_download_record": [C.c_void_p, ip, C.c_int, C.c_int],
     "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
@@ -154,6 +160,9 @@ def _addr(a):
         return a.ctypes.data
     assert a.is_contiguous() and str(a.dtype) == "torch.float64"
     return a.data_ptr()
+
+
+BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX = 0, 1, 2  # include/hexed_b200.h
 
 
 class Device:
@@ -401,6 +410,32 @@ class Device:
 
     def apply_flux_bcs(self):
         self._check(self.lib.hexed_b200_apply_flux_bcs(self.ctx))
+
+    # ---- pointwise loops of the artificial-viscosity pipelines (reference src/Solver.cpp:457-581, 1021-1038) ----
+    def av_scale_velocity(self, restore=False):
+        self._check(self.lib.hexed_b200_av_scale_velocity(self.ctx, int(restore)))
+
+    def av_project_forcing(self, node_weights, orthogonal):
+        w = np.ascontiguousarray(node_weights, dtype=np.float64); o = np.ascontiguousarray(orthogonal, dtype=np.float64)
+        self._check(self.lib.hexed_b200_av_project_forcing(self.ctx, w.ctypes.data_as(dp), o.ctypes.data_as(dp)))
+
+    def av_finish(self, mult, us_max, n_real, node_weights):
+        w = np.ascontiguousarray(node_weights, dtype=np.float64)
+        out = C.c_double(0.)
+        self._check(self.lib.hexed_b200_av_finish(self.ctx, float(mult), float(us_max), int(n_real), w.ctypes.data_as(dp),
+                                                  C.cast(C.byref(out), dp)))
+        return out.value
+
+    def interp_vertices(self, target, vertex_values, interp):
+        v = np.ascontiguousarray(vertex_values, dtype=np.float64); i = np.ascontiguousarray(interp, dtype=np.float64)
+        self._check(self.lib.hexed_b200_interp_vertices(self.ctx, int(target), v.ctypes.data_as(dp), i.ctypes.data_as(dp)))
+
+    def apply_aux_bcs(self, mode):
+        """BC_MODE_ADVECTION / BC_MODE_COPY_STATE / BC_MODE_NEGATE_FLUX: boundary loops of the AV and admissibility pipelines"""
+        self._check(self.lib.hexed_b200_apply_aux_bcs(self.ctx, int(mode)))
+
+    def av_swap(self):
+        self._check(self.lib.hexed_b200_av_swap(self.ctx))
 
     def set_jacobian(self, vertex_pos, node_adj=None):
         """element loop of Solver::calc_jacobian (reference src/Solver.cpp:281-286, src/Deformed_element.cpp:60-136): vertex_pos

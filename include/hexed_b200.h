@@ -214,6 +214,29 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 int hexed_b200_is_admissible(hexed_b200_ctx* ctx, int* admissible);
 int hexed_b200_download_record(hexed_b200_ctx* ctx, int* dst, int first_elem, int n_elem);
 
+/* ---- pointwise loops around the artificial-viscosity kernels: the host loops of
+ * Solver::update_art_visc_smoothness (src/Solver.cpp:457-581), fix_admissibility (:1021-1038,1080-1086), set_art_visc_admis (:636-658)
+ * and update_art_visc_elwise (:625-633), so that those pipelines can run with the state resident on the device.
+ *   av_scale_velocity(restore = 0 | 1)   momentum /= | *= sqrt(2*mass*energy)                      (:467-478 | :567-571)
+ *   av_project_forcing(w, orth)          forcing[0] = (sum_i advection_state_i*w_i*orth_i)^2*2*energy/mass, w = Basis::node_weights(),
+ *                                        orth = Basis::orthogonal(row_size - 1)                   (:527-541)
+ *   av_finish(mult, us_max, n_real, w, &residual)  f = mult*forcing[n_real]; bulk_av_coef = us_max*f/(us_max + f); velocity restored;
+ *                                        residual = sqrt(sum (old - new)^2 * quadrature weight * nominal_size^n_dim)  (:551-573)
+ *   interp_vertices(target, vertex_values[n_elem][2^n_dim], interp[row_size][2])  math::hypercube_matvec(interp, vertex values) into
+ *                                        bulk_av_coef (target 0) or laplacian_av_coef (target 1)   (:652-656, :1021-1031)
+ *   av_swap()                            swap bulk_av_coef and laplacian_av_coef                    (:1032-1038) ---- */
+int hexed_b200_av_scale_velocity(hexed_b200_ctx* ctx, int restore);
+int hexed_b200_av_project_forcing(hexed_b200_ctx* ctx, const double* node_weights, const double* orthogonal);
+int hexed_b200_av_finish(hexed_b200_ctx* ctx, double mult, double us_max, int n_real, const double* node_weights, double* residual);
+int hexed_b200_interp_vertices(hexed_b200_ctx* ctx, int target, const double* vertex_values, const double* interp);
+int hexed_b200_av_swap(hexed_b200_ctx* ctx);
+/* the boundary loops of the same pipelines for the boundary conditions registered with hexed_b200_bc_create:
+ *   MODE_ADVECTION    Flow_bc::apply_advection and its overrides (src/Boundary_condition.cpp:24-41,346-369,429-448,460-463), Solver.cpp:505-510
+ *   MODE_COPY_STATE   Flow_bc::apply_diffusion (:43-52; Solver::apply_avc_diff_bcs, Solver.cpp:83-91) and the ghost copy of :1063-1068
+ *   MODE_NEGATE_FLUX  Flow_bc::flux_diffusion (:54-60; Solver::apply_avc_diff_flux_bcs, Solver.cpp:93-101) and apply_fta_flux_bcs (:103-115) */
+enum { HEXED_B200_BC_MODE_ADVECTION = 0, HEXED_B200_BC_MODE_COPY_STATE = 1, HEXED_B200_BC_MODE_NEGATE_FLUX = 2 };
+int hexed_b200_apply_aux_bcs(hexed_b200_ctx* ctx, int mode);
+
 /* ---- metric terms on the device: the element loop of Solver::calc_jacobian (src/Solver.cpp:281-286), i.e.
  * Deformed_element::set_jacobian (src/Deformed_element.cpp:60-136, positions by :15-58 including the face-warping node adjustments)
  * for every deformed element and Element::set_jacobian (src/Element.cpp:99-112) for every Cartesian one. Host inputs:

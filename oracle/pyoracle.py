@@ -440,3 +440,97 @@ def set_jacobian(vert, node_adj, nom, basis):
             norm_sum += np.sqrt(sum(vn[i*nd + j, iv]**2 for j in range(nd)))
         vtss[iv] = nom*vd[iv]/norm_sum
     return dict(jac=jac, ref_normals=refn, det=det, face_normals=fn, vertex_tss=vtss, pos=pos)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pointwise loops of the artificial-viscosity pipelines, numpy on a FlatMesh. TEST INFRASTRUCTURE.
+# ---------------------------------------------------------------------------------------------------------------------
+def av_scale_velocity(m, restore=False):
+    """reference src/Solver.cpp:467-478 (restore: :567-571)"""
+    nd = m.n_dim
+    st = m.state()
+    scale = np.sqrt(2*st[:, nd]*st[:, nd + 1])
+    for d in range(nd):
+        st[:, d] = st[:, d]*scale if restore else st[:, d]/scale
+
+
+def av_project_forcing(m, weights, orth):
+    """reference src/Solver.cpp:527-541"""
+    nd, rs = m.n_dim, m.row_size
+    adv = m.elem_data[:, nd + 9:nd + 9 + rs]
+    proj = np.zeros_like(adv[:, 0])
+    for i in range(rs):
+        proj = proj + adv[:, i]*weights[i]*orth[i]
+    st = m.state()
+    m.elem_data[:, nd + 5] = proj*proj*2*st[:, nd + 1]/st[:, nd]
+
+
+def av_finish(m, mult, us_max, n_real, weights):
+    """reference src/Solver.cpp:551-573; returns art_visc_residual"""
+    nd, rs, nq = m.n_dim, m.row_size, m.nq
+    wq = np.ones(nq)
+    q = np.arange(nq)
+    for d in range(nd):
+        wq = wq*np.asarray(weights)[(q//rs**(nd - 1 - d)) % rs]
+    f = mult*m.elem_data[:, nd + 5 + n_real]
+    new_av = us_max*f/(us_max + f)
+    vol = np.asarray(m.nom_size)**nd
+    resid = (((m.elem_data[:, nd + 3] - new_av)**2)*wq[None, :]*vol[:, None]).sum()
+    m.elem_data[:, nd + 3] = new_av
+    av_scale_velocity(m, restore=True)
+    return float(np.sqrt(resid))
+
+
+def interp_vertices(m, target, vertex_values, interp):
+    """math::hypercube_matvec(interp, vertex values) -> bulk (0) or laplacian (1) AV coefficient (reference src/Solver.cpp:652-656,1021-1031)"""
+    nd, rs, nq = m.n_dim, m.row_size, m.nq
+    interp = np.asarray(interp).reshape(rs, 2)
+    for e in range(m.n_elem):
+        v = np.asarray(vertex_values[e], dtype=np.float64).copy()
+        for d in range(nd - 1, -1, -1):
+            v = _dimension_matvec(interp, v, d)
+        m.elem_data[e, nd + 3 + target] = v
+
+
+def av_swap(m):
+    nd = m.n_dim
+    tmp = m.elem_data[:, nd + 3].copy()
+    m.elem_data[:, nd + 3] = m.elem_data[:, nd + 4]
+    m.elem_data[:, nd + 4] = tmp
+
+
+def apply_aux_bcs(m, mode):
+    """boundary loops of the AV / admissibility pipelines, numpy (TEST INFRASTRUCTURE). mode 0: Flow_bc::apply_advection and overrides
+    (reference src/Boundary_condition.cpp:24-41,346-369,429-448,460-463) on the wide faces; 1: Flow_bc::apply_diffusion (:43-52) /
+    the ghost copy of Solver.cpp:1063-1068; 2: Flow_bc::flux_diffusion (:54-60) / Solver::apply_fta_flux_bcs (Solver.cpp:103-115)"""
+    from hexed_b200.mesh import BC_COPY, BC_NONPENETRATION, BC_NO_SLIP
+    nd, rs, nfq, nv = m.n_dim, m.row_size, m.nfq, m.n_dim + 2
+    for bc in m.bcs:
+        ins, gh = bc["inside_slot"], bc["ghost_slot"]
+        if ins.size == 0:
+            continue
+        if mode == 1:
+            m.face_state[gh] = m.face_state[ins]
+        elif mode == 2:
+            m.face_ldg[gh] = -m.face_ldg[ins]
+        else:
+            f = m.face_wide[ins].reshape(-1, nd + rs, nfq)
+            g = m.face_wide[gh].reshape(-1, nd + rs, nfq).copy()
+            if bc["kind"] == BC_COPY:
+                n_copy = min(2*nv, nd + rs)
+                g[:, :n_copy] = f[:, :n_copy]
+            elif bc["kind"] == BC_NONPENETRATION:
+                n = m.normals[bc["normal_slot"]]
+                dot = np.zeros((ins.size, nfq)); nsq = np.zeros((ins.size, nfq))
+                for d in range(nd):
+                    dot = dot + f[:, d]*n[:, d]; nsq = nsq + n[:, d]*n[:, d]
+                for d in range(nd):
+                    g[:, d] = f[:, d] - 2*dot*n[:, d]/nsq
+                g[:, nd:] = f[:, nd:]
+            elif bc["kind"] == BC_NO_SLIP:
+                g[:, :nd] = -f[:, :nd]
+                g[:, nd:] = f[:, nd:]
+            else:
+                g[:, :nd] = f[:, :nd]
+                g[:, nd:] = 2. - f[:, nd:]
+            m.face_wide[gh] = g.reshape(ins.size, -1)

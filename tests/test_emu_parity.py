@@ -154,3 +154,23 @@ def test_set_jacobian(emu_lib, nd, rs):
     """metric terms of deformed elements computed on the device from vertex positions and node adjustments"""
     from util import check_set_jacobian
     check_set_jacobian(emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 4), (2, 3), (3, 3)])
+def test_av_glue(emu_lib, nd, rs):
+    """pointwise loops of the artificial-viscosity pipelines on the device"""
+    from util import check_av_glue
+    check_av_glue(emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 3), (3, 2)])
+def test_aux_bcs(emu_lib, nd, rs):
+    from util import check_aux_bcs
+    check_aux_bcs(emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 3), (3, 2)])
+def test_av_smoothness_pipeline(oracle, emu_lib, nd, rs):
+    """the naca0012-class configuration's shock-capturing update, Solver::update_art_visc_smoothness, with no host loop left"""
+    from util import check_av_pipeline
+    check_av_pipeline(oracle, emu_lib, nd, rs)

@@ -345,3 +345,134 @@ def check_set_jacobian(lib, nd, rs, seed=21):
         for j in range(nd):
             assert np.all(fc[:, f, j] == (1. if f//2 == j else 0.))
     assert np.all(fc[:, :, nd:] == 7.) and np.all(vtss[:n_car] == 1.)
+
+
+def check_av_glue(lib, nd, rs, seed=8):
+    """SURVEY section 8 f-3: the pointwise loops of Solver::update_art_visc_smoothness / fix_admissibility on the device against their
+    numpy restatements, chained in the order the Solver runs them"""
+    import pyoracle
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=6, n_def=9, n_ref=0)
+    M.random_flow_state(m, rng)
+    m.elem_data[:, nd + 3:nd + 5] = rng.uniform(0., 2e-3, (m.n_elem, 2, m.nq))          # AV coefficients
+    m.elem_data[:, nd + 5:nd + 9] = rng.uniform(0., 1e-3, (m.n_elem, 4, m.nq))          # forcing
+    m.elem_data[:, nd + 9:nd + 9 + rs] = rng.normal(1., .3, (m.n_elem, rs, m.nq))       # advection state
+    m.nom_size = rng.choice([.25, .5, 1.], m.n_elem)
+    w = np.asarray(basis.weight); orth = np.asarray(basis.orthogonal).reshape(rs, rs)[rs - 1]  # Basis::orthogonal(row_size - 1)
+    vert = rng.uniform(0., 1., (m.n_elem, 2**nd))
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    # update_art_visc_smoothness: normalise, (advection kernels), project, (diffusion kernels), finish
+    dev.av_scale_velocity(); pyoracle.av_scale_velocity(ref)
+    dev.av_project_forcing(w, orth); pyoracle.av_project_forcing(ref, w, orth)
+    got = dev.av_finish(0.7, 3e-3, 3, w); want = pyoracle.av_finish(ref, 0.7, 3e-3, 3, w)
+    assert abs(got - want) <= 1e-12*abs(want), (got, want)
+    # fix_admissibility: vertex factors -> laplacian AV coefficient, swapped with the bulk coefficient
+    dev.interp_vertices(1, vert, interp); pyoracle.interp_vertices(ref, 1, vert, interp)
+    dev.av_swap(); pyoracle.av_swap(ref)
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    for name, lo, hi in (("state", 0, nd + 2), ("av", nd + 3, nd + 5), ("forcing", nd + 5, nd + 9)):
+        assert rel_l2(out.elem_data[:, lo:hi], ref.elem_data[:, lo:hi]) <= 1e-14, name
+    assert rel_l2(out.state(), m.state()) <= 1e-14  # the velocity normalisation is undone exactly to rounding
+
+
+def check_aux_bcs(lib, nd, rs, seed=13):
+    """the boundary loops of the AV / admissibility pipelines (advection ghosts on the wide faces, diffusion state copy, negated
+    LDG flux) for every registered boundary-condition kind"""
+    import pyoracle
+    from hexed_b200.kernels import BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=10, n_def=24, n_ref=2, with_ldg=True, with_wide=True)
+    M.random_flow_state(m, rng)
+    mixed_bcs(m, rng)
+    m.face_state[:] = rng.normal(0., 1., m.face_state.shape)
+    m.face_ldg[:] = rng.normal(0., 1., m.face_ldg.shape)
+    m.face_wide[:] = rng.normal(0., 1., m.face_wide.shape)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    for mode in (BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX):
+        dev.apply_aux_bcs(mode)
+        pyoracle.apply_aux_bcs(ref, mode)
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert np.array_equal(out.face_state, ref.face_state) and np.array_equal(out.face_ldg, ref.face_ldg)
+    assert rel_l2(out.face_wide, ref.face_wide) <= 1e-15
+    assert not np.array_equal(out.face_wide, m.face_wide)
+
+
+def check_av_pipeline(oracle, lib, nd, rs, seed=17, advect_iters=2, diff_iters=1, n_cheby=2):
+    """Solver::update_art_visc_smoothness (reference src/Solver.cpp:457-581, with diffuse_art_visc :428-455) end to end with nothing on
+    the host: velocity normalisation, advection pseudo-iterations with their ghost fill, Legendre projection into the forcing, smoothing
+    iterations with their state / flux ghosts, AV coefficient + residual + velocity restore, final write_face / prolong. Device calls
+    against the oracle's kernels and the numpy restatements of the glue, same order, same parameters."""
+    import pyoracle
+    from pyoracle import ADVECTION, SMOOTH_AV
+    from hexed_b200.kernels import BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=8, n_def=16, n_ref=2, with_ldg=True, with_wide=True)
+    M.random_flow_state(m, rng)
+    mixed_bcs(m, rng)
+    m.elem_data[:, nd + 9:nd + 9 + rs] = 1.   # advection state starts at 1 (the ghosts' "2 - inside" keeps it there)
+    m.elem_data[:, nd + 3] = rng.uniform(0., 1e-3, (m.n_elem, m.nq))
+    advect_length, adv_safety, diff_safety = 0.3, 0.5, 0.4
+    n_real = 3
+    diff_time = 0.5*advect_length*advect_length/n_real
+    mult, us_max = 0.8*advect_length, advect_length*0.2*np.sqrt(2*2.5e5/1.2)
+    w = np.asarray(basis.weight); orth = np.asarray(basis.orthogonal).reshape(rs, rs)[rs - 1]
+
+    def cheby(n, i):  # math::chebyshev_step, reference src/math.cpp:104-107
+        return 1/(1 - np.cos((n - i - .5)*np.pi/n))
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    # -- oracle
+    pyoracle.av_scale_velocity(ref)
+    oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref)
+    oracle.max_dt(ADVECTION, basis, ref, adv_safety, 1., True, advect_length=advect_length)
+    for _ in range(advect_iters):
+        oracle.compute_write_face(basis, ref, pde=ADVECTION); oracle.compute_prolong(basis, ref, pde=ADVECTION)
+        for i in (0, 1):
+            pyoracle.apply_aux_bcs(ref, BC_MODE_ADVECTION)
+            oracle.compute_advection(basis, ref, advect_length, dt=1., i_stage=i)
+    pyoracle.av_project_forcing(ref, w, orth)
+    oracle.max_dt(SMOOTH_AV, basis, ref, 1., diff_safety, True)
+    oracle.compute_write_face(basis, ref, pde=SMOOTH_AV); oracle.compute_prolong(basis, ref)
+    for _ in range(diff_iters):
+        for ic in range(n_cheby):
+            sc = cheby(n_cheby, ic)
+            pyoracle.apply_aux_bcs(ref, BC_MODE_COPY_STATE)
+            oracle.compute_smooth_av(basis, ref, lambda: pyoracle.apply_aux_bcs(ref, BC_MODE_NEGATE_FLUX), diff_time, sc, dt=sc, i_stage=0)
+    want = pyoracle.av_finish(ref, mult, us_max, n_real, w)
+    oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref)
+    # -- device
+    dev.av_scale_velocity()
+    dev.compute_write_face(); dev.compute_prolong()
+    dev.max_dt_advection(adv_safety, 1., True, advect_length)
+    for _ in range(advect_iters):
+        dev.compute_write_face_advection(); dev.compute_prolong_advection()
+        for i in (0, 1):
+            dev.apply_aux_bcs(BC_MODE_ADVECTION)
+            dev.compute_advection(advect_length, dt=1., i_stage=i)
+    dev.av_project_forcing(w, orth)
+    dev.max_dt_smooth_av(1., diff_safety, True)
+    dev.compute_write_face_smooth_av(); dev.compute_prolong()
+    for _ in range(diff_iters):
+        for ic in range(n_cheby):
+            sc = cheby(n_cheby, ic)
+            dev.apply_aux_bcs(BC_MODE_COPY_STATE)
+            dev.compute_smooth_av(lambda: dev.apply_aux_bcs(BC_MODE_NEGATE_FLUX), diff_time, sc, dt=sc, i_stage=0)
+    got = dev.av_finish(mult, us_max, n_real, w)
+    dev.compute_write_face(); dev.compute_prolong()
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert np.isfinite(want) and want > 0 and abs(got - want) <= 1e-10*want, (got, want)
+    assert_pde_parity(out, ref, [])
+    assert rel_l2(out.state(), m.state()) <= 1e-13          # the flow state comes back as it was found
+    assert not np.array_equal(out.elem_data[:, nd + 3], m.elem_data[:, nd + 3])
