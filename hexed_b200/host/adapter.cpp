@@ -603,6 +603,72 @@ bool is_admissible(Kernel_mesh km, std::vector<int>* record)
   return ok != 0;
 }
 
+// ---- pointwise loops of the artificial-viscosity pipelines ----
+namespace
+{
+std::vector<double> weights_of(const hexed::Basis& b)
+{
+  auto w = b.node_weights();
+  std::vector<double> out(b.row_size);
+  for (int i = 0; i < b.row_size; ++i) out[i] = w(i);
+  return out;
+}
+}
+
+void av_scale_velocity(Kernel_mesh km, bool restore)
+{ // src/Solver.cpp:467-478 | :567-571
+  Call call(km, state, state);
+  check(&call.m, hexed_b200_av_scale_velocity(call.m.ctx, restore));
+  call.finish();
+}
+
+void av_project_forcing(Kernel_mesh km)
+{ // src/Solver.cpp:527-541
+  Call call(km, state | advection | art_visc, art_visc);
+  auto w = weights_of(km.basis);
+  auto o = km.basis.orthogonal(km.row_size - 1);
+  std::vector<double> orth(km.row_size);
+  for (int i = 0; i < km.row_size; ++i) orth[i] = o(i);
+  check(&call.m, hexed_b200_av_project_forcing(call.m.ctx, w.data(), orth.data()));
+  call.finish();
+}
+
+double av_finish(Kernel_mesh km, double mult, double us_max, int n_real)
+{ // src/Solver.cpp:551-573
+  Call call(km, state | art_visc, state | art_visc);
+  auto w = weights_of(km.basis);
+  double resid = 0;
+  check(&call.m, hexed_b200_av_finish(call.m.ctx, mult, us_max, n_real, w.data(), &resid));
+  call.finish();
+  return resid;
+}
+
+void interp_vertices(Kernel_mesh km, int target, const std::vector<double>& vertex_values)
+{ // math::hypercube_matvec(interp, .) of src/Solver.cpp:652-656, :1021-1031 with interp = [1 - node, node]
+  Call call(km, art_visc, art_visc);
+  std::vector<double> interp(size_t(2)*km.row_size);
+  for (int i = 0; i < km.row_size; ++i) {interp[2*i] = 1. - km.basis.node(i); interp[2*i + 1] = km.basis.node(i);}
+  if (vertex_values.size() != call.m.tab.elem.size()*size_t(ipow(2, km.n_dim))) throw std::runtime_error("hexed_b200: interp_vertices: one value per element vertex expected");
+  check(&call.m, hexed_b200_interp_vertices(call.m.ctx, target, vertex_values.data(), interp.data()));
+  call.finish();
+}
+
+void av_swap(Kernel_mesh km)
+{ // src/Solver.cpp:1032-1038
+  Call call(km, art_visc, art_visc);
+  check(&call.m, hexed_b200_av_swap(call.m.ctx));
+  call.finish();
+}
+
+void apply_aux_bcs(Kernel_mesh km, int mode)
+{
+  const unsigned grp = mode == HEXED_B200_BC_MODE_ADVECTION ? unsigned(faces_wide) : unsigned(faces);
+  Call call(km, grp, grp);
+  check(&call.m, hexed_b200_apply_aux_bcs(call.m.ctx, mode));
+  call.m.device_bcs_ran = true;
+  call.finish();
+}
+
 void apply_flux_bcs(Kernel_mesh km)
 {
   Call call(km, faces, faces);

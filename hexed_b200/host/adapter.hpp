@@ -68,6 +68,18 @@ int add_device_bc(hexed::Kernel_mesh, int kind, const std::vector<double*>& insi
 void apply_state_bcs(hexed::Kernel_mesh);
 void apply_flux_bcs(hexed::Kernel_mesh);
 
+/*! \brief the pointwise loops `Solver::update_art_visc_smoothness` (src/Solver.cpp:457-581), `fix_admissibility` (:1021-1038) and
+ * `set_art_visc_admis` (:636-658) wrap around the kernels, on the device, so those pipelines run in `resident` mode
+ * without moving the state: see include/hexed_b200.h for the arithmetic of each. `apply_aux_bcs(mesh, HEXED_B200_BC_MODE_*)` stands in
+ * for the `flow_bc->apply_advection` loop (:505-510), `apply_avc_diff_bcs` / `apply_avc_diff_flux_bcs` (:83-101) and `apply_fta_flux_bcs`
+ * (:103-115) for the boundary conditions registered with `add_device_bc`. */
+void av_scale_velocity(hexed::Kernel_mesh, bool restore);
+void av_project_forcing(hexed::Kernel_mesh);
+double av_finish(hexed::Kernel_mesh, double mult, double us_max, int n_real); //!< returns `art_visc_residual`
+void interp_vertices(hexed::Kernel_mesh, int target, const std::vector<double>& vertex_values); //!< target 0 bulk / 1 laplacian AV coefficient
+void av_swap(hexed::Kernel_mesh);
+void apply_aux_bcs(hexed::Kernel_mesh, int mode);
+
 /*! \brief `Solver::is_admissible` (src/Solver.cpp:921-958) on the device: the check Solver::update makes after every
  * stage. Returns what the reference returns; `record`, if given, receives `Element::record` of every element in `Kernel_mesh::elems` order
  * (1 = inadmissible), which `fix_admissibility` spreads to the vertices. Throws `std::runtime_error("state is not finite")` like the

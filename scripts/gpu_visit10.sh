@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU visit 10: parity tests, racecheck of the aliased Navier-Stokes Local kernel, NS bench lines with three resident CTAs per SM, ncu
-TAG=${1:-r01j}
+TAG=${1:-r01k}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 600 compute-sanitizer --tool racecheck --racecheck-report all python -m pytest tests/test_gpu_parity.py -q -x -k "navier_stokes_3d_line_kernel" > gpurun_out/racecheck_ns.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/racecheck_ns.log
