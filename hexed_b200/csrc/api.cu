@@ -40,7 +40,8 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
   dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
   dev_free(c->cfl_approx); invalidate_cfl_cache(c); c->tss_is_one = false;
-  dev_free(c->record);
+  dev_free(c->record); dev_free(c->elem_vertex); dev_free(c->matchers); dev_free(c->vertex_vals); dev_free(c->vertex_scratch);
+  c->n_vertex = c->n_match = 0;
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
   for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
   c->lists.clear();
@@ -275,6 +276,7 @@ static int array_info(hexed_b200_ctx* c, int which, double*** arr, size_t* item,
     case HEXED_B200_FACE_WIDE: *arr = &c->face_wide; *item = (size_t)(c->nd + c->rs)*nfq; *count = c->n_face_slot; break;
     case HEXED_B200_NORMALS: *arr = &c->normals; *item = c->nd*nfq; *count = c->n_normal_slot; break;
     case HEXED_B200_UNCERT: *arr = &c->uncert; *item = 1; *count = c->n_elem; break;
+    case HEXED_B200_VERTEX_SCRATCH: *arr = &c->vertex_scratch; *item = c->n_vert; *count = c->n_elem; break;
     default: return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown array id");
   }
   if (!**arr && alloc) { int rc = dev_alloc(c, *arr, (*item)*(*count)); if (rc) return rc; }
@@ -740,6 +742,53 @@ int hexed_b200_interp_vertices(hexed_b200_ctx* c, int target, const double* vert
 
 int hexed_b200_av_swap(hexed_b200_ctx* c) { return launch_av_swap(c); }
 int hexed_b200_apply_aux_bcs(hexed_b200_ctx* c, int mode) { return launch_aux_bcs(c, mode); }
+
+int hexed_b200_vertex_topology(hexed_b200_ctx* c, const int* elem_vertex, int n_vertex, const int* matchers, int n_match)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (n_vertex < 0 || n_match < 0 || (c->n_elem && !elem_vertex) || (n_match && !matchers)) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad vertex topology");
+  const size_t n = (size_t)c->n_elem*c->n_vert;
+  for (size_t i = 0; i < n; ++i) if (elem_vertex[i] < 0 || elem_vertex[i] >= n_vertex) return fail(c, HEXED_B200_BAD_ARGUMENT, "vertex id out of range");
+  for (int i = 0; i < n_match; ++i) {
+    const int* row = matchers + (size_t)i*8;
+    if (row[0] < 0 || row[0] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "hanging vertex matcher: bad dimension");
+    for (int k = 0; k < 4; ++k) if (row[4 + k] >= c->n_elem) return fail(c, HEXED_B200_BAD_ARGUMENT, "hanging vertex matcher: element out of range");
+  }
+  dev_free(c->elem_vertex); dev_free(c->matchers); dev_free(c->vertex_vals);
+  int rc = dev_alloc(c, &c->elem_vertex, n, false);
+  if (!rc) rc = dev_alloc(c, &c->matchers, (size_t)n_match*8, false);
+  if (!rc) rc = dev_alloc(c, &c->vertex_vals, (size_t)n_vertex, true);
+  if (!rc && n) rc = check(c, cudaMemcpyAsync(c->elem_vertex, elem_vertex, sizeof(int)*n, cudaMemcpyHostToDevice, c->stream), "upload vertex ids");
+  if (!rc && n_match) rc = check(c, cudaMemcpyAsync(c->matchers, matchers, sizeof(int)*8*n_match, cudaMemcpyHostToDevice, c->stream), "upload matchers");
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "vertex_topology");
+  if (rc) return rc;
+  c->n_vertex = n_vertex; c->n_match = n_match;
+  return 0;
+}
+
+int hexed_b200_share_vertex_data(hexed_b200_ctx* c, int which, int op)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (op != 0 && op != 1) return fail(c, HEXED_B200_BAD_ARGUMENT, "op must be 0 (min) or 1 (max)");
+  double** arr; size_t item, count;
+  if (which != HEXED_B200_VERTEX_TSS && which != HEXED_B200_VERTEX_SCRATCH) return fail(c, HEXED_B200_BAD_ARGUMENT, "not a per-vertex array");
+  int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
+  if (which == HEXED_B200_VERTEX_TSS) invalidate_cfl_cache(c);
+  return launch_share_vertex_data(c, *arr, op);
+}
+
+int hexed_b200_fix_admis_spread(hexed_b200_ctx* c, const double* interp)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!interp) return fail(c, HEXED_B200_BAD_ARGUMENT, "null interpolation matrix");
+  double* d_interp = nullptr;
+  int rc = dev_alloc(c, &d_interp, (size_t)2*c->rs, false);
+  if (!rc) rc = check(c, cudaMemcpyAsync(d_interp, interp, sizeof(double)*2*c->rs, cudaMemcpyHostToDevice, c->stream), "upload interpolation matrix");
+  if (!rc) rc = launch_fix_admis_spread(c, d_interp);
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "fix_admis_spread");
+  dev_free(d_interp);
+  return rc;
+}
 
 int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
 {

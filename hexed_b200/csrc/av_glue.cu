@@ -226,4 +226,139 @@ int launch_av_swap(hexed_b200_ctx* c)
   return 0;
 }
 
+/* ---------------- Solver::share_vertex_data (reference src/Solver.cpp:35-54) ----------------
+ * Every mesh vertex reduces (min or max) the values its elements hold for it (Element::push_shareable_value / fetch_shareable_value,
+ * src/Element.cpp:149-161), then every Hanging_vertex_matcher overwrites the vertices of its fine elements that lie on the coarse
+ * face with the multilinear interpolant of the coarse corners (src/Hanging_vertex_matcher.cpp:13-41). The vertex connectivity is not
+ * part of Kernel_mesh: the caller provides it once per mesh epoch (hexed_b200_vertex_topology). */
+__device__ __forceinline__ void atomic_minmax(double* addr, double v, int is_max)
+{
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (true) {
+    const double cur = __longlong_as_double((long long)old);
+    if (is_max ? !(v > cur) : !(v < cur)) return;
+    const unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) return;
+    old = prev;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_double_kernel(double* dst, int n, double value)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
+}
+
+__global__ void __launch_bounds__(256)
+vertex_reduce_kernel(const double* elem_vals, const int* elem_vertex, long long n, double* vertex_vals, int is_max)
+{
+  const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) atomic_minmax(vertex_vals + elem_vertex[i], elem_vals[i], is_max);
+}
+
+__global__ void __launch_bounds__(256)
+vertex_fetch_kernel(double* elem_vals, const int* elem_vertex, long long n, const double* vertex_vals)
+{
+  const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) elem_vals[i] = vertex_vals[elem_vertex[i]];
+}
+
+/* one thread per Hanging_vertex_matcher; row = {i_dim, is_positive, stretch0, stretch1, fine element 0..3 (-1 = unused)} */
+__global__ void __launch_bounds__(128)
+hanging_vertex_kernel(double* elem_vals, const int* matchers, int n_match, int nd)
+{
+  const int im = blockIdx.x*blockDim.x + threadIdx.x;
+  if (im >= n_match) return;
+  const int* row = matchers + (size_t)im*8;
+  const int id = row[0], isp = row[1];
+  const int str[2] = {row[2], row[3]};
+  const int n_vert = 1 << (nd - 1), n_vert_elem = 1 << nd;
+  int n_fine = 0;
+  for (int i = 0; i < 4; ++i) if (row[4 + i] >= 0) ++n_fine;
+  int inds[4]; double values[4];
+  const int stride = 1 << (nd - 1 - id);
+  for (int iv = 0; iv < n_vert; ++iv) {
+    inds[iv] = iv/stride*stride*2 + iv % stride + isp*stride;
+    // math::stretched_ind (include/math.hpp:188-199): collapse the face-vertex index along stretched dimensions
+    int si = 0, st = 1;
+    for (int d = nd - 2; d >= 0; --d) {
+      const int bit = (iv >> (nd - 2 - d)) & 1;
+      if (!str[d]) { si += bit*st; st *= 2; }
+    }
+    values[iv] = elem_vals[(size_t)row[4 + si]*n_vert_elem + inds[iv]];
+  }
+  // hypercube_matvec of the 3 x 2 matrix {{1, 0}, {.5, .5}, {0, 1}}: corners and midpoints, 3 [x 3] values
+  double interp[9];
+  if (nd == 1) interp[0] = values[0];
+  else if (nd == 2) { interp[0] = values[0]; interp[1] = .5*values[0] + .5*values[1]; interp[2] = values[1]; }
+  else {
+    double rowv[2][3];
+    for (int a = 0; a < 2; ++a) { rowv[a][0] = values[2*a]; rowv[a][1] = .5*values[2*a] + .5*values[2*a + 1]; rowv[a][2] = values[2*a + 1]; }
+    for (int b = 0; b < 3; ++b) { interp[b] = rowv[0][b]; interp[3 + b] = .5*rowv[0][b] + .5*rowv[1][b]; interp[6 + b] = rowv[1][b]; }
+  }
+  for (int ie = 0; ie < n_fine; ++ie) {
+    for (int iv = 0; iv < n_vert; ++iv) {
+      int k = nd >= 2 ? (ie*!str[nd - 2]) % 2 + (iv % 2)*(1 + str[nd - 2]) : 0;
+      if (nd == 3) k += ((ie*!str[0])/(1 + !str[1]) + iv/2*(1 + str[0]))*3;
+      elem_vals[(size_t)row[4 + ie]*n_vert_elem + inds[iv]] = interp[k];
+    }
+  }
+}
+
+/* element's own record -> every vertex of the element (Solver.cpp:1000-1006) */
+__global__ void __launch_bounds__(256)
+record_to_vertices_kernel(const int* record, double* elem_vals, long long n, int n_vert)
+{
+  const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) elem_vals[i] = record[i/n_vert];
+}
+
+/* every vertex of an element takes the element's maximum (Solver.cpp:1008-1018) */
+__global__ void __launch_bounds__(256)
+element_max_kernel(double* elem_vals, int n_elem, int n_vert)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  double m = 0;
+  for (int v = 0; v < n_vert; ++v) m = fmax(m, elem_vals[(size_t)e*n_vert + v]);
+  for (int v = 0; v < n_vert; ++v) elem_vals[(size_t)e*n_vert + v] = m;
+}
+
+int launch_share_vertex_data(hexed_b200_ctx* c, double* elem_vals, int is_max)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->elem_vertex) return fail(c, HEXED_B200_BAD_ARGUMENT, "no vertex topology: call hexed_b200_vertex_topology first");
+  const long long n = (long long)c->n_elem*c->n_vert;
+  if (!n) return 0;
+  HB_LAUNCH(fill_double_kernel, (c->n_vertex + 255)/256, 256, 0, c->stream, c->vertex_vals, c->n_vertex, is_max ? -DBL_MAX : DBL_MAX);
+  HB_LAUNCH(vertex_reduce_kernel, grid_for(n), 256, 0, c->stream, elem_vals, c->elem_vertex, n, c->vertex_vals, is_max);
+  HB_LAUNCH(vertex_fetch_kernel, grid_for(n), 256, 0, c->stream, elem_vals, c->elem_vertex, n, c->vertex_vals);
+  c->launches += 3;
+  if (c->n_match) {
+    // matchers of one epoch touch disjoint fine elements except through shared vertices, which they set to the same interpolant
+    HB_LAUNCH(hanging_vertex_kernel, (c->n_match + 127)/128, 128, 0, c->stream, elem_vals, c->matchers, c->n_match, c->nd);
+    ++c->launches;
+  }
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int launch_fix_admis_spread(hexed_b200_ctx* c, const double* d_interp)
+{
+  if (!c->record) return fail(c, HEXED_B200_BAD_ARGUMENT, "no record yet: call hexed_b200_is_admissible first");
+  int rc = need_array(c, &c->vertex_scratch, (size_t)c->n_vert); if (rc) return rc;
+  const long long n = (long long)c->n_elem*c->n_vert;
+  if (!n) return 0;
+  HB_LAUNCH(record_to_vertices_kernel, grid_for(n), 256, 0, c->stream, c->record, c->vertex_scratch, n, c->n_vert);
+  ++c->launches;
+  rc = launch_share_vertex_data(c, c->vertex_scratch, 1); if (rc) return rc;
+  HB_LAUNCH(element_max_kernel, (c->n_elem + 255)/256, 256, 0, c->stream, c->vertex_scratch, c->n_elem, c->n_vert);
+  ++c->launches;
+  rc = launch_share_vertex_data(c, c->vertex_scratch, 1); if (rc) return rc;
+  rc = launch_interp_vertices(c, 1, c->vertex_scratch, d_interp); if (rc) return rc;
+  return launch_av_swap(c);
+}
+
 } // namespace hb

@@ -95,6 +95,9 @@ struct hexed_b200_ctx
   float* cfl_approx = nullptr;
   bool cfl_valid[2] = {false, false};
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
+  // vertex topology of the epoch (hexed_b200_vertex_topology) and per-element-vertex scratch (vertex_fix_admis_coef / vertex_elwise_av)
+  int* elem_vertex = nullptr; int n_vertex = 0; int* matchers = nullptr; int n_match = 0;
+  double* vertex_vals = nullptr; double* vertex_scratch = nullptr;
   int* record = nullptr;  // Element::record as left by is_admissible: 1 = thermodynamically inadmissible element
   int* d_flags = nullptr; int* h_flags = nullptr; // {inadmissible, non-finite} found by the last is_admissible
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -165,6 +168,8 @@ int launch_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, 
 int launch_interp_vertices(hexed_b200_ctx* c, int target, const double* d_vert, const double* d_interp);
 int launch_av_swap(hexed_b200_ctx* c);
 int launch_aux_bcs(hexed_b200_ctx* c, int mode);
+int launch_share_vertex_data(hexed_b200_ctx* c, double* elem_vals, int is_max);
+int launch_fix_admis_spread(hexed_b200_ctx* c, const double* d_interp);
 
 /* Thread -> line-task map. In the dense [i][j][k] field layout that the bulk copies deliver, lines of dimension 0 (stride RS^2) are
  * conflict-free for consecutive lanes, but with 8-byte accesses consecutive lines of dimension 1 (stride RS) and 2 (stride 1) hit every

@@ -541,99 +541,54 @@ ns_local_line_kernel(GArgs a, Ops ops)
   /* ---- P1: gradient ---- */
   if constexpr (DEF) {
     const int l = t % nfq, j = t/nfq; // task of every sub-phase: line l of the current direction, physical component j
-    auto sub_phase = [&](auto dc) {
-      constexpr int d = decltype(dc)::value;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
       if (t < ND*nfq) {
-        constexpr int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
+        const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
         const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
-        // lines of dimension 2 are contiguous: 16-byte accesses there are free of the bank conflicts that 8-byte accesses of
-        // consecutive stride-1 lines have (see LineMap, common.cuh)
-        constexpr bool vec = LineMap<RS>::vec2 && d == 2;
         double nk[RS]; // the 1/nominal-size factor of the gradient (Spatial.hpp:398) is folded into the normals once per line
-        if constexpr (vec) {
-          #pragma unroll
-          for (int k = 0; k + 1 < RS; k += 2) ld2(rn + (d*ND + j)*nq + q0 + k, nk[k], nk[k + 1]);
-        } else {
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride];
-        }
         #pragma unroll
-        for (int k = 0; k < RS; ++k) nk[k] *= inv_nom;
+        for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride]*inv_nom;
         const double fn0 = fn[((2*d)*ND + j)*nfq + l]*inv_nom, fn1 = fn[((2*d + 1)*ND + j)*nfq + l]*inv_nom;
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
           double p[RS];
-          if constexpr (vec) {
-            #pragma unroll
-            for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, p[k], p[k + 1]);
-          } else {
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
-          }
           #pragma unroll
-          for (int k = 0; k < RS; ++k) p[k] *= nk[k];
+          for (int k = 0; k < RS; ++k) p[k] = nk[k]*S[v*nq + q0 + k*stride];
           const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
-          double* g = G + (v*ND + j)*nq + q0;
-          double acc[RS];
           #pragma unroll
           for (int i = 0; i < RS; ++i) {
-            double a_ = 0;
+            double acc = 0;
             #pragma unroll
-            for (int k = 0; k < RS; ++k) a_ += ops.dfull[i][k]*p[k];
-            a_ += ops.lift[i][0]*b0;
-            a_ += ops.lift[i][1]*b1;
-            acc[i] = a_;
-          }
-          if constexpr (vec) {
-            #pragma unroll
-            for (int i = 0; i + 1 < RS; i += 2) {
-              double g0, g1;
-              ld2(g + i, g0, g1);
-              st2(g + i, g0 + acc[i], g1 + acc[i + 1]);
-            }
-          } else {
-            #pragma unroll
-            for (int i = 0; i < RS; ++i) { if (d == 0) g[i*stride] = acc[i]; else g[i*stride] += acc[i]; }
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            double* g = G + (v*ND + j)*nq + q0 + i*stride;
+            if (d == 0) *g = acc; else *g += acc;
           }
         }
       }
       __syncthreads();
-    };
-    sub_phase(IC<0>{}); sub_phase(IC<1>{}); sub_phase(IC<2>{});
+    }
   } else {
-    int d, l;
-    if (LineMap<RS>::get(t, d, l)) {
-      const bool vec = LineMap<RS>::vec2 && d == 2;
+    if (t < C::n_line) {
+      const int d = t/nfq, l = t % nfq;
       const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
       const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         double p[RS];
-        if (vec) {
-          #pragma unroll
-          for (int k = 0; k + 1 < RS; k += 2) ld2(S + v*nq + q0 + k, p[k], p[k + 1]);
-        } else {
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
-        }
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
         const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
-        double acc[RS];
         #pragma unroll
         for (int i = 0; i < RS; ++i) {
-          double a_ = 0;
+          double acc = 0;
           #pragma unroll
-          for (int k = 0; k < RS; ++k) a_ += ops.dfull[i][k]*p[k];
-          a_ += ops.lift[i][0]*b0;
-          a_ += ops.lift[i][1]*b1;
-          acc[i] = a_*inv_nom;
-        }
-        double* g = G + (v*ND + d)*nq + q0;
-        if (vec) {
-          #pragma unroll
-          for (int i = 0; i + 1 < RS; i += 2) st2(g + i, acc[i], acc[i + 1]);
-        } else {
-          #pragma unroll
-          for (int i = 0; i < RS; ++i) g[i*stride] = acc[i];
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          G[(v*ND + d)*nq + q0 + i*stride] = acc*inv_nom;
         }
       }
     }
@@ -676,36 +631,17 @@ ns_local_line_kernel(GArgs a, Ops ops)
   __syncthreads();
 
   /* ---- P3: line derivatives in place, diffusive flux to the LDG faces ---- */
-  int d3, l3;
-  if (LineMap<RS>::get(t, d3, l3)) {
-    const int d = d3, l = l3;
-    const bool vec = LineMap<RS>::vec2 && d == 2;
+  if (t < C::n_line) {
+    const int d = t/nfq, l = t % nfq;
     const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
     const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
     double* fl = a.faces_ldg + (size_t)e*2*ND*wl;
-    auto load_line = [&](const double* row, double (&x)[RS]) {
-      if (vec) {
-        #pragma unroll
-        for (int k = 0; k + 1 < RS; k += 2) ld2(row + k, x[k], x[k + 1]);
-      } else {
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) x[k] = row[k*stride];
-      }
-    };
-    auto store_line = [&](double* row, const double (&x)[RS]) {
-      if (vec) {
-        #pragma unroll
-        for (int k = 0; k + 1 < RS; k += 2) st2(row + k, x[k], x[k + 1]);
-      } else {
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) row[k*stride] = x[k];
-      }
-    };
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double* row = F + (d*nv + v)*nq + q0;
-      double f[RS], r[RS];
-      load_line(row, f);
+      double f[RS];
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
       const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
       #pragma unroll
       for (int i = 0; i < RS; ++i) {
@@ -714,11 +650,11 @@ ns_local_line_kernel(GArgs a, Ops ops)
         for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
         acc += ops.lift[i][0]*b0;
         acc += ops.lift[i][1]*b1;
-        r[i] = -acc;
+        row[i*stride] = -acc;
       }
-      store_line(row, r);
       double* drow = G + (d*nv + v)*nq + q0;
-      load_line(drow, f);
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
       double e0 = 0, e1 = 0;
       #pragma unroll
       for (int k = 0; k < RS; ++k) { e0 += ops.bnd[0][k]*f[k]; e1 += ops.bnd[1][k]*f[k]; }
@@ -729,9 +665,8 @@ ns_local_line_kernel(GArgs a, Ops ops)
         double acc = 0;
         #pragma unroll
         for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
-        r[i] = -acc;
+        drow[i*stride] = -acc;
       }
-      store_line(drow, r);
     }
   }
   __syncthreads();

@@ -19,7 +19,7 @@ from .mesh import (BC_FREESTREAM, BC_COPY, BC_NONPENETRATION, BC_OUTFLOW, BC_PRE
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhexed_b200.so")
 
-(NOMINAL_SIZE, VERTEX_TSS, REF_NORMALS, JAC_DET, FACE_STATE, FACE_LDG, FACE_WIDE, NORMALS, UNCERT) = range(9)
+(NOMINAL_SIZE, VERTEX_TSS, REF_NORMALS, JAC_DET, FACE_STATE, FACE_LDG, FACE_WIDE, NORMALS, UNCERT, VERTEX_SCRATCH) = range(10)
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -99,6 +99,9 @@ SIGNATURES = {
     "hexed_b200_av_swap": [C.c_void_p],
     "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
+    "hexed_b200_vertex_topology": [C.c_void_p, ip, C.c_int, ip, C.c_int],
+    "hexed_b200_share_vertex_data": [C.c_void_p, C.c_int, C.c_int],
+    "hexed_b200_fix_admis_spread": [C.c_void_p, dp],
     "hexed_b200_download_record": [C.c_void_p, ip, C.c_int, C.c_int],
     "hexed_b200_neighbor_euler": [C.c_void_p, C.c_int],
     "hexed_b200_local_euler": [C.c_void_p, C.c_int, Options],
@@ -443,6 +446,21 @@ class Device:
         v = np.ascontiguousarray(vertex_pos, dtype=np.float64)
         a = None if node_adj is None else np.ascontiguousarray(node_adj, dtype=np.float64)
         self._check(self.lib.hexed_b200_set_jacobian(self.ctx, v.ctypes.data_as(dp), None if a is None else a.ctypes.data_as(dp)))
+
+    def vertex_topology(self, elem_vertex, n_vertex, matchers=None):
+        """per-epoch vertex connectivity for share_vertex_data: elem_vertex (n_elem, 2^nd) vertex ids, matchers (n_match, 8) rows
+        {i_dim, is_positive, stretch0, stretch1, fine elements (4, -1 padded)} (reference src/Hanging_vertex_matcher.cpp)"""
+        ev = _i32(elem_vertex)
+        mt = _i32(matchers if matchers is not None else np.zeros((0, 8)))
+        self._check(self.lib.hexed_b200_vertex_topology(self.ctx, ev.ctypes.data_as(ip), int(n_vertex), mt.ctypes.data_as(ip), mt.shape[0] if mt.ndim == 2 else 0))
+
+    def share_vertex_data(self, which, op_max):
+        """Solver::share_vertex_data (reference src/Solver.cpp:35-54) on VERTEX_TSS or VERTEX_SCRATCH; op_max False = min"""
+        self._check(self.lib.hexed_b200_share_vertex_data(self.ctx, int(which), int(bool(op_max))))
+
+    def fix_admis_spread(self, interp):
+        i = np.ascontiguousarray(interp, dtype=np.float64)
+        self._check(self.lib.hexed_b200_fix_admis_spread(self.ctx, i.ctypes.data_as(dp)))
 
     def is_admissible(self):
         """Solver::is_admissible (reference src/Solver.cpp:921-958); raises RuntimeError("state is not finite") like the reference's

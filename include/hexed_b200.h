@@ -70,7 +70,8 @@ enum {
   HEXED_B200_FACE_LDG = 5,     /* [n_face_slot][nv*nfq]    item = face slot */
   HEXED_B200_FACE_WIDE = 6,    /* [n_face_slot][(n_dim+row_size)*nfq] item = face slot */
   HEXED_B200_NORMALS = 7,      /* [n_normal_slot][n_dim*nfq] item = normal slot */
-  HEXED_B200_UNCERT = 8        /* [n_elem]                 Kernel_element::uncert() */
+  HEXED_B200_UNCERT = 8,       /* [n_elem]                 Kernel_element::uncert() */
+  HEXED_B200_VERTEX_SCRATCH = 9 /* [n_elem][2^n_dim]       Element::vertex_fix_admis_coef(i) / vertex_elwise_av(i) */
 };
 
 enum { HEXED_B200_BC_FREESTREAM = 0, HEXED_B200_BC_COPY = 1, HEXED_B200_BC_NONPENETRATION = 2,
@@ -213,6 +214,17 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
  * Returns HEXED_B200_NOT_FINITE where the reference throws "state is not finite". ---- */
 int hexed_b200_is_admissible(hexed_b200_ctx* ctx, int* admissible);
 int hexed_b200_download_record(hexed_b200_ctx* ctx, int* dst, int first_elem, int n_elem);
+/* Solver::share_vertex_data (src/Solver.cpp:35-54): every mesh vertex takes the min (op 0) or max (op 1) over the elements that share
+ * it, then the Hanging_vertex_matchers interpolate onto hanging vertices (src/Hanging_vertex_matcher.cpp:13-41). The vertex connectivity
+ * is outside Kernel_mesh, so it is given once per mesh epoch: elem_vertex [n_elem][2^n_dim] = id in [0, n_vertex) of Element::vertex(i);
+ * matchers [n_match][8] = {i_dim, is_positive, stretch0, stretch1, fine element 0..3 (-1 = unused)} in the matcher's element order.
+ * which = HEXED_B200_VERTEX_TSS (calc_jacobian's last step, :380) or HEXED_B200_VERTEX_SCRATCH. */
+int hexed_b200_vertex_topology(hexed_b200_ctx* ctx, const int* elem_vertex, int n_vertex, const int* matchers, int n_match);
+int hexed_b200_share_vertex_data(hexed_b200_ctx* ctx, int which, int op);
+/* the spreading step of Solver::fix_admissibility (:1000-1038): record -> element vertices, share max, element-wise max, share max,
+ * interpolation to laplacian_av_coef with interp[row_size][2] = {1 - node, node}, swap with bulk_av_coef. With max_dt_fix_therm_admis,
+ * apply_aux_bcs and compute_fix_therm_admis the whole repair iteration then runs without touching the host objects. */
+int hexed_b200_fix_admis_spread(hexed_b200_ctx* ctx, const double* interp);
 
 /* ---- pointwise loops around the artificial-viscosity kernels: the host loops of
  * Solver::update_art_visc_smoothness (src/Solver.cpp:457-581), fix_admissibility (:1021-1038,1080-1086), set_art_visc_admis (:636-658)

@@ -534,3 +534,32 @@ def apply_aux_bcs(m, mode):
                 g[:, :nd] = f[:, :nd]
                 g[:, nd:] = 2. - f[:, nd:]
             m.face_wide[gh] = g.reshape(ins.size, -1)
+
+
+def share_vertex_data(elem_vals, elem_vertex, n_vertex, matchers, n_dim, is_max):
+    """Solver::share_vertex_data (reference src/Solver.cpp:35-54) on an (n_elem, 2^nd) array, in place: vertex-wise min/max over the
+    sharing elements, then every Hanging_vertex_matcher (rows {i_dim, is_positive, stretch0, stretch1, fine elements x4, -1 padded})
+    through the golden-vector-pinned hexed_b200.tables.hanging_vertex_match. numpy, TEST INFRASTRUCTURE."""
+    from hexed_b200.tables import hanging_vertex_match
+    ev = np.asarray(elem_vertex)
+    red = np.full(n_vertex, -np.inf if is_max else np.inf)
+    (np.maximum if is_max else np.minimum).at(red, ev.reshape(-1), elem_vals.reshape(-1))
+    elem_vals[:] = red[ev]
+    for row in np.asarray(matchers).reshape(-1, 8):
+        fine = [int(e) for e in row[4:] if e >= 0]
+        sub = elem_vals[fine].copy()
+        hanging_vertex_match(n_dim, sub, int(row[0]), bool(row[1]), (bool(row[2]), bool(row[3])))
+        elem_vals[fine] = sub
+    return elem_vals
+
+
+def fix_admis_spread(m, record, elem_vertex, n_vertex, matchers, interp):
+    """the spreading step of Solver::fix_admissibility (reference src/Solver.cpp:1000-1038)"""
+    nd = m.n_dim
+    v = np.repeat(np.asarray(record, dtype=np.float64)[:, None], 2**nd, axis=1)
+    share_vertex_data(v, elem_vertex, n_vertex, matchers, nd, True)
+    v[:] = v.max(axis=1, keepdims=True)
+    share_vertex_data(v, elem_vertex, n_vertex, matchers, nd, True)
+    interp_vertices(m, 1, v, interp)
+    av_swap(m)
+    return v

@@ -114,6 +114,7 @@ inline int __syncthreads_or(int pred)
   __syncthreads();
   return any;
 }
+template <class T> T atomicCAS(T* p, T expected, T desired) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; if (o == expected) *p = desired; return o; }
 template <class T> T atomicOr(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; *p = o | v; return o; }
 template <class T> T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; *p = o + v; return o; }
 template <class T> T atomicMin(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); T o = *p; if (v < o) *p = v; return o; }

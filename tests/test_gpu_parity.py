@@ -276,3 +276,10 @@ def test_av_smoothness_pipeline(oracle, gpu_lib, nd, rs):
     """the naca0012-class configuration's shock-capturing update, Solver::update_art_visc_smoothness, with no host loop left"""
     from util import check_av_pipeline
     check_av_pipeline(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6)])
+def test_vertex_sharing_and_fix_admis_spread(oracle, gpu_lib, nd, rs):
+    """share_vertex_data + the spreading step of fix_admissibility on the device"""
+    from util import check_vertex_sharing
+    check_vertex_sharing(oracle, gpu_lib, nd, rs)

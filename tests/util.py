@@ -476,3 +476,57 @@ def check_av_pipeline(oracle, lib, nd, rs, seed=17, advect_iters=2, diff_iters=1
     assert_pde_parity(out, ref, [])
     assert rel_l2(out.state(), m.state()) <= 1e-13          # the flow state comes back as it was found
     assert not np.array_equal(out.elem_data[:, nd + 3], m.elem_data[:, nd + 3])
+
+
+def check_vertex_sharing(oracle, lib, nd, rs, seed=23):
+    """Solver::share_vertex_data (min on the vertex time-step scale as at the end of calc_jacobian, max on the scratch array) with
+    hanging-vertex matchers of every stretch, and the spreading step of fix_admissibility built on it, against the numpy restatement
+    (whose matcher is the golden-vector-pinned hexed_b200.tables.hanging_vertex_match)"""
+    import pyoracle
+    from hexed_b200.kernels import VERTEX_TSS, VERTEX_SCRATCH
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=14, n_def=16, n_ref=0)
+    M.random_flow_state(m, rng)
+    oracle.compute_write_face(basis, m)
+    ne, n_vert = m.n_elem, 2**nd
+    n_vertex = ne*n_vert//3 + 5
+    elem_vertex = rng.integers(0, n_vertex, (ne, n_vert)).astype(np.int32)
+    for e in range(ne):  # an element's vertices are distinct mesh vertices
+        elem_vertex[e] = rng.choice(n_vertex, n_vert, replace=False)
+    matchers = []
+    if nd > 1:
+        free = list(rng.permutation(ne))
+        for stretch in ([(0, 0), (1, 0), (0, 1)] if nd == 3 else [(0, 0)]):
+            for i_dim in range(nd):
+                n_fine = 2**(nd - 1)//((1 + stretch[0])*(1 + stretch[1]))
+                fine = [int(free.pop()) for _ in range(n_fine)] + [-1]*(4 - n_fine)
+                matchers.append([i_dim, int(rng.integers(0, 2)), stretch[0], stretch[1]] + fine)
+    matchers = np.array(matchers, np.int32).reshape(-1, 8)
+    m.vertex_tss = rng.uniform(.1, 1., (ne, n_vert))
+    m.state()[3, nd, 0] = -1.; m.state()[9, nd + 1, 1] = -2.   # two inadmissible elements
+    m.elem_data[:, nd + 3:nd + 5] = rng.uniform(0., 1e-3, (ne, 2, m.nq))
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    dev.vertex_topology(elem_vertex, n_vertex, matchers)
+    dev.share_vertex_data(VERTEX_TSS, False)
+    got_tss = dev.download(VERTEX_TSS, np.zeros_like(m.vertex_tss))
+    want_tss = pyoracle.share_vertex_data(ref.vertex_tss.copy(), elem_vertex, n_vertex, matchers, nd, False)
+    close = lambda a, b: np.allclose(a, b, rtol=4e-16, atol=0.)  # noqa: E731  (the matcher's midpoints: contraction order, 1 ulp)
+    assert close(got_tss, want_tss)
+    scratch = rng.uniform(0., 1., (ne, n_vert))
+    dev.upload(VERTEX_SCRATCH, scratch)
+    dev.share_vertex_data(VERTEX_SCRATCH, True)
+    assert close(dev.download(VERTEX_SCRATCH, np.zeros_like(scratch)), pyoracle.share_vertex_data(scratch.copy(), elem_vertex, n_vertex, matchers, nd, True))
+    ok = dev.is_admissible()
+    want_ok, record = oracle.is_admissible(ref)
+    assert not ok and not want_ok and record.sum() == 2
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    dev.fix_admis_spread(interp)
+    v = pyoracle.fix_admis_spread(ref, record, elem_vertex, n_vertex, matchers, interp)
+    assert close(dev.download(VERTEX_SCRATCH, np.zeros_like(scratch)), v)
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert rel_l2(out.elem_data[:, nd + 3:nd + 5], ref.elem_data[:, nd + 3:nd + 5]) <= 1e-15
+    assert out.elem_data[:, nd + 3].max() > 0.5   # the flagged elements and their neighbours carry a factor ~1 in what is now the bulk slot
