@@ -11,7 +11,12 @@
  * reference's own closed-form test values (test/test_Max_dt.cpp, test_Derivative.cpp,
  * test_Prolong_refined.cpp, test_Restrict_refined.cpp, test_Face_permutation.cpp, ...)
  * as tests/ of this repo; the Euler/NS flux has no direct unit test in the reference
- * (test/test_pde.cpp is #if 0) and is pinned only through conservation/marching checks.
+ * (test/test_pde.cpp is #if 0) and is pinned only through conservation/marching checks;
+ * the LDG path (Neighbor average, gradient, compute_flux_diff, Neighbor_reconcile,
+ * Reconcile_ldg_flux) is pinned by the reference's analytic viscous-decay check
+ * (test/test_Solver.cpp:588-615, tests/test_oracle_kat.py::test_viscous_momentum_decay).
+ * PARITY UNPINNED beyond line-by-line restatement: Stab_art_visc and Fix_therm_admis
+ * (the reference has no dedicated test for either).
  *
  * Floating point: plain IEEE double, sums accumulated left to right in the order the
  * reference's loops imply; build with -ffp-contract=off for a machine-independent

@@ -19,12 +19,13 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KN" -
   python bench.py --n 64 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --pde navier_stokes > gpurun_out/ncu_launch_ns.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KN" -c 60 --csv --log-file gpurun_out/launches_${TAG}_2d.csv \
   python bench.py --dim 2 --n 512 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_2d.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:local_euler_pipe|neighbor_euler|max_dt_euler" -s 6 -c 6 -f -o gpurun_out/prof_${TAG}_euler \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:local_euler_pipe|neighbor_euler|max_dt_euler" -s 6 -c 5 -f -o gpurun_out/prof_${TAG}_euler \
   python bench.py --n 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_euler.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:local_euler_pipe" -s 4 -c 2 -f -o gpurun_out/prof_${TAG}_euler_car \
+timeout 900 ncu --set full --clock-control none -k "regex:local_euler_pipe" -s 4 -c 1 -f -o gpurun_out/prof_${TAG}_euler_car \
   python bench.py --n 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --mesh cartesian > gpurun_out/ncu_full_euler_car.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:ns_local|ns_reconcile|g_.*_kernel" -s 10 -c 7 -f -o gpurun_out/prof_${TAG}_ns \
+timeout 900 ncu --set full --clock-control none -k "regex:ns_local|ns_reconcile|g_.*_kernel" -s 10 -c 5 -f -o gpurun_out/prof_${TAG}_ns \
   python bench.py --n 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --pde navier_stokes > gpurun_out/ncu_full_ns.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:local_euler_pipe2d|neighbor_euler" -s 6 -c 4 -f -o gpurun_out/prof_${TAG}_2d \
+timeout 900 ncu --set full --clock-control none -k "regex:local_euler_pipe2d|neighbor_euler" -s 6 -c 3 -f -o gpurun_out/prof_${TAG}_2d \
   python bench.py --dim 2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_2d.log 2>&1
+du -sh gpurun_out
 for f in pytest_gpu bench_def bench_reference bench_car bench_ns bench_ns_car bench_2d_def bench_2d_car bench_2d_ns; do echo "== $f"; tail -n 3 gpurun_out/$f.log | cut -c1-260; done
