@@ -707,6 +707,8 @@ int hexed_b200_set_jacobian(hexed_b200_ctx* c, const double* vertex_pos, const d
   return rc;
 }
 
+int hexed_b200_calc_shared_normals(hexed_b200_ctx* c) { return launch_shared_normals(c); }
+
 int hexed_b200_av_scale_velocity(hexed_b200_ctx* c, int restore) { return launch_av_scale_velocity(c, restore); }
 
 int hexed_b200_av_project_forcing(hexed_b200_ctx* c, const double* node_weights, const double* orthogonal)

@@ -162,6 +162,7 @@ int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
 int launch_set_jacobian(hexed_b200_ctx* c, const double* d_vert, const double* d_node_adj);
+int launch_shared_normals(hexed_b200_ctx* c);
 int launch_av_scale_velocity(hexed_b200_ctx* c, int restore);
 int launch_av_project_forcing(hexed_b200_ctx* c, const double* weights, const double* orth);
 int launch_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, const double* node_weights, double* resid_sq);

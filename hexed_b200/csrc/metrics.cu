@@ -234,4 +234,128 @@ int launch_set_jacobian(hexed_b200_ctx* c, const double* d_vert, const double* d
   });
 }
 
+/* ---------------- shared face normals: the connection passes of Solver::calc_jacobian (reference src/Solver.cpp:287-357) ----------------
+ * After set_jacobian every element face holds ITS element's normal in the first n_dim*nfq doubles of its face storage. The passes:
+ *   1. coarse normals prolonged onto the mortar faces (compute_prolong(mesh, true), :299) -- the existing prolong kernel;
+ *   2. fine side of every fine connection := +-(coarse normal), through the face permutation (:301-317);
+ *   3. ghost face of every boundary connection := inside face (:319-326);
+ *   4. every deformed connection: permute side 1, average the two element normals with the flip signs, give each side its signed copy,
+ *      un-permute, store as Kernel_connection::normal() and as the kernel_face_normal() of the deformed elements on either side (:328-355);
+ *   5. coarse element face normal := its own normal (:357-369).
+ * All factors are 0.5 and +-1, so the result is bit-identical to the reference's whatever the evaluation order.
+ * slot_kind[s] = 1 marks mortar faces (fine faces of a refined face). Direction code = i_dim0 + 3*i_dim1 + 9*sign0 + 18*sign1. */
+__global__ void __launch_bounds__(128)
+mark_mortar_kernel(const int* ref_face, int n_ref, int nd, int* slot_kind)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n_ref) return;
+  const int* rf = ref_face + (size_t)i*8;
+  int n_fine = 1 << (nd - 1);
+  for (int k = 0; k < nd - 1; ++k) n_fine /= 1 + rf[5 + k];
+  for (int k = 0; k < n_fine; ++k) slot_kind[rf[1 + k]] = 1;
+}
+
+struct NormalArgs
+{
+  double* faces; double* normals; const int* def_con; const int* perm; const int* slot_kind; const int* ref_face;
+  int n_con, n_ref, nd, nfq, face_width, n_car, n_elem;
+};
+
+__device__ __forceinline__ void decode_flips(int code, int& s0, int& s1)
+{
+  const int sign0 = (code/9) % 2, sign1 = (code/18) % 2;
+  s0 = 1 - 2*(sign0 == 0); // 1 - 2*flip_normal(0), flip_normal(i) = (face_sign[i] == i)  (include/Kernel_connection.hpp:22-24)
+  s1 = 1 - 2*(sign1 == 1);
+}
+
+/* pass: 0 = fine connections, 1 = boundary ghosts, 2 = shared normal */
+__global__ void __launch_bounds__(256)
+connection_normal_kernel(NormalArgs a, int pass)
+{
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = (int)(gid/a.nfq), p = (int)(gid % a.nfq);
+  if (i >= a.n_con) return;
+  const int* row = a.def_con + (size_t)i*4;
+  const int slot0 = row[0], slot1 = row[1], code = row[2];
+  const int p1 = a.perm[code*a.nfq + p]; // matched[p] = original[p1]
+  const int n_elem_face = 2*a.nd*a.n_elem;
+  const bool mortar0 = a.slot_kind[slot0] == 1, mortar1 = a.slot_kind[slot1] == 1;
+  int s0, s1;
+  decode_flips(code, s0, s1);
+  double* f0 = a.faces + (size_t)slot0*a.face_width;
+  double* f1 = a.faces + (size_t)slot1*a.face_width;
+  if (pass == 0) {
+    if (mortar0 == mortar1) return;
+    // face[0] = the mortar (coarse) side, face[1] = the fine element's side; the reference permutes face[1] with the connection's
+    // side-1 permutation whichever side it is (:309-315)
+    const double* mort = mortar1 ? f1 : f0;
+    double* other = mortar1 ? f0 : f1;
+    const int sign = 1 - 2*((s0 < 0) != (s1 < 0));
+    for (int j = 0; j < a.nd; ++j) other[j*a.nfq + p1] = sign*mort[j*a.nfq + p];
+    return;
+  }
+  if (pass == 1) {
+    if (slot1 < n_elem_face || mortar1 || slot0 >= n_elem_face) return;
+    for (int j = 0; j < a.nd; ++j) f1[j*a.nfq + p] = f0[j*a.nfq + p];
+    return;
+  }
+  const int def_first = 2*a.nd*a.n_car;
+  for (int j = 0; j < a.nd; ++j) {
+    double n = 0;
+    n += 0.5*s0*f0[j*a.nfq + p];
+    n += 0.5*s1*f1[j*a.nfq + p1];
+    const double o0 = s0*n, o1 = s1*n;
+    f0[j*a.nfq + p] = o0;
+    f1[j*a.nfq + p1] = o1;
+    // Kernel_connection::normal() = normal(0) is the connection's own storage in the reference (include/connection.hpp:85-86); a table
+    // that points it at the side-1 element's face normal (which holds normal(1)) keeps the element's copy
+    const bool side1_owns = slot1 >= def_first && slot1 < n_elem_face && row[3] == slot1 - def_first;
+    if (!side1_owns) a.normals[((size_t)row[3]*a.nd + j)*a.nfq + p] = o0;
+    if (slot0 >= def_first && slot0 < n_elem_face) a.normals[((size_t)(slot0 - def_first)*a.nd + j)*a.nfq + p] = o0;
+    if (slot1 >= def_first && slot1 < n_elem_face) a.normals[((size_t)(slot1 - def_first)*a.nd + j)*a.nfq + p1] = o1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+coarse_normal_kernel(NormalArgs a)
+{
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = (int)(gid/a.nfq), p = (int)(gid % a.nfq);
+  if (i >= a.n_ref) return;
+  const int coarse = a.ref_face[(size_t)i*8];
+  const int def_first = 2*a.nd*a.n_car;
+  if (coarse < def_first || coarse >= 2*a.nd*a.n_elem) return;
+  for (int j = 0; j < a.nd; ++j) a.normals[((size_t)(coarse - def_first)*a.nd + j)*a.nfq + p] = a.faces[(size_t)coarse*a.face_width + j*a.nfq + p];
+}
+
+int launch_shared_normals(hexed_b200_ctx* c)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  int* slot_kind = nullptr;
+  HB_CUDA(c, cudaMalloc(&slot_kind, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1)));
+  HB_CUDA(c, cudaMemsetAsync(slot_kind, 0, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1), c->stream));
+  int rc = 0;
+  if (c->n_ref) {
+    HB_LAUNCH(mark_mortar_kernel, (c->n_ref + 127)/128, 128, 0, c->stream, c->ref_face, c->n_ref, c->nd, slot_kind);
+    ++c->launches;
+    rc = launch_prolong(c, 0, c->nv, 1);
+  }
+  NormalArgs a;
+  a.faces = c->face_state; a.normals = c->normals; a.def_con = c->def_con; a.perm = c->perm; a.slot_kind = slot_kind; a.ref_face = c->ref_face;
+  a.n_con = c->n_def_con; a.n_ref = c->n_ref; a.nd = c->nd; a.nfq = c->nfq; a.face_width = c->nv*c->nfq; a.n_car = c->n_car; a.n_elem = c->n_elem;
+  const long long n = (long long)c->n_def_con*c->nfq;
+  if (!rc && n) {
+    for (int pass = 0; pass < 3; ++pass) {
+      HB_LAUNCH(connection_normal_kernel, (int)((n + 255)/256), 256, 0, c->stream, a, pass);
+      ++c->launches;
+    }
+  }
+  const long long nr = (long long)c->n_ref*c->nfq;
+  if (!rc && nr) { HB_LAUNCH(coarse_normal_kernel, (int)((nr + 255)/256), 256, 0, c->stream, a); ++c->launches; }
+  if (!rc) rc = check(c, cudaGetLastError(), "shared normals");
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "shared normals");
+  cudaFree(slot_kind);
+  return rc;
+}
+
 } // namespace hb

@@ -92,6 +92,7 @@ SIGNATURES = {
     "hexed_b200_pde_kernel": [C.c_void_p, C.c_int, C.c_int, C.c_int, Options, Transport, Transport, C.c_double, C.c_double],
     "hexed_b200_apply_flux_bcs": [C.c_void_p],
     "hexed_b200_set_jacobian": [C.c_void_p, dp, dp],
+    "hexed_b200_calc_shared_normals": [C.c_void_p],
     "hexed_b200_av_scale_velocity": [C.c_void_p, C.c_int],
     "hexed_b200_av_project_forcing": [C.c_void_p, dp, dp],
     "hexed_b200_av_finish": [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp],
@@ -461,6 +462,10 @@ class Device:
     def fix_admis_spread(self, interp):
         i = np.ascontiguousarray(interp, dtype=np.float64)
         self._check(self.lib.hexed_b200_fix_admis_spread(self.ctx, i.ctypes.data_as(dp)))
+
+    def calc_shared_normals(self):
+        """connection passes of Solver::calc_jacobian (reference src/Solver.cpp:287-369)"""
+        self._check(self.lib.hexed_b200_calc_shared_normals(self.ctx))
 
     def is_admissible(self):
         """Solver::is_admissible (reference src/Solver.cpp:921-958); raises RuntimeError("state is not finite") like the reference's

@@ -257,6 +257,12 @@ int hexed_b200_apply_aux_bcs(hexed_b200_ctx* ctx, int mode);
  * determinant, vertex time-step scale of the deformed elements and, like the reference, each element's face normals into the first
  * n_dim*nfq doubles of its face storage (HEXED_B200_FACE_STATE), where the shared-normal pass of calc_jacobian (:287-357, host) reads them. ---- */
 int hexed_b200_set_jacobian(hexed_b200_ctx* ctx, const double* vertex_pos, const double* node_adj);
+/* the connection passes of the same function (:287-369) on what set_jacobian left in the face storage: coarse normals prolonged to the
+ * mortar faces, fine sides of fine connections, ghost faces, the sign-aware average of the two element normals of every deformed
+ * connection (stored as Kernel_connection::normal() and as kernel_face_normal() of the deformed elements on either side), coarse
+ * element face normals. The last step of calc_jacobian, share_vertex_data(vertex_time_step_scale, min) (:380), is
+ * hexed_b200_share_vertex_data(ctx, HEXED_B200_VERTEX_TSS, 0); the boundary surface positions (:370-379) are host-side geometry. */
+int hexed_b200_calc_shared_normals(hexed_b200_ctx* ctx);
 
 /* ---- domain decomposition (new in this implementation: the reference is single-process) ----
  * A rank's mesh is self-contained: faces of remote elements are HALO face slots (ordinary slots >= 2*n_dim*n_elem). The host

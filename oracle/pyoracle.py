@@ -563,3 +563,51 @@ def fix_admis_spread(m, record, elem_vertex, n_vertex, matchers, interp):
     interp_vertices(m, 1, v, interp)
     av_swap(m)
     return v
+
+
+def calc_shared_normals(oracle, basis, m):
+    """the connection passes of Solver::calc_jacobian (reference src/Solver.cpp:287-369) on a FlatMesh whose element faces hold their
+    element's normal in the first n_dim*nfq doubles (as Deformed_element::set_jacobian leaves them). numpy, TEST INFRASTRUCTURE; the
+    face permutation is hexed_b200.tables.face_permutation (pinned by the reference's Face_permutation tests)."""
+    from hexed_b200.tables import Connection_direction, face_permutation
+    nd, rs, nfq, ne = m.n_dim, m.row_size, m.nfq, m.n_elem
+    n_elem_face, def_first = 2*nd*ne, 2*nd*m.n_car
+    mortar = set()
+    for row in np.asarray(m.ref_face).reshape(-1, 7):
+        n_fine = 2**(nd - 1)
+        for k in range(nd - 1):
+            n_fine //= 1 + int(row[5 + k])
+        mortar.update(int(s) for s in row[1:1 + n_fine])
+    if len(mortar):
+        oracle.compute_prolong(basis, m, scale=True)
+    face = lambda s: m.face_state[s].reshape(nd + 2, nfq)[:nd]  # noqa: E731  (a view)
+    rows = np.asarray(m.def_con).reshape(-1, 7)
+    dirs = [Connection_direction(r[2:4], r[4:6]) for r in rows]
+    tables = [face_permutation(nd, rs, d) for d in dirs]
+    for r, d, t in zip(rows, dirs, tables):  # fine connections (:301-317)
+        m0, m1 = int(r[0]) in mortar, int(r[1]) in mortar
+        if m0 == m1:
+            continue
+        mort, other = (face(r[1]), face(r[0])) if m1 else (face(r[0]), face(r[1]))
+        sign = 1 - 2*(d.flip_normal(0) != d.flip_normal(1))
+        other[:, t] = sign*mort
+    for r in rows:  # boundary ghosts (:319-326)
+        if r[1] >= n_elem_face and int(r[1]) not in mortar and r[0] < n_elem_face:
+            face(r[1])[:] = face(r[0])
+    for r, d, t in zip(rows, dirs, tables):  # shared normal (:328-355)
+        s = [1 - 2*d.flip_normal(0), 1 - 2*d.flip_normal(1)]
+        f0, f1 = face(r[0]), face(r[1])
+        n = np.zeros((nd, nfq))
+        n = n + 0.5*s[0]*f0
+        n = n + 0.5*s[1]*f1[:, t]
+        f0[:] = s[0]*n
+        f1[:, t] = s[1]*n
+        if not (def_first <= r[1] < n_elem_face and r[6] == r[1] - def_first):  # normal() aliasing side 1's copy: the element's wins
+            m.normals[r[6]] = f0
+        if def_first <= r[0] < n_elem_face:
+            m.normals[r[0] - def_first] = f0
+        if def_first <= r[1] < n_elem_face:
+            m.normals[r[1] - def_first] = f1
+    for row in np.asarray(m.ref_face).reshape(-1, 7):  # coarse hanging faces (:357-369)
+        if def_first <= row[0] < n_elem_face:
+            m.normals[row[0] - def_first] = face(row[0])

@@ -181,3 +181,16 @@ def test_vertex_sharing_and_fix_admis_spread(oracle, emu_lib, nd, rs):
     """share_vertex_data + the spreading step of fix_admissibility on the device"""
     from util import check_vertex_sharing
     check_vertex_sharing(oracle, emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2), (3, 3)])
+def test_shared_normals_soup(oracle, emu_lib, nd, rs):
+    """SURVEY section 8 f-4: connection passes of Solver::calc_jacobian on the device"""
+    from util import check_shared_normals_soup
+    check_shared_normals_soup(oracle, emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 3, 4), (3, 2, 3)])
+def test_calc_jacobian_box(emu_lib, nd, rs, n):
+    from util import check_calc_jacobian_box
+    check_calc_jacobian_box(emu_lib, nd, rs, n)

@@ -283,3 +283,16 @@ def test_vertex_sharing_and_fix_admis_spread(oracle, gpu_lib, nd, rs):
     """share_vertex_data + the spreading step of fix_admissibility on the device"""
     from util import check_vertex_sharing
     check_vertex_sharing(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 4)])
+def test_shared_normals_soup(oracle, gpu_lib, nd, rs):
+    """SURVEY section 8 f-4: connection passes of Solver::calc_jacobian on the device"""
+    from util import check_shared_normals_soup
+    check_shared_normals_soup(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 12), (3, 6, 6), (3, 4, 8)])
+def test_calc_jacobian_box(gpu_lib, nd, rs, n):
+    from util import check_calc_jacobian_box
+    check_calc_jacobian_box(gpu_lib, nd, rs, n)

@@ -530,3 +530,57 @@ def check_vertex_sharing(oracle, lib, nd, rs, seed=23):
     dev.close()
     assert rel_l2(out.elem_data[:, nd + 3:nd + 5], ref.elem_data[:, nd + 3:nd + 5]) <= 1e-15
     assert out.elem_data[:, nd + 3].max() > 0.5   # the flagged elements and their neighbours carry a factor ~1 in what is now the bulk slot
+
+
+def check_shared_normals_soup(oracle, lib, nd, rs, seed=31):
+    """the connection passes of Solver::calc_jacobian on a soup mesh (every direction, hanging faces, boundary ghosts) with arbitrary
+    element-face normals: bit-identical to the numpy restatement (all factors are 0.5 and +-1)"""
+    import pyoracle
+    from hexed_b200.kernels import NORMALS
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=8, n_def=20, n_ref=4 if nd > 1 else 0)
+    m.face_state[:] = rng.normal(0., 1., m.face_state.shape)
+    m.normals[:] = -9.
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    dev.calc_shared_normals()
+    got_n = dev.download(NORMALS, np.zeros_like(m.normals))
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    pyoracle.calc_shared_normals(oracle, basis, ref)
+    written = ref.normals != -9.
+    assert written.any()
+    assert np.array_equal(got_n[written], ref.normals[written])
+    assert rel_l2(out.face_state, ref.face_state) <= 1e-15  # the prolonged mortar normals go through the interpolation matrices
+
+
+def check_calc_jacobian_box(lib, nd, rs, n):
+    """calc_jacobian end to end on the device (set_jacobian + connection passes + vertex minimum of the time-step scale) from nothing
+    but the vertex positions of the warped box reproduces the metric terms the mesh generator computed on the host"""
+    import torch
+    from hexed_b200.kernels import NORMALS, REF_NORMALS, JAC_DET, VERTEX_TSS
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_COPY)
+    h = 1./n
+    grid = torch.stack(torch.meshgrid(*[torch.arange(n + 1, dtype=torch.float64)*h]*nd, indexing="ij"), -1)
+    vpos = M.default_warp(grid, 0.1*h).reshape(-1, nd).numpy()
+    idx = np.stack(np.meshgrid(*[np.arange(n)]*nd, indexing="ij"), -1).reshape(-1, nd)
+    corner = np.array([[(i >> (nd - 1 - d)) & 1 for d in range(nd)] for i in range(2**nd)])
+    vstr = np.array([(n + 1)**(nd - 1 - d) for d in range(nd)])
+    vid = ((idx[:, None, :] + corner[None, :, :])*vstr).sum(-1).astype(np.int32)
+    want = dict(normals=np.asarray(m.normals).copy(), refn=np.asarray(m.ref_normals).copy(), det=np.asarray(m.det).copy(), vtss=m.vertex_tss.copy())
+    m.normals = np.full_like(want["normals"], -9.); m.ref_normals = np.zeros_like(want["refn"]); m.det = np.zeros_like(want["det"])
+    m.vertex_tss = np.zeros_like(want["vtss"])
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    dev.set_jacobian(vpos[vid])
+    dev.calc_shared_normals()
+    dev.vertex_topology(vid, (n + 1)**nd)
+    dev.share_vertex_data(VERTEX_TSS, False)
+    got = dict(normals=dev.download(NORMALS, np.zeros_like(want["normals"])), refn=dev.download(REF_NORMALS, np.zeros_like(want["refn"])),
+               det=dev.download(JAC_DET, np.zeros_like(want["det"])), vtss=dev.download(VERTEX_TSS, np.zeros_like(want["vtss"])))
+    dev.close()
+    for key in want:
+        assert rel_l2(got[key], want[key]) <= 1e-13, key
+        assert np.abs(got[key] - want[key]).max() <= 1e-12*np.abs(want[key]).max(), key
