@@ -5,5 +5,4 @@ mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/multigpu_check.py > gpurun_out/multigpu_check_$N.log 2>&1; echo "rc=$?" >> gpurun_out/multigpu_check_$N.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_def_$N.log 2>&1; echo "rc=$?" >> gpurun_out/bench_def_$N.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --pde navier_stokes > gpurun_out/bench_ns_$N.log 2>&1; echo "rc=$?" >> gpurun_out/bench_ns_$N.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$N.log 2>&1; echo "rc=$?" >> gpurun_out/bench_ref_$N.log
-for f in multigpu_check_$N bench_def_$N bench_ns_$N bench_ref_$N; do echo "== $f"; tail -n 3 gpurun_out/$f.log | cut -c1-1200; done
+for f in multigpu_check_$N bench_def_$N bench_ns_$N; do echo "== $f"; tail -n 3 gpurun_out/$f.log | cut -c1-1200; done
