@@ -345,6 +345,28 @@ int hbh_is_admissible(void* handle, int* ok, int* record)
   }
 }
 
+/* the adapter's wrappers of the AV glue (hexed_b200::av_*). what: 0 scale velocity (a = restore), 1 project forcing, 2 finish
+ * (a = mult, b = us_max, n = n_real; *out = residual), 3 interp_vertices (n = target, values = per element vertex), 4 swap, 5 apply_aux_bcs (n = mode) */
+int hbh_av_glue(void* handle, int what, double a, double b, int n, const double* values, int n_values, double* out)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    switch (what) {
+      case 0: hexed_b200::av_scale_velocity(h->mesh(), a != 0.); break;
+      case 1: hexed_b200::av_project_forcing(h->mesh()); break;
+      case 2: *out = hexed_b200::av_finish(h->mesh(), a, b, n); break;
+      case 3: hexed_b200::interp_vertices(h->mesh(), n, std::vector<double>(values, values + n_values)); break;
+      case 4: hexed_b200::av_swap(h->mesh()); break;
+      case 5: hexed_b200::apply_aux_bcs(h->mesh(), n); break;
+      default: throw std::runtime_error("unknown glue call");
+    }
+    return 0;
+  } catch (const std::exception& ex) {
+    h->error = ex.what();
+    return 1;
+  }
+}
+
 /* the adapter's flattening (device-free), translated back to the harness's slot numbering through the host pointers so the test
  * can compare it entry by entry with the tables the mesh was built from. counts[6] = n_car, n_def, n_face_slot, n_normal_slot,
  * n_boundary, n_null_normal */

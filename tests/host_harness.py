@@ -84,6 +84,7 @@ class HostHarness:
         L.hbh_add_device_bc.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, dp, C.c_int]
         L.hbh_apply_bcs.argtypes = [C.c_void_p, C.c_int]
         L.hbh_is_admissible.argtypes = [C.c_void_p, ip, ip]
+        L.hbh_av_glue.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_int, dp]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
         m = mesh
         self.m = m
@@ -151,6 +152,12 @@ class HostHarness:
         ok = np.zeros(1, np.int32); rec = np.zeros(max(self.m.n_elem, 1), np.int32)
         self._check(self.lib.hbh_is_admissible(self.h, _i(ok), _i(rec)))
         return bool(ok[0]), rec[:self.m.n_elem]
+
+    def av_glue(self, what, a=0., b=0., n=0, values=None):
+        v = np.ascontiguousarray(values if values is not None else np.zeros(1), dtype=np.float64)
+        out = np.zeros(1)
+        self._check(self.lib.hbh_av_glue(self.h, what, float(a), float(b), int(n), _d(v), v.size if values is not None else 0, _d(out)))
+        return float(out[0])
 
     def apply_state_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 0))
     def apply_flux_bcs(self): self._check(self.lib.hbh_apply_bcs(self.h, 1))

@@ -232,6 +232,41 @@ def test_adapter_is_admissible_emu(oracle, host_emu, resident):
     h.close()
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_av_glue_emu(oracle, host_emu, resident):
+    """hexed_b200::av_scale_velocity / av_project_forcing / av_finish / interp_vertices / av_swap through the pointer-graph adapter (the
+    basis operators come from `Kernel_mesh::basis`), against the numpy restatements, in both coherence modes"""
+    nd, rs = 2, 3
+    m, rng = soup(nd, rs, 19, n_car=6, n_def=8, n_ref=0)
+    basis = hb.gauss_legendre(rs)
+    m.elem_data[:, nd + 3:nd + 5] = rng.uniform(0., 2e-3, (m.n_elem, 2, m.nq))
+    m.elem_data[:, nd + 5:nd + 9] = rng.uniform(0., 1e-3, (m.n_elem, 4, m.nq))
+    m.elem_data[:, nd + 9:nd + 9 + rs] = rng.normal(1., .3, (m.n_elem, rs, m.nq))
+    m.nom_size = rng.choice([.25, .5, 1.], m.n_elem)
+    ref, work = m.copy(), m.copy()
+    w = np.asarray(basis.weight); orth = np.asarray(basis.orthogonal).reshape(rs, rs)[rs - 1]
+    vert = rng.uniform(0., 1., (m.n_elem, 2**nd))
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    h = H.HostHarness(host_emu, m, basis, seed=6)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    if resident:
+        h.to_device(H.ALL_ELEM | H.FACES)
+    h.av_glue(0); pyoracle.av_scale_velocity(ref)
+    h.av_glue(1); pyoracle.av_project_forcing(ref, w, orth)
+    got = h.av_glue(2, 0.7, 3e-3, 3); want = pyoracle.av_finish(ref, 0.7, 3e-3, 3, w)
+    h.av_glue(3, n=1, values=vert); pyoracle.interp_vertices(ref, 1, vert, interp)
+    h.av_glue(4); pyoracle.av_swap(ref)
+    if resident:
+        h.to_host(H.ALL_ELEM)
+    h.fetch(work)
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    assert abs(got - want) <= 1e-12*abs(want)
+    for lo, hi in ((0, nd + 2), (nd + 3, nd + 5), (nd + 5, nd + 9)):
+        assert rel_l2(work.elem_data[:, lo:hi], ref.elem_data[:, lo:hi]) <= 1e-14
+
+
 def check_adapter_device_bcs(oracle, host_emu, resident, nd, rs):
     """hexed_b200::add_device_bc / apply_state_bcs / apply_flux_bcs: a viscous step with every device-side boundary condition and no
     host boundary loop at all"""
