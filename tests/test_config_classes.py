@@ -1,0 +1,144 @@
+"""BASELINE configs C2 / C3 as parity cases on synthetic meshes of the same class:
+
+C3 (samples/cylinder): 2-D viscous Navier-Stokes, Sutherland viscosity / conductivity (include/Case.hil:83-90), isothermal No_slip wall
+   on one side and `characteristic` (Riemann_invariants) far field on the others, deformed quads, local time stepping -- every
+   ghost fill and flux condition on the device, several steps of Solver::update's loop.
+C2 (samples/naca0012): quads with hanging nodes, Euler stages followed by the artificial-viscosity smoothness update
+   (update_art_visc_smoothness) and a viscous stage that uses the new coefficient -- the shock-capturing cycle of that case.
+"""
+import numpy as np
+import pytest
+
+import hexed_b200 as hb
+import pyoracle
+from hexed_b200 import mesh as M
+from hexed_b200.kernels import Device, BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX
+from hexed_b200 import kernels as K
+from pyoracle import EULER, NAVIER_STOKES, ADVECTION, SMOOTH_AV
+from util import rel_l2, density_wave, freestream_state, assert_pde_parity, STATE_TOL
+
+
+def split_bcs_by_side(mesh, kinds):
+    """replace the single boundary condition of a box mesh by one per (dimension, sign) side; kinds[(d, sign)] = (kind, params)"""
+    src = mesh.bcs[0]
+    nd = mesh.n_dim
+    side = src["inside_slot"] % (2*nd)
+    bcs = []
+    for (d, sign), (kind, params) in kinds.items():
+        sel = np.nonzero(side == 2*d + sign)[0]
+        bcs.append(dict(kind=kind, params=params, **{k: np.ascontiguousarray(src[k][sel]) for k in ("inside_slot", "ghost_slot", "normal_slot", "con_index")}))
+    assert sum(b["inside_slot"].size for b in bcs) == src["inside_slot"].size
+    mesh.bcs = bcs
+    return mesh
+
+
+def run_cylinder_class(oracle, lib, n, rs, n_steps):
+    nd = 2
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd, mach=0.5)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_COPY, with_ldg=True)
+    wall = (M.BC_NO_SLIP, M.no_slip_params(M.THERMAL_ENERGY, 2.2e5))  # isothermal wall: prescribed specific energy
+    far = (M.BC_RIEMANN_INVARIANTS, fs)
+    split_bcs_by_side(m, {(0, 0): far, (0, 1): far, (1, 0): wall, (1, 1): far})
+    density_wave(m, basis, mach=0.5)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    visc_o, cond_o = pyoracle.sutherland(1.716e-5, 273., 111.), pyoracle.sutherland(.0241, 273., 194.)
+    visc_d, cond_d = K.sutherland(1.716e-5, 273., 111.), K.sutherland(.0241, 273., 194.)
+    dts = []
+    for _ in range(n_steps):
+        dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, True, visc_o, cond_o)
+        dt_d = dev.max_dt_navier_stokes(0.3, 0.3, True, visc_d, cond_d)
+        dts.append((dt_d, dt_o))
+        oracle.apply_state_bcs(ref); dev.apply_state_bcs()
+        oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0)
+        dev.compute_navier_stokes(dev.apply_flux_bcs, visc_d, cond_d, dt=dt_o, i_stage=0)
+        oracle.apply_state_bcs(ref); dev.apply_state_bcs()
+        oracle.compute_euler(basis, ref, dt=dt_o, i_stage=1)
+        dev.compute_euler(dt=dt_o, i_stage=1)
+    ok = dev.is_admissible()
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert ok == oracle.is_admissible(ref)[0]
+    assert_pde_parity(out, ref, dts)
+    assert rel_l2(out.state(), m.state()) > 1e-6  # the flow really moved
+
+
+def test_cylinder_class_emulated(oracle, emu_lib):
+    run_cylinder_class(oracle, emu_lib, n=4, rs=3, n_steps=2)
+
+
+@pytest.mark.gpu
+def test_cylinder_class_on_b200(oracle, gpu_lib):
+    run_cylinder_class(oracle, gpu_lib, n=24, rs=6, n_steps=10)
+
+
+def run_naca_class(oracle, lib, n, rs, n_cycles):
+    nd = 2
+    basis = hb.gauss_legendre(rs)
+    refine = np.zeros((n,)*nd, bool)
+    refine[n//3:2*n//3, n//3:2*n//3] = True   # a refined patch: hanging-node faces all around it
+    m = M.refined_box_mesh(nd, rs, n, basis, refine, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+    assert m.ref_face.shape[0] > 0
+    m.face_wide = np.zeros((m.n_face_slot, (nd + rs)*m.nfq))
+    density_wave(m, basis)
+    m.elem_data[:, nd + 9:nd + 9 + rs] = 1.
+    oracle.compute_write_face(basis, m); oracle.compute_prolong(basis, m)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    w = np.asarray(basis.weight); orth = np.asarray(basis.orthogonal).reshape(rs, rs)[rs - 1]
+    advect_length, n_real = 0.5/n, 3
+    diff_time = 0.5*advect_length**2/n_real
+    mult, us_max = 2.*advect_length, advect_length*0.5*np.sqrt(2*2.5e5/1.2)
+    inviscid_o, inviscid_d = pyoracle.inviscid(), K.inviscid()
+    dts = []
+    for _ in range(n_cycles):
+        # two Euler stages
+        dt_o = oracle.max_dt(EULER, basis, ref, 0.5, 0.5, False); dt_d = dev.max_dt_euler(0.5, 0.5, False)
+        dts.append((dt_d, dt_o))
+        for stage in (0, 1):
+            oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage)
+            dev.apply_state_bcs(); dev.compute_euler(dt=dt_o, i_stage=stage)
+        # update_art_visc_smoothness (reference src/Solver.cpp:457-581): one advection iteration, n_real + 1 smoothing sweeps
+        pyoracle.av_scale_velocity(ref); dev.av_scale_velocity()
+        oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref); dev.compute_write_face(); dev.compute_prolong()
+        oracle.max_dt(ADVECTION, basis, ref, 0.5, 1., True, advect_length=advect_length); dev.max_dt_advection(0.5, 1., True, advect_length)
+        oracle.compute_write_face(basis, ref, pde=ADVECTION); oracle.compute_prolong(basis, ref, pde=ADVECTION)
+        dev.compute_write_face_advection(); dev.compute_prolong_advection()
+        for i in (0, 1):
+            pyoracle.apply_aux_bcs(ref, BC_MODE_ADVECTION); oracle.compute_advection(basis, ref, advect_length, dt=1., i_stage=i)
+            dev.apply_aux_bcs(BC_MODE_ADVECTION); dev.compute_advection(advect_length, dt=1., i_stage=i)
+        pyoracle.av_project_forcing(ref, w, orth); dev.av_project_forcing(w, orth)
+        oracle.max_dt(SMOOTH_AV, basis, ref, 1., 0.4, True); dev.max_dt_smooth_av(1., 0.4, True)
+        oracle.compute_write_face(basis, ref, pde=SMOOTH_AV); oracle.compute_prolong(basis, ref)
+        dev.compute_write_face_smooth_av(); dev.compute_prolong()
+        for _sweep in range(n_real + 1):  # each sweep carries the forcing one real time step further down the chain of n_real
+            pyoracle.apply_aux_bcs(ref, BC_MODE_COPY_STATE); dev.apply_aux_bcs(BC_MODE_COPY_STATE)
+            oracle.compute_smooth_av(basis, ref, lambda: pyoracle.apply_aux_bcs(ref, BC_MODE_NEGATE_FLUX), diff_time, 1., dt=1., i_stage=0)
+            dev.compute_smooth_av(lambda: dev.apply_aux_bcs(BC_MODE_NEGATE_FLUX), diff_time, 1., dt=1., i_stage=0)
+        want = pyoracle.av_finish(ref, mult, us_max, n_real, w); got = dev.av_finish(mult, us_max, n_real, w)
+        assert abs(got - want) <= 1e-10*max(want, 1e-300)
+        oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref); dev.compute_write_face(); dev.compute_prolong()
+        # a stage with the artificial viscosity switched on (use_ldg() becomes true, src/Solver.cpp:117-120)
+        dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, False, inviscid_o, inviscid_o)
+        dt_d = dev.max_dt_navier_stokes(0.3, 0.3, False, inviscid_d, inviscid_d)
+        dts.append((dt_d, dt_o))
+        oracle.apply_state_bcs(ref); dev.apply_state_bcs()
+        oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), inviscid_o, inviscid_o, dt=dt_o, i_stage=0)
+        dev.compute_navier_stokes(dev.apply_flux_bcs, inviscid_d, inviscid_d, dt=dt_o, i_stage=0)
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert_pde_parity(out, ref, dts)
+    assert out.elem_data[:, nd + 3].max() > 0.   # a nonzero artificial viscosity came out of the smoothness update
+
+
+def test_naca_class_emulated(oracle, emu_lib):
+    run_naca_class(oracle, emu_lib, n=3, rs=3, n_cycles=1)
+
+
+@pytest.mark.gpu
+def test_naca_class_on_b200(oracle, gpu_lib):
+    run_naca_class(oracle, gpu_lib, n=12, rs=6, n_cycles=3)
