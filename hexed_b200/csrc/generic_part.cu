@@ -796,11 +796,262 @@ int launch_ns_reconcile_bulk(hexed_b200_ctx* c, const GArgs& a, int deformed)
   }
 }
 
+/* ---------------- Navier-Stokes Local, 2-D, batched line-task formulation ----------------
+ * The cylinder-class configurations (samples/cylinder, BASELINE config 3) are 2-D: an element is only row_size^2 points, so one CTA
+ * takes a BATCH of B consecutive elements and runs the phases of ns_local_line_kernel over all of them at once: (element, line,
+ * component) gradient tasks per direction sub-phase, pointwise fluxes, (element, direction, line) derivative tasks, pointwise update.
+ * Same arithmetic as g_local_kernel<2, RS, PdeNs<2, RS, true>, DEF> without the modal filter (reference include/Spatial.hpp:326-509).
+ * Per element in shared memory: state | flux faces | region A = [LDG faces | reference normals | face normals] | G, fetched by
+ * per-element 1-D bulk TMA copies (thread i issues the copies of element i) onto one mbarrier; F aliases region A starting two
+ * fields before the normals, so that its fields 2..5 coincide with the four reference normals (see NsCfg). 6.7 KB per element at
+ * row size 6 -> B = 10, 67 KB per CTA, three CTAs per SM. The generic point-per-thread kernel it replaces took 5.3 ms per launch at
+ * 1 M elements, 3.5x the Euler Local kernel. */
+template <int RS, bool DEF>
+struct Ns2Cfg
+{
+  static constexpr int ND = 2, nq = RS*RS, nfq = RS, nv = 4, lines = ND*nfq;
+  static constexpr int B = 128/lines; // elements per CTA
+  static constexpr int threads = 128;
+  static constexpr int s_state = 0, s_fc = s_state + nv*nq, s_ldg = s_fc + 2*ND*nv*nfq;
+  static constexpr int s_nrml = s_ldg + 2*ND*nv*nfq, s_fn = s_nrml + (DEF ? ND*ND*nq : 0);
+  static constexpr int a_end = s_fn + (DEF ? 2*ND*ND*nfq : 0);
+  static constexpr int lead = (2*ND*nv*nfq)/nq; // whole fields that fit in the LDG faces in front of the normals
+  static constexpr int s_flux = s_nrml - lead*nq;
+  static constexpr int s_grad = (a_end > s_flux + ND*nv*nq) ? a_end : s_flux + ND*nv*nq;
+  static constexpr int elem_doubles = s_grad + ND*nv*nq;
+  static_assert(elem_doubles % 2 == 0 && s_fc % 2 == 0 && s_ldg % 2 == 0 && s_nrml % 2 == 0 && s_fn % 2 == 0, "16-byte alignment of the bulk copies");
+  static constexpr size_t smem_bytes = sizeof(double)*B*elem_doubles + 2*sizeof(mbar_t);
+};
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(Ns2Cfg<RS, DEF>::threads, 3)
+ns_local_line2d_kernel(GArgs a, Ops ops)
+{
+  using C = Ns2Cfg<RS, DEF>;
+  using P = PdeNs<2, RS, true>;
+  constexpr int ND = 2, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads, B = C::B;
+  constexpr int cs = nv > RS ? nv : RS;
+  HB_DYN_SMEM(double, smem);
+  mbar_t* bar = reinterpret_cast<mbar_t*>(smem + B*C::elem_doubles);
+  const int t = threadIdx.x;
+  const int e0 = a.elem_begin + blockIdx.x*B;
+  if (e0 >= a.elem_end) return;
+  const int n = a.elem_end - e0 < B ? a.elem_end - e0 : B; // elements of this batch
+  if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncthreads();
+  constexpr unsigned b_field = sizeof(double)*nq, b_face = sizeof(double)*2*ND*nv*nfq;
+  constexpr unsigned b_elem = nv*b_field + 2*b_face + (DEF ? ND*ND*b_field + (unsigned)sizeof(double)*2*ND*ND*nfq : 0u);
+  if (t == 0) mbar_arrive_expect_tx(bar, b_elem*n);
+  __syncthreads(); // the expectation is posted before any copy can complete
+  if (t < n) {
+    const int e = e0 + t;
+    double* base = smem + t*C::elem_doubles;
+    bulk_g2s(base + C::s_state, a.ed.state + (size_t)e*nv*nq, nv*b_field, bar);
+    bulk_g2s(base + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
+    bulk_g2s(base + C::s_fc, a.faces + (size_t)e*2*ND*wl, b_face, bar);
+    if constexpr (DEF) {
+      bulk_g2s(base + C::s_nrml, a.refn + (size_t)(e - a.n_car)*ND*ND*nq, ND*ND*b_field, bar);
+      bulk_g2s(base + C::s_fn, a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq, sizeof(double)*2*ND*ND*nfq, bar);
+    }
+  }
+  // per-point scalars of the batch are contiguous runs in HBM: prefetch, read in P2 / P4
+  const double* g_tss = a.ed.tss + (size_t)e0*nq;
+  const double* g_av = a.ed.av + (size_t)e0*2*nq;
+  [[maybe_unused]] const double* g_det = DEF ? a.det + (size_t)(e0 - a.n_car)*nq : nullptr;
+  for (int i = t*16; i < n*nq; i += T*16) { prefetch_l1(g_tss + i); if constexpr (DEF) prefetch_l1(g_det + i); }
+  for (int i = t*16; i < n*2*nq; i += T*16) prefetch_l1(g_av + i);
+  mbar_wait(bar, 0);
+
+  /* ---- P1: gradient ---- */
+  if constexpr (DEF) {
+    const int le = t/(nfq*ND), j = (t/nfq) % ND, l = t % nfq; // element of the batch, physical component, line
+    const bool on = t < B*nfq*ND && le < n;
+    double* eb = smem + le*C::elem_doubles;
+    const double inv_nom = on ? 1./a.nom[e0 + le] : 0.;
+    auto sub_phase = [&](auto dc) {
+      constexpr int d = decltype(dc)::value;
+      if (on) {
+        constexpr int stride = d == 0 ? RS : 1;
+        const int q0 = d == 0 ? l : l*RS;
+        const double* S = eb + C::s_state; const double* rn = eb + C::s_nrml; const double* fn = eb + C::s_fn; const double* fldg = eb + C::s_ldg;
+        double* G = eb + C::s_grad;
+        double nk[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*nq + q0 + k*stride]*inv_nom;
+        const double fn0 = fn[((2*d)*ND + j)*nfq + l]*inv_nom, fn1 = fn[((2*d + 1)*ND + j)*nfq + l]*inv_nom;
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          double p[RS];
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) p[k] = nk[k]*S[v*nq + q0 + k*stride];
+          const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            double* g = G + (v*ND + j)*nq + q0 + i*stride;
+            if (d == 0) *g = acc; else *g += acc;
+          }
+        }
+      }
+      __syncthreads();
+    };
+    sub_phase(IC<0>{}); sub_phase(IC<1>{});
+  } else {
+    const int le = t/C::lines, d = (t % C::lines)/nfq, l = t % nfq;
+    if (t < B*C::lines && le < n) {
+      double* eb = smem + le*C::elem_doubles;
+      const double inv_nom = 1./a.nom[e0 + le];
+      const int stride = d == 0 ? RS : 1;
+      const int q0 = d == 0 ? l : l*RS;
+      const double* S = eb + C::s_state; const double* fldg = eb + C::s_ldg;
+      double* G = eb + C::s_grad;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double p[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
+        const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          G[(v*ND + d)*nq + q0 + i*stride] = acc*inv_nom;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  /* ---- P2: pointwise fluxes ---- */
+  for (int pt = t; pt < n*nq; pt += T) {
+    const int pe = pt/nq, q = pt % nq;
+    double* eb = smem + pe*C::elem_doubles;
+    const double* S = eb + C::s_state; [[maybe_unused]] const double* rn = eb + C::s_nrml;
+    double* G = eb + C::s_grad; double* F = eb + C::s_flux;
+    typename P::template Comp<ND> comp;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) comp.state[v] = S[v*nq + q];
+    comp.state[nv] = g_av[(size_t)pe*2*nq + q];
+    comp.state[nv + 1] = g_av[(size_t)pe*2*nq + nq + q];
+    if constexpr (DEF) {
+      const double inv_det = 1./g_det[pt];
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.normal[j][d] = rn[(d*ND + j)*nq + q];
+      #pragma unroll
+      for (int v = 0; v < nv; ++v)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q]*inv_det;
+    } else {
+      #pragma unroll
+      for (int v = 0; v < nv; ++v)
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*nq + q];
+    }
+    comp.compute_flux_conv(a.pp);
+    comp.compute_flux_diff(a.pp);
+    #pragma unroll
+    for (int d = 0; d < ND; ++d)
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        F[(d*nv + v)*nq + q] = comp.flux_conv[v][d]; // fields 2..5 overwrite this point's own normals, read above
+        G[(d*nv + v)*nq + q] = comp.flux_diff[v][d];
+      }
+  }
+  __syncthreads();
+
+  /* ---- P3: line derivatives in place, diffusive flux to the LDG faces ---- */
+  {
+    const int le = t/C::lines, d = (t % C::lines)/nfq, l = t % nfq;
+    if (t < B*C::lines && le < n) {
+      double* eb = smem + le*C::elem_doubles;
+      const double* fc = eb + C::s_fc;
+      double* G = eb + C::s_grad; double* F = eb + C::s_flux;
+      const int stride = d == 0 ? RS : 1;
+      const int q0 = d == 0 ? l : l*RS;
+      double* fl = a.faces_ldg + (size_t)(e0 + le)*2*ND*wl;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double* row = F + (d*nv + v)*nq + q0;
+        double f[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
+        const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          row[i*stride] = -acc;
+        }
+        double* drow = G + (d*nv + v)*nq + q0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
+        double x0 = 0, x1 = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) { x0 += ops.bnd[0][k]*f[k]; x1 += ops.bnd[1][k]*f[k]; }
+        fl[(size_t)(2*d)*wl + v*nfq + l] = x0;
+        fl[(size_t)(2*d + 1)*wl + v*nfq + l] = x1;
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
+          drow[i*stride] = -acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  /* ---- P4: combine and update ---- */
+  for (int pt = t; pt < n*nq; pt += T) {
+    const int pe = pt/nq, q = pt % nq;
+    const int e = e0 + pe;
+    const double* eb = smem + pe*C::elem_doubles;
+    const double* S = eb + C::s_state; const double* G = eb + C::s_grad; const double* F = eb + C::s_flux;
+    const double nom = a.nom[e];
+    double mult; // update*tss/nom/det with one division (<= 1 ulp)
+    if constexpr (DEF) mult = a.update*g_tss[pt]/(nom*g_det[pt]);
+    else mult = a.update*g_tss[pt]/nom;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      double r0 = 0., r1 = 0.;
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) { r0 += F[(d*nv + v)*nq + q]; r1 += G[(d*nv + v)*nq + q]; }
+      double* cache = a.ed.cache + ((size_t)e*cs + v)*nq + q;
+      double u = r0;
+      *cache = u;
+      u += r1;
+      u *= mult;
+      if (a.compute_residual) *cache = u;
+      else a.ed.state[((size_t)e*nv + v)*nq + q] = S[v*nq + q] + u;
+    }
+  }
+}
+
 /* returns -1 when the combination is not covered and the caller should use g_local_kernel */
 template <int ND, int RS>
 int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
 {
-  if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
+  if constexpr (ND == 2 && (RS == 4 || RS == 6 || RS == 8)) {
+    if (a.use_filter || !c->use_pipe) return -1;
+    using C0 = Ns2Cfg<RS, false>;
+    const int grid = (a.elem_end - a.elem_begin + C0::B - 1)/C0::B;
+    if (deformed) { using C = Ns2Cfg<RS, true>; auto k = ns_local_line2d_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    else { using C = Ns2Cfg<RS, false>; auto k = ns_local_line2d_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    return 0;
+  } else if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
     if (a.use_filter || !c->use_pipe) return -1;
     const int grid = a.elem_end - a.elem_begin;
     if (deformed) { using C = NsCfg<RS, true>; auto k = ns_local_line_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }

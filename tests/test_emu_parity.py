@@ -194,3 +194,24 @@ def test_shared_normals_soup(oracle, emu_lib, nd, rs):
 def test_calc_jacobian_box(emu_lib, nd, rs, n):
     from util import check_calc_jacobian_box
     check_calc_jacobian_box(emu_lib, nd, rs, n)
+
+
+@pytest.mark.parametrize("rs,n", [(4, 5), (6, 4), (8, 3)])
+@pytest.mark.parametrize("kind", ["soup", "box_car", "box_def"])
+def test_navier_stokes_2d_line_kernel(oracle, emu_lib, kind, rs, n):
+    """2-D row size 4 / 6 / 8 Navier-Stokes takes the batched line-task Local kernel (ns_local_line2d_kernel): several batches per
+    launch, the last one partial"""
+    rng = np.random.default_rng(78)
+    basis = hb.gauss_legendre(rs)
+    if kind == "soup":
+        m = M.soup_mesh(2, rs, rng, n_car=7, n_def=15, n_ref=2, with_ldg=True)
+        M.random_flow_state(m, rng)
+    else:
+        m = M.box_mesh(2, rs, n, basis, deformed=kind == "box_def", bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+        density_wave(m, basis)
+        oracle.compute_write_face(basis, m)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2)
+    assert_pde_parity(out, ref, dts)
+    out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
+    assert_pde_parity(out, ref, dts)

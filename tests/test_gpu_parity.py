@@ -296,3 +296,19 @@ def test_shared_normals_soup(oracle, gpu_lib, nd, rs):
 def test_calc_jacobian_box(gpu_lib, nd, rs, n):
     from util import check_calc_jacobian_box
     check_calc_jacobian_box(gpu_lib, nd, rs, n)
+
+
+@pytest.mark.parametrize("rs,n", [(4, 40), (6, 37), (8, 20)])
+@pytest.mark.parametrize("deformed", [False, True])
+def test_navier_stokes_2d_line_kernel(oracle, gpu_lib, deformed, rs, n):
+    """the cylinder-class kernel: 2-D batched line-task Navier-Stokes Local (partial last batch: n^2 is not a multiple of the batch)"""
+    rng = np.random.default_rng(79)
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(2, rs, n, basis, deformed=deformed, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1)
+    assert_pde_parity(out, ref, dts)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
+    assert_pde_parity(out, ref, dts)
