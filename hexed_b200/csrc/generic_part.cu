@@ -781,11 +781,102 @@ ns_reconcile_bulk_kernel(GArgs a, Ops ops)
   }
 }
 
+/* 2-D version: a batch of B consecutive elements per CTA (their state / LDG faces / tss / determinant are four contiguous runs) */
+template <int RS, bool DEF>
+struct NsRec2Cfg
+{
+  static constexpr int ND = 2, nq = RS*RS, nfq = RS, nv = 4, B = 16, threads = 256;
+  static constexpr int s_state = 0, s_ldg = s_state + B*nv*nq, s_tss = s_ldg + B*2*ND*nv*nfq, s_det = s_tss + B*nq;
+  static constexpr int smem_doubles = s_det + (DEF ? B*nq : 0);
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 2*sizeof(mbar_t);
+};
+
+template <int RS, bool DEF>
+__global__ void __launch_bounds__(NsRec2Cfg<RS, DEF>::threads)
+ns_reconcile_bulk2d_kernel(GArgs a, Ops ops)
+{
+  using C = NsRec2Cfg<RS, DEF>;
+  constexpr int ND = 2, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads, B = C::B;
+  HB_DYN_SMEM(double, smem);
+  double* S = smem + C::s_state;
+  const double* fldg = smem + C::s_ldg;
+  const double* s_tss = smem + C::s_tss;
+  const double* s_det = smem + C::s_det;
+  mbar_t* bar = reinterpret_cast<mbar_t*>(smem + C::smem_doubles);
+  const int t = threadIdx.x;
+  const int e0 = a.elem_begin + blockIdx.x*B;
+  if (e0 >= a.elem_end) return;
+  const int n = a.elem_end - e0 < B ? a.elem_end - e0 : B;
+  if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncthreads();
+  if (t == 0) {
+    const unsigned b_field = sizeof(double)*nq*n, b_face = sizeof(double)*2*ND*nv*nfq*n;
+    mbar_arrive_expect_tx(bar, nv*b_field + b_face + b_field + (DEF ? b_field : 0u));
+    bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e0*2*ND*wl, b_face, bar);
+    bulk_g2s(S, a.ed.state + (size_t)e0*nv*nq, nv*b_field, bar);
+    bulk_g2s(smem + C::s_tss, a.ed.tss + (size_t)e0*nq, b_field, bar);
+    if constexpr (DEF) bulk_g2s(smem + C::s_det, a.det + (size_t)(e0 - a.n_car)*nq, b_field, bar);
+  }
+  mbar_wait(bar, 0);
+  for (int pt = t; pt < n*nq; pt += T) {
+    const int pe = pt/nq, q = pt % nq;
+    double r[nv];
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) r[v] = 0.;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const int stride = d == 0 ? RS : 1;
+      const int node = (q/stride) % RS;
+      const int fq = (q/(stride*RS))*stride + q % stride;
+      const double l0 = ops.lift[node][0], l1 = ops.lift[node][1];
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double acc = 0;
+        acc += l0*fldg[(pe*2*ND + 2*d)*wl + v*nfq + fq];
+        acc += l1*fldg[(pe*2*ND + 2*d + 1)*wl + v*nfq + fq];
+        r[v] -= acc;
+      }
+    }
+    double mult = a.update*s_tss[pt]/a.nom[e0 + pe];
+    if constexpr (DEF) mult /= s_det[pt];
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      const double u = S[(pe*nv + v)*nq + q] + r[v]*mult;
+      S[(pe*nv + v)*nq + q] = u;
+      a.ed.state[((size_t)(e0 + pe)*nv + v)*nq + q] = u;
+    }
+  }
+  __syncthreads();
+  for (int item = t; item < n*ND*nv*nfq; item += T) {
+    const int pe = item/(ND*nv*nfq), rest = item % (ND*nv*nfq);
+    const int d = rest/(nv*nfq), v = (rest/nfq) % nv, fq = rest % nfq;
+    const int stride = d == 0 ? RS : 1;
+    const int base = (fq/stride)*stride*RS + fq % stride;
+    double x0 = 0, x1 = 0;
+    #pragma unroll
+    for (int k = 0; k < RS; ++k) {
+      const double x = S[(pe*nv + v)*nq + base + k*stride];
+      x0 += ops.bnd[0][k]*x;
+      x1 += ops.bnd[1][k]*x;
+    }
+    double* dst = a.faces + (size_t)(e0 + pe)*2*ND*wl;
+    dst[(size_t)(2*d)*wl + v*nfq + fq] = x0;
+    dst[(size_t)(2*d + 1)*wl + v*nfq + fq] = x1;
+  }
+}
+
 /* returns -1 when the combination is not covered and the caller should use g_reconcile_kernel */
 template <int ND, int RS>
 int launch_ns_reconcile_bulk(hexed_b200_ctx* c, const GArgs& a, int deformed)
 {
-  if constexpr (ND == 3 && (RS == 2 || RS == 4 || RS == 6)) { // bulk copies need 16-byte multiples: nq*8 with even row size
+  if constexpr (ND == 2 && (RS == 2 || RS == 4 || RS == 6 || RS == 8)) {
+    if (a.use_filter || a.compute_residual || !c->use_pipe) return -1;
+    using C0 = NsRec2Cfg<RS, false>;
+    const int grid = (a.elem_end - a.elem_begin + C0::B - 1)/C0::B;
+    if (deformed) { using C = NsRec2Cfg<RS, true>; auto k = ns_reconcile_bulk2d_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    else { using C = NsRec2Cfg<RS, false>; auto k = ns_reconcile_bulk2d_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+    return 0;
+  } else if constexpr (ND == 3 && (RS == 2 || RS == 4 || RS == 6)) { // bulk copies need 16-byte multiples: nq*8 with even row size
     if (a.use_filter || a.compute_residual || !c->use_pipe) return -1;
     const int grid = a.elem_end - a.elem_begin;
     if (deformed) { using C = NsRecCfg<RS, true>; auto k = ns_reconcile_bulk_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }

@@ -119,7 +119,7 @@ def run_naca_class(oracle, lib, n, rs, n_cycles):
             oracle.compute_smooth_av(basis, ref, lambda: pyoracle.apply_aux_bcs(ref, BC_MODE_NEGATE_FLUX), diff_time, 1., dt=1., i_stage=0)
             dev.compute_smooth_av(lambda: dev.apply_aux_bcs(BC_MODE_NEGATE_FLUX), diff_time, 1., dt=1., i_stage=0)
         want = pyoracle.av_finish(ref, mult, us_max, n_real, w); got = dev.av_finish(mult, us_max, n_real, w)
-        assert abs(got - want) <= 1e-10*max(want, 1e-300)
+        assert abs(got - want) <= 1e-10*want + 1e-14*us_max  # on a smooth flow the residual is round-off sized
         oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref); dev.compute_write_face(); dev.compute_prolong()
         # a stage with the artificial viscosity switched on (use_ldg() becomes true, src/Solver.cpp:117-120)
         dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, False, inviscid_o, inviscid_o)
