@@ -65,3 +65,14 @@ def test_adapter_defines_reference_entry_points():
                "compute_prolong", "compute_restrict", "compute_prolong_advection", "face_permutation", "compute_write_face",
                "compute_write_face_advection", "compute_write_face_smooth_av", "stabilizing_art_visc"):
         assert re.search(r" T hexed::%s\(" % fn, syms), fn
+
+
+def test_new_entry_points_are_declared_everywhere():
+    """the SURVEY section 8 f entry points exist in the header (and, by test_header_symbols_exported_and_bound, in the library and the
+    ctypes table)"""
+    names = declared_functions()
+    for name in ("hexed_b200_is_admissible", "hexed_b200_download_record", "hexed_b200_set_jacobian", "hexed_b200_calc_shared_normals",
+                 "hexed_b200_vertex_topology", "hexed_b200_share_vertex_data", "hexed_b200_fix_admis_spread", "hexed_b200_av_scale_velocity",
+                 "hexed_b200_av_project_forcing", "hexed_b200_av_finish", "hexed_b200_interp_vertices", "hexed_b200_av_swap",
+                 "hexed_b200_apply_aux_bcs"):
+        assert name in names and name in SIGNATURES
