@@ -84,6 +84,11 @@ def run_naca_class(oracle, lib, n, rs, n_cycles):
     assert m.ref_face.shape[0] > 0
     m.face_wide = np.zeros((m.n_face_slot, (nd + rs)*m.nfq))
     density_wave(m, basis)
+    # a steep (under-resolved) front in velocity, the thing the smoothness indicator exists to find: on a smooth flow the
+    # artificial viscosity it returns is round-off sized and there would be nothing to compare
+    x = np.asarray(m.qpoint_pos)
+    front = 1. + 0.3*np.tanh((x[:, 0] + 0.5*x[:, 1] - 0.7)/0.01)
+    m.state()[:, :nd] *= front[:, None, :]   # momentum only: the indicator advects along the velocity, so the velocity must jump
     m.elem_data[:, nd + 9:nd + 9 + rs] = 1.
     oracle.compute_write_face(basis, m); oracle.compute_prolong(basis, m)
     ref = m.copy()
@@ -101,15 +106,17 @@ def run_naca_class(oracle, lib, n, rs, n_cycles):
         for stage in (0, 1):
             oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage)
             dev.apply_state_bcs(); dev.compute_euler(dt=dt_o, i_stage=stage)
-        # update_art_visc_smoothness (reference src/Solver.cpp:457-581): one advection iteration, n_real + 1 smoothing sweeps
+        # update_art_visc_smoothness (reference src/Solver.cpp:457-581): row_size advection iterations, n_real + 1 smoothing sweeps
         pyoracle.av_scale_velocity(ref); dev.av_scale_velocity()
         oracle.compute_write_face(basis, ref); oracle.compute_prolong(basis, ref); dev.compute_write_face(); dev.compute_prolong()
         oracle.max_dt(ADVECTION, basis, ref, 0.5, 1., True, advect_length=advect_length); dev.max_dt_advection(0.5, 1., True, advect_length)
-        oracle.compute_write_face(basis, ref, pde=ADVECTION); oracle.compute_prolong(basis, ref, pde=ADVECTION)
-        dev.compute_write_face_advection(); dev.compute_prolong_advection()
-        for i in (0, 1):
-            pyoracle.apply_aux_bcs(ref, BC_MODE_ADVECTION); oracle.compute_advection(basis, ref, advect_length, dt=1., i_stage=i)
-            dev.apply_aux_bcs(BC_MODE_ADVECTION); dev.compute_advection(advect_length, dt=1., i_stage=i)
+        for _it in range(rs):  # every iteration raises the polynomial degree of the advection states in the node variable by one: the
+            # projection on the Legendre polynomial of degree row_size - 1 is round-off until row_size - 1 of them have run
+            oracle.compute_write_face(basis, ref, pde=ADVECTION); oracle.compute_prolong(basis, ref, pde=ADVECTION)
+            dev.compute_write_face_advection(); dev.compute_prolong_advection()
+            for i in (0, 1):
+                pyoracle.apply_aux_bcs(ref, BC_MODE_ADVECTION); oracle.compute_advection(basis, ref, advect_length, dt=1., i_stage=i)
+                dev.apply_aux_bcs(BC_MODE_ADVECTION); dev.compute_advection(advect_length, dt=1., i_stage=i)
         pyoracle.av_project_forcing(ref, w, orth); dev.av_project_forcing(w, orth)
         oracle.max_dt(SMOOTH_AV, basis, ref, 1., 0.4, True); dev.max_dt_smooth_av(1., 0.4, True)
         oracle.compute_write_face(basis, ref, pde=SMOOTH_AV); oracle.compute_prolong(basis, ref)
@@ -131,8 +138,22 @@ def run_naca_class(oracle, lib, n, rs, n_cycles):
     out = m.copy()
     dev.sync_to_host(out)
     dev.close()
-    assert_pde_parity(out, ref, dts)
-    assert out.elem_data[:, nd + 3].max() > 0.   # a nonzero artificial viscosity came out of the smoothness update
+    for dt_d, dt_o in dts:
+        assert abs(dt_d - dt_o) <= 1e-13*abs(dt_o)
+    assert rel_l2(out.state(), ref.state()) <= STATE_TOL
+    assert rel_l2(out.face_state, ref.face_state) <= STATE_TOL
+    # the LDG faces hold the artificial-viscosity flux, proportional to the coefficient discussed below: held to the flux scale
+    assert np.abs(out.face_ldg - ref.face_ldg).max() <= STATE_TOL*np.abs(ref.face_state).max()
+    assert rel_l2(out.elem_data[:, nd + 9:nd + 9 + rs], ref.elem_data[:, nd + 9:nd + 9 + rs]) <= STATE_TOL  # advection states
+    # The smoothness indicator is the SQUARE of the projection of the advection states (all ~1) on the top Legendre mode: forcing =
+    # proj^2 * 2E/rho with |proj| ~ 1e-6 here, so round-off eps*|adv| in the projection is a relative 1e-9 in the forcing and in the
+    # AV coefficient that is smoothed from it -- between two CPU builds of the oracle just as between oracle and device. Parity is
+    # therefore asked of what the arithmetic actually produces to working precision, the projection: sqrt(forcing) ~ |proj|*sqrt(2E/rho).
+    spec = float(np.sqrt(2*ref.state()[:, nd + 1]/ref.state()[:, nd]).max())
+    for lo, hi, scale in ((nd + 5, nd + 9, 1.), (nd + 3, nd + 4, mult)):
+        a, b = np.sqrt(np.abs(out.elem_data[:, lo:hi])/scale), np.sqrt(np.abs(ref.elem_data[:, lo:hi])/scale)
+        assert np.isfinite(b).all() and np.abs(a - b).max() <= 1e-12*spec, (lo, np.abs(a - b).max(), spec)
+    assert out.elem_data[:, nd + 3].max() > 1e-12*us_max and ref.elem_data[:, nd + 5].max() > 0.
 
 
 def test_naca_class_emulated(oracle, emu_lib):
