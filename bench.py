@@ -338,6 +338,28 @@ def main():
     admis_stat = [s for s in dev.kernel_stats() if s["name"] == "check admis."]
     aux = {"is_admissible_ms_per_call": admis_stat[0]["device_seconds"]/3*1e3 if admis_stat else None, "admissible": all(admissible),
            "is_admissible_bytes": ne*(nv*nq + 2*nd*nv*m.nfq)*8}
+    if not viscous and halo is None:
+        # the same check with HEXED_B200_OPT_FUSED_ADMIS: the Local kernels leave the bits, is_admissible after each stage reduces them
+        from hexed_b200.kernels import OPT_FUSED_ADMIS
+        dev.set_option(OPT_FUSED_ADMIS, 1)
+
+        def step_checked():
+            dt = dev.max_dt_euler(0.7, 0.7, False)
+            ok = True
+            for stage in (0, 1):
+                dev.apply_state_bcs()
+                dev.compute_euler(dt=dt, i_stage=stage)
+                ok = dev.is_admissible() and ok
+            return ok
+        step_checked()
+        fused_sec = timed(step_checked, n_prof)
+        dev.reset_stats(); dev.set_timing(True)
+        ok = step_checked()
+        dev.set_timing(False)
+        st = [s_ for s_ in dev.kernel_stats() if s_["name"] == "check admis."]
+        aux["fused_admis"] = {"ms_per_step_with_a_check_after_every_stage": fused_sec/n_prof*1e3, "is_admissible_ms_per_call": st[0]["device_seconds"]/2*1e3 if st else None,
+                              "admissible": bool(ok)}
+        dev.set_option(OPT_FUSED_ADMIS, 0)
     stage_gbs = value/world*(alg["stage"]*8/float(nv*nq))/1e9
 
     # ---- end to end through the public API with HOST buffers: the boundary condition is applied by the host (as the reference's

@@ -39,7 +39,7 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->nom); dev_free(c->vtss); dev_free(c->uncert); dev_free(c->refn); dev_free(c->det);
   dev_free(c->face_state); dev_free(c->face_ldg); dev_free(c->face_wide); dev_free(c->normals);
   dev_free(c->car_con); dev_free(c->def_con); dev_free(c->ref_face); dev_free(c->pre_prolong);
-  dev_free(c->cfl_approx); invalidate_cfl_cache(c); c->tss_is_one = false;
+  dev_free(c->cfl_approx); invalidate_cfl_cache(c); c->tss_is_one = false; // (also clears the fused admissibility flags)
   dev_free(c->record); dev_free(c->elem_vertex); dev_free(c->matchers); dev_free(c->vertex_vals); dev_free(c->vertex_scratch);
   c->n_vertex = c->n_match = 0;
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
@@ -291,6 +291,7 @@ int hexed_b200_upload(hexed_b200_ctx* c, int which, const double* src, size_t fi
   if (first + n > count) return fail(c, HEXED_B200_BAD_ARGUMENT, "upload range out of bounds");
   if (!n) return 0;
   if (which == HEXED_B200_VERTEX_TSS) invalidate_cfl_cache(c);
+  if (which == HEXED_B200_FACE_STATE) invalidate_admis(c);
   HB_CUDA(c, cudaMemcpyAsync(*arr + first*item, src, sizeof(double)*n*item, cudaMemcpyDefault, c->stream));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -887,6 +888,7 @@ int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
 {
   if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; return 0; }
   if (option == HEXED_B200_OPT_CFL_CACHE) { c->use_cfl_cache = value != 0; invalidate_cfl_cache(c); return 0; }
+  if (option == HEXED_B200_OPT_FUSED_ADMIS) { c->use_fused_admis = value != 0; invalidate_admis(c); return 0; }
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown option");
 }
 

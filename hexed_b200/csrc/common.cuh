@@ -94,6 +94,12 @@ struct hexed_b200_ctx
   bool use_cfl_cache = false; // measured break-even on B200 (profiles/r01g_ncu_full_euler.md): off unless asked for
   float* cfl_approx = nullptr;
   bool cfl_valid[2] = {false, false};
+  // fused admissibility (HEXED_B200_OPT_FUSED_ADMIS): the pipelined Local kernels leave Element::record-style bits of the state and
+  // faces they have just written; admis_valid[0|1] = the bits of every Cartesian | deformed element describe the CURRENT state and
+  // element faces. Every other writer of element state or element faces clears the flags (invalidate_admis), and is_admissible then
+  // runs its full scan.
+  bool use_fused_admis = false;
+  bool admis_valid[2] = {false, false};
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
   // vertex topology of the epoch (hexed_b200_vertex_topology) and per-element-vertex scratch (vertex_fix_admis_coef / vertex_elwise_av)
   int* elem_vertex = nullptr; int n_vertex = 0; int* matchers = nullptr; int n_match = 0;
@@ -132,7 +138,9 @@ struct StatScope
     }
   }
 };
-inline void invalidate_cfl_cache(hexed_b200_ctx* c) { c->cfl_valid[0] = c->cfl_valid[1] = false; }
+inline void invalidate_admis(hexed_b200_ctx* c) { c->admis_valid[0] = c->admis_valid[1] = false; }
+/* called by everything that rewrites the flow state (or the vertex spacing) outside the pipelined Local kernels */
+inline void invalidate_cfl_cache(hexed_b200_ctx* c) { c->cfl_valid[0] = c->cfl_valid[1] = false; invalidate_admis(c); }
 inline void count_launch(hexed_b200_ctx* c, int stat_id) { ++c->launches; ++c->stats[stat_id].launches; }
 
 /* launchers implemented in the kernel translation units; return a HEXED_B200_* code */

@@ -1354,6 +1354,7 @@ int g_neighbor(hexed_b200_ctx* c, int deformed, const PdeParams& pp, bool reconc
   StatScope scope(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR, n_con);
   GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc; // also allocates the LDG face storage on first use
   if (!n_con) return 0;
+  invalidate_admis(c);
   a.con = (deformed ? c->def_con : c->car_con) + (size_t)first*4; a.n_con = n_con;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
@@ -1428,6 +1429,7 @@ int g_local(hexed_b200_ctx* c, int deformed, hexed_b200_options o, const PdePara
 int g_write_face(hexed_b200_ctx* c, const PdeParams& pp)
 {
   StatScope scope(c, ST_WRITE_FACE, c->n_elem);
+  invalidate_admis(c);
   GArgs a; int rc = fill_args(c, a, pp); if (rc) return rc;
   if (!c->n_elem) return 0;
   return dispatch(c, [&](auto nd, auto rs) {

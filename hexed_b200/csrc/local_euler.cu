@@ -241,6 +241,7 @@ int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o)
     if (rc >= 0) return rc;
   }
   c->cfl_valid[deformed ? 1 : 0] = false; // the general kernel rewrites the state without leaving CFL ratios behind
+  invalidate_admis(c);
   LocalArgs a;
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
@@ -271,6 +272,7 @@ int launch_write_face(hexed_b200_ctx* c)
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   StatScope scope(c, ST_WRITE_FACE, c->n_elem);
   if (!c->n_elem) return 0;
+  invalidate_admis(c);
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     using C = LocalCfg<ND, RS>;

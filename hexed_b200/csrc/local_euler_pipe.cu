@@ -48,6 +48,7 @@ struct PipeArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
+  int* record; // non-null: leave Element::record-style admissibility bits of the NEW state and faces per element (bit 0 inadmissible, bit 1 non-finite)
   const double* vtss; float nodef[MAX_RS]; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
 
@@ -117,6 +118,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     const double* F = stage_buf + C::st_face;
     const double* N = stage_buf + C::st_nrml;
     mbar_wait(&bars[s], par);
+    int bad = 0; // thermodynamic admissibility of what this thread writes (Solver::is_admissible, fused: see misc_kernels.cu)
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if constexpr (Map::vec2) {
@@ -266,6 +268,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
             const double xv = S[v*nq + q] + u;
             S[v*nq + q] = xv;
             a.state[((size_t)e*nv + v)*nq + q] = xv;
+            if (a.record) bad |= (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
             if constexpr (CFL) x[v] = xv;
           }
         }
@@ -337,6 +340,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
           }
           fout[((2*d)*nv + v)*nfq + l] = e0;
           fout[((2*d + 1)*nv + v)*nfq + l] = e1;
+          if (a.record) bad |= ((isfinite(e0) && isfinite(e1)) ? 0 : 2) | ((v >= ND && !(e0 > 0. && e1 > 0.)) ? 1 : 0);
         }
       }
     } else {
@@ -353,10 +357,14 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
           }
           fout[((2*d)*nv + v)*nfq + l] = e0;
           fout[((2*d + 1)*nv + v)*nfq + l] = e1;
+          if (a.record) bad |= ((isfinite(e0) && isfinite(e1)) ? 0 : 2) | ((v >= ND && !(e0 > 0. && e1 > 0.)) ? 1 : 0);
         }
       }
     }
-    __syncthreads(); // stage buffer s free
+    if (a.record) { // uniform across the CTA; the two votes also are the barrier that frees stage buffer s
+      const int inadmissible = __syncthreads_or(bad & 1), nonfinite = __syncthreads_or(bad & 2);
+      if (t == 0) a.record[e] = (inadmissible ? 1 : 0) | (nonfinite ? 2 : 0);
+    } else __syncthreads(); // stage buffer s free
     if (t == 0 && e + 2*stride_e < a.elem_end) {
       fence_proxy_async();
       pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
@@ -397,6 +405,13 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   a.vtss = c->vtss; a.cfl_approx = nullptr;
+  a.record = nullptr;
+  c->admis_valid[deformed ? 1 : 0] = false;
+  const bool leave_admis = c->use_fused_admis && !a.compute_residual;
+  if (leave_admis) {
+    if (!c->record) HB_CUDA(c, cudaMalloc(&c->record, sizeof(int)*(c->n_elem ? c->n_elem : 1)));
+    a.record = c->record;
+  }
   for (int i = 0; i < MAX_RS; ++i) a.nodef[i] = (float)c->ops.node[i];
   c->cfl_valid[deformed ? 1 : 0] = false; // this launch rewrites the state of the set
   const bool leave_cfl = c->use_cfl_cache && a.stage && !a.compute_residual;
@@ -412,6 +427,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   else if (c->rs == 6) rc = deformed ? launch_pipe<6, true, false>(c, a) : launch_pipe<6, false, false>(c, a);
   else rc = deformed ? launch_pipe<4, true, false>(c, a) : launch_pipe<4, false, false>(c, a);
   if (rc == 0 && leave_cfl) c->cfl_valid[deformed ? 1 : 0] = true;
+  if (rc == 0 && leave_admis) c->admis_valid[deformed ? 1 : 0] = true;
   return rc;
 }
 

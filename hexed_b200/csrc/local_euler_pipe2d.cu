@@ -35,7 +35,7 @@ struct Pipe2Cfg
   static constexpr int late_doubles = lt_det + (DEF ? B*nq : 0);
   static constexpr int r_doubles = B*ND*nv*nq;
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
-  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t);
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 16*sizeof(int); // + per-element admissibility bits of the batch
 };
 
 struct Pipe2Args
@@ -43,6 +43,7 @@ struct Pipe2Args
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
+  int* record; // non-null: admissibility bits of the new state and faces per element (see local_euler_pipe.cu)
 };
 
 template <int RS, bool DEF>
@@ -78,6 +79,8 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
   double* late = smem + 2*C::stage_doubles;
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
+  int* s_bad = reinterpret_cast<int*>(bars + 4); // [B] admissibility bits of the batch's elements
+  static_assert(B <= 16, "s_bad holds 16 entries");
   const int t = threadIdx.x;
   const int stride_e = gridDim.x*B;
   int e0 = a.elem_begin + blockIdx.x*B;
@@ -110,6 +113,7 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     const double* F = stage_buf + C::st_face;
     const double* N = stage_buf + C::st_nrml;
     mbar_wait(&bars[s], par);
+    if (a.record && t < B) s_bad[t] = 0; // ordered before the first atomicOr by the barrier after phase A
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if (has_line) {
@@ -177,6 +181,10 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
           const double xv = S[pe*C::e_state + v*nq + q] + u;
           S[pe*C::e_state + v*nq + q] = xv;
           a.state[(size_t)e*C::e_state + v*nq + q] = xv;
+          if (a.record) {
+            const int bad = (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
+            if (bad) atomicOr(&s_bad[pe], bad);
+          }
         }
       }
     }
@@ -201,9 +209,14 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
         }
         fout[((2*d)*nv + v)*nfq + l] = x0;
         fout[((2*d + 1)*nv + v)*nfq + l] = x1;
+        if (a.record) {
+          const int bad = ((isfinite(x0) && isfinite(x1)) ? 0 : 2) | ((v >= ND && !(x0 > 0. && x1 > 0.)) ? 1 : 0);
+          if (bad) atomicOr(&s_bad[le], bad);
+        }
       }
     }
     __syncthreads(); // stage buffer s free
+    if (a.record && t < n) a.record[e0 + t] = s_bad[t];
     if (t == 0 && e0 + 2*stride_e < a.elem_end) {
       fence_proxy_async();
       pipe2_issue_stage<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), stage_buf, &bars[s]);
@@ -245,9 +258,19 @@ int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_option
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   c->cfl_valid[deformed ? 1 : 0] = false;
-  if (c->rs == 6) return deformed ? launch_pipe2<6, true>(c, a) : launch_pipe2<6, false>(c, a);
-  if (c->rs == 4) return deformed ? launch_pipe2<4, true>(c, a) : launch_pipe2<4, false>(c, a);
-  return deformed ? launch_pipe2<8, true>(c, a) : launch_pipe2<8, false>(c, a);
+  a.record = nullptr;
+  c->admis_valid[deformed ? 1 : 0] = false;
+  const bool leave_admis = c->use_fused_admis && !a.compute_residual;
+  if (leave_admis) {
+    if (!c->record) HB_CUDA(c, cudaMalloc(&c->record, sizeof(int)*(c->n_elem ? c->n_elem : 1)));
+    a.record = c->record;
+  }
+  int rc;
+  if (c->rs == 6) rc = deformed ? launch_pipe2<6, true>(c, a) : launch_pipe2<6, false>(c, a);
+  else if (c->rs == 4) rc = deformed ? launch_pipe2<4, true>(c, a) : launch_pipe2<4, false>(c, a);
+  else rc = deformed ? launch_pipe2<8, true>(c, a) : launch_pipe2<8, false>(c, a);
+  if (rc == 0 && leave_admis) c->admis_valid[deformed ? 1 : 0] = true;
+  return rc;
 }
 
 } // namespace hb

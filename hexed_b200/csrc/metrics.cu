@@ -331,6 +331,7 @@ coarse_normal_kernel(NormalArgs a)
 int launch_shared_normals(hexed_b200_ctx* c)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  invalidate_admis(c); // the face storage is used as scratch for the normals
   int* slot_kind = nullptr;
   HB_CUDA(c, cudaMalloc(&slot_kind, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1)));
   HB_CUDA(c, cudaMemsetAsync(slot_kind, 0, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1), c->stream));

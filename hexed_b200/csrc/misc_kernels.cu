@@ -264,6 +264,7 @@ static int launch_transfer(hexed_b200_ctx* c, int kind, int n_var, int scale, co
   if (!n_ref) return 0;
   double* faces = face_array(c, kind);
   if (!faces) return fail(c, HEXED_B200_BAD_ARGUMENT, "face storage of the requested kind has not been allocated");
+  if (!PROLONG && kind == 0) invalidate_admis(c); // restriction rewrites coarse ELEMENT faces (prolongation only mortar faces, which is_admissible always scans)
   const int width = face_width(c, kind);
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
@@ -317,6 +318,20 @@ admissible_kernel(const double* state, const double* faces, const int* ref_face,
   }
 }
 
+/* fused path: OR of the bits the pipelined Local kernels left; record[] is normalised to the reference's 0 / 1 on the way */
+__global__ void __launch_bounds__(256)
+record_reduce_kernel(int* record, int n_elem, int* flags)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  const int bits = e < n_elem ? record[e] : 0;
+  if (e < n_elem) record[e] = bits & 1;
+  const int inadmissible = __any_sync(0xffffffffu, bits & 1), nonfinite = __any_sync(0xffffffffu, bits & 2);
+  if (threadIdx.x % 32 == 0) {
+    if (inadmissible) atomicOr(&flags[0], 1);
+    if (nonfinite) atomicOr(&flags[1], 1);
+  }
+}
+
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
@@ -324,7 +339,19 @@ int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
   if (!c->d_flags) { HB_CUDA(c, cudaMalloc(&c->d_flags, 2*sizeof(int))); HB_CUDA(c, cudaMallocHost(&c->h_flags, 2*sizeof(int))); }
   StatScope scope(c, ST_ADMIS, c->n_elem);
   HB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2*sizeof(int), c->stream));
-  const long long warps = (long long)c->n_elem + c->n_ref;
+  const bool fused = c->use_fused_admis && (c->n_car == 0 || c->admis_valid[0]) && (c->n_def == 0 || c->admis_valid[1]);
+  if (fused) {
+    // the pipelined Local kernels left the bits of the state and element faces they wrote (nothing has touched either since): reduce
+    // 4 bytes per element instead of scanning 17 KB, then scan only the fine mortar faces
+    if (c->n_elem) { HB_LAUNCH(record_reduce_kernel, (c->n_elem + 255)/256, 256, 0, c->stream, c->record, c->n_elem, c->d_flags); count_launch(c, ST_ADMIS); }
+    if (c->n_ref) {
+      HB_LAUNCH(admissible_kernel, (int)(((long long)c->n_ref*32 + 255)/256), 256, 0, c->stream, c->state, c->face_state, c->ref_face, 0, c->n_ref,
+                c->nd, c->nq, c->nfq, c->record, c->d_flags);
+      count_launch(c, ST_ADMIS);
+    }
+    HB_CUDA(c, cudaGetLastError());
+  }
+  const long long warps = fused ? 0 : (long long)c->n_elem + c->n_ref;
   if (warps) {
     HB_LAUNCH(admissible_kernel, (int)((warps*32 + 255)/256), 256, 0, c->stream, c->state, c->face_state, c->ref_face, c->n_elem, c->n_ref,
               c->nd, c->nq, c->nfq, c->record, c->d_flags);
@@ -690,6 +717,7 @@ int launch_gather_faces(hexed_b200_ctx* c, const double* src, int width, const i
 }
 int launch_scatter_faces(hexed_b200_ctx* c, double* dst, int width, const int* d_slots, int n, const double* src)
 {
+  if (dst == c->face_state) invalidate_admis(c);
   const long long total = (long long)n*width;
   if (!total) return 0;
   HB_LAUNCH(scatter_kernel, (int)((total + 255)/256), 256, 0, c->stream, dst, width, d_slots, n, src);

@@ -72,6 +72,7 @@ int launch_neighbor_euler(hexed_b200_ctx* c, int deformed, int first, int count)
   const int n_con = count;
   StatScope scope(c, deformed ? ST_NEIGHBOR_DEF : ST_NEIGHBOR_CAR, n_con);
   if (!n_con) return 0;
+  invalidate_admis(c); // the element faces now hold numerical fluxes
   NeighborArgs a;
   a.faces = c->face_state; a.normals = c->normals; a.con = (deformed ? c->def_con : c->car_con) + (size_t)first*4; a.perm = c->perm; a.n_con = n_con;
   return dispatch(c, [&](auto nd, auto rs) {

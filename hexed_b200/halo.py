@@ -99,3 +99,13 @@ def allreduce_min(value, device=None, group=None):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return float(t.item())
+
+
+def allreduce_and(flag, device=None, group=None):
+    """`Solver::is_admissible` of a partitioned mesh: every rank's `Device.is_admissible()` must hold"""
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))

@@ -167,6 +167,7 @@ def _addr(a):
 
 
 BC_MODE_ADVECTION, BC_MODE_COPY_STATE, BC_MODE_NEGATE_FLUX = 0, 1, 2  # include/hexed_b200.h
+OPT_PIPELINED_LOCAL, OPT_CFL_CACHE, OPT_FUSED_ADMIS = 0, 1, 2      # hexed_b200_set_option
 
 
 class Device:

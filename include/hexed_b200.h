@@ -296,8 +296,11 @@ int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
  * Local kernel where it applies (3-D, row size 4 or 6, no modal filter); default 1
  * HEXED_B200_OPT_CFL_CACHE = the stage-1 Local kernel leaves min(spacing/char_speed) per element behind and the next global-time-step
  * max_dt_euler re-evaluates only the near-minimum elements instead of re-reading the whole state (any other write to the state
- * invalidates the screen); default 0 -- on B200 the extra work in the Local kernel costs what the saved pass over the state gains */
-enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1 };
+ * invalidates the screen); default 0 -- on B200 the extra work in the Local kernel costs what the saved pass over the state gains
+ * HEXED_B200_OPT_FUSED_ADMIS = the pipelined Euler Local kernels also leave, per element, whether the state and faces they have just written
+ * are admissible / finite; hexed_b200_is_admissible right after hexed_b200_compute_euler then reduces 4 bytes per element instead of scanning
+ * the state (same answer and record; anything else that writes element state or faces in between falls back to the full scan). Default 0. */
+enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1, HEXED_B200_OPT_FUSED_ADMIS = 2 };
 int hexed_b200_set_option(hexed_b200_ctx* ctx, int option, int value);
 int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);
 int hexed_b200_reset_stats(hexed_b200_ctx* ctx);

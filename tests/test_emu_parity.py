@@ -215,3 +215,9 @@ def test_navier_stokes_2d_line_kernel(oracle, emu_lib, kind, rs, n):
     assert_pde_parity(out, ref, dts)
     out, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
     assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 4, 5), (3, 4, 2)])
+def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
+    from util import check_fused_admissibility
+    check_fused_admissibility(oracle, emu_lib, nd, rs, n)

@@ -312,3 +312,9 @@ def test_navier_stokes_2d_line_kernel(oracle, gpu_lib, deformed, rs, n):
     assert_pde_parity(out, ref, dts)
     out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=1, compute_residual=True)
     assert_pde_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 40), (3, 6, 8), (3, 4, 9)])
+def test_fused_admissibility(oracle, gpu_lib, nd, rs, n):
+    from util import check_fused_admissibility
+    check_fused_admissibility(oracle, gpu_lib, nd, rs, n)

@@ -174,7 +174,7 @@ def _gloo_worker(rank, world, port, result_path):
             sys.path.insert(0, p)
     import torch.distributed as dist
     from pyoracle import Oracle
-    from hexed_b200.halo import MeshHalo, allreduce_min
+    from hexed_b200.halo import MeshHalo, allreduce_min, allreduce_and
     dist.init_process_group("gloo", rank=rank, world_size=world)
     oracle = Oracle()
     rng = np.random.default_rng(3)
@@ -189,6 +189,14 @@ def _gloo_worker(rank, world, port, result_path):
             halo.exchange()
             oracle_pre_prolong(oracle, basis, mine)
             oracle.compute_euler(basis, mine, dt=dt, i_stage=stage)
+    # Solver::is_admissible of the partitioned mesh = AND over the ranks: poison one element of rank 1 only
+    ok_before = allreduce_and(oracle.is_admissible(mine)[0])
+    saved = mine.state()[0, mine.n_dim, 0]
+    if rank == 1:
+        mine.state()[0, mine.n_dim, 0] = -1.
+    ok_after = allreduce_and(oracle.is_admissible(mine)[0])
+    mine.state()[0, mine.n_dim, 0] = saved
+    assert ok_before and not ok_after, (rank, ok_before, ok_after)
     np.save(result_path % rank, mine.elem_data)
     dist.barrier()
     dist.destroy_process_group()

@@ -585,3 +585,60 @@ def check_calc_jacobian_box(lib, nd, rs, n):
     for key in want:
         assert rel_l2(got[key], want[key]) <= 1e-13, key
         assert np.abs(got[key] - want[key]).max() <= 1e-12*np.abs(want[key]).max(), key
+
+
+def check_fused_admissibility(oracle, lib, nd, rs, n):
+    """HEXED_B200_OPT_FUSED_ADMIS: the pipelined Local kernels leave the admissibility bits of what they write, is_admissible right
+    after compute_euler reduces those instead of scanning the state. Same answer and record as the full scan and as the oracle, on an
+    admissible step, on a step that drives two elements inadmissible, and after something else has touched the faces (fallback)."""
+    from hexed_b200.kernels import OPT_FUSED_ADMIS, FACE_STATE
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=fs)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    dev.set_option(OPT_FUSED_ADMIS, 1)
+
+    def stage(i_stage, dt):
+        oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt, i_stage=i_stage)
+        dev.apply_state_bcs(); dev.compute_euler(dt=dt, i_stage=i_stage)
+
+    def both_ways():
+        launches0 = dev.launch_count()
+        fused = dev.is_admissible(); rec_fused = dev.record()
+        n_fused = dev.launch_count() - launches0
+        dev.set_option(OPT_FUSED_ADMIS, 0)       # clears the flags: full scan of the same device state
+        full = dev.is_admissible(); rec_full = dev.record()
+        dev.set_option(OPT_FUSED_ADMIS, 1)
+        want, rec_want = oracle.is_admissible(ref)
+        assert fused == full == want and np.array_equal(rec_fused, rec_full) and np.array_equal(rec_full, rec_want)
+        return fused, rec_fused, n_fused
+    dt = oracle.max_dt(EULER, basis, ref, 0.5, 0.5, False); dev.max_dt_euler(0.5, 0.5, False)
+    stage(0, dt)
+    ok, rec, _ = both_ways()
+    assert ok and not rec.any()
+    stage(1, dt)
+    ok, rec, _ = both_ways()
+    assert ok
+    # a time step far beyond the stability limit overshoots: finite, but mass / energy go non-positive in many elements
+    snapshot_dev, snapshot_ref = m.copy(), ref.copy()
+    dev.sync_to_host(snapshot_dev)
+    stage(0, 3e3*dt)
+    ok, rec, _ = both_ways()
+    assert not ok and 0 < rec.sum()
+    for a, b in ((snapshot_dev, m), (snapshot_ref, ref)):   # back to the admissible state on both sides
+        b.elem_data[:] = a.elem_data; b.face_state[:] = a.face_state
+    dev.upload_elements(m.elem_data); dev.upload(FACE_STATE, m.face_state)
+    assert dev.is_admissible() and oracle.is_admissible(ref)[0]
+    # fallback: the flags must not survive a write to the element faces by anybody else
+    stage(1, dt)
+    f = dev.download(FACE_STATE, np.zeros_like(m.face_state))
+    f[5].reshape(nd + 2, -1)[nd, 0] = -1.
+    ref.face_state[5].reshape(nd + 2, -1)[nd, 0] = -1.
+    dev.upload(FACE_STATE, f)
+    got = dev.is_admissible()
+    assert got == oracle.is_admissible(ref)[0] and not got
+    assert dev.record()[5//(2*nd)] == 1
+    dev.close()
