@@ -163,6 +163,7 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev1), "cudaEventCreate");
   if (!rc) rc = dev_alloc(c, &c->d_scalar, 8);
+  if (!rc) rc = dev_alloc(c, &c->d_step, 2);
   if (!rc) rc = check(c, cudaMallocHost(&c->h_scalar, sizeof(double)*8), "cudaMallocHost");
   // permutation tables for all 36 direction codes
   c->h_perm.assign((size_t)36*c->nfq, 0);
@@ -186,7 +187,7 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_mesh(c);
-  dev_free(c->perm); dev_free(c->d_scalar); dev_free(c->d_face_scratch);
+  dev_free(c->perm); dev_free(c->d_scalar); dev_free(c->d_step); dev_free(c->d_face_scratch);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->d_flags) cudaFree(c->d_flags);
@@ -437,6 +438,64 @@ int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
   if ((rc = launch_local_euler(c, 0, o))) return rc;
   if ((rc = launch_local_euler(c, 1, o))) return rc;
   if ((rc = launch_prolong(c, 0, c->nv, 0))) return rc;
+  return 0;
+}
+
+/* ---- the time loop of Solver::update for the inviscid case with device boundary conditions, without a host round trip per step ----
+ * One step = max_dt + 2 x (ghost fill + compute_euler) (reference src/Solver.cpp:834-886 with n_cheby_flow = 1). The reference API
+ * passes dt through the host (max_dt returns it, Kernel_options carries it), i.e. one device synchronisation per step; here the
+ * reduction leaves dt on the device, the Local kernels read it from there, and the step is captured ONCE in a CUDA graph and replayed.
+ * On the large meshes of the headline the step is 30 ms and none of this matters; on the meshes of the 2-D sample cases (vortex:
+ * 256 elements, ~10 launches of a few microseconds each) launch latency and the synchronisation ARE the step. */
+static int enqueue_euler_step(hexed_b200_ctx* c, double safety_conv)
+{
+  int rc = launch_max_dt_euler_device(c, safety_conv, c->d_step);
+  for (int stage = 0; stage < 2 && !rc; ++stage) {
+    hexed_b200_options o; o.dt = 1.; o.i_stage = stage; o.compute_residual = 0; o.use_filter = 0;
+    rc = launch_bcs(c);
+    if (!rc) rc = hexed_b200_compute_euler(c, o);
+  }
+  if (!rc) rc = launch_accumulate_time(c, c->d_step);
+  return rc;
+}
+
+int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (n_steps < 0) return fail(c, HEXED_B200_BAD_ARGUMENT, "negative step count");
+  const bool timing = c->timing;
+  c->timing = false; // per-launch events cannot be queried inside a capture; this entry point is timed as a whole by its caller
+  HB_CUDA(c, cudaMemsetAsync(c->d_step, 0, 2*sizeof(double), c->stream));
+  c->dt_dev_active = c->d_step;
+  int rc = 0, done = 0;
+  if (n_steps > 0) { rc = enqueue_euler_step(c, safety_conv); done = 1; } // eager: also performs every lazy allocation / attribute call
+#ifndef HB_EMULATE
+  if (!rc && use_graph && n_steps > done) {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    rc = check(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+    if (!rc) {
+      const int rc_step = enqueue_euler_step(c, safety_conv);
+      const int rc_end = check(c, cudaStreamEndCapture(c->stream, &graph), "end capture");
+      rc = rc_step ? rc_step : rc_end;
+    }
+    if (!rc) rc = check(c, cudaGraphInstantiate(&exec, graph, 0), "instantiate graph");
+    for (; !rc && done < n_steps; ++done) rc = check(c, cudaGraphLaunch(exec, c->stream), "launch graph");
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+#else
+  (void)use_graph;
+#endif
+  for (; !rc && done < n_steps; ++done) rc = enqueue_euler_step(c, safety_conv);
+  c->dt_dev_active = nullptr;
+  c->timing = timing;
+  if (rc) return rc;
+  HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (last_dt) *last_dt = *c->h_scalar;
+  HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (time_advanced) *time_advanced = *c->h_scalar;
   return 0;
 }
 

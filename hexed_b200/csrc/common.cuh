@@ -100,6 +100,9 @@ struct hexed_b200_ctx
   // runs its full scan.
   bool use_fused_admis = false;
   bool admis_valid[2] = {false, false};
+  // hexed_b200_update_euler: the time step stays on the device. d_step = {dt of the current step, accumulated flow time}; while
+  // dt_dev_active is non-null the Euler Local launchers hand it to their kernels, which multiply their `update` factor by it.
+  double* d_step = nullptr; const double* dt_dev_active = nullptr;
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
   // vertex topology of the epoch (hexed_b200_vertex_topology) and per-element-vertex scratch (vertex_fix_admis_coef / vertex_elwise_av)
   int* elem_vertex = nullptr; int n_vertex = 0; int* matchers = nullptr; int n_match = 0;
@@ -150,6 +153,8 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
 int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end);
 int launch_write_face(hexed_b200_ctx* c);
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
+int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_dt); // global time step, result left at d_dt (no read-back)
+int launch_accumulate_time(hexed_b200_ctx* c, double* d_step);
 int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index = nullptr, int n_index = 0);
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale);
 int launch_bcs(hexed_b200_ctx* c);

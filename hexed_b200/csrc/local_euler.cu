@@ -35,6 +35,7 @@ struct LocalArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual; int use_filter;
+  const double* dt_dev; // non-null: the time step lives on the device (hexed_b200_update_euler) and multiplies `update`
 };
 
 template <int ND, int RS, bool DEF>
@@ -147,7 +148,8 @@ local_euler_kernel(LocalArgs a, Ops ops, FilterOp filt)
 
   // two-stage update (reference include/Spatial.hpp:311-324,484-503)
   if (active) {
-    double mult = a.update*a.tss[(size_t)e*nq + q]/a.nom[e];
+    const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
+    double mult = update*a.tss[(size_t)e*nq + q]/a.nom[e];
     if constexpr (DEF) mult /= det;
     double* cache = a.cache + (size_t)e*C::cs*nq + q;
     #pragma unroll
@@ -246,6 +248,7 @@ int launch_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o)
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt; // Spatial.hpp:317 with Basis::step_ratio (src/Basis.cpp:11-14)
+  a.dt_dev = c->dt_dev_active;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual; a.use_filter = o.use_filter;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;

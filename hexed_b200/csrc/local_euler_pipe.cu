@@ -48,6 +48,7 @@ struct PipeArgs
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
+  const double* dt_dev; // non-null: the time step lives on the device and multiplies `update`
   int* record; // non-null: leave Element::record-style admissibility bits of the NEW state and faces per element (bit 0 inadmissible, bit 1 non-finite)
   const double* vtss; float nodef[MAX_RS]; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
@@ -242,6 +243,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_wait(&bars[2], it & 1);
     {
       const double nom = a.nom[e];
+      const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
       [[maybe_unused]] float cfl_min = 3.0e38f;
       [[maybe_unused]] float vt_f[8];
       if constexpr (CFL) {
@@ -251,8 +253,8 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
       for (int q = t; q < nq; q += C::threads) {
         // update*tss/nom/det (reference Spatial.hpp:484-487) with one division instead of two (<= 1 ulp)
         double mult;
-        if constexpr (DEF) mult = a.update*late[C::lt_tss + q]/(nom*late[C::lt_det + q]);
-        else mult = a.update*late[C::lt_tss + q]/nom;
+        if constexpr (DEF) mult = update*late[C::lt_tss + q]/(nom*late[C::lt_det + q]);
+        else mult = update*late[C::lt_tss + q]/nom;
         [[maybe_unused]] double x[nv];
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
@@ -403,6 +405,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
+  a.dt_dev = c->dt_dev_active;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   a.vtss = c->vtss; a.cfl_approx = nullptr;
   a.record = nullptr;

@@ -43,6 +43,7 @@ struct Pipe2Args
   double* state; const double* tss; double* cache; const double* nom; const double* refn; const double* det; double* faces;
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
+  const double* dt_dev; // non-null: the time step lives on the device and multiplies `update`
   int* record; // non-null: admissibility bits of the new state and faces per element (see local_euler_pipe.cu)
 };
 
@@ -162,12 +163,13 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
 
     /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
     mbar_wait(&bars[2], it & 1);
+    const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
     for (int pt = t; pt < n*nq; pt += C::threads) {
       const int pe = pt/nq, q = pt % nq;
       const int e = e0 + pe;
       double mult; // update*tss/nom/det with one division (<= 1 ulp)
-      if constexpr (DEF) mult = a.update*late[C::lt_tss + pt]/(a.nom[e]*late[C::lt_det + pt]);
-      else mult = a.update*late[C::lt_tss + pt]/a.nom[e];
+      if constexpr (DEF) mult = update*late[C::lt_tss + pt]/(a.nom[e]*late[C::lt_det + pt]);
+      else mult = update*late[C::lt_tss + pt]/a.nom[e];
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         double u = R[pe*ND*nv*nq + (0*nv + v)*nq + q];
@@ -256,6 +258,7 @@ int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_option
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
+  a.dt_dev = c->dt_dev_active;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   c->cfl_valid[deformed ? 1 : 0] = false;
   a.record = nullptr;

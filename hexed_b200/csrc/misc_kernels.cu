@@ -168,6 +168,38 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
   });
 }
 
+/* the same reduction with the result left on the device (hexed_b200_update_euler): no read-back, no synchronisation, graph-capturable */
+int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_dt)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  StatScope s_car(c, ST_MAX_DT_CAR, c->n_car);
+  c->stats[ST_MAX_DT_DEF].work_units += c->n_def;
+  return dispatch(c, [&](auto nd, auto rs) {
+    constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
+    const long long total = (long long)c->n_elem*ipow(RS, ND);
+    const int grid = (int)((total + 255)/256);
+    MaxDtArgs a;
+    a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
+    a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv;
+    a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(d_dt);
+    HB_CUDA(c, cudaMemsetAsync(d_dt, 0x7f, sizeof(double), c->stream));
+    if (grid) { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); count_launch(c, ST_MAX_DT_CAR); }
+    HB_CUDA(c, cudaGetLastError());
+    c->tss_is_one = true;
+    return 0;
+  });
+}
+
+__global__ void accumulate_time_kernel(double* step) { step[1] += step[0]; }
+
+int launch_accumulate_time(hexed_b200_ctx* c, double* d_step)
+{
+  HB_LAUNCH(accumulate_time_kernel, 1, 1, 0, c->stream, d_step);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 /* ---------------- hanging-node transfer: reference include/Spatial.hpp:153-206 (prolong), :230-285 (restrict) ----------------
  * One CTA per refined face; the fine faces are processed one after another in shared memory with the same
  * dimension-by-dimension in-place sweeps (and the same accumulation order into the coarse face) as the reference.

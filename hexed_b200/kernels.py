@@ -99,6 +99,7 @@ SIGNATURES = {
     "hexed_b200_interp_vertices": [C.c_void_p, C.c_int, dp, dp],
     "hexed_b200_av_swap": [C.c_void_p],
     "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
+    "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, dp, dp],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
     "hexed_b200_vertex_topology": [C.c_void_p, ip, C.c_int, ip, C.c_int],
     "hexed_b200_share_vertex_data": [C.c_void_p, C.c_int, C.c_int],
@@ -467,6 +468,14 @@ class Device:
     def calc_shared_normals(self):
         """connection passes of Solver::calc_jacobian (reference src/Solver.cpp:287-369)"""
         self._check(self.lib.hexed_b200_calc_shared_normals(self.ctx))
+
+    def update_euler(self, safety, n_steps, use_graph=True):
+        """n_steps of Solver::update's inviscid loop (max_dt + 2 stages with device ghost fills) without a host round trip per step;
+        returns (last dt, flow time advanced)"""
+        dt, t = C.c_double(0.), C.c_double(0.)
+        self._check(self.lib.hexed_b200_update_euler(self.ctx, float(safety), int(n_steps), int(bool(use_graph)),
+                                                     C.cast(C.byref(dt), dp), C.cast(C.byref(t), dp)))
+        return dt.value, t.value
 
     def is_admissible(self):
         """Solver::is_admissible (reference src/Solver.cpp:921-958); raises RuntimeError("state is not finite") like the reference's

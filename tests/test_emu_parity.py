@@ -221,3 +221,9 @@ def test_navier_stokes_2d_line_kernel(oracle, emu_lib, kind, rs, n):
 def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
     from util import check_fused_admissibility
     check_fused_admissibility(oracle, emu_lib, nd, rs, n)
+
+
+@pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 4, False), (2, 3, 3, True), (3, 4, 2, True)])
+def test_update_euler_device_time_step(oracle, emu_lib, nd, rs, n, deformed):
+    from util import check_update_euler
+    check_update_euler(oracle, emu_lib, nd, rs, n, n_steps=4, use_graph=False, deformed=deformed)

@@ -318,3 +318,11 @@ def test_navier_stokes_2d_line_kernel(oracle, gpu_lib, deformed, rs, n):
 def test_fused_admissibility(oracle, gpu_lib, nd, rs, n):
     from util import check_fused_admissibility
     check_fused_admissibility(oracle, gpu_lib, nd, rs, n)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 16, False), (2, 6, 24, True), (3, 6, 6, True), (3, 5, 4, False)])
+def test_update_euler_device_time_step(oracle, gpu_lib, nd, rs, n, deformed, use_graph):
+    """time step on the device + CUDA graph replay of the step: bit-identical to the call-by-call sequence"""
+    from util import check_update_euler
+    check_update_euler(oracle, gpu_lib, nd, rs, n, n_steps=25, use_graph=use_graph, deformed=deformed)

@@ -642,3 +642,32 @@ def check_fused_admissibility(oracle, lib, nd, rs, n):
     assert got == oracle.is_admissible(ref)[0] and not got
     assert dev.record()[5//(2*nd)] == 1
     dev.close()
+
+
+def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=False, bc="riemann"):
+    """hexed_b200_update_euler (time step kept on the device, optional CUDA graph) is bit-identical to the same steps made call by call
+    through the reference-shaped entry points, and both track the oracle"""
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd)
+    kind = M.BC_RIEMANN_INVARIANTS if bc == "riemann" else M.BC_FREESTREAM
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=kind, bc_params=fs)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    a = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    b = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    t_a = 0.
+    for _ in range(n_steps):
+        dt = a.max_dt_euler(0.4, 0.4, False)
+        dt_o = oracle.max_dt(EULER, basis, ref, 0.4, 0.4, False)
+        for stage in (0, 1):
+            a.apply_state_bcs(); a.compute_euler(dt=dt, i_stage=stage)
+            oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage)
+        t_a += dt
+    dt_b, t_b = b.update_euler(0.4, n_steps, use_graph)
+    out_a, out_b = m.copy(), m.copy()
+    a.sync_to_host(out_a); b.sync_to_host(out_b)
+    a.close(); b.close()
+    assert dt_b == dt and t_b == t_a
+    assert np.array_equal(out_a.elem_data, out_b.elem_data) and np.array_equal(out_a.face_state, out_b.face_state)
+    assert rel_l2(out_b.state(), ref.state()) <= STATE_TOL
