@@ -11,7 +11,8 @@
  * reference's own closed-form test values (test/test_Max_dt.cpp, test_Derivative.cpp,
  * test_Prolong_refined.cpp, test_Restrict_refined.cpp, test_Face_permutation.cpp, ...)
  * as tests/ of this repo; the Euler/NS flux has no direct unit test in the reference
- * (test/test_pde.cpp is #if 0) and is pinned only through conservation/marching checks;
+ * (test/test_pde.cpp is #if 0) and is pinned through conservation and the reference's analytic
+ * marching check (test/test_Solver.cpp:555-586, tests/test_oracle_kat.py::test_marching_residual);
  * the LDG path (Neighbor average, gradient, compute_flux_diff, Neighbor_reconcile,
  * Reconcile_ldg_flux) is pinned by the reference's analytic viscous-decay check
  * (test/test_Solver.cpp:588-615, tests/test_oracle_kat.py::test_viscous_momentum_decay).

@@ -526,3 +526,37 @@ def test_set_jacobian_oracle():
         for key in ("ref_normals", "det", "vertex_tss"):
             assert np.allclose(t[key].numpy()[0], a[key], rtol=1e-12, atol=1e-14), key
         assert np.allclose(t["face_normals"].numpy()[0], a["face_normals"], rtol=1e-12, atol=1e-14)
+
+
+# ---------------------------------------------------------------- test_Solver.cpp "Solver time marching"
+@pytest.mark.parametrize("nd,rs,deformed", [(1, 6, False), (2, 6, False), (2, 6, True), (3, 6, True), (3, 4, False)])
+def test_marching_residual(oracle, nd, rs, deformed):
+    """test/test_Solver.cpp:555-586 (`test_marching` with `Nonuniform_mass` :103-124 and its exact time derivative
+    `Nonuniform_residual` :149-170): a density wave carried by a uniform velocity at uniform pressure; the physical residual of one
+    `compute_euler` in residual mode must be the analytic d/dt of every variable to the reference's margin 1e-3*|state|. This is the
+    reference's pin on the convective path: pointwise flux, Derivative, the numerical flux on the faces, the lifting."""
+    if nd == 1 and deformed:
+        pytest.skip("no deformed 1-D elements")
+    velocs, wave_number = np.array([.3, -.7, .8])[:nd], np.array([-.1, .3, .2])[:nd]
+    b = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 3, b, deformed=deformed, bc_kind=M.BC_COPY, warp_amplitude=0.05)
+    x = np.asarray(m.qpoint_pos)
+    scaled_pos = sum(wave_number[d]*x[:, d] for d in range(nd))
+    mass = 1. + .1*np.sin(scaled_pos)
+    st = m.state()
+    for d in range(nd):
+        st[:, d] = mass*velocs[d]
+    st[:, nd] = mass
+    st[:, nd + 1] = 1e5/.4 + mass*.5*(velocs @ velocs)
+    oracle.compute_write_face(b, m)
+    oracle.max_dt(EULER, b, m, 1e-3, 1e-3, False)  # global time step: tss = 1
+    before = m.state().copy()
+    oracle.apply_state_bcs(m)
+    oracle.compute_euler(b, m, dt=1., i_stage=0, compute_residual=True)
+    assert np.array_equal(m.state(), before)
+    c = M.cache_slot(nd, rs)
+    resid = m.elem_data[:, c:c + nd + 2]
+    d_mass = -.1*(velocs @ wave_number)*np.cos(scaled_pos)
+    correct = np.stack([d_mass*velocs[d] for d in range(nd)] + [d_mass, d_mass*.5*(velocs @ velocs)], axis=1)
+    assert np.all(np.abs(resid - correct) <= 1e-3*np.abs(before))
+    assert np.abs(correct[:, nd]).max() > 1e-3  # the derivative is not trivially inside the margin of the mass equation
