@@ -15,6 +15,7 @@ from hexed_b200 import mesh as M
 from hexed_b200.basis import Basis
 from hexed_b200.tables import Connection_direction, vertex_inds
 import pyoracle
+from util import rel_l2
 from pyoracle import EULER, NAVIER_STOKES
 
 APPROX = 1.2e-5  # Catch::Approx default epsilon (100 * float epsilon)
@@ -560,3 +561,39 @@ def test_marching_residual(oracle, nd, rs, deformed):
     correct = np.stack([d_mass*velocs[d] for d in range(nd)] + [d_mass, d_mass*.5*(velocs @ velocs)], axis=1)
     assert np.all(np.abs(resid - correct) <= 1e-3*np.abs(before))
     assert np.abs(correct[:, nd]).max() > 1e-3  # the derivative is not trivially inside the margin of the mass equation
+
+
+# ---------------------------------------------------------------- Fix_therm_admis: no reference test; size-independent properties
+@pytest.mark.parametrize("nd,rs,deformed", [(2, 5, True), (3, 4, True), (2, 6, False)])
+def test_fix_therm_admis_is_conservative_and_smoothing(oracle, nd, rs, deformed):
+    """`Fix_therm_admis` (reference include/pde.hpp:400-493) has no test of its own in the reference. Two properties that do not
+    depend on its coefficients pin the restatement beyond line-by-line reading: with the ghost fills `Solver::fix_admissibility` uses
+    (state copied, flux negated: zero net boundary flux, src/Solver.cpp:1063-1074,103-115) a repair sweep (a) conserves the integral of
+    every variable and (b) reduces the variance of a rough field wherever the coefficient is positive."""
+    from pyoracle import FIX_THERM_ADMIS
+    rng = np.random.default_rng(2)
+    b = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 3, b, deformed=deformed, bc_kind=M.BC_COPY, with_ldg=True, warp_amplitude=0.05)
+    x = np.asarray(m.qpoint_pos)
+    st = m.state()
+    st[:] = 1. + .3*np.sin(7*x.sum(1))[:, None, :] + .05*rng.normal(0., 1., st.shape)
+    st[:, nd:] += 2.
+    m.elem_data[:, nd + 3] = 1.   # bulk_av_coef = the repair factor (swapped in by fix_admissibility)
+    m.elem_data[:, nd + 4] = 0.
+    oracle.compute_write_face(b, m)
+    w = np.asarray(b.weight)
+    wq = np.ones(m.nq)
+    q = np.arange(m.nq)
+    for d in range(nd):
+        wq = wq*w[(q//rs**(nd - 1 - d)) % rs]
+    vol = (np.asarray(m.det) if deformed else np.ones((m.n_elem, m.nq)))*wq[None, :]*(np.asarray(m.nom_size)**nd)[:, None]
+    integral = lambda: (m.state()*vol[:, None, :]).sum(axis=(0, 2))  # noqa: E731
+    before, var_before = integral(), m.state().var(axis=(0, 2))
+    dt = oracle.max_dt(FIX_THERM_ADMIS, b, m, 0.5, 0.5, False)  # GLOBAL step: a local pseudo-time step scale is not conservative by design
+    start = m.state().copy()
+    for s in (0.3, 0.7):
+        pyoracle.apply_aux_bcs(m, 1)
+        oracle.compute_fix_therm_admis(b, m, lambda: pyoracle.apply_aux_bcs(m, 2), dt=s*dt, i_stage=0)
+    assert rel_l2(m.state(), start) > 1e-4
+    assert np.all(np.abs(integral() - before) <= 1e-12*np.abs(before))
+    assert np.all(m.state().var(axis=(0, 2)) < var_before)
