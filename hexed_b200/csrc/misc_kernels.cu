@@ -14,25 +14,42 @@ struct MaxDtArgs
   const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; unsigned long long* global_min;
 };
 
+constexpr int max_dt_ppt = 2; // points per thread: both points' loads are in flight before either is used (the one-point version
+                              // ran at 4.1 TB/s with 7.6 cycles of long-scoreboard stall per issue, profiles/r01l_ncu_full_euler.md)
 template <int ND, int RS>
 __global__ void __launch_bounds__(256)
 max_dt_euler_kernel(MaxDtArgs a, Ops ops)
 {
-  constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND);
+  constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND), PPT = max_dt_ppt;
   __shared__ double warp_min[8];
-  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  const int e = (int)(gid/nq), q = (int)(gid % nq);
+  const long long first = (long long)blockIdx.x*(256*PPT) + threadIdx.x;
+  double st[PPT][nv], vt[PPT][n_vert];
+  int elem[PPT], pt[PPT];
+  #pragma unroll
+  for (int r = 0; r < PPT; ++r) {
+    const long long gid = first + r*256;
+    elem[r] = (int)(gid/nq); pt[r] = (int)(gid % nq);
+    if (elem[r] < a.n_elem) {
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) st[r][v] = a.state[((size_t)elem[r]*nv + v)*nq + pt[r]];
+      #pragma unroll
+      for (int i = 0; i < n_vert; ++i) vt[r][i] = a.vtss[(size_t)elem[r]*n_vert + i];
+    }
+  }
   double val = DBL_MAX;
-  if (e < a.n_elem) {
-    const double spacing = interp_vertex_spacing<ND, RS>(a.vtss + (size_t)e*n_vert, ops, q);
-    EulerPoint<ND> p;
-    #pragma unroll
-    for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
-    p.inv_mass = 1./p.s[ND];
-    // 1/scale with scale = char_speed/max_cfl/spacing (Spatial.hpp:808-822), rearranged to a single division
-    const double local_dt = a.max_cfl_c*spacing/p.char_speed();
-    if (a.is_local) a.tss[(size_t)e*nq + q] = local_dt;
-    else { a.tss[(size_t)e*nq + q] = 1.; val = local_dt; }
+  #pragma unroll
+  for (int r = 0; r < PPT; ++r) {
+    if (elem[r] < a.n_elem) {
+      const double spacing = interp_vertex_spacing<ND, RS>(vt[r], ops, pt[r]);
+      EulerPoint<ND> p;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) p.s[v] = st[r][v];
+      p.inv_mass = 1./p.s[ND];
+      // 1/scale with scale = char_speed/max_cfl/spacing (Spatial.hpp:808-822), rearranged to a single division
+      const double local_dt = a.max_cfl_c*spacing/p.char_speed();
+      if (a.is_local) a.tss[(size_t)elem[r]*nq + pt[r]] = local_dt;
+      else { a.tss[(size_t)elem[r]*nq + pt[r]] = 1.; val = fmin(val, local_dt); }
+    }
   }
   if (a.is_local) return;
   #pragma unroll
@@ -150,7 +167,7 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)c->n_elem*ipow(RS, ND);
-    const int grid = (int)((total + 255)/256);
+    const int grid = (int)((total + 256*max_dt_ppt - 1)/(256*max_dt_ppt));
     MaxDtArgs a;
     a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
     a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9) * safety (Spatial.hpp:777)
@@ -177,7 +194,7 @@ int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     const long long total = (long long)c->n_elem*ipow(RS, ND);
-    const int grid = (int)((total + 255)/256);
+    const int grid = (int)((total + 256*max_dt_ppt - 1)/(256*max_dt_ppt));
     MaxDtArgs a;
     a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
     a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv;
