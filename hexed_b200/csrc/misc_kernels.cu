@@ -14,8 +14,10 @@ struct MaxDtArgs
   const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; unsigned long long* global_min;
 };
 
-constexpr int max_dt_ppt = 2; // points per thread: both points' loads are in flight before either is used (the one-point version
-                              // ran at 4.1 TB/s with 7.6 cycles of long-scoreboard stall per issue, profiles/r01l_ncu_full_euler.md)
+constexpr int max_dt_ppt = 1; // points per thread. Measured with 2 (both points' loads in flight before either is used; 70 registers, 3 CTAs
+                              // of 256 per SM instead of 6): 3.0 ms against 2.54 ms at 1 M 3-D elements -- occupancy hides the load latency
+                              // better than per-thread memory-level parallelism does; the arithmetic (two square roots, a reciprocal and a
+                              // division per point, ~256 instructions) keeps the kernel at 4.1 TB/s (profiles/r01l_ncu_full_euler.md)
 template <int ND, int RS>
 __global__ void __launch_bounds__(256)
 max_dt_euler_kernel(MaxDtArgs a, Ops ops)
