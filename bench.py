@@ -219,6 +219,10 @@ def main():
                    blocks=blocks, block=M.block_coords(rank, blocks))
     ne, nq, nv = m.n_elem, m.nq, m.nv
     dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
+    # the generator's copies of the metric terms are dead once the device mirror holds them: 28 KB per element that a 2 M element
+    # mesh (the 16 M / 8 GPU configuration) needs back
+    m.ref_normals = None; m.det = None; m.normals = None
+    torch.cuda.empty_cache()
     # density wave initial condition, written from pinned host memory (the solver's state lives in host arrays in the reference)
     pos = torch.as_tensor(m.qpoint_pos, device=cuda) if not torch.is_tensor(m.qpoint_pos) else m.qpoint_pos
     phase = sum(torch.sin(2*np.pi*pos[:, d] + 0.3*d) for d in range(nd))/nd
