@@ -131,14 +131,18 @@ g_neighbor_reconcile_kernel(GArgs a)
   }
   double* l0 = a.faces_ldg + (size_t)tab[0]*wl + q0;
   double* l1 = a.faces_ldg + (size_t)tab[1]*wl + q1;
+  // every load before the first store: interleaved, each store had to be assumed to alias the next variable's loads, which chained
+  // n_update memory round trips per thread (202 cycles of long-scoreboard stall per issue, 4.0 TB/s, profiles/r01g_ncu_full_ns.md)
+  double g0[nu], g1[nu];
+  #pragma unroll
+  for (int v = 0; v < nu; ++v) { g0[v] = l0[v*nfq]; g1[v] = l1[v*nfq]; }
   #pragma unroll
   for (int v = 0; v < nu; ++v) {
-    const double g0 = l0[v*nfq], g1 = l1[v*nfq];
     double avg = 0;
-    avg += .5*sign0*g0;
-    avg += .5*sign1*g1;
-    l0[v*nfq] = sign0*avg - g0;
-    l1[v*nfq] = sign1*avg - g1;
+    avg += .5*sign0*g0[v];
+    avg += .5*sign1*g1[v];
+    l0[v*nfq] = sign0*avg - g0[v];
+    l1[v*nfq] = sign1*avg - g1[v];
   }
 }
 
