@@ -176,8 +176,9 @@ int launch_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, 
   if (!c->n_elem) return 0;
   ProjArgs p;
   for (int i = 0; i < MAX_RS; ++i) { p.w[i] = i < c->rs ? node_weights[i] : 0.; p.orth[i] = 0.; }
-  double* partial = nullptr;
-  HB_CUDA(c, cudaMalloc(&partial, sizeof(double)*c->n_elem));
+  DevScratch<double> scratch;
+  HB_CUDA(c, scratch.alloc(c->n_elem));
+  double* partial = scratch.p;
   rc = dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     constexpr int nq = ipow(RS, ND);
@@ -191,7 +192,6 @@ int launch_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, 
   });
   if (!rc) rc = check(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream), "read residual");
   if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "av_finish");
-  cudaFree(partial);
   if (!rc) *resid_sq = *c->h_scalar;
   return rc;
 }

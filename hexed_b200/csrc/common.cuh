@@ -141,6 +141,14 @@ struct StatScope
     }
   }
 };
+/* scratch device allocation released on every exit path */
+template <class T> struct DevScratch
+{
+  T* p = nullptr;
+  ~DevScratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T)*(n ? n : 1)); }
+};
+
 inline void invalidate_admis(hexed_b200_ctx* c) { c->admis_valid[0] = c->admis_valid[1] = false; }
 /* called by everything that rewrites the flow state (or the vertex spacing) outside the pipelined Local kernels */
 inline void invalidate_cfl_cache(hexed_b200_ctx* c) { c->cfl_valid[0] = c->cfl_valid[1] = false; invalidate_admis(c); }

@@ -332,8 +332,9 @@ int launch_shared_normals(hexed_b200_ctx* c)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   invalidate_admis(c); // the face storage is used as scratch for the normals
-  int* slot_kind = nullptr;
-  HB_CUDA(c, cudaMalloc(&slot_kind, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1)));
+  DevScratch<int> scratch;
+  HB_CUDA(c, scratch.alloc(c->n_face_slot));
+  int* slot_kind = scratch.p;
   HB_CUDA(c, cudaMemsetAsync(slot_kind, 0, sizeof(int)*(c->n_face_slot ? c->n_face_slot : 1), c->stream));
   int rc = 0;
   if (c->n_ref) {
@@ -355,8 +356,7 @@ int launch_shared_normals(hexed_b200_ctx* c)
   if (!rc && nr) { HB_LAUNCH(coarse_normal_kernel, (int)((nr + 255)/256), 256, 0, c->stream, a); ++c->launches; }
   if (!rc) rc = check(c, cudaGetLastError(), "shared normals");
   if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "shared normals");
-  cudaFree(slot_kind);
-  return rc;
+  return rc; // the scratch is released after the synchronisation
 }
 
 } // namespace hb
