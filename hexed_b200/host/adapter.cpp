@@ -604,6 +604,10 @@ double update_euler(Kernel_mesh km, double safety, int n_steps, double* last_dt,
 bool is_admissible(Kernel_mesh km, std::vector<int>* record)
 { // Solver::is_admissible, src/Solver.cpp:921-958
   Call call(km, state | faces, 0);
+  // a Solver that checks admissibility wants it after every stage: from now on the pipelined Local kernels leave the bits of what
+  // they write and the check right after a compute_euler reduces those (any other write to the state or faces, e.g. the uploads of
+  // sync_every_call mode, falls back to the full scan)
+  check(&call.m, hexed_b200_set_option(call.m.ctx, HEXED_B200_OPT_FUSED_ADMIS, 1));
   int ok = 0;
   check(&call.m, hexed_b200_is_admissible(call.m.ctx, &ok));
   if (record) {
