@@ -232,6 +232,45 @@ def test_adapter_is_admissible_emu(oracle, host_emu, resident):
     h.close()
 
 
+def test_adapter_is_admissible_after_stages_emu(oracle, host_emu):
+    """resident mode, the way Solver::update would use it: device boundary conditions, compute_euler, is_admissible after every stage.
+    The adapter switches the fused bits on at the first check, so the later ones take the 4-bytes-per-element path; same answers as
+    the oracle throughout, including after an over-long time step that leaves part of the mesh inadmissible."""
+    from util import density_wave, freestream_state
+    nd, rs = 2, 4
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 5, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    h = H.HostHarness(host_emu, m, basis, seed=2)
+    h.set_sync_mode(H.RESIDENT)
+    h.invalidate()
+    dt = oracle.max_dt(EULER, basis, ref, 0.5, 0.5, False)
+    h.call("max_dt_euler", 0.5, 0.5, False)
+    h.add_device_bcs(m)
+    seen = []
+    for step_dt in (dt, dt, 3e3*dt):
+        for stage in (0, 1):
+            oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=step_dt, i_stage=stage)
+            h.apply_state_bcs(); h.call("compute_euler", dt=step_dt, i_stage=stage)
+            try:
+                want, want_rec = oracle.is_admissible(ref)
+            except RuntimeError:
+                with pytest.raises(RuntimeError, match="state is not finite"):
+                    h.is_admissible()
+                seen.append("nonfinite")
+                break
+            got, rec = h.is_admissible()
+            assert got == want and np.array_equal(rec, want_rec)
+            seen.append(got)
+        if seen and seen[-1] == "nonfinite":
+            break
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    assert seen[:4] == [True]*4 and (False in seen or "nonfinite" in seen)
+
+
 @pytest.mark.parametrize("resident", [False, True])
 def test_adapter_av_glue_emu(oracle, host_emu, resident):
     """hexed_b200::av_scale_velocity / av_project_forcing / av_finish / interp_vertices / av_swap through the pointer-graph adapter (the
