@@ -577,6 +577,7 @@ static PdeParams make_params(hexed_b200_ctx* c, int pde, hexed_b200_transport vi
   PdeParams pp;
   std::memset(&pp, 0, sizeof(pp));
   pp.visc = visc; pp.cond = cond; pp.p0 = p0; pp.p1 = p1;
+  pp.visc_inv_sqrt_ref = 1./visc.sqrt_ref_temp; pp.cond_inv_sqrt_ref = 1./cond.sqrt_ref_temp;
   // pde::Advection uses the nodes of Gauss_legendre(row_size) mapped to [-1, 1] whatever the solution basis is (include/pde.hpp:281)
   for (int i = 0; i < c->rs; ++i) pp.adv_nodes[i] = 2*c->gl_node[i] - 1;
   (void)pde;

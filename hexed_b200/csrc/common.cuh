@@ -42,6 +42,7 @@ enum { ST_NEIGHBOR_CAR, ST_NEIGHBOR_DEF, ST_LOCAL_CAR, ST_LOCAL_DEF, ST_MAX_DT_C
 struct PdeParams
 {
   hexed_b200_transport visc, cond; // Navier-Stokes
+  double visc_inv_sqrt_ref, cond_inv_sqrt_ref; // 1/sqrt_ref_temp of the two models (one division per point and model less on the device)
   double p0, p1;                   // advection: advect_length | smooth_av: diff_time, chebyshev_step
   double adv_nodes[MAX_RS];        // advection: Gauss-Legendre nodes mapped to [-1, 1] (reference include/pde.hpp:281)
 };
