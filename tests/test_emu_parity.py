@@ -227,3 +227,8 @@ def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
 def test_update_euler_device_time_step(oracle, emu_lib, nd, rs, n, deformed):
     from util import check_update_euler
     check_update_euler(oracle, emu_lib, nd, rs, n, n_steps=4, use_graph=False, deformed=deformed)
+
+
+def test_update_euler_refined_mesh(oracle, emu_lib):
+    from util import check_update_euler
+    check_update_euler(oracle, emu_lib, 2, 4, 4, n_steps=3, use_graph=False, refined=True)

@@ -326,3 +326,10 @@ def test_update_euler_device_time_step(oracle, gpu_lib, nd, rs, n, deformed, use
     """time step on the device + CUDA graph replay of the step: bit-identical to the call-by-call sequence"""
     from util import check_update_euler
     check_update_euler(oracle, gpu_lib, nd, rs, n, n_steps=25, use_graph=use_graph, deformed=deformed)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 9), (3, 6, 4)])
+def test_update_euler_refined_mesh(oracle, gpu_lib, nd, rs, n):
+    """the graph-replayed step on a mesh with hanging-node faces"""
+    from util import check_update_euler
+    check_update_euler(oracle, gpu_lib, nd, rs, n, n_steps=20, use_graph=True, refined=True)

@@ -644,15 +644,23 @@ def check_fused_admissibility(oracle, lib, nd, rs, n):
     dev.close()
 
 
-def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=False, bc="riemann"):
+def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=False, bc="riemann", refined=False):
     """hexed_b200_update_euler (time step kept on the device, optional CUDA graph) is bit-identical to the same steps made call by call
     through the reference-shaped entry points, and both track the oracle"""
     basis = hb.gauss_legendre(rs)
     fs = freestream_state(nd)
     kind = M.BC_RIEMANN_INVARIANTS if bc == "riemann" else M.BC_FREESTREAM
-    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=kind, bc_params=fs)
+    if refined:  # hanging-node faces: Restrict / Prolong inside every stage of the captured step
+        refine = np.zeros((n,)*nd, bool)
+        refine[(slice(n//3, max(n//3 + 1, 2*n//3)),)*nd] = True
+        m = M.refined_box_mesh(nd, rs, n, basis, refine, bc_kind=M.BC_NONPENETRATION)
+        assert m.ref_face.shape[0] > 0
+    else:
+        m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=kind, bc_params=fs)
     density_wave(m, basis)
     oracle.compute_write_face(basis, m)
+    if refined:
+        oracle.compute_prolong(basis, m)
     ref = m.copy()
     a = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
     b = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
