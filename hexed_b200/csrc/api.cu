@@ -459,22 +459,49 @@ static int enqueue_euler_step(hexed_b200_ctx* c, double safety_conv)
   return rc;
 }
 
-int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced)
+/* viscous step (Solver::update with use_ldg(), src/Solver.cpp:857-865): max_dt_navier_stokes + ghost fill + compute_navier_stokes (stage 0,
+ * flux boundary conditions on the device) + ghost fill + compute_euler (stage 1) */
+struct ViscousStep { double safety_diff; hexed_b200_transport visc, cond; };
+static const GenericOps* generic_ops(int pde);
+static PdeParams make_params(hexed_b200_ctx* c, int pde, hexed_b200_transport visc, hexed_b200_transport cond, double p0, double p1);
+static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, const PdeParams& pp, hexed_b200_callback flux_bc, void* user);
+
+static void device_flux_bcs(void* user) { launch_flux_bcs(static_cast<hexed_b200_ctx*>(user)); }
+
+static int enqueue_viscous_step(hexed_b200_ctx* c, double safety_conv, const ViscousStep& v)
+{
+  const PdeParams pp = make_params(c, 1, v.visc, v.cond, 0., 0.);
+  double unused = 0;
+  c->max_dt_device_out = c->d_step;
+  int rc = generic_ops(1)->max_dt(c, pp, safety_conv, v.safety_diff, 0, &unused);
+  c->max_dt_device_out = nullptr;
+  hexed_b200_options o; o.dt = 1.; o.i_stage = 0; o.compute_residual = 0; o.use_filter = 0;
+  if (!rc) rc = launch_bcs(c);
+  if (!rc) rc = diffusion_stage(c, 1, o, pp, device_flux_bcs, c);
+  o.i_stage = 1;
+  if (!rc) rc = launch_bcs(c);
+  if (!rc) rc = hexed_b200_compute_euler(c, o);
+  if (!rc) rc = launch_accumulate_time(c, c->d_step);
+  return rc;
+}
+
+static int update_loop(hexed_b200_ctx* c, double safety_conv, const ViscousStep* viscous, int n_steps, int use_graph, double* last_dt, double* time_advanced)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (n_steps < 0) return fail(c, HEXED_B200_BAD_ARGUMENT, "negative step count");
+  auto enqueue = [&]() { return viscous ? enqueue_viscous_step(c, safety_conv, *viscous) : enqueue_euler_step(c, safety_conv); };
   const bool timing = c->timing;
   c->timing = false; // per-launch events cannot be queried inside a capture; this entry point is timed as a whole by its caller
   HB_CUDA(c, cudaMemsetAsync(c->d_step, 0, 2*sizeof(double), c->stream));
   c->dt_dev_active = c->d_step;
   int rc = 0, done = 0;
-  if (n_steps > 0) { rc = enqueue_euler_step(c, safety_conv); done = 1; } // eager: also performs every lazy allocation / attribute call
+  if (n_steps > 0) { rc = enqueue(); done = 1; } // eager: also performs every lazy allocation / attribute call
 #ifndef HB_EMULATE
   if (!rc && use_graph && n_steps > done) {
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     rc = check(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
     if (!rc) {
-      const int rc_step = enqueue_euler_step(c, safety_conv);
+      const int rc_step = enqueue();
       const int rc_end = check(c, cudaStreamEndCapture(c->stream, &graph), "end capture");
       rc = rc_step ? rc_step : rc_end;
     }
@@ -486,8 +513,8 @@ int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, 
 #else
   (void)use_graph;
 #endif
-  for (; !rc && done < n_steps; ++done) rc = enqueue_euler_step(c, safety_conv);
-  c->dt_dev_active = nullptr;
+  for (; !rc && done < n_steps; ++done) rc = enqueue();
+  c->dt_dev_active = nullptr; c->max_dt_device_out = nullptr;
   c->timing = timing;
   if (rc) return rc;
   HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -497,6 +524,16 @@ int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, 
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (time_advanced) *time_advanced = *c->h_scalar;
   return 0;
+}
+
+int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced)
+{ return update_loop(c, safety_conv, nullptr, n_steps, use_graph, last_dt, time_advanced); }
+
+int hexed_b200_update_navier_stokes(hexed_b200_ctx* c, double safety_conv, double safety_diff, hexed_b200_transport visc, hexed_b200_transport therm_cond,
+                                    int n_steps, int use_graph, double* last_dt, double* time_advanced)
+{
+  const ViscousStep v{safety_diff, visc, therm_cond};
+  return update_loop(c, safety_conv, &v, n_steps, use_graph, last_dt, time_advanced);
 }
 
 /* ---- domain decomposition ---- */

@@ -104,6 +104,7 @@ struct hexed_b200_ctx
   // hexed_b200_update_euler: the time step stays on the device. d_step = {dt of the current step, accumulated flow time}; while
   // dt_dev_active is non-null the Euler Local launchers hand it to their kernels, which multiply their `update` factor by it.
   double* d_step = nullptr; const double* dt_dev_active = nullptr;
+  double* max_dt_device_out = nullptr; // non-null: the generic max_dt leaves its result there instead of reading it back
   bool tss_is_one = false; // time_step_scale is known to hold 1. everywhere (written by a global-time-step max_dt)
   // vertex topology of the epoch (hexed_b200_vertex_topology) and per-element-vertex scratch (vertex_fix_admis_coef / vertex_elwise_av)
   int* elem_vertex = nullptr; int n_vertex = 0; int* matchers = nullptr; int n_match = 0;

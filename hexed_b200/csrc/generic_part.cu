@@ -27,6 +27,7 @@ struct GArgs
   const int* con; const int* perm; int n_con;
   int elem_begin, elem_end, n_car;
   double update; int stage, compute_residual, use_filter;
+  const double* dt_dev; // non-null: the time step lives on the device (hexed_b200_update_*) and multiplies `update`
   double max_cfl_c, max_cfl_d, inv_max_cfl_c, inv_max_cfl_d; int is_local; unsigned long long* global_min;
   PdeParams pp;
 };
@@ -423,7 +424,7 @@ g_local_kernel(GArgs a, Ops ops, FilterOp filt)
 
   // update: Spatial.hpp:484-503
   if (active) {
-    double mult = a.update*tss/nom;
+    double mult = (a.dt_dev ? *a.dt_dev*a.update : a.update)*tss/nom;
     if constexpr (DEF) mult /= det;
     double upd[nu]; double* tgt[nu];
     #pragma unroll
@@ -678,8 +679,9 @@ ns_local_line_kernel(GArgs a, Ops ops)
   /* ---- P4: combine and update ---- */
   for (int q = t; q < nq; q += T) {
     double mult; // update*tss/nom/det with one division (<= 1 ulp)
-    if constexpr (DEF) mult = a.update*g_tss[q]/(nom*g_det[q]);
-    else mult = a.update*g_tss[q]/nom;
+    const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
+    if constexpr (DEF) mult = update*g_tss[q]/(nom*g_det[q]);
+    else mult = update*g_tss[q]/nom;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double r0 = 0., r1 = 0.;
@@ -758,7 +760,7 @@ ns_reconcile_bulk_kernel(GArgs a, Ops ops)
         r[v] -= acc;
       }
     }
-    double mult = a.update*s_tss[q]/nom;
+    double mult = (a.dt_dev ? *a.dt_dev*a.update : a.update)*s_tss[q]/nom;
     if constexpr (DEF) mult /= s_det[q];
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
@@ -841,7 +843,7 @@ ns_reconcile_bulk2d_kernel(GArgs a, Ops ops)
         r[v] -= acc;
       }
     }
-    double mult = a.update*s_tss[pt]/a.nom[e0 + pe];
+    double mult = (a.dt_dev ? *a.dt_dev*a.update : a.update)*s_tss[pt]/a.nom[e0 + pe];
     if constexpr (DEF) mult /= s_det[pt];
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
@@ -1117,8 +1119,9 @@ ns_local_line2d_kernel(GArgs a, Ops ops)
     const double* S = eb + C::s_state; const double* G = eb + C::s_grad; const double* F = eb + C::s_flux;
     const double nom = a.nom[e];
     double mult; // update*tss/nom/det with one division (<= 1 ulp)
-    if constexpr (DEF) mult = a.update*g_tss[pt]/(nom*g_det[pt]);
-    else mult = a.update*g_tss[pt]/nom;
+    const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
+    if constexpr (DEF) mult = update*g_tss[pt]/(nom*g_det[pt]);
+    else mult = update*g_tss[pt]/nom;
     #pragma unroll
     for (int v = 0; v < nv; ++v) {
       double r0 = 0., r1 = 0.;
@@ -1225,7 +1228,7 @@ g_reconcile_kernel(GArgs a, Ops ops, FilterOp filt)
   }
   if (active) {
     const double tss = a.ed.tss[(size_t)e*nq + q];
-    double mult = a.update*tss/a.nom[e];
+    double mult = (a.dt_dev ? *a.dt_dev*a.update : a.update)*tss/a.nom[e];
     if constexpr (DEF) mult /= a.det[(size_t)(e - a.n_car)*nq + q];
     double upd[nu]; double* tgt[nu];
     #pragma unroll
@@ -1343,7 +1346,7 @@ int fill_args(hexed_b200_ctx* c, GArgs& a, const PdeParams& pp)
   a.face_width = (kind == 2 ? c->nd + c->rs : c->nv)*c->nfq;
   a.con = nullptr; a.perm = c->perm; a.n_con = 0;
   a.elem_begin = 0; a.elem_end = c->n_elem; a.n_car = c->n_car;
-  a.update = 0; a.stage = 0; a.compute_residual = 0; a.use_filter = 0;
+  a.update = 0; a.stage = 0; a.compute_residual = 0; a.use_filter = 0; a.dt_dev = c->dt_dev_active;
   a.max_cfl_c = 1; a.max_cfl_d = 1; a.inv_max_cfl_c = 1; a.inv_max_cfl_d = 1; a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
   a.pp = pp;
   return 0;
@@ -1466,12 +1469,15 @@ int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double 
     using P = Pde<ND, RS>;
     const long long total = (long long)c->n_elem*ipow(RS, ND);
     const int grid = (int)((total + 255)/256);
-    if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream));
+    double* result = c->max_dt_device_out ? c->max_dt_device_out : c->d_scalar; // hexed_b200_update_*: leave dt on the device
+    a.global_min = reinterpret_cast<unsigned long long*>(result);
+    if (!local_time) HB_CUDA(c, cudaMemsetAsync(result, 0x7f, sizeof(double), c->stream));
     { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
     c->tss_is_one = !local_time;
     if (local_time) { *dt = 1.; return 0; }
+    if (c->max_dt_device_out) { *dt = 1.; return 0; }
     HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(c, cudaStreamSynchronize(c->stream));
     *dt = *c->h_scalar;

@@ -100,6 +100,7 @@ SIGNATURES = {
     "hexed_b200_av_swap": [C.c_void_p],
     "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
     "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, dp, dp],
+    "hexed_b200_update_navier_stokes": [C.c_void_p, C.c_double, C.c_double, Transport, Transport, C.c_int, C.c_int, dp, dp],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
     "hexed_b200_vertex_topology": [C.c_void_p, ip, C.c_int, ip, C.c_int],
     "hexed_b200_share_vertex_data": [C.c_void_p, C.c_int, C.c_int],
@@ -475,6 +476,13 @@ class Device:
         dt, t = C.c_double(0.), C.c_double(0.)
         self._check(self.lib.hexed_b200_update_euler(self.ctx, float(safety), int(n_steps), int(bool(use_graph)),
                                                      C.cast(C.byref(dt), dp), C.cast(C.byref(t), dp)))
+        return dt.value, t.value
+
+    def update_navier_stokes(self, safety_conv, safety_diff, visc, therm_cond, n_steps, use_graph=True):
+        """the viscous counterpart of update_euler (stage 0 compute_navier_stokes with device flux boundary conditions, stage 1 compute_euler)"""
+        dt, t = C.c_double(0.), C.c_double(0.)
+        self._check(self.lib.hexed_b200_update_navier_stokes(self.ctx, float(safety_conv), float(safety_diff), visc, therm_cond, int(n_steps),
+                                                             int(bool(use_graph)), C.cast(C.byref(dt), dp), C.cast(C.byref(t), dp)))
         return dt.value, t.value
 
     def is_admissible(self):

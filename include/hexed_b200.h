@@ -212,6 +212,10 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
  * kept on the device (no synchronisation per step); with use_graph the step is captured once in a CUDA graph and replayed. Bit-identical
  * to the same calls made one by one. Returns the last time step and the flow time advanced. For launch-bound (small) meshes. ---- */
 int hexed_b200_update_euler(hexed_b200_ctx* ctx, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced);
+/* the same for the viscous case (use_ldg(), :857-865): max_dt_navier_stokes + ghost fill + compute_navier_stokes (stage 0, flux boundary
+ * conditions on the device) + ghost fill + compute_euler (stage 1) */
+int hexed_b200_update_navier_stokes(hexed_b200_ctx* ctx, double safety_conv, double safety_diff, hexed_b200_transport visc,
+                                    hexed_b200_transport therm_cond, int n_steps, int use_graph, double* last_dt, double* time_advanced);
 
 /* ---- thermodynamic admissibility: Solver::is_admissible (src/Solver.cpp:921-958, src/thermo.cpp:6-18), which
  * Solver::update runs after EVERY stage through fix_admissibility (:864-868). *admissible = 1 iff mass > 0 and energy > 0 at every

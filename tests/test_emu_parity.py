@@ -232,3 +232,9 @@ def test_update_euler_device_time_step(oracle, emu_lib, nd, rs, n, deformed):
 def test_update_euler_refined_mesh(oracle, emu_lib):
     from util import check_update_euler
     check_update_euler(oracle, emu_lib, 2, 4, 4, n_steps=3, use_graph=False, refined=True)
+
+
+@pytest.mark.parametrize("nd,rs,n", [(2, 4, 4), (2, 3, 3), (3, 4, 2)])
+def test_update_navier_stokes_device_time_step(oracle, emu_lib, nd, rs, n):
+    from util import check_update_navier_stokes
+    check_update_navier_stokes(oracle, emu_lib, nd, rs, n, n_steps=3, use_graph=False)

@@ -333,3 +333,11 @@ def test_update_euler_refined_mesh(oracle, gpu_lib, nd, rs, n):
     """the graph-replayed step on a mesh with hanging-node faces"""
     from util import check_update_euler
     check_update_euler(oracle, gpu_lib, nd, rs, n, n_steps=20, use_graph=True, refined=True)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 16), (3, 6, 5), (2, 5, 9)])
+def test_update_navier_stokes_device_time_step(oracle, gpu_lib, nd, rs, n, use_graph):
+    """the viscous loop with the time step on the device + CUDA graph replay: bit-identical to the call-by-call sequence"""
+    from util import check_update_navier_stokes
+    check_update_navier_stokes(oracle, gpu_lib, nd, rs, n, n_steps=12, use_graph=use_graph)

@@ -679,3 +679,36 @@ def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=Fals
     assert dt_b == dt and t_b == t_a
     assert np.array_equal(out_a.elem_data, out_b.elem_data) and np.array_equal(out_a.face_state, out_b.face_state)
     assert rel_l2(out_b.state(), ref.state()) <= STATE_TOL
+
+
+def check_update_navier_stokes(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=True):
+    """hexed_b200_update_navier_stokes (time step on the device, optional CUDA graph) is bit-identical to the same viscous steps made
+    call by call, and both track the oracle"""
+    import pyoracle
+    from hexed_b200 import kernels as K
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref = m.copy()
+    visc_o, cond_o = pyoracle.sutherland(1.716e-5, 273., 111.), pyoracle.sutherland(.0241, 273., 194.)
+    visc_d, cond_d = K.sutherland(1.716e-5, 273., 111.), K.sutherland(.0241, 273., 194.)
+    a = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    b = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    t_a = 0.
+    for _ in range(n_steps):
+        dt = a.max_dt_navier_stokes(0.3, 0.3, False, visc_d, cond_d)
+        dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, False, visc_o, cond_o)
+        a.apply_state_bcs(); a.compute_navier_stokes(a.apply_flux_bcs, visc_d, cond_d, dt=dt, i_stage=0)
+        a.apply_state_bcs(); a.compute_euler(dt=dt, i_stage=1)
+        oracle.apply_state_bcs(ref); oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0)
+        oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=1)
+        t_a += dt
+    dt_b, t_b = b.update_navier_stokes(0.3, 0.3, visc_d, cond_d, n_steps, use_graph)
+    out_a, out_b = m.copy(), m.copy()
+    a.sync_to_host(out_a); b.sync_to_host(out_b)
+    a.close(); b.close()
+    assert dt_b == dt and t_b == t_a
+    assert np.array_equal(out_a.elem_data, out_b.elem_data) and np.array_equal(out_a.face_state, out_b.face_state)
+    assert np.array_equal(out_a.face_ldg, out_b.face_ldg)
+    assert rel_l2(out_b.state(), ref.state()) <= STATE_TOL
