@@ -52,6 +52,30 @@ def main():
         res["dof_stage_per_s_graph"] = n*n*4*rs*rs*2/(res["device_dt_graph_us_per_step"]*1e-6)
         print(json.dumps(res))
         dev.close()
+    # the cylinder class: 2-D viscous, deformed quads, wall boundary conditions, Sutherland air
+    from hexed_b200 import kernels as K
+    from util import density_wave
+    visc, cond = K.sutherland(1.716e-5, 273., 111.), K.sutherland(.0241, 273., 194.)
+    for n in (16, 64):
+        m = M.box_mesh(2, rs, n, basis, deformed=True, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
+        density_wave(m, basis)
+        oracle.compute_write_face(basis, m)
+        dev = Device(2, rs, basis).load_mesh(m)
+        n_steps = 1000
+
+        def call_by_call_ns(k):
+            for _ in range(k):
+                dt = dev.max_dt_navier_stokes(0.1, 0.1, False, visc, cond)
+                dev.apply_state_bcs(); dev.compute_navier_stokes(dev.apply_flux_bcs, visc, cond, dt=dt, i_stage=0)
+                dev.apply_state_bcs(); dev.compute_euler(dt=dt, i_stage=1)
+        res = {"workload": "samples/cylinder class: %d x %d deformed quads, row size 6, Navier-Stokes, wall BCs" % (n, n), "elements": n*n, "steps": n_steps}
+        for name, fn in (("call_by_call", call_by_call_ns), ("device_dt", lambda k: dev.update_navier_stokes(0.1, 0.1, visc, cond, k, False)),
+                         ("device_dt_graph", lambda k: dev.update_navier_stokes(0.1, 0.1, visc, cond, k, True))):
+            fn(20); torch.cuda.synchronize()
+            t = time.perf_counter(); fn(n_steps); dev.synchronize(); el = time.perf_counter() - t
+            res[name + "_us_per_step"] = el/n_steps*1e6
+        print(json.dumps(res))
+        dev.close()
 
 
 if __name__ == "__main__":
