@@ -17,7 +17,9 @@ struct MaxDtArgs
 constexpr int max_dt_ppt = 1; // points per thread. Measured with 2 (both points' loads in flight before either is used; 70 registers, 3 CTAs
                               // of 256 per SM instead of 6): 3.0 ms against 2.54 ms at 1 M 3-D elements -- occupancy hides the load latency
                               // better than per-thread memory-level parallelism does; the arithmetic (two square roots, a reciprocal and a
-                              // division per point, ~256 instructions) keeps the kernel at 4.1 TB/s (profiles/r01l_ncu_full_euler.md)
+                              // division per point, ~256 instructions) keeps the kernel at 4.1 TB/s (profiles/r01l_ncu_full_euler.md).
+                              // Also measured: a single-precision screen with a block-wide minimum so that only the points within 2e-5 of it
+                              // take the FP64 path (dt stays bit-identical): 2.97 ms -- the extra barrier serialises the block's loads.
 template <int ND, int RS>
 __global__ void __launch_bounds__(256)
 max_dt_euler_kernel(MaxDtArgs a, Ops ops)
@@ -38,60 +40,10 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
       for (int i = 0; i < n_vert; ++i) vt[r][i] = a.vtss[(size_t)elem[r]*n_vert + i];
     }
   }
-  /* Global time step: only the minimum matters, and the exact FP64 evaluation (two square roots, a reciprocal and a division: ~110 of the
-   * kernel's ~256 instructions per point) is needed only where the minimum can be. Screen first in single precision (MUFU-assisted,
-   * good to ~1e-6 relative), take the block's minimum of the screen, and evaluate in FP64 only the points within 2e-5 of it: the
-   * block's true minimum is always among them, so dt is bit-identical; most warps skip the FP64 path altogether. A screen value
-   * that is not a positive finite float (0 below) always takes the exact path. */
-  bool exact[PPT];
-  #pragma unroll
-  for (int r = 0; r < PPT; ++r) exact[r] = elem[r] < a.n_elem;
-  if (!a.is_local) {
-    __shared__ float warp_screen[8];
-    float screen[PPT], smin = 3.0e38f;
-    #pragma unroll
-    for (int r = 0; r < PPT; ++r) {
-      screen[r] = 3.0e38f;
-      if (elem[r] < a.n_elem) {
-        float sv[n_vert];
-        #pragma unroll
-        for (int i = 0; i < n_vert; ++i) sv[i] = (float)vt[r][i];
-        int str = n_vert;
-        #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          const float coord = (float)ops.node[(pt[r]/ipow(RS, ND - 1 - d)) % RS];
-          str /= 2;
-          #pragma unroll
-          for (int i = 0; i < n_vert/2; ++i) if (i < str) sv[i] += coord*(sv[i + str] - sv[i]);
-        }
-        const float rho = (float)st[r][ND], en = (float)st[r][ND + 1];
-        float m2 = 0.f;
-        #pragma unroll
-        for (int i = 0; i < ND; ++i) m2 += (float)st[r][i]*(float)st[r][i];
-        const float inv = __fdividef(1.f, rho);
-        const float a2 = 0.56f*en*inv;
-        const float cs = a2*rsqrtf(a2) + m2*rsqrtf(m2 + 1e-30f)*inv; // sqrt(x) = x*rsqrt(x)
-        float rf = __fdividef(sv[0], cs);
-        if (!(rf > 0.f && rf < 3.0e38f)) rf = 0.f;
-        screen[r] = rf;
-        if (rf > 0.f) smin = fminf(smin, rf);
-      }
-    }
-    #pragma unroll
-    for (int off = 16; off > 0; off /= 2) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, off));
-    if (threadIdx.x % 32 == 0) warp_screen[threadIdx.x/32] = smin;
-    __syncthreads();
-    float bmin = warp_screen[0];
-    #pragma unroll
-    for (int i = 1; i < 8; ++i) bmin = fminf(bmin, warp_screen[i]);
-    #pragma unroll
-    for (int r = 0; r < PPT; ++r) exact[r] = exact[r] && (screen[r] == 0.f || screen[r] <= bmin*(1.f + 2e-5f));
-  }
   double val = DBL_MAX;
   #pragma unroll
   for (int r = 0; r < PPT; ++r) {
-    if (elem[r] < a.n_elem && !a.is_local) a.tss[(size_t)elem[r]*nq + pt[r]] = 1.;
-    if (exact[r]) {
+    if (elem[r] < a.n_elem) {
       const double spacing = interp_vertex_spacing<ND, RS>(vt[r], ops, pt[r]);
       EulerPoint<ND> p;
       #pragma unroll
@@ -100,7 +52,7 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
       // 1/scale with scale = char_speed/max_cfl/spacing (Spatial.hpp:808-822), rearranged to a single division
       const double local_dt = a.max_cfl_c*spacing/p.char_speed();
       if (a.is_local) a.tss[(size_t)elem[r]*nq + pt[r]] = local_dt;
-      else val = fmin(val, local_dt);
+      else { a.tss[(size_t)elem[r]*nq + pt[r]] = 1.; val = fmin(val, local_dt); }
     }
   }
   if (a.is_local) return;
