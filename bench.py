@@ -61,8 +61,8 @@ def parse():
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3 = the headline; 2 = the shape of the 2-D BASELINE configs (vortex / naca0012 / cylinder)")
     ap.add_argument("--pde", default="euler", choices=["euler", "navier_stokes"],
                     help="euler = the headline; navier_stokes = Solver::update with use_ldg (stage 0 viscous/LDG, stage 1 inviscid), 1 GPU only")
-    ap.add_argument("--cpu-n", type=int, default=32, help="box edge of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
+    ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -417,7 +417,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rate, cs, cores, sample = cpu_reference_rate(args, args.cpu_steps, 1)
+            rate, cs, cores, sample = cpu_reference_rate(args, args.cpu_steps, 3)
             cpu = {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample}
         except Exception as ex:  # the baseline is informative; never let it take the GPU number down
             cpu = {"value": None, "unit": "DOF-stage/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
