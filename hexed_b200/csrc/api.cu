@@ -163,7 +163,7 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev1), "cudaEventCreate");
   if (!rc) rc = dev_alloc(c, &c->d_scalar, 8);
-  if (!rc) rc = dev_alloc(c, &c->d_step, 2);
+  if (!rc) rc = dev_alloc(c, &c->d_step, 3);
   if (!rc) rc = check(c, cudaMallocHost(&c->h_scalar, sizeof(double)*8), "cudaMallocHost");
   // permutation tables for all 36 direction codes
   c->h_perm.assign((size_t)36*c->nfq, 0);
@@ -447,9 +447,12 @@ int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
  * reduction leaves dt on the device, the Local kernels read it from there, and the step is captured ONCE in a CUDA graph and replayed.
  * On the large meshes of the headline the step is 30 ms and none of this matters; on the meshes of the 2-D sample cases (vortex:
  * 256 elements, ~10 launches of a few microseconds each) launch latency and the synchronisation ARE the step. */
-static int enqueue_euler_step(hexed_b200_ctx* c, double safety_conv)
+static double chebyshev_step(int n_steps, int i_step) { return 1/(1 - std::cos((n_steps - i_step - 0.5)*M_PI/n_steps)); } // src/math.cpp:104-107
+
+static int enqueue_euler_step(hexed_b200_ctx* c, double safety_conv, double cheby_factor)
 {
   int rc = launch_max_dt_euler_device(c, safety_conv, c->d_step);
+  if (!rc) rc = launch_scale_dt(c, c->d_step, cheby_factor); // dt = nominal_dt*chebyshev_step(n_cheby, i_cheby), :850
   for (int stage = 0; stage < 2 && !rc; ++stage) {
     hexed_b200_options o; o.dt = 1.; o.i_stage = stage; o.compute_residual = 0; o.use_filter = 0;
     rc = launch_bcs(c);
@@ -468,13 +471,14 @@ static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, con
 
 static void device_flux_bcs(void* user) { launch_flux_bcs(static_cast<hexed_b200_ctx*>(user)); }
 
-static int enqueue_viscous_step(hexed_b200_ctx* c, double safety_conv, const ViscousStep& v)
+static int enqueue_viscous_step(hexed_b200_ctx* c, double safety_conv, const ViscousStep& v, double cheby_factor)
 {
   const PdeParams pp = make_params(c, 1, v.visc, v.cond, 0., 0.);
   double unused = 0;
   c->max_dt_device_out = c->d_step;
   int rc = generic_ops(1)->max_dt(c, pp, safety_conv, v.safety_diff, 0, &unused);
   c->max_dt_device_out = nullptr;
+  if (!rc) rc = launch_scale_dt(c, c->d_step, cheby_factor);
   hexed_b200_options o; o.dt = 1.; o.i_stage = 0; o.compute_residual = 0; o.use_filter = 0;
   if (!rc) rc = launch_bcs(c);
   if (!rc) rc = diffusion_stage(c, 1, o, pp, device_flux_bcs, c);
@@ -485,39 +489,45 @@ static int enqueue_viscous_step(hexed_b200_ctx* c, double safety_conv, const Vis
   return rc;
 }
 
-static int update_loop(hexed_b200_ctx* c, double safety_conv, const ViscousStep* viscous, int n_steps, int use_graph, double* last_dt, double* time_advanced)
+static int update_loop(hexed_b200_ctx* c, double safety, const ViscousStep* viscous, int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
-  if (n_steps < 0) return fail(c, HEXED_B200_BAD_ARGUMENT, "negative step count");
-  auto enqueue = [&]() { return viscous ? enqueue_viscous_step(c, safety_conv, *viscous) : enqueue_euler_step(c, safety_conv); };
+  if (n_steps < 0 || n_cheby < 1) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad step or Chebyshev count");
+  // Solver::update (:842-851): nominal_dt = max_dt(safety/max_cheby, safety), dt = nominal_dt*chebyshev_step(n_cheby, i_cheby)
+  const double safety_conv = safety/chebyshev_step(n_cheby, n_cheby - 1);
+  auto enqueue = [&](int i_step) {
+    const double f = chebyshev_step(n_cheby, i_step % n_cheby);
+    return viscous ? enqueue_viscous_step(c, safety_conv, *viscous, f) : enqueue_euler_step(c, safety_conv, f);
+  };
   const bool timing = c->timing;
   c->timing = false; // per-launch events cannot be queried inside a capture; this entry point is timed as a whole by its caller
-  HB_CUDA(c, cudaMemsetAsync(c->d_step, 0, 2*sizeof(double), c->stream));
-  c->dt_dev_active = c->d_step;
+  HB_CUDA(c, cudaMemsetAsync(c->d_step, 0, 3*sizeof(double), c->stream));
+  c->dt_dev_active = c->d_step + 2;
   int rc = 0, done = 0;
-  if (n_steps > 0) { rc = enqueue(); done = 1; } // eager: also performs every lazy allocation / attribute call
+  for (; !rc && done < n_steps && done < n_cheby; ++done) rc = enqueue(done); // one eager cycle: also performs every lazy allocation
 #ifndef HB_EMULATE
-  if (!rc && use_graph && n_steps > done) {
+  if (!rc && use_graph && n_steps - done >= n_cheby) {
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     rc = check(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
     if (!rc) {
-      const int rc_step = enqueue();
+      int rc_step = 0;
+      for (int i = 0; i < n_cheby && !rc_step; ++i) rc_step = enqueue(i); // one whole Chebyshev cycle per graph
       const int rc_end = check(c, cudaStreamEndCapture(c->stream, &graph), "end capture");
       rc = rc_step ? rc_step : rc_end;
     }
     if (!rc) rc = check(c, cudaGraphInstantiate(&exec, graph, 0), "instantiate graph");
-    for (; !rc && done < n_steps; ++done) rc = check(c, cudaGraphLaunch(exec, c->stream), "launch graph");
+    for (; !rc && n_steps - done >= n_cheby; done += n_cheby) rc = check(c, cudaGraphLaunch(exec, c->stream), "launch graph");
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
   }
 #else
   (void)use_graph;
 #endif
-  for (; !rc && done < n_steps; ++done) rc = enqueue();
+  for (; !rc && done < n_steps; ++done) rc = enqueue(done);
   c->dt_dev_active = nullptr; c->max_dt_device_out = nullptr;
   c->timing = timing;
   if (rc) return rc;
-  HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (last_dt) *last_dt = *c->h_scalar;
   HB_CUDA(c, cudaMemcpyAsync(c->h_scalar, c->d_step + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -526,14 +536,14 @@ static int update_loop(hexed_b200_ctx* c, double safety_conv, const ViscousStep*
   return 0;
 }
 
-int hexed_b200_update_euler(hexed_b200_ctx* c, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced)
-{ return update_loop(c, safety_conv, nullptr, n_steps, use_graph, last_dt, time_advanced); }
+int hexed_b200_update_euler(hexed_b200_ctx* c, double safety, int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced)
+{ return update_loop(c, safety, nullptr, n_cheby, n_steps, use_graph, last_dt, time_advanced); }
 
-int hexed_b200_update_navier_stokes(hexed_b200_ctx* c, double safety_conv, double safety_diff, hexed_b200_transport visc, hexed_b200_transport therm_cond,
-                                    int n_steps, int use_graph, double* last_dt, double* time_advanced)
+int hexed_b200_update_navier_stokes(hexed_b200_ctx* c, double safety, hexed_b200_transport visc, hexed_b200_transport therm_cond,
+                                    int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced)
 {
-  const ViscousStep v{safety_diff, visc, therm_cond};
-  return update_loop(c, safety_conv, &v, n_steps, use_graph, last_dt, time_advanced);
+  const ViscousStep v{safety, visc, therm_cond}; // max_dt(safety/max_cheby, safety): the diffusive safety is not divided (:849)
+  return update_loop(c, safety, &v, n_cheby, n_steps, use_graph, last_dt, time_advanced);
 }
 
 /* ---- domain decomposition ---- */

@@ -165,6 +165,7 @@ int launch_write_face(hexed_b200_ctx* c);
 int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, double* dt);
 int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_dt); // global time step, result left at d_dt (no read-back)
 int launch_accumulate_time(hexed_b200_ctx* c, double* d_step);
+int launch_scale_dt(hexed_b200_ctx* c, double* d_step, double factor);
 int launch_prolong(hexed_b200_ctx* c, int kind, int n_var, int scale, const int* ref_index = nullptr, int n_index = 0);
 int launch_restrict(hexed_b200_ctx* c, int kind, int n_var, int scale);
 int launch_bcs(hexed_b200_ctx* c);

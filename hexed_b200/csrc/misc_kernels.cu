@@ -211,7 +211,17 @@ int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_
   });
 }
 
-__global__ void accumulate_time_kernel(double* step) { step[1] += step[0]; }
+/* step = {nominal dt from the reduction, accumulated flow time, dt of this step = nominal * Chebyshev factor} */
+__global__ void scale_dt_kernel(double* step, double factor) { step[2] = step[0]*factor; }
+__global__ void accumulate_time_kernel(double* step) { step[1] += step[2]; }
+
+int launch_scale_dt(hexed_b200_ctx* c, double* d_step, double factor)
+{
+  HB_LAUNCH(scale_dt_kernel, 1, 1, 0, c->stream, d_step, factor);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
 
 int launch_accumulate_time(hexed_b200_ctx* c, double* d_step)
 {

@@ -590,11 +590,11 @@ void apply_state_bcs(Kernel_mesh km)
   call.finish();
 }
 
-double update_euler(Kernel_mesh km, double safety, int n_steps, double* last_dt, bool use_graph)
+double update_euler(Kernel_mesh km, double safety, int n_steps, double* last_dt, bool use_graph, int n_cheby)
 { // the flow loop of Solver::update (src/Solver.cpp:834-886) for the inviscid case, n_cheby_flow = 1, device boundary conditions
   Call call(km, state | tss | res_cache | faces, state | tss | res_cache | faces);
   double dt = 0, t = 0;
-  check(&call.m, hexed_b200_update_euler(call.m.ctx, safety, n_steps, use_graph, &dt, &t));
+  check(&call.m, hexed_b200_update_euler(call.m.ctx, safety, n_cheby, n_steps, use_graph, &dt, &t));
   call.m.device_bcs_ran = true;
   call.finish();
   if (last_dt) *last_dt = dt;

@@ -80,11 +80,11 @@ void interp_vertices(hexed::Kernel_mesh, int target, const std::vector<double>& 
 void av_swap(hexed::Kernel_mesh);
 void apply_aux_bcs(hexed::Kernel_mesh, int mode);
 
-/*! \brief `n_steps` passes of the flow loop of `Solver::update` (src/Solver.cpp:834-886) for the inviscid case with `n_cheby_flow = 1` and
+/*! \brief `n_steps` passes of the flow loop of `Solver::update` (src/Solver.cpp:834-886) for the inviscid case (`n_cheby` = `n_cheby_flow`) and
  * every boundary condition registered with `add_device_bc`: `max_dt_euler(safety)` + two stages, each `apply_state_bcs` + `compute_euler`.
  * The time step never leaves the device and the step is replayed from a CUDA graph (`use_graph`), which is what matters on the small
  * meshes of the 2-D sample cases. Returns the flow time advanced (add it to `status.flow_time`); `last_dt` receives `status.time_step`. */
-double update_euler(hexed::Kernel_mesh, double safety, int n_steps, double* last_dt = nullptr, bool use_graph = true);
+double update_euler(hexed::Kernel_mesh, double safety, int n_steps, double* last_dt = nullptr, bool use_graph = true, int n_cheby = 1);
 
 /*! \brief `Solver::is_admissible` (src/Solver.cpp:921-958) on the device: the check Solver::update makes after every
  * stage. Returns what the reference returns; `record`, if given, receives `Element::record` of every element in `Kernel_mesh::elems` order

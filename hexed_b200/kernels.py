@@ -99,8 +99,8 @@ SIGNATURES = {
     "hexed_b200_interp_vertices": [C.c_void_p, C.c_int, dp, dp],
     "hexed_b200_av_swap": [C.c_void_p],
     "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
-    "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, dp, dp],
-    "hexed_b200_update_navier_stokes": [C.c_void_p, C.c_double, C.c_double, Transport, Transport, C.c_int, C.c_int, dp, dp],
+    "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp],
+    "hexed_b200_update_navier_stokes": [C.c_void_p, C.c_double, Transport, Transport, C.c_int, C.c_int, C.c_int, dp, dp],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
     "hexed_b200_vertex_topology": [C.c_void_p, ip, C.c_int, ip, C.c_int],
     "hexed_b200_share_vertex_data": [C.c_void_p, C.c_int, C.c_int],
@@ -470,18 +470,18 @@ class Device:
         """connection passes of Solver::calc_jacobian (reference src/Solver.cpp:287-369)"""
         self._check(self.lib.hexed_b200_calc_shared_normals(self.ctx))
 
-    def update_euler(self, safety, n_steps, use_graph=True):
-        """n_steps of Solver::update's inviscid loop (max_dt + 2 stages with device ghost fills) without a host round trip per step;
-        returns (last dt, flow time advanced)"""
+    def update_euler(self, safety, n_steps, use_graph=True, n_cheby=1):
+        """n_steps of Solver::update's inviscid flow loop (max_dt + 2 stages with device ghost fills, Chebyshev factors cycling through
+        n_cheby) without a host round trip per step; returns (last dt, flow time advanced)"""
         dt, t = C.c_double(0.), C.c_double(0.)
-        self._check(self.lib.hexed_b200_update_euler(self.ctx, float(safety), int(n_steps), int(bool(use_graph)),
+        self._check(self.lib.hexed_b200_update_euler(self.ctx, float(safety), int(n_cheby), int(n_steps), int(bool(use_graph)),
                                                      C.cast(C.byref(dt), dp), C.cast(C.byref(t), dp)))
         return dt.value, t.value
 
-    def update_navier_stokes(self, safety_conv, safety_diff, visc, therm_cond, n_steps, use_graph=True):
+    def update_navier_stokes(self, safety, visc, therm_cond, n_steps, use_graph=True, n_cheby=1):
         """the viscous counterpart of update_euler (stage 0 compute_navier_stokes with device flux boundary conditions, stage 1 compute_euler)"""
         dt, t = C.c_double(0.), C.c_double(0.)
-        self._check(self.lib.hexed_b200_update_navier_stokes(self.ctx, float(safety_conv), float(safety_diff), visc, therm_cond, int(n_steps),
+        self._check(self.lib.hexed_b200_update_navier_stokes(self.ctx, float(safety), visc, therm_cond, int(n_cheby), int(n_steps),
                                                              int(bool(use_graph)), C.cast(C.byref(dt), dp), C.cast(C.byref(t), dp)))
         return dt.value, t.value
 

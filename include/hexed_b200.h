@@ -207,15 +207,16 @@ int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
  * (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341). The flux cache copy of :75-76 is host-side. */
 int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
 
-/* ---- the time loop of Solver::update (src/Solver.cpp:834-886, n_cheby_flow = 1) for the inviscid case with every boundary condition
- * registered on the device: n_steps x [max_dt_euler(safety, global time step) + 2 x (apply_state_bcs + compute_euler)] with the time step
- * kept on the device (no synchronisation per step); with use_graph the step is captured once in a CUDA graph and replayed. Bit-identical
- * to the same calls made one by one. Returns the last time step and the flow time advanced. For launch-bound (small) meshes. ---- */
-int hexed_b200_update_euler(hexed_b200_ctx* ctx, double safety_conv, int n_steps, int use_graph, double* last_dt, double* time_advanced);
-/* the same for the viscous case (use_ldg(), :857-865): max_dt_navier_stokes + ghost fill + compute_navier_stokes (stage 0, flux boundary
- * conditions on the device) + ghost fill + compute_euler (stage 1) */
-int hexed_b200_update_navier_stokes(hexed_b200_ctx* ctx, double safety_conv, double safety_diff, hexed_b200_transport visc,
-                                    hexed_b200_transport therm_cond, int n_steps, int use_graph, double* last_dt, double* time_advanced);
+/* ---- the flow loop of Solver::update (src/Solver.cpp:834-886) with every boundary condition registered on the device:
+ * n_steps x [nominal_dt = max_dt(safety/max_cheby, safety); dt = nominal_dt*chebyshev_step(n_cheby, i_cheby); 2 x (apply_state_bcs + stage)],
+ * i_cheby cycling through 0..n_cheby-1 (n_cheby = n_cheby_flow, default 1), with the time step kept on the device (no synchronisation per
+ * step); with use_graph one Chebyshev cycle is captured in a CUDA graph and replayed. Bit-identical to the same calls made one by one.
+ * Returns the last time step and the flow time advanced. For launch-bound (small) meshes.
+ * update_euler: both stages compute_euler. update_navier_stokes (use_ldg(), :857-865): stage 0 compute_navier_stokes with the flux
+ * boundary conditions on the device, stage 1 compute_euler. ---- */
+int hexed_b200_update_euler(hexed_b200_ctx* ctx, double safety, int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced);
+int hexed_b200_update_navier_stokes(hexed_b200_ctx* ctx, double safety, hexed_b200_transport visc, hexed_b200_transport therm_cond,
+                                    int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced);
 
 /* ---- thermodynamic admissibility: Solver::is_admissible (src/Solver.cpp:921-958, src/thermo.cpp:6-18), which
  * Solver::update runs after EVERY stage through fix_admissibility (:864-868). *admissible = 1 iff mass > 0 and energy > 0 at every

@@ -69,8 +69,8 @@ def main():
                 dev.apply_state_bcs(); dev.compute_navier_stokes(dev.apply_flux_bcs, visc, cond, dt=dt, i_stage=0)
                 dev.apply_state_bcs(); dev.compute_euler(dt=dt, i_stage=1)
         res = {"workload": "samples/cylinder class: %d x %d deformed quads, row size 6, Navier-Stokes, wall BCs" % (n, n), "elements": n*n, "steps": n_steps}
-        for name, fn in (("call_by_call", call_by_call_ns), ("device_dt", lambda k: dev.update_navier_stokes(0.1, 0.1, visc, cond, k, False)),
-                         ("device_dt_graph", lambda k: dev.update_navier_stokes(0.1, 0.1, visc, cond, k, True))):
+        for name, fn in (("call_by_call", call_by_call_ns), ("device_dt", lambda k: dev.update_navier_stokes(0.1, visc, cond, k, False)),
+                         ("device_dt_graph", lambda k: dev.update_navier_stokes(0.1, visc, cond, k, True))):
             fn(20); torch.cuda.synchronize()
             t = time.perf_counter(); fn(n_steps); dev.synchronize(); el = time.perf_counter() - t
             res[name + "_us_per_step"] = el/n_steps*1e6

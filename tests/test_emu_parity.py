@@ -238,3 +238,11 @@ def test_update_euler_refined_mesh(oracle, emu_lib):
 def test_update_navier_stokes_device_time_step(oracle, emu_lib, nd, rs, n):
     from util import check_update_navier_stokes
     check_update_navier_stokes(oracle, emu_lib, nd, rs, n, n_steps=3, use_graph=False)
+
+
+@pytest.mark.parametrize("n_cheby,n_steps", [(3, 8), (4, 9)])
+def test_update_loops_with_chebyshev_steps(oracle, emu_lib, n_cheby, n_steps):
+    """n_cheby_flow > 1 (the shock-capturing cases): Chebyshev factors cycle, one graph per cycle, a partial cycle at the end"""
+    from util import check_update_euler, check_update_navier_stokes
+    check_update_euler(oracle, emu_lib, 2, 4, 4, n_steps=n_steps, use_graph=False, deformed=True, n_cheby=n_cheby)
+    check_update_navier_stokes(oracle, emu_lib, 2, 4, 3, n_steps=n_steps, use_graph=False, n_cheby=n_cheby)

@@ -341,3 +341,11 @@ def test_update_navier_stokes_device_time_step(oracle, gpu_lib, nd, rs, n, use_g
     """the viscous loop with the time step on the device + CUDA graph replay: bit-identical to the call-by-call sequence"""
     from util import check_update_navier_stokes
     check_update_navier_stokes(oracle, gpu_lib, nd, rs, n, n_steps=12, use_graph=use_graph)
+
+
+@pytest.mark.parametrize("n_cheby,n_steps", [(3, 8), (4, 9)])
+def test_update_loops_with_chebyshev_steps(oracle, gpu_lib, n_cheby, n_steps):
+    """n_cheby_flow > 1 (the shock-capturing cases): Chebyshev factors cycle, one graph per cycle, a partial cycle at the end"""
+    from util import check_update_euler, check_update_navier_stokes
+    check_update_euler(oracle, gpu_lib, 2, 4, 4, n_steps=n_steps, use_graph=True, deformed=True, n_cheby=n_cheby)
+    check_update_navier_stokes(oracle, gpu_lib, 2, 4, 3, n_steps=n_steps, use_graph=True, n_cheby=n_cheby)

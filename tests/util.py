@@ -644,7 +644,11 @@ def check_fused_admissibility(oracle, lib, nd, rs, n):
     dev.close()
 
 
-def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=False, bc="riemann", refined=False):
+def _cheby(n, i):  # math::chebyshev_step, reference src/math.cpp:104-107
+    return 1/(1 - np.cos((n - i - .5)*np.pi/n))
+
+
+def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=False, bc="riemann", refined=False, n_cheby=1):
     """hexed_b200_update_euler (time step kept on the device, optional CUDA graph) is bit-identical to the same steps made call by call
     through the reference-shaped entry points, and both track the oracle"""
     basis = hb.gauss_legendre(rs)
@@ -665,14 +669,16 @@ def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=Fals
     a = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
     b = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
     t_a = 0.
-    for _ in range(n_steps):
-        dt = a.max_dt_euler(0.4, 0.4, False)
-        dt_o = oracle.max_dt(EULER, basis, ref, 0.4, 0.4, False)
+    max_cheby = _cheby(n_cheby, n_cheby - 1)
+    for i_step in range(n_steps):  # Solver::update, reference src/Solver.cpp:842-851
+        f = _cheby(n_cheby, i_step % n_cheby)
+        dt = a.max_dt_euler(0.4/max_cheby, 0.4, False)*f
+        dt_o = oracle.max_dt(EULER, basis, ref, 0.4/max_cheby, 0.4, False)*f
         for stage in (0, 1):
             a.apply_state_bcs(); a.compute_euler(dt=dt, i_stage=stage)
             oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage)
         t_a += dt
-    dt_b, t_b = b.update_euler(0.4, n_steps, use_graph)
+    dt_b, t_b = b.update_euler(0.4, n_steps, use_graph, n_cheby=n_cheby)
     out_a, out_b = m.copy(), m.copy()
     a.sync_to_host(out_a); b.sync_to_host(out_b)
     a.close(); b.close()
@@ -681,7 +687,7 @@ def check_update_euler(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=Fals
     assert rel_l2(out_b.state(), ref.state()) <= STATE_TOL
 
 
-def check_update_navier_stokes(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=True):
+def check_update_navier_stokes(oracle, lib, nd, rs, n, n_steps, use_graph, deformed=True, n_cheby=1):
     """hexed_b200_update_navier_stokes (time step on the device, optional CUDA graph) is bit-identical to the same viscous steps made
     call by call, and both track the oracle"""
     import pyoracle
@@ -696,15 +702,17 @@ def check_update_navier_stokes(oracle, lib, nd, rs, n, n_steps, use_graph, defor
     a = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
     b = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
     t_a = 0.
-    for _ in range(n_steps):
-        dt = a.max_dt_navier_stokes(0.3, 0.3, False, visc_d, cond_d)
-        dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3, 0.3, False, visc_o, cond_o)
+    max_cheby = _cheby(n_cheby, n_cheby - 1)
+    for i_step in range(n_steps):
+        f = _cheby(n_cheby, i_step % n_cheby)
+        dt = a.max_dt_navier_stokes(0.3/max_cheby, 0.3, False, visc_d, cond_d)*f
+        dt_o = oracle.max_dt(NAVIER_STOKES, basis, ref, 0.3/max_cheby, 0.3, False, visc_o, cond_o)*f
         a.apply_state_bcs(); a.compute_navier_stokes(a.apply_flux_bcs, visc_d, cond_d, dt=dt, i_stage=0)
         a.apply_state_bcs(); a.compute_euler(dt=dt, i_stage=1)
         oracle.apply_state_bcs(ref); oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0)
         oracle.apply_state_bcs(ref); oracle.compute_euler(basis, ref, dt=dt_o, i_stage=1)
         t_a += dt
-    dt_b, t_b = b.update_navier_stokes(0.3, 0.3, visc_d, cond_d, n_steps, use_graph)
+    dt_b, t_b = b.update_navier_stokes(0.3, visc_d, cond_d, n_steps, use_graph, n_cheby=n_cheby)
     out_a, out_b = m.copy(), m.copy()
     a.sync_to_host(out_a); b.sync_to_host(out_b)
     a.close(); b.close()
