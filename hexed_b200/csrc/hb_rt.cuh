@@ -38,6 +38,7 @@ __device__ __forceinline__ void mbar_wait(mbar_t* bar, unsigned parity)
   } while (!done);
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 /* orders earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes */
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 } // namespace hb

@@ -10,6 +10,12 @@
  * 3-D element. The point-per-thread kernel it replaces reached 47 % (Cartesian) / 62 % (deformed) of the measured HBM bandwidth
  * (profiles/r01g_bench_lines.jsonl): 144-thread CTAs with per-thread global loads between barriers.
  *
+ * Shared memory holds only what is reused: the state (double buffered, it is read in phases A, B and C), the numerical-flux faces and
+ * reference normals (single buffered: dead after phase A, so the copies of the NEXT batch are issued right after it) and R. The
+ * per-point late inputs (time-step scale, determinant, residual cache) are read once, straight from HBM after an L2 prefetch issued a
+ * phase earlier. 65 KB per CTA at row size 6 instead of 103 KB: three resident CTAs per SM instead of two (the kernel is latency-bound:
+ * 12 % occupancy, 27 % issue utilisation in profiles/r01l_ncu_full_2d.md).
+ *
  * Phases per batch: A (line tasks (element, dimension, line): pointwise flux on the line, derivative + lifted face flux -> R_d),
  * B (point tasks: r = R_0 + R_1, two-stage update, new state -> HBM and in place in shared memory),
  * C (line tasks: extrapolate the new state to both ends of the line -> HBM).
@@ -29,12 +35,11 @@ struct Pipe2Cfg
   static constexpr int cs = nv > RS ? nv : RS;            // slots per element of the residual cache array
   // per-element doubles of each staged array
   static constexpr int e_state = nv*nq, e_face = 2*ND*nv*nfq, e_nrml = DEF ? ND*ND*nq : 0;
-  static constexpr int st_state = 0, st_face = B*e_state, st_nrml = st_face + B*e_face;
-  static constexpr int stage_doubles = st_nrml + B*e_nrml;
-  static constexpr int lt_cache = 0, lt_tss = B*e_state, lt_det = lt_tss + B*nq;
-  static constexpr int late_doubles = lt_det + (DEF ? B*nq : 0);
+  static constexpr int state_doubles = B*e_state;                       // one of the two state buffers
+  static constexpr int fn_face = 0, fn_nrml = B*e_face, fn_doubles = B*(e_face + e_nrml); // faces | normals, single buffered
   static constexpr int r_doubles = B*ND*nv*nq;
-  static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
+  static constexpr int smem_doubles = 2*state_doubles + fn_doubles + r_doubles;
+  static constexpr int n_iter = (B*nq + threads - 1)/threads;           // point tasks per thread and batch
   static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 16*sizeof(int); // + per-element admissibility bits of the batch
 };
 
@@ -48,26 +53,34 @@ struct Pipe2Args
 };
 
 template <int RS, bool DEF>
-__device__ __forceinline__ void pipe2_issue_stage(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+__device__ __forceinline__ void pipe2_issue_state(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
 {
   using C = Pipe2Cfg<RS, DEF>;
-  const unsigned b_state = sizeof(double)*C::e_state*n, b_face = sizeof(double)*C::e_face*n, b_nrml = sizeof(double)*C::e_nrml*n;
-  mbar_arrive_expect_tx(bar, b_state + b_face + b_nrml);
-  bulk_g2s(buf + C::st_state, a.state + (size_t)e0*C::e_state, b_state, bar);
-  bulk_g2s(buf + C::st_face, a.faces + (size_t)e0*C::e_face, b_face, bar);
-  if constexpr (DEF) bulk_g2s(buf + C::st_nrml, a.refn + (size_t)(e0 - a.n_car)*C::e_nrml, b_nrml, bar);
+  const unsigned b_state = sizeof(double)*C::e_state*n;
+  mbar_arrive_expect_tx(bar, b_state);
+  bulk_g2s(buf, a.state + (size_t)e0*C::e_state, b_state, bar);
 }
 
 template <int RS, bool DEF>
-__device__ __forceinline__ void pipe2_issue_late(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+__device__ __forceinline__ void pipe2_issue_fn(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
 {
   using C = Pipe2Cfg<RS, DEF>;
-  const unsigned b_cache = sizeof(double)*C::e_state, b_pt = sizeof(double)*C::nq*n;
-  mbar_arrive_expect_tx(bar, (a.stage ? b_cache*n : 0u) + b_pt + (DEF ? b_pt : 0u));
-  // the residual cache array keeps max(nv, row_size) slots per element, of which Euler uses the first nv: one copy per element
-  if (a.stage) for (int i = 0; i < n; ++i) bulk_g2s(buf + C::lt_cache + i*C::e_state, a.cache + (size_t)(e0 + i)*C::cs*C::nq, b_cache, bar);
-  bulk_g2s(buf + C::lt_tss, a.tss + (size_t)e0*C::nq, b_pt, bar);
-  if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e0 - a.n_car)*C::nq, b_pt, bar);
+  const unsigned b_face = sizeof(double)*C::e_face*n, b_nrml = sizeof(double)*C::e_nrml*n;
+  mbar_arrive_expect_tx(bar, b_face + b_nrml);
+  bulk_g2s(buf + C::fn_face, a.faces + (size_t)e0*C::e_face, b_face, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::fn_nrml, a.refn + (size_t)(e0 - a.n_car)*C::e_nrml, b_nrml, bar);
+}
+
+/* the late inputs of batch e0 towards L2: one 128-byte line per call */
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe2_prefetch_late(const Pipe2Args& a, int e0, int n, int t, int n_threads)
+{
+  using C = Pipe2Cfg<RS, DEF>;
+  for (int i = t*16; i < n*C::nq; i += n_threads*16) {
+    prefetch_l2(a.tss + (size_t)e0*C::nq + i);
+    if constexpr (DEF) prefetch_l2(a.det + (size_t)(e0 - a.n_car)*C::nq + i);
+  }
+  if (a.stage) for (int i = t*16; i < n*C::cs*C::nq; i += n_threads*16) prefetch_l2(a.cache + (size_t)e0*C::cs*C::nq + i);
 }
 
 template <int RS, bool DEF>
@@ -77,9 +90,9 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
   using C = Pipe2Cfg<RS, DEF>;
   constexpr int ND = 2, nq = C::nq, nfq = C::nfq, nv = C::nv, B = C::B;
   HB_DYN_SMEM(double, smem);
-  double* late = smem + 2*C::stage_doubles;
-  double* R = late + C::late_doubles;
-  mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
+  double* FN = smem + 2*C::state_doubles;
+  double* R = FN + C::fn_doubles;
+  mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: state buffers; [2]: faces + normals
   int* s_bad = reinterpret_cast<int*>(bars + 4); // [B] admissibility bits of the batch's elements
   static_assert(B <= 16, "s_bad holds 16 entries");
   const int t = threadIdx.x;
@@ -94,10 +107,11 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
   }
   __syncthreads();
   if (t == 0) {
-    pipe2_issue_stage<RS, DEF>(a, e0, count(e0), smem, &bars[0]);
-    if (e0 + stride_e < a.elem_end) pipe2_issue_stage<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), smem + C::stage_doubles, &bars[1]);
-    pipe2_issue_late<RS, DEF>(a, e0, count(e0), late, &bars[2]);
+    pipe2_issue_state<RS, DEF>(a, e0, count(e0), smem, &bars[0]);
+    pipe2_issue_fn<RS, DEF>(a, e0, count(e0), FN, &bars[2]);
+    if (e0 + stride_e < a.elem_end) pipe2_issue_state<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), smem + C::state_doubles, &bars[1]);
   }
+  pipe2_prefetch_late<RS, DEF>(a, e0, count(e0), t, C::threads);
 
   // line task of this thread: element le of the batch, dimension d, line l; points q0 + k*stride
   const int le = t/C::lines_per_elem, d = (t % C::lines_per_elem)/nfq, l = t % nfq;
@@ -109,11 +123,11 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     const unsigned par = (it >> 1) & 1;
     const int n = count(e0);
     const bool has_line = t < C::n_line && le < n;
-    double* const stage_buf = smem + s*C::stage_doubles;
-    double* S = stage_buf + C::st_state;
-    const double* F = stage_buf + C::st_face;
-    const double* N = stage_buf + C::st_nrml;
+    double* S = smem + s*C::state_doubles;
+    const double* F = FN + C::fn_face;
+    const double* N = FN + C::fn_nrml;
     mbar_wait(&bars[s], par);
+    mbar_wait(&bars[2], it & 1);
     if (a.record && t < B) s_bad[t] = 0; // ordered before the first atomicOr by the barrier after phase A
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
@@ -159,42 +173,68 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
         }
       }
     }
-    __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
+    __syncthreads(); // R complete; the faces / normals buffer is dead, the state is still needed
+    if (t == 0 && e0 + stride_e < a.elem_end) {
+      fence_proxy_async();
+      pipe2_issue_fn<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), FN, &bars[2]);
+    }
+    if (e0 + stride_e < a.elem_end) pipe2_prefetch_late<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), t, C::threads);
 
     /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
-    mbar_wait(&bars[2], it & 1);
-    const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
-    for (int pt = t; pt < n*nq; pt += C::threads) {
-      const int pe = pt/nq, q = pt % nq;
-      const int e = e0 + pe;
-      double mult; // update*tss/nom/det with one division (<= 1 ulp)
-      if constexpr (DEF) mult = update*late[C::lt_tss + pt]/(a.nom[e]*late[C::lt_det + pt]);
-      else mult = update*late[C::lt_tss + pt]/a.nom[e];
+    {
+      const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
+      // every late input of this thread's points is loaded before its first store (a store could alias a later load and would chain
+      // the memory round trips)
+      double l_tss[C::n_iter], l_cache[C::n_iter][nv];
+      [[maybe_unused]] double l_det[C::n_iter];
+      double l_nom[C::n_iter];
       #pragma unroll
-      for (int v = 0; v < nv; ++v) {
-        double u = R[pe*ND*nv*nq + (0*nv + v)*nq + q];
-        u += R[pe*ND*nv*nq + (1*nv + v)*nq + q];
-        double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
-        if (a.stage) u -= late[C::lt_cache + pe*C::e_state + v*nq + q];
-        else if (!a.compute_residual) *cache = u;
-        u *= mult;
-        if (a.compute_residual) *cache = u;
-        else {
-          const double xv = S[pe*C::e_state + v*nq + q] + u;
-          S[pe*C::e_state + v*nq + q] = xv;
-          a.state[(size_t)e*C::e_state + v*nq + q] = xv;
-          if (a.record) {
-            const int bad = (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
-            if (bad) atomicOr(&s_bad[pe], bad);
+      for (int k = 0; k < C::n_iter; ++k) {
+        const int pt = t + k*C::threads;
+        if (pt < n*nq) {
+          const int pe = pt/nq, q = pt % nq;
+          const int e = e0 + pe;
+          l_tss[k] = a.tss[(size_t)e*nq + q];
+          l_nom[k] = a.nom[e];
+          if constexpr (DEF) l_det[k] = a.det[(size_t)(e - a.n_car)*nq + q];
+          if (a.stage) {
+            #pragma unroll
+            for (int v = 0; v < nv; ++v) l_cache[k][v] = a.cache[((size_t)e*C::cs + v)*nq + q];
+          }
+        }
+      }
+      #pragma unroll
+      for (int k = 0; k < C::n_iter; ++k) {
+        const int pt = t + k*C::threads;
+        if (pt < n*nq) {
+          const int pe = pt/nq, q = pt % nq;
+          const int e = e0 + pe;
+          double mult; // update*tss/nom/det with one division (<= 1 ulp)
+          if constexpr (DEF) mult = update*l_tss[k]/(l_nom[k]*l_det[k]);
+          else mult = update*l_tss[k]/l_nom[k];
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) {
+            double u = R[pe*ND*nv*nq + (0*nv + v)*nq + q];
+            u += R[pe*ND*nv*nq + (1*nv + v)*nq + q];
+            double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+            if (a.stage) u -= l_cache[k][v];
+            else if (!a.compute_residual) *cache = u;
+            u *= mult;
+            if (a.compute_residual) *cache = u;
+            else {
+              const double xv = S[pe*C::e_state + v*nq + q] + u;
+              S[pe*C::e_state + v*nq + q] = xv;
+              a.state[(size_t)e*C::e_state + v*nq + q] = xv;
+              if (a.record) {
+                const int bad = (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
+                if (bad) atomicOr(&s_bad[pe], bad);
+              }
+            }
           }
         }
       }
     }
-    __syncthreads(); // new state complete in S; late buffer free
-    if (t == 0 && e0 + stride_e < a.elem_end) {
-      fence_proxy_async();
-      pipe2_issue_late<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), late, &bars[2]);
-    }
+    __syncthreads(); // new state complete in S
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
     if (has_line) {
@@ -221,7 +261,7 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     if (a.record && t < n) a.record[e0 + t] = s_bad[t];
     if (t == 0 && e0 + 2*stride_e < a.elem_end) {
       fence_proxy_async();
-      pipe2_issue_stage<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), stage_buf, &bars[s]);
+      pipe2_issue_state<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), S, &bars[s]);
     }
   }
 }

@@ -124,7 +124,7 @@ inline unsigned atomicInc(unsigned* p, unsigned lim) { std::lock_guard<std::mute
 template <class T> T __ldg(const T* p) { return *p; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
-namespace hb { inline void prefetch_l1(const void*) {} }
+namespace hb { inline void prefetch_l1(const void*) {} inline void prefetch_l2(const void*) {} }
 inline float rsqrtf(float x) { return 1.f/std::sqrt(x); }
 inline float __fdividef(float a, float b) { return a/b; }
 inline int __float_as_int(float f) { int r; std::memcpy(&r, &f, 4); return r; }
