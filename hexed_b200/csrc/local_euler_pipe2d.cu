@@ -80,7 +80,10 @@ __device__ __forceinline__ void pipe2_prefetch_late(const Pipe2Args& a, int e0, 
     prefetch_l2(a.tss + (size_t)e0*C::nq + i);
     if constexpr (DEF) prefetch_l2(a.det + (size_t)(e0 - a.n_car)*C::nq + i);
   }
-  if (a.stage) for (int i = t*16; i < n*C::cs*C::nq; i += n_threads*16) prefetch_l2(a.cache + (size_t)e0*C::cs*C::nq + i);
+  if (a.stage) { // the cache array keeps max(nv, row_size) slots per element; only the first nv are read
+    constexpr int lines = (C::e_state + 15)/16;
+    for (int i = t; i < n*lines; i += n_threads) prefetch_l2(a.cache + ((size_t)(e0 + i/lines)*C::cs)*C::nq + (i % lines)*16);
+  }
 }
 
 template <int RS, bool DEF>
