@@ -16,6 +16,12 @@
  * phase earlier. 65 KB per CTA at row size 6 instead of 103 KB: three resident CTAs per SM instead of two (the kernel is latency-bound:
  * 12 % occupancy, 27 % issue utilisation in profiles/r01l_ncu_full_2d.md).
  *
+ * Shared-memory banks (profiles/r01o_ncu_full_2d.md: with three CTAs resident the kernel became LSU-bound, l1tex 88 % busy, 56 % of the
+ * shared wavefronts bank conflicts): the per-element strides of every staged array are padded by row_size doubles (so a batch is
+ * fetched with one bulk copy per element and array instead of one per array), warps are homogeneous in the line direction, the lines
+ * that are contiguous in memory (dimension 1) are moved with 128-bit accesses, and the two directions enumerate their tasks
+ * differently (dimension 0 element-major, dimension 1 line-major) so that a half / quarter warp touches distinct banks.
+ *
  * Phases per batch: A (line tasks (element, dimension, line): pointwise flux on the line, derivative + lifted face flux -> R_d),
  * B (point tasks: r = R_0 + R_1, two-stage update, new state -> HBM and in place in shared memory),
  * C (line tasks: extrapolate the new state to both ends of the line -> HBM).
@@ -35,9 +41,14 @@ struct Pipe2Cfg
   static constexpr int cs = nv > RS ? nv : RS;            // slots per element of the residual cache array
   // per-element doubles of each staged array
   static constexpr int e_state = nv*nq, e_face = 2*ND*nv*nfq, e_nrml = DEF ? ND*ND*nq : 0;
-  static constexpr int state_doubles = B*e_state;                       // one of the two state buffers
-  static constexpr int fn_face = 0, fn_nrml = B*e_face, fn_doubles = B*(e_face + e_nrml); // faces | normals, single buffered
-  static constexpr int r_doubles = B*ND*nv*nq;
+  // per-element strides in shared memory: padded by row_size doubles (16-byte multiples are kept: row_size is even)
+  static constexpr int pad = RS;
+  static constexpr int p_state = e_state + pad, p_face = e_face + pad, p_nrml = DEF ? e_nrml + pad : 0, p_r = ND*nv*nq + pad;
+  static constexpr int half = threads/2;                                // threads [0, half): lines in dimension 0, [half, threads): dimension 1
+  static_assert(RS % 2 == 0 && B*nfq <= half && B <= 32, "task layout");
+  static constexpr int state_doubles = B*p_state;                       // one of the two state buffers
+  static constexpr int fn_face = 0, fn_nrml = B*p_face, fn_doubles = B*(p_face + p_nrml); // faces | normals, single buffered
+  static constexpr int r_doubles = B*p_r;
   static constexpr int smem_doubles = 2*state_doubles + fn_doubles + r_doubles;
   static constexpr int n_iter = (B*nq + threads - 1)/threads;           // point tasks per thread and batch
   static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 16*sizeof(int); // + per-element admissibility bits of the batch
@@ -52,23 +63,28 @@ struct Pipe2Args
   int* record; // non-null: admissibility bits of the new state and faces per element (see local_euler_pipe.cu)
 };
 
+/* both issue functions are called by every lane of warp 0: lane 0 posts the byte count, lane i < n copies element i of the batch */
 template <int RS, bool DEF>
-__device__ __forceinline__ void pipe2_issue_state(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+__device__ __forceinline__ void pipe2_issue_state(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar, int lane)
 {
   using C = Pipe2Cfg<RS, DEF>;
-  const unsigned b_state = sizeof(double)*C::e_state*n;
-  mbar_arrive_expect_tx(bar, b_state);
-  bulk_g2s(buf, a.state + (size_t)e0*C::e_state, b_state, bar);
+  constexpr unsigned b_state = sizeof(double)*C::e_state;
+  if (lane == 0) mbar_arrive_expect_tx(bar, b_state*n);
+  __syncwarp();
+  if (lane < n) bulk_g2s(buf + lane*C::p_state, a.state + (size_t)(e0 + lane)*C::e_state, b_state, bar);
 }
 
 template <int RS, bool DEF>
-__device__ __forceinline__ void pipe2_issue_fn(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar)
+__device__ __forceinline__ void pipe2_issue_fn(const Pipe2Args& a, int e0, int n, double* buf, mbar_t* bar, int lane)
 {
   using C = Pipe2Cfg<RS, DEF>;
-  const unsigned b_face = sizeof(double)*C::e_face*n, b_nrml = sizeof(double)*C::e_nrml*n;
-  mbar_arrive_expect_tx(bar, b_face + b_nrml);
-  bulk_g2s(buf + C::fn_face, a.faces + (size_t)e0*C::e_face, b_face, bar);
-  if constexpr (DEF) bulk_g2s(buf + C::fn_nrml, a.refn + (size_t)(e0 - a.n_car)*C::e_nrml, b_nrml, bar);
+  constexpr unsigned b_face = sizeof(double)*C::e_face, b_nrml = sizeof(double)*C::e_nrml;
+  if (lane == 0) mbar_arrive_expect_tx(bar, (b_face + b_nrml)*n);
+  __syncwarp();
+  if (lane < n) {
+    bulk_g2s(buf + C::fn_face + lane*C::p_face, a.faces + (size_t)(e0 + lane)*C::e_face, b_face, bar);
+    if constexpr (DEF) bulk_g2s(buf + C::fn_nrml + lane*C::p_nrml, a.refn + (size_t)(e0 + lane - a.n_car)*C::e_nrml, b_nrml, bar);
+  }
 }
 
 /* the late inputs of batch e0 towards L2: one 128-byte line per call */
@@ -109,23 +125,34 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     mbar_init_fence();
   }
   __syncthreads();
-  if (t == 0) {
-    pipe2_issue_state<RS, DEF>(a, e0, count(e0), smem, &bars[0]);
-    pipe2_issue_fn<RS, DEF>(a, e0, count(e0), FN, &bars[2]);
-    if (e0 + stride_e < a.elem_end) pipe2_issue_state<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), smem + C::state_doubles, &bars[1]);
+  if (t < 32) {
+    pipe2_issue_state<RS, DEF>(a, e0, count(e0), smem, &bars[0], t);
+    pipe2_issue_fn<RS, DEF>(a, e0, count(e0), FN, &bars[2], t);
+    if (e0 + stride_e < a.elem_end) pipe2_issue_state<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), smem + C::state_doubles, &bars[1], t);
   }
   pipe2_prefetch_late<RS, DEF>(a, e0, count(e0), t, C::threads);
 
-  // line task of this thread: element le of the batch, dimension d, line l; points q0 + k*stride
-  const int le = t/C::lines_per_elem, d = (t % C::lines_per_elem)/nfq, l = t % nfq;
-  const int stride = d == 0 ? RS : 1;
+  // line task of this thread: element le of the batch, dimension d (uniform per warp), line l; points q0 + k*(d == 0 ? row_size : 1).
+  // dimension 0 enumerates element-major (consecutive threads: consecutive doubles), dimension 1 line-major (consecutive threads:
+  // the same line of consecutive elements, 16-byte chunks 3*(le + l) mod 8 apart at row size 6)
+  const int d = t >= C::half, ti = t - d*C::half;
+  const int le = d == 0 ? ti/nfq : ti % B, l = d == 0 ? ti % nfq : ti/B;
   const int q0 = d == 0 ? l : l*RS;
+  // points k, k + 1 (k even) of this thread's line in the field starting at `field`
+  auto load_pair = [&](const double* field, int k, double& x, double& y) {
+    if (d == 0) { x = field[q0 + k*RS]; y = field[q0 + (k + 1)*RS]; }
+    else ld2(field + q0 + k, x, y);
+  };
+  auto store_pair = [&](double* field, int k, double x, double y) {
+    if (d == 0) { field[q0 + k*RS] = x; field[q0 + (k + 1)*RS] = y; }
+    else st2(field + q0 + k, x, y);
+  };
 
   for (int it = 0; e0 < a.elem_end; ++it, e0 += stride_e) {
     const int s = it & 1;
     const unsigned par = (it >> 1) & 1;
     const int n = count(e0);
-    const bool has_line = t < C::n_line && le < n;
+    const bool has_line = ti < B*nfq && le < n;
     double* S = smem + s*C::state_doubles;
     const double* F = FN + C::fn_face;
     const double* N = FN + C::fn_nrml;
@@ -135,36 +162,41 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
     if (has_line) {
-      const double* Se = S + le*C::e_state;
+      const double* Se = S + le*C::p_state;
       double f[nv][RS];
       #pragma unroll
-      for (int k = 0; k < RS; ++k) {
-        EulerPoint<ND> p;
+      for (int k = 0; k < RS; k += 2) {
+        EulerPoint<ND> p[2];
         #pragma unroll
-        for (int v = 0; v < nv; ++v) p.s[v] = Se[v*nq + q0 + k*stride];
-        p.scalars();
-        double fl[nv];
+        for (int v = 0; v < nv; ++v) load_pair(Se + v*nq, k, p[0].s[v], p[1].s[v]);
+        [[maybe_unused]] double nr[2][ND];
         if constexpr (DEF) {
-          double nr[ND];
           #pragma unroll
-          for (int j = 0; j < ND; ++j) nr[j] = N[le*C::e_nrml + (d*ND + j)*nq + q0 + k*stride];
-          p.flux(nr, fl);
-        } else {
-          const double mass_flux = d == 0 ? p.s[0] : p.s[1];
-          const double vol_flux = mass_flux*p.inv_mass;
-          fl[ND] = mass_flux;
-          fl[ND + 1] = (p.s[ND + 1] + p.pressure)*vol_flux;
-          #pragma unroll
-          for (int j = 0; j < ND; ++j) fl[j] = p.s[j]*vol_flux + (j == d ? p.pressure : 0.);
+          for (int j = 0; j < ND; ++j) load_pair(N + le*C::p_nrml + (d*ND + j)*nq, k, nr[0][j], nr[1][j]);
         }
         #pragma unroll
-        for (int v = 0; v < nv; ++v) f[v][k] = fl[v];
+        for (int h = 0; h < 2; ++h) {
+          p[h].scalars();
+          double fl[nv];
+          if constexpr (DEF) p[h].flux(nr[h], fl);
+          else {
+            const double mass_flux = d == 0 ? p[h].s[0] : p[h].s[1];
+            const double vol_flux = mass_flux*p[h].inv_mass;
+            fl[ND] = mass_flux;
+            fl[ND + 1] = (p[h].s[ND + 1] + p[h].pressure)*vol_flux;
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) fl[j] = p[h].s[j]*vol_flux + (j == d ? p[h].pressure : 0.);
+          }
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) f[v][k + h] = fl[v];
+        }
       }
-      const double* Fe = F + le*C::e_face;
-      double* Re = R + le*ND*nv*nq;
+      const double* Fe = F + le*C::p_face;
+      double* Re = R + le*C::p_r;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         const double b0 = Fe[((2*d)*nv + v)*nfq + l], b1 = Fe[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
         #pragma unroll
         for (int i = 0; i < RS; ++i) {
           double acc = 0;
@@ -172,14 +204,16 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
           for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
           acc += ops.lift[i][0]*b0;
           acc += ops.lift[i][1]*b1;
-          Re[(d*nv + v)*nq + q0 + i*stride] = -acc;
+          r[i] = -acc;
         }
+        #pragma unroll
+        for (int i = 0; i < RS; i += 2) store_pair(Re + (d*nv + v)*nq, i, r[i], r[i + 1]);
       }
     }
     __syncthreads(); // R complete; the faces / normals buffer is dead, the state is still needed
-    if (t == 0 && e0 + stride_e < a.elem_end) {
+    if (t < 32 && e0 + stride_e < a.elem_end) {
       fence_proxy_async();
-      pipe2_issue_fn<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), FN, &bars[2]);
+      pipe2_issue_fn<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), FN, &bars[2], t);
     }
     if (e0 + stride_e < a.elem_end) pipe2_prefetch_late<RS, DEF>(a, e0 + stride_e, count(e0 + stride_e), t, C::threads);
 
@@ -217,16 +251,16 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
           else mult = update*l_tss[k]/l_nom[k];
           #pragma unroll
           for (int v = 0; v < nv; ++v) {
-            double u = R[pe*ND*nv*nq + (0*nv + v)*nq + q];
-            u += R[pe*ND*nv*nq + (1*nv + v)*nq + q];
+            double u = R[pe*C::p_r + (0*nv + v)*nq + q];
+            u += R[pe*C::p_r + (1*nv + v)*nq + q];
             double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
             if (a.stage) u -= l_cache[k][v];
             else if (!a.compute_residual) *cache = u;
             u *= mult;
             if (a.compute_residual) *cache = u;
             else {
-              const double xv = S[pe*C::e_state + v*nq + q] + u;
-              S[pe*C::e_state + v*nq + q] = xv;
+              const double xv = S[pe*C::p_state + v*nq + q] + u;
+              S[pe*C::p_state + v*nq + q] = xv;
               a.state[(size_t)e*C::e_state + v*nq + q] = xv;
               if (a.record) {
                 const int bad = (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
@@ -241,16 +275,18 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
     if (has_line) {
-      const double* Se = S + le*C::e_state;
+      const double* Se = S + le*C::p_state;
       double* fout = a.faces + (size_t)(e0 + le)*C::e_face;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
+        double x[RS];
+        #pragma unroll
+        for (int k = 0; k < RS; k += 2) load_pair(Se + v*nq, k, x[k], x[k + 1]);
         double x0 = 0, x1 = 0;
         #pragma unroll
         for (int k = 0; k < RS; ++k) {
-          const double x = Se[v*nq + q0 + k*stride];
-          x0 += ops.bnd[0][k]*x;
-          x1 += ops.bnd[1][k]*x;
+          x0 += ops.bnd[0][k]*x[k];
+          x1 += ops.bnd[1][k]*x[k];
         }
         fout[((2*d)*nv + v)*nfq + l] = x0;
         fout[((2*d + 1)*nv + v)*nfq + l] = x1;
@@ -262,9 +298,9 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     }
     __syncthreads(); // stage buffer s free
     if (a.record && t < n) a.record[e0 + t] = s_bad[t];
-    if (t == 0 && e0 + 2*stride_e < a.elem_end) {
+    if (t < 32 && e0 + 2*stride_e < a.elem_end) {
       fence_proxy_async();
-      pipe2_issue_state<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), S, &bars[s]);
+      pipe2_issue_state<RS, DEF>(a, e0 + 2*stride_e, count(e0 + 2*stride_e), S, &bars[s], t);
     }
   }
 }
