@@ -54,6 +54,16 @@ struct EulerPoint
     for (int i = 0; i < ND; ++i) sq += s[i]*s[i];
     return sound + sqrt(sq)*inv_mass;
   }
+  /* c_spacing/char_speed() (the local time step of Max_dt, reference include/Spatial.hpp:808-822) multiplied through by the density:
+   * one division and no reciprocal of the mass (FP64 division is ~30 instructions and max_dt_euler_kernel is FP64-issue-bound);
+   * differs from the two-division form by a few ulp, 3 orders inside the 1e-13 bar. Does not need scalars(). */
+  __device__ __forceinline__ double cfl_time_step(double c_spacing) const
+  {
+    double sq = 0;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) sq += s[i]*s[i];
+    return c_spacing*s[ND]/(sqrt(heat_rat*(heat_rat - 1)*s[ND + 1]*s[ND]) + sqrt(sq));
+  }
 };
 
 /* n-linear interpolation of the vertex time-step scale to quadrature point q (reference include/math.hpp:207-218 as used by

@@ -28,7 +28,7 @@ struct GArgs
   int elem_begin, elem_end, n_car;
   double update; int stage, compute_residual, use_filter;
   const double* dt_dev; // non-null: the time step lives on the device (hexed_b200_update_*) and multiplies `update`
-  double max_cfl_c, max_cfl_d, inv_max_cfl_c, inv_max_cfl_d; int is_local; unsigned long long* global_min;
+  double max_cfl_c, max_cfl_d, inv_max_cfl_c, inv_max_cfl_d; int is_local; unsigned long long* global_min; int write_tss = 1; // max_dt, global stepping: 0 = time_step_scale already holds 1 everywhere
   PdeParams pp;
 };
 
@@ -1299,7 +1299,7 @@ g_max_dt_kernel(GArgs a, Ops ops)
     if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed*a.inv_max_cfl_c*inv_spacing; }
     if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity*a.inv_max_cfl_d*inv_spacing*inv_spacing; }
     if (a.is_local) a.ed.tss[(size_t)e*nq + q] = 1./scale;
-    else { a.ed.tss[(size_t)e*nq + q] = 1.; val = 1./scale; }
+    else { if (a.write_tss) a.ed.tss[(size_t)e*nq + q] = 1.; val = 1./scale; }
   }
   if (a.is_local) return;
   #pragma unroll
@@ -1464,6 +1464,7 @@ int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double 
   a.max_cfl_d = -2/c->min_eig_diff*safety_diff;                   // Spatial.hpp:778
     a.inv_max_cfl_c = 1./a.max_cfl_c; a.inv_max_cfl_d = 1./a.max_cfl_d;
   a.is_local = local_time;
+  a.write_tss = !c->tss_is_one;
   return dispatch(c, [&](auto nd, auto rs) {
     constexpr int ND = decltype(nd)::value, RS = decltype(rs)::value;
     using P = Pde<ND, RS>;

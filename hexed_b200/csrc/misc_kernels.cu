@@ -12,6 +12,7 @@ namespace hb {
 struct MaxDtArgs
 {
   const double* state; double* tss; const double* vtss; int n_elem; double max_cfl_c; int is_local; unsigned long long* global_min;
+  int write_tss; // global time stepping: 0 = time_step_scale already holds 1 everywhere (ctx::tss_is_one), skip the 8 bytes per point
 };
 
 constexpr int max_dt_ppt = 1; // points per thread. Measured with 2 (both points' loads in flight before either is used; 70 registers, 3 CTAs
@@ -48,11 +49,10 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
       EulerPoint<ND> p;
       #pragma unroll
       for (int v = 0; v < nv; ++v) p.s[v] = st[r][v];
-      p.inv_mass = 1./p.s[ND];
       // 1/scale with scale = char_speed/max_cfl/spacing (Spatial.hpp:808-822), rearranged to a single division
-      const double local_dt = a.max_cfl_c*spacing/p.char_speed();
+      const double local_dt = p.cfl_time_step(a.max_cfl_c*spacing);
       if (a.is_local) a.tss[(size_t)elem[r]*nq + pt[r]] = local_dt;
-      else { a.tss[(size_t)elem[r]*nq + pt[r]] = 1.; val = fmin(val, local_dt); }
+      else { if (a.write_tss) a.tss[(size_t)elem[r]*nq + pt[r]] = 1.; val = fmin(val, local_dt); }
     }
   }
   if (a.is_local) return;
@@ -110,8 +110,7 @@ cfl_exact_kernel(MaxDtArgs a, Ops ops, const float* approx, const int* screen_mi
       EulerPoint<ND> p;
       #pragma unroll
       for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)e*nv + v)*nq + q];
-      p.inv_mass = 1./p.s[ND];
-      val = fmin(val, a.max_cfl_c*spacing/p.char_speed());
+      val = fmin(val, p.cfl_time_step(a.max_cfl_c*spacing));
     }
   }
   #pragma unroll
@@ -176,6 +175,7 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
     a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv; // Basis::max_cfl (src/Basis.cpp:6-9) * safety (Spatial.hpp:777)
     a.is_local = local_time; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
+    a.write_tss = !c->tss_is_one;
     if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream)); // 0x7f7f... = 1.4e306
     { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
@@ -203,6 +203,7 @@ int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_
     a.state = c->state; a.tss = c->tss; a.vtss = c->vtss; a.n_elem = c->n_elem;
     a.max_cfl_c = (-2*c->quad_safety/c->min_eig_conv)*safety_conv;
     a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(d_dt);
+    a.write_tss = !c->tss_is_one;
     HB_CUDA(c, cudaMemsetAsync(d_dt, 0x7f, sizeof(double), c->stream));
     if (grid) { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); count_launch(c, ST_MAX_DT_CAR); }
     HB_CUDA(c, cudaGetLastError());

@@ -223,6 +223,12 @@ def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
     check_fused_admissibility(oracle, emu_lib, nd, rs, n)
 
 
+@pytest.mark.parametrize("nd,rs,pde", [(2, 4, "euler"), (3, 3, "euler"), (2, 4, "navier_stokes")])
+def test_time_step_scale_write_skipped_only_when_known_one(oracle, emu_lib, nd, rs, pde):
+    from util import check_tss_write_skipped
+    check_tss_write_skipped(oracle, emu_lib, nd, rs, pde)
+
+
 @pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 4, False), (2, 3, 3, True), (3, 4, 2, True)])
 def test_update_euler_device_time_step(oracle, emu_lib, nd, rs, n, deformed):
     from util import check_update_euler

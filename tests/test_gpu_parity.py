@@ -320,6 +320,13 @@ def test_fused_admissibility(oracle, gpu_lib, nd, rs, n):
     check_fused_admissibility(oracle, gpu_lib, nd, rs, n)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("nd,rs,pde", [(2, 4, "euler"), (3, 3, "euler"), (2, 4, "navier_stokes")])
+def test_time_step_scale_write_skipped_only_when_known_one(oracle, gpu_lib, nd, rs, pde):
+    from util import check_tss_write_skipped
+    check_tss_write_skipped(oracle, gpu_lib, nd, rs, pde)
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 @pytest.mark.parametrize("nd,rs,n,deformed", [(2, 6, 16, False), (2, 6, 24, True), (3, 6, 6, True), (3, 5, 4, False)])
 def test_update_euler_device_time_step(oracle, gpu_lib, nd, rs, n, deformed, use_graph):

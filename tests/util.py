@@ -174,6 +174,40 @@ def check_cfl_cache(oracle, lib, rs, n):
     dev.close()
 
 
+def check_tss_write_skipped(oracle, lib, nd=2, rs=4, pde="euler"):
+    """global time stepping writes time_step_scale = 1 (reference Spatial.hpp:823-825); the device skips those 8 bytes per point when the
+    array is known to hold 1 already. Every way the array can change (local time stepping, a host upload of its slot) must bring the
+    write back."""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 5, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    nv = nd + 2
+    if pde == "euler":
+        max_dt = lambda local: dev.max_dt_euler(0.7, 0.7, local)
+        want = oracle.max_dt(EULER, basis, m, 0.7, 0.7, False)
+    else:
+        max_dt = lambda local: dev.max_dt_navier_stokes(0.7, 0.7, local, K.constant_transport(1e-3), K.constant_transport(2e-3))
+        want = oracle.max_dt(NAVIER_STOKES, basis, m, 0.7, 0.7, False, pyoracle.constant(1e-3), pyoracle.constant(2e-3))
+    ones = np.ones_like(m.tss())
+    def tss():
+        out = m.copy(); dev.sync_to_host(out); return out.tss()
+    for rep in range(3):                                     # first call writes, the others skip
+        assert abs(max_dt(False)/want - 1) <= MAX_DT_TOL
+        assert np.array_equal(tss(), ones)
+    junk = np.full((m.n_elem, 1) + m.tss().shape[1:], 7.)
+    dev.upload_elements(np.ascontiguousarray(junk), nv, 1)   # a host write to the time-step-scale slot
+    assert np.array_equal(tss(), junk[:, 0])
+    assert abs(max_dt(False)/want - 1) <= MAX_DT_TOL
+    assert np.array_equal(tss(), ones)
+    max_dt(True)                                             # local time stepping
+    assert not np.array_equal(tss(), ones)
+    assert abs(max_dt(False)/want - 1) <= MAX_DT_TOL
+    assert np.array_equal(tss(), ones)
+    dev.close()
+
+
 def mixed_bcs(mesh, rng):
     """replace the soup mesh's single boundary condition by one of every device-side kind over disjoint subsets of its faces"""
     src = mesh.bcs[0]
