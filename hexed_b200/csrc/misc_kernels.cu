@@ -68,6 +68,58 @@ max_dt_euler_kernel(MaxDtArgs a, Ops ops)
   }
 }
 
+/* Global time stepping with a RUNNING single-precision screen (no barrier, bit-identical result). max_dt_euler_kernel issues ~257
+ * instructions per point (two FP64 square roots and a division) and is issue-bound at 3.9 TB/s (profiles/r01q_ncu_full_maxdt.md), yet
+ * only the point that holds the minimum matters. Here every point evaluates the time step in single precision (good to ~1e-6),
+ * a warp takes the minimum with shuffles and lane 0 folds it into a device-wide running minimum (read through L1: a stale value only
+ * makes the screen less sharp; the atomic is issued only when it lowers the value). Points within 2e-5 of min(running, warp) -- and
+ * points whose screen value is not a positive finite float -- are evaluated with the exact FP64 arithmetic and folded into the result
+ * with atomicMin (again guarded by a cached read). The point holding the true minimum always passes the screen (its screen value is
+ * within 2e-6 of the smallest screen value there will ever be), so the result is the same double as the full reduction's.
+ * A uniform flow degenerates to screen + exact for every point (~1.2x the plain kernel). */
+constexpr bool max_dt_running_screen = true;
+
+template <int ND, int RS>
+__global__ void __launch_bounds__(256)
+max_dt_euler_screen_kernel(MaxDtArgs a, Ops ops, int* screen_bits)
+{
+  constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND);
+  const long long gid = (long long)blockIdx.x*256 + threadIdx.x;
+  const int elem = (int)(gid/nq), pt = (int)(gid % nq);
+  const bool valid = elem < a.n_elem;
+  EulerPoint<ND> p;
+  double c_spacing = 0;
+  float ap = 3.0e38f; // screen value; 0 = not representable, evaluate exactly
+  if (valid) {
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)elem*nv + v)*nq + pt];
+    c_spacing = a.max_cfl_c*interp_vertex_spacing<ND, RS>(a.vtss + (size_t)elem*n_vert, ops, pt);
+    if (a.write_tss) a.tss[(size_t)elem*nq + pt] = 1.; // Spatial.hpp:823-825
+    const float rho = (float)p.s[ND], en = (float)p.s[ND + 1];
+    float sq = 0;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) { const float m = (float)p.s[i]; sq += m*m; }
+    ap = __fdividef((float)c_spacing*rho, __fsqrt_rn((float)(heat_rat*(heat_rat - 1))*en*rho) + __fsqrt_rn(sq));
+    if (!(ap > 0.f && ap < 3.0e38f)) ap = 0.f;
+  }
+  float wm = ap > 0.f ? ap : 3.0e38f;
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+  float g = 3.0e38f;
+  if (threadIdx.x % 32 == 0) {
+    g = __int_as_float(__ldca(screen_bits));
+    if (wm < g) { atomicMin(screen_bits, __float_as_int(wm)); g = wm; } // positive floats order like their bit patterns
+  }
+  g = __shfl_sync(0xffffffffu, g, 0);
+  if (valid && (ap == 0.f || ap <= g*1.00002f)) {
+    const double exact = p.cfl_time_step(c_spacing);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(exact);
+    // time steps are positive, so the IEEE bit patterns order like unsigned integers (a NaN or negative value never lowers the minimum
+    // of the plain kernel either: fmin drops NaN; negative values are an inadmissible state and the caller's problem in both)
+    if (exact > 0. && bits < __ldca(a.global_min)) atomicMin(a.global_min, bits);
+  }
+}
+
 /* Global time step from the single-precision CFL screen that the stage-1 Local kernel leaves behind (local_euler_pipe.cu):
  *   1. cfl_screen_min_kernel: minimum of the positive screen values (bit pattern of a positive float orders like an int);
  *   2. cfl_exact_kernel: one warp per element; an element whose screen value is 0 (not representable) or within 1e-5 of that
@@ -177,7 +229,12 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     a.is_local = local_time; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
     a.write_tss = !c->tss_is_one;
     if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream)); // 0x7f7f... = 1.4e306
-    { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
+    if (!local_time && max_dt_running_screen) {
+      int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
+      HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream)); // 0x7f7f7f7f = 3.39e38
+      auto k = max_dt_euler_screen_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits);
+    }
+    else { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
     c->tss_is_one = !local_time;
@@ -205,7 +262,12 @@ int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_
     a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(d_dt);
     a.write_tss = !c->tss_is_one;
     HB_CUDA(c, cudaMemsetAsync(d_dt, 0x7f, sizeof(double), c->stream));
-    if (grid) { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); count_launch(c, ST_MAX_DT_CAR); }
+    if (grid && max_dt_running_screen) {
+      int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
+      HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream));
+      auto k = max_dt_euler_screen_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits); count_launch(c, ST_MAX_DT_CAR);
+    }
+    else if (grid) { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); count_launch(c, ST_MAX_DT_CAR); }
     HB_CUDA(c, cudaGetLastError());
     c->tss_is_one = true;
     return 0;

@@ -122,6 +122,8 @@ template <class T> T atomicMax(T* p, T v) { std::lock_guard<std::mutex> g(hb_emu
 inline unsigned atomicInc(unsigned* p, unsigned lim) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
 
 template <class T> T __ldg(const T* p) { return *p; }
+template <class T> T __ldca(const T* p) { std::lock_guard<std::mutex> g(hb_emu::g_atomic_mutex); return *p; }
+inline float __fsqrt_rn(float x) { return std::sqrt(x); }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
 namespace hb { inline void prefetch_l1(const void*) {} inline void prefetch_l2(const void*) {} }

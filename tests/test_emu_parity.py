@@ -223,6 +223,12 @@ def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
     check_fused_admissibility(oracle, emu_lib, nd, rs, n)
 
 
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 12), (3, 4, 5)])
+def test_max_dt_running_screen_is_exact(oracle, emu_lib, nd, rs, n):
+    from util import check_max_dt_running_screen
+    check_max_dt_running_screen(oracle, emu_lib, nd, rs, n)
+
+
 @pytest.mark.parametrize("nd,rs,pde", [(2, 4, "euler"), (3, 3, "euler"), (2, 4, "navier_stokes")])
 def test_time_step_scale_write_skipped_only_when_known_one(oracle, emu_lib, nd, rs, pde):
     from util import check_tss_write_skipped

@@ -208,6 +208,34 @@ def check_tss_write_skipped(oracle, lib, nd=2, rs=4, pde="euler"):
     dev.close()
 
 
+def check_max_dt_running_screen(oracle, lib, nd, rs, n):
+    """the global-time-step reduction evaluates only the points that pass a running single-precision screen with the FP64 formula;
+    the result must be THE double the unscreened arithmetic gives (the local-time-step kernel writes it per point), whatever the flow:
+    a smooth wave, a uniform flow (every point ties: all evaluated), a fluid at rest, a few extreme cells"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    density_wave(m, basis)
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    nv = nd + 2
+    rng = np.random.default_rng(nd*100 + rs)
+    wave = m.state().copy()
+    uniform = np.broadcast_to(freestream_state(nd)[None, :, None], wave.shape).copy()
+    rest = uniform.copy(); rest[:, :nd] = 0.
+    spiky = wave.copy()
+    for e in rng.integers(0, m.n_elem, 5):
+        spiky[e, nd + 1, rng.integers(0, m.nq)] *= rng.uniform(2., 50.)   # hot spots: the minimum sits in one of them
+    huge = wave.copy(); huge[:, nd + 1] *= 1e36; huge[:, :nd] *= 1e18           # energy*density overflows a float: exact path everywhere
+    for name, st in (("wave", wave), ("uniform", uniform), ("rest", rest), ("spiky", spiky), ("huge", huge)):
+        m.state()[:] = st
+        dev.upload_elements(np.ascontiguousarray(st), 0, nv)
+        dt = dev.max_dt_euler(0.7, 0.7, False)
+        dev.max_dt_euler(0.7, 0.7, True)
+        tss = np.empty((m.n_elem, 1, m.nq)); dev.download_elements(tss, nv, 1)
+        assert dt == tss.min(), (name, dt, tss.min())
+        assert abs(dt/oracle.max_dt(EULER, basis, m, 0.7, 0.7, False) - 1) <= MAX_DT_TOL, name
+    dev.close()
+
+
 def mixed_bcs(mesh, rng):
     """replace the soup mesh's single boundary condition by one of every device-side kind over disjoint subsets of its faces"""
     src = mesh.bcs[0]
