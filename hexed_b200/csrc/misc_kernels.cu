@@ -84,15 +84,16 @@ __global__ void __launch_bounds__(256)
 max_dt_euler_screen_kernel(MaxDtArgs a, Ops ops, int* screen_bits)
 {
   constexpr int nq = ipow(RS, ND), nv = ND + 2, n_vert = ipow(2, ND);
-  const long long gid = (long long)blockIdx.x*256 + threadIdx.x;
-  const int elem = (int)(gid/nq), pt = (int)(gid % nq);
-  const bool valid = elem < a.n_elem;
+  const unsigned gid = blockIdx.x*256u + threadIdx.x; // the launcher checks that the point count fits 32 bits (64-bit division by nq
+  const unsigned elem = gid/nq, pt = gid - elem*nq;    // is ~15 instructions and this kernel is issue-bound)
+  const bool valid = elem < (unsigned)a.n_elem;
   EulerPoint<ND> p;
   double c_spacing = 0;
   float ap = 3.0e38f; // screen value; 0 = not representable, evaluate exactly
   if (valid) {
+    const double* sp = a.state + (size_t)elem*(nv*nq) + pt;
     #pragma unroll
-    for (int v = 0; v < nv; ++v) p.s[v] = a.state[((size_t)elem*nv + v)*nq + pt];
+    for (int v = 0; v < nv; ++v) p.s[v] = sp[v*nq];
     c_spacing = a.max_cfl_c*interp_vertex_spacing<ND, RS>(a.vtss + (size_t)elem*n_vert, ops, pt);
     if (a.write_tss) a.tss[(size_t)elem*nq + pt] = 1.; // Spatial.hpp:823-825
     const float rho = (float)p.s[ND], en = (float)p.s[ND + 1];
@@ -229,7 +230,7 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     a.is_local = local_time; a.global_min = reinterpret_cast<unsigned long long*>(c->d_scalar);
     a.write_tss = !c->tss_is_one;
     if (!local_time) HB_CUDA(c, cudaMemsetAsync(c->d_scalar, 0x7f, sizeof(double), c->stream)); // 0x7f7f... = 1.4e306
-    if (!local_time && max_dt_running_screen) {
+    if (!local_time && max_dt_running_screen && total < (1ll << 32) - 256) {
       int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
       HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream)); // 0x7f7f7f7f = 3.39e38
       auto k = max_dt_euler_screen_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits);
@@ -262,7 +263,7 @@ int launch_max_dt_euler_device(hexed_b200_ctx* c, double safety_conv, double* d_
     a.is_local = 0; a.global_min = reinterpret_cast<unsigned long long*>(d_dt);
     a.write_tss = !c->tss_is_one;
     HB_CUDA(c, cudaMemsetAsync(d_dt, 0x7f, sizeof(double), c->stream));
-    if (grid && max_dt_running_screen) {
+    if (grid && max_dt_running_screen && total < (1ll << 32) - 256) {
       int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
       HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream));
       auto k = max_dt_euler_screen_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits); count_launch(c, ST_MAX_DT_CAR);
