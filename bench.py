@@ -63,6 +63,7 @@ def parse():
                     help="euler = the headline; navier_stokes = Solver::update with use_ldg (stage 0 viscous/LDG, stage 1 inviscid), 1 GPU only")
     ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
+    ap.add_argument("--pipe-mode", type=int, default=1, help="HEXED_B200_OPT_PIPELINED_LOCAL value (A/B: 2 = earlier shared-memory layout of the 3-D deformed kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -219,6 +220,8 @@ def main():
                    blocks=blocks, block=M.block_coords(rank, blocks))
     ne, nq, nv = m.n_elem, m.nq, m.nv
     dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
+    if args.pipe_mode != 1:
+        dev.set_option(0, args.pipe_mode)
     # the generator's copies of the metric terms are dead once the device mirror holds them: 28 KB per element that a 2 M element
     # mesh (the 16 M / 8 GPU configuration) needs back
     m.ref_normals = None; m.det = None; m.normals = None

@@ -23,7 +23,11 @@
 
 namespace hb {
 
-template <int RS, bool DEF>
+/* LEAN (deformed elements): only the state is double buffered; the numerical-flux faces and reference normals are dead after phase A
+ * and live in ONE buffer that is refilled right after it; time-step scale, determinant and residual cache are read once, straight from
+ * HBM after an L2 prefetch issued a phase earlier. 67 KB instead of 105 KB per CTA at row size 6: three resident CTAs per SM instead
+ * of two (the same restructuring took the 2-D kernel from 0.72 to 0.88 of the HBM bandwidth, local_euler_pipe2d.cu). */
+template <int RS, bool DEF, bool LEAN = false>
 struct PipeCfg
 {
   static constexpr int ND = 3, nq = RS*RS*RS, nfq = RS*RS, nv = 5;
@@ -31,14 +35,16 @@ struct PipeCfg
   static constexpr int threads = ((n_line + 31)/32)*32;
   static_assert(RS % 2 == 0, "the line tasks process points in pairs");
   static constexpr int cs = nv > RS ? nv : RS;
-  // double-buffered stage: state | numerical flux faces | reference level normals
+  // double-buffered stage: state | numerical flux faces | reference level normals (LEAN: the state only)
   static constexpr int st_state = 0, st_face = nv*nq, st_nrml = st_face + 2*ND*nv*nfq;
-  static constexpr int stage_doubles = st_nrml + (DEF ? ND*ND*nq : 0);
-  // single-buffered late inputs: residual cache | tss | det
+  static constexpr int stage_doubles = LEAN ? nv*nq : st_nrml + (DEF ? ND*ND*nq : 0);
+  // single-buffered late inputs: residual cache | tss | det (LEAN: this region holds faces | normals instead)
   static constexpr int lt_cache = 0, lt_tss = nv*nq, lt_det = lt_tss + nq;
   static constexpr int lt_vtss = lt_det + (DEF ? nq : 0);
-  static constexpr int late_doubles = lt_vtss + 8; // + the 2^3 vertex time-step scales (used by the CFL screen)
+  static constexpr int fn_face = 0, fn_nrml = 2*ND*nv*nfq;
+  static constexpr int late_doubles = LEAN ? fn_nrml + (DEF ? ND*ND*nq : 0) : lt_vtss + 8; // + the 2^3 vertex time-step scales (used by the CFL screen)
   static constexpr int r_doubles = ND*nv*nq;
+  static constexpr int n_iter = (nq + threads - 1)/threads; // point tasks per thread
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
   static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + CFL screen scratch (4 per-warp minima, 8 vertex spacings, floats)
 };
@@ -64,6 +70,46 @@ __device__ __forceinline__ void pipe_issue_stage(const PipeArgs& a, int e, doubl
   if constexpr (DEF) bulk_g2s(buf + C::st_nrml, a.refn + (size_t)(e - a.n_car)*C::ND*C::ND*C::nq, b_nrml, bar);
 }
 
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe_issue_state(const PipeArgs& a, int e, double* buf, mbar_t* bar)
+{
+  using C = PipeCfg<RS, DEF, true>;
+  constexpr unsigned b_state = sizeof(double)*C::nv*C::nq;
+  mbar_arrive_expect_tx(bar, b_state);
+  bulk_g2s(buf, a.state + (size_t)e*C::nv*C::nq, b_state, bar);
+}
+
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe_issue_fn(const PipeArgs& a, int e, double* buf, mbar_t* bar)
+{
+  using C = PipeCfg<RS, DEF, true>;
+  constexpr unsigned b_face = sizeof(double)*2*C::ND*C::nv*C::nfq, b_nrml = sizeof(double)*C::ND*C::ND*C::nq;
+  mbar_arrive_expect_tx(bar, b_face + (DEF ? b_nrml : 0u));
+  bulk_g2s(buf + C::fn_face, a.faces + (size_t)e*2*C::ND*C::nv*C::nfq, b_face, bar);
+  if constexpr (DEF) bulk_g2s(buf + C::fn_nrml, a.refn + (size_t)(e - a.n_car)*C::ND*C::ND*C::nq, b_nrml, bar);
+}
+
+/* the late inputs of element e towards L2: one 128-byte line per call (the arrays are only 64-byte aligned per element: the last
+ * line is touched explicitly) */
+template <int RS, bool DEF>
+__device__ __forceinline__ void pipe_prefetch_late(const PipeArgs& a, int e, int t)
+{
+  using C = PipeCfg<RS, DEF, true>;
+  const double* tss = a.tss + (size_t)e*C::nq;
+  for (int i = t*16; i < C::nq; i += C::threads*16) prefetch_l2(tss + i);
+  if (t == 0) prefetch_l2(tss + C::nq - 1);
+  if constexpr (DEF) {
+    const double* det = a.det + (size_t)(e - a.n_car)*C::nq;
+    for (int i = t*16; i < C::nq; i += C::threads*16) prefetch_l2(det + i);
+    if (t == 1) prefetch_l2(det + C::nq - 1);
+  }
+  if (a.stage) {
+    const double* cache = a.cache + (size_t)e*C::cs*C::nq;
+    for (int i = t*16; i < C::nv*C::nq; i += C::threads*16) prefetch_l2(cache + i);
+    if (t == 2) prefetch_l2(cache + C::nv*C::nq - 1);
+  }
+}
+
 template <int RS, bool DEF, bool CFL>
 __device__ __forceinline__ void pipe_issue_late(const PipeArgs& a, int e, double* buf, mbar_t* bar)
 {
@@ -76,11 +122,12 @@ __device__ __forceinline__ void pipe_issue_late(const PipeArgs& a, int e, double
   if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e - a.n_car)*C::nq, b_pt, bar);
 }
 
-template <int RS, bool DEF, bool CFL>
+template <int RS, bool DEF, bool CFL, bool LEAN = false>
 __global__ void __launch_bounds__(PipeCfg<RS, DEF>::threads)
 local_euler_pipe_kernel(PipeArgs a, Ops ops)
 {
-  using C = PipeCfg<RS, DEF>;
+  using C = PipeCfg<RS, DEF, LEAN>;
+  static_assert(!(LEAN && CFL), "the CFL-screen instantiation keeps the classic layout");
   constexpr int ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv;
   HB_DYN_SMEM(double, smem);
   double* late = smem + 2*C::stage_doubles;
@@ -97,7 +144,14 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     mbar_init_fence();
   }
   __syncthreads();
-  if (t == 0) {
+  if constexpr (LEAN) {
+    if (t == 0) {
+      pipe_issue_state<RS, DEF>(a, e, smem, &bars[0]);
+      pipe_issue_fn<RS, DEF>(a, e, late, &bars[2]);
+      if (e + stride_e < a.elem_end) pipe_issue_state<RS, DEF>(a, e + stride_e, smem + C::stage_doubles, &bars[1]);
+    }
+    pipe_prefetch_late<RS, DEF>(a, e, t);
+  } else if (t == 0) {
     pipe_issue_stage<RS, DEF>(a, e, smem, &bars[0]);
     if (e + stride_e < a.elem_end) pipe_issue_stage<RS, DEF>(a, e + stride_e, smem + C::stage_doubles, &bars[1]);
     pipe_issue_late<RS, DEF, CFL>(a, e, late, &bars[2]);
@@ -116,9 +170,10 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     const unsigned par = (it >> 1) & 1;
     double* const stage_buf = smem + s*C::stage_doubles;
     double* S = stage_buf + C::st_state;
-    const double* F = stage_buf + C::st_face;
-    const double* N = stage_buf + C::st_nrml;
+    const double* F = LEAN ? late + C::fn_face : stage_buf + C::st_face;
+    const double* N = LEAN ? late + C::fn_nrml : stage_buf + C::st_nrml;
     mbar_wait(&bars[s], par);
+    if constexpr (LEAN) mbar_wait(&bars[2], it & 1);
     int bad = 0; // thermodynamic admissibility of what this thread writes (Solver::is_admissible, fused: see misc_kernels.cu)
 
     /* ---- phase A: flux on the line, then D(flux, face flux) -> R_d ---- */
@@ -239,6 +294,56 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     }
     __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
 
+    if constexpr (LEAN) {
+      // faces / normals buffer is dead: refill it for the next element, and pull that element's late inputs towards L2
+      if (e + stride_e < a.elem_end) {
+        if (t == 0) { fence_proxy_async(); pipe_issue_fn<RS, DEF>(a, e + stride_e, late, &bars[2]); }
+        pipe_prefetch_late<RS, DEF>(a, e + stride_e, t);
+      }
+      /* ---- phase B (lean): the late inputs of this thread's points are loaded from HBM (L2 hits) before its first store ---- */
+      const double nom = a.nom[e];
+      const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
+      double l_tss[C::n_iter], l_cache[C::n_iter][nv];
+      [[maybe_unused]] double l_det[C::n_iter];
+      #pragma unroll
+      for (int k = 0; k < C::n_iter; ++k) {
+        const int q = t + k*C::threads;
+        if (q < nq) {
+          l_tss[k] = a.tss[(size_t)e*nq + q];
+          if constexpr (DEF) l_det[k] = a.det[(size_t)(e - a.n_car)*nq + q];
+          if (a.stage) {
+            #pragma unroll
+            for (int v = 0; v < nv; ++v) l_cache[k][v] = a.cache[((size_t)e*C::cs + v)*nq + q];
+          }
+        }
+      }
+      #pragma unroll
+      for (int k = 0; k < C::n_iter; ++k) {
+        const int q = t + k*C::threads;
+        if (q < nq) {
+          double mult; // update*tss/nom/det (reference Spatial.hpp:484-487) with one division instead of two (<= 1 ulp)
+          if constexpr (DEF) mult = update*l_tss[k]/(nom*l_det[k]);
+          else mult = update*l_tss[k]/nom;
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) {
+            double u = R[(0*nv + v)*nq + q];
+            u += R[(1*nv + v)*nq + q];
+            u += R[(2*nv + v)*nq + q];
+            double* cache = a.cache + ((size_t)e*C::cs + v)*nq + q;
+            if (a.stage) u -= l_cache[k][v];
+            else if (!a.compute_residual) *cache = u;
+            u *= mult;
+            if (a.compute_residual) *cache = u;
+            else {
+              const double xv = S[v*nq + q] + u;
+              S[v*nq + q] = xv;
+              a.state[((size_t)e*nv + v)*nq + q] = xv;
+              if (a.record) bad |= (isfinite(xv) ? 0 : 2) | ((v >= ND && !(xv > 0.)) ? 1 : 0);
+            }
+          }
+        }
+      }
+    } else {
     /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
     mbar_wait(&bars[2], it & 1);
     {
@@ -306,6 +411,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
         if (t % 32 == 0) warp_cfl[t/32] = cfl_min;
       }
     }
+    }
     __syncthreads(); // new state complete in S; late buffer free
     if constexpr (CFL) {
       if (t == 0) {
@@ -315,9 +421,11 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
         a.cfl_approx[e] = m;
       }
     }
-    if (t == 0 && e + stride_e < a.elem_end) {
-      fence_proxy_async();
-      pipe_issue_late<RS, DEF, CFL>(a, e + stride_e, late, &bars[2]);
+    if constexpr (!LEAN) {
+      if (t == 0 && e + stride_e < a.elem_end) {
+        fence_proxy_async();
+        pipe_issue_late<RS, DEF, CFL>(a, e + stride_e, late, &bars[2]);
+      }
     }
 
     /* ---- phase C: write_face from the updated state (reference Spatial.hpp:41-57) ---- */
@@ -369,16 +477,17 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
     } else __syncthreads(); // stage buffer s free
     if (t == 0 && e + 2*stride_e < a.elem_end) {
       fence_proxy_async();
-      pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
+      if constexpr (LEAN) pipe_issue_state<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
+      else pipe_issue_stage<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
     }
   }
 }
 
-template <int RS, bool DEF, bool CFL>
+template <int RS, bool DEF, bool CFL, bool LEAN = false>
 static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
 {
-  using C = PipeCfg<RS, DEF>;
-  auto k = local_euler_pipe_kernel<RS, DEF, CFL>;
+  using C = PipeCfg<RS, DEF, LEAN>;
+  auto k = local_euler_pipe_kernel<RS, DEF, CFL, LEAN>;
   static int blocks_per_sm = 0; // per instantiation
   if (!blocks_per_sm) {
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
@@ -427,6 +536,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
     if (c->rs == 6) rc = deformed ? launch_pipe<6, true, true>(c, a) : launch_pipe<6, false, true>(c, a);
     else rc = deformed ? launch_pipe<4, true, true>(c, a) : launch_pipe<4, false, true>(c, a);
   }
+  else if (deformed && c->pipe_lean) rc = c->rs == 6 ? launch_pipe<6, true, false, true>(c, a) : launch_pipe<4, true, false, true>(c, a);
   else if (c->rs == 6) rc = deformed ? launch_pipe<6, true, false>(c, a) : launch_pipe<6, false, false>(c, a);
   else rc = deformed ? launch_pipe<4, true, false>(c, a) : launch_pipe<4, false, false>(c, a);
   if (rc == 0 && leave_cfl) c->cfl_valid[deformed ? 1 : 0] = true;

@@ -223,6 +223,19 @@ def test_fused_admissibility(oracle, emu_lib, nd, rs, n):
     check_fused_admissibility(oracle, emu_lib, nd, rs, n)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("rs,n", [(6, 3), (4, 3)])
+def test_box_3d_other_local_kernels(oracle, emu_lib, rs, n, mode):
+    """HEXED_B200_OPT_PIPELINED_LOCAL = 0 (the general Local kernel) and 2 (the pipelined kernel with its earlier, fully staged
+    shared-memory layout) stay available for A/B measurements: same parity bar as the default (lean) deformed kernel"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(3, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler_pair(oracle, emu_lib, m, basis, n_steps=2, options=((0, mode),))
+    assert_euler_parity(out, ref, dts)
+
+
 @pytest.mark.parametrize("nd,rs,n", [(2, 6, 12), (3, 4, 5)])
 def test_max_dt_running_screen_is_exact(oracle, emu_lib, nd, rs, n):
     from util import check_max_dt_running_screen

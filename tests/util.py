@@ -15,11 +15,13 @@ def rel_l2(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b))/max(np.linalg.norm(b), 1e-300))
 
 
-def run_euler_pair(oracle, lib_path, mesh, basis, n_steps=2, local_time=False, use_filter=False, safety=0.7):
+def run_euler_pair(oracle, lib_path, mesh, basis, n_steps=2, local_time=False, use_filter=False, safety=0.7, options=()):
     """advance `mesh` n_steps (each: max_dt + 2 stages with ghost-state BCs) on both implementations.
     Returns (device result mesh, oracle result mesh, list of (dt_device, dt_oracle))."""
     ref = mesh.copy()
     dev = Device(mesh.n_dim, mesh.row_size, basis, lib_path=lib_path).load_mesh(mesh)
+    for opt, val in options:
+        dev.set_option(opt, val)
     dts = []
     for _ in range(n_steps):
         dt_o = oracle.max_dt(EULER, basis, ref, safety, safety, local_time)
