@@ -122,9 +122,8 @@ __device__ __forceinline__ void pipe_issue_late(const PipeArgs& a, int e, double
   if constexpr (DEF) bulk_g2s(buf + C::lt_det, a.det + (size_t)(e - a.n_car)*C::nq, b_pt, bar);
 }
 
-template <int RS, bool DEF, bool CFL, bool LEAN = false>
-__global__ void __launch_bounds__(PipeCfg<RS, DEF>::threads)
-local_euler_pipe_kernel(PipeArgs a, Ops ops)
+template <int RS, bool DEF, bool CFL, bool LEAN>
+__device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
 {
   using C = PipeCfg<RS, DEF, LEAN>;
   static_assert(!(LEAN && CFL), "the CFL-screen instantiation keeps the classic layout");
@@ -159,7 +158,7 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
 
   // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
   int d, l;
-  using Map = LineMap<RS, !DEF>; // measured: pays off for the Cartesian kernel only (see common.cuh)
+  using Map = LineMap<RS, !DEF && !LEAN>; // measured: pays off for the (classic) Cartesian kernel only (see common.cuh)
   const bool has_line = Map::get(t, d, l);
   const bool vec = Map::vec2 && d == 2; // this thread's line is contiguous: 16-byte accesses
   const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
@@ -484,13 +483,24 @@ local_euler_pipe_kernel(PipeArgs a, Ops ops)
 }
 
 template <int RS, bool DEF, bool CFL, bool LEAN = false>
+__global__ void __launch_bounds__(PipeCfg<RS, DEF>::threads)
+local_euler_pipe_kernel(PipeArgs a, Ops ops) { pipe_body<RS, DEF, CFL, LEAN>(a, ops); }
+
+/* Cartesian elements in the lean layout need 52 KB: four CTAs fit one SM if the kernel keeps to 128 registers */
+template <int RS>
+__global__ void __launch_bounds__(PipeCfg<RS, false>::threads, 4)
+local_euler_pipe4_kernel(PipeArgs a, Ops ops) { pipe_body<RS, false, false, true>(a, ops); }
+
+template <int RS, bool DEF, bool CFL, bool LEAN = false>
 static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
 {
   using C = PipeCfg<RS, DEF, LEAN>;
-  auto k = local_euler_pipe_kernel<RS, DEF, CFL, LEAN>;
+  void (*k)(PipeArgs, Ops) = local_euler_pipe_kernel<RS, DEF, CFL, LEAN>;
+  if constexpr (LEAN && !DEF) k = local_euler_pipe4_kernel<RS>;
   static int blocks_per_sm = 0; // per instantiation
   if (!blocks_per_sm) {
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
+    HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int n = 0;
     HB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::threads, C::smem_bytes));
     if (n < 1) return fail(c, HEXED_B200_CUDA_ERROR, "pipelined local kernel does not fit on this device");
@@ -537,6 +547,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
     else rc = deformed ? launch_pipe<4, true, true>(c, a) : launch_pipe<4, false, true>(c, a);
   }
   else if (deformed && c->pipe_lean) rc = c->rs == 6 ? launch_pipe<6, true, false, true>(c, a) : launch_pipe<4, true, false, true>(c, a);
+  else if (!deformed && c->pipe_lean4) rc = c->rs == 6 ? launch_pipe<6, false, false, true>(c, a) : launch_pipe<4, false, false, true>(c, a);
   else if (c->rs == 6) rc = deformed ? launch_pipe<6, true, false>(c, a) : launch_pipe<6, false, false>(c, a);
   else rc = deformed ? launch_pipe<4, true, false>(c, a) : launch_pipe<4, false, false>(c, a);
   if (rc == 0 && leave_cfl) c->cfl_valid[deformed ? 1 : 0] = true;

@@ -320,13 +320,14 @@ def test_fused_admissibility(oracle, gpu_lib, nd, rs, n):
     check_fused_admissibility(oracle, gpu_lib, nd, rs, n)
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode,deformed", [(0, True), (2, True), (3, False)])
 @pytest.mark.parametrize("rs,n", [(6, 7), (4, 9)])
-def test_box_3d_other_local_kernels(oracle, gpu_lib, rs, n, mode):
+def test_box_3d_other_local_kernels(oracle, gpu_lib, rs, n, mode, deformed):
     """HEXED_B200_OPT_PIPELINED_LOCAL = 0 (the general Local kernel) and 2 (the pipelined kernel with its earlier, fully staged
-    shared-memory layout) stay available for A/B measurements: same parity bar as the default (lean) deformed kernel"""
+    shared-memory layout) stay available for A/B measurements, 3 = Cartesian elements in the lean layout with four resident CTAs:
+    same parity bar as the default kernels"""
     basis = hb.gauss_legendre(rs)
-    m = M.box_mesh(3, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    m = M.box_mesh(3, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
     density_wave(m, basis)
     oracle.compute_write_face(basis, m)
     out, ref, dts, _ = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=2, options=((0, mode),))
