@@ -334,6 +334,12 @@ def test_box_3d_other_local_kernels(oracle, gpu_lib, rs, n, mode, deformed):
     assert_euler_parity(out, ref, dts)
 
 
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 60), (3, 6, 16), (3, 4, 20)])
+def test_max_dt_running_screen_random_states(oracle, gpu_lib, nd, rs, n):
+    from util import check_max_dt_running_screen_random
+    check_max_dt_running_screen_random(oracle, gpu_lib, nd, rs, n, range(40))
+
+
 @pytest.mark.parametrize("nd,rs,n", [(2, 6, 150), (3, 6, 40), (3, 3, 30)])
 def test_max_dt_running_screen_is_exact(oracle, gpu_lib, nd, rs, n):
     from util import check_max_dt_running_screen

@@ -238,6 +238,36 @@ def check_max_dt_running_screen(oracle, lib, nd, rs, n):
     dev.close()
 
 
+def check_max_dt_running_screen_random(oracle, lib, nd, rs, n, seeds):
+    """the same bit-identity on random admissible states with a wide dynamic range (densities over 3 decades, Mach 0 to ~30, cells at
+    rest, ties between elements): whatever passes the single-precision screen, the minimum is the unscreened double"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    nv = nd + 2
+    shape = m.state().shape
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        st = np.empty(shape)
+        rho = 10.**rng.uniform(-2, 1, (shape[0], shape[2]))
+        sound = 10.**rng.uniform(1.5, 3., (shape[0], shape[2]))
+        mach = rng.uniform(0., 30., (shape[0], 1))*rng.integers(0, 2, (shape[0], 1))      # half of the elements at rest
+        direction = rng.normal(size=(shape[0], nd, shape[2])); direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+        st[:, :nd] = (rho*sound*mach)[:, None, :]*direction
+        st[:, nd] = rho
+        st[:, nd + 1] = rho*sound**2/(1.4*0.4) + 0.5*np.sum(st[:, :nd]**2, axis=1)/rho
+        if seed % 3 == 0:                                                                   # exact ties between two elements
+            st[1] = st[0]
+        m.state()[:] = st
+        dev.upload_elements(np.ascontiguousarray(st), 0, nv)
+        dt = dev.max_dt_euler(0.7, 0.7, False)
+        dev.max_dt_euler(0.7, 0.7, True)
+        tss = np.empty((m.n_elem, 1, m.nq)); dev.download_elements(tss, nv, 1)
+        assert dt == tss.min(), (seed, dt, tss.min())
+        assert abs(dt/oracle.max_dt(EULER, basis, m, 0.7, 0.7, False) - 1) <= MAX_DT_TOL, seed
+    dev.close()
+
+
 def mixed_bcs(mesh, rng):
     """replace the soup mesh's single boundary condition by one of every device-side kind over disjoint subsets of its faces"""
     src = mesh.bcs[0]
