@@ -1267,39 +1267,56 @@ g_write_face_kernel(GArgs a, Ops ops)
 }
 
 /* ---------------- Max_dt ---------------- */
+/* n-linear interpolation of the vertex spacing to point q (reference include/math.hpp:207-218) */
+template <int ND, int RS>
+__device__ __forceinline__ double g_point_spacing(const GArgs& a, const Ops& ops, int e, int q)
+{
+  constexpr int n_vert = ipow(2, ND);
+  double vals[n_vert];
+  #pragma unroll
+  for (int i = 0; i < n_vert; ++i) vals[i] = a.vtss[(size_t)e*n_vert + i];
+  int stride = n_vert;
+  #pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
+    stride /= 2;
+    #pragma unroll
+    for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
+  }
+  return vals[0];
+}
+
+/* the local time step 1/scale of one point from its state (already in comp.state) and spacing: Spatial.hpp:808-822 with the five
+ * divisions by max_cfl / spacing replaced by one reciprocal of the spacing and the host-side reciprocals of the CFL numbers
+ * (<= 1 ulp per use; FP64 division is ~30 instructions and this kernel was issue-bound). ONE function for every caller, so that the
+ * screened reduction below returns the very double the unscreened one does. */
+template <int ND, class P, class COMP>
+__device__ __forceinline__ double g_point_dt(const GArgs& a, COMP& comp, double spacing)
+{
+  const double inv_spacing = 1./spacing;
+  double scale = 0;
+  if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed*a.inv_max_cfl_c*inv_spacing; }
+  if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity*a.inv_max_cfl_d*inv_spacing*inv_spacing; }
+  return 1./scale;
+}
+
 template <int ND, int RS, class P>
 __global__ void __launch_bounds__(256)
 g_max_dt_kernel(GArgs a, Ops ops)
 {
-  constexpr int nq = ipow(RS, ND), n_vert = ipow(2, ND);
+  constexpr int nq = ipow(RS, ND);
   __shared__ double warp_min[8];
   const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
   const int e = (int)(gid/nq), q = (int)(gid % nq);
   double val = DBL_MAX;
   if (e < a.elem_end) {
-    double vals[n_vert];
-    #pragma unroll
-    for (int i = 0; i < n_vert; ++i) vals[i] = a.vtss[(size_t)e*n_vert + i];
-    int stride = n_vert;
-    #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      const double coord = ops.node[(q/ipow(RS, ND - 1 - d)) % RS];
-      stride /= 2;
-      #pragma unroll
-      for (int i = 0; i < n_vert/2; ++i) if (i < stride) vals[i] += coord*(vals[i + stride] - vals[i]);
-    }
-    const double spacing = vals[0];
+    const double spacing = g_point_spacing<ND, RS>(a, ops, e, q);
     typename P::template Comp<ND> comp;
     #pragma unroll
     for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>(e, P::state_slot(i))[q];
-    // Spatial.hpp:808-822 with the five divisions by max_cfl / spacing replaced by one reciprocal of the spacing and the
-    // host-side reciprocals of the CFL numbers (<= 1 ulp per use; FP64 division is ~30 instructions and this kernel was issue-bound)
-    const double inv_spacing = 1./spacing;
-    double scale = 0;
-    if constexpr (P::has_convection) { comp.compute_char_speed(); scale += comp.char_speed*a.inv_max_cfl_c*inv_spacing; }
-    if constexpr (P::has_diffusion) { comp.compute_diffusivity(a.pp); scale += comp.diffusivity*a.inv_max_cfl_d*inv_spacing*inv_spacing; }
-    if (a.is_local) a.ed.tss[(size_t)e*nq + q] = 1./scale;
-    else { if (a.write_tss) a.ed.tss[(size_t)e*nq + q] = 1.; val = 1./scale; }
+    const double local_dt = g_point_dt<ND, P>(a, comp, spacing);
+    if (a.is_local) a.ed.tss[(size_t)e*nq + q] = local_dt;
+    else { if (a.write_tss) a.ed.tss[(size_t)e*nq + q] = 1.; val = local_dt; }
   }
   if (a.is_local) return;
   #pragma unroll
@@ -1310,6 +1327,48 @@ g_max_dt_kernel(GArgs a, Ops ops)
     double m = warp_min[0];
     for (int i = 1; i < (int)blockDim.x/32; ++i) m = fmin(m, warp_min[i]);
     atomicMin(a.global_min, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+/* Global time stepping with a running single-precision screen: the scheme of max_dt_euler_screen_kernel (misc_kernels.cu) for the
+ * PDEs that provide P::screen_dt (Navier-Stokes). Points whose screen value is within P::screen_margin of min(running, warp minimum)
+ * -- or 0 = not trustworthy -- are evaluated with g_point_dt and folded into the result with atomicMin; everything else is skipped. */
+template <int ND, int RS, class P>
+__global__ void __launch_bounds__(256)
+g_max_dt_screen_kernel(GArgs a, Ops ops, int* screen_bits)
+{
+  constexpr int nq = ipow(RS, ND);
+  const unsigned gid = blockIdx.x*256u + threadIdx.x; // the launcher checks that the point count fits 32 bits
+  const unsigned e = gid/nq, q = gid - e*nq;
+  const bool valid = e < (unsigned)a.elem_end;
+  typename P::template Comp<ND> comp;
+  double spacing = 1.;
+  float ap = 3.0e38f;
+  if (valid) {
+    spacing = g_point_spacing<ND, RS>(a, ops, (int)e, (int)q);
+    #pragma unroll
+    for (int i = 0; i < P::n_state; ++i) comp.state[i] = a.ed.template slot<ND, RS>((int)e, P::state_slot(i))[q];
+    if (a.write_tss) a.ed.tss[(size_t)e*nq + q] = 1.;
+    float s[P::n_state];
+    #pragma unroll
+    for (int i = 0; i < P::n_state; ++i) s[i] = (float)comp.state[i];
+    const float inv_h = __fdividef(1.f, (float)spacing);
+    ap = P::screen_dt(s, a.pp, (float)a.inv_max_cfl_c*inv_h, (float)a.inv_max_cfl_d*inv_h*inv_h);
+    if (!(ap > 0.f && ap < 3.0e38f)) ap = 0.f;
+  }
+  float wm = ap > 0.f ? ap : 3.0e38f;
+  #pragma unroll
+  for (int off = 16; off > 0; off /= 2) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+  float g = 3.0e38f;
+  if (threadIdx.x % 32 == 0) {
+    g = __int_as_float(__ldca(screen_bits));
+    if (wm < g) { atomicMin(screen_bits, __float_as_int(wm)); g = wm; }
+  }
+  g = __shfl_sync(0xffffffffu, g, 0);
+  if (valid && (ap == 0.f || ap <= g*P::screen_margin)) {
+    const double exact = g_point_dt<ND, P>(a, comp, spacing);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(exact);
+    if (exact > 0. && bits < __ldca(a.global_min)) atomicMin(a.global_min, bits);
   }
 }
 
@@ -1473,7 +1532,15 @@ int g_max_dt(hexed_b200_ctx* c, const PdeParams& pp, double safety_conv, double 
     double* result = c->max_dt_device_out ? c->max_dt_device_out : c->d_scalar; // hexed_b200_update_*: leave dt on the device
     a.global_min = reinterpret_cast<unsigned long long*>(result);
     if (!local_time) HB_CUDA(c, cudaMemsetAsync(result, 0x7f, sizeof(double), c->stream));
-    { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
+    if constexpr (P::has_float_screen) {
+      if (!local_time && total < (1ll << 32) - 256) {
+        int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
+        HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream)); // 0x7f7f7f7f = 3.39e38
+        auto k = g_max_dt_screen_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits);
+      }
+      else { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
+    }
+    else { auto k = g_max_dt_kernel<ND, RS, P>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }
     count_launch(c, ST_MAX_DT_CAR);
     HB_CUDA(c, cudaGetLastError());
     c->tss_is_one = !local_time;

@@ -43,12 +43,45 @@ __device__ __forceinline__ double transport_coef(const hexed_b200_transport& t, 
   return t.const_val + t.ref_val*cube*(t.ref_temp + t.temp_offset)/(sqrt_temp*sqrt_temp + t.temp_offset);
 }
 
+/* single-precision restatement for the max_dt screen (generic_part.cu); the uniform parameters are converted once per thread */
+__device__ __forceinline__ float transport_coef_f(const hexed_b200_transport& t, double inv_sqrt_ref_temp, float sqrt_temp, float temp)
+{
+  const float r = sqrt_temp*(float)inv_sqrt_ref_temp;
+  return (float)t.const_val + (float)(t.ref_val*(t.ref_temp + t.temp_offset))*(r*r*r)*__fdividef(1.f, temp + (float)t.temp_offset);
+}
+
 /* ---------------- Navier-Stokes / Euler: include/pde.hpp:27-175 ---------------- */
 template <int ND, int RS, bool VISC>
 struct PdeNs
 {
   static constexpr bool has_diffusion = VISC, has_convection = true, has_source = false;
   static constexpr int n_update = ND + 2, n_state = ND + 4, n_extrap = ND + 2, face_kind = 0;
+  /* Max_dt screen: 1/scale (the local time step, reference include/Spatial.hpp:808-822) in single precision, or 0 where the estimate
+   * cannot be trusted to 1.5e-5 relative: the temperature is a difference of total and kinetic energy, so above Mach ~7 (internal
+   * energy below 3 % of the total) and for inadmissible states the caller must take the FP64 path. Error budget where a value is
+   * returned: inputs and arithmetic ~1e-6; temperature <= 1.2e-7*(E + ke)/(E - ke) <= 8e-6, Sutherland's law amplifies it by <= 1.5;
+   * the two terms of the scale are positive, so the sum is no worse than its worst term. The screen margin is 1e-4. */
+  static constexpr bool has_float_screen = VISC;
+  static constexpr float screen_margin = 1.0001f;
+  __device__ static float screen_dt(const float (&s)[n_state], const PdeParams& p, float inv_c_h, float inv_d_h2)
+  {
+    const float rho = s[ND], en = s[ND + 1];
+    float sq = 0;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) sq += s[i]*s[i];
+    const float inv = __fdividef(1.f, rho);
+    const float int_ener = en - .5f*sq*inv;
+    if (!(int_ener > 0.03f*en)) return 0.f;
+    const float speed = __fsqrt_rn((float)(heat_rat_ns*(heat_rat_ns - 1))*en*inv) + __fsqrt_rn(sq)*inv;
+    constexpr float gm1_over_r = (float)((heat_rat_ns - 1)/specific_gas_air);
+    const float temp = int_ener*inv*gm1_over_r;
+    const float sqrt_temp = __fsqrt_rn(temp);
+    const float visc = transport_coef_f(p.visc, p.visc_inv_sqrt_ref, sqrt_temp, temp);
+    const float cond = transport_coef_f(p.cond, p.cond_inv_sqrt_ref, sqrt_temp, temp)*gm1_over_r;
+    const float diffusivity = fabsf(s[ND + 3]) + fmaxf(fabsf(s[ND + 2]) + visc*inv, cond*inv);
+    const float r = __fdividef(1.f, speed*inv_c_h + diffusivity*inv_d_h2);
+    return (r > 0.f && r < 3.0e38f) ? r : 0.f;
+  }
   static constexpr bool needs_av = VISC, needs_forcing = false, needs_adv = false;
   __device__ static constexpr int extrap_slot(int v) { return v; }
   __device__ static constexpr int state_slot(int i) { return i < ND + 2 ? i : i + 1; } // ND+2 -> bulk av (ND+3), ND+3 -> laplacian av (ND+4)
@@ -184,6 +217,7 @@ template <int ND, int RS>
 struct PdeAdvection
 {
   static constexpr bool has_diffusion = false, has_convection = true, has_source = true;
+  static constexpr bool has_float_screen = false;
   static constexpr int n_adv = RS, n_state = ND + RS, n_extrap = ND + RS, n_update = RS, face_kind = 2;
   static constexpr bool needs_av = false, needs_forcing = false, needs_adv = true;
   __device__ static constexpr int extrap_slot(int v) { return v < ND ? v : ND + 9 + (v - ND); }
@@ -281,6 +315,7 @@ template <int ND, int RS>
 struct PdeSmoothAv
 {
   static constexpr bool has_diffusion = true, has_convection = false, has_source = true;
+  static constexpr bool has_float_screen = false;
   static constexpr int n_state = 4, n_extrap = 3, n_update = 3, face_kind = 0;
   static constexpr bool needs_av = false, needs_forcing = true, needs_adv = false;
   __device__ static constexpr int extrap_slot(int v) { return ND + 5 + 1 + v; }
@@ -319,6 +354,7 @@ template <int ND, int RS>
 struct PdeFta
 {
   static constexpr bool has_diffusion = true, has_convection = false, has_source = false;
+  static constexpr bool has_float_screen = false;
   static constexpr int n_state = ND + 2, n_extrap = ND + 2, n_update = ND + 2, face_kind = 0;
   static constexpr bool needs_av = false, needs_forcing = false, needs_adv = false;
   __device__ static constexpr int extrap_slot(int v) { return v; }

@@ -243,6 +243,12 @@ def test_max_dt_running_screen_random_states(oracle, emu_lib, nd, rs, n):
     check_max_dt_running_screen_random(oracle, emu_lib, nd, rs, n, range(12))
 
 
+@pytest.mark.parametrize("nd,rs,n", [(2, 4, 6), (3, 2, 4)])
+def test_max_dt_running_screen_navier_stokes(oracle, emu_lib, nd, rs, n):
+    from util import check_max_dt_running_screen_ns
+    check_max_dt_running_screen_ns(oracle, emu_lib, nd, rs, n, range(12))
+
+
 @pytest.mark.parametrize("nd,rs,n", [(2, 6, 12), (3, 4, 5)])
 def test_max_dt_running_screen_is_exact(oracle, emu_lib, nd, rs, n):
     from util import check_max_dt_running_screen

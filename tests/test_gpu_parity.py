@@ -340,6 +340,12 @@ def test_max_dt_running_screen_random_states(oracle, gpu_lib, nd, rs, n):
     check_max_dt_running_screen_random(oracle, gpu_lib, nd, rs, n, range(40))
 
 
+@pytest.mark.parametrize("nd,rs,n", [(2, 6, 60), (3, 6, 16), (3, 4, 20)])
+def test_max_dt_running_screen_navier_stokes(oracle, gpu_lib, nd, rs, n):
+    from util import check_max_dt_running_screen_ns
+    check_max_dt_running_screen_ns(oracle, gpu_lib, nd, rs, n, range(40))
+
+
 @pytest.mark.parametrize("nd,rs,n", [(2, 6, 150), (3, 6, 40), (3, 3, 30)])
 def test_max_dt_running_screen_is_exact(oracle, gpu_lib, nd, rs, n):
     from util import check_max_dt_running_screen

@@ -268,6 +268,45 @@ def check_max_dt_running_screen_random(oracle, lib, nd, rs, n, seeds):
     dev.close()
 
 
+def check_max_dt_running_screen_ns(oracle, lib, nd, rs, n, seeds):
+    """the Navier-Stokes global time step (g_max_dt_screen_kernel) against the unscreened per-point values of local time stepping:
+    bit-identical on random admissible states (densities over 3 decades, Mach 0 to ~30 so that the forced-exact branch above Mach ~7
+    is taken, artificial-viscosity coefficients that make the diffusive term dominate in places, tiny cells), and against the oracle"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, n, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    nv = nd + 2
+    shape = m.state().shape
+    ne, nq = shape[0], shape[2]
+    models = ((K.sutherland(1.716e-5, 273., 111.), K.sutherland(.0241, 273., 194.), pyoracle.sutherland(1.716e-5, 273., 111.), pyoracle.sutherland(.0241, 273., 194.)),
+              (K.constant_transport(3e-2), K.constant_transport(50.), pyoracle.constant(3e-2), pyoracle.constant(50.)))
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        visc_d, cond_d, visc_o, cond_o = models[seed % 2]
+        st = np.empty(shape)
+        rho = 10.**rng.uniform(-2, 1, (ne, nq))
+        sound = 10.**rng.uniform(1.5, 3., (ne, nq))
+        mach = rng.uniform(0., 30., (ne, 1))*rng.integers(0, 2, (ne, 1))
+        direction = rng.normal(size=(ne, nd, nq)); direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+        st[:, :nd] = (rho*sound*mach)[:, None, :]*direction
+        st[:, nd] = rho
+        st[:, nd + 1] = rho*sound**2/(1.4*0.4) + 0.5*np.sum(st[:, :nd]**2, axis=1)/rho
+        if seed % 3 == 0:
+            st[1] = st[0]
+        av = 10.**rng.uniform(-6, 1 if seed % 4 == 0 else -3, (ne, 2, nq))*rng.choice([-1., 1.], (ne, 2, nq))
+        m.state()[:] = st
+        m.elem_data[:, M.BULK_AV_SLOT(nd)] = av[:, 0]
+        m.elem_data[:, M.LAPLACIAN_AV_SLOT(nd)] = av[:, 1]
+        dev.upload_elements(np.ascontiguousarray(st), 0, nv)
+        dev.upload_elements(np.ascontiguousarray(av), M.BULK_AV_SLOT(nd), 2)
+        dt = dev.max_dt_navier_stokes(0.7, 0.6, False, visc_d, cond_d)
+        dev.max_dt_navier_stokes(0.7, 0.6, True, visc_d, cond_d)
+        tss = np.empty((ne, 1, nq)); dev.download_elements(tss, nv, 1)
+        assert dt == tss.min(), (seed, dt, tss.min())
+        assert abs(dt/oracle.max_dt(NAVIER_STOKES, basis, m, 0.7, 0.6, False, visc_o, cond_o) - 1) <= MAX_DT_TOL, seed
+    dev.close()
+
+
 def mixed_bcs(mesh, rng):
     """replace the soup mesh's single boundary condition by one of every device-side kind over disjoint subsets of its faces"""
     src = mesh.bcs[0]
