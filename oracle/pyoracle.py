@@ -344,6 +344,84 @@ class Oracle:
                 m.face_ldg[gh] = g.reshape(len(gh), -1)
 
 
+REF_LIB = os.path.join(HERE, "_ref", "libhexed_ref.so")
+
+
+def build_ref(jobs=8):
+    """compile the reference's own kernel sources (oracle/Makefile.ref); needs /root/reference, i.e. only works in the build container"""
+    subprocess.run(["make", "-C", HERE, "-f", "Makefile.ref", "-j%d" % jobs], check=True, stdout=subprocess.DEVNULL)
+
+
+def ref_available():
+    return os.path.exists(REF_LIB)
+
+
+class _RefLib:
+    """attribute proxy: `ho_x` resolves to the reference build's `hr_x` where it exists, else to the restated oracle's `ho_x`
+    (boundary-condition fills, which oracle/_ref does not contain)"""
+
+    def __init__(self, ref, port):
+        self._ref, self._port = ref, port
+
+    def __getattr__(self, name):
+        if name.startswith("ho_"):
+            try:
+                return getattr(self._ref, "hr_" + name[3:])
+            except AttributeError:
+                pass
+        return getattr(self._port, name)
+
+
+class RefOracle(Oracle):
+    """Same interface as `Oracle`, but every kernel call lands in oracle/_ref/libhexed_ref.so: the REFERENCE's own
+    src/kernels_*.cpp + include/Spatial.hpp / pde.hpp compiled unmodified (oracle/Makefile.ref, oracle/ref_harness.cpp) on the
+    reference's own generated Gauss_legendre basis. The `basis` argument of the methods is accepted and ignored."""
+
+    def __init__(self, lib="liboracle.so"):
+        if not ref_available():
+            if os.path.isdir("/root/reference"):
+                build_ref()
+            else:
+                raise FileNotFoundError(REF_LIB)
+        Oracle.__init__(self, lib)
+        port = self.lib
+        self.ref = C.CDLL(REF_LIB)
+        self.lib = _RefLib(self.ref, port)
+        R = self.ref
+        for name in ("compute_euler", "compute_advection", "compute_navier_stokes", "compute_smooth_av", "compute_fix_therm_admis", "max_dt",
+                     "compute_write_face", "compute_prolong", "compute_restrict", "face_permutation", "stabilizing_art_visc", "derivative",
+                     "characteristics"):
+            getattr(R, "hr_" + name).argtypes = getattr(port, "ho_" + name).argtypes
+        R.hr_basis.argtypes = [C.c_int, C.POINTER(ho_basis)]
+        R.hr_basis_max_cfl.argtypes = [C.c_int]; R.hr_basis_max_cfl.restype = C.c_double
+        R.hr_basis_step_ratio.argtypes = [C.c_int]; R.hr_basis_step_ratio.restype = C.c_double
+        R.hr_chebyshev_step.argtypes = [C.c_int, C.c_int]; R.hr_chebyshev_step.restype = C.c_double
+        R.hr_view_create.argtypes = [C.POINTER(ho_mesh)]; R.hr_view_create.restype = C.c_void_p
+        R.hr_view_destroy.argtypes = [C.c_void_p]; R.hr_view_destroy.restype = None
+        R.hr_view_store.argtypes = [C.c_void_p]; R.hr_view_store.restype = None
+        R.hr_view_compute_euler.argtypes = [C.c_void_p, ho_options]
+        R.hr_view_compute_navier_stokes.argtypes = [C.c_void_p, ho_options, ho_transport, ho_transport]
+        R.hr_view_max_dt_euler.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, dp]
+        R.hr_view_bc_freestream.argtypes = [C.c_void_p, C.c_int, ip, dp]
+
+    def num_threads(self):
+        return self.ref.hr_num_threads()
+
+    def basis_tables(self, row_size):
+        """the reference's generated Gauss-Legendre tables as a dict of numpy arrays (M[i][j] mathematical indexing)"""
+        b = ho_basis()
+        self._check(self.ref.hr_basis(row_size, C.byref(b)))
+        rs = row_size
+
+        def arr(field, *shape):
+            return np.array(list(field), dtype=np.float64).reshape(shape)
+        return dict(node=arr(b.node, 8)[:rs], weight=arr(b.weight, 8)[:rs], diff_mat=arr(b.diff_mat, 8, 8)[:rs, :rs],
+                    boundary=arr(b.boundary, 2, 8)[:, :rs], orthogonal=arr(b.orthogonal, 8, 8)[:rs, :rs], filter=arr(b.filter, 8, 8)[:rs, :rs],
+                    prolong=arr(b.prolong, 2, 8, 8)[:, :rs, :rs], restrict=arr(b.restrict_, 2, 8, 8)[:, :rs, :rs],
+                    min_eig_convection=b.min_eig_convection, min_eig_diffusion=b.min_eig_diffusion, quadratic_safety=b.quadratic_safety,
+                    max_cfl=self.ref.hr_basis_max_cfl(rs), step_ratio=self.ref.hr_basis_step_ratio(rs))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # metric terms (SURVEY section 8 f-4): numpy restatement of Deformed_element::position / set_jacobian, one element at a time with
 # plain loops (small cases only). TEST INFRASTRUCTURE like everything else in this directory.

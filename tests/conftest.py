@@ -13,10 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
-def oracle():
-    from pyoracle import Oracle
-    return Oracle()
+def _ref_possible():
+    import pyoracle
+    return pyoracle.ref_available() or os.path.isdir("/root/reference")
+
+
+@pytest.fixture(scope="session", params=["port", "ref"])
+def oracle(request):
+    """the checker every parity test compares against: "port" = the restated CPU oracle (oracle/oracle_impl.hpp), "ref" = the
+    REFERENCE'S OWN kernels compiled from /root/reference (oracle/_ref/libhexed_ref.so, built here, shipped to the GPU box);
+    both expose the same interface (pyoracle.Oracle / pyoracle.RefOracle), so every test runs against both."""
+    import pyoracle
+    if request.param == "ref":
+        if not _ref_possible():
+            pytest.skip("oracle/_ref/libhexed_ref.so is absent and /root/reference is not here to build it from")
+        return pyoracle.RefOracle()
+    return pyoracle.Oracle()
 
 
 @pytest.fixture(scope="session")
