@@ -198,11 +198,12 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   return 0;
 }
 
-int hexed_b200_synchronize(hexed_b200_ctx* c) { HB_CUDA(c, cudaStreamSynchronize(c->stream)); return 0; }
+int hexed_b200_synchronize(hexed_b200_ctx* c) { HB_ENTER(c); HB_CUDA(c, cudaStreamSynchronize(c->stream)); return 0; }
 int hexed_b200_cuda_stream(hexed_b200_ctx* c, void** stream) { *stream = (void*)c->stream; return 0; }
 
 int hexed_b200_mesh_create(hexed_b200_ctx* c, const hexed_b200_mesh_desc* d)
 {
+  HB_ENTER(c);
   HB_CUDA(c, cudaSetDevice(c->device));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   free_mesh(c);
@@ -286,6 +287,7 @@ static int array_info(hexed_b200_ctx* c, int which, double*** arr, size_t* item,
 
 int hexed_b200_upload(hexed_b200_ctx* c, int which, const double* src, size_t first, size_t n)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   double** arr; size_t item, count;
   int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
@@ -300,6 +302,7 @@ int hexed_b200_upload(hexed_b200_ctx* c, int which, const double* src, size_t fi
 
 int hexed_b200_download(hexed_b200_ctx* c, int which, double* dst, size_t first, size_t n)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   double** arr; size_t item, count;
   int rc = array_info(c, which, &arr, &item, &count, true); if (rc) return rc;
@@ -348,13 +351,14 @@ static int move_slots(hexed_b200_ctx* c, double* host, size_t elem_stride, int f
 }
 
 int hexed_b200_upload_elem_slots(hexed_b200_ctx* c, const double* src, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem)
-{ return move_slots(c, const_cast<double*>(src), elem_stride, first_slot, n_slots, first_elem, n_elem, true); }
+{ HB_ENTER(c); return move_slots(c, const_cast<double*>(src), elem_stride, first_slot, n_slots, first_elem, n_elem, true); }
 
 int hexed_b200_download_elem_slots(hexed_b200_ctx* c, double* dst, size_t elem_stride, int first_slot, int n_slots, int first_elem, int n_elem)
-{ return move_slots(c, dst, elem_stride, first_slot, n_slots, first_elem, n_elem, false); }
+{ HB_ENTER(c); return move_slots(c, dst, elem_stride, first_slot, n_slots, first_elem, n_elem, false); }
 
 int hexed_b200_face_list_create(hexed_b200_ctx* c, const int* slots, int n, int* list_id)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   for (int i = 0; i < n; ++i) if (slots[i] < 0 || slots[i] >= c->n_face_slot) return fail(c, HEXED_B200_BAD_ARGUMENT, "face slot out of range");
   FaceList l; l.n = n;
@@ -379,6 +383,7 @@ static int list_face_array(hexed_b200_ctx* c, int kind, double** arr, int* width
 
 int hexed_b200_face_list_download(hexed_b200_ctx* c, int list_id, int kind, double* dst)
 {
+  HB_ENTER(c);
   if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
   FaceList& l = c->lists[list_id];
   double* arr; int width;
@@ -391,6 +396,7 @@ int hexed_b200_face_list_download(hexed_b200_ctx* c, int list_id, int kind, doub
 
 int hexed_b200_face_list_upload(hexed_b200_ctx* c, int list_id, int kind, const double* src)
 {
+  HB_ENTER(c);
   if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
   FaceList& l = c->lists[list_id];
   double* arr; int width;
@@ -401,6 +407,7 @@ int hexed_b200_face_list_upload(hexed_b200_ctx* c, int list_id, int kind, const 
 
 int hexed_b200_face_permutation_table(hexed_b200_ctx* c, const int dir[4], int* out)
 {
+  HB_ENTER(c);
   if (dir[0] < 0 || dir[0] >= c->nd || dir[1] < 0 || dir[1] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad direction");
   const int* t = c->h_perm.data() + (size_t)dir_code(dir[0], dir[1], dir[2] != 0, dir[3] != 0)*c->nfq;
   for (int q = 0; q < c->nfq; ++q) out[q] = t[q];
@@ -417,6 +424,7 @@ int hexed_b200_face_permutation_indices(int n_dim, int row_size, const int dir[4
 
 int hexed_b200_face_permutation(hexed_b200_ctx* c, const int dir[4], int restore, double* data)
 {
+  HB_ENTER(c);
   if (dir[0] < 0 || dir[0] >= c->nd || dir[1] < 0 || dir[1] >= c->nd) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad direction");
   const size_t n = (size_t)c->nv*c->nfq;
   HB_CUDA(c, cudaMemcpyAsync(c->d_face_scratch, data, sizeof(double)*n, cudaMemcpyDefault, c->stream));
@@ -430,6 +438,7 @@ int hexed_b200_face_permutation(hexed_b200_ctx* c, const int dir[4], int restore
 
 int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
 {
+  HB_ENTER(c);
   // reference src/kernels_convective.cpp:8-16: Neighbor(car) Neighbor(def) Restrict Local(car) Local(def) Prolong
   int rc;
   if ((rc = launch_neighbor_euler(c, 0))) return rc;
@@ -537,11 +546,12 @@ static int update_loop(hexed_b200_ctx* c, double safety, const ViscousStep* visc
 }
 
 int hexed_b200_update_euler(hexed_b200_ctx* c, double safety, int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced)
-{ return update_loop(c, safety, nullptr, n_cheby, n_steps, use_graph, last_dt, time_advanced); }
+{ HB_ENTER(c); return update_loop(c, safety, nullptr, n_cheby, n_steps, use_graph, last_dt, time_advanced); }
 
 int hexed_b200_update_navier_stokes(hexed_b200_ctx* c, double safety, hexed_b200_transport visc, hexed_b200_transport therm_cond,
                                     int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced)
 {
+  HB_ENTER(c);
   const ViscousStep v{safety, visc, therm_cond}; // max_dt(safety/max_cheby, safety): the diffusive safety is not divided (:849)
   return update_loop(c, safety, &v, n_cheby, n_steps, use_graph, last_dt, time_advanced);
 }
@@ -549,6 +559,7 @@ int hexed_b200_update_navier_stokes(hexed_b200_ctx* c, double safety, hexed_b200
 /* ---- domain decomposition ---- */
 int hexed_b200_set_partition(hexed_b200_ctx* c, int n_cut_car, int n_cut_def, int n_pre_prolong, const int* pre_prolong_ref)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (n_cut_car < 0 || n_cut_car > c->n_car_con || n_cut_def < 0 || n_cut_def > c->n_def_con || n_pre_prolong < 0)
     return fail(c, HEXED_B200_BAD_ARGUMENT, "cut connection counts out of range");
@@ -563,6 +574,7 @@ int hexed_b200_set_partition(hexed_b200_ctx* c, int n_cut_car, int n_cut_def, in
 
 int hexed_b200_face_list_gather(hexed_b200_ctx* c, int list_id, int kind, double* device_dst)
 {
+  HB_ENTER(c);
   if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
   FaceList& l = c->lists[list_id];
   double* arr; int width;
@@ -572,6 +584,7 @@ int hexed_b200_face_list_gather(hexed_b200_ctx* c, int list_id, int kind, double
 
 int hexed_b200_face_list_scatter(hexed_b200_ctx* c, int list_id, int kind, const double* device_src)
 {
+  HB_ENTER(c);
   if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
   FaceList& l = c->lists[list_id];
   double* arr; int width;
@@ -585,6 +598,7 @@ int hexed_b200_face_list_scatter(hexed_b200_ctx* c, int list_id, int kind, const
  *           of the reference sequence (src/kernels_convective.cpp:8-16) */
 int hexed_b200_compute_euler_begin(hexed_b200_ctx* c)
 {
+  HB_ENTER(c);
   int rc;
   if ((rc = launch_neighbor_euler(c, 0, 0, c->n_car_con - c->n_cut_car))) return rc;
   if ((rc = launch_neighbor_euler(c, 1, 0, c->n_def_con - c->n_cut_def))) return rc;
@@ -593,6 +607,7 @@ int hexed_b200_compute_euler_begin(hexed_b200_ctx* c)
 
 int hexed_b200_compute_euler_finish(hexed_b200_ctx* c, hexed_b200_options o)
 {
+  HB_ENTER(c);
   int rc;
   if (c->n_pre_prolong && (rc = launch_prolong(c, 0, c->nv, 0, c->pre_prolong, c->n_pre_prolong))) return rc;
   if ((rc = launch_neighbor_euler(c, 0, c->n_car_con - c->n_cut_car, c->n_cut_car))) return rc;
@@ -605,7 +620,7 @@ int hexed_b200_compute_euler_finish(hexed_b200_ctx* c, hexed_b200_options o)
 }
 
 int hexed_b200_max_dt_euler(hexed_b200_ctx* c, hexed_b200_options, double safety_conv, double, int local_time, double* dt)
-{ return launch_max_dt_euler(c, safety_conv, local_time, dt); }
+{ HB_ENTER(c); return launch_max_dt_euler(c, safety_conv, local_time, dt); }
 
 /* ---- generic PDEs ---- */
 static const GenericOps* generic_ops(int pde)
@@ -680,6 +695,7 @@ static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, con
 /* compute_navier_stokes in three parts around the two halo exchanges of a partitioned mesh (see include/hexed_b200.h) */
 int hexed_b200_compute_navier_stokes_begin(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
   const GenericOps* g = generic_ops(1);
@@ -689,9 +705,12 @@ int hexed_b200_compute_navier_stokes_begin(hexed_b200_ctx* c, hexed_b200_options
   return 0;
 }
 
-int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
-                                            hexed_b200_transport visc, hexed_b200_transport therm_cond)
+/* the middle part in its two halves: everything up to the Prolong of the viscous flux (what the flux boundary conditions read), and
+ * the reconciliation of the interior connections that overlaps the second exchange. hexed_b200_compute_navier_stokes_middle runs both
+ * around the callback; the device group (group.cu) runs them for every rank around ONE call of the host callback. */
+int hexed_b200_compute_navier_stokes_middle_local(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
   const GenericOps* g = generic_ops(1);
@@ -704,18 +723,57 @@ int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* c, hexed_b200_option
   if ((rc = launch_restrict(c, 1, ne, 0))) return rc;
   if ((rc = g->local(c, 0, o, pp, false))) return rc;
   if ((rc = g->local(c, 1, o, pp, false))) return rc;
-  if (!o.i_stage) {
-    if ((rc = launch_prolong(c, 1, ne, 1))) return rc;
-    if (flux_bc) flux_bc(user);
-    // the viscous-flux faces of the cut connections travel now; the interior connections are reconciled meanwhile
-    if ((rc = g->neighbor(c, 0, pp, true, 0, c->n_car_con - c->n_cut_car))) return rc;
-    if ((rc = g->neighbor(c, 1, pp, true, 0, c->n_def_con - c->n_cut_def))) return rc;
-  }
+  if (!o.i_stage && (rc = launch_prolong(c, 1, ne, 1))) return rc;
   return 0;
+}
+
+int hexed_b200_compute_navier_stokes_middle_reconcile(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{
+  HB_ENTER(c);
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (o.i_stage) return 0;
+  const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
+  const GenericOps* g = generic_ops(1);
+  int rc;
+  // the viscous-flux faces of the cut connections travel now; the interior connections are reconciled meanwhile
+  if ((rc = g->neighbor(c, 0, pp, true, 0, c->n_car_con - c->n_cut_car))) return rc;
+  if ((rc = g->neighbor(c, 1, pp, true, 0, c->n_def_con - c->n_cut_def))) return rc;
+  return 0;
+}
+
+int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
+                                            hexed_b200_transport visc, hexed_b200_transport therm_cond)
+{
+  int rc = hexed_b200_compute_navier_stokes_middle_local(c, o, visc, therm_cond);
+  if (rc) return rc;
+  if (!o.i_stage && flux_bc) flux_bc(user);
+  return hexed_b200_compute_navier_stokes_middle_reconcile(c, o, visc, therm_cond);
+}
+
+/* max_dt of any of the five PDEs with the result LEFT ON THE DEVICE at `d_out` (no read-back, no synchronisation): what the device
+ * group reduces across ranks with ncclAllReduce(min). pde: 0 Euler, 1 Navier-Stokes, 2 advection, 3 smooth AV, 4 fix therm admis. */
+int hexed_b200_max_dt_device(hexed_b200_ctx* c, int pde, double sc, double sd, int local_time, hexed_b200_transport visc,
+                             hexed_b200_transport therm_cond, double advect_length, double* d_out)
+{
+  HB_ENTER(c);
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (pde < 0 || pde > 4) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown PDE");
+  double dummy = 0.;
+  if (local_time) { // no reduction: the kernels write time_step_scale and the answer is 1 (include/Spatial.hpp:827)
+    if (pde == 0) return launch_max_dt_euler(c, sc, 1, &dummy);
+    return generic_ops(pde)->max_dt(c, make_params(c, pde, visc, therm_cond, pde == 3 ? 1. : advect_length, pde == 3 ? 1. : 0.), sc, sd, 1, &dummy);
+  }
+  if (!c->n_elem) { HB_CUDA(c, cudaMemsetAsync(d_out, 0x7f, sizeof(double), c->stream)); return 0; }
+  if (pde == 0) return launch_max_dt_euler_device(c, sc, d_out);
+  c->max_dt_device_out = d_out;
+  int rc = generic_ops(pde)->max_dt(c, make_params(c, pde, visc, therm_cond, pde == 3 ? 1. : advect_length, pde == 3 ? 1. : 0.), sc, sd, 0, &dummy);
+  c->max_dt_device_out = nullptr;
+  return rc;
 }
 
 int hexed_b200_compute_navier_stokes_finish(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
   const GenericOps* g = generic_ops(1);
@@ -734,68 +792,76 @@ int hexed_b200_compute_navier_stokes_finish(hexed_b200_ctx* c, hexed_b200_option
 }
 
 int hexed_b200_compute_advection(hexed_b200_ctx* c, hexed_b200_options o, double advect_length)
-{ return convection_stage(c, 2, o, make_params(c, 2, no_transport, no_transport, advect_length, 0.)); }
+{ HB_ENTER(c); return convection_stage(c, 2, o, make_params(c, 2, no_transport, no_transport, advect_length, 0.)); }
 
 int hexed_b200_compute_navier_stokes(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
                                      hexed_b200_transport visc, hexed_b200_transport therm_cond)
-{ return diffusion_stage(c, 1, o, make_params(c, 1, visc, therm_cond, 0., 0.), flux_bc, user); }
+{ HB_ENTER(c); return diffusion_stage(c, 1, o, make_params(c, 1, visc, therm_cond, 0., 0.), flux_bc, user); }
 
 int hexed_b200_compute_smooth_av(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user, double diff_time, double chebyshev_step)
-{ return diffusion_stage(c, 3, o, make_params(c, 3, no_transport, no_transport, diff_time, chebyshev_step), flux_bc, user); }
+{ HB_ENTER(c); return diffusion_stage(c, 3, o, make_params(c, 3, no_transport, no_transport, diff_time, chebyshev_step), flux_bc, user); }
 
 int hexed_b200_compute_fix_therm_admis(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user)
-{ return diffusion_stage(c, 4, o, make_params(c, 4, no_transport, no_transport, 0., 0.), flux_bc, user); }
+{ HB_ENTER(c); return diffusion_stage(c, 4, o, make_params(c, 4, no_transport, no_transport, 0., 0.), flux_bc, user); }
 
 int hexed_b200_max_dt_navier_stokes(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time,
                                     hexed_b200_transport visc, hexed_b200_transport therm_cond, double* dt)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(1)->max_dt(c, make_params(c, 1, visc, therm_cond, 0., 0.), sc, sd, local_time, dt);
 }
 
 int hexed_b200_max_dt_advection(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double advect_length, double* dt)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(2)->max_dt(c, make_params(c, 2, no_transport, no_transport, advect_length, 0.), sc, sd, local_time, dt);
 }
 
 int hexed_b200_max_dt_smooth_av(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double* dt)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(3)->max_dt(c, make_params(c, 3, no_transport, no_transport, 1., 1.), sc, sd, local_time, dt); // src/kernels_max_dt.cpp:20
 }
 
 int hexed_b200_max_dt_fix_therm_admis(hexed_b200_ctx* c, hexed_b200_options, double sc, double sd, int local_time, double* dt)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(4)->max_dt(c, make_params(c, 4, no_transport, no_transport, 0., 0.), sc, sd, local_time, dt);
 }
 
 int hexed_b200_compute_write_face_advection(hexed_b200_ctx* c)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(2)->write_face(c, make_params(c, 2, no_transport, no_transport, 1., 0.)); // src/kernels_convective.cpp:48-51
 }
 
 int hexed_b200_compute_write_face_smooth_av(hexed_b200_ctx* c)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   return generic_ops(3)->write_face(c, make_params(c, 3, no_transport, no_transport, 1., 1.)); // src/kernels_convective.cpp:53-56
 }
 
 int hexed_b200_compute_prolong_advection(hexed_b200_ctx* c)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (!c->face_wide) { int rc = dev_alloc(c, &c->face_wide, (size_t)c->n_face_slot*(c->nd + c->rs)*c->nfq); if (rc) return rc; }
   return launch_prolong(c, 2, c->nd + c->rs, 0); // src/kernels_convective.cpp:33-36
 }
 
-int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* c, double char_speed) { return launch_stab_art_visc(c, char_speed); }
+int hexed_b200_stabilizing_art_visc(hexed_b200_ctx* c, double char_speed) { HB_ENTER(c); return launch_stab_art_visc(c, char_speed); }
 
-int hexed_b200_apply_flux_bcs(hexed_b200_ctx* c) { return launch_flux_bcs(c); }
+int hexed_b200_apply_flux_bcs(hexed_b200_ctx* c) { HB_ENTER(c); return launch_flux_bcs(c); }
 
 int hexed_b200_set_jacobian(hexed_b200_ctx* c, const double* vertex_pos, const double* node_adj)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (c->n_def && !vertex_pos) return fail(c, HEXED_B200_BAD_ARGUMENT, "vertex positions of the deformed elements are required");
   double *d_vert = nullptr, *d_adj = nullptr;
@@ -815,18 +881,20 @@ int hexed_b200_set_jacobian(hexed_b200_ctx* c, const double* vertex_pos, const d
   return rc;
 }
 
-int hexed_b200_calc_shared_normals(hexed_b200_ctx* c) { return launch_shared_normals(c); }
+int hexed_b200_calc_shared_normals(hexed_b200_ctx* c) { HB_ENTER(c); return launch_shared_normals(c); }
 
-int hexed_b200_av_scale_velocity(hexed_b200_ctx* c, int restore) { return launch_av_scale_velocity(c, restore); }
+int hexed_b200_av_scale_velocity(hexed_b200_ctx* c, int restore) { HB_ENTER(c); return launch_av_scale_velocity(c, restore); }
 
 int hexed_b200_av_project_forcing(hexed_b200_ctx* c, const double* node_weights, const double* orthogonal)
 {
+  HB_ENTER(c);
   if (!node_weights || !orthogonal) return fail(c, HEXED_B200_BAD_ARGUMENT, "null operator");
   return launch_av_project_forcing(c, node_weights, orthogonal);
 }
 
 int hexed_b200_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_real, const double* node_weights, double* residual)
 {
+  HB_ENTER(c);
   if (!node_weights || !residual) return fail(c, HEXED_B200_BAD_ARGUMENT, "null argument");
   double sq = 0;
   int rc = launch_av_finish(c, mult, us_max, n_real, node_weights, &sq);
@@ -836,6 +904,7 @@ int hexed_b200_av_finish(hexed_b200_ctx* c, double mult, double us_max, int n_re
 
 int hexed_b200_interp_vertices(hexed_b200_ctx* c, int target, const double* vertex_values, const double* interp)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (!vertex_values || !interp) return fail(c, HEXED_B200_BAD_ARGUMENT, "null argument");
   double *d_vert = nullptr, *d_interp = nullptr;
@@ -850,11 +919,12 @@ int hexed_b200_interp_vertices(hexed_b200_ctx* c, int target, const double* vert
   return rc;
 }
 
-int hexed_b200_av_swap(hexed_b200_ctx* c) { return launch_av_swap(c); }
-int hexed_b200_apply_aux_bcs(hexed_b200_ctx* c, int mode) { return launch_aux_bcs(c, mode); }
+int hexed_b200_av_swap(hexed_b200_ctx* c) { HB_ENTER(c); return launch_av_swap(c); }
+int hexed_b200_apply_aux_bcs(hexed_b200_ctx* c, int mode) { HB_ENTER(c); return launch_aux_bcs(c, mode); }
 
 int hexed_b200_vertex_topology(hexed_b200_ctx* c, const int* elem_vertex, int n_vertex, const int* matchers, int n_match)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (n_vertex < 0 || n_match < 0 || (c->n_elem && !elem_vertex) || (n_match && !matchers)) return fail(c, HEXED_B200_BAD_ARGUMENT, "bad vertex topology");
   const size_t n = (size_t)c->n_elem*c->n_vert;
@@ -878,6 +948,7 @@ int hexed_b200_vertex_topology(hexed_b200_ctx* c, const int* elem_vertex, int n_
 
 int hexed_b200_share_vertex_data(hexed_b200_ctx* c, int which, int op)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (op != 0 && op != 1) return fail(c, HEXED_B200_BAD_ARGUMENT, "op must be 0 (min) or 1 (max)");
   double** arr; size_t item, count;
@@ -889,6 +960,7 @@ int hexed_b200_share_vertex_data(hexed_b200_ctx* c, int which, int op)
 
 int hexed_b200_fix_admis_spread(hexed_b200_ctx* c, const double* interp)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (!interp) return fail(c, HEXED_B200_BAD_ARGUMENT, "null interpolation matrix");
   double* d_interp = nullptr;
@@ -902,12 +974,14 @@ int hexed_b200_fix_admis_spread(hexed_b200_ctx* c, const double* interp)
 
 int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
 {
+  HB_ENTER(c);
   if (!admissible) return fail(c, HEXED_B200_BAD_ARGUMENT, "null result pointer");
   return launch_is_admissible(c, admissible);
 }
 
 int hexed_b200_download_record(hexed_b200_ctx* c, int* dst, int first_elem, int n_elem)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (first_elem < 0 || n_elem < 0 || first_elem + n_elem > c->n_elem) return fail(c, HEXED_B200_BAD_ARGUMENT, "element range out of bounds");
   if (!c->record) return fail(c, HEXED_B200_BAD_ARGUMENT, "no record yet: call hexed_b200_is_admissible first");
@@ -920,6 +994,7 @@ int hexed_b200_download_record(hexed_b200_ctx* c, int* dst, int first_elem, int 
 int hexed_b200_pde_kernel(hexed_b200_ctx* c, int pde, int which, int deformed, hexed_b200_options o,
                           hexed_b200_transport visc, hexed_b200_transport therm_cond, double p0, double p1)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   const GenericOps* g = generic_ops(pde);
   if (!g) return fail(c, HEXED_B200_BAD_ARGUMENT, "pde must be 1 (Navier-Stokes), 2 (advection), 3 (smooth AV) or 4 (fix therm admis)");
@@ -933,26 +1008,29 @@ int hexed_b200_pde_kernel(hexed_b200_ctx* c, int pde, int which, int deformed, h
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown kernel id");
 }
 
-int hexed_b200_compute_write_face(hexed_b200_ctx* c) { return launch_write_face(c); }
+int hexed_b200_compute_write_face(hexed_b200_ctx* c) { HB_ENTER(c); return launch_write_face(c); }
 
 int hexed_b200_compute_prolong(hexed_b200_ctx* c, int scale, int offset)
 {
+  HB_ENTER(c);
   if (offset && !c->face_ldg) { int rc = dev_alloc(c, &c->face_ldg, (size_t)c->n_face_slot*c->nv*c->nfq); if (rc) return rc; }
   return launch_prolong(c, offset ? 1 : 0, c->nv, scale);
 }
 
 int hexed_b200_compute_restrict(hexed_b200_ctx* c, int scale, int offset)
 {
+  HB_ENTER(c);
   if (offset && !c->face_ldg) { int rc = dev_alloc(c, &c->face_ldg, (size_t)c->n_face_slot*c->nv*c->nfq); if (rc) return rc; }
   return launch_restrict(c, offset ? 1 : 0, c->nv, scale);
 }
 
-int hexed_b200_neighbor_euler(hexed_b200_ctx* c, int deformed) { return launch_neighbor_euler(c, deformed); }
-int hexed_b200_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o) { return launch_local_euler(c, deformed, o); }
+int hexed_b200_neighbor_euler(hexed_b200_ctx* c, int deformed) { HB_ENTER(c); return launch_neighbor_euler(c, deformed); }
+int hexed_b200_local_euler(hexed_b200_ctx* c, int deformed, hexed_b200_options o) { HB_ENTER(c); return launch_local_euler(c, deformed, o); }
 
 int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, const int* ghost, const int* normal,
                          const double* params, int n_params, int* bc_id)
 {
+  HB_ENTER(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (kind < 0 || kind > HEXED_B200_BC_RIEMANN_INVARIANTS) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary condition kind");
   if ((kind == HEXED_B200_BC_FREESTREAM || kind == HEXED_B200_BC_RIEMANN_INVARIANTS) && n_params != c->nv)
@@ -987,12 +1065,13 @@ int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, 
   return 0;
 }
 
-int hexed_b200_apply_state_bcs(hexed_b200_ctx* c) { return launch_bcs(c); }
+int hexed_b200_apply_state_bcs(hexed_b200_ctx* c) { HB_ENTER(c); return launch_bcs(c); }
 
 int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled != 0; return 0; }
 
 int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
 {
+  HB_ENTER(c);
   if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; c->pipe_lean = value != 2; c->pipe_lean4 = value == 3; return 0; }
   if (option == HEXED_B200_OPT_CFL_CACHE) { c->use_cfl_cache = value != 0; invalidate_cfl_cache(c); return 0; }
   if (option == HEXED_B200_OPT_FUSED_ADMIS) { // a change of the setting forgets the bits; setting it again does not
@@ -1004,6 +1083,7 @@ int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
 
 int hexed_b200_kernel_stats(hexed_b200_ctx* c, hexed_b200_kernel_stat* out, int capacity, int* n_out)
 {
+  HB_ENTER(c);
   int n = 0;
   for (int i = 0; i < ST_COUNT && n < capacity; ++i, ++n) {
     out[n].name = c->stats[i].name; out[n].deformed = c->stats[i].deformed; out[n].work_units = c->stats[i].work_units;
@@ -1015,6 +1095,7 @@ int hexed_b200_kernel_stats(hexed_b200_ctx* c, hexed_b200_kernel_stat* out, int 
 
 int hexed_b200_reset_stats(hexed_b200_ctx* c)
 {
+  HB_ENTER(c);
   for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].work_units = 0; c->stats[i].launches = 0; c->stats[i].seconds = 0; }
   return 0;
 }

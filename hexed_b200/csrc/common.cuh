@@ -126,6 +126,9 @@ __host__ __device__ inline int dir_code(int d0, int d1, int s0, int s1) { return
 int fail(hexed_b200_ctx* c, int code, const std::string& msg);
 int check(hexed_b200_ctx* c, cudaError_t e, const char* what);
 #define HB_CUDA(c, call) do { int hb_rc_ = hb::check(c, (call), #call); if (hb_rc_) return hb_rc_; } while (0)
+/* every C ABI entry point makes its context's device current: one host thread may drive several contexts on different devices
+ * (hexed_b200_group_*, the single-process multi-GPU path behind the C++ adapter) */
+#define HB_ENTER(c) do { cudaSetDevice((c)->device); } while (0)
 
 struct StatScope
 {

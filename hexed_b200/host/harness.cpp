@@ -432,3 +432,78 @@ int hbh_face_permutation(int nd, int rs, const int* dir, int restore, double* da
 }
 
 }
+
+// ---- the C++ partitioner (partition.hpp), exposed table by table so that tests can compare it with hexed_b200/partition.py ----
+#include "partition.hpp"
+
+namespace
+{
+struct Partition_result {std::vector<hexed_b200::Rank_mesh> parts;};
+int give(const std::vector<int>& v, int* out) {if (out) std::copy(v.begin(), v.end(), out); return int(v.size());}
+}
+
+extern "C" {
+
+void* hbp_partition(int n_dim, int n_car, int n_def, int n_face_slot, int n_normal_slot, const int* car_con, int n_cc,
+                    const int* def_con, int n_dc, const int* ref_face, int n_rf, const int* boundary_con, int n_bc,
+                    const int* owner, int n_parts)
+{
+  try {
+    hexed_b200::Mesh_graph g;
+    g.n_dim = n_dim; g.n_car = n_car; g.n_def = n_def; g.n_face_slot = n_face_slot; g.n_normal_slot = n_normal_slot;
+    g.car_con.assign(car_con, car_con + size_t(n_cc)*3); g.def_con.assign(def_con, def_con + size_t(n_dc)*7);
+    g.ref_face.assign(ref_face, ref_face + size_t(n_rf)*7); g.boundary_con.assign(boundary_con, boundary_con + n_bc);
+    auto* r = new Partition_result;
+    r->parts = hexed_b200::partition(g, std::vector<int>(owner, owner + n_car + n_def), n_parts);
+    return r;
+  } catch (...) {return nullptr;}
+}
+
+void hbp_free(void* h) {delete static_cast<Partition_result*>(h);}
+
+/* what: 0 car_con, 1 def_con, 2 ref_face, 3 global_elem, 4 global_face, 5 global_normal, 6 pre_prolong, 7 peers,
+ * 8 {n_car, n_def, n_cut_car, n_cut_def, n_face_slot, n_normal_slot}, 9 boundary_con (local def_con rows), 10 face_owned, 11 global_def_con,
+ * 100 + k send slots of peer k, 200 + k receive slots of peer k. Returns the number of ints; `out` may be null. */
+int hbp_query(void* h, int rank, int what, int* out)
+{
+  auto& m = static_cast<Partition_result*>(h)->parts.at(rank);
+  switch (what) {
+    case 0: return give(m.graph.car_con, out);
+    case 1: return give(m.graph.def_con, out);
+    case 2: return give(m.graph.ref_face, out);
+    case 3: return give(m.global_elem, out);
+    case 4: return give(m.global_face, out);
+    case 5: return give(m.global_normal, out);
+    case 6: return give(m.pre_prolong, out);
+    case 7: return give(m.peers, out);
+    case 8: return give({m.graph.n_car, m.graph.n_def, m.n_cut_car, m.n_cut_def, m.graph.n_face_slot, m.graph.n_normal_slot}, out);
+    case 9: return give(m.graph.boundary_con, out);
+    case 10: return give(std::vector<int>(m.face_owned.begin(), m.face_owned.end()), out);
+    case 11: return give(m.global_def_con, out);
+  }
+  if (what >= 100 && what < 100 + int(m.peers.size())) return give(m.send_slots[what - 100], out);
+  if (what >= 200 && what < 200 + int(m.peers.size())) return give(m.recv_slots[what - 200], out);
+  return -1;
+}
+
+int hbp_owners_by_graph(int n_dim, int n_car, int n_def, const int* car_con, int n_cc, const int* def_con, int n_dc, const int* ref_face, int n_rf,
+                        int n_parts, int* owner_out)
+{
+  hexed_b200::Mesh_graph g;
+  g.n_dim = n_dim; g.n_car = n_car; g.n_def = n_def;
+  g.car_con.assign(car_con, car_con + size_t(n_cc)*3); g.def_con.assign(def_con, def_con + size_t(n_dc)*7); g.ref_face.assign(ref_face, ref_face + size_t(n_rf)*7);
+  auto o = hexed_b200::owners_by_graph(g, n_parts);
+  std::copy(o.begin(), o.end(), owner_out);
+  return 0;
+}
+
+int hbp_owners_by_morton(int n_dim, int n_car, int n_elem, const int* coords, int n_parts, int* owner_out)
+{
+  std::vector<std::array<int, 3>> c(n_elem, std::array<int, 3>{0, 0, 0});
+  for (int e = 0; e < n_elem; ++e) for (int d = 0; d < n_dim; ++d) c[e][d] = coords[e*n_dim + d];
+  auto o = hexed_b200::owners_by_morton(c, n_dim, n_car, n_parts);
+  std::copy(o.begin(), o.end(), owner_out);
+  return 0;
+}
+
+}

@@ -70,6 +70,21 @@ SIGNATURES = {
     "hexed_b200_compute_euler_finish": [C.c_void_p, Options],
     "hexed_b200_compute_navier_stokes_begin": [C.c_void_p, Options, Transport, Transport],
     "hexed_b200_compute_navier_stokes_middle": [C.c_void_p, Options, C.c_void_p, C.c_void_p, Transport, Transport],
+    "hexed_b200_compute_navier_stokes_middle_local": [C.c_void_p, Options, Transport, Transport],
+    "hexed_b200_compute_navier_stokes_middle_reconcile": [C.c_void_p, Options, Transport, Transport],
+    "hexed_b200_max_dt_device": [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, Transport, Transport, C.c_double, C.c_void_p],
+    "hexed_b200_group_create": [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)],
+    "hexed_b200_group_destroy": [C.c_void_p],
+    "hexed_b200_group_last_error": [C.c_void_p],
+    "hexed_b200_group_size": [C.c_void_p],
+    "hexed_b200_group_ctx": [C.c_void_p, C.c_int],
+    "hexed_b200_group_info": [C.c_void_p, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
+    "hexed_b200_group_set_halo": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, ip, ip],
+    "hexed_b200_group_exchange": [C.c_void_p, C.c_int],
+    "hexed_b200_group_synchronize": [C.c_void_p],
+    "hexed_b200_group_compute_euler": [C.c_void_p, Options],
+    "hexed_b200_group_compute_navier_stokes": [C.c_void_p, Options, C.c_void_p, C.c_void_p, Transport, Transport],
+    "hexed_b200_group_max_dt": [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, Transport, Transport, C.c_double, dp],
     "hexed_b200_compute_navier_stokes_finish": [C.c_void_p, Options, Transport, Transport],
     "hexed_b200_compute_euler": [C.c_void_p, Options],
     "hexed_b200_max_dt_euler": [C.c_void_p, Options, C.c_double, C.c_double, C.c_int, dp],
@@ -116,7 +131,8 @@ SIGNATURES = {
     "hexed_b200_reset_stats": [C.c_void_p],
     "hexed_b200_launch_count": [C.c_void_p],
 }
-_RESTYPES = {"hexed_b200_last_error": C.c_char_p, "hexed_b200_launch_count": C.c_longlong}
+_RESTYPES = {"hexed_b200_last_error": C.c_char_p, "hexed_b200_launch_count": C.c_longlong,
+             "hexed_b200_group_last_error": C.c_char_p, "hexed_b200_group_ctx": C.c_void_p}
 
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p)

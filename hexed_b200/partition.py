@@ -73,10 +73,11 @@ def partition_mesh(mesh, part, n_parts):
     ref_ranks = [set() for _ in range(len(mesh.ref_face))]
     for r, row in enumerate(mesh.ref_face):
         ref_ranks[r].add(owner_of_slot(int(row[0])))
-    for con in mesh.def_con:
-        for side in (0, 1):
-            if int(con[side]) in mortar_ref:
-                ref_ranks[mortar_ref[int(con[side])]].add(owner_of_slot(int(con[1 - side])))
+    for table in (mesh.car_con, mesh.def_con):  # Cartesian hanging faces keep their fine connections in car_con
+        for con in table:
+            for side in (0, 1):
+                if int(con[side]) in mortar_ref:
+                    ref_ranks[mortar_ref[int(con[side])]].add(owner_of_slot(int(con[1 - side])))
     bc_of_con = {}
     for ib, bc in enumerate(mesh.bcs):
         for k, ci in enumerate(bc["con_index"]):
@@ -116,36 +117,32 @@ def partition_mesh(mesh, part, n_parts):
 
         car_int, car_cut, def_int, def_cut = [], [], [], []
         bc_local = [dict(kind=bc["kind"], params=bc.get("params"), inside_slot=[], ghost_slot=[], normal_slot=[], con_index=[]) for bc in mesh.bcs]
+        def classify(s0, s1):
+            """(kept on rank p, must wait for the exchange) for a connection between face slots s0 and s1"""
+            r = mortar_ref.get(s0, mortar_ref.get(s1))
+            if r is not None:
+                # fine connection of a hanging-node face: kept where the fine element is local, or where the coarse element is local;
+                # on the fine element's rank the mortar face is only valid after the coarse face arrived and was prolonged locally
+                fine_owner = owner_of_slot(s1 if s0 in mortar_ref else s0)
+                coarse_owner = owner_of_slot(int(mesh.ref_face[r][0]))
+                return p in (fine_owner, coarse_owner), (fine_owner != p or coarse_owner != p)
+            o0, o1 = owner_of_slot(s0), owner_of_slot(s1)
+            if o0 < 0 or o1 < 0:
+                return (o1 if o0 < 0 else o0) == p, False  # boundary connection: belongs to its element's rank
+            return p in (o0, o1), o0 != o1
+
         for con in mesh.car_con:
-            o0, o1 = owner_of_slot(int(con[0])), owner_of_slot(int(con[1]))
-            if p not in (o0, o1):
+            keep, cut = classify(int(con[0]), int(con[1]))
+            if not keep:
                 continue
             row = [lslot(con[0]), lslot(con[1]), int(con[2])]
-            (car_int if o0 == o1 else car_cut).append(row)
+            (car_cut if cut else car_int).append(row)
         def_rows = []  # (is_cut, row, bc tag)
         for ci, con in enumerate(mesh.def_con):
             s0, s1 = int(con[0]), int(con[1])
-            owners = []
-            for side, s in ((0, s0), (1, s1)):
-                if s < n_elem_slots:
-                    owners.append(owner_of_slot(s))
-            r = mortar_ref.get(s0, mortar_ref.get(s1))
-            if r is not None:
-                # fine connection of a hanging-node face: kept where the fine element is local, or where the coarse element is local
-                coarse_owner = owner_of_slot(int(mesh.ref_face[r][0]))
-                fine_owner = owners[0]
-                if p != fine_owner and p != coarse_owner:
-                    continue
-                # on the fine element's rank the mortar face is only valid after the coarse face arrived and was prolonged locally
-                cut = fine_owner != p or coarse_owner != p
-            elif len(owners) == 1:
-                if owners[0] != p:
-                    continue  # boundary connection of a remote element
-                cut = False
-            else:
-                if p not in owners:
-                    continue
-                cut = owners[0] != owners[1]
+            keep, cut = classify(s0, s1)
+            if not keep:
+                continue
             row = [lslot(s0), lslot(s1), int(con[2]), int(con[3]), int(con[4]), int(con[5]), lnormal(con[6])]
             def_rows.append((cut, row, bc_of_con.get(ci)))
         def_rows.sort(key=lambda x: x[0])  # stable: interior first, cut last

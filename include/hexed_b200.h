@@ -301,6 +301,40 @@ int hexed_b200_compute_navier_stokes_middle(hexed_b200_ctx* ctx, hexed_b200_opti
                                             hexed_b200_transport visc, hexed_b200_transport therm_cond);
 int hexed_b200_compute_navier_stokes_finish(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_transport visc, hexed_b200_transport therm_cond);
 
+/* the two halves of `middle` (before / after the flux_bc callback), and max_dt of any PDE with the result left on the device at
+ * `device_out` (pde: 0 Euler, 1 Navier-Stokes, 2 advection, 3 smooth AV, 4 fix therm admis); used by the device group below */
+int hexed_b200_compute_navier_stokes_middle_local(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_transport visc, hexed_b200_transport therm_cond);
+int hexed_b200_compute_navier_stokes_middle_reconcile(hexed_b200_ctx* ctx, hexed_b200_options opts, hexed_b200_transport visc, hexed_b200_transport therm_cond);
+int hexed_b200_max_dt_device(hexed_b200_ctx* ctx, int pde, double convective_safety, double diffusive_safety, int local_time,
+                             hexed_b200_transport visc, hexed_b200_transport therm_cond, double advect_length, double* device_out);
+
+/* ---- device group: ONE mesh on several GPUs driven by one host thread (what the C++ adapter uses when the Solver process owns more
+ * than one device; the reference hands over a single Kernel_mesh, include/Kernel_mesh.hpp:14-25, so the split happens below the
+ * drop-in boundary). The caller partitions the flattened tables (hexed_b200::partition in hexed_b200/host/partition.hpp), creates one
+ * context per device, uploads each rank's mesh + hexed_b200_set_partition, registers each rank's halo and then calls the group
+ * versions of the stage drivers. Transport: NCCL (bound at run time from libnccl.so.2; ncclCommInitAll over the contexts' devices),
+ * ncclSend/ncclRecv of the cut faces on a communication stream per rank, overlapped with the interior Neighbor kernels, and
+ * ncclAllReduce(min) of the time step. Results are those of the undivided mesh (same kernels, same operands; both owners of a cut
+ * connection evaluate it). ---- */
+typedef struct hexed_b200_group hexed_b200_group;
+int hexed_b200_group_create(hexed_b200_group** group, int n, hexed_b200_ctx* const* contexts); /* contexts on n distinct devices */
+int hexed_b200_group_destroy(hexed_b200_group* group);                                       /* the contexts stay alive */
+const char* hexed_b200_group_last_error(const hexed_b200_group* group);                      /* group may be NULL: error of the last failed create */
+int hexed_b200_group_size(const hexed_b200_group* group);
+hexed_b200_ctx* hexed_b200_group_ctx(hexed_b200_group* group, int rank);
+int hexed_b200_group_info(const hexed_b200_group* group, int* nccl_version, long long* exchanges, long long* bytes_sent);
+/* rank's halo: for each of its n_peers peers, the n_send[i] local face slots it sends (concatenated in send_slots, ordered as the peer's
+ * receive list) and the n_recv[i] halo slots it fills (recv_slots). Call after the rank's hexed_b200_mesh_create. */
+int hexed_b200_group_set_halo(hexed_b200_group* group, int rank, int n_peers, const int* peers, const int* n_send, const int* send_slots,
+                              const int* n_recv, const int* recv_slots);
+int hexed_b200_group_exchange(hexed_b200_group* group, int kind); /* one face kind, e.g. after compute_write_face at initialisation */
+int hexed_b200_group_synchronize(hexed_b200_group* group);
+int hexed_b200_group_compute_euler(hexed_b200_group* group, hexed_b200_options opts);
+int hexed_b200_group_compute_navier_stokes(hexed_b200_group* group, hexed_b200_options opts, hexed_b200_callback flux_bc, void* user,
+                                           hexed_b200_transport visc, hexed_b200_transport therm_cond);
+int hexed_b200_group_max_dt(hexed_b200_group* group, int pde, double convective_safety, double diffusive_safety, int local_time,
+                            hexed_b200_transport visc, hexed_b200_transport therm_cond, double advect_length, double* dt);
+
 /* ---- profiling side-contract ---- */
 int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
 /* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined

@@ -72,6 +72,18 @@ def _make_case(kind, rng):
         basis = hb.gauss_legendre(2)
         m = M.soup_mesh(3, 2, rng, n_car=8, n_def=14, n_ref=8, with_ldg=False)
         M.random_flow_state(m, rng)
+    elif kind.startswith("refined_box"):
+        # C5 class: Cartesian hanging-node faces as `Refined_connection<Element>` builds them, cut by the partition
+        nd = 3 if kind.endswith("3d") else 2
+        basis = hb.gauss_legendre(3)
+        n = 3 if nd == 3 else 5
+        refine = np.zeros((n,)*nd, bool)
+        refine[(1,)*nd] = True
+        refine[(n - 1,)*nd] = True
+        if nd == 2:
+            refine[2, 3] = refine[3, 3] = True
+        m = M.refined_box_mesh(nd, 3, n, basis, refine, bc_kind=M.BC_COPY)
+        M.random_flow_state(m, rng, mach=0.2)
     elif kind == "box_def":
         basis = hb.gauss_legendre(3)
         m = M.box_mesh(3, 3, 4, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
@@ -97,11 +109,16 @@ def reference_run(oracle, basis, m, n_steps, safety=0.3):
     return ref, dts
 
 
-@pytest.mark.parametrize("kind,n_parts", [("soup2d", 2), ("soup2d", 3), ("soup3d", 4), ("box_def", 2), ("box_def", 8), ("box_car", 4)])
+@pytest.mark.parametrize("kind,n_parts", [("soup2d", 2), ("soup2d", 3), ("soup3d", 4), ("box_def", 2), ("box_def", 8), ("box_car", 4),
+                                          ("refined_box2d", 2), ("refined_box2d", 5), ("refined_box3d", 3)])
 def test_partitioned_oracle_matches_undivided(oracle, kind, n_parts):
     rng = np.random.default_rng(42)
     basis, m = make_case(kind, rng)
-    if kind.startswith("box"):
+    if kind.startswith("refined_box"):
+        oracle.compute_write_face(basis, m)
+        oracle.compute_prolong(basis, m)
+        part = rng.integers(0, n_parts, m.n_elem)
+    elif kind.startswith("box"):
         oracle.compute_write_face(basis, m)
         part = P.split_by_curve(P.morton_keys(m.elem_index), n_parts)
     else:
