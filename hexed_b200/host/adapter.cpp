@@ -7,6 +7,7 @@
  * library finds no CUDA device every entry point throws.
  */
 #include "adapter.hpp"
+#include "partition.hpp"
 #include "../../include/hexed_b200.h"
 
 #include <algorithm>
@@ -105,49 +106,96 @@ hexed_b200_transport transport(const hexed::Transport_model& t)
   return out;
 }
 
-struct Mirror
+//! one device's share of the mesh: a context plus the host addresses behind its element, face and normal slots
+struct Rank
 {
   hexed_b200_ctx* ctx = nullptr;
-  int n_dim = 0, row_size = 0;
-  Flat_tables tab;
-  bool have_mesh = false;
-  std::vector<const void*> fingerprint;
-  int boundary_list = -1; // face list id of the boundary connections' faces
+  int device = 0;
+  int n_car = 0, n_def = 0, n_face_slot = 0, n_normal_slot = 0;
+  std::vector<hexed::Kernel_element*> elem; // car then def, local order
+  std::vector<int> global_elem;             // local element -> position in Kernel_mesh::elems
+  std::vector<double*> face_ptr;            // local face slot -> host storage (halo slots point at the remote element's face)
+  std::vector<char> face_owned;             // this rank's copy is the one written back to the host
+  std::vector<double*> normal_ptr;
+  std::vector<int> def_con;                 // local [n][7]
+  std::vector<int> boundary_con;            // local def_con rows that are boundary connections
+  int boundary_list = -1;                   // face list id of the boundary connections' faces
   std::vector<int> boundary_slots;
   std::vector<double> staging;
+};
+
+struct Mirror
+{
+  int n_dim = 0, row_size = 0;
+  std::vector<Rank> ranks;
+  hexed_b200_group* group = nullptr; // more than one rank: halo exchange + allreduce (include/hexed_b200.h "device group")
+  Flat_tables tab;                   // the undivided tables
+  std::vector<int> owner;            // element -> rank
+  bool have_mesh = false;
+  bool explicitly_invalidated = false;
+  std::vector<const void*> fingerprint;
+  std::vector<std::array<int, 3>> coords; // optional integer element coordinates for the Morton split (set_element_coordinates)
+  std::vector<double> packed_basis;
   bool device_bcs_ran = false; // set by apply_state_bcs / apply_flux_bcs; lets the flux_bc thunk see what its callback did
-  ~Mirror() {if (ctx) hexed_b200_destroy(ctx);}
+  hexed_b200_ctx* ctx0() {return ranks.empty() ? nullptr : ranks[0].ctx;}
+  void destroy_device_side()
+  {
+    if (group) hexed_b200_group_destroy(group);
+    group = nullptr;
+    for (Rank& r : ranks) if (r.ctx) hexed_b200_destroy(r.ctx);
+    ranks.clear();
+  }
+  ~Mirror() {destroy_device_side();}
 };
 
 Sync_mode g_mode = sync_every_call;
-int g_device = 0;
-std::map<std::pair<int, int>, std::unique_ptr<Mirror>> g_mirrors;
+std::vector<int> g_devices {0};
+//! keyed by the identity of the mesh (the address of its `elems` view, which belongs to one Solver / Accessible_mesh) and its shape
+std::map<std::tuple<const void*, int, int>, std::unique_ptr<Mirror>> g_mirrors;
 
-void check(Mirror* m, int rc)
+void check(Mirror* m, int rc, hexed_b200_ctx* ctx = nullptr)
 {
   if (!rc) return;
   if (rc == HEXED_B200_INVALID_KERNEL) throw std::runtime_error("demand for invalid kernel"); // include/kernel_factory.hpp:114-116
   if (rc == HEXED_B200_NOT_FINITE) throw std::runtime_error("state is not finite"); // HEXED_ASSERT of src/thermo.cpp:14
-  throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_last_error(m ? m->ctx : nullptr));
+  if (!ctx && m) ctx = m->ctx0();
+  throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_last_error(ctx));
 }
 
-std::vector<const void*> make_fingerprint(Kernel_mesh& km)
+void check_group(Mirror& m, int rc)
+{
+  if (!rc) return;
+  if (rc == HEXED_B200_INVALID_KERNEL) throw std::runtime_error("demand for invalid kernel");
+  if (rc == HEXED_B200_NOT_FINITE) throw std::runtime_error("state is not finite");
+  throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_group_last_error(m.group));
+}
+
+/* What identifies a mesh epoch. `thorough` (sync_every_call mode, where a walk over the views is small against the PCIe traffic of the
+ * call) folds EVERY element's and connection's storage addresses into a rolling hash, so that a same-size mesh edit that moves any
+ * object is noticed; resident mode samples three objects per view and relies on invalidate() after mesh changes (adapter.hpp). */
+std::vector<const void*> make_fingerprint(Kernel_mesh& km, bool thorough)
 {
   std::vector<const void*> f;
-  auto num = [&](int n) {f.push_back(reinterpret_cast<const void*>(size_t(n)));};
+  auto num = [&](size_t n) {f.push_back(reinterpret_cast<const void*>(n));};
   num(km.n_dim); num(km.row_size);
   f.push_back(&km.basis);
+  size_t hash = 1469598103934665603ull;
+  auto mix = [&](const void* p) {hash = (hash ^ reinterpret_cast<size_t>(p))*1099511628211ull;};
   auto elems = [&](hexed::Sequence<hexed::Kernel_element&>& s) {
     int n = s.size(); num(n);
     for (int i : {0, n/2, n - 1}) if (n) {auto& e = s[i]; f.push_back(e.state()); f.push_back(e.face(0, false));}
+    if (thorough) for (int i = 0; i < n; ++i) {auto& e = s[i]; mix(&e); mix(e.state()); mix(e.face(0, false));}
   };
   auto cons = [&](hexed::Sequence<hexed::Kernel_connection&>& s) {
     int n = s.size(); num(n);
     for (int i : {0, n/2, n - 1}) if (n) {auto& c = s[i]; f.push_back(c.state(0, false)); f.push_back(c.state(1, false));}
+    if (thorough) for (int i = 0; i < n; ++i) {auto& c = s[i]; mix(c.state(0, false)); mix(c.state(1, false));}
   };
   elems(km.car_elems); elems(km.def_elems); cons(km.car_cons); cons(km.def_cons);
   int nr = km.ref_faces.size(); num(nr);
   for (int i : {0, nr/2, nr - 1}) if (nr) f.push_back(km.ref_faces[i].coarse);
+  if (thorough) for (int i = 0; i < nr; ++i) {auto& r = km.ref_faces[i]; mix(r.coarse); for (double* p : r.fine) mix(p);}
+  num(thorough ? hash : 0);
   return f;
 }
 
@@ -264,165 +312,255 @@ std::vector<Slot_range> slot_ranges(const Mirror& m, unsigned groups)
   return merged;
 }
 
-void move_elements(Mirror& m, unsigned groups, bool up)
+void move_elements(Mirror& m, Rank& k, unsigned groups, bool up)
 {
   const int nq = ipow(m.row_size, m.n_dim);
-  const int ne = int(m.tab.elem.size());
+  const int ne = int(k.elem.size());
   const int chunk = 8192;
   for (auto range : slot_ranges(m, groups)) {
     const size_t per_elem = size_t(range.n)*nq;
-    m.staging.resize(per_elem*std::min(chunk, std::max(ne, 1)));
+    k.staging.resize(per_elem*std::min(chunk, std::max(ne, 1)));
     for (int first = 0; first < ne; first += chunk) {
       const int n = std::min(chunk, ne - first);
       if (up) {
         #pragma omp parallel for
-        for (int i = 0; i < n; ++i) std::memcpy(m.staging.data() + per_elem*i, m.tab.elem[first + i]->state() + size_t(range.first)*nq, per_elem*sizeof(double));
-        check(&m, hexed_b200_upload_elem_slots(m.ctx, m.staging.data(), per_elem, range.first, range.n, first, n));
+        for (int i = 0; i < n; ++i) std::memcpy(k.staging.data() + per_elem*i, k.elem[first + i]->state() + size_t(range.first)*nq, per_elem*sizeof(double));
+        check(&m, hexed_b200_upload_elem_slots(k.ctx, k.staging.data(), per_elem, range.first, range.n, first, n), k.ctx);
       } else {
-        check(&m, hexed_b200_download_elem_slots(m.ctx, m.staging.data(), per_elem, range.first, range.n, first, n));
+        check(&m, hexed_b200_download_elem_slots(k.ctx, k.staging.data(), per_elem, range.first, range.n, first, n), k.ctx);
         #pragma omp parallel for
-        for (int i = 0; i < n; ++i) std::memcpy(m.tab.elem[first + i]->state() + size_t(range.first)*nq, m.staging.data() + per_elem*i, per_elem*sizeof(double));
+        for (int i = 0; i < n; ++i) std::memcpy(k.elem[first + i]->state() + size_t(range.first)*nq, k.staging.data() + per_elem*i, per_elem*sizeof(double));
       }
     }
   }
 }
 
-//! one face array (`which` = HEXED_B200_FACE_STATE / _LDG / _WIDE) for all slots; `offset` doubles into each host face
-void move_face_array(Mirror& m, int which, size_t width, size_t offset, bool up)
+//! one face array (`which` = HEXED_B200_FACE_STATE / _LDG / _WIDE) for all slots; `offset` doubles into each host face.
+//! Downloads write only the copies this rank owns (halo slots and replicated connection faces belong to another rank).
+void move_face_array(Mirror& m, Rank& k, int which, size_t width, size_t offset, bool up)
 {
-  const int ns = m.tab.n_face_slot;
+  const int ns = k.n_face_slot;
   const int chunk = 1 << 16;
-  m.staging.resize(width*std::min(chunk, std::max(ns, 1)));
+  k.staging.resize(width*std::min(chunk, std::max(ns, 1)));
   for (int first = 0; first < ns; first += chunk) {
     const int n = std::min(chunk, ns - first);
     if (up) {
       #pragma omp parallel for
       for (int i = 0; i < n; ++i) {
-        double* p = m.tab.face_ptr[first + i];
-        if (p) std::memcpy(m.staging.data() + width*i, p + offset, width*sizeof(double));
-        else std::memset(m.staging.data() + width*i, 0, width*sizeof(double));
+        double* p = k.face_ptr[first + i];
+        if (p) std::memcpy(k.staging.data() + width*i, p + offset, width*sizeof(double));
+        else std::memset(k.staging.data() + width*i, 0, width*sizeof(double));
       }
-      check(&m, hexed_b200_upload(m.ctx, which, m.staging.data(), first, n));
+      check(&m, hexed_b200_upload(k.ctx, which, k.staging.data(), first, n), k.ctx);
     } else {
-      check(&m, hexed_b200_download(m.ctx, which, m.staging.data(), first, n));
+      check(&m, hexed_b200_download(k.ctx, which, k.staging.data(), first, n), k.ctx);
       #pragma omp parallel for
       for (int i = 0; i < n; ++i) {
-        double* p = m.tab.face_ptr[first + i];
-        if (p) std::memcpy(p + offset, m.staging.data() + width*i, width*sizeof(double));
+        double* p = k.face_ptr[first + i];
+        if (p && k.face_owned[first + i]) std::memcpy(p + offset, k.staging.data() + width*i, width*sizeof(double));
       }
     }
   }
 }
 
-void move_faces(Mirror& m, unsigned groups, bool up)
+void move_faces(Mirror& m, Rank& k, unsigned groups, bool up)
 {
   const int nfq = ipow(m.row_size, m.n_dim - 1), nv = m.n_dim + 2;
   if (groups & faces) { // `face(i, is_ldg)` = storage + is_ldg*n_var*nfq (src/Element.cpp:189, include/connection.hpp:66)
-    move_face_array(m, HEXED_B200_FACE_STATE, size_t(nv)*nfq, 0, up);
-    move_face_array(m, HEXED_B200_FACE_LDG, size_t(nv)*nfq, size_t(nv)*nfq, up);
+    move_face_array(m, k, HEXED_B200_FACE_STATE, size_t(nv)*nfq, 0, up);
+    move_face_array(m, k, HEXED_B200_FACE_LDG, size_t(nv)*nfq, size_t(nv)*nfq, up);
   }
-  if (groups & faces_wide) move_face_array(m, HEXED_B200_FACE_WIDE, size_t(m.n_dim + m.row_size)*nfq, 0, up);
+  if (groups & faces_wide) move_face_array(m, k, HEXED_B200_FACE_WIDE, size_t(m.n_dim + m.row_size)*nfq, 0, up);
 }
 
-void upload_geometry(Mirror& m)
+void upload_vertex_tss(Mirror& m, Rank& k)
+{ // vertex_time_step_scale is rewritten by Solver::set_local_tss between calls; it is tiny
+  const int n_vert = ipow(2, m.n_dim), ne = int(k.elem.size());
+  std::vector<double> buf(size_t(ne)*n_vert);
+  for (int e = 0; e < ne; ++e) for (int v = 0; v < n_vert; ++v) buf[size_t(e)*n_vert + v] = k.elem[e]->vertex_time_step_scale(v);
+  check(&m, hexed_b200_upload(k.ctx, HEXED_B200_VERTEX_TSS, buf.data(), 0, ne), k.ctx);
+}
+
+void upload_geometry(Mirror& m, Rank& k)
 {
-  const int nd = m.n_dim, nq = ipow(m.row_size, nd), nfq = nq/m.row_size, nf = 2*nd, n_vert = ipow(2, nd);
-  const int ne = int(m.tab.elem.size()), n_def = m.tab.n_def, n_car = m.tab.n_car;
+  const int nd = m.n_dim, nq = ipow(m.row_size, nd), nfq = nq/m.row_size, nf = 2*nd;
+  const int ne = int(k.elem.size()), n_def = k.n_def, n_car = k.n_car;
   std::vector<double> buf(ne);
-  for (int e = 0; e < ne; ++e) buf[e] = m.tab.elem[e]->nominal_size();
-  check(&m, hexed_b200_upload(m.ctx, HEXED_B200_NOMINAL_SIZE, buf.data(), 0, ne));
-  buf.resize(size_t(ne)*n_vert);
-  for (int e = 0; e < ne; ++e) for (int v = 0; v < n_vert; ++v) buf[size_t(e)*n_vert + v] = m.tab.elem[e]->vertex_time_step_scale(v);
-  check(&m, hexed_b200_upload(m.ctx, HEXED_B200_VERTEX_TSS, buf.data(), 0, ne));
+  for (int e = 0; e < ne; ++e) buf[e] = k.elem[e]->nominal_size();
+  check(&m, hexed_b200_upload(k.ctx, HEXED_B200_NOMINAL_SIZE, buf.data(), 0, ne), k.ctx);
+  upload_vertex_tss(m, k);
   const int chunk = 8192;
   for (int first = 0; first < n_def; first += chunk) {
     const int n = std::min(chunk, n_def - first);
     buf.resize(size_t(n)*nd*nd*nq);
     #pragma omp parallel for
-    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nd*nd*nq, m.tab.elem[n_car + first + i]->reference_level_normals(), sizeof(double)*nd*nd*nq);
-    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_REF_NORMALS, buf.data(), first, n));
+    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nd*nd*nq, k.elem[n_car + first + i]->reference_level_normals(), sizeof(double)*nd*nd*nq);
+    check(&m, hexed_b200_upload(k.ctx, HEXED_B200_REF_NORMALS, buf.data(), first, n), k.ctx);
     #pragma omp parallel for
-    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nq, m.tab.elem[n_car + first + i]->jacobian_determinant(), sizeof(double)*nq);
-    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_JAC_DET, buf.data(), first, n));
+    for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nq, k.elem[n_car + first + i]->jacobian_determinant(), sizeof(double)*nq);
+    check(&m, hexed_b200_upload(k.ctx, HEXED_B200_JAC_DET, buf.data(), first, n), k.ctx);
   }
-  const int nn = m.tab.n_normal_slot;
+  const int nn = k.n_normal_slot;
   buf.assign(size_t(nn)*nd*nfq, 0.);
   for (int s = 0; s < nn; ++s) {
     double* dst = buf.data() + size_t(s)*nd*nfq;
-    if (m.tab.normal_ptr[s]) std::memcpy(dst, m.tab.normal_ptr[s], sizeof(double)*nd*nfq);
+    if (k.normal_ptr[s]) std::memcpy(dst, k.normal_ptr[s], sizeof(double)*nd*nfq);
     else { // deformed element face in a Cartesian connection: unit normal of the face's dimension (include/Spatial.hpp:331-339,366)
       const int i_dim = (s % nf)/2;
       for (int q = 0; q < nfq; ++q) dst[size_t(i_dim)*nfq + q] = 1.;
     }
   }
-  if (nn) check(&m, hexed_b200_upload(m.ctx, HEXED_B200_NORMALS, buf.data(), 0, nn));
+  if (nn) check(&m, hexed_b200_upload(k.ctx, HEXED_B200_NORMALS, buf.data(), 0, nn), k.ctx);
 }
 
-void download_uncert(Mirror& m)
+void download_uncert(Mirror& m, Rank& k)
 {
-  const int ne = int(m.tab.elem.size());
+  const int ne = int(k.elem.size());
   std::vector<double> buf(ne);
-  check(&m, hexed_b200_download(m.ctx, HEXED_B200_UNCERT, buf.data(), 0, ne));
-  for (int e = 0; e < ne; ++e) m.tab.elem[e]->uncert() = buf[e];
+  check(&m, hexed_b200_download(k.ctx, HEXED_B200_UNCERT, buf.data(), 0, ne), k.ctx);
+  for (int e = 0; e < ne; ++e) k.elem[e]->uncert() = buf[e];
 }
 
 void move(Mirror& m, unsigned groups, bool up)
 {
-  move_elements(m, groups, up);
-  move_faces(m, groups, up);
-  if (up && (groups & geometry)) upload_geometry(m);
-  if (!up && (groups & uncert)) download_uncert(m);
+  for (Rank& k : m.ranks) {
+    move_elements(m, k, groups, up);
+    move_faces(m, k, groups, up);
+    if (up && (groups & geometry)) upload_geometry(m, k);
+    if (!up && (groups & uncert)) download_uncert(m, k);
+  }
 }
 
 void move_boundary(Mirror& m, bool up)
 {
-  if (m.boundary_slots.empty()) return;
   const int nfq = ipow(m.row_size, m.n_dim - 1), nv = m.n_dim + 2;
-  const size_t width = size_t(nv)*nfq, n = m.boundary_slots.size();
-  m.staging.resize(width*n);
-  for (int kind = 0; kind < 2; ++kind) { // 0: state half, 1: LDG half
-    if (up) {
-      #pragma omp parallel for
-      for (size_t i = 0; i < n; ++i) std::memcpy(m.staging.data() + width*i, m.tab.face_ptr[m.boundary_slots[i]] + kind*width, width*sizeof(double));
-      check(&m, hexed_b200_face_list_upload(m.ctx, m.boundary_list, kind, m.staging.data()));
-    } else {
-      check(&m, hexed_b200_face_list_download(m.ctx, m.boundary_list, kind, m.staging.data()));
-      #pragma omp parallel for
-      for (size_t i = 0; i < n; ++i) std::memcpy(m.tab.face_ptr[m.boundary_slots[i]] + kind*width, m.staging.data() + width*i, width*sizeof(double));
+  const size_t width = size_t(nv)*nfq;
+  for (Rank& k : m.ranks) {
+    if (k.boundary_slots.empty()) continue;
+    const size_t n = k.boundary_slots.size();
+    k.staging.resize(width*n);
+    for (int kind = 0; kind < 2; ++kind) { // 0: state half, 1: LDG half
+      if (up) {
+        #pragma omp parallel for
+        for (size_t i = 0; i < n; ++i) std::memcpy(k.staging.data() + width*i, k.face_ptr[k.boundary_slots[i]] + kind*width, width*sizeof(double));
+        check(&m, hexed_b200_face_list_upload(k.ctx, k.boundary_list, kind, k.staging.data()), k.ctx);
+      } else {
+        check(&m, hexed_b200_face_list_download(k.ctx, k.boundary_list, kind, k.staging.data()), k.ctx);
+        #pragma omp parallel for
+        for (size_t i = 0; i < n; ++i) std::memcpy(k.face_ptr[k.boundary_slots[i]] + kind*width, k.staging.data() + width*i, width*sizeof(double));
+      }
     }
+  }
+}
+
+Mesh_graph graph_of(const Flat_tables& t)
+{
+  Mesh_graph g;
+  g.n_dim = t.n_dim; g.n_car = t.n_car; g.n_def = t.n_def; g.n_face_slot = t.n_face_slot; g.n_normal_slot = t.n_normal_slot;
+  g.car_con = t.car_con; g.def_con = t.def_con; g.ref_face = t.ref_face; g.boundary_con = t.boundary_con;
+  return g;
+}
+
+//! (re)builds the device side of a mirror from its freshly flattened tables: one rank per device, the group when there are several
+void build_device_side(Mirror& m)
+{
+  const int n_ranks = int(g_devices.size());
+  if (int(m.ranks.size()) != n_ranks) {
+    m.destroy_device_side();
+    m.ranks.resize(n_ranks);
+    for (int r = 0; r < n_ranks; ++r) {
+      m.ranks[r].device = g_devices[r];
+      check(nullptr, hexed_b200_create(&m.ranks[r].ctx, g_devices[r], m.n_dim, m.row_size, m.packed_basis.data(), int(m.packed_basis.size())));
+    }
+    if (n_ranks > 1) {
+      std::vector<hexed_b200_ctx*> ctxs;
+      for (Rank& k : m.ranks) ctxs.push_back(k.ctx);
+      int rc = hexed_b200_group_create(&m.group, n_ranks, ctxs.data());
+      if (rc) throw std::runtime_error(std::string("hexed_b200: ") + hexed_b200_group_last_error(nullptr));
+    }
+  }
+  const Flat_tables& t = m.tab;
+  std::vector<Rank_mesh> parts;
+  if (n_ranks == 1) { // the undivided mesh is the one rank's mesh
+    Rank_mesh whole;
+    whole.graph = graph_of(t);
+    parts.push_back(std::move(whole));
+    m.owner.assign(t.elem.size(), 0);
+  } else {
+    Mesh_graph g = graph_of(t);
+    if (m.coords.size() == t.elem.size()) m.owner = owners_by_morton(m.coords, t.n_dim, t.n_car, n_ranks);
+    else m.owner = owners_by_graph(g, n_ranks);
+    parts = partition(g, m.owner, n_ranks);
+  }
+  for (int r = 0; r < n_ranks; ++r) {
+    Rank& k = m.ranks[r];
+    Rank_mesh& pm = parts[r];
+    const Mesh_graph& lg = pm.graph;
+    k.n_car = lg.n_car; k.n_def = lg.n_def; k.n_face_slot = lg.n_face_slot; k.n_normal_slot = lg.n_normal_slot;
+    if (n_ranks == 1) {
+      k.elem = t.elem; k.face_ptr = t.face_ptr; k.normal_ptr = t.normal_ptr;
+      k.global_elem.resize(t.elem.size());
+      for (size_t i = 0; i < t.elem.size(); ++i) k.global_elem[i] = int(i);
+      k.face_owned.assign(t.face_ptr.size(), 1);
+    } else {
+      k.global_elem = pm.global_elem;
+      k.elem.resize(pm.global_elem.size());
+      for (size_t i = 0; i < k.elem.size(); ++i) k.elem[i] = t.elem[pm.global_elem[i]];
+      k.face_ptr.resize(pm.global_face.size());
+      for (size_t i = 0; i < k.face_ptr.size(); ++i) k.face_ptr[i] = t.face_ptr[pm.global_face[i]];
+      k.normal_ptr.resize(pm.global_normal.size());
+      for (size_t i = 0; i < k.normal_ptr.size(); ++i) k.normal_ptr[i] = t.normal_ptr[pm.global_normal[i]];
+      k.face_owned = pm.face_owned;
+    }
+    k.def_con = lg.def_con; k.boundary_con = lg.boundary_con;
+    hexed_b200_mesh_desc d {};
+    d.n_car = lg.n_car; d.n_def = lg.n_def; d.n_face_slot = lg.n_face_slot; d.n_normal_slot = lg.n_normal_slot;
+    d.n_car_con = int(lg.car_con.size()/3); d.n_def_con = int(lg.def_con.size()/7); d.n_ref = int(lg.ref_face.size()/7);
+    d.car_con = lg.car_con.data(); d.def_con = lg.def_con.data(); d.ref_face = lg.ref_face.data();
+    check(&m, hexed_b200_mesh_create(k.ctx, &d), k.ctx);
+    if (n_ranks > 1) {
+      check(&m, hexed_b200_set_partition(k.ctx, pm.n_cut_car, pm.n_cut_def, int(pm.pre_prolong.size()), pm.pre_prolong.data()), k.ctx);
+      std::vector<int> n_send, n_recv, send, recv;
+      for (size_t i = 0; i < pm.peers.size(); ++i) {
+        n_send.push_back(int(pm.send_slots[i].size())); n_recv.push_back(int(pm.recv_slots[i].size()));
+        send.insert(send.end(), pm.send_slots[i].begin(), pm.send_slots[i].end());
+        recv.insert(recv.end(), pm.recv_slots[i].begin(), pm.recv_slots[i].end());
+      }
+      check_group(m, hexed_b200_group_set_halo(m.group, r, int(pm.peers.size()), pm.peers.data(), n_send.data(), send.data(), n_recv.data(), recv.data()));
+    }
+    k.boundary_slots.clear();
+    for (int i : lg.boundary_con) {k.boundary_slots.push_back(lg.def_con[size_t(i)*7]); k.boundary_slots.push_back(lg.def_con[size_t(i)*7 + 1]);}
+    k.boundary_list = -1;
+    if (!k.boundary_slots.empty()) check(&m, hexed_b200_face_list_create(k.ctx, k.boundary_slots.data(), int(k.boundary_slots.size()), &k.boundary_list), k.ctx);
+    upload_geometry(m, k);
   }
 }
 
 //! finds (or builds) the device mirror of `km`; a new mesh epoch uploads geometry and, in resident mode, all data
 Mirror& mirror(Kernel_mesh& km)
 {
-  auto key = std::make_pair(km.n_dim, km.row_size);
+  auto key = std::make_tuple(static_cast<const void*>(&km.elems), km.n_dim, km.row_size);
   auto& slot = g_mirrors[key];
   if (!slot) {
     std::unique_ptr<Mirror> m(new Mirror);
     m->n_dim = km.n_dim; m->row_size = km.row_size;
-    std::vector<double> packed;
-    if (km.n_dim >= 1 && km.n_dim <= 3 && km.row_size >= 2 && km.row_size <= 8) packed = pack_basis(km.basis);
-    else packed.assign(1, 0.); // the library answers "demand for invalid kernel" before it looks at the table
-    check(nullptr, hexed_b200_create(&m->ctx, g_device, km.n_dim, km.row_size, packed.data(), int(packed.size())));
+    if (km.n_dim >= 1 && km.n_dim <= 3 && km.row_size >= 2 && km.row_size <= 8) m->packed_basis = pack_basis(km.basis);
+    else m->packed_basis.assign(1, 0.); // the library answers "demand for invalid kernel" before it looks at the table
     slot = std::move(m);
   }
   Mirror& m = *slot;
-  auto fp = make_fingerprint(km);
+  auto fp = make_fingerprint(km, g_mode == sync_every_call);
   if (m.have_mesh && fp == m.fingerprint) return m;
+  if (m.have_mesh && g_mode == resident && !m.explicitly_invalidated) {
+    // the device copy is authoritative in resident mode: re-flattening would upload host data over results only the device holds
+    throw std::runtime_error("hexed_b200: the mesh changed while its state is resident on the device; call to_host() before changing the "
+                             "mesh and invalidate() after (adapter.hpp)");
+  }
   m.tab = flatten(km);
-  hexed_b200_mesh_desc d {};
-  d.n_car = m.tab.n_car; d.n_def = m.tab.n_def; d.n_face_slot = m.tab.n_face_slot; d.n_normal_slot = m.tab.n_normal_slot;
-  d.n_car_con = int(m.tab.car_con.size()/3); d.n_def_con = int(m.tab.def_con.size()/7); d.n_ref = int(m.tab.ref_face.size()/7);
-  d.car_con = m.tab.car_con.data(); d.def_con = m.tab.def_con.data(); d.ref_face = m.tab.ref_face.data();
-  check(&m, hexed_b200_mesh_create(m.ctx, &d));
-  m.boundary_slots.clear();
-  for (int i : m.tab.boundary_con) {m.boundary_slots.push_back(m.tab.def_con[size_t(i)*7]); m.boundary_slots.push_back(m.tab.def_con[size_t(i)*7 + 1]);}
-  m.boundary_list = -1;
-  if (!m.boundary_slots.empty()) check(&m, hexed_b200_face_list_create(m.ctx, m.boundary_slots.data(), int(m.boundary_slots.size()), &m.boundary_list));
+  build_device_side(m);
   m.fingerprint = fp;
   m.have_mesh = true;
-  upload_geometry(m);
+  m.explicitly_invalidated = false;
   if (g_mode == resident) move(m, all_elem | faces | faces_wide, true);
   return m;
 }
@@ -440,19 +578,22 @@ struct Call
       // kernels write their outputs only partly (e.g. write_face leaves ghost and mortar faces alone), so everything that will be
       // downloaded must first hold the host's values
       in |= out & ~unsigned(uncert);
-      if (in & tss) upload_geometry_light();
+      // "always correct with no Solver change" includes the metric terms: Solver::calc_jacobian, vertex relaxation and snap_faces
+      // rewrite normals, determinants and nominal data IN PLACE (same pointers, same sizes), so this mode re-reads them with the state
+      if (in & (state | tss)) in |= geometry;
       move(m, in, true);
     }
   }
-  void upload_geometry_light()
-  { // vertex_time_step_scale is rewritten by Solver::set_local_tss between calls; it is tiny, so it always travels with tss
-    const int n_vert = ipow(2, m.n_dim), ne = int(m.tab.elem.size());
-    std::vector<double> buf(size_t(ne)*n_vert);
-    for (int e = 0; e < ne; ++e) for (int v = 0; v < n_vert; ++v) buf[size_t(e)*n_vert + v] = m.tab.elem[e]->vertex_time_step_scale(v);
-    check(&m, hexed_b200_upload(m.ctx, HEXED_B200_VERTEX_TSS, buf.data(), 0, ne));
-  }
   void finish() {if (g_mode == sync_every_call) move(m, out, false);}
+  //! `f(ctx)` on every rank
+  template <typename F> void each(F f) {for (Rank& k : m.ranks) check(&m, f(k.ctx), k.ctx);}
+  bool multi() const {return m.group != nullptr;}
 };
+
+void single_device_only(Mirror& m, const char* what)
+{
+  if (m.group) throw std::runtime_error(std::string("hexed_b200: ") + what + " is not available on more than one device (set_devices)");
+}
 
 // the Stopwatch_tree side-contract (include/kernel_factory.hpp:32-45): every kernel call adds sequence.size() work units to its
 // child. Device work of one stage is a single asynchronous C call, so its host time is charged to the category stopwatches
@@ -498,25 +639,40 @@ struct Flux_bc_thunk
     // the host callback reads and writes boundary faces (Solver::apply_flux_bcs, src/Solver.cpp:69-81)
     // (resident mode: a callback that applies its conditions on the device through hexed_b200::apply_flux_bcs owns the boundary faces
     // itself -- uploading the host copy afterwards would overwrite what the device just computed)
-    if (g_mode == sync_every_call) move_faces(*self->m, faces, false); else move_boundary(*self->m, false);
+    if (g_mode == sync_every_call) {for (Rank& k : self->m->ranks) move_faces(*self->m, k, faces, false);} else move_boundary(*self->m, false);
     self->m->device_bcs_ran = false;
     (*self->fun)();
-    if (g_mode == sync_every_call) move_faces(*self->m, faces, true);
+    if (g_mode == sync_every_call) {for (Rank& k : self->m->ranks) move_faces(*self->m, k, faces, true);}
     else if (!self->m->device_bcs_ran) move_boundary(*self->m, true);
   }
 };
 
-template <typename F>
-double max_dt_call(Kernel_mesh& km, Kernel_options& o, unsigned in, F launch)
+//! the five max_dt_* entry points: pde 0 Euler, 1 Navier-Stokes, 2 advection, 3 smooth AV, 4 fix therm admis
+double max_dt_call(Kernel_mesh& km, Kernel_options& o, unsigned in, int pde, double sc, double sd, bool local_time,
+                   hexed_b200_transport visc, hexed_b200_transport cond, double advect_length)
 {
   Call call(km, in | tss, tss);
   Watch w; w.start(o.sw_car); w.start(o.sw_def);
   double dt = 0.;
-  check(&call.m, launch(call.m.ctx, &dt));
+  if (call.multi()) check_group(call.m, hexed_b200_group_max_dt(call.m.group, pde, sc, sd, local_time, visc, cond, advect_length, &dt));
+  else {
+    hexed_b200_ctx* c = call.m.ctx0();
+    int rc = 0;
+    switch (pde) {
+      case 0: rc = hexed_b200_max_dt_euler(c, options(o), sc, sd, local_time, &dt); break;
+      case 1: rc = hexed_b200_max_dt_navier_stokes(c, options(o), sc, sd, local_time, visc, cond, &dt); break;
+      case 2: rc = hexed_b200_max_dt_advection(c, options(o), sc, sd, local_time, advect_length, &dt); break;
+      case 3: rc = hexed_b200_max_dt_smooth_av(c, options(o), sc, sd, local_time, &dt); break;
+      default: rc = hexed_b200_max_dt_fix_therm_admis(c, options(o), sc, sd, local_time, &dt); break;
+    }
+    check(&call.m, rc);
+  }
   count(o.sw_car, "compute time step", km.car_elems.size()); count(o.sw_def, "compute time step", km.def_elems.size());
   call.finish();
   return dt;
 }
+
+const hexed_b200_transport no_transport {0., 0., 1., 1., 1., 0};
 
 class Face_permutation_host : public hexed::Face_permutation_dynamic
 {
@@ -556,36 +712,89 @@ class Face_permutation_host : public hexed::Face_permutation_dynamic
 
 void set_sync_mode(Sync_mode mode) {g_mode = mode;}
 Sync_mode sync_mode() {return g_mode;}
-void set_device(int d) {g_device = d;}
-void invalidate() {for (auto& kv : g_mirrors) if (kv.second) kv.second->have_mesh = false;}
+void set_device(int d) {set_devices({d});}
+void set_devices(const std::vector<int>& devices)
+{
+  if (devices.empty()) throw std::runtime_error("hexed_b200: set_devices needs at least one device");
+  if (devices == g_devices) return;
+  g_devices = devices;
+  for (auto& kv : g_mirrors) if (kv.second) { // existing mirrors are rebuilt on the new device set at their next call
+    if (kv.second->have_mesh && g_mode == resident) throw std::runtime_error("hexed_b200: set_devices while a mesh is resident; call to_host() and release() first");
+    kv.second->destroy_device_side();
+    kv.second->have_mesh = false;
+  }
+}
+int n_devices() {return int(g_devices.size());}
+void set_element_coordinates(Kernel_mesh km, const std::vector<std::array<int, 3>>& coords)
+{
+  auto key = std::make_tuple(static_cast<const void*>(&km.elems), km.n_dim, km.row_size);
+  auto& slot = g_mirrors[key];
+  if (!slot) {
+    slot.reset(new Mirror);
+    slot->n_dim = km.n_dim; slot->row_size = km.row_size;
+    if (km.n_dim >= 1 && km.n_dim <= 3 && km.row_size >= 2 && km.row_size <= 8) slot->packed_basis = pack_basis(km.basis);
+    else slot->packed_basis.assign(1, 0.);
+  }
+  if (int(coords.size()) != km.elems.size()) throw std::runtime_error("hexed_b200: set_element_coordinates: one coordinate triple per element of Kernel_mesh::elems");
+  slot->coords = coords;
+  if (slot->have_mesh && g_devices.size() > 1) {
+    if (g_mode == resident) throw std::runtime_error("hexed_b200: set_element_coordinates while a mesh is resident");
+    slot->have_mesh = false;
+  }
+}
+std::vector<int> element_owners(Kernel_mesh km) {return mirror(km).owner;}
+void invalidate() {for (auto& kv : g_mirrors) if (kv.second) {kv.second->have_mesh = false; kv.second->explicitly_invalidated = true;}}
 void release() {g_mirrors.clear();}
 void to_host(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(geometry), false);}
 void to_device(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(uncert), true);}
 void boundary_faces_to_host(Kernel_mesh km) {move_boundary(mirror(km), false);}
 void ghost_faces_to_device(Kernel_mesh km) {move_boundary(mirror(km), true);}
-void synchronize(Kernel_mesh km) {Mirror& m = mirror(km); check(&m, hexed_b200_synchronize(m.ctx));}
+void synchronize(Kernel_mesh km)
+{
+  Mirror& m = mirror(km);
+  if (m.group) check_group(m, hexed_b200_group_synchronize(m.group));
+  else check(&m, hexed_b200_synchronize(m.ctx0()));
+}
+std::string transport_description(Kernel_mesh km)
+{
+  Mirror& m = mirror(km);
+  if (!m.group) return "single device";
+  int v = 0; long long ex = 0, bytes = 0;
+  hexed_b200_group_info(m.group, &v, &ex, &bytes);
+  return "NCCL " + std::to_string(v/10000) + "." + std::to_string(v/100%100) + "." + std::to_string(v%100) + " send/recv over " + std::to_string(m.ranks.size())
+         + " devices, " + std::to_string(ex) + " exchanges, " + std::to_string(bytes) + " bytes sent";
+}
 
 int add_device_bc(Kernel_mesh km, int kind, const std::vector<double*>& inside_faces, const std::vector<double>& params)
 {
   Mirror& m = mirror(km);
-  std::unordered_map<const double*, int> con_of_inside; // inside face of a boundary connection -> its row in def_con
-  for (int i : m.tab.boundary_con) con_of_inside[m.tab.face_ptr[m.tab.def_con[size_t(i)*7]]] = i;
-  std::vector<int> inside, ghost, normal;
-  for (double* p : inside_faces) {
-    auto it = con_of_inside.find(p);
-    if (it == con_of_inside.end()) throw std::runtime_error("hexed_b200: add_device_bc: not the inside face of a boundary connection");
-    const int* row = m.tab.def_con.data() + size_t(it->second)*7;
-    inside.push_back(row[0]); ghost.push_back(row[1]); normal.push_back(row[6]);
-  }
   int id = -1;
-  check(&m, hexed_b200_bc_create(m.ctx, kind, int(inside.size()), inside.data(), ghost.data(), normal.data(), params.data(), int(params.size()), &id));
+  // every rank registers the condition for the boundary connections it owns (possibly none), so that ids agree across ranks
+  std::vector<char> found(inside_faces.size(), 0);
+  for (Rank& k : m.ranks) {
+    std::unordered_map<const double*, int> con_of_inside; // inside face of a boundary connection -> its row in the rank's def_con
+    for (int i : k.boundary_con) con_of_inside[k.face_ptr[k.def_con[size_t(i)*7]]] = i;
+    std::vector<int> inside, ghost, normal;
+    for (size_t j = 0; j < inside_faces.size(); ++j) {
+      auto it = con_of_inside.find(inside_faces[j]);
+      if (it == con_of_inside.end()) continue;
+      found[j] = 1;
+      const int* row = k.def_con.data() + size_t(it->second)*7;
+      inside.push_back(row[0]); ghost.push_back(row[1]); normal.push_back(row[6]);
+    }
+    int rank_id = -1;
+    check(&m, hexed_b200_bc_create(k.ctx, kind, int(inside.size()), inside.data(), ghost.data(), normal.data(), params.data(), int(params.size()), &rank_id), k.ctx);
+    if (id >= 0 && rank_id != id) throw std::runtime_error("hexed_b200: boundary condition ids diverged between devices");
+    id = rank_id;
+  }
+  for (char f : found) if (!f) throw std::runtime_error("hexed_b200: add_device_bc: not the inside face of a boundary connection");
   return id;
 }
 
 void apply_state_bcs(Kernel_mesh km)
 {
   Call call(km, faces, faces);
-  check(&call.m, hexed_b200_apply_state_bcs(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_apply_state_bcs(c);});
   call.m.device_bcs_ran = true;
   call.finish();
 }
@@ -593,8 +802,9 @@ void apply_state_bcs(Kernel_mesh km)
 double update_euler(Kernel_mesh km, double safety, int n_steps, double* last_dt, bool use_graph, int n_cheby)
 { // the flow loop of Solver::update (src/Solver.cpp:834-886) for the inviscid case, n_cheby_flow = 1, device boundary conditions
   Call call(km, state | tss | res_cache | faces, state | tss | res_cache | faces);
+  single_device_only(call.m, "update_euler (the CUDA-graph flow loop)");
   double dt = 0, t = 0;
-  check(&call.m, hexed_b200_update_euler(call.m.ctx, safety, n_cheby, n_steps, use_graph, &dt, &t));
+  check(&call.m, hexed_b200_update_euler(call.m.ctx0(), safety, n_cheby, n_steps, use_graph, &dt, &t));
   call.m.device_bcs_ran = true;
   call.finish();
   if (last_dt) *last_dt = dt;
@@ -607,15 +817,21 @@ bool is_admissible(Kernel_mesh km, std::vector<int>* record)
   // a Solver that checks admissibility wants it after every stage: from now on the pipelined Local kernels leave the bits of what
   // they write and the check right after a compute_euler reduces those (any other write to the state or faces, e.g. the uploads of
   // sync_every_call mode, falls back to the full scan)
-  check(&call.m, hexed_b200_set_option(call.m.ctx, HEXED_B200_OPT_FUSED_ADMIS, 1));
-  int ok = 0;
-  check(&call.m, hexed_b200_is_admissible(call.m.ctx, &ok));
-  if (record) {
-    record->resize(call.m.tab.elem.size());
-    check(&call.m, hexed_b200_download_record(call.m.ctx, record->data(), 0, int(record->size())));
+  bool all_ok = true;
+  if (record) record->assign(call.m.tab.elem.size(), 0);
+  for (Rank& k : call.m.ranks) { // every rank checks its elements, faces and the mortar faces it holds; the answer is the AND
+    check(&call.m, hexed_b200_set_option(k.ctx, HEXED_B200_OPT_FUSED_ADMIS, 1), k.ctx);
+    int ok = 0;
+    check(&call.m, hexed_b200_is_admissible(k.ctx, &ok), k.ctx);
+    all_ok = all_ok && ok != 0;
+    if (record && !k.elem.empty()) {
+      std::vector<int> local(k.elem.size());
+      check(&call.m, hexed_b200_download_record(k.ctx, local.data(), 0, int(local.size())), k.ctx);
+      for (size_t i = 0; i < local.size(); ++i) (*record)[k.global_elem[i]] = local[i];
+    }
   }
   call.finish();
-  return ok != 0;
+  return all_ok;
 }
 
 // ---- pointwise loops of the artificial-viscosity pipelines ----
@@ -633,7 +849,7 @@ std::vector<double> weights_of(const hexed::Basis& b)
 void av_scale_velocity(Kernel_mesh km, bool restore)
 { // src/Solver.cpp:467-478 | :567-571
   Call call(km, state, state);
-  check(&call.m, hexed_b200_av_scale_velocity(call.m.ctx, restore));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_av_scale_velocity(c, restore);});
   call.finish();
 }
 
@@ -644,7 +860,7 @@ void av_project_forcing(Kernel_mesh km)
   auto o = km.basis.orthogonal(km.row_size - 1);
   std::vector<double> orth(km.row_size);
   for (int i = 0; i < km.row_size; ++i) orth[i] = o(i);
-  check(&call.m, hexed_b200_av_project_forcing(call.m.ctx, w.data(), orth.data()));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_av_project_forcing(c, w.data(), orth.data());});
   call.finish();
 }
 
@@ -653,7 +869,8 @@ double av_finish(Kernel_mesh km, double mult, double us_max, int n_real)
   Call call(km, state | art_visc, state | art_visc);
   auto w = weights_of(km.basis);
   double resid = 0;
-  check(&call.m, hexed_b200_av_finish(call.m.ctx, mult, us_max, n_real, w.data(), &resid));
+  single_device_only(call.m, "av_finish");
+  check(&call.m, hexed_b200_av_finish(call.m.ctx0(), mult, us_max, n_real, w.data(), &resid));
   call.finish();
   return resid;
 }
@@ -664,14 +881,15 @@ void interp_vertices(Kernel_mesh km, int target, const std::vector<double>& vert
   std::vector<double> interp(size_t(2)*km.row_size);
   for (int i = 0; i < km.row_size; ++i) {interp[2*i] = 1. - km.basis.node(i); interp[2*i + 1] = km.basis.node(i);}
   if (vertex_values.size() != call.m.tab.elem.size()*size_t(ipow(2, km.n_dim))) throw std::runtime_error("hexed_b200: interp_vertices: one value per element vertex expected");
-  check(&call.m, hexed_b200_interp_vertices(call.m.ctx, target, vertex_values.data(), interp.data()));
+  single_device_only(call.m, "interp_vertices");
+  check(&call.m, hexed_b200_interp_vertices(call.m.ctx0(), target, vertex_values.data(), interp.data()));
   call.finish();
 }
 
 void av_swap(Kernel_mesh km)
 { // src/Solver.cpp:1032-1038
   Call call(km, art_visc, art_visc);
-  check(&call.m, hexed_b200_av_swap(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_av_swap(c);});
   call.finish();
 }
 
@@ -679,7 +897,7 @@ void apply_aux_bcs(Kernel_mesh km, int mode)
 {
   const unsigned grp = mode == HEXED_B200_BC_MODE_ADVECTION ? unsigned(faces_wide) : unsigned(faces);
   Call call(km, grp, grp);
-  check(&call.m, hexed_b200_apply_aux_bcs(call.m.ctx, mode));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_apply_aux_bcs(c, mode);});
   call.m.device_bcs_ran = true;
   call.finish();
 }
@@ -687,7 +905,7 @@ void apply_aux_bcs(Kernel_mesh km, int mode)
 void apply_flux_bcs(Kernel_mesh km)
 {
   Call call(km, faces, faces);
-  check(&call.m, hexed_b200_apply_flux_bcs(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_apply_flux_bcs(c);});
   call.m.device_bcs_ran = true;
   call.finish();
 }
@@ -706,7 +924,8 @@ void compute_euler(Kernel_mesh mesh, Kernel_options opts)
 { // src/kernels_convective.cpp:18
   Call call(mesh, state | tss | res_cache | faces, state | res_cache | faces);
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
-  check(&call.m, hexed_b200_compute_euler(call.m.ctx, options(opts)));
+  if (call.multi()) check_group(call.m, hexed_b200_group_compute_euler(call.m.group, options(opts)));
+  else check(&call.m, hexed_b200_compute_euler(call.m.ctx0(), options(opts)));
   count_convective(mesh, opts);
   call.finish();
 }
@@ -715,7 +934,8 @@ void compute_advection(Kernel_mesh mesh, Kernel_options opts, double advect_leng
 { // src/kernels_convective.cpp:19
   Call call(mesh, state | tss | advection | res_cache | faces_wide, advection | res_cache | faces_wide);
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
-  check(&call.m, hexed_b200_compute_advection(call.m.ctx, options(opts), advect_length));
+  single_device_only(call.m, "compute_advection");
+  check(&call.m, hexed_b200_compute_advection(call.m.ctx0(), options(opts), advect_length));
   count_convective(mesh, opts);
   call.finish();
 }
@@ -725,7 +945,8 @@ void compute_navier_stokes(Kernel_mesh mesh, Kernel_options opts, std::function<
   Call call(mesh, state | tss | art_visc | res_cache | faces, state | res_cache | faces);
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
   Flux_bc_thunk thunk {&call.m, &flux_bc};
-  check(&call.m, hexed_b200_compute_navier_stokes(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
+  if (call.multi()) check_group(call.m, hexed_b200_group_compute_navier_stokes(call.m.group, options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
+  else check(&call.m, hexed_b200_compute_navier_stokes(call.m.ctx0(), options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
   count_diffusive(mesh, opts);
   call.finish();
 }
@@ -735,7 +956,8 @@ void compute_smooth_av(Kernel_mesh mesh, Kernel_options opts, std::function<void
   Call call(mesh, state | tss | art_visc | res_cache | faces, art_visc | res_cache | faces);
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
   Flux_bc_thunk thunk {&call.m, &flux_bc};
-  check(&call.m, hexed_b200_compute_smooth_av(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk, diff_time, chebyshev_step));
+  single_device_only(call.m, "compute_smooth_av");
+  check(&call.m, hexed_b200_compute_smooth_av(call.m.ctx0(), options(opts), &Flux_bc_thunk::call, &thunk, diff_time, chebyshev_step));
   count_diffusive(mesh, opts);
   call.finish();
 }
@@ -745,61 +967,57 @@ void compute_fix_therm_admis(Kernel_mesh mesh, Kernel_options opts, std::functio
   Call call(mesh, state | tss | art_visc | res_cache | faces, state | res_cache | faces);
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
   Flux_bc_thunk thunk {&call.m, &flux_bc};
-  check(&call.m, hexed_b200_compute_fix_therm_admis(call.m.ctx, options(opts), &Flux_bc_thunk::call, &thunk));
+  single_device_only(call.m, "compute_fix_therm_admis");
+  check(&call.m, hexed_b200_compute_fix_therm_admis(call.m.ctx0(), options(opts), &Flux_bc_thunk::call, &thunk));
   count_diffusive(mesh, opts);
   call.finish();
 }
 
 double max_dt_euler(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
 { // src/kernels_max_dt.cpp:14
-  return max_dt_call(mesh, opts, state, [&](hexed_b200_ctx* c, double* dt) {
-    return hexed_b200_max_dt_euler(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+  return max_dt_call(mesh, opts, state, 0, convective_safety, diffusive_safety, local_time, no_transport, no_transport, 0.);
 }
 
 double max_dt_navier_stokes(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time,
                             Transport_model visc, Transport_model therm_cond)
 { // src/kernels_max_dt.cpp:15-17
-  auto v = transport(visc), k = transport(therm_cond);
-  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
-    return hexed_b200_max_dt_navier_stokes(c, options(opts), convective_safety, diffusive_safety, local_time, v, k, dt);});
+  return max_dt_call(mesh, opts, state | art_visc, 1, convective_safety, diffusive_safety, local_time, transport(visc), transport(therm_cond), 0.);
 }
 
 double max_dt_advection(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time, double advect_length)
 { // src/kernels_max_dt.cpp:18-19
-  return max_dt_call(mesh, opts, state | advection, [&](hexed_b200_ctx* c, double* dt) {
-    return hexed_b200_max_dt_advection(c, options(opts), convective_safety, diffusive_safety, local_time, advect_length, dt);});
+  return max_dt_call(mesh, opts, state | advection, 2, convective_safety, diffusive_safety, local_time, no_transport, no_transport, advect_length);
 }
 
 double max_dt_smooth_av(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
 { // src/kernels_max_dt.cpp:20
-  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
-    return hexed_b200_max_dt_smooth_av(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+  return max_dt_call(mesh, opts, state | art_visc, 3, convective_safety, diffusive_safety, local_time, no_transport, no_transport, 0.);
 }
 
 double max_dt_fix_therm_admis(Kernel_mesh mesh, Kernel_options opts, double convective_safety, double diffusive_safety, bool local_time)
 { // src/kernels_max_dt.cpp:21
-  return max_dt_call(mesh, opts, state | art_visc, [&](hexed_b200_ctx* c, double* dt) {
-    return hexed_b200_max_dt_fix_therm_admis(c, options(opts), convective_safety, diffusive_safety, local_time, dt);});
+  return max_dt_call(mesh, opts, state | art_visc, 4, convective_safety, diffusive_safety, local_time, no_transport, no_transport, 0.);
 }
 
 void compute_prolong(Kernel_mesh mesh, bool scale, bool offset)
 { // src/kernels_convective.cpp:23-26
   Call call(mesh, faces, faces);
-  check(&call.m, hexed_b200_compute_prolong(call.m.ctx, scale, offset));
+  if (call.multi()) check_group(call.m, hexed_b200_group_exchange(call.m.group, offset ? 1 : 0)); // a remote coarse face must be current before it is prolonged here
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_prolong(c, scale, offset);});
   call.finish();
 }
 
 void compute_restrict(Kernel_mesh mesh, bool scale, bool offset)
 { // src/kernels_convective.cpp:28-31
   Call call(mesh, faces, faces);
-  check(&call.m, hexed_b200_compute_restrict(call.m.ctx, scale, offset));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_restrict(c, scale, offset);});
   call.finish();
 }
 
 void compute_prolong_advection(Kernel_mesh mesh)
 { // src/kernels_convective.cpp:33-36
   Call call(mesh, faces_wide, faces_wide);
-  check(&call.m, hexed_b200_compute_prolong_advection(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_prolong_advection(c);});
   call.finish();
 }
 
@@ -811,28 +1029,28 @@ std::unique_ptr<Face_permutation_dynamic> face_permutation(int n_dim, int row_si
 void compute_write_face(Kernel_mesh mesh)
 { // src/kernels_convective.cpp:43-46
   Call call(mesh, state, faces);
-  check(&call.m, hexed_b200_compute_write_face(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_write_face(c);});
   call.finish();
 }
 
 void compute_write_face_advection(Kernel_mesh mesh)
 { // src/kernels_convective.cpp:48-51
   Call call(mesh, state | advection, faces_wide);
-  check(&call.m, hexed_b200_compute_write_face_advection(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_write_face_advection(c);});
   call.finish();
 }
 
 void compute_write_face_smooth_av(Kernel_mesh mesh)
 { // src/kernels_convective.cpp:53-56
   Call call(mesh, state | art_visc, faces);
-  check(&call.m, hexed_b200_compute_write_face_smooth_av(call.m.ctx));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_compute_write_face_smooth_av(c);});
   call.finish();
 }
 
 void stabilizing_art_visc(Kernel_mesh mesh, double char_speed)
 { // src/stabilizing_art_visc.cpp:8-66
   Call call(mesh, state, uncert);
-  check(&call.m, hexed_b200_stabilizing_art_visc(call.m.ctx, char_speed));
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_stabilizing_art_visc(c, char_speed);});
   call.finish();
 }
 

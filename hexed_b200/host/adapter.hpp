@@ -16,6 +16,8 @@
 #ifndef HEXED_B200_ADAPTER_HPP_
 #define HEXED_B200_ADAPTER_HPP_
 
+#include <array>
+#include <string>
 #include <vector>
 #ifdef HEXED_B200_WITH_HEXED_HEADERS
 #include <kernels.hpp>
@@ -46,9 +48,27 @@ enum Data_group : unsigned {
 
 void set_sync_mode(Sync_mode);
 Sync_mode sync_mode();
-void set_device(int cuda_device); //!< device used for contexts created from now on (default 0)
-//! forget the flattened mesh: the next entry point re-walks the Sequence views (call after mesh adaptation or `calc_jacobian`).
-//! Changes of the sequence sizes or of the first/middle/last storage pointers are detected without this.
+void set_device(int cuda_device); //!< run on this one device (default 0); same as set_devices({cuda_device})
+/*! \brief run every Kernel_mesh on SEVERAL GPUs of the box, below the kernels.hpp boundary: the Solver still hands
+ * over one Kernel_mesh and still is one process. The flattened mesh is split by a space-filling curve (Morton order of the integer
+ * element coordinates given with `set_element_coordinates`; without coordinates a breadth-first ordering of the connection graph),
+ * each device gets a self-contained sub-mesh whose cut faces are halo slots, and `compute_euler` / `compute_navier_stokes` /
+ * `max_dt_*` run as: NCCL send/recv of the cut faces overlapped with the interior Neighbor kernels, ncclAllReduce(min) of the time
+ * step (include/hexed_b200.h "device group", hexed_b200/csrc/group.cu). Results are those of one device (same kernels, same operands).
+ * Entry points without a multi-device version (the artificial-viscosity PDE drivers, update_euler) throw when more than one device is set. */
+void set_devices(const std::vector<int>& cuda_devices);
+int n_devices();
+/*! integer coordinates of every element of `Kernel_mesh::elems` in units of the finest element size (e.g. `Element::nominal_position()`
+ * shifted to its refinement level), used for the Morton split. Optional. Must be called before the first kernel call of the epoch. */
+void set_element_coordinates(hexed::Kernel_mesh, const std::vector<std::array<int, 3>>& coords);
+std::vector<int> element_owners(hexed::Kernel_mesh); //!< device rank of every element of `Kernel_mesh::elems` (all 0 on one device)
+std::string transport_description(hexed::Kernel_mesh); //!< e.g. "NCCL 2.27.3 send/recv over 8 devices, ..."
+/*! forget the flattened mesh: the next entry point re-walks the Sequence views (call after mesh adaptation).
+ * sync_every_call mode needs no such call: it fingerprints every element's and connection's storage address on each call and re-reads
+ * the metric terms with the state, so in-place edits (`calc_jacobian`, vertex relaxation, `snap_faces`) and same-size mesh changes are
+ * picked up by themselves. resident mode samples three objects per view; after a mesh change there, call to_host() first, change the
+ * mesh, then invalidate() -- a changed fingerprint without invalidate() throws rather than overwrite device-only results. Metric terms
+ * rewritten in place in resident mode travel with to_device(mesh, geometry). */
 void invalidate();
 void release(); //!< destroy every device context (also done at exit)
 

@@ -303,6 +303,45 @@ int hbh_control(void* handle, int what, unsigned arg)
   }
 }
 
+/* multi-device controls: hexed_b200::set_devices(devices[n]); optional integer element coordinates [n_elem][3] for the Morton split */
+int hbh_set_devices(void* handle, const int* devices, int n)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {hexed_b200::set_devices(std::vector<int>(devices, devices + n)); return 0;}
+  catch (const std::exception& ex) {if (h) h->error = ex.what(); return 1;}
+}
+
+int hbh_set_element_coordinates(void* handle, const int* coords)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    std::vector<std::array<int, 3>> c(h->elems.size());
+    for (size_t e = 0; e < c.size(); ++e) for (int d = 0; d < 3; ++d) c[e][d] = coords[e*3 + d];
+    hexed_b200::set_element_coordinates(h->mesh(), c);
+    return 0;
+  } catch (const std::exception& ex) {h->error = ex.what(); return 1;}
+}
+
+int hbh_element_owners(void* handle, int* out)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    auto o = hexed_b200::element_owners(h->mesh());
+    std::copy(o.begin(), o.end(), out);
+    return 0;
+  } catch (const std::exception& ex) {h->error = ex.what(); return 1;}
+}
+
+int hbh_transport_description(void* handle, char* out, int cap)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    std::string d = hexed_b200::transport_description(h->mesh());
+    std::snprintf(out, cap, "%s", d.c_str());
+    return 0;
+  } catch (const std::exception& ex) {h->error = ex.what(); return 1;}
+}
+
 /* registers a device boundary condition for the boundary connections whose def_con rows are listed, then the two apply calls */
 int hbh_add_device_bc(void* handle, int kind, const int* def_con_index, int n, const double* params, int n_params)
 {

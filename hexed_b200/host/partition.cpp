@@ -215,8 +215,9 @@ std::vector<Rank_mesh> partition(const Mesh_graph& g, const std::vector<int>& ow
     lg.n_face_slot = int(m.global_face.size());
     lg.n_normal_slot = int(m.global_normal.size());
   }
-  // which copy of a face is written back to the host: element faces by their owner; connection-owned faces (ghosts, mortar faces)
-  // by the lowest rank that holds them (every copy holds the same values)
+  // which copy of a face is written back to the host: element faces by their owner; mortar faces by the rank that owns the coarse
+  // element (the only one whose Prolong always starts from a current coarse face -- elsewhere the copy is refreshed by pre_prolong
+  // just before use and may be stale in between); other connection-owned faces (boundary ghosts) by the one rank that holds them
   std::unordered_map<int, int> first_holder;
   for (int p = 0; p < n_parts; ++p) for (int s : parts[p].global_face) if (s >= n_elem_slots && !first_holder.count(s)) first_holder[s] = p;
   for (int p = 0; p < n_parts; ++p) {
@@ -224,7 +225,11 @@ std::vector<Rank_mesh> partition(const Mesh_graph& g, const std::vector<int>& ow
     m.face_owned.resize(m.global_face.size());
     for (size_t l = 0; l < m.global_face.size(); ++l) {
       const int s = m.global_face[l];
-      m.face_owned[l] = s < n_elem_slots ? owner[s/nf] == p : first_holder[s] == p;
+      if (s < n_elem_slots) m.face_owned[l] = owner[s/nf] == p;
+      else {
+        auto it = mortar_ref.find(s);
+        m.face_owned[l] = (it != mortar_ref.end() ? owner_of_slot(g.ref_face[size_t(it->second)*7]) : first_holder[s]) == p;
+      }
     }
   }
   // halo lists: what q receives from p is what p sends to q, both in ascending global slot order

@@ -86,6 +86,10 @@ class HostHarness:
         L.hbh_is_admissible.argtypes = [C.c_void_p, ip, ip]
         L.hbh_av_glue.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_int, dp]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
+        L.hbh_set_devices.argtypes = [C.c_void_p, ip, C.c_int]
+        L.hbh_set_element_coordinates.argtypes = [C.c_void_p, ip]
+        L.hbh_element_owners.argtypes = [C.c_void_p, ip]
+        L.hbh_transport_description.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         m = mesh
         self.m = m
         packed = np.ascontiguousarray(basis.packed())
@@ -139,6 +143,25 @@ class HostHarness:
     def ghost_faces_to_device(self): self.control(4)
     def invalidate(self): self.control(5)
     def release(self): self.control(6)
+
+    def set_devices(self, devices):
+        d = np.ascontiguousarray(devices, dtype=np.int32)
+        self._check(self.lib.hbh_set_devices(self.h, _i(d), d.size))
+
+    def set_element_coordinates(self, index):
+        c = np.zeros((self.m.n_elem, 3), np.int32)
+        c[:, :index.shape[1]] = index
+        self._check(self.lib.hbh_set_element_coordinates(self.h, _i(c)))
+
+    def element_owners(self):
+        out = np.zeros(max(self.m.n_elem, 1), np.int32)
+        self._check(self.lib.hbh_element_owners(self.h, _i(out)))
+        return out[:self.m.n_elem]
+
+    def transport_description(self):
+        buf = C.create_string_buffer(512)
+        self._check(self.lib.hbh_transport_description(self.h, buf, 512))
+        return buf.value.decode()
 
     def add_device_bcs(self, mesh):
         """register every boundary condition of `mesh` on the device through hexed_b200::add_device_bc"""

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import hexed_b200 as hb
+from hexed_b200.cases import density_wave, freestream_state
 from hexed_b200 import mesh as M
 from hexed_b200.tables import Connection_direction
 import host_harness as H
@@ -78,9 +79,13 @@ def host_bcs(oracle, h, work, resident, flux=False):
         h.ghost_faces_to_device()
 
 
-def run_euler(oracle, lib, m, basis, resident, n_steps=2, local_time=False, use_filter=False, safety=0.7):
+def run_euler(oracle, lib, m, basis, resident, n_steps=2, local_time=False, use_filter=False, safety=0.7, devices=None, coords=None):
     ref, work = m.copy(), m.copy()
     h = H.HostHarness(lib, m, basis, seed=3)
+    if devices is not None:
+        h.set_devices(devices)
+        if coords is not None:
+            h.set_element_coordinates(coords)
     h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
     h.invalidate()
     dts = []
@@ -97,8 +102,13 @@ def run_euler(oracle, lib, m, basis, resident, n_steps=2, local_time=False, use_
         h.to_host(H.ALL_ELEM | H.FACES | H.UNCERT)
     h.fetch(work)
     units = h.work_units()
+    if devices is not None:
+        run_euler.last_owners = h.element_owners().copy()
+        run_euler.last_transport = h.transport_description()
     h.set_sync_mode(H.SYNC_EVERY_CALL)
     h.close()
+    if devices is not None:
+        h2 = H.HostHarness(lib, m, basis, seed=3); h2.set_devices([0]); h2.close()
     return work, ref, dts, units
 
 
@@ -112,10 +122,12 @@ def check_work_units(m, units, n_steps, diffusive_stage0=0):
     assert units[9] > 0
 
 
-def run_pde(oracle, lib, m, basis, pde, resident):
+def run_pde(oracle, lib, m, basis, pde, resident, devices=None):
     ref, work = m.copy(), m.copy()
     wide = pde == ADVECTION
     h = H.HostHarness(lib, m, basis, seed=4)
+    if devices is not None:
+        h.set_devices(devices)
     if wide:
         h.put(m, wide=True)
     h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
@@ -163,6 +175,8 @@ def run_pde(oracle, lib, m, basis, pde, resident):
         work.face_wide, ref.face_wide = None, None
     h.set_sync_mode(H.SYNC_EVERY_CALL)
     h.close()
+    if devices is not None:
+        h2 = H.HostHarness(lib, m, basis, seed=4); h2.set_devices([0]); h2.close()
     return work, ref, [(dt_d, dt_o)]
 
 
@@ -189,6 +203,64 @@ def test_adapter_other_pdes_emu(oracle, host_emu, pde, resident):
     prepare_pde_state(m, rng, pde)
     out, ref, dts = run_pde(oracle, host_emu, m, hb.gauss_legendre(3), pde, resident)
     assert_pde_parity(out, ref, dts)
+
+
+# ---- one Kernel_mesh on several devices BEHIND the kernels.hpp boundary (hexed_b200::set_devices). The emulation build
+# runs the same partitioning, halo bookkeeping and stage splitting with memcpy where the product posts the NCCL group.
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("nd,rs,n_dev", [(2, 3, 2), (2, 3, 3), (3, 2, 4)])
+def test_adapter_multi_device_euler_emu(oracle, host_emu, nd, rs, n_dev, resident):
+    m, _ = soup(nd, rs, 61, with_ldg=True)  # hanging faces, every direction; the graph ordering cuts through all of it
+    oracle.compute_prolong(hb.gauss_legendre(rs), m)  # the soup's faces are random: make the mortar faces what they are after any stage
+    n_steps = 2 if nd == 2 else 1  # (the meaningless 3-D soup geometry goes non-finite in its fourth stage, reference included)
+    out, ref, dts, units = run_euler(oracle, host_emu, m, hb.gauss_legendre(rs), resident, n_steps=n_steps, devices=[0]*n_dev)
+    assert np.isfinite(ref.state()).all()
+    assert_euler_parity(out, ref, dts)
+    check_work_units(m, units, n_steps)
+    assert len(set(run_euler.last_owners.tolist())) == n_dev
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_multi_device_box_morton_emu(oracle, host_emu, resident):
+    basis = hb.gauss_legendre(3)
+    m = M.box_mesh(3, 3, 4, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler(oracle, host_emu, m, basis, resident, n_steps=2, devices=[0]*8, coords=m.elem_index)
+    assert_euler_parity(out, ref, dts)
+    from hexed_b200 import partition as P
+    assert np.array_equal(run_euler.last_owners, P.split_by_curve(P.morton_keys(m.elem_index), 8))  # 8 octants of 8 elements
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_multi_device_refined_box_emu(oracle, host_emu, resident):
+    """the onera_m6 class: Cartesian hanging-node faces cut by the device split"""
+    basis = hb.gauss_legendre(3)
+    refine = np.zeros((4, 4), bool); refine[1, 1] = refine[2, 2] = refine[3, 0] = True
+    m = M.refined_box_mesh(2, 3, 4, basis, refine, bc_kind=M.BC_COPY)
+    M.random_flow_state(m, np.random.default_rng(5), mach=0.2)
+    oracle.compute_write_face(basis, m); oracle.compute_prolong(basis, m)
+    out, ref, dts, _ = run_euler(oracle, host_emu, m, basis, resident, n_steps=2, devices=[0]*3)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_multi_device_navier_stokes_emu(oracle, host_emu, resident):
+    m, rng = soup(2, 3, 62, with_ldg=True, with_wide=True)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    oracle.compute_prolong(hb.gauss_legendre(3), m)
+    out, ref, dts = run_pde(oracle, host_emu, m, hb.gauss_legendre(3), NAVIER_STOKES, resident, devices=[0, 0, 0])
+    assert_pde_parity(out, ref, dts)
+
+
+def test_adapter_multi_device_unsupported_entry_points_say_so(oracle, host_emu):
+    m, rng = soup(2, 3, 63, with_ldg=True, with_wide=True)
+    h = H.HostHarness(host_emu, m, hb.gauss_legendre(3))
+    h.set_devices([0, 0])
+    with pytest.raises(RuntimeError, match="not available on more than one device"):
+        h.call("compute_advection", 0.7, dt=1e-4, i_stage=0)
+    h.set_devices([0])
+    h.close()
 
 
 @pytest.mark.parametrize("resident", [False, True])
@@ -437,4 +509,71 @@ def test_adapter_other_pdes_gpu(oracle, host_gpu, pde, resident):
     m, rng = soup(3, 4, 80 + pde, with_ldg=True, with_wide=True)
     prepare_pde_state(m, rng, pde)
     out, ref, dts = run_pde(oracle, host_gpu, m, hb.gauss_legendre(4), pde, resident)
+    assert_pde_parity(out, ref, dts)
+
+
+# ------------------------------------------------------------------------------------------------ B200s: one Kernel_mesh on several GPUs through the adapter
+def _gpu_devices(n):
+    import ctypes
+    from hexed_b200.kernels import load_library
+    count = ctypes.c_int(0)
+    load_library().hexed_b200_device_count(ctypes.byref(count))
+    if count.value < n:
+        pytest.skip("needs %d CUDA devices, this box has %d" % (n, count.value))
+    return list(range(n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("nd,rs,n_dev", [(2, 6, 2), (3, 4, 2), (3, 6, 2), (3, 6, 4), (3, 6, 8)])
+def test_adapter_multi_device_euler_gpu(oracle, host_gpu, nd, rs, n_dev, resident):
+    """hexed::compute_euler / max_dt_euler of ONE Kernel_mesh on n_dev B200s: NCCL send/recv of the cut faces + ncclAllReduce(min),
+    hanging faces of every stretch split across devices, against the CPU checker on the undivided mesh"""
+    devices = _gpu_devices(n_dev)
+    m, _ = soup(nd, rs, 71, n_car=16, n_def=40, n_ref=8, with_ldg=True)
+    oracle.compute_prolong(hb.gauss_legendre(rs), m)
+    out, ref, dts, units = run_euler(oracle, host_gpu, m, hb.gauss_legendre(rs), resident, n_steps=1, devices=devices)
+    assert np.isfinite(ref.state()).all()
+    assert_euler_parity(out, ref, dts)
+    check_work_units(m, units, 1)
+    assert len(set(run_euler.last_owners.tolist())) == n_dev
+    assert "NCCL" in run_euler.last_transport
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("n_dev", [2, 8])
+def test_adapter_multi_device_box_gpu(oracle, host_gpu, n_dev, resident):
+    devices = _gpu_devices(n_dev)
+    basis = hb.gauss_legendre(6)
+    m = M.box_mesh(3, 6, 8, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler(oracle, host_gpu, m, basis, resident, n_steps=2, devices=devices, coords=m.elem_index)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_multi_device_refined_box_gpu(oracle, host_gpu, resident):
+    """C5 class on hardware: Cartesian hanging-node faces cut by the device split"""
+    devices = _gpu_devices(2)
+    basis = hb.gauss_legendre(6)
+    refine = np.zeros((4, 4, 4), bool); refine[1, 1, 1] = refine[2, 2, 1] = refine[3, 0, 2] = True
+    m = M.refined_box_mesh(3, 6, 4, basis, refine, bc_kind=M.BC_COPY)
+    M.random_flow_state(m, np.random.default_rng(5), mach=0.2)
+    oracle.compute_write_face(basis, m); oracle.compute_prolong(basis, m)
+    out, ref, dts, _ = run_euler(oracle, host_gpu, m, basis, resident, n_steps=2, devices=devices)
+    assert_euler_parity(out, ref, dts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("n_dev", [2, 4])
+def test_adapter_multi_device_navier_stokes_gpu(oracle, host_gpu, n_dev, resident):
+    devices = _gpu_devices(n_dev)
+    m, rng = soup(3, 4, 72, n_car=12, n_def=30, n_ref=6, with_ldg=True, with_wide=True)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    oracle.compute_prolong(hb.gauss_legendre(4), m)
+    out, ref, dts = run_pde(oracle, host_gpu, m, hb.gauss_legendre(4), NAVIER_STOKES, resident, devices=devices)
     assert_pde_parity(out, ref, dts)

@@ -146,13 +146,17 @@ def test_morton_split_is_balanced_and_compact():
         assert (sel.max(0) - sel.min(0)).tolist() == [3, 3, 3]
 
 
-@pytest.mark.parametrize("kind,n_parts", [("soup2d", 3), ("box_def", 2)])
+@pytest.mark.parametrize("kind,n_parts", [("soup2d", 3), ("box_def", 2), ("soup3d", 4), ("refined_box3d", 3)])
 def test_partitioned_device_begin_finish(oracle, emu_lib, kind, n_parts):
     """the split stage (compute_euler_begin / exchange / compute_euler_finish) of the CUDA sources, several parts in one process"""
     from hexed_b200.kernels import Device
     rng = np.random.default_rng(7)
     basis, m = make_case(kind, rng)
-    if kind.startswith("box"):
+    if kind.startswith("refined_box"):
+        oracle.compute_write_face(basis, m)
+        oracle.compute_prolong(basis, m)
+        part = rng.integers(0, n_parts, m.n_elem)
+    elif kind.startswith("box"):
         oracle.compute_write_face(basis, m)
         part = P.split_by_curve(P.morton_keys(m.elem_index), n_parts)
     else:
