@@ -497,7 +497,9 @@ static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
   using C = PipeCfg<RS, DEF, LEAN>;
   void (*k)(PipeArgs, Ops) = local_euler_pipe_kernel<RS, DEF, CFL, LEAN>;
   if constexpr (LEAN && !DEF) k = local_euler_pipe4_kernel<RS>;
-  static int blocks_per_sm = 0; // per instantiation
+  // function attributes and occupancy are per DEVICE (one host process may drive several: hexed_b200_group_*): cached per instantiation and device
+  static int blocks_per_sm_of [64] = {};
+  int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
   if (!blocks_per_sm) {
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

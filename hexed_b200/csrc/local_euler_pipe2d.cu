@@ -310,7 +310,8 @@ static int launch_pipe2(hexed_b200_ctx* c, const Pipe2Args& a)
 {
   using C = Pipe2Cfg<RS, DEF>;
   auto k = local_euler_pipe2d_kernel<RS, DEF>;
-  static int blocks_per_sm = 0; // per instantiation
+  static int blocks_per_sm_of [64] = {}; // per instantiation and device (function attributes are per device)
+  int& blocks_per_sm = blocks_per_sm_of[c->device & 63];
   if (!blocks_per_sm) {
     HB_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
     int n = 0;

@@ -233,6 +233,7 @@ int launch_max_dt_euler(hexed_b200_ctx* c, double safety_conv, int local_time, d
     if (!local_time && max_dt_running_screen && total < (1ll << 32) - 256) {
       int* screen_bits = reinterpret_cast<int*>(c->d_scalar + 1);
       HB_CUDA(c, cudaMemsetAsync(screen_bits, 0x7f, sizeof(int), c->stream)); // 0x7f7f7f7f = 3.39e38
+      static_assert(max_dt_ppt == 1, "max_dt_euler_screen_kernel handles exactly one point per thread: its grid must cover `total` threads");
       auto k = max_dt_euler_screen_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops, screen_bits);
     }
     else { auto k = max_dt_euler_kernel<ND, RS>; HB_LAUNCH(k, grid, 256, 0, c->stream, a, c->ops); }

@@ -11,6 +11,7 @@
 #include "adapter.hpp"
 
 #include <algorithm>
+#include <omp.h>
 #include <cstring>
 #include <random>
 #include <unordered_map>
@@ -545,4 +546,51 @@ int hbp_owners_by_morton(int n_dim, int n_car, int n_elem, const int* coords, in
   return 0;
 }
 
+}
+
+// ---- the host boundary-condition loop of Solver::apply_state_bcs (src/Solver.cpp:56-67): an OpenMP loop over the boundary
+// connections with one virtual Flow_bc::apply_state call per face, written the way the reference's conditions are (this is what a
+// Solver keeps doing on the host between kernel calls when its conditions are not registered on the device). bench.py times it
+// inside its end-to-end step; kind: 0 Freestream (src/Boundary_condition.cpp:66-76), 2 Nonpenetration (:301-327). ----
+namespace
+{
+struct Host_bc {virtual ~Host_bc() = default; virtual void apply_state(double* inside, double* ghost, const double* normal, int nd, int nfq) = 0;};
+struct Host_freestream : Host_bc
+{
+  std::vector<double> fs;
+  void apply_state(double*, double* ghost, const double*, int nd, int nfq) override
+  {
+    for (int v = 0; v < nd + 2; ++v) for (int q = 0; q < nfq; ++q) ghost[v*nfq + q] = fs[v];
+  }
+};
+struct Host_nonpenetration : Host_bc
+{
+  void apply_state(double* inside, double* ghost, const double* n, int nd, int nfq) override
+  {
+    for (int k = 0; k < (nd + 2)*nfq; ++k) ghost[k] = inside[k];
+    for (int q = 0; q < nfq; ++q) {
+      double dot = 0., nsq = 0.;
+      for (int d = 0; d < nd; ++d) {dot += ghost[d*nfq + q]*n[d*nfq + q]; nsq += n[d*nfq + q]*n[d*nfq + q];}
+      for (int d = 0; d < nd; ++d) ghost[d*nfq + q] -= 2*dot*n[d*nfq + q]/nsq;
+    }
+  }
+};
+}
+
+extern "C" int hbh_host_state_bcs(void* handle, int kind, const double* params, int n_params, const int* def_con_index, int n, int n_threads)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    std::unique_ptr<Host_bc> bc;
+    if (kind == 0) {auto* f = new Host_freestream; f->fs.assign(params, params + n_params); bc.reset(f);}
+    else if (kind == 2) bc.reset(new Host_nonpenetration);
+    else throw std::runtime_error("host boundary condition kind not provided by the harness");
+    const int nd = h->nd, nfq = h->nfq;
+    #pragma omp parallel for num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+    for (int i = 0; i < n; ++i) {
+      H_connection& c = *h->def_cons[def_con_index[i]];
+      bc->apply_state(c.state(0, false), c.state(1, false), c.normal(), nd, nfq);
+    }
+    return 0;
+  } catch (const std::exception& ex) {h->error = ex.what(); return 1;}
 }

@@ -16,7 +16,8 @@
 TAG=${TAG:-r02}
 N=${N:-2}
 mkdir -p gpurun_out
-logs=()
+(nvidia-smi --query-gpu=index,name,memory.total --format=csv,noheader; echo "nproc $(nproc)"; lscpu | grep -m1 "Model name"; free -g | head -2; ulimit -a | grep -E "memory|locked") > gpurun_out/box_$TAG.log 2>&1
+logs=(box_$TAG)
 run() { # name, command...
   local name=$1; shift
   "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log

@@ -86,6 +86,7 @@ class HostHarness:
         L.hbh_is_admissible.argtypes = [C.c_void_p, ip, ip]
         L.hbh_av_glue.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_int, dp]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
+        L.hbh_host_state_bcs.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, ip, C.c_int, C.c_int]
         L.hbh_set_devices.argtypes = [C.c_void_p, ip, C.c_int]
         L.hbh_set_element_coordinates.argtypes = [C.c_void_p, ip]
         L.hbh_element_owners.argtypes = [C.c_void_p, ip]
@@ -143,6 +144,12 @@ class HostHarness:
     def ghost_faces_to_device(self): self.control(4)
     def invalidate(self): self.control(5)
     def release(self): self.control(6)
+
+    def host_state_bcs(self, kind, params, def_con_index, n_threads=0):
+        """the host loop of Solver::apply_state_bcs over the listed boundary connections (Freestream = 0, Nonpenetration = 2)"""
+        p = np.ascontiguousarray(params if params is not None else np.zeros(1), dtype=np.float64)
+        idx = np.ascontiguousarray(def_con_index, dtype=np.int32)
+        self._check(self.lib.hbh_host_state_bcs(self.h, kind, _d(p), p.size, _i(idx), idx.size, n_threads))
 
     def set_devices(self, devices):
         d = np.ascontiguousarray(devices, dtype=np.int32)
