@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
     ap.add_argument("--pipe-mode", type=int, default=1, help="HEXED_B200_OPT_PIPELINED_LOCAL value (A/B: 2 = earlier shared-memory layout of the 3-D deformed kernel)")
+    ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 64, or 48 when host memory is short: "
+                    "the reference keeps 85 KB of host objects per deformed element)")
+    ap.add_argument("--no-aux-lines", action="store_true", help="skip the Navier-Stokes / Cartesian sub-lines of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -127,6 +130,131 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    avail = 0.
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = float(line.split()[1])/1e6
+    except OSError:
+        pass
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return {"cpu_model": model, "cores": cores, "mem_available_gb": avail}
+
+
+def adapter_e2e(args, n_dev, viscous, steps, warmup, sync_every_call=False, n_override=None):
+    """The metric measured the way a Hexed user would see it: through hexed::max_dt_* / hexed::compute_* of the C++ adapter
+    (hexed_b200/libhexed_b200_host.so = adapter.cpp + the pointer-graph mesh of harness.cpp standing in for Solver's Accessible_mesh),
+    one Kernel_mesh on n_dev GPUs (hexed_b200::set_devices: Morton split, NCCL halo exchange, dt allreduce -- all below the boundary),
+    state resident on the devices, boundary conditions applied BY THE HOST every stage as Solver::apply_state_bcs does
+    (src/Solver.cpp:56-67): inside faces D2H, an OpenMP loop of per-face virtual Flow_bc calls over the host objects, ghost faces H2D.
+    Timed with the host clock between device synchronisations (the host loop is part of the step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import hexed_b200 as hb
+    from hexed_b200 import mesh as M
+    from hexed_b200.cases import density_wave, freestream_state
+    import host_harness as H
+    info = host_info()
+    nd, rs = args.dim, 6
+    n_gpu = n_override or args.adapter_n or (64 if info["mem_available_gb"] >= 60.*n_dev else 48)
+    if nd == 2:
+        n_gpu = int(round(n_gpu**1.5))
+    n = int(round(n_gpu*n_dev**(1./nd)))
+    deformed = args.mesh == "deformed"
+    basis = hb.gauss_legendre(rs)
+    fs = freestream_state(nd)
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=fs, with_ldg=viscous)
+    density_wave(m, basis)
+    if viscous:
+        m.elem_data[:, M.BULK_AV_SLOT(nd)] = 0.; m.elem_data[:, M.LAPLACIAN_AV_SLOT(nd)] = 0.
+    ne, nv, nq, nfq = m.n_elem, m.nv, m.nq, m.nfq
+    rows = np.ascontiguousarray(m.bcs[0]["con_index"], dtype=np.int32)
+    coords = np.ascontiguousarray(m.elem_index)
+    h = H.HostHarness(H.build(emu=False), m, basis)
+    m.elem_data = None; m.ref_normals = None; m.det = None; m.face_state = None; m.face_ldg = None  # the host objects hold the data now
+    threads = info["cores"]
+    try:
+        h.set_devices(list(range(n_dev)))
+        if n_dev > 1:
+            h.set_element_coordinates(coords)
+        h.set_sync_mode(H.SYNC_EVERY_CALL if sync_every_call else H.RESIDENT)
+        h.invalidate()
+        h.call("compute_write_face")
+        visc, cond = H.sutherland(1.716e-5, 273., 111.), H.sutherland(0.0241, 273., 194.)
+
+        def state_bcs():
+            if not sync_every_call:
+                h.inside_state_faces_to_host()
+            h.host_state_bcs(0, fs, rows, threads)
+            if not sync_every_call:
+                h.ghost_state_faces_to_device()
+
+        def flux_bcs():  # runs inside compute_navier_stokes (its flux_bc callback), like Solver::apply_flux_bcs
+            if not sync_every_call:
+                h.inside_ldg_faces_to_host()
+            h.host_flux_bcs(rows, threads)
+            if not sync_every_call:
+                h.ghost_ldg_faces_to_device()
+        if viscous:
+            h.set_flux_bc(flux_bcs)
+
+        def step():
+            if viscous:
+                dt = h.call("max_dt_navier_stokes", 0.7, 0.7, False, *visc, *cond)
+                state_bcs()
+                h.call("compute_navier_stokes", *visc, *cond, dt=dt, i_stage=0)
+                state_bcs()
+                h.call("compute_euler", dt=dt, i_stage=1)
+            else:
+                dt = h.call("max_dt_euler", 0.7, 0.7, False)
+                for stage in (0, 1):
+                    state_bcs()
+                    h.call("compute_euler", dt=dt, i_stage=stage)
+        for _ in range(warmup):
+            step()
+        h.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        h.synchronize()
+        sec = time.perf_counter() - t0
+        transport = h.transport_description()
+        owners = np.bincount(h.element_owners(), minlength=n_dev).tolist()
+    finally:
+        h.set_sync_mode(H.SYNC_EVERY_CALL)
+        h.release()
+        h.set_devices([0])
+        h.close()
+    nb, w = rows.size, nv*nfq
+    per_stage = nb*w*8
+    n_exch = 2 + (2 if viscous else 0)  # state faces every stage (+ LDG faces down and up inside the viscous stage)
+    if sync_every_call:
+        elem_bytes = ne*(nv + 1 + (6 if viscous else 0) + max(nv, rs))*nq*8
+        face_bytes = m.n_face_slot*2*w*8
+        geom = ne*((nd*nd + 1)*nq*8 if deformed else 0)
+        h2d = 3*(elem_bytes + face_bytes + geom)
+        d2h = 2*(elem_bytes + face_bytes) + ne*nq*8
+        mode = ("sync_every_call (the zero-Solver-change default of the adapter): every hexed:: call uploads what it reads from the host objects, "
+                "metric terms included, and downloads what it wrote")
+    else:
+        h2d, d2h = n_exch*per_stage, n_exch*per_stage + 8
+        mode = ("adapter (hexed::max_dt_*/compute_* of hexed_b200/host/adapter.cpp on a pointer-graph Kernel_mesh), resident; per stage: inside boundary faces "
+                "D2H (prefetched on a copy stream, pinned), host OpenMP loop of per-face Freestream::apply_state over the host objects (%d threads), ghost faces H2D "
+                "(deferred: lands after the interior Neighbor kernels); dt D2H per step" % threads)
+    return {"value": ne*nv*nq*2*steps/sec, "unit": "DOF-stage/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec/steps*1e3,
+            "mode": mode, "elements": ne, "elements_per_gpu": owners, "box": "%d^%d" % (n, nd), "transport": transport, "host": info,
+            "timing": "host clock between device synchronisations, %d steps after %d warm-up" % (steps, warmup)}
 
 
 def build_native_oracle():
@@ -204,6 +332,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # for waits that must not park a spinning NCCL kernel on the other ranks' GPUs
     nd, rs, n = args.dim, 6, args.n
     if nd == 2 and args.n == 100:
         n = 1000  # 10^6 quads
@@ -311,11 +440,30 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    launches0 = dev.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    sec = timed(step, args.steps)
-    clocks = sampler.stop() if sampler else None
-    launches = dev.launch_count() - launches0
+    # One GPU: the headline is the flow loop of Solver::update with the time step kept on the device (hexed_b200_update_euler /
+    # _navier_stokes: max_dt -> dt never read back, boundary conditions on the device, one CUDA graph per step), i.e. no host
+    # synchronisation inside the timed region. Several GPUs under torchrun: call by call (one dt allreduce + read-back per step).
+    device_loop = world == 1
+    if device_loop:
+        def run_steps(k):
+            if viscous:
+                dev.update_navier_stokes(0.7, visc, cond, k)
+            else:
+                dev.update_euler(0.7, k)
+        run_steps(max(args.warmup, 1))
+        l0 = dev.launch_count(); run_steps(1); launches_per_step = dev.launch_count() - l0
+        sampler = ClockSampler(local_rank)
+        sec = timed(lambda: run_steps(args.steps), 1)
+        clocks = sampler.stop()
+        launches = launches_per_step*args.steps  # (graph replays do not pass through the host-side counter)
+        sec_call_by_call = timed(step, args.steps)
+    else:
+        launches0 = dev.launch_count()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sec = timed(step, args.steps)
+        clocks = sampler.stop() if sampler else None
+        launches = dev.launch_count() - launches0
+        sec_call_by_call = sec
     dof_stage = ne*nv*nq*2*args.steps*world
     value = dof_stage/sec
 
@@ -373,8 +521,8 @@ def main():
     # Solver::apply_state_bcs does, src/Solver.cpp:56-67), so every stage the inside boundary faces go D2H and the ghost faces
     # come back H2D, pinned memory, inside the timed region. The boundary connections are declared "late" (set_partition), so the
     # flux on interior connections (compute_euler_begin) runs while the faces cross PCIe on a copy stream. ----
-    e2e = None
-    if not args.no_e2e and not viscous:
+    e2e_api = None
+    if not args.no_e2e and not viscous and world == 1:
         bc = m.bcs[0]
         inside_list, ghost_list = dev.face_list(bc["inside_slot"]), dev.face_list(bc["ghost_slot"])
         nb, w = bc["inside_slot"].size, nv*m.nfq
@@ -413,9 +561,33 @@ def main():
             step_e2e()
         sec_e2e = timed(step_e2e, args.steps)
         dev.set_partition(n_cut_car, n_cut_def, getattr(m, "pre_prolong", ()))
-        e2e = {"value": dof_stage/sec_e2e, "unit": "DOF-stage/s", "h2d_bytes_per_step": 2*nb*w*8, "d2h_bytes_per_step": 2*nb*w*8 + 8,
-               "mode": "resident state; per stage the inside boundary faces go D2H (pinned), the host applies the ghost-state BC, ghost "
-                       "faces go H2D; copies on a side stream overlap the interior-connection flux; dt D2H per step"}
+        e2e_api = {"value": dof_stage/sec_e2e, "unit": "DOF-stage/s", "h2d_bytes_per_step": 2*nb*w*8, "d2h_bytes_per_step": 2*nb*w*8 + 8,
+                   "mode": "C ABI driven from Python (ctypes Device), resident state, 1 M elements; per stage the inside boundary faces go D2H (pinned), a "
+                           "constant ghost state is broadcast into a pinned buffer, ghost faces go H2D; copies on a side stream overlap the "
+                           "interior-connection flux; dt D2H per step. The lower bound of what host-applied boundary conditions cost: no host objects to scatter into"}
+        aux["e2e_c_abi_from_python"] = e2e_api
+
+    # ---- end to end the way a Hexed user would call it: hexed::max_dt_* / compute_* of the C++ adapter on a pointer-graph Kernel_mesh with
+    # the host boundary-condition loop of Solver::apply_state_bcs; at N > 1 rank 0's process drives all N GPUs through ONE Kernel_mesh
+    # (the split, the NCCL halo exchange and the dt allreduce happen below the kernels.hpp boundary) while the other ranks wait ----
+    e2e = None
+    if not args.no_e2e:
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                e2e = adapter_e2e(args, world, viscous, args.steps, 3)
+            except Exception as ex:
+                e2e = {"value": None, "unit": "DOF-stage/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "mode": "adapter run failed: %r" % (ex,)}
+            if world == 1 and not args.no_aux_lines and not viscous:
+                try:  # what the adapter's zero-Solver-change default costs (every call moves everything over PCIe), once, on a small mesh
+                    sc = adapter_e2e(args, 1, False, 2, 1, sync_every_call=True, n_override=24)
+                    aux["e2e_adapter_sync_every_call"] = {k: sc[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "elements", "mode")}
+                except Exception as ex:
+                    aux["e2e_adapter_sync_every_call"] = {"value": None, "mode": "failed: %r" % (ex,)}
+        if dist is not None:
+            dist.barrier(group=host_group)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -431,6 +603,10 @@ def main():
             "ms_per_step": sec/args.steps*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, viscous),
+                       "timed_path": ("hexed_b200_update_%s: the flow loop of Solver::update with dt kept on the device, device boundary conditions, one CUDA graph per "
+                                      "step, no host synchronisation in the timed region (call by call through compute_euler/max_dt_euler with a dt read-back per step: "
+                                      "%.2f ms/step)" % ("navier_stokes" if viscous else "euler", sec_call_by_call/args.steps*1e3)) if device_loop else
+                                     "call by call: max_dt (NCCL allreduce + read-back) + 2 x (device boundary conditions + split stage around the halo exchange)",
                        "elements_per_gpu": ne, "dof_per_element": nv*nq, "stages_per_step": 2,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (ne*(50e3 if nd == 3 else 6.2e3)/1e9),
                        "parallelism": "1 GPU" if world == 1 else
@@ -441,9 +617,15 @@ def main():
             "roofline": {"bound": "hbm", "kernel": local_name,
                          "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak,
                          "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+                         "frac_traffic": (traffic["bytes"]/local_sec/1e9/peak) if traffic else None,
+                         "algorithmic_bytes_note": "SURVEY 8(d) fixed denominator; for Euler it charges the Local kernel 648 doubles/element of face normals that "
+                                                   "neither the reference's Euler Local nor ours reads, hence frac_traffic (DRAM bytes measured by ncu) < frac",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
                          "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/float(nv*nq)},
-                         "kernel_seconds_per_step": shares},
+                         "kernel_seconds_per_step": shares,
+                         "accounting": {"sum_kernels_ms": sum(shares.values())*1e3, "ms_per_step": sec/args.steps*1e3,
+                                        "unaccounted_frac": 1. - sum(shares.values())/(sec/args.steps),
+                                        "note": "kernel times from a separate pass with per-launch CUDA events; the step itself is timed without them"}},
             "e2e": e2e, "cpu_baseline": cpu, "aux": aux,
         }
         print(json.dumps(out))

@@ -43,7 +43,14 @@ static void free_mesh(hexed_b200_ctx* c)
   dev_free(c->record); dev_free(c->elem_vertex); dev_free(c->matchers); dev_free(c->vertex_vals); dev_free(c->vertex_scratch);
   c->n_vertex = c->n_match = 0;
   c->n_cut_car = c->n_cut_def = c->n_pre_prolong = 0;
-  for (auto& l : c->lists) { dev_free(l.d_slots); dev_free(l.d_buf); }
+  for (auto& l : c->lists) {
+    dev_free(l.d_slots); dev_free(l.d_buf); dev_free(l.d_up);
+    if (l.h_down) cudaFreeHost(l.h_down);
+    if (l.h_up) cudaFreeHost(l.h_up);
+    if (l.ev_down) cudaEventDestroy(l.ev_down);
+    if (l.ev_up) cudaEventDestroy(l.ev_up);
+  }
+  c->n_pending_uploads = 0;
   c->lists.clear();
   for (auto& b : c->bcs) { dev_free(b.inside); dev_free(b.ghost); dev_free(b.normal); dev_free(b.params); dev_free(b.cache); }
   c->bcs.clear();
@@ -160,6 +167,8 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2, 0, 1, 2};
   for (int i = 0; i < ST_COUNT; ++i) { c->stats[i].name = names[i]; c->stats[i].deformed = trees[i]; }
   int rc = check(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  if (!rc) rc = check(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  if (!rc) rc = check(c, cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming), "cudaEventCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev0), "cudaEventCreate");
   if (!rc) rc = check(c, cudaEventCreate(&c->ev1), "cudaEventCreate");
   if (!rc) rc = dev_alloc(c, &c->d_scalar, 8);
@@ -186,6 +195,7 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   free_mesh(c);
   dev_free(c->perm); dev_free(c->d_scalar); dev_free(c->d_step); dev_free(c->d_face_scratch);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -193,6 +203,8 @@ int hexed_b200_destroy(hexed_b200_ctx* c)
   if (c->d_flags) cudaFree(c->d_flags);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -388,6 +400,7 @@ int hexed_b200_face_list_download(hexed_b200_ctx* c, int list_id, int kind, doub
   FaceList& l = c->lists[list_id];
   double* arr; int width;
   int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  if (l.down_kind >= 0) HB_CUDA(c, cudaStreamWaitEvent(c->stream, l.ev_down, 0)); // a prefetch is still reading d_buf
   rc = launch_gather_faces(c, arr, width, l.d_slots, l.n, l.d_buf); if (rc) return rc;
   if (l.n) HB_CUDA(c, cudaMemcpyAsync(dst, l.d_buf, sizeof(double)*l.n*width, cudaMemcpyDefault, c->stream));
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -403,6 +416,100 @@ int hexed_b200_face_list_upload(hexed_b200_ctx* c, int list_id, int kind, const 
   int rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
   if (l.n) HB_CUDA(c, cudaMemcpyAsync(l.d_buf, src, sizeof(double)*l.n*width, cudaMemcpyDefault, c->stream));
   return launch_scatter_faces(c, arr, width, l.d_slots, l.n, l.d_buf);
+}
+
+/* ---- asynchronous host traffic for HOST-applied boundary conditions (Solver::apply_state_bcs, src/Solver.cpp:56-67, when the
+ * conditions are not registered on the device): downloads are started as soon as the faces exist and collected later; uploads are
+ * started at once and land in the face storage inside the next stage driver, after its interior Neighbor kernels. ---- */
+static int list_async_buffers(hexed_b200_ctx* c, FaceList& l)
+{
+  if (l.h_down) return 0;
+  const size_t bytes = sizeof(double)*(l.buf_doubles ? l.buf_doubles : 1);
+  HB_CUDA(c, cudaMallocHost(&l.h_down, bytes));
+  HB_CUDA(c, cudaMallocHost(&l.h_up, bytes));
+  int rc = dev_alloc(c, &l.d_up, l.buf_doubles, false); if (rc) return rc;
+  HB_CUDA(c, cudaEventCreateWithFlags(&l.ev_down, cudaEventDisableTiming));
+  HB_CUDA(c, cudaEventCreateWithFlags(&l.ev_up, cudaEventDisableTiming));
+  return 0;
+}
+
+int hexed_b200_face_list_prefetch(hexed_b200_ctx* c, int list_id, int kind)
+{
+  HB_ENTER(c);
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  int rc = list_async_buffers(c, l); if (rc) return rc;
+  double* arr; int width;
+  rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  if (l.down_kind >= 0) HB_CUDA(c, cudaStreamWaitEvent(c->stream, l.ev_down, 0)); // an uncollected earlier prefetch still reads d_buf
+  rc = launch_gather_faces(c, arr, width, l.d_slots, l.n, l.d_buf); if (rc) return rc;
+  HB_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+  HB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+  if (l.n) HB_CUDA(c, cudaMemcpyAsync(l.h_down, l.d_buf, sizeof(double)*l.n*width, cudaMemcpyDeviceToHost, c->copy_stream));
+  HB_CUDA(c, cudaEventRecord(l.ev_down, c->copy_stream));
+  l.down_kind = kind;
+  return 0;
+}
+
+int hexed_b200_face_list_prefetched(hexed_b200_ctx* c, int list_id, int kind, const double** host)
+{
+  HB_ENTER(c);
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  if (l.down_kind != kind) { // nothing in flight for this kind: fetch now
+    int rc = hexed_b200_face_list_prefetch(c, list_id, kind); if (rc) return rc;
+  }
+  HB_CUDA(c, cudaEventSynchronize(l.ev_down));
+  l.down_kind = -1;
+  *host = l.h_down;
+  return 0;
+}
+
+int hexed_b200_face_list_staging(hexed_b200_ctx* c, int list_id, double** host)
+{
+  HB_ENTER_KEEP(c);
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  int rc = list_async_buffers(c, l); if (rc) return rc;
+  if (l.up_kind >= 0) HB_CUDA(c, cudaEventSynchronize(l.ev_up)); // the previous contents are still being read by the copy engine
+  *host = l.h_up;
+  return 0;
+}
+
+int hexed_b200_face_list_upload_deferred(hexed_b200_ctx* c, int list_id, int kind)
+{
+  HB_ENTER_KEEP(c);
+  if (list_id < 0 || list_id >= (int)c->lists.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown face list");
+  FaceList& l = c->lists[list_id];
+  int rc = list_async_buffers(c, l); if (rc) return rc;
+  double* arr; int width;
+  rc = list_face_array(c, kind, &arr, &width); if (rc) return rc;
+  if (l.up_kind >= 0) { rc = flush_pending_uploads(c); if (rc) return rc; }
+  // the scatter of the previous upload from d_up has been enqueued on `stream`: the copy engine must not overwrite d_up before it ran
+  HB_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+  HB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+  if (l.n) HB_CUDA(c, cudaMemcpyAsync(l.d_up, l.h_up, sizeof(double)*l.n*width, cudaMemcpyHostToDevice, c->copy_stream));
+  HB_CUDA(c, cudaEventRecord(l.ev_up, c->copy_stream));
+  l.up_kind = kind;
+  ++c->n_pending_uploads;
+  return 0;
+}
+
+extern "C++" {
+namespace hb {
+int flush_pending_uploads(hexed_b200_ctx* c)
+{
+  for (FaceList& l : c->lists) if (l.up_kind >= 0) {
+    double* arr; int width;
+    int rc = list_face_array(c, l.up_kind, &arr, &width); if (rc) return rc;
+    HB_CUDA(c, cudaStreamWaitEvent(c->stream, l.ev_up, 0));
+    rc = launch_scatter_faces(c, arr, width, l.d_slots, l.n, l.d_up); if (rc) return rc;
+    l.up_kind = -1;
+  }
+  c->n_pending_uploads = 0;
+  return 0;
+}
+}
 }
 
 int hexed_b200_face_permutation_table(hexed_b200_ctx* c, const int dir[4], int* out)
@@ -438,7 +545,12 @@ int hexed_b200_face_permutation(hexed_b200_ctx* c, const int dir[4], int restore
 
 int hexed_b200_compute_euler(hexed_b200_ctx* c, hexed_b200_options o)
 {
-  HB_ENTER(c);
+  HB_ENTER_KEEP(c);
+  if (c->n_pending_uploads) { // ghost faces still crossing PCIe: the connections declared late (hexed_b200_set_partition) wait for them, the rest runs now
+    int rc = hexed_b200_compute_euler_begin(c);
+    if (!rc) rc = hexed_b200_compute_euler_finish(c, o);
+    return rc;
+  }
   // reference src/kernels_convective.cpp:8-16: Neighbor(car) Neighbor(def) Restrict Local(car) Local(def) Prolong
   int rc;
   if ((rc = launch_neighbor_euler(c, 0))) return rc;
@@ -598,7 +710,7 @@ int hexed_b200_face_list_scatter(hexed_b200_ctx* c, int list_id, int kind, const
  *           of the reference sequence (src/kernels_convective.cpp:8-16) */
 int hexed_b200_compute_euler_begin(hexed_b200_ctx* c)
 {
-  HB_ENTER(c);
+  HB_ENTER_KEEP(c);
   int rc;
   if ((rc = launch_neighbor_euler(c, 0, 0, c->n_car_con - c->n_cut_car))) return rc;
   if ((rc = launch_neighbor_euler(c, 1, 0, c->n_def_con - c->n_cut_def))) return rc;
@@ -607,7 +719,7 @@ int hexed_b200_compute_euler_begin(hexed_b200_ctx* c)
 
 int hexed_b200_compute_euler_finish(hexed_b200_ctx* c, hexed_b200_options o)
 {
-  HB_ENTER(c);
+  HB_ENTER(c); // (scatters deferred ghost-face uploads: they have had the interior Neighbor kernels to arrive)
   int rc;
   if (c->n_pre_prolong && (rc = launch_prolong(c, 0, c->nv, 0, c->pre_prolong, c->n_pre_prolong))) return rc;
   if ((rc = launch_neighbor_euler(c, 0, c->n_car_con - c->n_cut_car, c->n_cut_car))) return rc;
@@ -695,7 +807,7 @@ static int diffusion_stage(hexed_b200_ctx* c, int pde, hexed_b200_options o, con
 /* compute_navier_stokes in three parts around the two halo exchanges of a partitioned mesh (see include/hexed_b200.h) */
 int hexed_b200_compute_navier_stokes_begin(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_transport visc, hexed_b200_transport therm_cond)
 {
-  HB_ENTER(c);
+  HB_ENTER_KEEP(c);
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   const PdeParams pp = make_params(c, 1, visc, therm_cond, 0., 0.);
   const GenericOps* g = generic_ops(1);
@@ -796,7 +908,16 @@ int hexed_b200_compute_advection(hexed_b200_ctx* c, hexed_b200_options o, double
 
 int hexed_b200_compute_navier_stokes(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user,
                                      hexed_b200_transport visc, hexed_b200_transport therm_cond)
-{ HB_ENTER(c); return diffusion_stage(c, 1, o, make_params(c, 1, visc, therm_cond, 0., 0.), flux_bc, user); }
+{
+  HB_ENTER_KEEP(c);
+  if (c->n_pending_uploads) { // as in hexed_b200_compute_euler
+    int rc = hexed_b200_compute_navier_stokes_begin(c, o, visc, therm_cond);
+    if (!rc) rc = hexed_b200_compute_navier_stokes_middle(c, o, flux_bc, user, visc, therm_cond);
+    if (!rc) rc = hexed_b200_compute_navier_stokes_finish(c, o, visc, therm_cond);
+    return rc;
+  }
+  return diffusion_stage(c, 1, o, make_params(c, 1, visc, therm_cond, 0., 0.), flux_bc, user);
+}
 
 int hexed_b200_compute_smooth_av(hexed_b200_ctx* c, hexed_b200_options o, hexed_b200_callback flux_bc, void* user, double diff_time, double chebyshev_step)
 { HB_ENTER(c); return diffusion_stage(c, 3, o, make_params(c, 3, no_transport, no_transport, diff_time, chebyshev_step), flux_bc, user); }

@@ -47,7 +47,16 @@ struct PdeParams
   double adv_nodes[MAX_RS];        // advection: Gauss-Legendre nodes mapped to [-1, 1] (reference include/pde.hpp:281)
 };
 
-struct FaceList { int n = 0; int* d_slots = nullptr; double* d_buf = nullptr; size_t buf_doubles = 0; };
+struct FaceList
+{
+  int n = 0; int* d_slots = nullptr; double* d_buf = nullptr; size_t buf_doubles = 0;
+  // asynchronous host traffic of host-applied boundary conditions (hexed_b200_face_list_prefetch / _upload_deferred): pinned host
+  // buffers, a second device buffer for the upload so that it cannot collide with a download in flight, events on the copy stream
+  double* h_down = nullptr; double* h_up = nullptr; double* d_up = nullptr;
+  cudaEvent_t ev_down = nullptr, ev_up = nullptr;
+  int down_kind = -1; // face kind of the prefetch in flight (-1: none)
+  int up_kind = -1;   // face kind of the deferred upload waiting to be scattered (-1: none)
+};
 struct Bc { int kind; int n; int *inside = nullptr, *ghost = nullptr, *normal = nullptr; double* params = nullptr; int n_params = 0;
             double* cache = nullptr; /* No_slip: Boundary_face::state_cache(), [n][nv*nfq] */ };
 
@@ -65,6 +74,9 @@ struct hexed_b200_ctx
   double orthogonal[hb::MAX_RS][hb::MAX_RS];
   double min_eig_conv = 0, min_eig_diff = 0, quad_safety = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // PCIe traffic of host-applied boundary conditions, overlapped with kernels on `stream`
+  cudaEvent_t ev_copy = nullptr;
+  int n_pending_uploads = 0;          // face lists whose deferred upload has not been scattered yet
   // mesh
   bool have_mesh = false;
   int n_car = 0, n_def = 0, n_elem = 0, n_face_slot = 0, n_normal_slot = 0, n_car_con = 0, n_def_con = 0, n_ref = 0;
@@ -124,11 +136,15 @@ namespace hb {
 __host__ __device__ inline int dir_code(int d0, int d1, int s0, int s1) { return d0 + 3*d1 + 9*s0 + 18*s1; }
 
 int fail(hexed_b200_ctx* c, int code, const std::string& msg);
+int flush_pending_uploads(hexed_b200_ctx* c);
 int check(hexed_b200_ctx* c, cudaError_t e, const char* what);
 #define HB_CUDA(c, call) do { int hb_rc_ = hb::check(c, (call), #call); if (hb_rc_) return hb_rc_; } while (0)
 /* every C ABI entry point makes its context's device current: one host thread may drive several contexts on different devices
  * (hexed_b200_group_*, the single-process multi-GPU path behind the C++ adapter) */
-#define HB_ENTER(c) do { cudaSetDevice((c)->device); } while (0)
+#define HB_ENTER_KEEP(c) do { cudaSetDevice((c)->device); } while (0)
+/* ... and, unless the entry point places them itself (the stage drivers scatter them after their interior Neighbor kernels), completes
+ * deferred ghost-face uploads first, so that nothing ever reads a face that is still on its way */
+#define HB_ENTER(c) do { cudaSetDevice((c)->device); if ((c)->n_pending_uploads) { int hb_rc_ = hb::flush_pending_uploads(c); if (hb_rc_) return hb_rc_; } } while (0)
 
 struct StatScope
 {

@@ -119,8 +119,8 @@ struct Rank
   std::vector<double*> normal_ptr;
   std::vector<int> def_con;                 // local [n][7]
   std::vector<int> boundary_con;            // local def_con rows that are boundary connections
-  int boundary_list = -1;                   // face list id of the boundary connections' faces
-  std::vector<int> boundary_slots;
+  int side_list [2] {-1, -1};               // face list ids: inside faces / ghost faces of the boundary connections
+  std::vector<int> side_slots [2];
   std::vector<double> staging;
 };
 
@@ -137,6 +137,8 @@ struct Mirror
   std::vector<std::array<int, 3>> coords; // optional integer element coordinates for the Morton split (set_element_coordinates)
   std::vector<double> packed_basis;
   bool device_bcs_ran = false; // set by apply_state_bcs / apply_flux_bcs; lets the flux_bc thunk see what its callback did
+  bool prefetch_inside = false; // resident mode, host-applied state BCs: stage drivers start the download of the inside faces themselves
+  bool prefetch_valid = false;  // nothing has touched the device faces since the last prefetch was started
   hexed_b200_ctx* ctx0() {return ranks.empty() ? nullptr : ranks[0].ctx;}
   void destroy_device_side()
   {
@@ -431,26 +433,53 @@ void move(Mirror& m, unsigned groups, bool up)
   }
 }
 
-void move_boundary(Mirror& m, bool up)
+/* boundary faces between the host objects and the device. side 0 = inside faces, 1 = ghost faces; half 0 = state, 1 = LDG.
+ * The two combinations a state boundary-condition loop needs, (inside, state, down) and (ghost, state, up), take the asynchronous
+ * route of include/hexed_b200.h "asynchronous variants" in resident mode. */
+void move_boundary(Mirror& m, bool up, unsigned sides = both_sides, unsigned halves = both_halves)
 {
   const int nfq = ipow(m.row_size, m.n_dim - 1), nv = m.n_dim + 2;
   const size_t width = size_t(nv)*nfq;
-  for (Rank& k : m.ranks) {
-    if (k.boundary_slots.empty()) continue;
-    const size_t n = k.boundary_slots.size();
-    k.staging.resize(width*n);
-    for (int kind = 0; kind < 2; ++kind) { // 0: state half, 1: LDG half
+  for (Rank& k : m.ranks) for (int side = 0; side < 2; ++side) {
+    if (!(sides & (1u << side)) || k.side_slots[side].empty()) continue;
+    const std::vector<int>& slots = k.side_slots[side];
+    const size_t n = slots.size();
+    for (int half = 0; half < 2; ++half) {
+      if (!(halves & (1u << half))) continue;
+      const bool fast = g_mode == resident && half == 0 && ((!up && side == 0) || (up && side == 1));
       if (up) {
+        double* buf;
+        if (fast) check(&m, hexed_b200_face_list_staging(k.ctx, k.side_list[side], &buf), k.ctx);
+        else {k.staging.resize(width*n); buf = k.staging.data();}
         #pragma omp parallel for
-        for (size_t i = 0; i < n; ++i) std::memcpy(k.staging.data() + width*i, k.face_ptr[k.boundary_slots[i]] + kind*width, width*sizeof(double));
-        check(&m, hexed_b200_face_list_upload(k.ctx, k.boundary_list, kind, k.staging.data()), k.ctx);
+        for (size_t i = 0; i < n; ++i) std::memcpy(buf + width*i, k.face_ptr[slots[i]] + half*width, width*sizeof(double));
+        if (fast) check(&m, hexed_b200_face_list_upload_deferred(k.ctx, k.side_list[side], half), k.ctx);
+        else check(&m, hexed_b200_face_list_upload(k.ctx, k.side_list[side], half, buf), k.ctx);
       } else {
-        check(&m, hexed_b200_face_list_download(k.ctx, k.boundary_list, kind, k.staging.data()), k.ctx);
+        const double* buf;
+        if (fast) {
+          if (!m.prefetch_valid) check(&m, hexed_b200_face_list_prefetch(k.ctx, k.side_list[side], half), k.ctx); // what is in flight (if anything) is stale
+          check(&m, hexed_b200_face_list_prefetched(k.ctx, k.side_list[side], half, &buf), k.ctx);
+        }
+        else {
+          k.staging.resize(width*n);
+          check(&m, hexed_b200_face_list_download(k.ctx, k.side_list[side], half, k.staging.data()), k.ctx);
+          buf = k.staging.data();
+        }
         #pragma omp parallel for
-        for (size_t i = 0; i < n; ++i) std::memcpy(k.face_ptr[k.boundary_slots[i]] + kind*width, k.staging.data() + width*i, width*sizeof(double));
+        for (size_t i = 0; i < n; ++i) std::memcpy(k.face_ptr[slots[i]] + half*width, buf + width*i, width*sizeof(double));
       }
     }
   }
+  if (!up && g_mode == resident && (sides & inside) && (halves & state_half)) m.prefetch_inside = true;
+}
+
+//! resident mode with host-applied state BCs: start the download of the inside boundary faces the stage has just produced
+void prefetch_boundary(Mirror& m)
+{
+  if (!m.prefetch_inside || g_mode != resident) return;
+  for (Rank& k : m.ranks) if (!k.side_slots[0].empty()) check(&m, hexed_b200_face_list_prefetch(k.ctx, k.side_list[0], 0), k.ctx);
+  m.prefetch_valid = true;
 }
 
 Mesh_graph graph_of(const Flat_tables& t)
@@ -512,14 +541,30 @@ void build_device_side(Mirror& m)
       for (size_t i = 0; i < k.normal_ptr.size(); ++i) k.normal_ptr[i] = t.normal_ptr[pm.global_normal[i]];
       k.face_owned = pm.face_owned;
     }
-    k.def_con = lg.def_con; k.boundary_con = lg.boundary_con;
+    // local def_con order: [other interior connections | boundary connections | cut connections]. Boundary connections count as
+    // "late" like the cut ones (hexed_b200_set_partition), so that ghost faces uploaded by a host boundary-condition loop may still be
+    // on their way while the Neighbor kernels of the other connections run.
+    const size_t n_dc = lg.def_con.size()/7;
+    const size_t n_interior = n_dc - size_t(pm.n_cut_def);
+    std::vector<char> is_bnd(n_dc, 0);
+    for (int i : lg.boundary_con) is_bnd[i] = 1;
+    std::vector<size_t> order;
+    for (size_t i = 0; i < n_interior; ++i) if (!is_bnd[i]) order.push_back(i);
+    const size_t first_bnd = order.size();
+    for (size_t i = 0; i < n_interior; ++i) if (is_bnd[i]) order.push_back(i);
+    const int n_bnd = int(order.size() - first_bnd);
+    for (size_t i = n_interior; i < n_dc; ++i) order.push_back(i);
+    k.def_con.resize(lg.def_con.size());
+    for (size_t i = 0; i < n_dc; ++i) std::copy(lg.def_con.begin() + order[i]*7, lg.def_con.begin() + order[i]*7 + 7, k.def_con.begin() + i*7);
+    k.boundary_con.resize(n_bnd);
+    for (int i = 0; i < n_bnd; ++i) k.boundary_con[i] = int(first_bnd) + i;
     hexed_b200_mesh_desc d {};
     d.n_car = lg.n_car; d.n_def = lg.n_def; d.n_face_slot = lg.n_face_slot; d.n_normal_slot = lg.n_normal_slot;
-    d.n_car_con = int(lg.car_con.size()/3); d.n_def_con = int(lg.def_con.size()/7); d.n_ref = int(lg.ref_face.size()/7);
-    d.car_con = lg.car_con.data(); d.def_con = lg.def_con.data(); d.ref_face = lg.ref_face.data();
+    d.n_car_con = int(lg.car_con.size()/3); d.n_def_con = int(n_dc); d.n_ref = int(lg.ref_face.size()/7);
+    d.car_con = lg.car_con.data(); d.def_con = k.def_con.data(); d.ref_face = lg.ref_face.data();
     check(&m, hexed_b200_mesh_create(k.ctx, &d), k.ctx);
+    check(&m, hexed_b200_set_partition(k.ctx, pm.n_cut_car, pm.n_cut_def + n_bnd, int(pm.pre_prolong.size()), pm.pre_prolong.data()), k.ctx);
     if (n_ranks > 1) {
-      check(&m, hexed_b200_set_partition(k.ctx, pm.n_cut_car, pm.n_cut_def, int(pm.pre_prolong.size()), pm.pre_prolong.data()), k.ctx);
       std::vector<int> n_send, n_recv, send, recv;
       for (size_t i = 0; i < pm.peers.size(); ++i) {
         n_send.push_back(int(pm.send_slots[i].size())); n_recv.push_back(int(pm.recv_slots[i].size()));
@@ -528,10 +573,12 @@ void build_device_side(Mirror& m)
       }
       check_group(m, hexed_b200_group_set_halo(m.group, r, int(pm.peers.size()), pm.peers.data(), n_send.data(), send.data(), n_recv.data(), recv.data()));
     }
-    k.boundary_slots.clear();
-    for (int i : lg.boundary_con) {k.boundary_slots.push_back(lg.def_con[size_t(i)*7]); k.boundary_slots.push_back(lg.def_con[size_t(i)*7 + 1]);}
-    k.boundary_list = -1;
-    if (!k.boundary_slots.empty()) check(&m, hexed_b200_face_list_create(k.ctx, k.boundary_slots.data(), int(k.boundary_slots.size()), &k.boundary_list), k.ctx);
+    for (int side = 0; side < 2; ++side) {
+      k.side_slots[side].clear();
+      for (int i : k.boundary_con) k.side_slots[side].push_back(k.def_con[size_t(i)*7 + side]);
+      k.side_list[side] = -1;
+      if (n_bnd) check(&m, hexed_b200_face_list_create(k.ctx, k.side_slots[side].data(), n_bnd, &k.side_list[side]), k.ctx);
+    }
     upload_geometry(m, k);
   }
 }
@@ -574,6 +621,7 @@ struct Call
   unsigned out;
   Call(Kernel_mesh& km, unsigned in, unsigned out_groups) : m{mirror(km)}, out{out_groups}
   {
+    m.prefetch_valid = false; // this entry point may write faces: a download started earlier no longer describes them
     if (g_mode == sync_every_call) {
       // kernels write their outputs only partly (e.g. write_face leaves ghost and mortar faces alone), so everything that will be
       // downloaded must first hold the host's values
@@ -746,9 +794,11 @@ std::vector<int> element_owners(Kernel_mesh km) {return mirror(km).owner;}
 void invalidate() {for (auto& kv : g_mirrors) if (kv.second) {kv.second->have_mesh = false; kv.second->explicitly_invalidated = true;}}
 void release() {g_mirrors.clear();}
 void to_host(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(geometry), false);}
-void to_device(Kernel_mesh km, unsigned groups) {move(mirror(km), groups & ~unsigned(uncert), true);}
+void to_device(Kernel_mesh km, unsigned groups) {Mirror& m = mirror(km); m.prefetch_valid = false; move(m, groups & ~unsigned(uncert), true);}
 void boundary_faces_to_host(Kernel_mesh km) {move_boundary(mirror(km), false);}
 void ghost_faces_to_device(Kernel_mesh km) {move_boundary(mirror(km), true);}
+void boundary_faces_to_host(Kernel_mesh km, unsigned sides, unsigned halves) {move_boundary(mirror(km), false, sides, halves);}
+void ghost_faces_to_device(Kernel_mesh km, unsigned sides, unsigned halves) {move_boundary(mirror(km), true, sides, halves);}
 void synchronize(Kernel_mesh km)
 {
   Mirror& m = mirror(km);
@@ -926,6 +976,7 @@ void compute_euler(Kernel_mesh mesh, Kernel_options opts)
   Watch w; w.start(opts.sw_car); w.start(opts.sw_def);
   if (call.multi()) check_group(call.m, hexed_b200_group_compute_euler(call.m.group, options(opts)));
   else check(&call.m, hexed_b200_compute_euler(call.m.ctx0(), options(opts)));
+  prefetch_boundary(call.m);
   count_convective(mesh, opts);
   call.finish();
 }
@@ -947,6 +998,7 @@ void compute_navier_stokes(Kernel_mesh mesh, Kernel_options opts, std::function<
   Flux_bc_thunk thunk {&call.m, &flux_bc};
   if (call.multi()) check_group(call.m, hexed_b200_group_compute_navier_stokes(call.m.group, options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
   else check(&call.m, hexed_b200_compute_navier_stokes(call.m.ctx0(), options(opts), &Flux_bc_thunk::call, &thunk, transport(visc), transport(therm_cond)));
+  prefetch_boundary(call.m);
   count_diffusive(mesh, opts);
   call.finish();
 }

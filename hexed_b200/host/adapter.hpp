@@ -76,6 +76,17 @@ void to_host(hexed::Kernel_mesh, unsigned groups = everything);
 void to_device(hexed::Kernel_mesh, unsigned groups = everything | geometry);
 void boundary_faces_to_host(hexed::Kernel_mesh);  //!< both sides of every boundary connection, state + LDG halves
 void ghost_faces_to_device(hexed::Kernel_mesh);   //!< the same faces back
+/*! \brief the same traffic, only as much of it as a boundary-condition loop needs, and asynchronous where that pays.
+ * `Solver::apply_state_bcs` (src/Solver.cpp:56-67) reads `inside_face(false)` and writes `ghost_face(false)`: use
+ * `boundary_faces_to_host(mesh, inside, state_half)` before the loop and `ghost_faces_to_device(mesh, ghost, state_half)` after it. In
+ * resident mode the download of the inside faces is then STARTED by every stage driver as soon as its kernels are enqueued (pinned
+ * memory, copy stream) and only collected here, and the upload of the ghost faces is started here and lands in the face storage
+ * inside the next stage driver after its Neighbor kernels on the non-boundary connections, i.e. both PCIe trips overlap device work.
+ * `apply_flux_bcs` (:69-81) uses the LDG halves: (inside, ldg_half) / (ghost, ldg_half). */
+enum Face_side : unsigned {inside = 1, ghost = 2, both_sides = 3};
+enum Face_half : unsigned {state_half = 1, ldg_half = 2, both_halves = 3};
+void boundary_faces_to_host(hexed::Kernel_mesh, unsigned sides, unsigned halves);
+void ghost_faces_to_device(hexed::Kernel_mesh, unsigned sides, unsigned halves);
 void synchronize(hexed::Kernel_mesh);
 
 /*! \brief device-resident boundary conditions: removes the per-stage PCIe round trip of the boundary faces.

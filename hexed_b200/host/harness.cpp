@@ -295,6 +295,8 @@ int hbh_control(void* handle, int what, unsigned arg)
       case 5: hexed_b200::invalidate(); break;
       case 6: hexed_b200::release(); break;
       case 7: hexed_b200::synchronize(h->mesh()); break;
+      case 8: hexed_b200::boundary_faces_to_host(h->mesh(), arg & 3u, arg >> 2); break; // arg = sides | halves << 2
+      case 9: hexed_b200::ghost_faces_to_device(h->mesh(), arg & 3u, arg >> 2); break;
       default: throw std::runtime_error("unknown control code");
     }
     return 0;
@@ -593,4 +595,18 @@ extern "C" int hbh_host_state_bcs(void* handle, int kind, const double* params, 
     }
     return 0;
   } catch (const std::exception& ex) {h->error = ex.what(); return 1;}
+}
+
+// `Freestream::apply_flux` / `Copy::apply_flux` = copy_state of the LDG halves (src/Boundary_condition.cpp:12-23,304-305,455-458): the host
+// loop of Solver::apply_flux_bcs (src/Solver.cpp:69-81) for such conditions
+extern "C" int hbh_host_flux_bcs(void* handle, const int* def_con_index, int n, int n_threads)
+{
+  auto* h = static_cast<Harness*>(handle);
+  const size_t w = size_t(h->nv)*h->nfq;
+  #pragma omp parallel for num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+  for (int i = 0; i < n; ++i) {
+    H_connection& c = *h->def_cons[def_con_index[i]];
+    std::memcpy(c.state(1, true), c.state(0, true), w*sizeof(double));
+  }
+  return 0;
 }

@@ -66,6 +66,10 @@ SIGNATURES = {
     "hexed_b200_set_partition": [C.c_void_p, C.c_int, C.c_int, C.c_int, ip],
     "hexed_b200_face_list_gather": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "hexed_b200_face_list_scatter": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "hexed_b200_face_list_prefetch": [C.c_void_p, C.c_int, C.c_int],
+    "hexed_b200_face_list_prefetched": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
+    "hexed_b200_face_list_staging": [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)],
+    "hexed_b200_face_list_upload_deferred": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_compute_euler_begin": [C.c_void_p],
     "hexed_b200_compute_euler_finish": [C.c_void_p, Options],
     "hexed_b200_compute_navier_stokes_begin": [C.c_void_p, Options, Transport, Transport],

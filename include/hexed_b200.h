@@ -133,6 +133,19 @@ int hexed_b200_download_elem_slots(hexed_b200_ctx* ctx, double* dst, size_t elem
 int hexed_b200_face_list_create(hexed_b200_ctx* ctx, const int* slots, int n, int* list_id);
 int hexed_b200_face_list_download(hexed_b200_ctx* ctx, int list_id, int kind, double* dst);
 int hexed_b200_face_list_upload(hexed_b200_ctx* ctx, int list_id, int kind, const double* src);
+/* asynchronous variants for the per-stage traffic of HOST-applied boundary conditions (Solver::apply_state_bcs, src/Solver.cpp:56-67):
+ *   prefetch         gather the list's faces and start their device-to-host copy into a pinned buffer of the list, on a copy stream
+ *                    (call it right after the stage that produced the faces; returns at once)
+ *   prefetched       wait for that copy (starting it now if none is in flight) and return the pinned buffer [n][width(kind)]
+ *   staging          the list's pinned upload buffer [n][widest kind]: the caller writes the faces there ...
+ *   upload_deferred  ... and this starts the host-to-device copy at once; the faces are scattered into the face storage inside the next
+ *                    stage driver AFTER its Neighbor kernels on the connections not declared late by hexed_b200_set_partition (declare
+ *                    the boundary connections late and the copy overlaps the interior flux work). Any other entry point that could read
+ *                    the faces completes the upload first. */
+int hexed_b200_face_list_prefetch(hexed_b200_ctx* ctx, int list_id, int kind);
+int hexed_b200_face_list_prefetched(hexed_b200_ctx* ctx, int list_id, int kind, const double** host);
+int hexed_b200_face_list_staging(hexed_b200_ctx* ctx, int list_id, double** host);
+int hexed_b200_face_list_upload_deferred(hexed_b200_ctx* ctx, int list_id, int kind);
 /* integer table the kernels use for `Face_permutation::match_faces` (include/Spatial.hpp:85-129): out[nfq] */
 int hexed_b200_face_permutation_table(hexed_b200_ctx* ctx, const int dir[4], int* out);
 /* the same table without a context or a device (pure integer host logic, used by the C++ adapter's `face_permutation`):

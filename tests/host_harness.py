@@ -87,6 +87,7 @@ class HostHarness:
         L.hbh_av_glue.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, dp, C.c_int, dp]
         L.hbh_face_permutation.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_char_p, C.c_int]
         L.hbh_host_state_bcs.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, ip, C.c_int, C.c_int]
+        L.hbh_host_flux_bcs.argtypes = [C.c_void_p, ip, C.c_int, C.c_int]
         L.hbh_set_devices.argtypes = [C.c_void_p, ip, C.c_int]
         L.hbh_set_element_coordinates.argtypes = [C.c_void_p, ip]
         L.hbh_element_owners.argtypes = [C.c_void_p, ip]
@@ -142,6 +143,8 @@ class HostHarness:
     def to_device(self, groups): self.control(2, groups)
     def boundary_faces_to_host(self): self.control(3)
     def ghost_faces_to_device(self): self.control(4)
+    def inside_state_faces_to_host(self): self.control(8, 1 | 1 << 2)   # (inside, state_half): what Solver::apply_state_bcs reads
+    def ghost_state_faces_to_device(self): self.control(9, 2 | 1 << 2)  # (ghost, state_half): what it writes
     def invalidate(self): self.control(5)
     def release(self): self.control(6)
 
@@ -150,6 +153,14 @@ class HostHarness:
         p = np.ascontiguousarray(params if params is not None else np.zeros(1), dtype=np.float64)
         idx = np.ascontiguousarray(def_con_index, dtype=np.int32)
         self._check(self.lib.hbh_host_state_bcs(self.h, kind, _d(p), p.size, _i(idx), idx.size, n_threads))
+
+    def host_flux_bcs(self, def_con_index, n_threads=0):
+        idx = np.ascontiguousarray(def_con_index, dtype=np.int32)
+        self._check(self.lib.hbh_host_flux_bcs(self.h, _i(idx), idx.size, n_threads))
+
+    def inside_ldg_faces_to_host(self): self.control(8, 1 | 2 << 2)
+    def ghost_ldg_faces_to_device(self): self.control(9, 2 | 2 << 2)
+    def synchronize(self): self.control(7)
 
     def set_devices(self, devices):
         d = np.ascontiguousarray(devices, dtype=np.int32)

@@ -70,13 +70,21 @@ def test_flatten_box_with_cartesian_boundaries(host_emu):
 # ------------------------------------------------------------------------------------------------ drivers shared by emu and GPU
 def host_bcs(oracle, h, work, resident, flux=False):
     """what Solver::apply_state_bcs / apply_flux_bcs do: read the inside faces of the host objects, write the ghost faces"""
-    if resident:
+    lean = host_bcs.lean and resident and not flux
+    if lean:
+        h.inside_state_faces_to_host()  # asynchronous route: collected from the download the previous stage driver started
+    elif resident:
         h.boundary_faces_to_host()
     h.fetch(work)
     (oracle.apply_flux_bcs if flux else oracle.apply_state_bcs)(work)
     h.put(work)
-    if resident:
+    if lean:
+        h.ghost_state_faces_to_device()  # lands in the face storage inside the next stage driver, after its interior Neighbor kernels
+    elif resident:
         h.ghost_faces_to_device()
+
+
+host_bcs.lean = False
 
 
 def run_euler(oracle, lib, m, basis, resident, n_steps=2, local_time=False, use_filter=False, safety=0.7, devices=None, coords=None):
@@ -188,6 +196,19 @@ def test_adapter_euler_emu(oracle, host_emu, nd, rs, resident):
     out, ref, dts, units = run_euler(oracle, host_emu, m, hb.gauss_legendre(rs), resident, n_steps=2)
     assert_euler_parity(out, ref, dts)
     check_work_units(m, units, 2)
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0, 0]])
+def test_adapter_async_boundary_traffic_emu(oracle, host_emu, devices):
+    """resident mode with only (inside, state) down and (ghost, state) up, prefetched / deferred (adapter.hpp): same answer"""
+    m, _ = soup(2, 4, 23, with_ldg=True)
+    oracle.compute_prolong(hb.gauss_legendre(4), m)
+    host_bcs.lean = True
+    try:
+        out, ref, dts, _ = run_euler(oracle, host_emu, m, hb.gauss_legendre(4), True, n_steps=3, devices=devices)
+    finally:
+        host_bcs.lean = False
+    assert_euler_parity(out, ref, dts)
 
 
 def test_adapter_euler_options_emu(oracle, host_emu):
@@ -488,6 +509,22 @@ def test_adapter_euler_gpu(oracle, host_gpu, nd, rs, resident):
     out, ref, dts, units = run_euler(oracle, host_gpu, m, hb.gauss_legendre(rs), resident, n_steps=2)
     assert_euler_parity(out, ref, dts)
     check_work_units(m, units, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6)])
+def test_adapter_async_boundary_traffic_gpu(oracle, host_gpu, nd, rs):
+    """prefetched download of the inside faces + deferred upload of the ghost faces (copy stream, pinned memory) on a B200"""
+    basis = hb.gauss_legendre(rs)
+    m = M.box_mesh(nd, rs, 6, basis, deformed=True, bc_kind=M.BC_NONPENETRATION)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    host_bcs.lean = True
+    try:
+        out, ref, dts, _ = run_euler(oracle, host_gpu, m, basis, True, n_steps=3)
+    finally:
+        host_bcs.lean = False
+    assert_euler_parity(out, ref, dts)
 
 
 @pytest.mark.gpu
