@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
     ap.add_argument("--pipe-mode", type=int, default=1, help="HEXED_B200_OPT_PIPELINED_LOCAL value (A/B: 2 = earlier shared-memory layout of the 3-D deformed kernel)")
-    ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 64, or 48 when host memory is short: "
+    ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 80, 64 or 48 as host memory allows: "
                     "the reference keeps 85 KB of host objects per deformed element)")
     ap.add_argument("--no-aux-lines", action="store_true", help="skip the Navier-Stokes / Cartesian sub-lines of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -152,109 +152,157 @@ def host_info():
     return {"cpu_model": model, "cores": cores, "mem_available_gb": avail}
 
 
-def adapter_e2e(args, n_dev, viscous, steps, warmup, sync_every_call=False, n_override=None):
+def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_override=None):
     """The metric measured the way a Hexed user would see it: through hexed::max_dt_* / hexed::compute_* of the C++ adapter
     (hexed_b200/libhexed_b200_host.so = adapter.cpp + the pointer-graph mesh of harness.cpp standing in for Solver's Accessible_mesh),
-    one Kernel_mesh on n_dev GPUs (hexed_b200::set_devices: Morton split, NCCL halo exchange, dt allreduce -- all below the boundary),
-    state resident on the devices, boundary conditions applied BY THE HOST every stage as Solver::apply_state_bcs does
-    (src/Solver.cpp:56-67): inside faces D2H, an OpenMP loop of per-face virtual Flow_bc calls over the host objects, ghost faces H2D.
-    Timed with the host clock between device synchronisations (the host loop is part of the step)."""
+    one Kernel_mesh on n_dev GPUs (hexed_b200::set_devices: Morton split, NCCL halo exchange, dt allreduce -- all below the boundary).
+    Timed with the host clock between device synchronisations (host loops are part of the step). One harness, several modes:
+      host_bcs        state resident on the devices, boundary conditions applied BY THE HOST every stage as Solver::apply_state_bcs does
+                      (src/Solver.cpp:56-67): inside faces D2H, an OpenMP loop of per-face Flow_bc calls over the host objects, ghost faces H2D
+      device_bcs      the flow INTEGRATION.md section 3a recommends: conditions registered once with hexed_b200::add_device_bc and applied by
+                      hexed_b200::apply_state_bcs / apply_flux_bcs on the devices; after every stage the host asks hexed_b200::is_admissible as
+                      Solver::update does (fix_admissibility, src/Solver.cpp:960-975): per step dt, the flags and Element::record cross PCIe
+      sync_every_call the adapter's zero-Solver-change default: every hexed:: call moves what it reads and writes over PCIe
+    Returns {mode: result}."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
+    import torch
     import hexed_b200 as hb
     from hexed_b200 import mesh as M
     from hexed_b200.cases import density_wave, freestream_state
     import host_harness as H
     info = host_info()
     nd, rs = args.dim, 6
-    n_gpu = n_override or args.adapter_n or (64 if info["mem_available_gb"] >= 60.*n_dev else 48)
+    # host memory: the reference keeps ~85 KB of host objects per deformed 3-D element (+ the flat mesh while they are being filled)
+    avail = info["mem_available_gb"]/n_dev
+    n_gpu = n_override or args.adapter_n or (80 if avail >= 150. else 64 if avail >= 45. else 48)
     if nd == 2:
         n_gpu = int(round(n_gpu**1.5))
     n = int(round(n_gpu*n_dev**(1./nd)))
     deformed = args.mesh == "deformed"
     basis = hb.gauss_legendre(rs)
     fs = freestream_state(nd)
-    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=fs, with_ldg=viscous)
+    m = M.box_mesh(nd, rs, n, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=fs, with_ldg=viscous,
+                   device="cuda:0" if torch.cuda.is_available() else None)  # (metric terms of the synthetic mesh evaluated on the device, returned on the host)
     density_wave(m, basis)
     if viscous:
         m.elem_data[:, M.BULK_AV_SLOT(nd)] = 0.; m.elem_data[:, M.LAPLACIAN_AV_SLOT(nd)] = 0.
     ne, nv, nq, nfq = m.n_elem, m.nv, m.nq, m.nfq
+    n_face_slot = m.n_face_slot
     rows = np.ascontiguousarray(m.bcs[0]["con_index"], dtype=np.int32)
     coords = np.ascontiguousarray(m.elem_index)
     h = H.HostHarness(H.build(emu=False), m, basis)
     m.elem_data = None; m.ref_normals = None; m.det = None; m.face_state = None; m.face_ldg = None  # the host objects hold the data now
     threads = info["cores"]
+    visc, cond = H.sutherland(1.716e-5, 273., 111.), H.sutherland(0.0241, 273., 194.)
+    nb, w = rows.size, nv*nfq
+    per_stage = nb*w*8
+    n_exch = 2 + (2 if viscous else 0)  # state faces every stage (+ LDG faces down and up inside the viscous stage)
+    results = {}
+
+    def measure(mode):
+        sync = mode == "sync_every_call"
+        dev_bcs = mode == "device_bcs"
+        host_s = {"inside_faces_to_host": 0., "host_bc_loop": 0., "ghost_faces_to_device": 0., "hexed_calls": 0.}
+
+        def clocked(key, fn, *a, **kw):
+            t = time.perf_counter(); r = fn(*a, **kw); host_s[key] += time.perf_counter() - t
+            return r
+
+        def state_bcs():
+            if dev_bcs:
+                return clocked("hexed_calls", h.apply_state_bcs)
+            if not sync:
+                clocked("inside_faces_to_host", h.inside_state_faces_to_host)
+            clocked("host_bc_loop", h.host_state_bcs, 0, fs, rows, threads)
+            if not sync:
+                clocked("ghost_faces_to_device", h.ghost_state_faces_to_device)
+
+        def flux_bcs():  # runs inside compute_navier_stokes (its flux_bc callback), like Solver::apply_flux_bcs
+            if dev_bcs:
+                return h.apply_flux_bcs()
+            if not sync:
+                h.inside_ldg_faces_to_host()
+            h.host_flux_bcs(rows, threads)
+            if not sync:
+                h.ghost_ldg_faces_to_device()
+
+        def admissible():
+            if dev_bcs and not clocked("hexed_calls", h.is_admissible)[0]:
+                raise RuntimeError("inadmissible state in the benchmark flow")
+
+        def step():
+            if viscous:
+                dt = clocked("hexed_calls", h.call, "max_dt_navier_stokes", 0.7, 0.7, False, *visc, *cond)
+                state_bcs()
+                clocked("hexed_calls", h.call, "compute_navier_stokes", *visc, *cond, dt=dt, i_stage=0)
+                admissible()
+                state_bcs()
+                clocked("hexed_calls", h.call, "compute_euler", dt=dt, i_stage=1)
+                admissible()
+            else:
+                dt = clocked("hexed_calls", h.call, "max_dt_euler", 0.7, 0.7, False)
+                for stage in (0, 1):
+                    state_bcs()
+                    clocked("hexed_calls", h.call, "compute_euler", dt=dt, i_stage=stage)
+                    admissible()
+        h.set_sync_mode(H.SYNC_EVERY_CALL if sync else H.RESIDENT)
+        if dev_bcs:
+            h.add_device_bcs(m)
+        if viscous:
+            h.set_flux_bc(flux_bcs)
+        k_steps, k_warm = (min(steps, 2), 1) if sync else (steps, warmup)
+        for _ in range(k_warm):
+            step()
+        h.synchronize()
+        for k in host_s:
+            host_s[k] = 0.
+        t0 = time.perf_counter()
+        for _ in range(k_steps):
+            step()
+        h.synchronize()
+        sec = time.perf_counter() - t0
+        if sync:
+            elem_bytes = ne*(nv + 1 + (6 if viscous else 0) + max(nv, rs))*nq*8
+            face_bytes = n_face_slot*2*w*8
+            geom = ne*((nd*nd + 1)*nq*8 if deformed else 0)
+            h2d = 3*(elem_bytes + face_bytes + geom)
+            d2h = 2*(elem_bytes + face_bytes) + ne*nq*8
+            text = ("sync_every_call (the zero-Solver-change default of the adapter): every hexed:: call uploads what it reads from the host objects, "
+                    "metric terms included, and downloads what it wrote")
+        elif dev_bcs:
+            h2d, d2h = 0, 8 + 2*(4*n_dev + 4*ne)
+            text = ("adapter (hexed::max_dt_*/compute_* + hexed_b200::apply_state_bcs / is_admissible of hexed_b200/host/adapter.cpp on a pointer-graph "
+                    "Kernel_mesh), resident, boundary conditions registered on the devices; per step: dt D2H, and after each stage the admissibility flag of "
+                    "every device and Element::record (4 B per element) D2H")
+        else:
+            h2d, d2h = n_exch*per_stage, n_exch*per_stage + 8
+            text = ("adapter (hexed::max_dt_*/compute_* of hexed_b200/host/adapter.cpp on a pointer-graph Kernel_mesh), resident; per stage: inside boundary "
+                    "faces D2H (prefetched on a copy stream, pinned), host OpenMP loop of per-face Freestream::apply_state over the host objects (%d threads), "
+                    "ghost faces H2D (deferred: lands after the interior Neighbor kernels); dt D2H per step" % threads)
+        return {"value": ne*nv*nq*2*k_steps/sec, "unit": "DOF-stage/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec/k_steps*1e3,
+                "mode": text, "elements": ne, "elements_per_gpu": np.bincount(h.element_owners(), minlength=n_dev).tolist(), "box": "%d^%d" % (n, nd),
+                "transport": h.transport_description(), "host": info, "boundary_faces": int(nb),
+                "host_ms_per_step": {k: v/k_steps*1e3 for k, v in host_s.items()},
+                "timing": "host clock between device synchronisations, %d steps after %d warm-up" % (k_steps, k_warm)}
     try:
         h.set_devices(list(range(n_dev)))
         if n_dev > 1:
             h.set_element_coordinates(coords)
-        h.set_sync_mode(H.SYNC_EVERY_CALL if sync_every_call else H.RESIDENT)
+        h.set_sync_mode(H.RESIDENT)
         h.invalidate()
         h.call("compute_write_face")
-        visc, cond = H.sutherland(1.716e-5, 273., 111.), H.sutherland(0.0241, 273., 194.)
-
-        def state_bcs():
-            if not sync_every_call:
-                h.inside_state_faces_to_host()
-            h.host_state_bcs(0, fs, rows, threads)
-            if not sync_every_call:
-                h.ghost_state_faces_to_device()
-
-        def flux_bcs():  # runs inside compute_navier_stokes (its flux_bc callback), like Solver::apply_flux_bcs
-            if not sync_every_call:
-                h.inside_ldg_faces_to_host()
-            h.host_flux_bcs(rows, threads)
-            if not sync_every_call:
-                h.ghost_ldg_faces_to_device()
-        if viscous:
-            h.set_flux_bc(flux_bcs)
-
-        def step():
-            if viscous:
-                dt = h.call("max_dt_navier_stokes", 0.7, 0.7, False, *visc, *cond)
-                state_bcs()
-                h.call("compute_navier_stokes", *visc, *cond, dt=dt, i_stage=0)
-                state_bcs()
-                h.call("compute_euler", dt=dt, i_stage=1)
-            else:
-                dt = h.call("max_dt_euler", 0.7, 0.7, False)
-                for stage in (0, 1):
-                    state_bcs()
-                    h.call("compute_euler", dt=dt, i_stage=stage)
-        for _ in range(warmup):
-            step()
-        h.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            step()
-        h.synchronize()
-        sec = time.perf_counter() - t0
-        transport = h.transport_description()
-        owners = np.bincount(h.element_owners(), minlength=n_dev).tolist()
+        for mode in modes:  # (device_bcs registers the conditions on the devices: keep it after host_bcs)
+            try:
+                results[mode] = measure(mode)
+            except Exception as ex:
+                results[mode] = {"value": None, "unit": "DOF-stage/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "mode": "%s failed: %r" % (mode, ex)}
     finally:
         h.set_sync_mode(H.SYNC_EVERY_CALL)
         h.release()
         h.set_devices([0])
         h.close()
-    nb, w = rows.size, nv*nfq
-    per_stage = nb*w*8
-    n_exch = 2 + (2 if viscous else 0)  # state faces every stage (+ LDG faces down and up inside the viscous stage)
-    if sync_every_call:
-        elem_bytes = ne*(nv + 1 + (6 if viscous else 0) + max(nv, rs))*nq*8
-        face_bytes = m.n_face_slot*2*w*8
-        geom = ne*((nd*nd + 1)*nq*8 if deformed else 0)
-        h2d = 3*(elem_bytes + face_bytes + geom)
-        d2h = 2*(elem_bytes + face_bytes) + ne*nq*8
-        mode = ("sync_every_call (the zero-Solver-change default of the adapter): every hexed:: call uploads what it reads from the host objects, "
-                "metric terms included, and downloads what it wrote")
-    else:
-        h2d, d2h = n_exch*per_stage, n_exch*per_stage + 8
-        mode = ("adapter (hexed::max_dt_*/compute_* of hexed_b200/host/adapter.cpp on a pointer-graph Kernel_mesh), resident; per stage: inside boundary faces "
-                "D2H (prefetched on a copy stream, pinned), host OpenMP loop of per-face Freestream::apply_state over the host objects (%d threads), ghost faces H2D "
-                "(deferred: lands after the interior Neighbor kernels); dt D2H per step" % threads)
-    return {"value": ne*nv*nq*2*steps/sec, "unit": "DOF-stage/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec/steps*1e3,
-            "mode": mode, "elements": ne, "elements_per_gpu": owners, "box": "%d^%d" % (n, nd), "transport": transport, "host": info,
-            "timing": "host clock between device synchronisations, %d steps after %d warm-up" % (steps, warmup)}
+    return results
 
 
 def build_native_oracle():
@@ -266,49 +314,91 @@ def build_native_oracle():
         return "liboracle_fast.so"
 
 
-def cpu_reference_rate(args, steps, warmup):
-    """the CPU port of the reference kernels (oracle) on a bounded sample of the same workload, all host threads"""
+def cpu_reference_rate(args, steps, warmup, n=None):
+    """The reference's OWN CPU kernels (oracle/_ref/libhexed_ref.so: src/kernels_convective.cpp, kernels_max_dt.cpp + include/Spatial.hpp
+    compiled unmodified, oracle/Makefile.ref; built where /root/reference exists and shipped with the snapshot) on a Kernel_mesh stood up once
+    over the same flat mesh, all host threads (OpenMP, as the reference's `threaded` build): kind "reference". Without that library the restated
+    oracle (kind "port"). Returns (rate, seconds per step, threads, kind, sample description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core (libgomp reads this at load time)
     os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    import ctypes as C
+    import numpy as np
     import hexed_b200 as hb
     from hexed_b200 import mesh as M
+    import pyoracle
     from pyoracle import Oracle, EULER
     from hexed_b200.cases import density_wave, freestream_state
-    lib = build_native_oracle()
-    o = Oracle(lib)
     basis = hb.gauss_legendre(6)
     nd = args.dim
-    n = args.cpu_n if nd == 3 else int(round(args.cpu_n**1.5))
-    m = M.box_mesh(nd, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(nd))
+    if n is None:
+        n = args.cpu_n if nd == 3 else int(round(args.cpu_n**1.5))
+    fs = freestream_state(nd)
+    m = M.box_mesh(nd, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=fs)
     density_wave(m, basis)
-    o.compute_write_face(basis, m)
+    use_ref = pyoracle.ref_available()
+    if use_ref:
+        o = pyoracle.RefOracle()
+        o.compute_write_face(basis, m)
+        packed = o.pack_mesh(m)
+        view = o.ref.hr_view_create(C.byref(packed))
+        if not view:
+            raise RuntimeError("hr_view_create failed")
+        ghost = np.ascontiguousarray(m.bcs[0]["ghost_slot"], dtype=np.int32)
+        fs_a = np.ascontiguousarray(fs, dtype=np.float64)
+        gp, fp = ghost.ctypes.data_as(C.POINTER(C.c_int)), fs_a.ctypes.data_as(C.POINTER(C.c_double))
+        dt = C.c_double()
 
-    def step():
-        dt = o.max_dt(EULER, basis, m, 0.7, 0.7, False)
-        for stage in (0, 1):
-            o.apply_state_bcs(m)
-            o.compute_euler(basis, m, dt=dt, i_stage=stage)
+        def step():
+            o._check(o.ref.hr_view_max_dt_euler(view, 0.7, 0.7, 0, C.byref(dt)))
+            for stage in (0, 1):
+                o.ref.hr_view_bc_freestream(view, ghost.size, gp, fp)
+                o._check(o.ref.hr_view_compute_euler(view, o.opts(dt=dt.value, i_stage=stage)))
+        lib, kind = "oracle/_ref/libhexed_ref.so (the reference's own kernels, -O3 -march=x86-64-v3)", "reference"
+    else:
+        lib = build_native_oracle()
+        o = Oracle(lib)
+        o.compute_write_face(basis, m)
+        kind = "port"
+
+        def step():
+            dt = o.max_dt(EULER, basis, m, 0.7, 0.7, False)
+            for stage in (0, 1):
+                o.apply_state_bcs(m)
+                o.compute_euler(basis, m, dt=dt, i_stage=stage)
     for _ in range(warmup):
         step()
     t = time.perf_counter()
     for _ in range(steps):
         step()
     el = time.perf_counter() - t
+    if use_ref:
+        o.ref.hr_view_destroy(view)
     rate = m.n_elem*m.nv*m.nq*2*steps/el
-    return rate, el/steps, o.num_threads(), "%d^%d = %d %s elements, %d steps (max_dt + 2 stages), %s, OpenMP" % (n, nd, m.n_elem, args.mesh, steps, lib)
+    return rate, el/steps, o.num_threads(), kind, "%d^%d = %d %s elements, %d steps (max_dt + 2 x (freestream ghost fill + compute_euler)), %s, OpenMP" % (
+        n, nd, m.n_elem, args.mesh, steps, lib)
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, on the bench's own config when the
+    host has the memory for it (1 M deformed 3-D elements = 50 GB of flat mesh + 26 GB of reference-layout face storage), else on the
+    bounded --cpu-n sample; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, sec, cores, sample = cpu_reference_rate(args, args.steps, args.warmup)
+    info = host_info()
+    nd = args.dim
+    n_full = 1000 if (nd == 2 and args.n == 100) else args.n
+    need_gb = n_full**nd*(80e3 if nd == 3 else 9e3)/1e9*1.6  # flat mesh + reference-layout faces + generation scratch
+    full = info["mem_available_gb"] >= need_gb and n_full**nd*(args.steps + args.warmup) <= 40e6
+    rate, sec, cores, kind, sample = cpu_reference_rate(args, args.steps, args.warmup, n=n_full if full else None)
     out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "DOF-stage/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args), "sample": "CPU arm timed on a bounded sample of that workload: " + sample},
-           "cpu_baseline": {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": workload_name(args), "same_config": bool(full),
+                      "sample": ("CPU arm timed on the full workload: " if full else "CPU arm timed on a bounded sample of that workload: ") + sample,
+                      "host": info},
+           "cpu_baseline": {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": kind, "sample": sample, "host_cpu": info["cpu_model"]},
            "e2e": {"value": rate, "unit": "DOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -576,14 +666,19 @@ def main():
             torch.cuda.synchronize()
             dist.barrier(group=host_group)
         if rank == 0:
+            keep = ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "elements", "elements_per_gpu", "box", "transport",
+                    "boundary_faces", "host_ms_per_step", "mode")
             try:
-                e2e = adapter_e2e(args, world, viscous, args.steps, 3)
+                res = adapter_e2e(args, world, viscous, args.steps, 3, modes=("host_bcs",) if args.no_aux_lines else ("host_bcs", "device_bcs"))
+                e2e = res["host_bcs"]
+                if "device_bcs" in res:
+                    aux["e2e_adapter_device_bcs"] = {k: res["device_bcs"].get(k) for k in keep}
             except Exception as ex:
                 e2e = {"value": None, "unit": "DOF-stage/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "mode": "adapter run failed: %r" % (ex,)}
             if world == 1 and not args.no_aux_lines and not viscous:
                 try:  # what the adapter's zero-Solver-change default costs (every call moves everything over PCIe), once, on a small mesh
-                    sc = adapter_e2e(args, 1, False, 2, 1, sync_every_call=True, n_override=24)
-                    aux["e2e_adapter_sync_every_call"] = {k: sc[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "elements", "mode")}
+                    sc = adapter_e2e(args, 1, False, 2, 1, modes=("sync_every_call",), n_override=24)["sync_every_call"]
+                    aux["e2e_adapter_sync_every_call"] = {k: sc.get(k) for k in keep}
                 except Exception as ex:
                     aux["e2e_adapter_sync_every_call"] = {"value": None, "mode": "failed: %r" % (ex,)}
         if dist is not None:
@@ -592,8 +687,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rate, cs, cores, sample = cpu_reference_rate(args, args.cpu_steps, 3)
-            cpu = {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": "port", "sample": sample}
+            rate, cs, cores, kind, sample = cpu_reference_rate(args, args.cpu_steps, 3)
+            cpu = {"value": rate, "unit": "DOF-stage/s", "cores": cores, "kind": kind, "sample": sample, "host_cpu": host_info()["cpu_model"]}
         except Exception as ex:  # the baseline is informative; never let it take the GPU number down
             cpu = {"value": None, "unit": "DOF-stage/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
 

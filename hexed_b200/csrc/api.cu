@@ -1041,6 +1041,27 @@ int hexed_b200_interp_vertices(hexed_b200_ctx* c, int target, const double* vert
 }
 
 int hexed_b200_av_swap(hexed_b200_ctx* c) { HB_ENTER(c); return launch_av_swap(c); }
+
+int hexed_b200_av_elwise_ramp(hexed_b200_ctx* c, double scale) { HB_ENTER(c); return launch_av_elwise_ramp(c, scale); }
+int hexed_b200_av_elwise_forcing(hexed_b200_ctx* c, int restore)
+{
+  HB_ENTER(c);
+  if (restore != 0 && restore != 1) return fail(c, HEXED_B200_BAD_ARGUMENT, "restore must be 0 or 1");
+  return launch_av_elwise_forcing(c, restore);
+}
+int hexed_b200_av_elwise_vertices(hexed_b200_ctx* c, const double* interp)
+{
+  HB_ENTER(c);
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!interp) return fail(c, HEXED_B200_BAD_ARGUMENT, "null interpolation matrix");
+  double* d_interp = nullptr;
+  int rc = dev_alloc(c, &d_interp, (size_t)2*c->rs, false);
+  if (!rc) rc = check(c, cudaMemcpyAsync(d_interp, interp, sizeof(double)*2*c->rs, cudaMemcpyHostToDevice, c->stream), "upload interpolation matrix");
+  if (!rc) rc = launch_av_elwise_vertices(c, d_interp);
+  if (!rc) rc = check(c, cudaStreamSynchronize(c->stream), "av_elwise_vertices");
+  dev_free(d_interp);
+  return rc;
+}
 int hexed_b200_apply_aux_bcs(hexed_b200_ctx* c, int mode) { HB_ENTER(c); return launch_aux_bcs(c, mode); }
 
 int hexed_b200_vertex_topology(hexed_b200_ctx* c, const int* elem_vertex, int n_vertex, const int* matchers, int n_match)

@@ -127,6 +127,44 @@ av_swap_kernel(double* av, long long n_point_total, int nq)
   const double t = a[0]; a[0] = a[nq]; a[nq] = t;
 }
 
+/* ---------------- Solver::update_art_visc_elwise (reference src/Solver.cpp:584-633) ----------------
+ * the scalar ramp that turns Element::uncertainty (a non-smoothness indicator) into an element-wise viscosity (:591-601) ... */
+__global__ void __launch_bounds__(256)
+av_elwise_ramp_kernel(double* uncert, int n_elem, double ramp_center, double scale)
+{
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  double u = uncert[e];
+  u = 2*log(u)/log(10.);
+  const double half_width = 0.5;
+  if (!(u > ramp_center - half_width)) u = 0;
+  else if (u >= ramp_center + half_width) u = 1;
+  else u = .5*(1 + sin(3.14159265358979323846*(u - ramp_center)/2/half_width));
+  uncert[e] = u*scale;
+}
+
+/* ... and the point loops of its PDE-based branch: forcing[0] = element value, forcing[1] = laplacian_av_coef (:603-612, dir 0);
+ * laplacian_av_coef = forcing[1] after the diffusion (:614-619, dir 1) */
+__global__ void __launch_bounds__(256)
+av_elwise_forcing_kernel(const double* uncert, double* av, double* forcing, long long n_point_total, int nq, int dir)
+{
+  const long long gid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (gid >= n_point_total) return;
+  const long long e = gid/nq; const int q = (int)(gid % nq);
+  double* lap = av + ((size_t)e*2 + 1)*nq + q;
+  double* f = forcing + (size_t)e*4*nq + q;
+  if (dir == 0) { f[0] = uncert[e]; f[nq] = *lap; }
+  else *lap = f[nq];
+}
+
+/* the element's value on each of its vertices (the `get` functor of the share_vertex_data call at :621-623) */
+__global__ void __launch_bounds__(256)
+elem_value_to_vertices_kernel(const double* vals, double* elem_vals, long long n, int n_vert)
+{
+  const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) elem_vals[i] = vals[i/n_vert];
+}
+
 static int need_array(hexed_b200_ctx* c, double** arr, size_t per_elem)
 {
   if (*arr) return 0;
@@ -359,6 +397,43 @@ int launch_fix_admis_spread(hexed_b200_ctx* c, const double* d_interp)
   rc = launch_share_vertex_data(c, c->vertex_scratch, 1); if (rc) return rc;
   rc = launch_interp_vertices(c, 1, c->vertex_scratch, d_interp); if (rc) return rc;
   return launch_av_swap(c);
+}
+
+int launch_av_elwise_ramp(hexed_b200_ctx* c, double scale)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  if (!c->n_elem) return 0;
+  const double ramp_center = -4 - 4.25*std::log(double(c->rs - 1))/std::log(10.); // Solver.cpp:595
+  HB_LAUNCH(av_elwise_ramp_kernel, (c->n_elem + 255)/256, 256, 0, c->stream, c->uncert, c->n_elem, ramp_center, scale);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int launch_av_elwise_forcing(hexed_b200_ctx* c, int dir)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  int rc = need_array(c, &c->av, (size_t)2*c->nq); if (rc) return rc;
+  rc = need_array(c, &c->forcing, (size_t)4*c->nq); if (rc) return rc;
+  const long long n = (long long)c->n_elem*c->nq;
+  if (!n) return 0;
+  HB_LAUNCH(av_elwise_forcing_kernel, grid_for(n), 256, 0, c->stream, c->uncert, c->av, c->forcing, n, c->nq, dir);
+  ++c->launches;
+  HB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+/* the vertex-based branch (:620-632): element value -> its vertices, share_vertex_data(max), multilinear interpolation to laplacian_av_coef */
+int launch_av_elwise_vertices(hexed_b200_ctx* c, const double* d_interp)
+{
+  if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
+  int rc = need_array(c, &c->vertex_scratch, (size_t)c->n_vert); if (rc) return rc;
+  const long long n = (long long)c->n_elem*c->n_vert;
+  if (!n) return 0;
+  HB_LAUNCH(elem_value_to_vertices_kernel, grid_for(n), 256, 0, c->stream, c->uncert, c->vertex_scratch, n, c->n_vert);
+  ++c->launches;
+  rc = launch_share_vertex_data(c, c->vertex_scratch, 1); if (rc) return rc;
+  return launch_interp_vertices(c, 1, c->vertex_scratch, d_interp);
 }
 
 } // namespace hb

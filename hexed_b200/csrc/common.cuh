@@ -216,6 +216,9 @@ int launch_av_swap(hexed_b200_ctx* c);
 int launch_aux_bcs(hexed_b200_ctx* c, int mode);
 int launch_share_vertex_data(hexed_b200_ctx* c, double* elem_vals, int is_max);
 int launch_fix_admis_spread(hexed_b200_ctx* c, const double* d_interp);
+int launch_av_elwise_ramp(hexed_b200_ctx* c, double scale);
+int launch_av_elwise_forcing(hexed_b200_ctx* c, int dir);
+int launch_av_elwise_vertices(hexed_b200_ctx* c, const double* d_interp);
 
 /* Thread -> line-task map. In the dense [i][j][k] field layout that the bulk copies deliver, lines of dimension 0 (stride RS^2) are
  * conflict-free for consecutive lanes, but with 8-byte accesses consecutive lines of dimension 1 (stride RS) and 2 (stride 1) hit every

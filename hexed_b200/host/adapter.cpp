@@ -943,6 +943,44 @@ void av_swap(Kernel_mesh km)
   call.finish();
 }
 
+void vertex_topology(Kernel_mesh km, const std::vector<int>& elem_vertex, int n_vertex, const std::vector<int>& matchers)
+{
+  Mirror& m = mirror(km);
+  single_device_only(m, "vertex_topology");
+  if (elem_vertex.size() != m.tab.elem.size()*size_t(ipow(2, km.n_dim)) || matchers.size() % 8) throw std::runtime_error("hexed_b200: vertex_topology: bad table size");
+  check(&m, hexed_b200_vertex_topology(m.ctx0(), elem_vertex.data(), n_vertex, matchers.data(), int(matchers.size()/8)));
+}
+
+void av_elwise_ramp(Kernel_mesh km, double scale)
+{ // src/Solver.cpp:590-601
+  Call call(km, 0, uncert);
+  for (Rank& k : call.m.ranks) {
+    const int ne = int(k.elem.size());
+    std::vector<double> buf(ne);
+    for (int e = 0; e < ne; ++e) buf[e] = k.elem[e]->uncert();
+    if (ne) check(&call.m, hexed_b200_upload(k.ctx, HEXED_B200_UNCERT, buf.data(), 0, ne), k.ctx);
+    check(&call.m, hexed_b200_av_elwise_ramp(k.ctx, scale), k.ctx);
+    download_uncert(call.m, k); // the reference leaves the ramped value in Element::uncertainty, whatever the coherence mode
+  }
+}
+
+void av_elwise_forcing(Kernel_mesh km, bool restore)
+{ // src/Solver.cpp:603-612 | :614-619
+  Call call(km, art_visc, art_visc);
+  call.each([&](hexed_b200_ctx* c) {return hexed_b200_av_elwise_forcing(c, restore);});
+  call.finish();
+}
+
+void av_elwise_vertices(Kernel_mesh km)
+{ // src/Solver.cpp:620-632 with interp = Gauss_lobatto(2).interpolate(nodes) = [1 - node, node]
+  Call call(km, art_visc, art_visc);
+  std::vector<double> interp(size_t(2)*km.row_size);
+  for (int i = 0; i < km.row_size; ++i) {interp[2*i] = 1. - km.basis.node(i); interp[2*i + 1] = km.basis.node(i);}
+  single_device_only(call.m, "av_elwise_vertices");
+  check(&call.m, hexed_b200_av_elwise_vertices(call.m.ctx0(), interp.data()));
+  call.finish();
+}
+
 void apply_aux_bcs(Kernel_mesh km, int mode)
 {
   const unsigned grp = mode == HEXED_B200_BC_MODE_ADVECTION ? unsigned(faces_wide) : unsigned(faces);

@@ -227,6 +227,13 @@ void hbh_put(void* handle, const double* elem_data, const double* nom, const dou
   }
 }
 
+// Element::uncertainty <- array (what Solver::set_uncertainty leaves behind, src/Solver.cpp:672-679)
+void hbh_put_uncert(void* handle, const double* uncert)
+{
+  auto* h = static_cast<Harness*>(handle);
+  for (size_t e = 0; e < h->elems.size(); ++e) h->elems[e]->uncertainty = uncert[e];
+}
+
 // flat arrays <- host objects
 void hbh_fetch(void* handle, double* elem_data, double* face_state, double* face_ldg, double* face_wide, double* uncert)
 {
@@ -400,6 +407,17 @@ int hbh_av_glue(void* handle, int what, double a, double b, int n, const double*
       case 3: hexed_b200::interp_vertices(h->mesh(), n, std::vector<double>(values, values + n_values)); break;
       case 4: hexed_b200::av_swap(h->mesh()); break;
       case 5: hexed_b200::apply_aux_bcs(h->mesh(), n); break;
+      case 6: hexed_b200::av_elwise_ramp(h->mesh(), a); break;
+      case 7: hexed_b200::av_elwise_forcing(h->mesh(), n != 0); break;
+      case 8: hexed_b200::av_elwise_vertices(h->mesh()); break;
+      case 9: { // values = [n_vertex, n_elem*2^nd vertex ids..., matcher rows...] as doubles
+        const size_t n_ev = h->elems.size()*size_t(ipow(2, h->nd));
+        std::vector<int> ev(n_ev), mt;
+        for (size_t i = 0; i < n_ev; ++i) ev[i] = int(values[1 + i]);
+        for (size_t i = 1 + n_ev; i < size_t(n_values); ++i) mt.push_back(int(values[i]));
+        hexed_b200::vertex_topology(h->mesh(), ev, int(values[0]), mt);
+        break;
+      }
       default: throw std::runtime_error("unknown glue call");
     }
     return 0;

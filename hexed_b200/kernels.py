@@ -117,6 +117,9 @@ SIGNATURES = {
     "hexed_b200_av_finish": [C.c_void_p, C.c_double, C.c_double, C.c_int, dp, dp],
     "hexed_b200_interp_vertices": [C.c_void_p, C.c_int, dp, dp],
     "hexed_b200_av_swap": [C.c_void_p],
+    "hexed_b200_av_elwise_ramp": [C.c_void_p, C.c_double],
+    "hexed_b200_av_elwise_forcing": [C.c_void_p, C.c_int],
+    "hexed_b200_av_elwise_vertices": [C.c_void_p, dp],
     "hexed_b200_apply_aux_bcs": [C.c_void_p, C.c_int],
     "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp],
     "hexed_b200_update_navier_stokes": [C.c_void_p, C.c_double, Transport, Transport, C.c_int, C.c_int, C.c_int, dp, dp],
@@ -463,6 +466,17 @@ class Device:
 
     def av_swap(self):
         self._check(self.lib.hexed_b200_av_swap(self.ctx))
+
+    def av_elwise_ramp(self, scale):
+        """Solver::update_art_visc_elwise, the ramp of src/Solver.cpp:590-601 on the element uncertainties"""
+        self._check(self.lib.hexed_b200_av_elwise_ramp(self.ctx, scale))
+
+    def av_elwise_forcing(self, restore):
+        self._check(self.lib.hexed_b200_av_elwise_forcing(self.ctx, int(restore)))
+
+    def av_elwise_vertices(self, interp):
+        a = np.ascontiguousarray(interp, dtype=np.float64)
+        self._check(self.lib.hexed_b200_av_elwise_vertices(self.ctx, a.ctypes.data_as(dp)))
 
     def set_jacobian(self, vertex_pos, node_adj=None):
         """element loop of Solver::calc_jacobian (reference src/Solver.cpp:281-286, src/Deformed_element.cpp:60-136): vertex_pos

@@ -266,6 +266,16 @@ int hexed_b200_av_project_forcing(hexed_b200_ctx* ctx, const double* node_weight
 int hexed_b200_av_finish(hexed_b200_ctx* ctx, double mult, double us_max, int n_real, const double* node_weights, double* residual);
 int hexed_b200_interp_vertices(hexed_b200_ctx* ctx, int target, const double* vertex_values, const double* interp);
 int hexed_b200_av_swap(hexed_b200_ctx* ctx);
+/* Solver::update_art_visc_elwise (src/Solver.cpp:584-633) after its set_uncertainty call, on HEXED_B200_UNCERT [n_elem]:
+ *   av_elwise_ramp(scale)        u <- ramp(2*log10(u)) * scale: 0 below, 1 above, half a sine period across a window of width 1 centred at
+ *                                -4 - 4.25*log10(row_size - 1); scale = width/(row_size - 1)*(freestream speed + sound speed)   (:590-601)
+ *   av_elwise_forcing(restore)   0: art_visc_forcing[0] = u, art_visc_forcing[1] = laplacian_av_coef (:603-612, before diffuse_art_visc);
+ *                                1: laplacian_av_coef = art_visc_forcing[1] (:614-619, after it)
+ *   av_elwise_vertices(interp)   the other branch (:620-632): u -> vertex_elwise_av of every vertex of the element, share_vertex_data(max)
+ *                                (needs hexed_b200_vertex_topology), laplacian_av_coef = hypercube_matvec(interp[row_size][2], vertex values) */
+int hexed_b200_av_elwise_ramp(hexed_b200_ctx* ctx, double scale);
+int hexed_b200_av_elwise_forcing(hexed_b200_ctx* ctx, int restore);
+int hexed_b200_av_elwise_vertices(hexed_b200_ctx* ctx, const double* interp);
 /* the boundary loops of the same pipelines for the boundary conditions registered with hexed_b200_bc_create:
  *   MODE_ADVECTION    Flow_bc::apply_advection and its overrides (src/Boundary_condition.cpp:24-41,346-369,429-448,460-463), Solver.cpp:505-510
  *   MODE_COPY_STATE   Flow_bc::apply_diffusion (:43-52; Solver::apply_avc_diff_bcs, Solver.cpp:83-91) and the ghost copy of :1063-1068

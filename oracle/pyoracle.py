@@ -577,6 +577,39 @@ def av_swap(m):
     m.elem_data[:, nd + 4] = tmp
 
 
+def av_elwise_ramp(m, scale):
+    """Solver::update_art_visc_elwise, reference src/Solver.cpp:590-601, on m.uncert (one value per element)"""
+    rs = m.row_size
+    ramp_center = -4 - 4.25*np.log(rs - 1)/np.log(10)
+    half_width = 0.5
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = 2*np.log(m.uncert)/np.log(10)
+        out = np.where(~(u > ramp_center - half_width), 0., np.where(u >= ramp_center + half_width, 1.,
+                                                                     .5*(1 + np.sin(np.pi*(u - ramp_center)/2/half_width))))
+    m.uncert[:] = out*scale
+
+
+def av_elwise_forcing(m, restore):
+    """the point loops of the PDE-based branch, reference src/Solver.cpp:603-612 (restore false) and :614-619 (restore true)"""
+    nd = m.n_dim
+    lap, f0 = nd + 4, nd + 5  # laplacian_av_coef, first art_visc_forcing slot (reference src/Element.cpp:114-142)
+    if restore:
+        m.elem_data[:, lap] = m.elem_data[:, f0 + 1]
+    else:
+        m.elem_data[:, f0] = m.uncert[:, None]
+        m.elem_data[:, f0 + 1] = m.elem_data[:, lap]
+
+
+def av_elwise_vertices(m, elem_vertex, n_vertex, matchers, interp):
+    """the vertex-based branch, reference src/Solver.cpp:620-632: element value on its vertices, share_vertex_data(vector_max),
+    laplacian_av_coef = hypercube_matvec(interp, vertex values)"""
+    n_vert = 2**m.n_dim
+    vals = np.repeat(m.uncert[:, None], n_vert, axis=1).astype(np.float64)
+    vals = share_vertex_data(vals, elem_vertex, n_vertex, matchers, m.n_dim, True)
+    interp_vertices(m, 1, vals, interp)
+    return vals
+
+
 def apply_aux_bcs(m, mode):
     """boundary loops of the AV / admissibility pipelines, numpy (TEST INFRASTRUCTURE). mode 0: Flow_bc::apply_advection and overrides
     (reference src/Boundary_condition.cpp:24-41,346-369,429-448,460-463) on the wide faces; 1: Flow_bc::apply_diffusion (:43-52) /

@@ -119,6 +119,11 @@ class HostHarness:
                          _d(m.normals) if g and m.n_normal_slot else None,
                          None if wide else _d(m.face_state), None if wide else _d(m.face_ldg), _d(m.face_wide) if wide else None)
 
+    def put_uncert(self, uncert):
+        u = np.ascontiguousarray(uncert, dtype=np.float64)
+        self.lib.hbh_put_uncert.argtypes = [C.c_void_p, dp]
+        self.lib.hbh_put_uncert(self.h, _d(u))
+
     def fetch(self, m, wide=False):
         """FlatMesh <- host objects"""
         self.lib.hbh_fetch(self.h, _d(m.elem_data), None if wide else _d(m.face_state), None if wide else _d(m.face_ldg),

@@ -74,5 +74,5 @@ def test_new_entry_points_are_declared_everywhere():
     for name in ("hexed_b200_is_admissible", "hexed_b200_download_record", "hexed_b200_set_jacobian", "hexed_b200_calc_shared_normals",
                  "hexed_b200_vertex_topology", "hexed_b200_share_vertex_data", "hexed_b200_fix_admis_spread", "hexed_b200_av_scale_velocity",
                  "hexed_b200_av_project_forcing", "hexed_b200_av_finish", "hexed_b200_interp_vertices", "hexed_b200_av_swap",
-                 "hexed_b200_apply_aux_bcs"):
+                 "hexed_b200_apply_aux_bcs", "hexed_b200_av_elwise_ramp", "hexed_b200_av_elwise_forcing", "hexed_b200_av_elwise_vertices"):
         assert name in names and name in SIGNATURES

@@ -177,6 +177,13 @@ def test_av_smoothness_pipeline(oracle, emu_lib, nd, rs):
 
 
 @pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
+def test_av_elwise(emu_lib, nd, rs):
+    """Solver::update_art_visc_elwise: ramp, forcing loops, vertex branch"""
+    from util import check_av_elwise
+    check_av_elwise(emu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
 def test_vertex_sharing_and_fix_admis_spread(oracle, emu_lib, nd, rs):
     """share_vertex_data + the spreading step of fix_admissibility on the device"""
     from util import check_vertex_sharing

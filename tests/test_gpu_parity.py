@@ -197,6 +197,47 @@ def test_navier_stokes_3d_line_kernel(oracle, gpu_lib, rs):
     assert_pde_parity(out, ref, dts)
 
 
+@pytest.mark.parametrize("options", [(), ((1, 1), (2, 1))], ids=["default", "cfl_cache+fused_admis"])
+@pytest.mark.parametrize("rs", [6, 4])
+def test_large_mixed_soup_every_persistent_cta_loops(oracle, gpu_lib, rs, options):
+    """The persistent pipelined Local kernels run 3 CTAs on each of 148 SMs (444 CTAs): with 1 900 Cartesian + 1 900 deformed elements in
+    ONE mesh every CTA of both launches goes through its double-buffer wrap-around >= 4 times, the deformed launch starts at
+    elem_begin = n_car > 0, 300 hanging-node faces (every stretch flag) sit in between, and the result is compared with the oracle
+    element by element -- with the defaults and with the CFL cache and the fused admissibility bits switched on."""
+    rng = np.random.default_rng(5)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(3, rs, rng, n_car=1900, n_def=1900, n_ref=300, with_ldg=False)
+    M.random_flow_state(m, rng)
+    out, ref, dts, _ = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=2, safety=0.05, options=options)
+    assert_euler_parity(out, ref, dts)
+    per_elem = np.linalg.norm((out.state() - ref.state()).reshape(m.n_elem, -1), axis=1)/np.linalg.norm(ref.state().reshape(m.n_elem, -1), axis=1)
+    assert per_elem.max() <= 1e-11, int(per_elem.argmax())  # no single element may hide behind the mesh-wide norm
+
+
+@pytest.mark.parametrize("deformed", [True, False])
+def test_box_3d_every_persistent_cta_loops(oracle, gpu_lib, deformed):
+    """14^3 = 2 744 elements of the headline shape (3-D, row size 6): >= 6 iterations per persistent CTA, oracle-compared"""
+    basis = hb.gauss_legendre(6)
+    m = M.box_mesh(3, 6, 14, basis, deformed=deformed, bc_kind=M.BC_FREESTREAM, bc_params=freestream_state(3))
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    out, ref, dts, _ = run_euler_pair(oracle, gpu_lib, m, basis, n_steps=3)
+    assert_euler_parity(out, ref, dts)
+
+
+def test_navier_stokes_3d_large_mixed_soup(oracle, gpu_lib):
+    """ns_local_line_kernel / ns_reconcile_bulk_kernel on 1 000 + 1 000 elements with 200 hanging faces, element by element"""
+    rng = np.random.default_rng(92)
+    basis = hb.gauss_legendre(6)
+    m = M.soup_mesh(3, 6, rng, n_car=1000, n_def=1000, n_ref=200, with_ldg=True)
+    M.random_flow_state(m, rng)
+    prepare_pde_state(m, rng, NAVIER_STOKES)
+    out, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1)
+    assert_pde_parity(out, ref, dts)
+    per_elem = np.linalg.norm((out.state() - ref.state()).reshape(m.n_elem, -1), axis=1)/np.linalg.norm(ref.state().reshape(m.n_elem, -1), axis=1)
+    assert per_elem.max() <= 1e-11, int(per_elem.argmax())
+
+
 @pytest.mark.parametrize("rs,n", [(4, 5), (6, 4)])
 def test_cfl_cache_follows_the_state(oracle, gpu_lib, rs, n):
     from util import check_cfl_cache
@@ -283,6 +324,12 @@ def test_vertex_sharing_and_fix_admis_spread(oracle, gpu_lib, nd, rs):
     """share_vertex_data + the spreading step of fix_admissibility on the device"""
     from util import check_vertex_sharing
     check_vertex_sharing(oracle, gpu_lib, nd, rs)
+
+
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 3)])
+def test_av_elwise(gpu_lib, nd, rs):
+    from util import check_av_elwise
+    check_av_elwise(gpu_lib, nd, rs)
 
 
 @pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 4)])

@@ -399,6 +399,46 @@ def test_adapter_av_glue_emu(oracle, host_emu, resident):
         assert rel_l2(work.elem_data[:, lo:hi], ref.elem_data[:, lo:hi]) <= 1e-14
 
 
+@pytest.mark.parametrize("resident", [False, True])
+def test_adapter_av_elwise_emu(oracle, host_emu, resident):
+    """hexed_b200::av_elwise_ramp / av_elwise_forcing / vertex_topology / av_elwise_vertices: the loops of Solver::update_art_visc_elwise
+    (src/Solver.cpp:584-633) on Element::uncertainty of the host objects, against the numpy restatement"""
+    nd, rs = 2, 3
+    m, rng = soup(nd, rs, 27, n_car=6, n_def=8, n_ref=0)
+    basis = hb.gauss_legendre(rs)
+    ne, n_vert = m.n_elem, 2**nd
+    center = -4 - 4.25*np.log10(rs - 1)
+    m.uncert = 10**(0.5*rng.uniform(center - 1.5, center + 1.5, ne))
+    m.uncert[0] = 0.
+    m.elem_data[:, nd + 3:nd + 9] = rng.uniform(0., 1e-3, (ne, 6, m.nq))
+    n_vertex = ne*n_vert//3 + 5
+    elem_vertex = np.stack([rng.choice(n_vertex, n_vert, replace=False) for _ in range(ne)]).astype(np.int32)
+    matchers = np.array([[1, 0, 0, 0, 3, 5, -1, -1]], np.int32)
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    ref, work = m.copy(), m.copy()
+    h = H.HostHarness(host_emu, m, basis, seed=6)
+    h.put_uncert(m.uncert)
+    h.set_sync_mode(H.RESIDENT if resident else H.SYNC_EVERY_CALL)
+    h.invalidate()
+    if resident:
+        h.to_device(H.ALL_ELEM | H.FACES)
+    scale = 0.02
+    h.av_glue(6, scale); pyoracle.av_elwise_ramp(ref, scale)
+    h.fetch(work)   # the ramped value is back in Element::uncertainty in either mode
+    assert work.uncert[0] == 0. and np.allclose(work.uncert, ref.uncert, rtol=1e-13, atol=1e-18)
+    ref.uncert[:] = work.uncert
+    h.av_glue(7, n=0); pyoracle.av_elwise_forcing(ref, False)
+    h.av_glue(7, n=1); pyoracle.av_elwise_forcing(ref, True)
+    h.av_glue(9, values=np.concatenate([[n_vertex], elem_vertex.reshape(-1), matchers.reshape(-1)]).astype(np.float64))
+    h.av_glue(8); pyoracle.av_elwise_vertices(ref, elem_vertex, n_vertex, matchers, interp)
+    if resident:
+        h.to_host(H.ALL_ELEM)
+    h.fetch(work)
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    assert rel_l2(work.elem_data[:, nd + 3:nd + 9], ref.elem_data[:, nd + 3:nd + 9]) <= 1e-15
+
+
 def check_adapter_device_bcs(oracle, host_emu, resident, nd, rs):
     """hexed_b200::add_device_bc / apply_state_bcs / apply_flux_bcs: a viscous step with every device-side boundary condition and no
     host boundary loop at all"""

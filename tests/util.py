@@ -665,6 +665,58 @@ def check_vertex_sharing(oracle, lib, nd, rs, seed=23):
     assert out.elem_data[:, nd + 3].max() > 0.5   # the flagged elements and their neighbours carry a factor ~1 in what is now the bulk slot
 
 
+def check_av_elwise(lib, nd, rs, seed=29):
+    """Solver::update_art_visc_elwise (reference src/Solver.cpp:584-633) after set_uncertainty: the scalar ramp on Element::uncertainty
+    (values below, inside and above the ramp window, zero and denormal-small included), the two point loops of the PDE-based branch, and
+    the vertex-based branch (share_vertex_data(max) with hanging-vertex matchers + multilinear interpolation), against the numpy restatement"""
+    import pyoracle
+    from hexed_b200.kernels import UNCERT, VERTEX_SCRATCH
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=14, n_def=16, n_ref=0)
+    ne, n_vert = m.n_elem, 2**nd
+    center = -4 - 4.25*np.log10(rs - 1)
+    m.uncert = 10**(0.5*rng.uniform(center - 1.5, center + 1.5, ne))   # 2*log10(u) spread across the window [center - .5, center + .5]
+    m.uncert[:4] = [0., 1e-300, 10**(0.5*(center - 0.5)), 10**(0.5*(center + 0.5))]
+    m.elem_data[:, nd + 3:nd + 9] = rng.uniform(0., 1e-3, (ne, 6, m.nq))
+    scale = 0.013/(rs - 1)*(1.7 + 2.3)
+    n_vertex = ne*n_vert//3 + 5
+    elem_vertex = np.stack([rng.choice(n_vertex, n_vert, replace=False) for _ in range(ne)]).astype(np.int32)
+    matchers = []
+    if nd > 1:
+        free = list(rng.permutation(ne))
+        for stretch in ([(0, 0), (1, 0), (0, 1)] if nd == 3 else [(0, 0)]):
+            n_fine = 2**(nd - 1)//((1 + stretch[0])*(1 + stretch[1]))
+            matchers.append([int(rng.integers(0, nd)), int(rng.integers(0, 2)), stretch[0], stretch[1]] + [int(free.pop()) for _ in range(n_fine)] + [-1]*(4 - n_fine))
+    matchers = np.array(matchers, np.int32).reshape(-1, 8)
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    dev.upload(UNCERT, m.uncert)
+    dev.av_elwise_ramp(scale); pyoracle.av_elwise_ramp(ref, scale)
+    got = dev.download(UNCERT, np.zeros(ne))
+    assert np.all(got[:3] == 0.) and got[3] == scale and ((got > 0) & (got < scale)).sum() > 3   # all three branches of the ramp taken
+    assert np.allclose(got, ref.uncert, rtol=1e-13, atol=1e-16*scale)   # (log / sin of the device library against libm's)
+    ref.uncert[:] = got   # from here on the two must agree exactly
+    dev.av_elwise_forcing(False); pyoracle.av_elwise_forcing(ref, False)
+    out = m.copy(); dev.sync_to_host(out)
+    assert np.array_equal(out.elem_data[:, nd + 3:nd + 9], ref.elem_data[:, nd + 3:nd + 9])
+    junk = rng.uniform(0., 1e-3, (ne, m.nq))
+    ref.elem_data[:, nd + 6] = junk; out.elem_data[:, nd + 6] = junk   # what diffuse_art_visc would have left in forcing[1]
+    dev.upload_elements(out.elem_data)
+    dev.av_elwise_forcing(True); pyoracle.av_elwise_forcing(ref, True)
+    dev.sync_to_host(out)
+    assert np.array_equal(out.elem_data[:, nd + 3:nd + 9], ref.elem_data[:, nd + 3:nd + 9])
+    dev.vertex_topology(elem_vertex, n_vertex, matchers)
+    dev.av_elwise_vertices(interp)
+    v = pyoracle.av_elwise_vertices(ref, elem_vertex, n_vertex, matchers, interp)
+    assert np.allclose(dev.download(VERTEX_SCRATCH, np.zeros((ne, n_vert))), v, rtol=4e-16, atol=0.)
+    dev.sync_to_host(out)
+    dev.close()
+    assert rel_l2(out.elem_data[:, nd + 4], ref.elem_data[:, nd + 4]) <= 1e-15
+    assert np.array_equal(out.elem_data[:, nd + 3], ref.elem_data[:, nd + 3])   # bulk coefficient untouched
+
+
 def check_shared_normals_soup(oracle, lib, nd, rs, seed=31):
     """the connection passes of Solver::calc_jacobian on a soup mesh (every direction, hanging faces, boundary ghosts) with arbitrary
     element-face normals: bit-identical to the numpy restatement (all factors are 0.5 and +-1)"""
