@@ -271,10 +271,10 @@ def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_over
             text = ("sync_every_call (the zero-Solver-change default of the adapter): every hexed:: call uploads what it reads from the host objects, "
                     "metric terms included, and downloads what it wrote")
         elif dev_bcs:
-            h2d, d2h = 0, 8 + 2*(4*n_dev + 4*ne)
+            h2d, d2h = 0, 8 + 2*8*n_dev
             text = ("adapter (hexed::max_dt_*/compute_* + hexed_b200::apply_state_bcs / is_admissible of hexed_b200/host/adapter.cpp on a pointer-graph "
-                    "Kernel_mesh), resident, boundary conditions registered on the devices; per step: dt D2H, and after each stage the admissibility flag of "
-                    "every device and Element::record (4 B per element) D2H")
+                    "Kernel_mesh), resident, boundary conditions registered on the devices; per step: dt D2H, and after each stage the admissibility flags of "
+                    "every device D2H (Element::record only when a device reports an inadmissible state)")
         else:
             h2d, d2h = n_exch*per_stage, n_exch*per_stage + 8
             text = ("adapter (hexed::max_dt_*/compute_* of hexed_b200/host/adapter.cpp on a pointer-graph Kernel_mesh), resident; per stage: inside boundary "
@@ -683,6 +683,23 @@ def main():
                     aux["e2e_adapter_sync_every_call"] = {"value": None, "mode": "failed: %r" % (ex,)}
         if dist is not None:
             dist.barrier(group=host_group)
+
+    # ---- the other workloads of the BASELINE config list on the same box, as sub-lines of the default run (own processes, 1 M elements each) ----
+    if rank == 0 and world == 1 and not args.no_aux_lines and args.n == 100 and nd == 3 and not viscous and deformed:
+        sub = {}
+        for name, extra in (("3d_cartesian_euler", ["--mesh", "cartesian"]), ("3d_deformed_navier_stokes", ["--pde", "navier_stokes"]),
+                            ("3d_cartesian_navier_stokes", ["--pde", "navier_stokes", "--mesh", "cartesian"])):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3)), "--no-e2e",
+                                    "--no-cpu-baseline", "--no-aux-lines"] + extra, capture_output=True, text=True, timeout=600)
+                line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+                sub[name] = {"value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "workload": line["config"]["workload"],
+                             "timed_path": line["config"].get("timed_path"), "gpu_launches": line.get("gpu_launches"), "clocks": line.get("clocks"),
+                             "roofline": {k: line["roofline"].get(k) for k in ("kernel", "achieved", "peak", "frac", "frac_traffic", "avg_launch_ms", "whole_stage",
+                                                                                  "kernel_seconds_per_step", "accounting")}}
+            except Exception as ex:
+                sub[name] = {"value": None, "error": repr(ex)}
+        aux["sub_lines"] = sub
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -874,7 +874,7 @@ bool is_admissible(Kernel_mesh km, std::vector<int>* record)
     int ok = 0;
     check(&call.m, hexed_b200_is_admissible(k.ctx, &ok), k.ctx);
     all_ok = all_ok && ok != 0;
-    if (record && !k.elem.empty()) {
+    if (record && !ok && !k.elem.empty()) { // (all of an admissible rank's records are 0, which `record` already holds: nothing to fetch)
       std::vector<int> local(k.elem.size());
       check(&call.m, hexed_b200_download_record(k.ctx, local.data(), 0, int(local.size())), k.ctx);
       for (size_t i = 0; i < local.size(); ++i) (*record)[k.global_elem[i]] = local[i];
