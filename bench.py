@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
     ap.add_argument("--pipe-mode", type=int, default=1, help="HEXED_B200_OPT_PIPELINED_LOCAL value (A/B: 2 = earlier shared-memory layout of the 3-D deformed kernel)")
+    ap.add_argument("--ns-layout", type=int, default=1, help="HEXED_B200_OPT_NS_LOCAL_LAYOUT (A/B: 0 = dense shared-memory layout of the 3-D Navier-Stokes Local kernel)")
     ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 80, 64 or 48 as host memory allows: "
                     "the reference keeps 85 KB of host objects per deformed element)")
     ap.add_argument("--no-aux-lines", action="store_true", help="skip the Navier-Stokes / Cartesian sub-lines of the default run")
@@ -441,6 +442,8 @@ def main():
     dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
     if args.pipe_mode != 1:
         dev.set_option(0, args.pipe_mode)
+    if args.ns_layout != 1:
+        dev.set_option(3, args.ns_layout)
     # the generator's copies of the metric terms are dead once the device mirror holds them: 28 KB per element that a 2 M element
     # mesh (the 16 M / 8 GPU configuration) needs back
     m.ref_normals = None; m.det = None; m.normals = None

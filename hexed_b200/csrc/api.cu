@@ -1207,6 +1207,17 @@ int hexed_b200_bc_create(hexed_b200_ctx* c, int kind, int n, const int* inside, 
   return 0;
 }
 
+int hexed_b200_bc_set_params(hexed_b200_ctx* c, int bc_id, const double* params, int n_params)
+{
+  HB_ENTER(c);
+  if (bc_id < 0 || bc_id >= (int)c->bcs.size()) return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown boundary condition");
+  Bc& b = c->bcs[bc_id];
+  if (n_params != b.n_params || (n_params && !params)) return fail(c, HEXED_B200_BAD_ARGUMENT, "parameter count differs from the registered one");
+  // stream-ordered: every apply_*_bcs enqueued so far still reads the old block (small pageable sources are staged by the runtime at call time)
+  if (n_params) HB_CUDA(c, cudaMemcpyAsync(b.params, params, sizeof(double)*n_params, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
 int hexed_b200_apply_state_bcs(hexed_b200_ctx* c) { HB_ENTER(c); return launch_bcs(c); }
 
 int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled != 0; return 0; }
@@ -1220,6 +1231,7 @@ int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
     if (c->use_fused_admis != (value != 0)) { c->use_fused_admis = value != 0; invalidate_admis(c); }
     return 0;
   }
+  if (option == HEXED_B200_OPT_NS_LOCAL_LAYOUT) { c->ns_pad = value != 0; return 0; }
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown option");
 }
 

@@ -698,6 +698,347 @@ ns_local_line_kernel(GArgs a, Ops ops)
   }
 }
 
+/* ---------------- Navier-Stokes Local, 3-D row size 6, bank-conflict-free layout ----------------
+ * Same phases and the same arithmetic, operation for operation, as ns_local_line_kernel<6, DEF> (the two give bit-identical results), laid
+ * out for the shared-memory pipe, which is what bounds that kernel: profiles/r01j_ncu_full_ns.md has it 82 % busy with 31 % of its
+ * wavefronts (1 930 of 6 230 per element) caused by bank conflicts -- 8-byte accesses of consecutive lines of dimension 1 (stride 6) and
+ * dimension 2 (stride 1) in a dense [6][6][6] field hit every bank twice. Here
+ *   - every field in shared memory has a PLANE pitch of 38 doubles (field pitch 228): the six dimension-1 line starts of consecutive planes
+ *     then fall 6 banks apart, so 16 consecutive lines of dimension 1 cover the 16 8-byte banks exactly once; dimension 0 (stride 38) keeps
+ *     consecutive lanes on consecutive doubles. The bulk copies deliver a field plane by plane (30 + 54 copies of 288 B issued by the 32
+ *     lanes of warp 0 instead of 2 copies by one thread);
+ *   - dimension-2 lines are contiguous: 16-byte accesses, lines dealt to lanes so that every quarter-warp holds one line of each residue
+ *     (x + y) mod 8, i.e. eight distinct 16-byte bank groups (c_ns_diag; a search also made the face points of a half-warp distinct);
+ *   - tasks are dealt half-warp by half-warp (16 lines of one direction / one physical component), the four left-over lines of each group
+ *     of 36 share the last half-warps;
+ *   - point tasks take 16 consecutive points of ONE plane per half-warp (the 6 x 4 left-over points: two half-warps of 12 lanes whose
+ *     plane offsets are 6 banks apart), so the 2-double gap between planes never falls inside a half-warp;
+ *   - the face normals (two per task and direction) are read from HBM after an L2 prefetch instead of being staged, which pays for the
+ *     padding: 72.5 KB per CTA as before, three resident CTAs. */
+__constant__ unsigned char c_ns_diag[36] = {0, 29, 35, 8, 4, 15, 11, 17,  23, 34, 12, 18, 14, 25, 26, 22,  28, 1, 7, 3, 24, 20, 21, 27,
+                                            33, 6, 2, 13, 9, 10, 31, 32,  19, 30, 5, 16};
+
+template <bool DEF>
+struct NsPadCfg
+{
+  static constexpr int RS = 6, ND = 3, nq = 216, nfq = 36, nv = 5, n_line = 108, threads = 128;
+  static constexpr int PX = 38, FP = 6*PX; // plane and field pitch in shared memory
+  //   state | flux faces | region A = [LDG faces (padded to nv field pitches) | reference normals] | (free) | G ; F aliases region A as in NsCfg
+  static constexpr int s_state = 0, s_fc = s_state + nv*FP, s_ldg = s_fc + 2*ND*nv*nfq, s_nrml = s_ldg + nv*FP;
+  static constexpr int a_end = s_nrml + (DEF ? ND*ND*FP : 0);
+  static constexpr int s_flux = s_nrml - nv*FP; // = s_ldg: F field 5 lands on the first reference normal
+  static_assert(2*ND*nv*nfq <= nv*FP, "LDG faces must fit the first nv field pitches of F");
+  static constexpr int s_grad = (a_end > s_flux + ND*nv*FP) ? a_end : s_flux + ND*nv*FP;
+  static constexpr int smem_doubles = s_grad + ND*nv*FP;
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 2*sizeof(mbar_t);
+};
+
+/* line task (direction d, line l) of thread slot t for the phases whose tasks are lines of all three directions: warps 0 / 1 / 2 take 32
+ * lines of direction 0 / 1 / 2 (warp 2 through c_ns_diag, with 16-byte accesses), warp 3 the left-over four lines of each */
+__device__ __forceinline__ bool ns_pad_line(int t, int& d, int& l)
+{
+  if (t < 96) { d = t/32; l = d == 2 ? c_ns_diag[t % 32] : t % 32; return true; }
+  if (t < 100) { d = 0; l = 32 + (t - 96); return true; }
+  if (t < 104) { d = 2; l = c_ns_diag[32 + (t - 100)]; return true; }
+  if (t >= 112 && t < 116) { d = 1; l = 32 + (t - 112); return true; }
+  d = 0; l = 0;
+  return false;
+}
+
+/* point of slot s = t + 128*pass (see the header comment); -1: none */
+__device__ __forceinline__ int ns_pad_point(int s)
+{
+  const int hw = s/16, lane = s % 16;
+  if (hw < 12) return (hw/2)*36 + (hw % 2)*16 + lane;
+  if (hw < 14 && lane < 12) return ((hw - 12)*3 + lane/4)*36 + 32 + lane % 4;
+  return -1;
+}
+
+template <bool DEF>
+__global__ void __launch_bounds__(128, 3)
+ns_local_pad_kernel(GArgs a, Ops ops)
+{
+  using C = NsPadCfg<DEF>;
+  using P = PdeNs<3, 6, true>;
+  constexpr int RS = 6, ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads, PX = C::PX, FP = C::FP;
+  constexpr int cs = nv > RS ? nv : RS;
+  HB_DYN_SMEM(double, smem);
+  double* S = smem + C::s_state;
+  const double* fldg = smem + C::s_ldg;
+  const double* fc = smem + C::s_fc;
+  const double* rn = smem + C::s_nrml;
+  double* G = smem + C::s_grad;
+  double* F = smem + C::s_flux;
+  mbar_t* bar = reinterpret_cast<mbar_t*>(smem + C::smem_doubles);
+  const int t = threadIdx.x;
+  const int e = a.elem_begin + blockIdx.x;
+  if (e >= a.elem_end) return;
+  constexpr unsigned b_plane = sizeof(double)*nfq, b_face = sizeof(double)*2*ND*nv*nfq;
+  if (t == 0) {
+    mbar_init(bar, 1); mbar_init_fence();
+    mbar_arrive_expect_tx(bar, nv*RS*b_plane + 2*b_face + (DEF ? ND*ND*RS*b_plane : 0u));
+  }
+  __syncthreads();
+  if (t < 32) { // one 288-byte copy per (field, plane) into the padded layout + the two face blocks
+    const double* g_state = a.ed.state + (size_t)e*nv*nq;
+    for (int c = t; c < nv*RS; c += 32) bulk_g2s(S + (c/RS)*FP + (c % RS)*PX, g_state + (size_t)c*nfq, b_plane, bar);
+    if constexpr (DEF) {
+      const double* g_rn = a.refn + (size_t)(e - a.n_car)*ND*ND*nq;
+      for (int c = t; c < ND*ND*RS; c += 32) bulk_g2s(smem + C::s_nrml + (c/RS)*FP + (c % RS)*PX, g_rn + (size_t)c*nfq, b_plane, bar);
+    }
+    if (t == 30) bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
+    if (t == 31) bulk_g2s(smem + C::s_fc, a.faces + (size_t)e*2*ND*wl, b_face, bar);
+  }
+  // per-point scalars and the face normals: prefetch their cache lines now, read them in P1 / P2 / P4
+  const double* g_tss = a.ed.tss + (size_t)e*nq;
+  const double* g_av = a.ed.av + (size_t)e*2*nq;
+  [[maybe_unused]] const double* g_det = DEF ? a.det + (size_t)(e - a.n_car)*nq : nullptr;
+  [[maybe_unused]] const double* g_fn = DEF ? a.normals + (size_t)(e - a.n_car)*2*ND*ND*nfq : nullptr;
+  {
+    constexpr int lines = (nq*8 + 127)/128, fn_lines = (2*ND*ND*nfq*8 + 127)/128 + 1; // 128-byte lines per field / of the face normals
+    for (int i = t; i < (DEF ? 4*lines + fn_lines : 3*lines); i += T) {
+      const int fld = i/lines, off = (i % lines)*16;
+      if (fld < 4) prefetch_l1(fld == 0 ? g_tss + off : fld == 1 ? g_av + off : fld == 2 ? g_av + nq + off : g_det + off);
+      else { const int o = (i - 4*lines)*16; prefetch_l1(g_fn + (o < 2*ND*ND*nfq ? o : 2*ND*ND*nfq - 1)); }
+    }
+  }
+  const double nom = a.nom[e];
+  const double inv_nom = 1./nom; // reciprocals instead of divisions, see g_local_kernel
+  int ld, ll;
+  const bool has_line = ns_pad_line(t, ld, ll);
+  const bool vec = t >= 64 && t < 96; // warp 2: contiguous lines, 16-byte accesses
+  const int lstride = ld == 0 ? PX : ld == 1 ? RS : 1;
+  const int lq0 = ld == 0 ? ll : ld == 1 ? (ll/RS)*PX + ll % RS : (ll/RS)*PX + (ll % RS)*RS;
+  mbar_wait(bar, 0);
+
+  /* ---- P1: gradient ---- */
+  if constexpr (DEF) {
+    // task of every sub-phase: line l of the current direction, physical component j
+    const bool active = t < 108;
+    const int j = t < 96 ? t/32 : (t - 96)/4;
+    const int slot = t < 96 ? t % 32 : 32 + (t - 96) % 4;
+    #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (active) {
+        const int l = d == 2 ? c_ns_diag[slot] : slot;
+        const int stride = d == 0 ? PX : d == 1 ? RS : 1;
+        const int q0 = d == 0 ? l : d == 1 ? (l/RS)*PX + l % RS : (l/RS)*PX + (l % RS)*RS;
+        double nk[RS]; // the 1/nominal-size factor of the gradient (Spatial.hpp:398) is folded into the normals once per line
+        if (d == 2) {
+          #pragma unroll
+          for (int k = 0; k < RS; k += 2) ld2(rn + (d*ND + j)*FP + q0 + k, nk[k], nk[k + 1]);
+        } else {
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) nk[k] = rn[(d*ND + j)*FP + q0 + k*stride];
+        }
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) nk[k] *= inv_nom;
+        const double fn0 = g_fn[((2*d)*ND + j)*nfq + l]*inv_nom, fn1 = g_fn[((2*d + 1)*ND + j)*nfq + l]*inv_nom;
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          double p[RS];
+          if (d == 2) {
+            #pragma unroll
+            for (int k = 0; k < RS; k += 2) ld2(S + v*FP + q0 + k, p[k], p[k + 1]);
+          } else {
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) p[k] = S[v*FP + q0 + k*stride];
+          }
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) p[k] = nk[k]*p[k];
+          const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
+          double r[RS];
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) {
+            double acc = 0;
+            #pragma unroll
+            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+            acc += ops.lift[i][0]*b0;
+            acc += ops.lift[i][1]*b1;
+            r[i] = acc;
+          }
+          double* g = G + (v*ND + j)*FP + q0;
+          if (d == 0) {
+            #pragma unroll
+            for (int i = 0; i < RS; ++i) g[i*stride] = r[i];
+          } else if (d == 1) {
+            #pragma unroll
+            for (int i = 0; i < RS; ++i) g[i*stride] += r[i];
+          } else {
+            #pragma unroll
+            for (int i = 0; i < RS; i += 2) { double g0, g1; ld2(g + i, g0, g1); st2(g + i, g0 + r[i], g1 + r[i + 1]); }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    if (has_line) {
+      const int d = ld, l = ll, stride = lstride, q0 = lq0;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double p[RS];
+        if (vec) {
+          #pragma unroll
+          for (int k = 0; k < RS; k += 2) ld2(S + v*FP + q0 + k, p[k], p[k + 1]);
+        } else {
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) p[k] = S[v*FP + q0 + k*stride];
+        }
+        const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) {
+          double acc = 0;
+          #pragma unroll
+          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
+          acc += ops.lift[i][0]*b0;
+          acc += ops.lift[i][1]*b1;
+          r[i] = acc*inv_nom;
+        }
+        double* g = G + (v*ND + d)*FP + q0;
+        if (vec) {
+          #pragma unroll
+          for (int i = 0; i < RS; i += 2) st2(g + i, r[i], r[i + 1]);
+        } else {
+          #pragma unroll
+          for (int i = 0; i < RS; ++i) g[i*stride] = r[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  /* ---- P2: pointwise fluxes ---- */
+  #pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q = ns_pad_point(t + pass*T);
+    if (q >= 0) {
+      const int qp = q + 2*(q/nfq);
+      typename P::template Comp<ND> comp;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) comp.state[v] = S[v*FP + qp];
+      comp.state[nv] = g_av[q];
+      comp.state[nv + 1] = g_av[nq + q];
+      if constexpr (DEF) {
+        const double inv_det = 1./g_det[q];
+        #pragma unroll
+        for (int d = 0; d < ND; ++d)
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) comp.normal[j][d] = rn[(d*ND + j)*FP + qp];
+        #pragma unroll
+        for (int v = 0; v < nv; ++v)
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*FP + qp]*inv_det;
+      } else {
+        #pragma unroll
+        for (int v = 0; v < nv; ++v)
+          #pragma unroll
+          for (int j = 0; j < ND; ++j) comp.gradient[v][j] = G[(v*ND + j)*FP + qp];
+      }
+      comp.compute_flux_conv(a.pp);
+      comp.compute_flux_diff(a.pp);
+      #pragma unroll
+      for (int d = 0; d < ND; ++d)
+        #pragma unroll
+        for (int v = 0; v < nv; ++v) {
+          F[(d*nv + v)*FP + qp] = comp.flux_conv[v][d];
+          G[(d*nv + v)*FP + qp] = comp.flux_diff[v][d]; // all of this point's gradient entries are in registers by now
+        }
+    }
+  }
+  __syncthreads();
+
+  /* ---- P3: line derivatives in place, diffusive flux to the LDG faces ---- */
+  if (has_line) {
+    const int d = ld, l = ll, stride = lstride, q0 = lq0;
+    double* fl = a.faces_ldg + (size_t)e*2*ND*wl;
+    #pragma unroll
+    for (int v = 0; v < nv; ++v) {
+      double* row = F + (d*nv + v)*FP + q0;
+      double f[RS], r[RS];
+      if (vec) {
+        #pragma unroll
+        for (int k = 0; k < RS; k += 2) ld2(row + k, f[k], f[k + 1]);
+      } else {
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
+      }
+      const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
+      #pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        double acc = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
+        acc += ops.lift[i][0]*b0;
+        acc += ops.lift[i][1]*b1;
+        r[i] = -acc;
+      }
+      if (vec) {
+        #pragma unroll
+        for (int i = 0; i < RS; i += 2) st2(row + i, r[i], r[i + 1]);
+      } else {
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
+      }
+      double* drow = G + (d*nv + v)*FP + q0;
+      if (vec) {
+        #pragma unroll
+        for (int k = 0; k < RS; k += 2) ld2(drow + k, f[k], f[k + 1]);
+      } else {
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
+      }
+      double e0 = 0, e1 = 0;
+      #pragma unroll
+      for (int k = 0; k < RS; ++k) { e0 += ops.bnd[0][k]*f[k]; e1 += ops.bnd[1][k]*f[k]; }
+      fl[(size_t)(2*d)*wl + v*nfq + l] = e0;
+      fl[(size_t)(2*d + 1)*wl + v*nfq + l] = e1;
+      #pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        double acc = 0;
+        #pragma unroll
+        for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
+        r[i] = -acc;
+      }
+      if (vec) {
+        #pragma unroll
+        for (int i = 0; i < RS; i += 2) st2(drow + i, r[i], r[i + 1]);
+      } else {
+        #pragma unroll
+        for (int i = 0; i < RS; ++i) drow[i*stride] = r[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  /* ---- P4: combine and update ---- */
+  #pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q = ns_pad_point(t + pass*T);
+    if (q >= 0) {
+      const int qp = q + 2*(q/nfq);
+      double mult; // update*tss/nom/det with one division (<= 1 ulp)
+      const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
+      if constexpr (DEF) mult = update*g_tss[q]/(nom*g_det[q]);
+      else mult = update*g_tss[q]/nom;
+      #pragma unroll
+      for (int v = 0; v < nv; ++v) {
+        double r0 = 0., r1 = 0.;
+        #pragma unroll
+        for (int d = 0; d < ND; ++d) { r0 += F[(d*nv + v)*FP + qp]; r1 += G[(d*nv + v)*FP + qp]; }
+        double* cache = a.ed.cache + ((size_t)e*cs + v)*nq + q;
+        double u = r0;
+        *cache = u;
+        u += r1;
+        u *= mult;
+        if (a.compute_residual) *cache = u;
+        else a.ed.state[((size_t)e*nv + v)*nq + q] = S[v*FP + qp] + u;
+      }
+    }
+  }
+}
+
 /* ---------------- Navier-Stokes Reconcile_ldg_flux, 3-D, bulk-copy staging ----------------
  * Same arithmetic as g_reconcile_kernel<3, RS, PdeNs<3, RS, true>, DEF> without the modal filter and outside residual mode
  * (reference include/Spatial.hpp:543-594). The kernel is a pure stream (38 KB in+out per element at row size 6 against ~60 flops
@@ -1152,6 +1493,13 @@ int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
   } else if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
     if (a.use_filter || !c->use_pipe) return -1;
     const int grid = a.elem_end - a.elem_begin;
+    if constexpr (RS == 6) {
+      if (c->ns_pad) { // the bank-conflict-free layout (default; HEXED_B200_OPT_NS_LOCAL_LAYOUT = 0 keeps the dense one for A/B)
+        if (deformed) { using C = NsPadCfg<true>; auto k = ns_local_pad_kernel<true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+        else { using C = NsPadCfg<false>; auto k = ns_local_pad_kernel<false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+        return 0;
+      }
+    }
     if (deformed) { using C = NsCfg<RS, true>; auto k = ns_local_line_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
     else { using C = NsCfg<RS, false>; auto k = ns_local_line_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
     return 0;

@@ -841,6 +841,12 @@ int add_device_bc(Kernel_mesh km, int kind, const std::vector<double*>& inside_f
   return id;
 }
 
+void set_device_bc_params(Kernel_mesh km, int id, const std::vector<double>& params)
+{
+  Mirror& m = mirror(km);
+  for (Rank& k : m.ranks) check(&m, hexed_b200_bc_set_params(k.ctx, id, params.data(), int(params.size())), k.ctx);
+}
+
 void apply_state_bcs(Kernel_mesh km)
 {
   Call call(km, faces, faces);

@@ -96,6 +96,7 @@ void synchronize(hexed::Kernel_mesh);
  * `apply_state_bcs` / `apply_flux_bcs` then stand in for the loops of `Solver::apply_state_bcs` / `apply_flux_bcs`
  * (src/Solver.cpp:56-81) for the registered faces. */
 int add_device_bc(hexed::Kernel_mesh, int kind, const std::vector<double*>& inside_faces, const std::vector<double>& params);
+void set_device_bc_params(hexed::Kernel_mesh, int id, const std::vector<double>& params); //!< e.g. a freestream state that changes between iterations
 void apply_state_bcs(hexed::Kernel_mesh);
 void apply_flux_bcs(hexed::Kernel_mesh);
 

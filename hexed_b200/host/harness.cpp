@@ -367,6 +367,18 @@ int hbh_add_device_bc(void* handle, int kind, const int* def_con_index, int n, c
   }
 }
 
+int hbh_set_device_bc_params(void* handle, int id, const double* params, int n_params)
+{
+  auto* h = static_cast<Harness*>(handle);
+  try {
+    hexed_b200::set_device_bc_params(h->mesh(), id, std::vector<double>(params, params + n_params));
+    return 0;
+  } catch (const std::exception& ex) {
+    h->error = ex.what();
+    return 1;
+  }
+}
+
 int hbh_apply_bcs(void* handle, int flux)
 {
   auto* h = static_cast<Harness*>(handle);

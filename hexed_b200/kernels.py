@@ -132,6 +132,7 @@ SIGNATURES = {
     "hexed_b200_local_euler": [C.c_void_p, C.c_int, Options],
     "hexed_b200_bc_create": [C.c_void_p, C.c_int, C.c_int, ip, ip, ip, dp, C.c_int, ip],
     "hexed_b200_apply_state_bcs": [C.c_void_p],
+    "hexed_b200_bc_set_params": [C.c_void_p, C.c_int, dp, C.c_int],
     "hexed_b200_set_timing": [C.c_void_p, C.c_int],
     "hexed_b200_set_option": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_kernel_stats": [C.c_void_p, C.POINTER(KernelStat), C.c_int, ip],
@@ -541,6 +542,11 @@ class Device:
 
     def apply_state_bcs(self):
         self._check(self.lib.hexed_b200_apply_state_bcs(self.ctx))
+
+    def bc_set_params(self, bc_id, params):
+        """new parameter block for a registered boundary condition (e.g. a time-dependent freestream state)"""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(self.lib.hexed_b200_bc_set_params(self.ctx, int(bc_id), p.ctypes.data_as(dp), p.size))
 
     # ---- profiling side-contract ----
     def set_timing(self, enabled):

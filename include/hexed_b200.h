@@ -215,6 +215,9 @@ int hexed_b200_local_euler(hexed_b200_ctx* ctx, int deformed, hexed_b200_options
  * 3x3 column-pivoted Householder QR done per face point in registers; state cache on the device) */
 int hexed_b200_bc_create(hexed_b200_ctx* ctx, int kind, int n, const int* inside_slot, const int* ghost_slot,
                          const int* normal_slot, const double* params, int n_params, int* bc_id);
+/* new values for the parameter block of a registered condition, e.g. a freestream state that HIL changes between iterations
+ * (`Freestream::fs`, include/Boundary_condition.hpp): stream-ordered, read by every apply_*_bcs enqueued after this call */
+int hexed_b200_bc_set_params(hexed_b200_ctx* ctx, int bc_id, const double* params, int n_params);
 int hexed_b200_apply_state_bcs(hexed_b200_ctx* ctx);
 /* Solver::apply_flux_bcs (src/Solver.cpp:69-81) for the same boundary conditions: Freestream/Copy::apply_flux = copy_state
  * (src/Boundary_condition.cpp:12-23,304-305,455-458), Nonpenetration::apply_flux (:329-341). The flux cache copy of :75-76 is host-side. */
@@ -370,7 +373,9 @@ int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
  * HEXED_B200_OPT_FUSED_ADMIS = the pipelined Euler Local kernels also leave, per element, whether the state and faces they have just written
  * are admissible / finite; hexed_b200_is_admissible right after hexed_b200_compute_euler then reduces 4 bytes per element instead of scanning
  * the state (same answer and record; anything else that writes element state or faces in between falls back to the full scan). Default 0. */
-enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1, HEXED_B200_OPT_FUSED_ADMIS = 2 };
+enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1, HEXED_B200_OPT_FUSED_ADMIS = 2,
+       HEXED_B200_OPT_NS_LOCAL_LAYOUT = 3 /* 3-D row-size-6 Navier-Stokes Local: 1 (default) = bank-conflict-free padded shared-memory layout
+                                             (ns_local_pad_kernel), 0 = the dense layout of ns_local_line_kernel; bit-identical results */ };
 int hexed_b200_set_option(hexed_b200_ctx* ctx, int option, int value);
 int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);
 int hexed_b200_reset_stats(hexed_b200_ctx* ctx);

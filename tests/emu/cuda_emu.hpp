@@ -21,6 +21,7 @@
 
 #define __global__
 #define __device__
+#define __constant__
 #define __host__
 #define __forceinline__ inline
 #define __shared__ static

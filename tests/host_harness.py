@@ -194,6 +194,11 @@ class HostHarness:
             n_params = params.size if bc.get("params") is not None else 0
             self._check(self.lib.hbh_add_device_bc(self.h, bc["kind"], _i(idx), idx.size, _d(params), n_params))
 
+    def set_device_bc_params(self, bc_id, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self.lib.hbh_set_device_bc_params.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+        self._check(self.lib.hbh_set_device_bc_params(self.h, int(bc_id), _d(p), p.size))
+
     def is_admissible(self):
         ok = np.zeros(1, np.int32); rec = np.zeros(max(self.m.n_elem, 1), np.int32)
         self._check(self.lib.hbh_is_admissible(self.h, _i(ok), _i(rec)))

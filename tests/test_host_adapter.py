@@ -295,6 +295,44 @@ def test_adapter_device_bcs_gpu(oracle, host_gpu, resident):
     check_adapter_device_bcs(oracle, host_gpu, resident, 3, 4)
 
 
+def test_adapter_device_bc_params_change_emu(oracle, host_emu):
+    """hexed_b200::set_device_bc_params: a freestream state that changes between steps (stream-ordered update of the parameter block)"""
+    basis = hb.gauss_legendre(3)
+    fs = freestream_state(2)
+    m = M.box_mesh(2, 3, 4, basis, deformed=True, bc_kind=M.BC_FREESTREAM, bc_params=fs)
+    density_wave(m, basis)
+    oracle.compute_write_face(basis, m)
+    ref, work = m.copy(), m.copy()
+    h = H.HostHarness(host_emu, m, basis, seed=4)
+    h.set_sync_mode(H.RESIDENT)
+    h.invalidate()
+    dts = []
+    for step in range(3):
+        new_fs = np.asarray(fs)*(1. + 0.01*step)
+        ref.bcs[0]["params"] = new_fs
+        dt_o = oracle.max_dt(EULER, basis, ref, 0.5, 0.5, False)
+        dt_d = h.call("max_dt_euler", 0.5, 0.5, False)
+        if step == 0:
+            h.add_device_bcs(m)
+        h.set_device_bc_params(0, new_fs)
+        dts.append((dt_d, dt_o))
+        for stage in (0, 1):
+            oracle.apply_state_bcs(ref); h.apply_state_bcs()
+            oracle.compute_euler(basis, ref, dt=dt_o, i_stage=stage); h.call("compute_euler", dt=dt_o, i_stage=stage)
+    h.to_host(H.ALL_ELEM | H.FACES)
+    h.fetch(work)
+    h.set_sync_mode(H.SYNC_EVERY_CALL)
+    h.close()
+    assert_euler_parity(work, ref, dts)
+    with pytest.raises(RuntimeError):
+        h2 = H.HostHarness(host_emu, m, basis, seed=4)
+        try:
+            h2.call("max_dt_euler", 0.5, 0.5, False)
+            h2.set_device_bc_params(7, fs)
+        finally:
+            h2.close()
+
+
 @pytest.mark.parametrize("resident", [False, True])
 def test_adapter_is_admissible_emu(oracle, host_emu, resident):
     """hexed_b200::is_admissible through the pointer-graph adapter: same answer and Element::record as the oracle's restatement of

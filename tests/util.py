@@ -72,10 +72,12 @@ def prepare_pde_state(mesh, rng, pde):
         d[:, M.FORCING_SLOT(nd):M.FORCING_SLOT(nd) + 4] = rng.standard_normal((ne, 4, nq))
 
 
-def run_pde_pair(oracle, lib_path, mesh, basis, pde, n_steps=1, local_time=False, use_filter=False, safety=0.3, compute_residual=False):
+def run_pde_pair(oracle, lib_path, mesh, basis, pde, n_steps=1, local_time=False, use_filter=False, safety=0.3, compute_residual=False, options=()):
     """one `max_dt_*` + stage sequence per step on both implementations, mirroring how Solver drives each PDE"""
     ref = mesh.copy()
     dev = Device(mesh.n_dim, mesh.row_size, basis, lib_path=lib_path).load_mesh(mesh)
+    for opt, val in options:
+        dev.set_option(opt, val)
     visc_o, cond_o = pyoracle.sutherland(1.7e-5, 273., 110.), pyoracle.constant(2.5e-2)
     visc_d, cond_d = K.sutherland(1.7e-5, 273., 110.), K.constant_transport(2.5e-2)
     dts = []
