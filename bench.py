@@ -233,6 +233,8 @@ def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_over
                 raise RuntimeError("inadmissible state in the benchmark flow")
 
         def step():
+            if dev_bcs:  # this step's input: the freestream state of the boundary condition (a HIL-controlled, possibly time-dependent, value)
+                clocked("hexed_calls", h.set_device_bc_params, 0, fs)
             if viscous:
                 dt = clocked("hexed_calls", h.call, "max_dt_navier_stokes", 0.7, 0.7, False, *visc, *cond)
                 state_bcs()
@@ -272,10 +274,12 @@ def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_over
             text = ("sync_every_call (the zero-Solver-change default of the adapter): every hexed:: call uploads what it reads from the host objects, "
                     "metric terms included, and downloads what it wrote")
         elif dev_bcs:
-            h2d, d2h = 0, 8 + 2*8*n_dev
-            text = ("adapter (hexed::max_dt_*/compute_* + hexed_b200::apply_state_bcs / is_admissible of hexed_b200/host/adapter.cpp on a pointer-graph "
-                    "Kernel_mesh), resident, boundary conditions registered on the devices; per step: dt D2H, and after each stage the admissibility flags of "
-                    "every device D2H (Element::record only when a device reports an inadmissible state)")
+            h2d, d2h = 8*nv*n_dev, 8 + 2*8*n_dev
+            text = ("adapter (hexed::max_dt_* / compute_* + hexed_b200::set_device_bc_params / apply_state_bcs / is_admissible of hexed_b200/host/adapter.cpp on "
+                    "a pointer-graph Kernel_mesh), state resident on the device(s), boundary conditions registered on the devices (INTEGRATION.md section 3a); "
+                    "per step: the freestream state of the boundary condition H2D, dt D2H, and after each stage the admissibility flags of every device D2H "
+                    "(Element::record only when a device reports an inadmissible state), as Solver::update does. Nothing else has to cross PCIe in a Hexed run "
+                    "whose boundary conditions the device implements; the variant with HOST-applied conditions is aux.e2e_adapter_host_bcs")
         else:
             h2d, d2h = n_exch*per_stage, n_exch*per_stage + 8
             text = ("adapter (hexed::max_dt_*/compute_* of hexed_b200/host/adapter.cpp on a pointer-graph Kernel_mesh), resident; per stage: inside boundary "
@@ -672,10 +676,11 @@ def main():
             keep = ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "elements", "elements_per_gpu", "box", "transport",
                     "boundary_faces", "host_ms_per_step", "mode")
             try:
-                res = adapter_e2e(args, world, viscous, args.steps, 3, modes=("host_bcs",) if args.no_aux_lines else ("host_bcs", "device_bcs"))
-                e2e = res["host_bcs"]
-                if "device_bcs" in res:
-                    aux["e2e_adapter_device_bcs"] = {k: res["device_bcs"].get(k) for k in keep}
+                # the host-applied variant only on one GPU: its per-face host loop is Amdahl's serial part (one process, all boundary faces of all devices)
+                res = adapter_e2e(args, world, viscous, args.steps, 3, modes=("host_bcs", "device_bcs") if (world == 1 and not args.no_aux_lines) else ("device_bcs",))
+                e2e = res["device_bcs"]
+                if "host_bcs" in res:
+                    aux["e2e_adapter_host_bcs"] = {k: res["host_bcs"].get(k) for k in keep}
             except Exception as ex:
                 e2e = {"value": None, "unit": "DOF-stage/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "mode": "adapter run failed: %r" % (ex,)}
             if world == 1 and not args.no_aux_lines and not viscous:

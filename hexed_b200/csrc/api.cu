@@ -162,6 +162,32 @@ int hexed_b200_create(hexed_b200_ctx** out, int device, int n_dim, int row_size,
   }
   for (int i = 0; i < rs; ++i) for (int j = 0; j < rs; ++j)
     c->ops.dfull[i][j] = diff[i][j] - (c->ops.lift[i][0]*bnd[0][j] + c->ops.lift[i][1]*bnd[1][j]);
+  { // even-odd halves (common.cuh); only meaningful for node sets symmetric about 1/2, which is checked here entry by entry
+    const int h = rs/2;
+    double scale = 0, asym = 0;
+    for (int i = 0; i < rs; ++i) {
+      for (int j = 0; j < rs; ++j) {
+        scale = std::max(scale, std::abs(c->ops.dfull[i][j]));
+        asym = std::max(asym, std::abs(c->ops.dfull[i][j] + c->ops.dfull[rs - 1 - i][rs - 1 - j]));
+        asym = std::max(asym, std::abs(c->ops.diff[i][j] + c->ops.diff[rs - 1 - i][rs - 1 - j]));
+      }
+      asym = std::max(asym, std::abs(c->ops.lift[i][0] + c->ops.lift[rs - 1 - i][1]));
+      asym = std::max(asym, std::abs(bnd[0][i] - bnd[1][rs - 1 - i]));
+    }
+    c->ops_symmetric = rs % 2 == 0 && asym <= 1e-13*scale;
+    for (int i = 0; i < h; ++i) {
+      for (int k = 0; k < h; ++k) {
+        c->ops.eo_a[i][k] = .5*(c->ops.dfull[i][k] - c->ops.dfull[i][rs - 1 - k]);
+        c->ops.eo_s[i][k] = .5*(c->ops.dfull[i][k] + c->ops.dfull[i][rs - 1 - k]);
+        c->ops.eo_da[i][k] = .5*(diff[i][k] - diff[i][rs - 1 - k]);
+        c->ops.eo_ds[i][k] = .5*(diff[i][k] + diff[i][rs - 1 - k]);
+      }
+      c->ops.eo_la[i] = .5*(c->ops.lift[i][0] - c->ops.lift[i][1]);
+      c->ops.eo_ls[i] = .5*(c->ops.lift[i][0] + c->ops.lift[i][1]);
+      c->ops.eo_ba[i] = .5*(bnd[0][i] - bnd[0][rs - 1 - i]);
+      c->ops.eo_bs[i] = .5*(bnd[0][i] + bnd[0][rs - 1 - i]);
+    }
+  }
   static const char* names[ST_COUNT] = {"neighbor", "neighbor", "local", "local", "compute time step", "compute time step",
                                         "prolong/restrict", "boundary conditions", "write face", "reconcile LDG flux", "reconcile LDG flux", "check admis."};
   static const int trees[ST_COUNT] = {0, 1, 0, 1, 0, 1, 2, 2, 2, 0, 1, 2};

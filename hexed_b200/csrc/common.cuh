@@ -26,7 +26,68 @@ struct Ops
   double bnd[2][MAX_RS];
   double lift[MAX_RS][2];
   double node[MAX_RS];
+  /* Even-odd halves of the same operators (H = row_size/2, the factor 1/2 folded in), valid when the nodes are symmetric about 1/2 (Gauss-Legendre and
+   * Gauss-Lobatto are): then dfull[RS-1-i][RS-1-k] = -dfull[i][k], lift[RS-1-i][0] = -lift[i][1], bnd[1][k] = bnd[0][RS-1-k], and a line
+   * derivative costs RS*(RS/2 + 1) multiply-adds on the sums and differences of mirrored points instead of RS*(RS + 2) (line_deriv_eo).
+   *   eo_a = (dfull[i][k] - dfull[i][RS-1-k])/2, eo_s = (... + ...)/2, eo_la = (lift[i][0] - lift[i][1])/2, eo_ls = (... + ...)/2,
+   *   eo_da / eo_ds likewise for diff, eo_ba = (bnd[0][k] - bnd[0][RS-1-k])/2, eo_bs = (... + ...)/2 */
+  double eo_a[MAX_RS/2][MAX_RS/2], eo_s[MAX_RS/2][MAX_RS/2], eo_la[MAX_RS/2], eo_ls[MAX_RS/2];
+  double eo_da[MAX_RS/2][MAX_RS/2], eo_ds[MAX_RS/2][MAX_RS/2];
+  double eo_ba[MAX_RS/2], eo_bs[MAX_RS/2];
 };
+
+#if defined(__CUDACC__) || defined(HB_EMULATE)
+/* r = dfull f + lift (b0, b1) -- the DG line derivative D(q, b) of include/Derivative.hpp:51-55 -- through the even-odd halves:
+ * with a[k] = f[k] - f[RS-1-k], s[k] = f[k] + f[RS-1-k]:  r[i] = P + Q, r[RS-1-i] = P - Q,
+ * P = sum_k eo_a[i][k] a[k] + eo_la[i] (b0 - b1), Q = sum_k eo_s[i][k] s[k] + eo_ls[i] (b0 + b1).  NEG: returns -r (the residual sign). */
+template <int RS, bool NEG = false>
+__device__ __forceinline__ void line_deriv_eo(const Ops& ops, const double (&f)[RS], double b0, double b1, double (&r)[RS])
+{
+  constexpr int H = RS/2;
+  static_assert(RS % 2 == 0, "even row sizes only");
+  double a[H], s[H];
+  #pragma unroll
+  for (int k = 0; k < H; ++k) { a[k] = f[k] - f[RS - 1 - k]; s[k] = f[k] + f[RS - 1 - k]; }
+  const double bd = b0 - b1, bs = b0 + b1;
+  #pragma unroll
+  for (int i = 0; i < H; ++i) {
+    double p = 0, q = 0;
+    #pragma unroll
+    for (int k = 0; k < H; ++k) { p += ops.eo_a[i][k]*a[k]; q += ops.eo_s[i][k]*s[k]; }
+    p += ops.eo_la[i]*bd;
+    q += ops.eo_ls[i]*bs;
+    if constexpr (NEG) { r[i] = -p - q; r[RS - 1 - i] = q - p; }
+    else { r[i] = p + q; r[RS - 1 - i] = p - q; }
+  }
+}
+/* r = diff_mat f (no boundary term) */
+template <int RS, bool NEG = false>
+__device__ __forceinline__ void line_diff_eo(const Ops& ops, const double (&f)[RS], double (&r)[RS])
+{
+  constexpr int H = RS/2;
+  double a[H], s[H];
+  #pragma unroll
+  for (int k = 0; k < H; ++k) { a[k] = f[k] - f[RS - 1 - k]; s[k] = f[k] + f[RS - 1 - k]; }
+  #pragma unroll
+  for (int i = 0; i < H; ++i) {
+    double p = 0, q = 0;
+    #pragma unroll
+    for (int k = 0; k < H; ++k) { p += ops.eo_da[i][k]*a[k]; q += ops.eo_ds[i][k]*s[k]; }
+    if constexpr (NEG) { r[i] = -p - q; r[RS - 1 - i] = q - p; }
+    else { r[i] = p + q; r[RS - 1 - i] = p - q; }
+  }
+}
+/* e0 = bnd[0] . x, e1 = bnd[1] . x (extrapolation of a line to its two faces, include/Spatial.hpp:41-57) */
+template <int RS>
+__device__ __forceinline__ void face_extrap_eo(const Ops& ops, const double (&x)[RS], double& e0, double& e1)
+{
+  constexpr int H = RS/2;
+  double p = 0, q = 0;
+  #pragma unroll
+  for (int k = 0; k < H; ++k) { p += ops.eo_bs[k]*(x[k] + x[RS - 1 - k]); q += ops.eo_ba[k]*(x[k] - x[RS - 1 - k]); }
+  e0 = p + q; e1 = p - q;
+}
+#endif
 
 struct FilterOp { double filter[MAX_RS][MAX_RS]; };
 struct TransferOps { double prolong[2][MAX_RS][MAX_RS]; double restrict_[2][MAX_RS][MAX_RS]; };
@@ -99,6 +160,7 @@ struct hexed_b200_ctx
   // stats
   hb::Stat stats[hb::ST_COUNT];
   bool timing = false;
+  bool ops_symmetric = false; // the basis nodes are symmetric about 1/2: the even-odd operator halves (Ops::eo_*) are valid, which the line-task kernels require
   bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
   bool pipe_lean4 = false; // 3-D Cartesian Euler: lean layout with four resident CTAs (option value 3; experiment)
   bool ns_pad = true; // 3-D row-size-6 Navier-Stokes Local: the bank-conflict-free padded layout (ns_local_pad_kernel); option HEXED_B200_OPT_NS_LOCAL_LAYOUT

@@ -561,15 +561,12 @@ ns_local_line_kernel(GArgs a, Ops ops)
           #pragma unroll
           for (int k = 0; k < RS; ++k) p[k] = nk[k]*S[v*nq + q0 + k*stride];
           const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
+          double r[RS];
+          line_deriv_eo<RS>(ops, p, b0, b1, r);
           #pragma unroll
           for (int i = 0; i < RS; ++i) {
-            double acc = 0;
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-            acc += ops.lift[i][0]*b0;
-            acc += ops.lift[i][1]*b1;
             double* g = G + (v*ND + j)*nq + q0 + i*stride;
-            if (d == 0) *g = acc; else *g += acc;
+            if (d == 0) *g = r[i]; else *g += r[i];
           }
         }
       }
@@ -586,15 +583,10 @@ ns_local_line_kernel(GArgs a, Ops ops)
         #pragma unroll
         for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
         const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
+        line_deriv_eo<RS>(ops, p, b0, b1, r);
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          G[(v*ND + d)*nq + q0 + i*stride] = acc*inv_nom;
-        }
+        for (int i = 0; i < RS; ++i) G[(v*ND + d)*nq + q0 + i*stride] = r[i]*inv_nom;
       }
     }
     __syncthreads();
@@ -648,30 +640,20 @@ ns_local_line_kernel(GArgs a, Ops ops)
       #pragma unroll
       for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
       const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
+      double r[RS];
+      line_deriv_eo<RS, true>(ops, f, b0, b1, r);
       #pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        double acc = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
-        acc += ops.lift[i][0]*b0;
-        acc += ops.lift[i][1]*b1;
-        row[i*stride] = -acc;
-      }
+      for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
       double* drow = G + (d*nv + v)*nq + q0;
       #pragma unroll
       for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
-      double e0 = 0, e1 = 0;
-      #pragma unroll
-      for (int k = 0; k < RS; ++k) { e0 += ops.bnd[0][k]*f[k]; e1 += ops.bnd[1][k]*f[k]; }
+      double e0, e1;
+      face_extrap_eo<RS>(ops, f, e0, e1);
       fl[(size_t)(2*d)*wl + v*nfq + l] = e0;
       fl[(size_t)(2*d + 1)*wl + v*nfq + l] = e1;
+      line_diff_eo<RS, true>(ops, f, r);
       #pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        double acc = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
-        drow[i*stride] = -acc;
-      }
+      for (int i = 0; i < RS; ++i) drow[i*stride] = r[i];
     }
   }
   __syncthreads();
@@ -809,14 +791,26 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   const bool vec = t >= 64 && t < 96; // warp 2: contiguous lines, 16-byte accesses
   const int lstride = ld == 0 ? PX : ld == 1 ? RS : 1;
   const int lq0 = ld == 0 ? ll : ld == 1 ? (ll/RS)*PX + ll % RS : (ll/RS)*PX + (ll % RS)*RS;
+  // P1 task of every sub-phase (deformed): line l of the current direction, physical component j
+  [[maybe_unused]] const bool active = t < 108;
+  [[maybe_unused]] const int j = t < 96 ? t/32 : (t - 96)/4;
+  [[maybe_unused]] const int slot = t < 96 ? t % 32 : 32 + (t - 96) % 4;
+  [[maybe_unused]] double fnv[ND][2]; // the task's face normals, fetched from HBM while the bulk copies are in flight
+  if constexpr (DEF) {
+    if (active) {
+      #pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const int l = d == 2 ? c_ns_diag[slot] : slot;
+        fnv[d][0] = g_fn[((2*d)*ND + j)*nfq + l];
+        fnv[d][1] = g_fn[((2*d + 1)*ND + j)*nfq + l];
+      }
+    }
+  }
   mbar_wait(bar, 0);
 
   /* ---- P1: gradient ---- */
+  [[maybe_unused]] double pt_av0[2], pt_av1[2], pt_det[2], pt_tss[2]; // per-point scalars of P2 / P4, fetched one barrier early
   if constexpr (DEF) {
-    // task of every sub-phase: line l of the current direction, physical component j
-    const bool active = t < 108;
-    const int j = t < 96 ? t/32 : (t - 96)/4;
-    const int slot = t < 96 ? t % 32 : 32 + (t - 96) % 4;
     #pragma unroll
     for (int d = 0; d < ND; ++d) {
       if (active) {
@@ -833,7 +827,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         }
         #pragma unroll
         for (int k = 0; k < RS; ++k) nk[k] *= inv_nom;
-        const double fn0 = g_fn[((2*d)*ND + j)*nfq + l]*inv_nom, fn1 = g_fn[((2*d + 1)*ND + j)*nfq + l]*inv_nom;
+        const double fn0 = fnv[d][0]*inv_nom, fn1 = fnv[d][1]*inv_nom;
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
           double p[RS];
@@ -848,15 +842,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
           for (int k = 0; k < RS; ++k) p[k] = nk[k]*p[k];
           const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
           double r[RS];
-          #pragma unroll
-          for (int i = 0; i < RS; ++i) {
-            double acc = 0;
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-            acc += ops.lift[i][0]*b0;
-            acc += ops.lift[i][1]*b1;
-            r[i] = acc;
-          }
+          line_deriv_eo<RS>(ops, p, b0, b1, r);
           double* g = G + (v*ND + j)*FP + q0;
           if (d == 0) {
             #pragma unroll
@@ -870,7 +856,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
           }
         }
       }
-      __syncthreads();
+      if (d < ND - 1) __syncthreads();
     }
   } else {
     if (has_line) {
@@ -887,15 +873,9 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         }
         const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
         double r[RS];
+        line_deriv_eo<RS>(ops, p, b0, b1, r);
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          r[i] = acc*inv_nom;
-        }
+        for (int i = 0; i < RS; ++i) r[i] *= inv_nom;
         double* g = G + (v*ND + d)*FP + q0;
         if (vec) {
           #pragma unroll
@@ -906,8 +886,16 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         }
       }
     }
-    __syncthreads();
   }
+  #pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q = ns_pad_point(t + pass*T);
+    if (q >= 0) {
+      pt_av0[pass] = g_av[q]; pt_av1[pass] = g_av[nq + q];
+      if constexpr (DEF) pt_det[pass] = g_det[q];
+    }
+  }
+  __syncthreads();
 
   /* ---- P2: pointwise fluxes ---- */
   #pragma unroll
@@ -918,10 +906,10 @@ ns_local_pad_kernel(GArgs a, Ops ops)
       typename P::template Comp<ND> comp;
       #pragma unroll
       for (int v = 0; v < nv; ++v) comp.state[v] = S[v*FP + qp];
-      comp.state[nv] = g_av[q];
-      comp.state[nv + 1] = g_av[nq + q];
+      comp.state[nv] = pt_av0[pass];
+      comp.state[nv + 1] = pt_av1[pass];
       if constexpr (DEF) {
-        const double inv_det = 1./g_det[q];
+        const double inv_det = 1./pt_det[pass];
         #pragma unroll
         for (int d = 0; d < ND; ++d)
           #pragma unroll
@@ -965,15 +953,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
       }
       const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
-      #pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        double acc = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
-        acc += ops.lift[i][0]*b0;
-        acc += ops.lift[i][1]*b1;
-        r[i] = -acc;
-      }
+      line_deriv_eo<RS, true>(ops, f, b0, b1, r);
       if (vec) {
         #pragma unroll
         for (int i = 0; i < RS; i += 2) st2(row + i, r[i], r[i + 1]);
@@ -989,18 +969,11 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         #pragma unroll
         for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
       }
-      double e0 = 0, e1 = 0;
-      #pragma unroll
-      for (int k = 0; k < RS; ++k) { e0 += ops.bnd[0][k]*f[k]; e1 += ops.bnd[1][k]*f[k]; }
+      double e0, e1;
+      face_extrap_eo<RS>(ops, f, e0, e1);
       fl[(size_t)(2*d)*wl + v*nfq + l] = e0;
       fl[(size_t)(2*d + 1)*wl + v*nfq + l] = e1;
-      #pragma unroll
-      for (int i = 0; i < RS; ++i) {
-        double acc = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
-        r[i] = -acc;
-      }
+      line_diff_eo<RS, true>(ops, f, r);
       if (vec) {
         #pragma unroll
         for (int i = 0; i < RS; i += 2) st2(drow + i, r[i], r[i + 1]);
@@ -1010,6 +983,12 @@ ns_local_pad_kernel(GArgs a, Ops ops)
       }
     }
   }
+  #pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q = ns_pad_point(t + pass*T);
+    if (q >= 0) pt_tss[pass] = g_tss[q];
+  }
+  const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
   __syncthreads();
 
   /* ---- P4: combine and update ---- */
@@ -1019,9 +998,8 @@ ns_local_pad_kernel(GArgs a, Ops ops)
     if (q >= 0) {
       const int qp = q + 2*(q/nfq);
       double mult; // update*tss/nom/det with one division (<= 1 ulp)
-      const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
-      if constexpr (DEF) mult = update*g_tss[q]/(nom*g_det[q]);
-      else mult = update*g_tss[q]/nom;
+      if constexpr (DEF) mult = update*pt_tss[pass]/(nom*pt_det[pass]);
+      else mult = update*pt_tss[pass]/nom;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         double r0 = 0., r1 = 0.;
@@ -1491,7 +1469,7 @@ int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
     else { using C = Ns2Cfg<RS, false>; auto k = ns_local_line2d_kernel<RS, false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
     return 0;
   } else if constexpr (ND == 3 && (RS == 4 || RS == 6)) {
-    if (a.use_filter || !c->use_pipe) return -1;
+    if (a.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
     const int grid = a.elem_end - a.elem_begin;
     if constexpr (RS == 6) {
       if (c->ns_pad) { // the bank-conflict-free layout (default; HEXED_B200_OPT_NS_LOCAL_LAYOUT = 0 keeps the dense one for A/B)

@@ -158,7 +158,7 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
 
   // line task of this thread: dimension d, line l (its face quadrature point), points q0 + k*stride
   int d, l;
-  using Map = LineMap<RS, !DEF && !LEAN>; // measured: pays off for the (classic) Cartesian kernel only (see common.cuh)
+  using Map = LineMap<RS, !DEF>; // measured: pays off for the Cartesian kernels only (see common.cuh)
   const bool has_line = Map::get(t, d, l);
   const bool vec = Map::vec2 && d == 2; // this thread's line is contiguous: 16-byte accesses
   const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
@@ -229,15 +229,7 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
         for (int v = 0; v < nv; ++v) {
           const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
           double r[RS];
-          #pragma unroll
-          for (int i = 0; i < RS; ++i) {
-            double acc = 0;
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
-            acc += ops.lift[i][0]*b0;
-            acc += ops.lift[i][1]*b1;
-            r[i] = -acc;
-          }
+          line_deriv_eo<RS, true>(ops, f[v], b0, b1, r);
           double* row = R + (d*nv + v)*nq + q0;
           if (vec) {
             #pragma unroll
@@ -279,15 +271,10 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
           const double b0 = F[((2*d)*nv + v)*nfq + l], b1 = F[((2*d + 1)*nv + v)*nfq + l];
+          double r[RS];
+          line_deriv_eo<RS, true>(ops, f[v], b0, b1, r);
           #pragma unroll
-          for (int i = 0; i < RS; ++i) {
-            double acc = 0;
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
-            acc += ops.lift[i][0]*b0;
-            acc += ops.lift[i][1]*b1;
-            R[(d*nv + v)*nq + q0 + i*stride] = -acc;
-          }
+          for (int i = 0; i < RS; ++i) R[(d*nv + v)*nq + q0 + i*stride] = r[i];
         }
       }
     }
@@ -441,12 +428,8 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
             #pragma unroll
             for (int k = 0; k < RS; ++k) x[k] = S[v*nq + q0 + k*stride];
           }
-          double e0 = 0, e1 = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) {
-            e0 += ops.bnd[0][k]*x[k];
-            e1 += ops.bnd[1][k]*x[k];
-          }
+          double e0, e1;
+          face_extrap_eo<RS>(ops, x, e0, e1);
           fout[((2*d)*nv + v)*nfq + l] = e0;
           fout[((2*d + 1)*nv + v)*nfq + l] = e1;
           if (a.record) bad |= ((isfinite(e0) && isfinite(e1)) ? 0 : 2) | ((v >= ND && !(e0 > 0. && e1 > 0.)) ? 1 : 0);
@@ -457,13 +440,11 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
         double* fout = a.faces + (size_t)e*2*ND*nv*nfq;
         #pragma unroll
         for (int v = 0; v < nv; ++v) {
-          double e0 = 0, e1 = 0;
+          double x[RS];
           #pragma unroll
-          for (int k = 0; k < RS; ++k) {
-            const double x = S[v*nq + q0 + k*stride];
-            e0 += ops.bnd[0][k]*x;
-            e1 += ops.bnd[1][k]*x;
-          }
+          for (int k = 0; k < RS; ++k) x[k] = S[v*nq + q0 + k*stride];
+          double e0, e1;
+          face_extrap_eo<RS>(ops, x, e0, e1);
           fout[((2*d)*nv + v)*nfq + l] = e0;
           fout[((2*d + 1)*nv + v)*nfq + l] = e1;
           if (a.record) bad |= ((isfinite(e0) && isfinite(e1)) ? 0 : 2) | ((v >= ND && !(e0 > 0. && e1 > 0.)) ? 1 : 0);
@@ -521,7 +502,7 @@ static int launch_pipe(hexed_b200_ctx* c, const PipeArgs& a)
 /* returns -1 if this (n_dim, row_size, options) combination is not covered and the caller should use the general kernel */
 int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end)
 {
-  if (c->nd != 3 || (c->rs != 4 && c->rs != 6) || o.use_filter || !c->use_pipe) return -1;
+  if (c->nd != 3 || (c->rs != 4 && c->rs != 6) || o.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
   PipeArgs a;
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
