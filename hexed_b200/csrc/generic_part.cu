@@ -1301,15 +1301,12 @@ ns_local_line2d_kernel(GArgs a, Ops ops)
           #pragma unroll
           for (int k = 0; k < RS; ++k) p[k] = nk[k]*S[v*nq + q0 + k*stride];
           const double b0 = fn0*fldg[((2*d)*nv + v)*nfq + l], b1 = fn1*fldg[((2*d + 1)*nv + v)*nfq + l];
+          double r[RS];
+          line_deriv_eo<RS>(ops, p, b0, b1, r);
           #pragma unroll
           for (int i = 0; i < RS; ++i) {
-            double acc = 0;
-            #pragma unroll
-            for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-            acc += ops.lift[i][0]*b0;
-            acc += ops.lift[i][1]*b1;
             double* g = G + (v*ND + j)*nq + q0 + i*stride;
-            if (d == 0) *g = acc; else *g += acc;
+            if (d == 0) *g = r[i]; else *g += r[i];
           }
         }
       }
@@ -1331,15 +1328,10 @@ ns_local_line2d_kernel(GArgs a, Ops ops)
         #pragma unroll
         for (int k = 0; k < RS; ++k) p[k] = S[v*nq + q0 + k*stride];
         const double b0 = fldg[((2*d)*nv + v)*nfq + l], b1 = fldg[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
+        line_deriv_eo<RS>(ops, p, b0, b1, r);
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*p[k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          G[(v*ND + d)*nq + q0 + i*stride] = acc*inv_nom;
-        }
+        for (int i = 0; i < RS; ++i) G[(v*ND + d)*nq + q0 + i*stride] = r[i]*inv_nom;
       }
     }
     __syncthreads();
@@ -1401,30 +1393,20 @@ ns_local_line2d_kernel(GArgs a, Ops ops)
         #pragma unroll
         for (int k = 0; k < RS; ++k) f[k] = row[k*stride];
         const double b0 = fc[((2*d)*nv + v)*nfq + l], b1 = fc[((2*d + 1)*nv + v)*nfq + l];
+        double r[RS];
+        line_deriv_eo<RS, true>(ops, f, b0, b1, r);
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          row[i*stride] = -acc;
-        }
+        for (int i = 0; i < RS; ++i) row[i*stride] = r[i];
         double* drow = G + (d*nv + v)*nq + q0;
         #pragma unroll
         for (int k = 0; k < RS; ++k) f[k] = drow[k*stride];
-        double x0 = 0, x1 = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) { x0 += ops.bnd[0][k]*f[k]; x1 += ops.bnd[1][k]*f[k]; }
+        double x0, x1;
+        face_extrap_eo<RS>(ops, f, x0, x1);
         fl[(size_t)(2*d)*wl + v*nfq + l] = x0;
         fl[(size_t)(2*d + 1)*wl + v*nfq + l] = x1;
+        line_diff_eo<RS, true>(ops, f, r);
         #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.diff[i][k]*f[k];
-          drow[i*stride] = -acc;
-        }
+        for (int i = 0; i < RS; ++i) drow[i*stride] = r[i];
       }
     }
   }
@@ -1462,7 +1444,7 @@ template <int ND, int RS>
 int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
 {
   if constexpr (ND == 2 && (RS == 4 || RS == 6 || RS == 8)) {
-    if (a.use_filter || !c->use_pipe) return -1;
+    if (a.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
     using C0 = Ns2Cfg<RS, false>;
     const int grid = (a.elem_end - a.elem_begin + C0::B - 1)/C0::B;
     if (deformed) { using C = Ns2Cfg<RS, true>; auto k = ns_local_line2d_kernel<RS, true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }

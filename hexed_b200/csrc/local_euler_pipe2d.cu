@@ -197,15 +197,7 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
       for (int v = 0; v < nv; ++v) {
         const double b0 = Fe[((2*d)*nv + v)*nfq + l], b1 = Fe[((2*d + 1)*nv + v)*nfq + l];
         double r[RS];
-        #pragma unroll
-        for (int i = 0; i < RS; ++i) {
-          double acc = 0;
-          #pragma unroll
-          for (int k = 0; k < RS; ++k) acc += ops.dfull[i][k]*f[v][k];
-          acc += ops.lift[i][0]*b0;
-          acc += ops.lift[i][1]*b1;
-          r[i] = -acc;
-        }
+        line_deriv_eo<RS, true>(ops, f[v], b0, b1, r);
         #pragma unroll
         for (int i = 0; i < RS; i += 2) store_pair(Re + (d*nv + v)*nq, i, r[i], r[i + 1]);
       }
@@ -282,12 +274,8 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
         double x[RS];
         #pragma unroll
         for (int k = 0; k < RS; k += 2) load_pair(Se + v*nq, k, x[k], x[k + 1]);
-        double x0 = 0, x1 = 0;
-        #pragma unroll
-        for (int k = 0; k < RS; ++k) {
-          x0 += ops.bnd[0][k]*x[k];
-          x1 += ops.bnd[1][k]*x[k];
-        }
+        double x0, x1;
+        face_extrap_eo<RS>(ops, x, x0, x1);
         fout[((2*d)*nv + v)*nfq + l] = x0;
         fout[((2*d + 1)*nv + v)*nfq + l] = x1;
         if (a.record) {
@@ -333,7 +321,7 @@ static int launch_pipe2(hexed_b200_ctx* c, const Pipe2Args& a)
  * Bulk copies need 16-byte multiples: row_size^2*8 bytes per field -> even row sizes. */
 int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_options o, int begin, int end)
 {
-  if (c->nd != 2 || (c->rs != 4 && c->rs != 6 && c->rs != 8) || o.use_filter || !c->use_pipe) return -1;
+  if (c->nd != 2 || (c->rs != 4 && c->rs != 6 && c->rs != 8) || o.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
   Pipe2Args a;
   a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
