@@ -64,8 +64,8 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=48, help="box edge of the bounded CPU sample (48^3 = 110 592 elements, 6 GB working set)")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed steps of the CPU sample (10 steps = 20 stages, SURVEY section 8d), after 3 warm-up steps")
     ap.add_argument("--pipe-mode", type=int, default=1, help="HEXED_B200_OPT_PIPELINED_LOCAL value (A/B: 2 = earlier shared-memory layout of the 3-D deformed kernel)")
-    ap.add_argument("--ns-layout", type=int, default=1, help="HEXED_B200_OPT_NS_LOCAL_LAYOUT (A/B: 0 = dense shared-memory layout of the 3-D Navier-Stokes Local kernel)")
-    ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 80, 64 or 48 as host memory allows: "
+    ap.add_argument("--ns-layout", type=int, default=-1, help="HEXED_B200_OPT_NS_LOCAL_LAYOUT (A/B of the 3-D Navier-Stokes Local kernel variants 0 / 1 / 2; -1 = library default)")
+    ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 64, or 48 when host memory is short: "
                     "the reference keeps 85 KB of host objects per deformed element)")
     ap.add_argument("--no-aux-lines", action="store_true", help="skip the Navier-Stokes / Cartesian sub-lines of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -176,7 +176,8 @@ def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_over
     nd, rs = args.dim, 6
     # host memory: the reference keeps ~85 KB of host objects per deformed 3-D element (+ the flat mesh while they are being filled)
     avail = info["mem_available_gb"]/n_dev
-    n_gpu = n_override or args.adapter_n or (80 if avail >= 150. else 64 if avail >= 45. else 48)
+    # the same per-GPU size at every N, so that the driver's weak-scaling ratio compares like with like: 64^3 (262 144 elements, 22 GB of host objects per GPU)
+    n_gpu = n_override or args.adapter_n or (64 if avail >= 40. else 48)
     if nd == 2:
         n_gpu = int(round(n_gpu**1.5))
     n = int(round(n_gpu*n_dev**(1./nd)))
@@ -446,7 +447,7 @@ def main():
     dev = Device(nd, rs, basis, device=local_rank).load_mesh(m, upload_elem_data=False)
     if args.pipe_mode != 1:
         dev.set_option(0, args.pipe_mode)
-    if args.ns_layout != 1:
+    if args.ns_layout >= 0:
         dev.set_option(3, args.ns_layout)
     # the generator's copies of the metric terms are dead once the device mirror holds them: 28 KB per element that a 2 M element
     # mesh (the 16 M / 8 GPU configuration) needs back
@@ -664,9 +665,10 @@ def main():
                            "interior-connection flux; dt D2H per step. The lower bound of what host-applied boundary conditions cost: no host objects to scatter into"}
         aux["e2e_c_abi_from_python"] = e2e_api
 
-    # ---- end to end the way a Hexed user would call it: hexed::max_dt_* / compute_* of the C++ adapter on a pointer-graph Kernel_mesh with
-    # the host boundary-condition loop of Solver::apply_state_bcs; at N > 1 rank 0's process drives all N GPUs through ONE Kernel_mesh
-    # (the split, the NCCL halo exchange and the dt allreduce happen below the kernels.hpp boundary) while the other ranks wait ----
+    # ---- end to end the way a Hexed user would call it: hexed::max_dt_* / compute_* of the C++ adapter on a pointer-graph Kernel_mesh, boundary
+    # conditions registered on the devices (headline) or applied by the host loop of Solver::apply_state_bcs (aux, one GPU); at N > 1 rank 0's
+    # process drives all N GPUs through ONE Kernel_mesh (the split, the NCCL halo exchange and the dt allreduce happen below the kernels.hpp
+    # boundary) while the other ranks wait ----
     e2e = None
     if not args.no_e2e:
         if dist is not None:

@@ -1257,7 +1257,7 @@ int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
     if (c->use_fused_admis != (value != 0)) { c->use_fused_admis = value != 0; invalidate_admis(c); }
     return 0;
   }
-  if (option == HEXED_B200_OPT_NS_LOCAL_LAYOUT) { c->ns_pad = value != 0; return 0; }
+  if (option == HEXED_B200_OPT_NS_LOCAL_LAYOUT) { if (value < 0 || value > 2) return fail(c, HEXED_B200_BAD_ARGUMENT, "layout 0, 1 or 2"); c->ns_layout = value; return 0; }
   return fail(c, HEXED_B200_BAD_ARGUMENT, "unknown option");
 }
 

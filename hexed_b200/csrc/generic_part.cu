@@ -700,11 +700,13 @@ ns_local_line_kernel(GArgs a, Ops ops)
 __constant__ unsigned char c_ns_diag[36] = {0, 29, 35, 8, 4, 15, 11, 17,  23, 34, 12, 18, 14, 25, 26, 22,  28, 1, 7, 3, 24, 20, 21, 27,
                                             33, 6, 2, 13, 9, 10, 31, 32,  19, 30, 5, 16};
 
-template <bool DEF>
+/* PX = 38: the padded layout described above; PX = 36: the dense layout (one bulk copy per array, natural line and point order) with the same
+ * task dealing, 16-byte accesses and early global loads -- kept to measure what the padding itself buys (HEXED_B200_OPT_NS_LOCAL_LAYOUT = 2) */
+template <bool DEF, int PX_ = 38>
 struct NsPadCfg
 {
   static constexpr int RS = 6, ND = 3, nq = 216, nfq = 36, nv = 5, n_line = 108, threads = 128;
-  static constexpr int PX = 38, FP = 6*PX; // plane and field pitch in shared memory
+  static constexpr int PX = PX_, FP = 6*PX; // plane and field pitch in shared memory
   //   state | flux faces | region A = [LDG faces (padded to nv field pitches) | reference normals] | (free) | G ; F aliases region A as in NsCfg
   static constexpr int s_state = 0, s_fc = s_state + nv*FP, s_ldg = s_fc + 2*ND*nv*nfq, s_nrml = s_ldg + nv*FP;
   static constexpr int a_end = s_nrml + (DEF ? ND*ND*FP : 0);
@@ -717,30 +719,36 @@ struct NsPadCfg
 
 /* line task (direction d, line l) of thread slot t for the phases whose tasks are lines of all three directions: warps 0 / 1 / 2 take 32
  * lines of direction 0 / 1 / 2 (warp 2 through c_ns_diag, with 16-byte accesses), warp 3 the left-over four lines of each */
+template <int PX>
+__device__ __forceinline__ int ns_pad_diag(int slot) { if constexpr (PX == 38) return c_ns_diag[slot]; else return slot; }
+
+template <int PX>
 __device__ __forceinline__ bool ns_pad_line(int t, int& d, int& l)
 {
-  if (t < 96) { d = t/32; l = d == 2 ? c_ns_diag[t % 32] : t % 32; return true; }
+  if (t < 96) { d = t/32; l = d == 2 ? ns_pad_diag<PX>(t % 32) : t % 32; return true; }
   if (t < 100) { d = 0; l = 32 + (t - 96); return true; }
-  if (t < 104) { d = 2; l = c_ns_diag[32 + (t - 100)]; return true; }
+  if (t < 104) { d = 2; l = ns_pad_diag<PX>(32 + (t - 100)); return true; }
   if (t >= 112 && t < 116) { d = 1; l = 32 + (t - 112); return true; }
   d = 0; l = 0;
   return false;
 }
 
 /* point of slot s = t + 128*pass (see the header comment); -1: none */
+template <int PX>
 __device__ __forceinline__ int ns_pad_point(int s)
 {
+  if constexpr (PX != 38) return s < 216 ? s : -1;
   const int hw = s/16, lane = s % 16;
   if (hw < 12) return (hw/2)*36 + (hw % 2)*16 + lane;
   if (hw < 14 && lane < 12) return ((hw - 12)*3 + lane/4)*36 + 32 + lane % 4;
   return -1;
 }
 
-template <bool DEF>
+template <bool DEF, int PX_>
 __global__ void __launch_bounds__(128, 3)
 ns_local_pad_kernel(GArgs a, Ops ops)
 {
-  using C = NsPadCfg<DEF>;
+  using C = NsPadCfg<DEF, PX_>;
   using P = PdeNs<3, 6, true>;
   constexpr int RS = 6, ND = 3, nq = C::nq, nfq = C::nfq, nv = C::nv, wl = nv*nfq, T = C::threads, PX = C::PX, FP = C::FP;
   constexpr int cs = nv > RS ? nv : RS;
@@ -761,7 +769,12 @@ ns_local_pad_kernel(GArgs a, Ops ops)
     mbar_arrive_expect_tx(bar, nv*RS*b_plane + 2*b_face + (DEF ? ND*ND*RS*b_plane : 0u));
   }
   __syncthreads();
-  if (t < 32) { // one 288-byte copy per (field, plane) into the padded layout + the two face blocks
+  if constexpr (PX == nfq) { // dense: one copy per array
+    if (t == 0) bulk_g2s(S, a.ed.state + (size_t)e*nv*nq, nv*RS*b_plane, bar);
+    if (t == 1) bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
+    if (t == 2) bulk_g2s(smem + C::s_fc, a.faces + (size_t)e*2*ND*wl, b_face, bar);
+    if constexpr (DEF) { if (t == 3) bulk_g2s(smem + C::s_nrml, a.refn + (size_t)(e - a.n_car)*ND*ND*nq, ND*ND*RS*b_plane, bar); }
+  } else if (t < 32) { // one 288-byte copy per (field, plane) into the padded layout + the two face blocks
     const double* g_state = a.ed.state + (size_t)e*nv*nq;
     for (int c = t; c < nv*RS; c += 32) bulk_g2s(S + (c/RS)*FP + (c % RS)*PX, g_state + (size_t)c*nfq, b_plane, bar);
     if constexpr (DEF) {
@@ -787,7 +800,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   const double nom = a.nom[e];
   const double inv_nom = 1./nom; // reciprocals instead of divisions, see g_local_kernel
   int ld, ll;
-  const bool has_line = ns_pad_line(t, ld, ll);
+  const bool has_line = ns_pad_line<PX>(t, ld, ll);
   const bool vec = t >= 64 && t < 96; // warp 2: contiguous lines, 16-byte accesses
   const int lstride = ld == 0 ? PX : ld == 1 ? RS : 1;
   const int lq0 = ld == 0 ? ll : ld == 1 ? (ll/RS)*PX + ll % RS : (ll/RS)*PX + (ll % RS)*RS;
@@ -800,7 +813,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
     if (active) {
       #pragma unroll
       for (int d = 0; d < ND; ++d) {
-        const int l = d == 2 ? c_ns_diag[slot] : slot;
+        const int l = d == 2 ? ns_pad_diag<PX>(slot) : slot;
         fnv[d][0] = g_fn[((2*d)*ND + j)*nfq + l];
         fnv[d][1] = g_fn[((2*d + 1)*ND + j)*nfq + l];
       }
@@ -814,7 +827,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
     #pragma unroll
     for (int d = 0; d < ND; ++d) {
       if (active) {
-        const int l = d == 2 ? c_ns_diag[slot] : slot;
+        const int l = d == 2 ? ns_pad_diag<PX>(slot) : slot;
         const int stride = d == 0 ? PX : d == 1 ? RS : 1;
         const int q0 = d == 0 ? l : d == 1 ? (l/RS)*PX + l % RS : (l/RS)*PX + (l % RS)*RS;
         double nk[RS]; // the 1/nominal-size factor of the gradient (Spatial.hpp:398) is folded into the normals once per line
@@ -889,7 +902,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   }
   #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int q = ns_pad_point(t + pass*T);
+    const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) {
       pt_av0[pass] = g_av[q]; pt_av1[pass] = g_av[nq + q];
       if constexpr (DEF) pt_det[pass] = g_det[q];
@@ -900,9 +913,9 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   /* ---- P2: pointwise fluxes ---- */
   #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int q = ns_pad_point(t + pass*T);
+    const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) {
-      const int qp = q + 2*(q/nfq);
+      const int qp = q + (PX - nfq)*(q/nfq);
       typename P::template Comp<ND> comp;
       #pragma unroll
       for (int v = 0; v < nv; ++v) comp.state[v] = S[v*FP + qp];
@@ -985,7 +998,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   }
   #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int q = ns_pad_point(t + pass*T);
+    const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) pt_tss[pass] = g_tss[q];
   }
   const double update = (a.dt_dev ? *a.dt_dev*a.update : a.update);
@@ -994,9 +1007,9 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   /* ---- P4: combine and update ---- */
   #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int q = ns_pad_point(t + pass*T);
+    const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) {
-      const int qp = q + 2*(q/nfq);
+      const int qp = q + (PX - nfq)*(q/nfq);
       double mult; // update*tss/nom/det with one division (<= 1 ulp)
       if constexpr (DEF) mult = update*pt_tss[pass]/(nom*pt_det[pass]);
       else mult = update*pt_tss[pass]/nom;
@@ -1454,9 +1467,14 @@ int launch_ns_local_line(hexed_b200_ctx* c, const GArgs& a, int deformed)
     if (a.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
     const int grid = a.elem_end - a.elem_begin;
     if constexpr (RS == 6) {
-      if (c->ns_pad) { // the bank-conflict-free layout (default; HEXED_B200_OPT_NS_LOCAL_LAYOUT = 0 keeps the dense one for A/B)
-        if (deformed) { using C = NsPadCfg<true>; auto k = ns_local_pad_kernel<true>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
-        else { using C = NsPadCfg<false>; auto k = ns_local_pad_kernel<false>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+      if (c->ns_layout == 1) { // the padded, bank-conflict-free layout
+        if (deformed) { using C = NsPadCfg<true, 38>; auto k = ns_local_pad_kernel<true, 38>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+        else { using C = NsPadCfg<false, 38>; auto k = ns_local_pad_kernel<false, 38>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+        return 0;
+      }
+      if (c->ns_layout == 2) { // dense layout, half-warp-aligned tasks, 16-byte accesses on contiguous lines
+        if (deformed) { using C = NsPadCfg<true, 36>; auto k = ns_local_pad_kernel<true, 36>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
+        else { using C = NsPadCfg<false, 36>; auto k = ns_local_pad_kernel<false, 36>; int r = set_smem(c, k, C::smem_bytes); if (r) return r; HB_LAUNCH(k, grid, C::threads, C::smem_bytes, c->stream, a, c->ops); }
         return 0;
       }
     }

@@ -374,8 +374,10 @@ int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
  * are admissible / finite; hexed_b200_is_admissible right after hexed_b200_compute_euler then reduces 4 bytes per element instead of scanning
  * the state (same answer and record; anything else that writes element state or faces in between falls back to the full scan). Default 0. */
 enum { HEXED_B200_OPT_PIPELINED_LOCAL = 0, HEXED_B200_OPT_CFL_CACHE = 1, HEXED_B200_OPT_FUSED_ADMIS = 2,
-       HEXED_B200_OPT_NS_LOCAL_LAYOUT = 3 /* 3-D row-size-6 Navier-Stokes Local: 1 (default) = bank-conflict-free padded shared-memory layout
-                                             (ns_local_pad_kernel), 0 = the dense layout of ns_local_line_kernel; bit-identical results */ };
+       HEXED_B200_OPT_NS_LOCAL_LAYOUT = 3 /* 3-D row-size-6 Navier-Stokes Local, three variants with bit-identical results: 0 = ns_local_line_kernel (dense
+                                             shared-memory fields, one bulk copy per array); 1 = ns_local_pad_kernel<38> (plane pitch 38: bank-conflict-free,
+                                             one bulk copy per field plane); 2 = ns_local_pad_kernel<36> (dense fields with the task dealing, 16-byte accesses
+                                             and early global loads of variant 1). The default is the one measured fastest on B200 */ };
 int hexed_b200_set_option(hexed_b200_ctx* ctx, int option, int value);
 int hexed_b200_kernel_stats(hexed_b200_ctx* ctx, hexed_b200_kernel_stat* out, int capacity, int* n_out);
 int hexed_b200_reset_stats(hexed_b200_ctx* ctx);
