@@ -93,7 +93,7 @@ __device__ __forceinline__ void pipe2_prefetch_late(const Pipe2Args& a, int e0, 
 {
   using C = Pipe2Cfg<RS, DEF>;
   for (int i = t*16; i < n*C::nq; i += n_threads*16) {
-    prefetch_l2(a.tss + (size_t)e0*C::nq + i);
+    if (a.tss) prefetch_l2(a.tss + (size_t)e0*C::nq + i);
     if constexpr (DEF) prefetch_l2(a.det + (size_t)(e0 - a.n_car)*C::nq + i);
   }
   if (a.stage) { // the cache array keeps max(nv, row_size) slots per element; only the first nv are read
@@ -223,7 +223,7 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
         if (pt < n*nq) {
           const int pe = pt/nq, q = pt % nq;
           const int e = e0 + pe;
-          l_tss[k] = a.tss[(size_t)e*nq + q];
+          l_tss[k] = a.tss ? a.tss[(size_t)e*nq + q] : 1.;
           l_nom[k] = a.nom[e];
           if constexpr (DEF) l_det[k] = a.det[(size_t)(e - a.n_car)*nq + q];
           if (a.stage) {
@@ -323,7 +323,7 @@ int launch_local_euler_pipe2d(hexed_b200_ctx* c, int deformed, hexed_b200_option
 {
   if (c->nd != 2 || (c->rs != 4 && c->rs != 6 && c->rs != 8) || o.use_filter || !c->use_pipe || !c->ops_symmetric) return -1;
   Pipe2Args a;
-  a.state = c->state; a.tss = c->tss; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
+  a.state = c->state; a.tss = c->tss_is_one ? nullptr : c->tss /* null: time_step_scale known to hold 1, not read */; a.cache = c->cache; a.nom = c->nom; a.refn = c->refn; a.det = c->det; a.faces = c->face_state;
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.dt_dev = c->dt_dev_active;

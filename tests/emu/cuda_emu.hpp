@@ -191,7 +191,7 @@ namespace hb {
 struct mbar_t { std::atomic<long long> pending{0}; std::atomic<unsigned> phase{0}; };
 inline void mbar_init(mbar_t* bar, unsigned) { bar->pending = 0; bar->phase = 0; }
 inline void mbar_init_fence() {}
-inline void mbar_arrive_expect_tx(mbar_t* bar, unsigned bytes) { bar->pending += (long long)bytes; }
+inline void mbar_arrive_expect_tx(mbar_t* bar, unsigned bytes) { if ((bar->pending += (long long)bytes) == 0) bar->phase++; } // (nothing expected: the arrival alone completes the phase)
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* bar)
 {
   std::memcpy(dst, src, bytes);
