@@ -841,7 +841,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
         #pragma unroll
         for (int k = 0; k < RS; ++k) nk[k] *= inv_nom;
         const double fn0 = fnv[d][0]*inv_nom, fn1 = fnv[d][1]*inv_nom;
-        #pragma unroll
+        #pragma unroll 1 // (code size: the unrolled kernel was 58 KB of SASS and lost 15 % of its issue slots to instruction fetch, profiles/r02k)
         for (int v = 0; v < nv; ++v) {
           double p[RS];
           if (d == 2) {
@@ -874,7 +874,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   } else {
     if (has_line) {
       const int d = ld, l = ll, stride = lstride, q0 = lq0;
-      #pragma unroll
+      #pragma unroll 1
       for (int v = 0; v < nv; ++v) {
         double p[RS];
         if (vec) {
@@ -911,7 +911,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   __syncthreads();
 
   /* ---- P2: pointwise fluxes ---- */
-  #pragma unroll
+  #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) {
@@ -919,10 +919,10 @@ ns_local_pad_kernel(GArgs a, Ops ops)
       typename P::template Comp<ND> comp;
       #pragma unroll
       for (int v = 0; v < nv; ++v) comp.state[v] = S[v*FP + qp];
-      comp.state[nv] = pt_av0[pass];
-      comp.state[nv + 1] = pt_av1[pass];
+      comp.state[nv] = pass ? pt_av0[1] : pt_av0[0];
+      comp.state[nv + 1] = pass ? pt_av1[1] : pt_av1[0];
       if constexpr (DEF) {
-        const double inv_det = 1./pt_det[pass];
+        const double inv_det = 1./(pass ? pt_det[1] : pt_det[0]);
         #pragma unroll
         for (int d = 0; d < ND; ++d)
           #pragma unroll
@@ -954,7 +954,7 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   if (has_line) {
     const int d = ld, l = ll, stride = lstride, q0 = lq0;
     double* fl = a.faces_ldg + (size_t)e*2*ND*wl;
-    #pragma unroll
+    #pragma unroll 1
     for (int v = 0; v < nv; ++v) {
       double* row = F + (d*nv + v)*FP + q0;
       double f[RS], r[RS];
@@ -1005,14 +1005,15 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   __syncthreads();
 
   /* ---- P4: combine and update ---- */
-  #pragma unroll
+  #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     const int q = ns_pad_point<PX>(t + pass*T);
     if (q >= 0) {
       const int qp = q + (PX - nfq)*(q/nfq);
+      const double tss_q = pass ? pt_tss[1] : pt_tss[0];
       double mult; // update*tss/nom/det with one division (<= 1 ulp)
-      if constexpr (DEF) mult = update*pt_tss[pass]/(nom*pt_det[pass]);
-      else mult = update*pt_tss[pass]/nom;
+      if constexpr (DEF) mult = update*tss_q/(nom*(pass ? pt_det[1] : pt_det[0]));
+      else mult = update*tss_q/nom;
       #pragma unroll
       for (int v = 0; v < nv; ++v) {
         double r0 = 0., r1 = 0.;
