@@ -163,7 +163,7 @@ struct hexed_b200_ctx
   bool ops_symmetric = false; // the basis nodes are symmetric about 1/2: the even-odd operator halves (Ops::eo_*) are valid, which the line-task kernels require
   bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
   bool pipe_lean4 = false; // 3-D Cartesian Euler: lean layout with four resident CTAs (option value 3; experiment)
-  int ns_layout = 0; // 3-D row-size-6 Navier-Stokes Local kernel variant, option HEXED_B200_OPT_NS_LOCAL_LAYOUT (include/hexed_b200.h)
+  int ns_layout = 2; // 3-D row-size-6 Navier-Stokes Local kernel variant, option HEXED_B200_OPT_NS_LOCAL_LAYOUT (include/hexed_b200.h)
   bool pipe_lean = true; // 3-D deformed Euler: the 67 KB / three-CTA layout of the pipelined kernel (option value 2 = the classic 105 KB one)
   // CFL screen: single-precision min over the element's points of spacing/char_speed of the state the stage-1 Local kernel has
   // just written (0 = not representable, always re-evaluate); cfl_valid[0|1] = every Cartesian | deformed element's entry belongs
