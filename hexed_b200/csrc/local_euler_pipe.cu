@@ -285,17 +285,11 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
         }
       }
     }
-    __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
-
+    /* (lean) the late inputs of this thread's points are loaded from HBM (L2 hits after the prefetch of a phase ago) BEFORE the barrier that
+     * ends phase A: they depend on nothing phase A computes, and their latency then overlaps the wait for the slowest warp
+     * (profiles/r02n_ncu_full_euler.md: 11 % of all stall samples sat on the first use of these loads at the top of phase B) */
+    [[maybe_unused]] double l_tss[C::n_iter], l_cache[C::n_iter][nv], l_det[C::n_iter];
     if constexpr (LEAN) {
-      // faces / normals buffer is dead: refill it for the next element, and pull that element's late inputs towards L2
-      if (e + stride_e < a.elem_end) {
-        if (t == 0) { fence_proxy_async(); pipe_issue_fn<RS, DEF>(a, e + stride_e, late, &bars[2]); }
-        pipe_prefetch_late<RS, DEF>(a, e + stride_e, t);
-      }
-      /* ---- phase B (lean): the late inputs of this thread's points are loaded from HBM (L2 hits) before its first store ---- */
-      double l_tss[C::n_iter], l_cache[C::n_iter][nv];
-      [[maybe_unused]] double l_det[C::n_iter];
       #pragma unroll
       for (int k = 0; k < C::n_iter; ++k) {
         const int q = t + k*C::threads;
@@ -308,6 +302,16 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
           }
         }
       }
+    }
+    __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
+
+    if constexpr (LEAN) {
+      // faces / normals buffer is dead: refill it for the next element, and pull that element's late inputs towards L2
+      if (e + stride_e < a.elem_end) {
+        if (t == 0) { fence_proxy_async(); pipe_issue_fn<RS, DEF>(a, e + stride_e, late, &bars[2]); }
+        pipe_prefetch_late<RS, DEF>(a, e + stride_e, t);
+      }
+      /* ---- phase B (lean) ---- */
       #pragma unroll
       for (int k = 0; k < C::n_iter; ++k) {
         const int q = t + k*C::threads;

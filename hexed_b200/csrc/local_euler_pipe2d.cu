@@ -202,6 +202,27 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
         for (int i = 0; i < RS; i += 2) store_pair(Re + (d*nv + v)*nq, i, r[i], r[i + 1]);
       }
     }
+    // every late input of this thread's points is loaded before the barrier that ends phase A (nothing phase A computes is needed for them:
+    // their latency overlaps the wait for the slowest warp) and before the thread's first store (a store could alias a later load and would
+    // chain the memory round trips)
+    double l_tss[C::n_iter], l_cache[C::n_iter][nv];
+    [[maybe_unused]] double l_det[C::n_iter];
+    double l_nom[C::n_iter];
+    #pragma unroll
+    for (int k = 0; k < C::n_iter; ++k) {
+      const int pt = t + k*C::threads;
+      if (pt < n*nq) {
+        const int pe = pt/nq, q = pt % nq;
+        const int e = e0 + pe;
+        l_tss[k] = a.tss ? a.tss[(size_t)e*nq + q] : 1.;
+        l_nom[k] = a.nom[e];
+        if constexpr (DEF) l_det[k] = a.det[(size_t)(e - a.n_car)*nq + q];
+        if (a.stage) {
+          #pragma unroll
+          for (int v = 0; v < nv; ++v) l_cache[k][v] = a.cache[((size_t)e*C::cs + v)*nq + q];
+        }
+      }
+    }
     __syncthreads(); // R complete; the faces / normals buffer is dead, the state is still needed
     if (t < 32 && e0 + stride_e < a.elem_end) {
       fence_proxy_async();
@@ -212,26 +233,6 @@ local_euler_pipe2d_kernel(Pipe2Args a, Ops ops)
     /* ---- phase B: combine, two-stage update (reference Spatial.hpp:484-503) ---- */
     {
       const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
-      // every late input of this thread's points is loaded before its first store (a store could alias a later load and would chain
-      // the memory round trips)
-      double l_tss[C::n_iter], l_cache[C::n_iter][nv];
-      [[maybe_unused]] double l_det[C::n_iter];
-      double l_nom[C::n_iter];
-      #pragma unroll
-      for (int k = 0; k < C::n_iter; ++k) {
-        const int pt = t + k*C::threads;
-        if (pt < n*nq) {
-          const int pe = pt/nq, q = pt % nq;
-          const int e = e0 + pe;
-          l_tss[k] = a.tss ? a.tss[(size_t)e*nq + q] : 1.;
-          l_nom[k] = a.nom[e];
-          if constexpr (DEF) l_det[k] = a.det[(size_t)(e - a.n_car)*nq + q];
-          if (a.stage) {
-            #pragma unroll
-            for (int v = 0; v < nv; ++v) l_cache[k][v] = a.cache[((size_t)e*C::cs + v)*nq + q];
-          }
-        }
-      }
       #pragma unroll
       for (int k = 0; k < C::n_iter; ++k) {
         const int pt = t + k*C::threads;

@@ -35,8 +35,11 @@ def oracle(request):
 def emu_lib():
     """host-thread emulation build of the CUDA sources (tests only; see tests/emu/cuda_emu.hpp)"""
     import subprocess
+    import fcntl
     path = os.path.join(ROOT, "tests", "emu", "libhexed_b200_emu.so")
-    subprocess.run(["make", "-C", os.path.join(ROOT, "hexed_b200", "csrc"), "-j8", "emu"], check=True, stdout=subprocess.DEVNULL)
+    with open(os.path.join(ROOT, "tests", "emu", ".build.lock"), "w") as lock:  # pytest-xdist workers must not rebuild it under each other
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hexed_b200", "csrc"), "-j8", "emu"], check=True, stdout=subprocess.DEVNULL)
     return path
 
 

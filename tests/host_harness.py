@@ -25,8 +25,11 @@ FLUX_CB = C.CFUNCTYPE(None)
 
 def build(emu):
     if emu:
-        subprocess.run(["make", "-C", os.path.join(ROOT, "hexed_b200", "csrc"), "-j8", "emu"], check=True, stdout=subprocess.DEVNULL)
-        subprocess.run(["make", "-C", HOST_DIR, "emu"], check=True, stdout=subprocess.DEVNULL)
+        import fcntl
+        with open(os.path.join(ROOT, "tests", "emu", ".build.lock"), "w") as lock:  # (pytest-xdist workers share the build tree)
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            subprocess.run(["make", "-C", os.path.join(ROOT, "hexed_b200", "csrc"), "-j8", "emu"], check=True, stdout=subprocess.DEVNULL)
+            subprocess.run(["make", "-C", HOST_DIR, "emu"], check=True, stdout=subprocess.DEVNULL)
         return EMU_LIB
     if not os.path.exists(GPU_LIB):
         raise RuntimeError("%s not built: run __graft_entry__.build()" % GPU_LIB)
