@@ -601,6 +601,7 @@ def main():
     dev.set_timing(False)
     stats = dev.kernel_stats()
     alg = alg_doubles(nd, rs, deformed)
+    nfq_ = rs**(nd - 1)
     assert nd != 3 or alg == ALG_DOUBLES[args.mesh]
     peak, peak_src = peaks()
     local_stat = max((s for s in stats if s["name"] == "local" and s["deformed"] == int(deformed)), key=lambda s: s["launches"])
@@ -769,10 +770,16 @@ def main():
                          "achieved": local_gbs, "peak": peak, "unit": "GB/s", "frac": local_gbs/peak,
                          "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
                          "frac_traffic": (traffic["bytes"]/local_sec/1e9/peak) if traffic else None,
-                         "algorithmic_bytes_note": "SURVEY 8(d) fixed denominator; for Euler it charges the Local kernel 648 doubles/element of face normals that "
-                                                   "neither the reference's Euler Local nor ours reads, hence frac_traffic (DRAM bytes measured by ncu) < frac",
+                         "algorithmic_bytes_note": "frac uses the fixed SURVEY 8(d) denominator, which charges the Euler Local kernel bytes that are never moved: 648 "
+                                                   "doubles/element of face normals (neither the reference's Euler Local nor ours reads them) and the time-step scale "
+                                                   "(216 doubles/element; not read while it is known to hold 1 after a global-time-step max_dt). So frac can exceed "
+                                                   "1; frac_traffic (DRAM bytes measured by ncu per launch / the same time) is the fraction of the measured HBM "
+                                                   "bandwidth the kernel really sustains",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ne*alg["local"]*8, "avg_launch_ms": local_sec*1e3,
-                         "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/float(nv*nq)},
+                         "whole_stage": {"achieved": stage_gbs, "frac": stage_gbs/peak, "bytes_per_dof_stage": alg["stage"]*8/float(nv*nq),
+                                         "frac_moved": (stage_gbs/peak*(1. - (2*deformed*nd*nd*nfq_ + 1.5*nq)/float(alg["stage"]))) if not viscous else None,
+                                         "frac_moved_note": "the same with the bytes that are not moved taken out of the denominator: face normals in Local, "
+                                                            "the time-step scale read in Local and its write in max_dt"},
                          "kernel_seconds_per_step": shares,
                          "accounting": {"sum_kernels_ms": sum(shares.values())*1e3, "ms_per_step": sec/args.steps*1e3,
                                         "unaccounted_frac": 1. - sum(shares.values())/(sec/args.steps),

@@ -156,6 +156,9 @@ int hexed_b200_face_permutation_indices(int n_dim, int row_size, const int dir[4
 /* void compute_euler(Kernel_mesh, Kernel_options)                                  include/kernels.hpp:22, src/kernels_convective.cpp:18 */
 int hexed_b200_compute_euler(hexed_b200_ctx* ctx, hexed_b200_options opts);
 /* double max_dt_euler(Kernel_mesh, Kernel_options, double, double, bool)           include/kernels.hpp:29, src/kernels_max_dt.cpp:14 */
+/* The five max_dt_* assume an ADMISSIBLE state (positive density and energy, finite), which Solver::update guarantees by calling
+ * is_admissible after every stage: the reduction keeps positive finite local time steps only, so a negative or NaN local value -- which the
+ * reference's std::min would carry through as an obviously wrong dt -- is ignored here. Call hexed_b200_is_admissible first where that matters. */
 int hexed_b200_max_dt_euler(hexed_b200_ctx* ctx, hexed_b200_options opts, double convective_safety, double diffusive_safety, int local_time, double* dt);
 /* void compute_write_face(Kernel_mesh)                                             include/kernels.hpp:40, src/kernels_convective.cpp:43-46 */
 int hexed_b200_compute_write_face(hexed_b200_ctx* ctx);
@@ -229,7 +232,12 @@ int hexed_b200_apply_flux_bcs(hexed_b200_ctx* ctx);
  * step); with use_graph one Chebyshev cycle is captured in a CUDA graph and replayed. Bit-identical to the same calls made one by one.
  * Returns the last time step and the flow time advanced. For launch-bound (small) meshes.
  * update_euler: both stages compute_euler. update_navier_stokes (use_ldg(), :857-865): stage 0 compute_navier_stokes with the flux
- * boundary conditions on the device, stage 1 compute_euler. ---- */
+ * boundary conditions on the device, stage 1 compute_euler.
+ * PRECONDITIONS (what the loop of the reference does and these two do not; a caller that needs one of them uses the call-by-call entry points):
+ *   - no `min(nominal_dt, max_time_step)` clamp (:851): `max_time_step` must not bind;
+ *   - no `fix_admissibility` after each stage and therefore no early exit from the Chebyshev cycle (:866-868): check
+ *     hexed_b200_is_admissible after the call (free with HEXED_B200_OPT_FUSED_ADMIS) and repair / redo on the host side if it fails;
+ *   - global time stepping (`local_time` false) and `use_filter` 0. ---- */
 int hexed_b200_update_euler(hexed_b200_ctx* ctx, double safety, int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced);
 int hexed_b200_update_navier_stokes(hexed_b200_ctx* ctx, double safety, hexed_b200_transport visc, hexed_b200_transport therm_cond,
                                     int n_cheby, int n_steps, int use_graph, double* last_dt, double* time_advanced);
