@@ -597,3 +597,30 @@ def test_fix_therm_admis_is_conservative_and_smoothing(oracle, nd, rs, deformed)
     assert rel_l2(m.state(), start) > 1e-4
     assert np.all(np.abs(integral() - before) <= 1e-12*np.abs(before))
     assert np.all(m.state().var(axis=(0, 2)) < var_before)
+
+
+def test_reference_kernel_vectors(oracle):
+    """tests/golden/ref_kernel_vectors.npz holds what the REFERENCE'S OWN compiled kernels (oracle/_ref, built by oracle/Makefile.ref from the
+    sources under /root/reference) leave behind after the call sequences Solver makes for each of the five PDEs on small structurally complete
+    meshes (generator: tests/golden/gen_ref_kernel_vectors.py). The restated oracle must reproduce them to 1e-13 (FMA contraction and
+    summation order are the only differences), dt to 1e-14 -- on any machine, with or without the reference tree."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import gen_ref_kernel_vectors as G
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kernel_vectors.npz"))
+    assert [tuple(r) for r in gold["cases"]] == list(G.CASES)
+    for i, (pde, nd, rs, seed) in enumerate(G.CASES):
+        m, dts = G.run(oracle, pde, nd, rs, seed)
+        for got, want in zip(dts, gold["dt_%d" % i]):
+            assert abs(got - want) <= 1e-14*abs(want), (i, got, want)
+        for name, got in (("elem", m.elem_data), ("face_state", m.face_state), ("face_ldg", m.face_ldg), ("face_wide", m.face_wide)):
+            want = gold["%s_%d" % (name, i)]
+            assert got.shape == want.shape
+            for j in range(got.shape[1] if name == "elem" else 1):   # slot by slot for the element data: small slots must not hide behind large ones
+                x, y = (got[:, j], want[:, j]) if name == "elem" else (got, want)
+                ny = np.linalg.norm(y)
+                if ny == 0:
+                    assert np.array_equal(x, y), (i, name, j)
+                else:
+                    assert np.linalg.norm(x - y) <= 2e-13*ny, (i, name, j, np.linalg.norm(x - y)/ny)
