@@ -321,10 +321,15 @@ def build_native_oracle():
 
 
 def cpu_reference_rate(args, steps, warmup, n=None):
-    """The reference's OWN CPU kernels (oracle/_ref/libhexed_ref.so: src/kernels_convective.cpp, kernels_max_dt.cpp + include/Spatial.hpp
-    compiled unmodified, oracle/Makefile.ref; built where /root/reference exists and shipped with the snapshot) on a Kernel_mesh stood up once
-    over the same flat mesh, all host threads (OpenMP, as the reference's `threaded` build): kind "reference". Without that library the restated
-    oracle (kind "port"). Returns (rate, seconds per step, threads, kind, sample description)."""
+    """The CPU arm: two implementations of the same path are available on the host and the FASTER one is what gets timed for `steps` steps
+    after `warmup` (both are probed for two steps first; `cpu_reference_rate.both` keeps the two probe rates):
+      "reference"  the reference's OWN kernels (oracle/_ref/libhexed_ref.so: src/kernels_convective.cpp, kernels_max_dt.cpp + include/Spatial.hpp
+                   compiled unmodified, oracle/Makefile.ref; built where /root/reference exists and shipped with the snapshot) on a Kernel_mesh stood up
+                   once over the flat mesh. It compiles here only against oracle/eigen_shim (eager evaluation, no expression templates), which costs
+                   it speed a genuine-Eigen build would not pay;
+      "port"       the restated kernels (oracle/oracle_impl.hpp, plain loops, rebuilt -march=native for this host).
+    So the GPU number is never compared with a handicapped CPU one. All host threads (OpenMP, as the reference's `threaded` build).
+    Returns (rate, seconds per step, threads, kind, sample description)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core (libgomp reads this at load time)
     os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
@@ -342,74 +347,58 @@ def cpu_reference_rate(args, steps, warmup, n=None):
     fs = freestream_state(nd)
     m = M.box_mesh(nd, 6, n, basis, deformed=args.mesh == "deformed", bc_kind=M.BC_FREESTREAM, bc_params=fs)
     density_wave(m, basis)
-    use_ref = pyoracle.ref_available()
-    if use_ref:
+    plib = build_native_oracle()
+    po = Oracle(plib)
+    po.compute_write_face(basis, m)
+    impls = {}
+
+    def port_step():
+        dt = po.max_dt(EULER, basis, m, 0.7, 0.7, False)
+        for stage in (0, 1):
+            po.apply_state_bcs(m)
+            po.compute_euler(basis, m, dt=dt, i_stage=stage)
+    impls["port"] = (port_step, "oracle/%s (restated kernels, -march=native)" % plib)
+    view = None
+    if pyoracle.ref_available():
         o = pyoracle.RefOracle()
-        o.compute_write_face(basis, m)
         packed = o.pack_mesh(m)
         view = o.ref.hr_view_create(C.byref(packed))
-        if not view:
-            raise RuntimeError("hr_view_create failed")
-        ghost = np.ascontiguousarray(m.bcs[0]["ghost_slot"], dtype=np.int32)
-        fs_a = np.ascontiguousarray(fs, dtype=np.float64)
-        gp, fp = ghost.ctypes.data_as(C.POINTER(C.c_int)), fs_a.ctypes.data_as(C.POINTER(C.c_double))
-        dt = C.c_double()
+        if view:
+            ghost = np.ascontiguousarray(m.bcs[0]["ghost_slot"], dtype=np.int32)
+            fs_a = np.ascontiguousarray(fs, dtype=np.float64)
+            gp, fp = ghost.ctypes.data_as(C.POINTER(C.c_int)), fs_a.ctypes.data_as(C.POINTER(C.c_double))
+            dt_c = C.c_double()
 
-        def step():
-            o._check(o.ref.hr_view_max_dt_euler(view, 0.7, 0.7, 0, C.byref(dt)))
-            for stage in (0, 1):
-                o.ref.hr_view_bc_freestream(view, ghost.size, gp, fp)
-                o._check(o.ref.hr_view_compute_euler(view, o.opts(dt=dt.value, i_stage=stage)))
-        lib, kind = "oracle/_ref/libhexed_ref.so (the reference's own kernels, -O3 -march=x86-64-v3)", "reference"
-    else:
-        lib = build_native_oracle()
-        o = Oracle(lib)
-        o.compute_write_face(basis, m)
-        kind = "port"
-
-        def step():
-            dt = o.max_dt(EULER, basis, m, 0.7, 0.7, False)
-            for stage in (0, 1):
-                o.apply_state_bcs(m)
-                o.compute_euler(basis, m, dt=dt, i_stage=stage)
-    for _ in range(warmup):
-        step()
-    t = time.perf_counter()
-    for _ in range(steps):
-        step()
-    el = time.perf_counter() - t
-    rate = m.n_elem*m.nv*m.nq*2*steps/el
-    other = None
-    if use_ref:
-        o.ref.hr_view_destroy(view)
-        # The reference compiles here only against oracle/eigen_shim (eager evaluation, no expression templates), which costs it speed a
-        # genuine-Eigen build would not pay. So the restated kernels (oracle_impl.hpp, plain loops, -march=native) are timed on the same mesh
-        # as well and the FASTER of the two is reported as the CPU baseline: the GPU number is never compared with a handicapped CPU one.
-        try:
-            plib = build_native_oracle()
-            po = Oracle(plib)
-            k_steps = max(2, min(steps, 5))
-
-            def pstep():
-                dt = po.max_dt(EULER, basis, m, 0.7, 0.7, False)
+            def ref_step():
+                o._check(o.ref.hr_view_max_dt_euler(view, 0.7, 0.7, 0, C.byref(dt_c)))
                 for stage in (0, 1):
-                    po.apply_state_bcs(m)
-                    po.compute_euler(basis, m, dt=dt, i_stage=stage)
-            pstep()
-            t = time.perf_counter()
-            for _ in range(k_steps):
-                pstep()
-            pel = (time.perf_counter() - t)/k_steps
-            prate = m.n_elem*m.nv*m.nq*2/pel
-            other = {"reference_kernels_on_eigen_shim": rate, "restated_port_" + plib: prate}
-            if prate > rate:
-                rate, el, steps, kind, lib = prate, pel*k_steps, k_steps, "port", ("oracle/%s (restated kernels, -march=native; faster here than the reference's own "
-                                                                                  "sources on the Eigen stand-in: %.3g against %.3g DOF-stage/s)" % (plib, prate, other["reference_kernels_on_eigen_shim"]))
-        except Exception:
-            pass
-    desc = "%d^%d = %d %s elements, %d steps (max_dt + 2 x (freestream ghost fill + compute_euler)), %s, OpenMP" % (n, nd, m.n_elem, args.mesh, steps, lib)
-    cpu_reference_rate.both = other
-    return rate, el/steps, o.num_threads(), kind, desc
+                    o.ref.hr_view_bc_freestream(view, ghost.size, gp, fp)
+                    o._check(o.ref.hr_view_compute_euler(view, o.opts(dt=dt_c.value, i_stage=stage)))
+            impls["reference"] = (ref_step, "oracle/_ref/libhexed_ref.so (the reference's own kernel sources on the Eigen stand-in, -O3 -march=x86-64-v3)")
+
+    def rate_of(fn, k):
+        t = time.perf_counter()
+        for _ in range(k):
+            fn()
+        el = time.perf_counter() - t
+        return m.n_elem*m.nv*m.nq*2*k/el, el
+    probe = {}
+    for kind, (fn, _) in impls.items():
+        fn()
+        probe[kind] = rate_of(fn, 2)[0]
+    kind = max(probe, key=probe.get)
+    if view and kind != "reference":
+        o.ref.hr_view_destroy(view); view = None   # 26 GB of reference-layout face storage at 1 M elements
+    fn, lib = impls[kind]
+    for _ in range(warmup):
+        fn()
+    rate, el = rate_of(fn, steps)
+    if view:
+        o.ref.hr_view_destroy(view)
+    cpu_reference_rate.both = {"probe_steps": 2, "reference_kernels_on_eigen_shim": probe.get("reference"), "restated_port": probe.get("port")}
+    desc = "%d^%d = %d %s elements, %d steps (max_dt + 2 x (freestream ghost fill + compute_euler)), %s, OpenMP; the faster of the two CPU implementations (%s)" % (
+        n, nd, m.n_elem, args.mesh, steps, lib, ", ".join("%s %.3g" % kv for kv in probe.items()))
+    return rate, el/steps, po.num_threads(), kind, desc
 
 
 def run_reference(args):
