@@ -46,7 +46,7 @@ struct PipeCfg
   static constexpr int r_doubles = ND*nv*nq;
   static constexpr int n_iter = (nq + threads - 1)/threads; // point tasks per thread
   static constexpr int smem_doubles = 2*stage_doubles + late_doubles + r_doubles;
-  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 8*sizeof(double); // + mbarriers + CFL screen scratch (4 per-warp minima, 8 vertex spacings, floats)
+  static constexpr size_t smem_bytes = sizeof(double)*smem_doubles + 4*sizeof(mbar_t) + 9*sizeof(double); // + mbarriers + CFL screen scratch (4 per-warp minima, 8 vertex spacings, floats) + the element's nominal size
 };
 
 struct PipeArgs
@@ -135,6 +135,7 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
   double* R = late + C::late_doubles;
   mbar_t* bars = reinterpret_cast<mbar_t*>(R + C::r_doubles); // [0],[1]: stage buffers; [2]: late inputs
   [[maybe_unused]] float* warp_cfl = reinterpret_cast<float*>(bars + 4); // per-warp minima of the single-precision CFL screen
+  double* s_nom = reinterpret_cast<double*>(bars + 4) + 8;                // the element's nominal size, broadcast by thread 0
   const int t = threadIdx.x;
   const int stride_e = gridDim.x;
   int e = a.elem_begin + blockIdx.x;
@@ -166,12 +167,14 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
   const int stride = d == 0 ? RS*RS : d == 1 ? RS : 1;
   const int q0 = d == 0 ? l : d == 1 ? (l/RS)*RS*RS + l % RS : l*RS;
 
-  // the time step (when it lives on the device) is the same for every element; the nominal size of an element is fetched at the top of its
-  // iteration so that the HBM latency hides behind phase A (profiles/r02k_ncu_full_euler_car.md: 12 % of all stall samples sat on the
-  // reciprocal that consumed it in phase B)
+  // the time step (when it lives on the device) is the same for every element. The nominal size of an element is fetched by thread 0 at the top
+  // of its iteration and handed to the others through shared memory just before the barrier that ends phase A, so that the HBM latency hides
+  // behind phase A: read where it is used it cost 12 % of all stall samples (profiles/r02k_ncu_full_euler_car.md: the reciprocal in phase B), and
+  // read by every thread at the top the compiler moved it to a uniform register at once, with the same wait (profiles/r02t_ncu_full_euler_car.md)
   const double update = a.dt_dev ? *a.dt_dev*a.update : a.update;
   for (int it = 0; e < a.elem_end; ++it, e += stride_e) {
-    const double nom = a.nom[e];
+    double nom_t0 = 0.;
+    if (t == 0) nom_t0 = a.nom[e];
     const int s = it & 1;
     const unsigned par = (it >> 1) & 1;
     double* const stage_buf = smem + s*C::stage_doubles;
@@ -303,7 +306,9 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
         }
       }
     }
+    if (t == 0) *s_nom = nom_t0;
     __syncthreads(); // R complete; faces / normals of this stage buffer are dead, the state is still needed
+    const double nom = *s_nom;
 
     if constexpr (LEAN) {
       // faces / normals buffer is dead: refill it for the next element, and pull that element's late inputs towards L2

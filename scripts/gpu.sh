@@ -37,7 +37,7 @@ for step in "$@"; do
            else run bench_default_$TAG timeout 900 python bench.py; fi ;;
     launches) run ncu_launch_$TAG timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KN" -s 20 -c 60 --csv \
                 --log-file gpurun_out/launches_$TAG.csv python bench.py --n 64 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e $a1s ;;
-    full) name=$(echo "$a1" | tr -c 'a-zA-Z0-9\n' '_'); run ncu_full_${name}_$TAG timeout 900 ncu --set full --clock-control none --import-source on \
+    full) name=$(echo "$a1$a2" | tr -c 'a-zA-Z0-9\n' '_'); run ncu_full_${name}_$TAG timeout 900 ncu --set full --clock-control none --import-source on \
                 -k "regex:$a1" -s 4 -c 2 -f -o gpurun_out/prof_${name}_$TAG python bench.py --n 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e $a2s ;;
     multi_check) port=$((port+1)); run multigpu_check_${N}_$(echo "$a1" | tr -c 'a-zA-Z0-9\n' '_')_$TAG timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
                 --master-addr 127.0.0.1 --master-port $port scripts/multigpu_check.py $a1s ;;
