@@ -24,6 +24,9 @@ __device__ __forceinline__ void mbar_init(mbar_t* bar, unsigned count)
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(mbar_t* bar, unsigned bytes)
 { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+/* plain arrival (release semantics at CTA scope): the consumer side of a producer / consumer hand-over, no transaction bytes */
+__device__ __forceinline__ void mbar_arrive(mbar_t* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, mbar_t* bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -55,6 +55,7 @@ struct PipeArgs
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
   const double* dt_dev; // non-null: the time step lives on the device and multiplies `update`
+  int end_barrier; // A/B switch (HEXED_B200_OPT_PIPELINED_LOCAL value 4): end every iteration with a CTA barrier instead of the mbarrier hand-over
   int* record; // non-null: leave Element::record-style admissibility bits of the NEW state and faces per element (bit 0 inadmissible, bit 1 non-finite)
   const double* vtss; float nodef[MAX_RS]; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
@@ -143,6 +144,7 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
 
   if (t == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], C::threads); // "stage buffer consumed": every thread arrives after phase C, only the refilling thread waits
     mbar_init_fence();
   }
   __syncthreads();
@@ -467,7 +469,15 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
     if (a.record) { // uniform across the CTA; the two votes also are the barrier that frees stage buffer s
       const int inadmissible = __syncthreads_or(bad & 1), nonfinite = __syncthreads_or(bad & 2);
       if (t == 0) a.record[e] = (inadmissible ? 1 : 0) | (nonfinite ? 2 : 0);
-    } else __syncthreads(); // stage buffer s free
+    } else if (a.end_barrier) __syncthreads();
+    else {
+      // Stage buffer s is handed back without stopping the CTA: every thread arrives on the "consumed" mbarrier when its phase C is done
+      // and goes straight on to the next element (whose inputs sit in the other stage buffer; R, the late buffer and the scalars are
+      // protected by the barriers after phases A and B); only the thread that refills the buffer waits for all arrivals.
+      // (10 % of the kernel's stall samples were barrier waits, a third of them here: profiles/r02t_ncu_full_euler_car.md)
+      mbar_arrive(&bars[3]);
+      if (t == 0 && e + 2*stride_e < a.elem_end) mbar_wait(&bars[3], it & 1);
+    }
     if (t == 0 && e + 2*stride_e < a.elem_end) {
       fence_proxy_async();
       if constexpr (LEAN) pipe_issue_state<RS, DEF>(a, e + 2*stride_e, stage_buf, &bars[s]);
@@ -521,6 +531,7 @@ int launch_local_euler_pipe(hexed_b200_ctx* c, int deformed, hexed_b200_options 
   a.elem_begin = begin; a.elem_end = end; a.n_car = c->n_car;
   a.update = o.i_stage ? o.dt*(.5/c->quad_safety) : o.dt;
   a.dt_dev = c->dt_dev_active;
+  a.end_barrier = c->pipe_end_barrier;
   a.stage = o.i_stage != 0; a.compute_residual = o.compute_residual;
   a.vtss = c->vtss; a.cfl_approx = nullptr;
   a.record = nullptr;

@@ -188,8 +188,10 @@ template <class F> cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int
 
 /* emulated mbarrier + bulk copy: the copy is done synchronously by the issuing thread; waiters spin on the phase counter */
 namespace hb {
-struct mbar_t { std::atomic<long long> pending{0}; std::atomic<unsigned> phase{0}; };
-inline void mbar_init(mbar_t* bar, unsigned) { bar->pending = 0; bar->phase = 0; }
+struct mbar_t { std::atomic<long long> pending{0}; std::atomic<unsigned> phase{0}; std::atomic<unsigned> arrived{0}; unsigned count = 1; };
+inline void mbar_init(mbar_t* bar, unsigned count) { bar->pending = 0; bar->phase = 0; bar->arrived = 0; bar->count = count; }
+/* plain arrivals (no transaction bytes): the phase completes when `count` threads have arrived */
+inline void mbar_arrive(mbar_t* bar) { if (++bar->arrived == bar->count) { bar->arrived = 0; bar->phase++; } }
 inline void mbar_init_fence() {}
 inline void mbar_arrive_expect_tx(mbar_t* bar, unsigned bytes) { if ((bar->pending += (long long)bytes) == 0) bar->phase++; } // (nothing expected: the arrival alone completes the phase)
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* bar)
