@@ -1251,7 +1251,7 @@ int hexed_b200_set_timing(hexed_b200_ctx* c, int enabled) { c->timing = enabled 
 int hexed_b200_set_option(hexed_b200_ctx* c, int option, int value)
 {
   HB_ENTER(c);
-  if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; c->pipe_lean = value != 2; c->pipe_lean4 = value == 3; c->pipe_end_barrier = value == 4; return 0; }
+  if (option == HEXED_B200_OPT_PIPELINED_LOCAL) { c->use_pipe = value != 0; c->pipe_lean = value != 2; c->pipe_lean4 = value == 3; c->pipe_end_barrier = value != 4; return 0; }
   if (option == HEXED_B200_OPT_CFL_CACHE) { c->use_cfl_cache = value != 0; invalidate_cfl_cache(c); return 0; }
   if (option == HEXED_B200_OPT_FUSED_ADMIS) { // a change of the setting forgets the bits; setting it again does not
     if (c->use_fused_admis != (value != 0)) { c->use_fused_admis = value != 0; invalidate_admis(c); }

@@ -164,7 +164,7 @@ struct hexed_b200_ctx
   bool use_pipe = true; // TMA-pipelined Local kernel where it applies (hexed_b200_set_option)
   bool pipe_lean4 = false; // 3-D Cartesian Euler: lean layout with four resident CTAs (option value 3; experiment)
   int ns_layout = 2; // 3-D row-size-6 Navier-Stokes Local kernel variant, option HEXED_B200_OPT_NS_LOCAL_LAYOUT (include/hexed_b200.h)
-  bool pipe_end_barrier = false; // 3-D Euler pipelined kernels: CTA barrier at the end of an iteration instead of the mbarrier hand-over (option value 4; A/B)
+  bool pipe_end_barrier = true; // 3-D Euler pipelined kernels: CTA barrier at the end of an iteration; false (option value 4) = mbarrier hand-over of the stage buffer, measured equal
   bool pipe_lean = true; // 3-D deformed Euler: the 67 KB / three-CTA layout of the pipelined kernel (option value 2 = the classic 105 KB one)
   // CFL screen: single-precision min over the element's points of spacing/char_speed of the state the stage-1 Local kernel has
   // just written (0 = not representable, always re-evaluate); cfl_valid[0|1] = every Cartesian | deformed element's entry belongs

@@ -55,7 +55,7 @@ struct PipeArgs
   int elem_begin, elem_end, n_car;
   double update; int stage; int compute_residual;
   const double* dt_dev; // non-null: the time step lives on the device and multiplies `update`
-  int end_barrier; // A/B switch (HEXED_B200_OPT_PIPELINED_LOCAL value 4): end every iteration with a CTA barrier instead of the mbarrier hand-over
+  int end_barrier; // 1 (default): end every iteration with a CTA barrier; 0 (HEXED_B200_OPT_PIPELINED_LOCAL value 4): mbarrier hand-over of the stage buffer
   int* record; // non-null: leave Element::record-style admissibility bits of the NEW state and faces per element (bit 0 inadmissible, bit 1 non-finite)
   const double* vtss; float nodef[MAX_RS]; float* cfl_approx; // CFL instantiation: single-precision min_q spacing/char_speed of the NEW state per element
 };
@@ -474,7 +474,8 @@ __device__ __forceinline__ void pipe_body(const PipeArgs& a, const Ops& ops)
       // Stage buffer s is handed back without stopping the CTA: every thread arrives on the "consumed" mbarrier when its phase C is done
       // and goes straight on to the next element (whose inputs sit in the other stage buffer; R, the late buffer and the scalars are
       // protected by the barriers after phases A and B); only the thread that refills the buffer waits for all arrivals.
-      // (10 % of the kernel's stall samples were barrier waits, a third of them here: profiles/r02t_ncu_full_euler_car.md)
+      // (10 % of the kernel's stall samples were barrier waits, a third of them here, profiles/r02t_ncu_full_euler_car.md -- and yet the step
+      // time did not move: 25.91 against 25.96 ms Cartesian, 30.50 against 30.57 ms deformed on one box, visit r02v. Kept as an option.)
       mbar_arrive(&bars[3]);
       if (t == 0 && e + 2*stride_e < a.elem_end) mbar_wait(&bars[3], it & 1);
     }

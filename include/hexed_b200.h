@@ -374,8 +374,8 @@ int hexed_b200_set_timing(hexed_b200_ctx* ctx, int enabled);
 /* implementation switches (for A/B measurements and tests): HEXED_B200_OPT_PIPELINED_LOCAL = use the persistent TMA-pipelined
  * Local kernel where it applies (3-D row size 4 or 6, 2-D row size 4, 6 or 8, no modal filter); default 1. Value 2 = pipelined, but the
  * 3-D deformed kernel keeps its earlier shared-memory layout (everything staged, two resident CTAs per SM) instead of the lean one; 3 = additionally the lean layout with four
- * resident CTAs for 3-D Cartesian elements (measured slower on B200); 4 = the default kernels, but with a CTA barrier at the end of
- * every element instead of the mbarrier hand-over of the stage buffer (A/B)
+ * resident CTAs for 3-D Cartesian elements (measured slower on B200); 4 = the default kernels, but the stage buffer of an
+ * element is handed back through an mbarrier (every thread arrives, only the refilling thread waits) instead of a CTA barrier (measured equal)
  * HEXED_B200_OPT_CFL_CACHE = the stage-1 Local kernel leaves min(spacing/char_speed) per element behind and the next global-time-step
  * max_dt_euler re-evaluates only the near-minimum elements instead of re-reading the whole state (any other write to the state
  * invalidates the screen); default 0 -- on B200 the extra work in the Local kernel costs what the saved pass over the state gains
