@@ -382,7 +382,7 @@ def test_fused_admissibility(oracle, gpu_lib, nd, rs, n):
     check_fused_admissibility(oracle, gpu_lib, nd, rs, n)
 
 
-@pytest.mark.parametrize("mode,deformed", [(0, True), (2, True), (3, False)])
+@pytest.mark.parametrize("mode,deformed", [(0, True), (2, True), (3, False), (4, True), (4, False)])
 @pytest.mark.parametrize("rs,n", [(6, 7), (4, 9)])
 def test_box_3d_other_local_kernels(oracle, gpu_lib, rs, n, mode, deformed):
     """HEXED_B200_OPT_PIPELINED_LOCAL = 0 (the general Local kernel) and 2 (the pipelined kernel with its earlier, fully staged
