@@ -16,6 +16,7 @@
 #include <map>
 #include <string>
 #include <memory>
+#include <thread>
 #include <unordered_map>
 
 #ifdef HEXED_B200_WITH_HEXED_HEADERS
@@ -151,6 +152,14 @@ struct Mirror
 };
 
 Sync_mode g_mode = sync_every_call;
+int g_host_threads = 0; // 0: every hardware thread (NOT omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1, and a Hexed
+                        // process that drives several GPUs wants its copy loops on all cores)
+int host_threads()
+{
+  if (g_host_threads > 0) return g_host_threads;
+  static const int hw = std::max(1u, std::thread::hardware_concurrency());
+  return hw;
+}
 std::vector<int> g_devices {0};
 //! keyed by the identity of the mesh (the address of its `elems` view, which belongs to one Solver / Accessible_mesh) and its shape
 std::map<std::tuple<const void*, int, int>, std::unique_ptr<Mirror>> g_mirrors;
@@ -325,12 +334,12 @@ void move_elements(Mirror& m, Rank& k, unsigned groups, bool up)
     for (int first = 0; first < ne; first += chunk) {
       const int n = std::min(chunk, ne - first);
       if (up) {
-        #pragma omp parallel for
+        #pragma omp parallel for num_threads(host_threads())
         for (int i = 0; i < n; ++i) std::memcpy(k.staging.data() + per_elem*i, k.elem[first + i]->state() + size_t(range.first)*nq, per_elem*sizeof(double));
         check(&m, hexed_b200_upload_elem_slots(k.ctx, k.staging.data(), per_elem, range.first, range.n, first, n), k.ctx);
       } else {
         check(&m, hexed_b200_download_elem_slots(k.ctx, k.staging.data(), per_elem, range.first, range.n, first, n), k.ctx);
-        #pragma omp parallel for
+        #pragma omp parallel for num_threads(host_threads())
         for (int i = 0; i < n; ++i) std::memcpy(k.elem[first + i]->state() + size_t(range.first)*nq, k.staging.data() + per_elem*i, per_elem*sizeof(double));
       }
     }
@@ -347,7 +356,7 @@ void move_face_array(Mirror& m, Rank& k, int which, size_t width, size_t offset,
   for (int first = 0; first < ns; first += chunk) {
     const int n = std::min(chunk, ns - first);
     if (up) {
-      #pragma omp parallel for
+      #pragma omp parallel for num_threads(host_threads())
       for (int i = 0; i < n; ++i) {
         double* p = k.face_ptr[first + i];
         if (p) std::memcpy(k.staging.data() + width*i, p + offset, width*sizeof(double));
@@ -356,7 +365,7 @@ void move_face_array(Mirror& m, Rank& k, int which, size_t width, size_t offset,
       check(&m, hexed_b200_upload(k.ctx, which, k.staging.data(), first, n), k.ctx);
     } else {
       check(&m, hexed_b200_download(k.ctx, which, k.staging.data(), first, n), k.ctx);
-      #pragma omp parallel for
+      #pragma omp parallel for num_threads(host_threads())
       for (int i = 0; i < n; ++i) {
         double* p = k.face_ptr[first + i];
         if (p && k.face_owned[first + i]) std::memcpy(p + offset, k.staging.data() + width*i, width*sizeof(double));
@@ -395,10 +404,10 @@ void upload_geometry(Mirror& m, Rank& k)
   for (int first = 0; first < n_def; first += chunk) {
     const int n = std::min(chunk, n_def - first);
     buf.resize(size_t(n)*nd*nd*nq);
-    #pragma omp parallel for
+    #pragma omp parallel for num_threads(host_threads())
     for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nd*nd*nq, k.elem[n_car + first + i]->reference_level_normals(), sizeof(double)*nd*nd*nq);
     check(&m, hexed_b200_upload(k.ctx, HEXED_B200_REF_NORMALS, buf.data(), first, n), k.ctx);
-    #pragma omp parallel for
+    #pragma omp parallel for num_threads(host_threads())
     for (int i = 0; i < n; ++i) std::memcpy(buf.data() + size_t(i)*nq, k.elem[n_car + first + i]->jacobian_determinant(), sizeof(double)*nq);
     check(&m, hexed_b200_upload(k.ctx, HEXED_B200_JAC_DET, buf.data(), first, n), k.ctx);
   }
@@ -451,7 +460,7 @@ void move_boundary(Mirror& m, bool up, unsigned sides = both_sides, unsigned hal
         double* buf;
         if (fast) check(&m, hexed_b200_face_list_staging(k.ctx, k.side_list[side], &buf), k.ctx);
         else {k.staging.resize(width*n); buf = k.staging.data();}
-        #pragma omp parallel for
+        #pragma omp parallel for num_threads(host_threads())
         for (size_t i = 0; i < n; ++i) std::memcpy(buf + width*i, k.face_ptr[slots[i]] + half*width, width*sizeof(double));
         if (fast) check(&m, hexed_b200_face_list_upload_deferred(k.ctx, k.side_list[side], half), k.ctx);
         else check(&m, hexed_b200_face_list_upload(k.ctx, k.side_list[side], half, buf), k.ctx);
@@ -466,7 +475,7 @@ void move_boundary(Mirror& m, bool up, unsigned sides = both_sides, unsigned hal
           check(&m, hexed_b200_face_list_download(k.ctx, k.side_list[side], half, k.staging.data()), k.ctx);
           buf = k.staging.data();
         }
-        #pragma omp parallel for
+        #pragma omp parallel for num_threads(host_threads())
         for (size_t i = 0; i < n; ++i) std::memcpy(k.face_ptr[slots[i]] + half*width, buf + width*i, width*sizeof(double));
       }
     }
@@ -759,6 +768,7 @@ class Face_permutation_host : public hexed::Face_permutation_dynamic
 } // namespace
 
 void set_sync_mode(Sync_mode mode) {g_mode = mode;}
+void set_host_threads(int n) {g_host_threads = n;}
 Sync_mode sync_mode() {return g_mode;}
 void set_device(int d) {set_devices({d});}
 void set_devices(const std::vector<int>& devices)

@@ -88,6 +88,8 @@ enum Face_half : unsigned {state_half = 1, ldg_half = 2, both_halves = 3};
 void boundary_faces_to_host(hexed::Kernel_mesh, unsigned sides, unsigned halves);
 void ghost_faces_to_device(hexed::Kernel_mesh, unsigned sides, unsigned halves);
 void synchronize(hexed::Kernel_mesh);
+//! host threads of the adapter's own copy loops (0 = every hardware thread, the default; the OpenMP environment is deliberately not consulted)
+void set_host_threads(int n);
 
 /*! \brief device-resident boundary conditions: removes the per-stage PCIe round trip of the boundary faces.
  * \details `kind` / `params` as in `hexed_b200_bc_create` (include/hexed_b200.h: Freestream, Copy, Nonpenetration, Outflow,
