@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--adapter-n", type=int, default=0, help="box edge per GPU of the end-to-end run through the C++ adapter (0 = 64, or 48 when host memory is short: "
                     "the reference keeps 85 KB of host objects per deformed element)")
     ap.add_argument("--no-aux-lines", action="store_true", help="skip the Navier-Stokes / Cartesian sub-lines of the default run")
+    ap.add_argument("--cbc-first", action="store_true", help="time the call-by-call loop before the device-resident loop (measurement-order experiment)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -567,11 +568,14 @@ def main():
                 dev.update_euler(0.7, k)
         run_steps(max(args.warmup, 1))
         l0 = dev.launch_count(); run_steps(1); launches_per_step = dev.launch_count() - l0
+        if args.cbc_first:  # (order experiment: is the device loop slower, or whichever of the two is timed first?)
+            sec_call_by_call = timed(step, args.steps)
         sampler = ClockSampler(local_rank)
         sec = timed(lambda: run_steps(args.steps), 1)
         clocks = sampler.stop()
         launches = launches_per_step*args.steps  # (graph replays do not pass through the host-side counter)
-        sec_call_by_call = timed(step, args.steps)
+        if not args.cbc_first:
+            sec_call_by_call = timed(step, args.steps)
     else:
         launches0 = dev.launch_count()
         sampler = ClockSampler(local_rank) if rank == 0 else None
