@@ -719,13 +719,15 @@ def main():
     # ---- the other workloads of the BASELINE config list on the same box, as sub-lines of the default run (own processes, 1 M elements each) ----
     if rank == 0 and world == 1 and not args.no_aux_lines and args.n == 100 and nd == 3 and not viscous and deformed:
         sub = {}
-        for name, extra in (("3d_cartesian_euler", ["--mesh", "cartesian"]), ("3d_deformed_navier_stokes", ["--pde", "navier_stokes"]),
-                            ("3d_cartesian_navier_stokes", ["--pde", "navier_stokes", "--mesh", "cartesian"])):
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3)), "--no-e2e",
-                                    "--no-cpu-baseline", "--no-aux-lines"] + extra, capture_output=True, text=True, timeout=600)
+        for name, extra in (("3d_cartesian_euler", ["--mesh", "cartesian", "--no-e2e"]), ("3d_deformed_navier_stokes", ["--pde", "navier_stokes"]),
+                            ("3d_cartesian_navier_stokes", ["--pde", "navier_stokes", "--mesh", "cartesian", "--no-e2e"])):
+            try:  # (the deformed Navier-Stokes sub-line also carries its end-to-end number through the adapter: viscous stage with the flux_bc callback)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3)),
+                                    "--no-cpu-baseline", "--no-aux-lines"] + extra, capture_output=True, text=True, timeout=900)
                 line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
                 sub[name] = {"value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "workload": line["config"]["workload"],
+                             "e2e": ({k: line["e2e"].get(k) for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "elements", "box")}
+                                     if line.get("e2e") else None),
                              "timed_path": line["config"].get("timed_path"), "gpu_launches": line.get("gpu_launches"), "clocks": line.get("clocks"),
                              "roofline": {k: line["roofline"].get(k) for k in ("kernel", "achieved", "peak", "frac", "frac_traffic", "avg_launch_ms", "whole_stage",
                                                                                   "kernel_seconds_per_step", "accounting")}}

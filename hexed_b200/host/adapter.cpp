@@ -693,14 +693,16 @@ struct Flux_bc_thunk
   {
     auto* self = static_cast<Flux_bc_thunk*>(user);
     if (!*self->fun) return;
-    // the host callback reads and writes boundary faces (Solver::apply_flux_bcs, src/Solver.cpp:69-81)
-    // (resident mode: a callback that applies its conditions on the device through hexed_b200::apply_flux_bcs owns the boundary faces
-    // itself -- uploading the host copy afterwards would overwrite what the device just computed)
-    if (g_mode == sync_every_call) {for (Rank& k : self->m->ranks) move_faces(*self->m, k, faces, false);} else move_boundary(*self->m, false);
+    // the host callback reads and writes boundary faces (Solver::apply_flux_bcs, src/Solver.cpp:69-81): sync_every_call mode brackets it with
+    // the face traffic. In resident mode the callback owns that traffic, exactly like the patched apply_state_bcs:
+    // a host loop calls boundary_faces_to_host(mesh, inside, ldg_half) / ghost_faces_to_device(mesh, ghost, ldg_half) around itself, a
+    // callback that applies its conditions on the device (hexed_b200::apply_flux_bcs) moves nothing -- an unconditional download here cost
+    // that path 141 MB of PCIe traffic and a host pass over every boundary object per step (26.1 ms against 14.4 ms of device time at 262 k
+    // elements, visit r02y)
+    if (g_mode == sync_every_call) {for (Rank& k : self->m->ranks) move_faces(*self->m, k, faces, false);}
     self->m->device_bcs_ran = false;
     (*self->fun)();
     if (g_mode == sync_every_call) {for (Rank& k : self->m->ranks) move_faces(*self->m, k, faces, true);}
-    else if (!self->m->device_bcs_ran) move_boundary(*self->m, true);
   }
 };
 

@@ -150,8 +150,8 @@ def run_pde(oracle, lib, m, basis, pde, resident, devices=None):
         oracle.compute_navier_stokes(basis, ref, lambda: oracle.apply_flux_bcs(ref), visc_o, cond_o, dt=dt_o, i_stage=0)
         host_bcs(oracle, h, work, resident)
 
-        def flux_bc():  # the adapter has already brought the faces the callback touches back to the host objects
-            h.fetch(work); oracle.apply_flux_bcs(work); h.put(work)
+        def flux_bc():  # resident mode: the callback owns its face traffic, like Solver::apply_flux_bcs with the two added lines
+            host_bcs(oracle, h, work, resident, flux=True)
         h.set_flux_bc(flux_bc)
         h.call("compute_navier_stokes", *visc_h, *cond_h, dt=dt_o, i_stage=0)
         oracle.apply_state_bcs(ref)
