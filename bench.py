@@ -231,7 +231,7 @@ def adapter_e2e(args, n_dev, viscous, steps, warmup, modes=("host_bcs",), n_over
                 h.ghost_ldg_faces_to_device()
 
         def admissible():
-            if dev_bcs and not clocked("hexed_calls", h.is_admissible)[0]:
+            if dev_bcs and not clocked("hexed_calls", h.is_admissible_flag):
                 raise RuntimeError("inadmissible state in the benchmark flow")
 
         def step():

@@ -396,6 +396,10 @@ int hbh_is_admissible(void* handle, int* ok, int* record)
 {
   auto* h = static_cast<Harness*>(handle);
   try {
+    if (!record) { // the answer alone, as Solver::update needs it after a stage: Element::record is only read when the answer is "no"
+      *ok = hexed_b200::is_admissible(h->mesh(), nullptr) ? 1 : 0;
+      return 0;
+    }
     std::vector<int> rec;
     *ok = hexed_b200::is_admissible(h->mesh(), &rec) ? 1 : 0;
     for (size_t i = 0; i < rec.size(); ++i) record[i] = rec[i];

@@ -207,6 +207,12 @@ class HostHarness:
         self._check(self.lib.hbh_is_admissible(self.h, _i(ok), _i(rec)))
         return bool(ok[0]), rec[:self.m.n_elem]
 
+    def is_admissible_flag(self):
+        """hexed_b200::is_admissible(mesh) without the per-element records (what Solver::update needs after a stage that went well)"""
+        ok = np.zeros(1, np.int32)
+        self._check(self.lib.hbh_is_admissible(self.h, _i(ok), None))
+        return bool(ok[0])
+
     def av_glue(self, what, a=0., b=0., n=0, values=None):
         v = np.ascontiguousarray(values if values is not None else np.zeros(1), dtype=np.float64)
         out = np.zeros(1)
