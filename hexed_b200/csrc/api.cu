@@ -1147,6 +1147,14 @@ int hexed_b200_is_admissible(hexed_b200_ctx* c, int* admissible)
   return launch_is_admissible(c, admissible);
 }
 
+int hexed_b200_is_admissible_begin(hexed_b200_ctx* c) { HB_ENTER(c); return launch_is_admissible_begin(c); }
+int hexed_b200_is_admissible_finish(hexed_b200_ctx* c, int* admissible)
+{
+  HB_ENTER_KEEP(c);
+  if (!admissible) return fail(c, HEXED_B200_BAD_ARGUMENT, "null result pointer");
+  return launch_is_admissible_finish(c, admissible);
+}
+
 int hexed_b200_download_record(hexed_b200_ctx* c, int* dst, int first_elem, int n_elem)
 {
   HB_ENTER(c);

@@ -270,6 +270,8 @@ extern const GenericOps generic_ops_pde1, generic_ops_pde2, generic_ops_pde3, ge
 int launch_stab_art_visc(hexed_b200_ctx* c, double char_speed);
 int launch_flux_bcs(hexed_b200_ctx* c);
 int launch_is_admissible(hexed_b200_ctx* c, int* admissible);
+int launch_is_admissible_begin(hexed_b200_ctx* c);
+int launch_is_admissible_finish(hexed_b200_ctx* c, int* admissible);
 int launch_set_jacobian(hexed_b200_ctx* c, const double* d_vert, const double* d_node_adj);
 int launch_shared_normals(hexed_b200_ctx* c);
 int launch_av_scale_velocity(hexed_b200_ctx* c, int restore);

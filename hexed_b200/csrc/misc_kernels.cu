@@ -460,7 +460,9 @@ record_reduce_kernel(int* record, int n_elem, int* flags)
   }
 }
 
-int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
+/* enqueue the check and the asynchronous read-back of its two flags; launch_is_admissible_finish waits for them. Split so that one host thread
+ * driving several devices (hexed_b200_group_*) starts the check everywhere before it waits anywhere. */
+int launch_is_admissible_begin(hexed_b200_ctx* c)
 {
   if (!c->have_mesh) return fail(c, HEXED_B200_NO_MESH, "no mesh uploaded");
   if (!c->record) { HB_CUDA(c, cudaMalloc(&c->record, sizeof(int)*(c->n_elem ? c->n_elem : 1))); }
@@ -487,10 +489,22 @@ int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
     HB_CUDA(c, cudaGetLastError());
   }
   HB_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 2*sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+int launch_is_admissible_finish(hexed_b200_ctx* c, int* admissible)
+{
+  if (!c->h_flags) return fail(c, HEXED_B200_BAD_ARGUMENT, "hexed_b200_is_admissible_finish without _begin");
   HB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_flags[1]) return fail(c, HEXED_B200_NOT_FINITE, "state is not finite");
   *admissible = c->h_flags[0] ? 0 : 1;
   return 0;
+}
+
+int launch_is_admissible(hexed_b200_ctx* c, int* admissible)
+{
+  int rc = launch_is_admissible_begin(c);
+  return rc ? rc : launch_is_admissible_finish(c, admissible);
 }
 
 /* ---------------- ghost-state boundary conditions (reference src/Boundary_condition.cpp) ---------------- */

@@ -887,10 +887,13 @@ bool is_admissible(Kernel_mesh km, std::vector<int>* record)
   // sync_every_call mode, falls back to the full scan)
   bool all_ok = true;
   if (record) record->assign(call.m.tab.elem.size(), 0);
-  for (Rank& k : call.m.ranks) { // every rank checks its elements, faces and the mortar faces it holds; the answer is the AND
+  for (Rank& k : call.m.ranks) { // every rank checks its elements, faces and the mortar faces it holds: started everywhere before any wait
     check(&call.m, hexed_b200_set_option(k.ctx, HEXED_B200_OPT_FUSED_ADMIS, 1), k.ctx);
+    check(&call.m, hexed_b200_is_admissible_begin(k.ctx), k.ctx);
+  }
+  for (Rank& k : call.m.ranks) { // the answer is the AND
     int ok = 0;
-    check(&call.m, hexed_b200_is_admissible(k.ctx, &ok), k.ctx);
+    check(&call.m, hexed_b200_is_admissible_finish(k.ctx, &ok), k.ctx);
     all_ok = all_ok && ok != 0;
     if (record && !ok && !k.elem.empty()) { // (all of an admissible rank's records are 0, which `record` already holds: nothing to fetch)
       std::vector<int> local(k.elem.size());

@@ -124,6 +124,8 @@ SIGNATURES = {
     "hexed_b200_update_euler": [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp],
     "hexed_b200_update_navier_stokes": [C.c_void_p, C.c_double, Transport, Transport, C.c_int, C.c_int, C.c_int, dp, dp],
     "hexed_b200_is_admissible": [C.c_void_p, ip],
+    "hexed_b200_is_admissible_begin": [C.c_void_p],
+    "hexed_b200_is_admissible_finish": [C.c_void_p, C.POINTER(C.c_int)],
     "hexed_b200_vertex_topology": [C.c_void_p, ip, C.c_int, ip, C.c_int],
     "hexed_b200_share_vertex_data": [C.c_void_p, C.c_int, C.c_int],
     "hexed_b200_fix_admis_spread": [C.c_void_p, dp],

@@ -248,6 +248,10 @@ int hexed_b200_update_navier_stokes(hexed_b200_ctx* ctx, double safety, hexed_b2
  * (Element::record, 1 = inadmissible) stays on the device for hexed_b200_download_record. One 8-byte read-back per call.
  * Returns HEXED_B200_NOT_FINITE where the reference throws "state is not finite". ---- */
 int hexed_b200_is_admissible(hexed_b200_ctx* ctx, int* admissible);
+/* the same in two parts -- enqueue the check and the read-back of its flags / wait for them -- so that one host thread driving several
+ * devices starts the check on all of them before it waits for any (nothing else may be enqueued on the context in between) */
+int hexed_b200_is_admissible_begin(hexed_b200_ctx* ctx);
+int hexed_b200_is_admissible_finish(hexed_b200_ctx* ctx, int* admissible);
 int hexed_b200_download_record(hexed_b200_ctx* ctx, int* dst, int first_elem, int n_elem);
 /* Solver::share_vertex_data (src/Solver.cpp:35-54): every mesh vertex takes the min (op 0) or max (op 1) over the elements that share
  * it, then the Hanging_vertex_matchers interpolate onto hanging vertices (src/Hanging_vertex_matcher.cpp:13-41). The vertex connectivity
