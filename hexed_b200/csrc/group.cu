@@ -18,8 +18,13 @@
  */
 #include "common.cuh"
 
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef HB_EMULATE
@@ -69,10 +74,81 @@ struct Link
   double* d_send = nullptr; double* d_recv = nullptr; // [n][widest face kind]
 };
 
+/* One enqueueing thread per rank. A stage is ~8 kernel launches per rank; issued by ONE host thread rank after rank, the last of eight devices
+ * starts a stage ~0.3 ms after the first, every stage, because nothing can be enqueued ahead of the admissibility answer Solver::update waits
+ * for. run(f) executes f(r) for every rank -- rank 0 on the caller, the others on their workers -- and returns the
+ * first non-zero code. NCCL group calls stay on the calling thread. The host-thread emulation build keeps the serial loop (its launches share
+ * global state). HEXED_B200_GROUP_THREADS=0 in the environment keeps the serial loop as well. */
+struct Workers
+{
+  int n = 0;
+  bool threaded = false;
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  const std::function<int(int)>* job = nullptr;
+  unsigned long long epoch = 0;
+  int pending = 0;
+  bool stop = false;
+  std::vector<int> rc;
+
+  void start(int n_)
+  {
+    n = n_; rc.assign(n, 0);
+#ifndef HB_EMULATE
+    const char* env = std::getenv("HEXED_B200_GROUP_THREADS");
+    threaded = n > 1 && !(env && env[0] == '0');
+#endif
+    if (!threaded) return;
+    for (int r = 1; r < n; ++r) th.emplace_back([this, r]() {
+      unsigned long long seen = 0;
+      for (;;) {
+        const std::function<int(int)>* f;
+        {
+          std::unique_lock<std::mutex> lk(m);
+          cv_go.wait(lk, [&]() {return stop || epoch != seen;});
+          if (stop) return;
+          seen = epoch; f = job;
+        }
+        const int code = (*f)(r);
+        {
+          std::lock_guard<std::mutex> lk(m);
+          rc[r] = code;
+          if (--pending == 0) cv_done.notify_one();
+        }
+      }
+    });
+  }
+  int run(const std::function<int(int)>& f)
+  {
+    if (!threaded) { for (int r = 0; r < n; ++r) { const int code = f(r); if (code) return code; } return 0; }
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = &f; pending = n - 1; ++epoch;
+    }
+    cv_go.notify_all();
+    rc[0] = f(0);
+    {
+      std::unique_lock<std::mutex> lk(m);
+      cv_done.wait(lk, [&]() {return pending == 0;});
+    }
+    for (int r = 0; r < n; ++r) if (rc[r]) return rc[r];
+    return 0;
+  }
+  ~Workers()
+  {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv_go.notify_all();
+    for (std::thread& t : th) t.join();
+  }
+};
+
 } // namespace
 
 struct hexed_b200_group
 {
+  Workers workers;
+  std::mutex err_mutex;
   int n = 0;
   std::vector<hexed_b200_ctx*> ctx;
   std::vector<std::vector<Link>> links;
@@ -92,7 +168,11 @@ namespace
 
 std::string g_group_create_error;
 
-int gfail(hexed_b200_group* g, int code, const std::string& msg) { if (g) g->err = msg; else g_group_create_error = msg; return code; }
+int gfail(hexed_b200_group* g, int code, const std::string& msg)
+{
+  if (g) { std::lock_guard<std::mutex> lk(g->err_mutex); g->err = msg; } else g_group_create_error = msg;
+  return code;
+}
 
 #define HG_CUDA(g, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return gfail(g, HEXED_B200_CUDA_ERROR, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 #define HG_CTX(g, r, call) do { int rc_ = (call); if (rc_) return gfail(g, rc_, "rank " + std::to_string(r) + ": " + hexed_b200_last_error((g)->ctx[r])); } while (0)
@@ -111,13 +191,15 @@ const Link* find_link(const hexed_b200_group* g, int rank, int peer)
 /* gather on every context stream, then one NCCL group on the comm streams (ordered after the gathers by events) */
 int exchange_start(hexed_b200_group* g, int kind)
 {
-  for (int r = 0; r < g->n; ++r) {
+  int rc = g->workers.run([&](int r) -> int {
     hexed_b200_ctx* c = g->ctx[r];
     for (const Link& l : g->links[r]) if (l.n_send) HG_CTX(g, r, hexed_b200_face_list_gather(c, l.send_list, kind, l.d_send));
     HG_CUDA(g, cudaSetDevice(c->device));
     HG_CUDA(g, cudaEventRecord(g->ev_ready[r], c->stream));
     HG_CUDA(g, cudaStreamWaitEvent(g->comm_stream[r], g->ev_ready[r], 0));
-  }
+    return 0;
+  });
+  if (rc) return rc;
 #ifndef HB_EMULATE
   HG_NCCL(g, g_nccl.GroupStart());
   for (int r = 0; r < g->n; ++r) {
@@ -151,13 +233,13 @@ int exchange_start(hexed_b200_group* g, int kind)
 /* the context streams wait for the transfer (the host does not) and unpack into the halo slots */
 int exchange_finish(hexed_b200_group* g, int kind)
 {
-  for (int r = 0; r < g->n; ++r) {
+  return g->workers.run([&](int r) -> int {
     hexed_b200_ctx* c = g->ctx[r];
     HG_CUDA(g, cudaSetDevice(c->device));
     HG_CUDA(g, cudaStreamWaitEvent(c->stream, g->ev_done[r], 0));
     for (const Link& l : g->links[r]) if (l.n_recv) HG_CTX(g, r, hexed_b200_face_list_scatter(c, l.recv_list, kind, l.d_recv));
-  }
-  return 0;
+    return 0;
+  });
 }
 
 void free_links(hexed_b200_group* g, int r)
@@ -187,6 +269,7 @@ int hexed_b200_group_create(hexed_b200_group** out, int n, hexed_b200_ctx* const
   hexed_b200_group* g = new hexed_b200_group();
   g->n = n;
   g->ctx.assign(ctxs, ctxs + n);
+  g->workers.start(n);
   g->links.resize(n); g->comm_stream.assign(n, nullptr); g->ev_ready.assign(n, nullptr); g->ev_done.assign(n, nullptr); g->d_dt.assign(n, nullptr);
   auto bail = [&](int code, const std::string& msg) { g_group_create_error = msg; hexed_b200_group_destroy(g); return code; };
   for (int r = 0; r < n; ++r) {
@@ -290,10 +373,16 @@ int hexed_b200_group_synchronize(hexed_b200_group* g)
 int hexed_b200_group_compute_euler(hexed_b200_group* g, hexed_b200_options o)
 {
   int rc = exchange_start(g, 0); if (rc) return rc;
-  for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_euler_begin(g->ctx[r]));
-  if ((rc = exchange_finish(g, 0))) return rc;
-  for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_euler_finish(g->ctx[r], o));
-  return 0;
+  // (one dispatch for the rest of the stage: interior flux, wait for the transfer, unpack, everything else)
+  return g->workers.run([&](int r) -> int {
+    hexed_b200_ctx* c = g->ctx[r];
+    HG_CTX(g, r, hexed_b200_compute_euler_begin(c));
+    HG_CUDA(g, cudaSetDevice(c->device));
+    HG_CUDA(g, cudaStreamWaitEvent(c->stream, g->ev_done[r], 0));
+    for (const Link& l : g->links[r]) if (l.n_recv) HG_CTX(g, r, hexed_b200_face_list_scatter(c, l.recv_list, 0, l.d_recv));
+    HG_CTX(g, r, hexed_b200_compute_euler_finish(c, o));
+    return 0;
+  });
 }
 
 /* void compute_navier_stokes(Kernel_mesh, Kernel_options, flux_bc, visc, therm_cond)     include/kernels.hpp:24-25, src/kernels_diffusive.cpp:28-29
@@ -302,16 +391,16 @@ int hexed_b200_group_compute_navier_stokes(hexed_b200_group* g, hexed_b200_optio
                                            hexed_b200_transport visc, hexed_b200_transport therm_cond)
 {
   int rc = exchange_start(g, 0); if (rc) return rc;
-  for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_navier_stokes_begin(g->ctx[r], o, visc, therm_cond));
+  if ((rc = g->workers.run([&](int r) -> int { HG_CTX(g, r, hexed_b200_compute_navier_stokes_begin(g->ctx[r], o, visc, therm_cond)); return 0; }))) return rc;
   if ((rc = exchange_finish(g, 0))) return rc;
-  for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_navier_stokes_middle_local(g->ctx[r], o, visc, therm_cond));
+  if ((rc = g->workers.run([&](int r) -> int { HG_CTX(g, r, hexed_b200_compute_navier_stokes_middle_local(g->ctx[r], o, visc, therm_cond)); return 0; }))) return rc;
   if (!o.i_stage) {
     if (flux_bc) flux_bc(user);
     if ((rc = exchange_start(g, 1))) return rc;
-    for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_navier_stokes_middle_reconcile(g->ctx[r], o, visc, therm_cond));
+    if ((rc = g->workers.run([&](int r) -> int { HG_CTX(g, r, hexed_b200_compute_navier_stokes_middle_reconcile(g->ctx[r], o, visc, therm_cond)); return 0; }))) return rc;
     if ((rc = exchange_finish(g, 1))) return rc;
   }
-  for (int r = 0; r < g->n; ++r) HG_CTX(g, r, hexed_b200_compute_navier_stokes_finish(g->ctx[r], o, visc, therm_cond));
+  if ((rc = g->workers.run([&](int r) -> int { HG_CTX(g, r, hexed_b200_compute_navier_stokes_finish(g->ctx[r], o, visc, therm_cond)); return 0; }))) return rc;
   return 0;
 }
 
@@ -320,8 +409,11 @@ int hexed_b200_group_compute_navier_stokes(hexed_b200_group* g, hexed_b200_optio
 int hexed_b200_group_max_dt(hexed_b200_group* g, int pde, double convective_safety, double diffusive_safety, int local_time,
                             hexed_b200_transport visc, hexed_b200_transport therm_cond, double advect_length, double* dt)
 {
-  for (int r = 0; r < g->n; ++r)
+  int rc = g->workers.run([&](int r) -> int {
     HG_CTX(g, r, hexed_b200_max_dt_device(g->ctx[r], pde, convective_safety, diffusive_safety, local_time, visc, therm_cond, advect_length, g->d_dt[r]));
+    return 0;
+  });
+  if (rc) return rc;
   if (local_time) { *dt = 1.; return 0; }
 #ifndef HB_EMULATE
   if (g->n > 1) {
