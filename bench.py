@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="box edge in elements per GPU (100 -> 1M elements)")
+    ap.add_argument("--n", "--box-n", dest="n", type=int, default=100, help="box edge in elements per GPU (100 -> 1M elements); --box-n is the spelling torchrun does not trip over")
     ap.add_argument("--mesh", default="deformed", choices=["deformed", "cartesian"])
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3 = the headline; 2 = the shape of the 2-D BASELINE configs (vortex / naca0012 / cylinder)")
     ap.add_argument("--pde", default="euler", choices=["euler", "navier_stokes"],
