@@ -115,7 +115,8 @@ void av_swap(hexed::Kernel_mesh);
 /*! \brief `Solver::update_art_visc_elwise` (src/Solver.cpp:584-633) after its `set_uncertainty` call. `av_elwise_ramp` sends `Element::uncertainty`
  * up, applies the ramp of :590-601 (`scale` = width/(row_size - 1)*(freestream_speed + freestream_sound_speed)) and writes it back to the host
  * objects as the reference leaves it; `av_elwise_forcing(false)` / `(true)` are the point loops before / after `diffuse_art_visc` in the
- * PDE-based branch (:603-619); `av_elwise_vertices` is the vertex-based branch (:620-632; needs the vertex topology, single device). */
+ * PDE-based branch (:603-619); `av_elwise_vertices` is the vertex-based branch (:620-632; needs the vertex topology, single device) and, after
+ * `hexed::stabilizing_art_visc`, all that is left of `Solver::set_art_visc_admis` (:636-658). */
 /*! \brief the vertex connectivity `Solver::share_vertex_data` walks (src/Solver.cpp:35-54), which a Kernel_mesh does not carry: `elem_vertex`
  * [n_elem][2^n_dim] = an id in [0, n_vertex) for `Element::vertex(i)` of every element in `Kernel_mesh::elems` order, `matchers` [n][8] = one row
  * {i_dim, is_positive, stretch0, stretch1, fine element 0..3 (-1 unused)} per `Hanging_vertex_matcher`. Belongs to the current mesh epoch; single device. */

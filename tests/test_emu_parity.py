@@ -176,6 +176,12 @@ def test_av_smoothness_pipeline(oracle, emu_lib, nd, rs):
     check_av_pipeline(oracle, emu_lib, nd, rs)
 
 
+@pytest.mark.parametrize("nd,rs", [(2, 4), (3, 3)])
+def test_set_art_visc_admis(oracle, emu_lib, nd, rs):
+    from util import check_set_art_visc_admis
+    check_set_art_visc_admis(oracle, emu_lib, nd, rs)
+
+
 @pytest.mark.parametrize("nd,rs", [(1, 3), (2, 3), (3, 2)])
 def test_av_elwise(emu_lib, nd, rs):
     """Solver::update_art_visc_elwise: ramp, forcing loops, vertex branch"""

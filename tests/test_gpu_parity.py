@@ -341,6 +341,12 @@ def test_vertex_sharing_and_fix_admis_spread(oracle, gpu_lib, nd, rs):
     check_vertex_sharing(oracle, gpu_lib, nd, rs)
 
 
+@pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6)])
+def test_set_art_visc_admis(oracle, gpu_lib, nd, rs):
+    from util import check_set_art_visc_admis
+    check_set_art_visc_admis(oracle, gpu_lib, nd, rs)
+
+
 @pytest.mark.parametrize("nd,rs", [(2, 6), (3, 6), (3, 3)])
 def test_av_elwise(gpu_lib, nd, rs):
     from util import check_av_elwise

@@ -719,6 +719,40 @@ def check_av_elwise(lib, nd, rs, seed=29):
     assert np.array_equal(out.elem_data[:, nd + 3], ref.elem_data[:, nd + 3])   # bulk coefficient untouched
 
 
+def check_set_art_visc_admis(oracle, lib, nd, rs, seed=37):
+    """Solver::set_art_visc_admis (reference src/Solver.cpp:636-658) with nothing on the host: stabilizing_art_visc leaves the desired viscosity
+    in Element::uncertainty, share_vertex_data(vector_max) makes it C0 at the vertices (hanging-vertex matchers included), hypercube_matvec
+    interpolates it to laplacian_av_coef = hexed_b200_stabilizing_art_visc + hexed_b200_vertex_topology + hexed_b200_av_elwise_vertices"""
+    import pyoracle
+    from hexed_b200.kernels import VERTEX_SCRATCH
+    rng = np.random.default_rng(seed)
+    basis = hb.gauss_legendre(rs)
+    m = M.soup_mesh(nd, rs, rng, n_car=10, n_def=12, n_ref=0, with_ldg=False)
+    M.random_flow_state(m, rng)
+    m.state()[:, nd] *= 1 + 0.3*rng.random(m.state()[:, nd].shape)
+    m.elem_data[:, nd + 3:nd + 5] = rng.uniform(0., 1e-3, (m.n_elem, 2, m.nq))
+    ne, n_vert = m.n_elem, 2**nd
+    n_vertex = ne*n_vert//3 + 5
+    elem_vertex = np.stack([rng.choice(n_vertex, n_vert, replace=False) for _ in range(ne)]).astype(np.int32)
+    matchers = np.array([[nd - 1, 1, 0, 0] + [2, 7, 11, 13][:2**(nd - 1)] + [-1]*(4 - 2**(nd - 1))], np.int32) if nd > 1 else np.zeros((0, 8), np.int32)
+    interp = np.stack([1. - np.asarray(basis.node), np.asarray(basis.node)], axis=1)
+    ref = m.copy()
+    dev = Device(nd, rs, basis, lib_path=lib).load_mesh(m)
+    oracle.stabilizing_art_visc(basis, ref, 340.)
+    v = pyoracle.av_elwise_vertices(ref, elem_vertex, n_vertex, matchers, interp)
+    dev.stabilizing_art_visc(340.)
+    dev.vertex_topology(elem_vertex, n_vertex, matchers)
+    dev.av_elwise_vertices(interp)
+    got_v = dev.download(VERTEX_SCRATCH, np.zeros((ne, n_vert)))
+    out = m.copy()
+    dev.sync_to_host(out)
+    dev.close()
+    assert np.abs(out.uncert - ref.uncert).max() <= 1e-11*np.abs(ref.uncert).max()
+    assert np.abs(got_v - v).max() <= 1e-11*np.abs(v).max()
+    assert rel_l2(out.elem_data[:, nd + 4], ref.elem_data[:, nd + 4]) <= 1e-11
+    assert np.array_equal(out.elem_data[:, nd + 3], ref.elem_data[:, nd + 3])
+
+
 def check_shared_normals_soup(oracle, lib, nd, rs, seed=31):
     """the connection passes of Solver::calc_jacobian on a soup mesh (every direction, hanging faces, boundary ghosts) with arbitrary
     element-face normals: bit-identical to the numpy restatement (all factors are 0.5 and +-1)"""
