@@ -210,7 +210,7 @@ def test_calc_jacobian_box(emu_lib, nd, rs, n):
 
 
 @pytest.mark.parametrize("kind", ["soup", "box_def"])
-def test_navier_stokes_3d_padded_layout_is_bit_identical(oracle, emu_lib, kind):
+def test_navier_stokes_3d_padded_layout_is_bit_identical(port_oracle, emu_lib, kind):
     """ns_local_pad_kernel (row size 6 default: plane-padded shared memory, lines dealt to lanes through tables, 16-byte accesses on the
     contiguous lines) performs the operations of ns_local_line_kernel in the same order: HEXED_B200_OPT_NS_LOCAL_LAYOUT = 0 / 1 must agree
     bit for bit, state, LDG faces and residual cache"""
@@ -222,12 +222,12 @@ def test_navier_stokes_3d_padded_layout_is_bit_identical(oracle, emu_lib, kind):
     else:
         m = M.box_mesh(3, 6, 2, basis, deformed=True, bc_kind=M.BC_NONPENETRATION, with_ldg=True)
         density_wave(m, basis)
-        oracle.compute_write_face(basis, m)
+        port_oracle.compute_write_face(basis, m)
     prepare_pde_state(m, rng, NAVIER_STOKES)
-    a, ref, dts = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2, options=((3, 0),))
+    a, ref, dts = run_pde_pair(port_oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2, options=((3, 0),))
     assert_pde_parity(a, ref, dts)
     for layout in (1, 2):
-        b, _, _ = run_pde_pair(oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2, options=((3, layout),))
+        b, _, _ = run_pde_pair(port_oracle, emu_lib, m, basis, NAVIER_STOKES, n_steps=2, options=((3, layout),))
         assert np.array_equal(a.elem_data, b.elem_data) and np.array_equal(a.face_ldg, b.face_ldg) and np.array_equal(a.face_state, b.face_state), layout
 
 

@@ -225,7 +225,7 @@ def test_box_3d_every_persistent_cta_loops(oracle, gpu_lib, deformed):
     assert_euler_parity(out, ref, dts)
 
 
-def test_navier_stokes_3d_padded_layout_is_bit_identical(oracle, gpu_lib):
+def test_navier_stokes_3d_padded_layout_is_bit_identical(port_oracle, gpu_lib):
     """HEXED_B200_OPT_NS_LOCAL_LAYOUT 1 (ns_local_pad_kernel, default) against 0 (ns_local_line_kernel): same operations in the same
     order, so bit-identical state, faces and residual cache on 500 + 500 elements with hanging faces"""
     rng = np.random.default_rng(93)
@@ -233,10 +233,10 @@ def test_navier_stokes_3d_padded_layout_is_bit_identical(oracle, gpu_lib):
     m = M.soup_mesh(3, 6, rng, n_car=500, n_def=500, n_ref=100, with_ldg=True)
     M.random_flow_state(m, rng)
     prepare_pde_state(m, rng, NAVIER_STOKES)
-    a, ref, dts = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1, options=((3, 0),))
+    a, ref, dts = run_pde_pair(port_oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1, options=((3, 0),))
     assert_pde_parity(a, ref, dts)
     for layout in (1, 2):
-        b, _, _ = run_pde_pair(oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1, options=((3, layout),))
+        b, _, _ = run_pde_pair(port_oracle, gpu_lib, m, basis, NAVIER_STOKES, n_steps=2, safety=0.1, options=((3, layout),))
         assert np.array_equal(a.elem_data, b.elem_data) and np.array_equal(a.face_ldg, b.face_ldg) and np.array_equal(a.face_state, b.face_state), layout
 
 
