@@ -140,6 +140,7 @@ struct Mirror
   bool device_bcs_ran = false; // set by apply_state_bcs / apply_flux_bcs; lets the flux_bc thunk see what its callback did
   bool prefetch_inside = false; // resident mode, host-applied state BCs: stage drivers start the download of the inside faces themselves
   bool prefetch_valid = false;  // nothing has touched the device faces since the last prefetch was started
+  bool prefetch_collected = true; // the last prefetch was picked up by boundary_faces_to_host (if not, the host has stopped asking: stop prefetching)
   hexed_b200_ctx* ctx0() {return ranks.empty() ? nullptr : ranks[0].ctx;}
   void destroy_device_side()
   {
@@ -480,15 +481,20 @@ void move_boundary(Mirror& m, bool up, unsigned sides = both_sides, unsigned hal
       }
     }
   }
-  if (!up && g_mode == resident && (sides & inside) && (halves & state_half)) m.prefetch_inside = true;
+  if (!up && g_mode == resident && (sides & inside) && (halves & state_half)) { m.prefetch_inside = true; m.prefetch_collected = true; }
 }
 
 //! resident mode with host-applied state BCs: start the download of the inside boundary faces the stage has just produced
 void prefetch_boundary(Mirror& m)
 {
   if (!m.prefetch_inside || g_mode != resident) return;
+  if (!m.prefetch_collected) { // a whole stage went by without the host collecting the faces (e.g. the conditions moved to the device): no more copies
+    m.prefetch_inside = false;
+    return;
+  }
   for (Rank& k : m.ranks) if (!k.side_slots[0].empty()) check(&m, hexed_b200_face_list_prefetch(k.ctx, k.side_list[0], 0), k.ctx);
   m.prefetch_valid = true;
+  m.prefetch_collected = false;
 }
 
 Mesh_graph graph_of(const Flat_tables& t)
