@@ -764,11 +764,10 @@ ns_local_pad_kernel(GArgs a, Ops ops)
   const int e = a.elem_begin + blockIdx.x;
   if (e >= a.elem_end) return;
   constexpr unsigned b_plane = sizeof(double)*nfq, b_face = sizeof(double)*2*ND*nv*nfq;
-  if (t == 0) {
-    mbar_init(bar, 1); mbar_init_fence();
-    mbar_arrive_expect_tx(bar, nv*RS*b_plane + 2*b_face + (DEF ? ND*ND*RS*b_plane : 0u));
-  }
+  if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
   __syncthreads();
+  // (the one arrival that carries the byte count may come before or after the other lanes' copies: the phase cannot complete without it)
+  if (t == 0) mbar_arrive_expect_tx(bar, nv*RS*b_plane + 2*b_face + (DEF ? ND*ND*RS*b_plane : 0u));
   if constexpr (PX == nfq) { // dense: one copy per array
     if (t == 0) bulk_g2s(S, a.ed.state + (size_t)e*nv*nq, nv*RS*b_plane, bar);
     if (t == 1) bulk_g2s(smem + C::s_ldg, a.faces_ldg + (size_t)e*2*ND*wl, b_face, bar);
