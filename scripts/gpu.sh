@@ -10,7 +10,7 @@
 #   ref              bench.py --impl reference             bench          default bench line
 #   bench:<args>     bench.py --steps 10 --warmup 3 --no-cpu-baseline <args with , for space>   (e.g. bench:--pde,navier_stokes)
 #   launches[:<args>]  ncu launch list (gpu__time_duration) of bench steps at --n 64
-#   full:<regex>[:<args>]  ncu --set full capture of the kernels matching <regex>
+#   full:<regex>[:<args>]  ncu --set full capture of the kernels matching <regex> (report named after regex + args: several per visit are fine)
 #   multi_check / multi_bench[:<args>]   torchrun over $N GPUs: scripts/multigpu_check.py / bench.py --gpus $N
 #   py:<script>[:<args>]   python <script> <args>
 TAG=${TAG:-r02}
